@@ -1,0 +1,309 @@
+// Host side of the tcgen05 implicit-GEMM convolution: tap tables, TMA tensor maps, tile-shape choice, launch.
+#include "conv_gemm.cuh"
+
+#include <cudaTypedefs.h>
+
+#include "common.h"
+
+namespace gp {
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+static int gcd_int(int a, int b) {
+  while (b) {
+    int t = a % b;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+
+// Factor a block of `total` pixels (a power of two) over the (N, H, W) grid so that every tile is a box.
+static void factor_tile(int total, int H, int W, int* Nt, int* Ht, int* Wt) {
+  *Wt = gcd_int(W, total);
+  *Ht = gcd_int(H, total / *Wt);
+  *Nt = total / (*Wt * *Ht);
+}
+
+// 4-D bf16 NHWC view (C, W, H, N) with explicit element strides; box = (64 channels, bw, bh, bn), 128B swizzle.
+static int make_map_nhwc(CUtensorMap* m, const void* base, int C, int W, int H, int N, long long sW, long long sH,
+                         long long sN, int bw, int bh, int bn) {
+  auto fn = get_encode_fn();
+  if (fn == nullptr) return set_error(GP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sN * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 3; ++i)
+    if (strides[i] % 16 != 0) return set_error(GP_ERR_INVALID, "TMA stride %d not a multiple of 16 bytes", i);
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(GP_ERR_INVALID, "TMA base not 16B aligned");
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(GP_ERR_CUDA, "cuTensorMapEncodeTiled(4d) failed: %d (C=%d W=%d H=%d N=%d box=%d,%d,%d)", (int)r,
+                     C, W, H, N, bw, bh, bn);
+  return GP_OK;
+}
+
+static int make_map_2d(CUtensorMap* m, const void* base, long long inner, long long outer, int box_outer) {
+  auto fn = get_encode_fn();
+  if (fn == nullptr) return set_error(GP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)inner * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  if (strides[0] % 16 != 0) return set_error(GP_ERR_INVALID, "packed weight row (%lld) not a multiple of 8", inner);
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(GP_ERR_INVALID, "TMA base not 16B aligned");
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(GP_ERR_CUDA, "cuTensorMapEncodeTiled(2d) failed: %d", (int)r);
+  return GP_OK;
+}
+
+// Strided (k4 s2 p1) gather: input row ih = 2*oh - 1 + kh  ==  parity r = (kh+1)&1, half-row oh + floor((kh-1)/2).
+static void k4s2_tap(int kh, int* parity, int* d) {
+  *parity = (kh + 1) & 1;
+  *d = (kh == 0) ? -1 : ((kh == 3) ? 1 : 0);
+}
+
+static int pick_bn(int n) {
+  if (n >= 256 && n % 256 == 0) return 256;
+  if (n >= 128) return 128;
+  return 64;
+}
+
+template <int MODE>
+static int launch(const ConvGemmParams& prm, int bn, int num_tiles, cudaStream_t st) {
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  if (grid <= 0) return GP_OK;
+#define GP_LAUNCH_BN(BNV)                                                                                        \
+  {                                                                                                              \
+    auto kfn = conv_gemm_kernel<MODE, BNV>;                                                                      \
+    GP_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BNV>::kSmemBytes)); \
+    kfn<<<grid, kNumThreads, GemmCfg<BNV>::kSmemBytes, st>>>(prm);                                               \
+  }
+  if (bn == 256) GP_LAUNCH_BN(256)
+  else if (bn == 128) GP_LAUNCH_BN(128)
+  else GP_LAUNCH_BN(64)
+#undef GP_LAUNCH_BN
+  GP_CHECK_LAUNCH();
+  return GP_OK;
+}
+
+}  // namespace gp
+
+using namespace gp;
+
+extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
+  GP_REQUIRE(a != nullptr && a->in && a->w && a->out, "gp_conv_fwd: null pointer");
+  GP_REQUIRE(a->NB > 0 && a->Cin > 0 && a->Nout > 0, "gp_conv_fwd: empty problem");
+  GP_REQUIRE(a->Cin % 8 == 0, "gp_conv_fwd: Cin=%d must be a multiple of 8 (16-byte TMA rows)", a->Cin);
+  GP_REQUIRE(a->Nout % 8 == 0, "gp_conv_fwd: Nout=%d must be a multiple of 8", a->Nout);
+  ConvGemmParams prm;
+  memset(&prm, 0, sizeof(prm));
+  const int Cin = a->Cin;
+  int ntaps_total = 0;
+  int rc;
+  const long long inW = Cin, inH = (long long)a->Win * Cin, inN = (long long)a->Hin * a->Win * Cin;
+  switch (a->kind) {
+    case GP_KIND_CONV_K4S2: {
+      GP_REQUIRE(a->Hin == 2 * a->Hout && a->Win == 2 * a->Wout, "gp_conv_fwd: k4s2 needs Hin=2*Hout");
+      prm.Hs = a->Hout;
+      prm.Ws = a->Wout;
+      prm.n_phases = 1;
+      prm.taps_per_phase = 16;
+      factor_tile(kBlockM, prm.Hs, prm.Ws, &prm.Nt, &prm.Ht, &prm.Wt);
+      for (int r = 0; r < 2; ++r)
+        for (int s = 0; s < 2; ++s) {
+          const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(a->in) + ((long long)r * a->Win + s) * Cin;
+          rc = make_map_nhwc(&prm.map_g[r * 2 + s], base, Cin, a->Win / 2, a->Hin / 2, a->NB, 2 * inW, 2 * inH, inN,
+                             prm.Wt, prm.Ht, prm.Nt);
+          if (rc) return rc;
+        }
+      for (int kh = 0; kh < 4; ++kh)
+        for (int kw = 0; kw < 4; ++kw) {
+          int r, dh, s, dw;
+          k4s2_tap(kh, &r, &dh);
+          k4s2_tap(kw, &s, &dw);
+          Tap& t = prm.taps[ntaps_total++];
+          t.map = (int8_t)(r * 2 + s);
+          t.dh = (int8_t)dh;
+          t.dw = (int8_t)dw;
+          t.koff = (kh * 4 + kw) * Cin;
+        }
+      prm.out_sN = (long long)a->Hout * a->Wout * a->Nout;
+      prm.out_sH = (long long)a->Wout * a->Nout;
+      prm.out_sW = a->Nout;
+      break;
+    }
+    case GP_KIND_CONVT_K4S2: {
+      GP_REQUIRE(a->Hout == 2 * a->Hin && a->Wout == 2 * a->Win, "gp_conv_fwd: convT k4s2 needs Hout=2*Hin");
+      prm.Hs = a->Hin;
+      prm.Ws = a->Win;
+      prm.n_phases = 4;
+      prm.taps_per_phase = 4;
+      factor_tile(kBlockM, prm.Hs, prm.Ws, &prm.Nt, &prm.Ht, &prm.Wt);
+      rc = make_map_nhwc(&prm.map_g[0], a->in, Cin, a->Win, a->Hin, a->NB, inW, inH, inN, prm.Wt, prm.Ht, prm.Nt);
+      if (rc) return rc;
+      for (int i = 1; i < 4; ++i) prm.map_g[i] = prm.map_g[0];
+      // output row oh = 2*ih - 1 + kh. Phase ph = oh & 1: ph=0 -> (kh=1, ih=i), (kh=3, ih=i-1); ph=1 -> (kh=0, ih=i+1), (kh=2, ih=i)
+      static const int kk[2][2] = {{1, 3}, {0, 2}};
+      static const int dd[2][2] = {{0, -1}, {1, 0}};
+      for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+          for (int ta = 0; ta < 2; ++ta)
+            for (int tb = 0; tb < 2; ++tb) {
+              Tap& t = prm.taps[ntaps_total++];
+              t.map = 0;
+              t.dh = (int8_t)dd[ph][ta];
+              t.dw = (int8_t)dd[pw][tb];
+              t.koff = (kk[ph][ta] * 4 + kk[pw][tb]) * Cin;
+            }
+          prm.phase_off[ph * 2 + pw] = ((long long)ph * a->Wout + pw) * a->Nout;
+        }
+      prm.out_sN = (long long)a->Hout * a->Wout * a->Nout;
+      prm.out_sH = 2LL * a->Wout * a->Nout;
+      prm.out_sW = 2LL * a->Nout;
+      break;
+    }
+    case GP_KIND_CONV_K3S1:
+    case GP_KIND_CONV_K1S1: {
+      GP_REQUIRE(a->Hin == a->Hout && a->Win == a->Wout, "gp_conv_fwd: stride-1 conv needs Hin=Hout");
+      const int k = (a->kind == GP_KIND_CONV_K3S1) ? 3 : 1;
+      prm.Hs = a->Hin;
+      prm.Ws = a->Win;
+      prm.n_phases = 1;
+      prm.taps_per_phase = k * k;
+      factor_tile(kBlockM, prm.Hs, prm.Ws, &prm.Nt, &prm.Ht, &prm.Wt);
+      rc = make_map_nhwc(&prm.map_g[0], a->in, Cin, a->Win, a->Hin, a->NB, inW, inH, inN, prm.Wt, prm.Ht, prm.Nt);
+      if (rc) return rc;
+      for (int i = 1; i < 4; ++i) prm.map_g[i] = prm.map_g[0];
+      for (int kh = 0; kh < k; ++kh)
+        for (int kw = 0; kw < k; ++kw) {
+          Tap& t = prm.taps[ntaps_total++];
+          t.map = 0;
+          t.dh = (int8_t)(kh - k / 2);
+          t.dw = (int8_t)(kw - k / 2);
+          t.koff = (kh * k + kw) * Cin;
+        }
+      prm.out_sN = (long long)a->Hout * a->Wout * a->Nout;
+      prm.out_sH = (long long)a->Wout * a->Nout;
+      prm.out_sW = a->Nout;
+      break;
+    }
+    default:
+      return set_error(GP_ERR_UNSUPPORTED, "gp_conv_fwd: unknown kind %d", a->kind);
+  }
+  const int bn = pick_bn(a->Nout);
+  const long long ktot = (long long)ntaps_total * Cin;  // packed row = every tap of the kernel window
+  rc = make_map_2d(&prm.map_w, a->w, ktot, a->Nout, bn);
+  if (rc) return rc;
+  prm.map_d = prm.map_g[0];
+  prm.NB = a->NB;
+  prm.C = Cin;
+  prm.N = a->Nout;
+  prm.out = static_cast<__nv_bfloat16*>(a->out);
+  prm.bias = a->bias;
+  prm.act = a->act;
+  prm.col_sum = a->col_sum;
+  prm.col_sumsq = a->col_sumsq;
+  GP_REQUIRE((a->col_sum == nullptr) == (a->col_sumsq == nullptr), "gp_conv_fwd: col_sum and col_sumsq go together");
+  const int mtiles = ((a->NB + prm.Nt - 1) / prm.Nt) * (prm.Hs / prm.Ht) * (prm.Ws / prm.Wt);
+  const int ntn = (a->Nout + bn - 1) / bn;
+  return launch<MODE_FWD>(prm, bn, prm.n_phases * mtiles * ntn, as_stream(stream));
+}
+
+extern "C" int gp_conv_wgrad(const gp_conv_wgrad_t* a, void* stream) {
+  GP_REQUIRE(a != nullptr && a->dense && a->gath && a->dw, "gp_conv_wgrad: null pointer");
+  GP_REQUIRE(a->NB > 0 && a->Cd > 0 && a->Cg > 0, "gp_conv_wgrad: empty problem");
+  GP_REQUIRE(a->Cd % 8 == 0 && a->Cg % 8 == 0, "gp_conv_wgrad: channel counts must be multiples of 8");
+  ConvGemmParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.NB = a->NB;
+  prm.Hs = a->Hs;
+  prm.Ws = a->Ws;
+  factor_tile(kBlockK, prm.Hs, prm.Ws, &prm.Nt, &prm.Ht, &prm.Wt);
+  int rc = make_map_nhwc(&prm.map_d, a->dense, a->Cd, a->Ws, a->Hs, a->NB, a->Cd, (long long)a->Ws * a->Cd,
+                         (long long)a->Hs * a->Ws * a->Cd, prm.Wt, prm.Ht, prm.Nt);
+  if (rc) return rc;
+  const int Cg = a->Cg;
+  const long long gW = Cg, gH = (long long)a->Wg * Cg, gN = (long long)a->Hg * a->Wg * Cg;
+  int ntaps = 0;
+  switch (a->kind) {
+    case GP_KIND_CONV_K4S2: {
+      GP_REQUIRE(a->Hg == 2 * a->Hs && a->Wg == 2 * a->Ws, "gp_conv_wgrad: k4s2 needs Hg=2*Hs");
+      for (int r = 0; r < 2; ++r)
+        for (int s = 0; s < 2; ++s) {
+          const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(a->gath) + ((long long)r * a->Wg + s) * Cg;
+          rc = make_map_nhwc(&prm.map_g[r * 2 + s], base, Cg, a->Wg / 2, a->Hg / 2, a->NB, 2 * gW, 2 * gH, gN, prm.Wt,
+                             prm.Ht, prm.Nt);
+          if (rc) return rc;
+        }
+      for (int kh = 0; kh < 4; ++kh)
+        for (int kw = 0; kw < 4; ++kw) {
+          int r, dh, s, dw;
+          k4s2_tap(kh, &r, &dh);
+          k4s2_tap(kw, &s, &dw);
+          Tap& t = prm.taps[ntaps++];
+          t.map = (int8_t)(r * 2 + s);
+          t.dh = (int8_t)dh;
+          t.dw = (int8_t)dw;
+          t.koff = (kh * 4 + kw) * Cg;
+        }
+      break;
+    }
+    case GP_KIND_CONV_K3S1:
+    case GP_KIND_CONV_K1S1: {
+      GP_REQUIRE(a->Hg == a->Hs && a->Wg == a->Ws, "gp_conv_wgrad: stride-1 needs Hg=Hs");
+      const int k = (a->kind == GP_KIND_CONV_K3S1) ? 3 : 1;
+      rc = make_map_nhwc(&prm.map_g[0], a->gath, Cg, a->Wg, a->Hg, a->NB, gW, gH, gN, prm.Wt, prm.Ht, prm.Nt);
+      if (rc) return rc;
+      for (int i = 1; i < 4; ++i) prm.map_g[i] = prm.map_g[0];
+      for (int kh = 0; kh < k; ++kh)
+        for (int kw = 0; kw < k; ++kw) {
+          Tap& t = prm.taps[ntaps++];
+          t.map = 0;
+          t.dh = (int8_t)(kh - k / 2);
+          t.dw = (int8_t)(kw - k / 2);
+          t.koff = (kh * k + kw) * Cg;
+        }
+      break;
+    }
+    default:
+      return set_error(GP_ERR_UNSUPPORTED, "gp_conv_wgrad: unsupported kind %d", a->kind);
+  }
+  prm.map_w = prm.map_d;
+  prm.n_phases = 1;
+  prm.taps_per_phase = ntaps;
+  prm.M = a->Cd;
+  prm.N = Cg;
+  prm.dw = a->dw;
+  prm.ldw = ntaps * Cg;
+  const int bn = pick_bn(Cg);
+  const int mtiles = (a->Cd + kBlockM - 1) / kBlockM;
+  const int ntn = (Cg + bn - 1) / bn;
+  const int base_tiles = mtiles * ntaps * ntn;
+  prm.kblocks_total = ((a->NB + prm.Nt - 1) / prm.Nt) * (prm.Hs / prm.Ht) * (prm.Ws / prm.Wt);
+  // split-K over pixel blocks: aim for >= 2 waves of tiles, but keep >= 8 k-blocks per split.
+  int splits = (2 * num_sms() + base_tiles - 1) / base_tiles;
+  const int max_splits = prm.kblocks_total / 8 > 0 ? prm.kblocks_total / 8 : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  // drop empty trailing splits
+  const int per = (prm.kblocks_total + splits - 1) / splits;
+  splits = (prm.kblocks_total + per - 1) / per;
+  prm.splits = splits;
+  return launch<MODE_WGRAD>(prm, bn, splits * base_tiles, as_stream(stream));
+}

@@ -1,0 +1,283 @@
+"""ORACLE — test infrastructure only. NOT part of the product path.
+
+A CPU, fp32, *functional* restatement of the reference's one-training-step hot path (hermanprawiro/gan-playground):
+networks are pure functions of a reference-layout ``state_dict`` (name -> tensor), evaluated with plain
+``torch.nn.functional`` ops on the CPU. Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs may import this file; the product package
+(``gan_playground_b200``) never does and fails loudly when its CUDA extension is missing.
+
+The arithmetic of the reference lives in PyTorch (third-party; container-pinned torch 2.11.0); this file restates
+the reference's *composition* of those ops, each function citing the reference file:line it follows, and torch's
+own ``spectral_norm`` hook (``torch:nn/utils/spectral_norm.py``) as explicit formulas.
+
+Pinning: the reference ships no tests or golden vectors, so the oracle is pinned against the
+reference itself: ``oracle/make_golden.py`` imports the unmodified reference from /root/reference, runs it on seeded
+inputs and commits the outputs under ``tests/golden/``; ``tests/test_oracle_golden.py`` checks this file against
+those fixtures (and against the live reference when /root/reference is present).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------------------------------------------
+# Architecture tables
+# --------------------------------------------------------------------------------------------------------------
+
+
+def g_arch(ngf=64):
+    """Channel tables of the DCGAN generator. Reference: models/dcgan.py:5-19 (same in dcgan_specnorm.py, acgan.py)."""
+    mult = {32: ([8, 4], [4, 2]), 64: ([16, 8, 4], [8, 4, 2]), 128: ([16, 8, 4, 2], [8, 4, 2, 1])}
+    return {r: {"in_channels": [ngf * m for m in i], "out_channels": [ngf * m for m in o]} for r, (i, o) in mult.items()}
+
+
+def d_arch(ndf=64, img_dim=3):
+    """Channel tables of the DCGAN discriminator. Reference: models/dcgan.py:78-92."""
+    mult = {32: ([2, 4], [2, 4, 8]), 64: ([2, 4, 8], [2, 4, 8, 16]), 128: ([1, 2, 4, 8], [1, 2, 4, 8, 16])}
+    return {r: {"in_channels": [img_dim] + [ndf * m for m in i], "out_channels": [ndf * m for m in o]}
+            for r, (i, o) in mult.items()}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Building blocks
+# --------------------------------------------------------------------------------------------------------------
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def batch_norm_train(x, weight, bias, buffers=None, prefix=None):
+    """Training-mode BatchNorm2d as torch's nn.BatchNorm2d does it (torch: aten::native_batch_norm):
+    normalise with the biased batch variance, update running stats with the unbiased one (momentum 0.1),
+    bump num_batches_tracked. `buffers` (a dict) is updated in place when given."""
+    mean = x.mean(dim=(0, 2, 3))
+    var = x.var(dim=(0, 2, 3), unbiased=False)
+    if buffers is not None:
+        n = x.numel() // x.shape[1]
+        rm, rv = buffers[prefix + "running_mean"], buffers[prefix + "running_var"]
+        rm.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * mean.detach())
+        rv.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * var.detach() * n / max(n - 1, 1))
+        buffers[prefix + "num_batches_tracked"] += 1
+    xhat = (x - mean[None, :, None, None]) * torch.rsqrt(var[None, :, None, None] + BN_EPS)
+    if weight is not None:
+        xhat = xhat * weight[None, :, None, None] + bias[None, :, None, None]
+    return xhat
+
+
+def spectral_norm_weight(sd, prefix, dim, training=True, eps=1e-12, update_buffers=True):
+    """torch.nn.utils.spectral_norm's pre-forward hook as formulas (torch:nn/utils/spectral_norm.py:62-114):
+    W_mat = W_orig permuted so `dim` is first, flattened; one power iteration under no_grad, in place on u and v
+    (training only); sigma = u . (W_mat v) differentiable w.r.t. W_orig; weight = W_orig / sigma.
+    `dim` is 0 for Conv2d/Linear/Embedding and 1 for ConvTranspose2d (torch:...spectral_norm.py:322-334)."""
+    w = sd[prefix + "weight_orig"]
+    u, v = sd[prefix + "weight_u"], sd[prefix + "weight_v"]
+    wm = w
+    if dim != 0:
+        wm = wm.permute(dim, *[d for d in range(wm.dim()) if d != dim])
+    wm = wm.reshape(wm.size(0), -1)
+    if training:
+        with torch.no_grad():
+            v_new = F.normalize(torch.mv(wm.t(), u), dim=0, eps=eps)
+            u_new = F.normalize(torch.mv(wm, v_new), dim=0, eps=eps)
+            if update_buffers:
+                v.copy_(v_new)
+                u.copy_(u_new)
+            u, v = u_new.clone(), v_new.clone()
+    sigma = torch.dot(u, torch.mv(wm, v))
+    return w / sigma
+
+
+def _weight(sd, prefix, sn, dim, training):
+    if sn:
+        return spectral_norm_weight(sd, prefix, dim, training)
+    return sd[prefix + "weight"]
+
+
+# --------------------------------------------------------------------------------------------------------------
+# DCGAN family (models/dcgan.py, models/dcgan_specnorm.py, models/acgan.py)
+# --------------------------------------------------------------------------------------------------------------
+
+
+def dcgan_generator(sd, z, y=None, *, sn=False, acgan=False, bottom_width=4, training=True, buffers=None, acts=None):
+    """Generator.forward. Reference: models/dcgan.py:49-57 (relu(linear(z)) -> view -> [ConvT4s2p1+BN+ReLU]* ->
+    ConvT4s2p1 -> Tanh); models/dcgan_specnorm.py:49-57 (same with spectral-normed ConvT, dim=1);
+    models/acgan.py:49-57 (linear(cat[z, y]) with NO ReLU)."""
+    if acgan:
+        h = F.linear(torch.cat([z, y], 1), sd["linear.weight"], sd["linear.bias"])
+    else:
+        h = F.relu(F.linear(z, sd["linear.weight"], sd["linear.bias"]))
+    h = h.view(h.size(0), -1, bottom_width, bottom_width)
+    if acts is not None:
+        acts["linear"] = h
+    i = 0
+    while ("blocks.%d.0.bias" % i) in sd:
+        p = "blocks.%d." % i
+        h = F.conv_transpose2d(h, _weight(sd, p + "0.", sn, 1, training), sd[p + "0.bias"], stride=2, padding=1)
+        if acts is not None:
+            acts[p + "0"] = h
+        h = F.relu(batch_norm_train(h, sd[p + "1.weight"], sd[p + "1.bias"], buffers, p + "1."))
+        if acts is not None:
+            acts[p + "2"] = h
+        i += 1
+    h = F.conv_transpose2d(h, _weight(sd, "out_layer.0.", sn, 1, training), sd["out_layer.0.bias"], stride=2, padding=1)
+    return torch.tanh(h)
+
+
+def dcgan_discriminator(sd, x, *, sn=False, acgan=False, flatten_head=False, training=True, buffers=None, acts=None):
+    """Discriminator.forward. Reference: models/dcgan.py:117-124 ([Conv4s2p1 (+BN from block 1) + LeakyReLU(0.2)]*
+    -> sum over (H, W) -> Linear); models/dcgan_specnorm.py:120-131 (spectral-normed convs, flatten head);
+    models/acgan.py:118-126 (extra out_aux Linear head, returns a pair)."""
+    h = x
+    i = 0
+    while ("blocks.%d.0.bias" % i) in sd:
+        p = "blocks.%d." % i
+        h = F.conv2d(h, _weight(sd, p + "0.", sn, 0, training), sd[p + "0.bias"], stride=2, padding=1)
+        if acts is not None:
+            acts[p + "0"] = h
+        if (p + "1.weight") in sd:
+            h = batch_norm_train(h, sd[p + "1.weight"], sd[p + "1.bias"], buffers, p + "1.")
+        h = F.leaky_relu(h, 0.2)
+        if acts is not None:
+            acts[p + "act"] = h
+        i += 1
+    h = h.flatten(1) if flatten_head else h.sum(dim=(2, 3))
+    out = F.linear(h, sd["out_layer.weight"], sd["out_layer.bias"])
+    if acgan:
+        return out, F.linear(h, sd["out_aux.weight"], sd["out_aux.bias"])
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# SNGAN projection (models/sngan_projection.py)
+# --------------------------------------------------------------------------------------------------------------
+
+
+def _cbn(sd, p, x, y, buffers):
+    """ConditionalBatchNorm2d.forward. Reference: models/sngan_projection.py:15-19."""
+    c = x.shape[1]
+    out = batch_norm_train(x, None, None, buffers, p + "bn.")
+    emb = F.embedding(y, sd[p + "embed.weight"])
+    gamma, beta = emb[:, :c], emb[:, c:]
+    return gamma[:, :, None, None] * out + beta[:, :, None, None]
+
+
+def _res_gen_block(sd, p, x, y, buffers):
+    """ResGenBlock.forward (upsample=True, learnable shortcut). Reference: models/sngan_projection.py:48-66."""
+    h = F.relu(_cbn(sd, p + "b1.", x, y, buffers))
+    h = F.interpolate(h, scale_factor=2)
+    h = F.conv2d(h, sd[p + "c1.weight"], sd[p + "c1.bias"], padding=1)
+    h = F.relu(_cbn(sd, p + "b2.", h, y, buffers))
+    h = F.conv2d(h, sd[p + "c2.weight"], sd[p + "c2.bias"], padding=1)
+    sc = F.conv2d(F.interpolate(x, scale_factor=2), sd[p + "c_sc.weight"], sd[p + "c_sc.bias"])
+    return h + sc
+
+
+def sngan_generator(sd, z, y, *, bottom_width=4, buffers=None):
+    """ResNetGenerator.forward. Reference: models/sngan_projection.py:83-97."""
+    h = F.linear(z, sd["l1.weight"], sd["l1.bias"])
+    h = h.reshape(h.shape[0], -1, bottom_width, bottom_width)
+    for b in ("block2.", "block3.", "block4.", "block5."):
+        h = _res_gen_block(sd, b, h, y, buffers)
+    h = F.relu(batch_norm_train(h, sd["b6.weight"], sd["b6.bias"], buffers, "b6."))
+    return torch.tanh(F.conv2d(h, sd["l6.weight"], sd["l6.bias"], padding=1))
+
+
+def _sn_conv(sd, p, x, padding, training):
+    return F.conv2d(x, spectral_norm_weight(sd, p, 0, training), sd[p + "bias"], padding=padding)
+
+
+def sngan_discriminator(sd, x, y=None, *, training=True):
+    """SNResNetProjectionDiscriminator.forward. Reference: models/sngan_projection.py:183-196, blocks :125-136
+    (ResDisBlock) and :156-164 (ResDisOptimizedBlock). Every conv / l6 / l_y is spectral-normed (dim 0)."""
+    # block1 (optimized block): c1 -> relu -> c2 -> avgpool ; shortcut c_sc(x) -> avgpool
+    h = _sn_conv(sd, "block1.c1.", x, 1, training)
+    h = _sn_conv(sd, "block1.c2.", F.relu(h), 1, training)
+    h = F.avg_pool2d(h, 2)
+    sc = F.avg_pool2d(_sn_conv(sd, "block1.c_sc.", x, 0, training), 2)
+    h = h + sc
+    for b in ("block2.", "block3.", "block4.", "block5."):
+        xin = h
+        t = _sn_conv(sd, b + "c1.", F.relu(xin), 1, training)
+        t = _sn_conv(sd, b + "c2.", F.relu(t), 1, training)
+        t = F.avg_pool2d(t, 2)
+        sc = F.avg_pool2d(_sn_conv(sd, b + "c_sc.", xin, 0, training), 2)
+        h = t + sc
+    h = F.relu(h).sum(dim=(2, 3))
+    out = F.linear(h, spectral_norm_weight(sd, "l6.", 0, training), sd["l6.bias"])
+    if y is not None:
+        w_y = F.embedding(y, spectral_norm_weight(sd, "l_y.", 0, training))
+        out = out + (w_y * h).sum(dim=1, keepdim=True)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Losses (utils/criterion.py)
+# --------------------------------------------------------------------------------------------------------------
+
+
+def gan_loss(mode, pred, is_real, is_generator=False, real_label=1.0, fake_label=0.0, fake_g_label=1.0):
+    """GANLoss.forward. Reference: utils/criterion.py:21-41 — vanilla = BCE-with-logits against a constant soft label
+    (mean), lsgan = MSE, hinge = relu(1 -/+ p).mean() for D and -p.mean() for G."""
+    if mode in ("vanilla", "lsgan"):
+        t = real_label if is_real else (fake_g_label if is_generator else fake_label)
+        target = torch.full_like(pred, float(t))
+        if mode == "vanilla":
+            return F.binary_cross_entropy_with_logits(pred, target)
+        return F.mse_loss(pred, target)
+    if mode == "hinge":
+        if is_real:
+            return F.relu(1.0 - pred).mean()
+        if is_generator:
+            return -pred.mean()
+        return F.relu(1.0 + pred).mean()
+    raise NotImplementedError("GAN mode %s is not implemented" % mode)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# One training step (main_dcgan.py:68-95) as a pure function of parameter dicts — used for gradients / loss traces
+# --------------------------------------------------------------------------------------------------------------
+
+
+def split_state(sd):
+    """Split a state_dict into differentiable leaves (float params) and buffers (BN stats, SN u/v)."""
+    params, buffers = {}, {}
+    for k, v in sd.items():
+        is_buf = k.endswith(("running_mean", "running_var", "num_batches_tracked", "weight_u", "weight_v"))
+        (buffers if is_buf else params)[k] = v
+    return params, buffers
+
+
+def dcgan_step_grads(sd_g, sd_d, x_real, z1, z2, labels=(0.9, 0.1, 0.9), mode="vanilla", **net_kw):
+    """Gradients of the three backward passes of one step, following main_dcgan.py:68-95:
+    D-real backward, D-fake backward (on G(z1).detach()), G-step backward through D (on G(z2)).
+    Returns dict with losses, D grads (accumulated real+fake), G grads, and the logits."""
+    rl, fl, gl = labels
+    g_kw = {k: v for k, v in net_kw.items() if k in ("sn", "bottom_width")}
+    d_kw = {k: v for k, v in net_kw.items() if k in ("sn", "flatten_head")}
+    pg = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd_g.items()}
+    pd = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd_d.items()}
+    out = {}
+    d_real = dcgan_discriminator(pd, x_real, **d_kw)
+    loss_real = gan_loss(mode, d_real, True, False, rl, fl, gl)
+    fake1 = dcgan_generator(pg, z1, **g_kw).detach()
+    d_fake = dcgan_discriminator(pd, fake1, **d_kw)
+    loss_fake = gan_loss(mode, d_fake, False, False, rl, fl, gl)
+    d_leaves = [k for k, v in pd.items() if v.requires_grad]
+    gr = torch.autograd.grad(loss_real, [pd[k] for k in d_leaves], allow_unused=True)
+    gf = torch.autograd.grad(loss_fake, [pd[k] for k in d_leaves], allow_unused=True)
+    out["d_grads_real"] = {k: g for k, g in zip(d_leaves, gr) if g is not None}
+    out["d_grads_fake"] = {k: g for k, g in zip(d_leaves, gf) if g is not None}
+    fake2 = dcgan_generator(pg, z2, **g_kw)
+    d_g = dcgan_discriminator(pd, fake2, **d_kw)
+    loss_g = gan_loss(mode, d_g, False, True, rl, fl, gl)
+    g_leaves = [k for k, v in pg.items() if v.requires_grad]
+    gg = torch.autograd.grad(loss_g, [pg[k] for k in g_leaves], allow_unused=True)
+    out["g_grads"] = {k: g for k, g in zip(g_leaves, gg) if g is not None}
+    out.update(loss_real=loss_real.detach(), loss_fake=loss_fake.detach(), loss_g=loss_g.detach(),
+               d_real=d_real.detach(), d_fake=d_fake.detach(), d_g=d_g.detach(), fake1=fake1, fake2=fake2.detach())
+    return out
+
+
+def step_flops_dcgan64(batch):
+    """Minimal algorithmic FLOPs of one DCGAN-64 step: 9.7994 GFLOP per image."""
+    return 9.7994e9 * batch
