@@ -1,0 +1,39 @@
+"""GANLoss: API mirror of the reference's utils/criterion.py:4-41 with the loss value and its gradient computed by one
+fused reduction kernel (gp_gan_loss). Labels are registered buffers exactly as upstream (so .to(device) and
+state_dict() behave the same: keys real_label / fake_label / fake_G_label)."""
+import torch
+import torch.nn as nn
+
+from . import functional as GF
+from . import ops
+from ._lib import GpError
+
+
+class GANLoss(nn.Module):
+    def __init__(self, gan_mode, target_real_label=1.0, target_fake_label=0.0, target_fake_G_label=1.0):
+        super().__init__()
+        self.gan_mode = gan_mode
+        self.register_buffer('real_label', torch.tensor(target_real_label))
+        self.register_buffer('fake_label', torch.tensor(target_fake_label))
+        self.register_buffer('fake_G_label', torch.tensor(target_fake_G_label))
+        if gan_mode not in ('vanilla', 'lsgan', 'hinge'):
+            raise NotImplementedError('GAN mode %s is not implemented' % gan_mode)
+        self.loss = None  # upstream stores an nn loss module here; the fused kernel needs none
+        # host copies of the labels: reading the device buffers every call would be a sync in the hot loop
+        self._host_labels = (float(target_real_label), float(target_fake_label), float(target_fake_G_label))
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        self._host_labels = (float(self.real_label), float(self.fake_label), float(self.fake_G_label))
+
+    def forward(self, prediction, is_real, is_generator=False):
+        if not prediction.is_cuda:
+            raise GpError("GANLoss: prediction is on %s — CUDA only, no CPU fallback" % prediction.device)
+        r, f, g = self._host_labels
+        if self.gan_mode in ('vanilla', 'lsgan'):
+            target = r if is_real else (g if is_generator else f)
+            mode = ops.LOSS_BCE if self.gan_mode == 'vanilla' else ops.LOSS_MSE
+        else:
+            target = 0.0
+            mode = ops.LOSS_HINGE_REAL if is_real else (ops.LOSS_NEG_MEAN if is_generator else ops.LOSS_HINGE_FAKE)
+        return GF.GanLossFn.apply(prediction, mode, target)

@@ -1,0 +1,280 @@
+"""Autograd nodes of the hot path. Each node is one fused block of the reference networks
+(conv / conv-transpose [+ BatchNorm] + activation, the first Linear, the image-side layers, the heads, the loss) whose
+forward and backward are sequences of C-ABI kernel calls (ops.py). Activations between nodes are NHWC bf16 tensors;
+parameters stay fp32 nn.Parameters in torch's layout and receive fp32 gradients, so torch.optim.Adam and
+state_dict()/torch.save work unchanged."""
+import torch
+
+from . import ops, parallel
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+class WeightCache:
+    """bf16 GEMM-operand copies of fp32 parameters, re-staged only when the parameter changes (optimizer.step bumps
+    tensor._version). One D forward per step packs; the other two reuse (main_dcgan.py:70,80,91)."""
+
+    def __init__(self):
+        self._d = {}
+
+    def get(self, key, param, make):
+        if not param.is_leaf:  # derived weight (e.g. W / sigma of spectral norm): new tensor every forward
+            return make()
+        ver = param._version
+        ent = self._d.get(key)
+        if ent is not None and ent[0] == ver and ent[1] == param.data_ptr():
+            return ent[2]
+        val = make()
+        self._d[key] = (ver, param.data_ptr(), val)
+        return val
+
+    def clear(self):
+        self._d.clear()
+
+
+def _bn_forward(y, gamma, beta, bufs, act, training=True):
+    """y: bf16 NHWC pre-BN conv output. Returns (a, fin[4,C], count).
+    training: batch statistics (all-reduced over ranks) + running-stat update, as nn.BatchNorm2d.train();
+    eval: normalise with the running statistics."""
+    C = y.shape[-1]
+    count = (y.numel() // C) * parallel.world_size()
+    rm, rv, nbt = bufs if bufs is not None else (None, None, None)
+    if training or rm is None:
+        st = ops.bn_stats(y)
+        parallel.all_reduce_sum_(st)
+        fin = ops.bn_finalize(st, count, gamma, beta, rm, rv, nbt, BN_EPS, BN_MOMENTUM)
+    else:
+        fin = ops.bn_eval_params(rm, rv, gamma, beta, BN_EPS)
+    a = ops.bn_apply_act(y, fin, act)
+    return a, fin, count
+
+
+def _bn_backward(da, y, fin, count, act, training=True):
+    """Returns (dy, dgamma, dbeta)."""
+    red = ops.bn_bwd_reduce(da, y, fin, act)
+    parallel.all_reduce_sum_(red)
+    # eval mode: statistics are constants, so the two batch-coupling terms vanish
+    dy = ops.bn_bwd_apply(da, y, fin, red if training else torch.zeros_like(red), count, act)
+    # dbeta = sum dz, dgamma = sum dz * xhat: local shares are red / world after the all-reduce made them global;
+    # parameter gradients are averaged over ranks later, so hand back the global sums divided by world.
+    w = parallel.world_size()
+    dgamma, dbeta = red[1], red[0]
+    if w > 1:
+        dgamma, dbeta = dgamma / w, dbeta / w
+    return dy, dgamma.clone(), dbeta.clone()
+
+
+class ConvBlock(torch.autograd.Function):
+    """[Conv2d | ConvTranspose2d](k4 s2 p1, bias) [+ BatchNorm2d(train)] + activation on NHWC bf16.
+    Reference: models/dcgan.py:35-40 (G blocks) and :104-110 (D blocks)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, bufs, transposed, act, cache, key, training=True):
+        NB, H, W, Cin = x.shape
+        if transposed:
+            Cout = weight.shape[1]
+            wp = cache.get((key, "fwd"), weight, lambda: ops.pack_conv_weight(weight.detach(), 1))
+            Ho, Wo, kind = 2 * H, 2 * W, ops.KIND_CONVT_K4S2
+        else:
+            Cout = weight.shape[0]
+            wp = cache.get((key, "fwd"), weight, lambda: ops.pack_conv_weight(weight.detach(), 0))
+            Ho, Wo, kind = H // 2, W // 2, ops.KIND_CONV_K4S2
+        has_bn = gamma is not None or bufs is not None
+        y = ops.conv_fwd(x, wp, bias.detach() if bias is not None else None, kind, Ho, Wo,
+                         ops.ACT_NONE if has_bn else act)
+        ctx.transposed, ctx.act, ctx.has_bn, ctx.cache, ctx.key = transposed, act, has_bn, cache, key
+        if has_bn:
+            a, fin, count = _bn_forward(y, gamma.detach() if gamma is not None else None,
+                                        beta.detach() if beta is not None else None, bufs, act, training)
+            ctx.count, ctx.training = count, training
+            ctx.save_for_backward(x, weight, y, fin)
+        else:
+            a = y
+            ctx.save_for_backward(x, weight, a)
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        da = da.contiguous()
+        if ctx.has_bn:
+            x, weight, y, fin = ctx.saved_tensors
+            dy, dgamma, dbeta = _bn_backward(da, y, fin, ctx.count, ctx.act, ctx.training)
+            dbias = torch.zeros(dy.shape[-1], device=dy.device, dtype=torch.float32)  # analytically zero before BN
+        else:
+            x, weight, a = ctx.saved_tensors
+            dy = ops.act_bwd(da, a, ctx.act) if ctx.act != ops.ACT_NONE else da
+            dgamma = dbeta = None
+            dbias = ops.colsum(dy)
+        dweight = dx = None
+        if ctx.needs_input_grad[1]:
+            if ctx.transposed:   # dW[Cin][tap][Cout]: dense = x (input grid), gathered = dy (output grid)
+                dwp = ops.conv_wgrad(x, dy, ops.KIND_CONV_K4S2, 16)
+            else:                # dW[Cout][tap][Cin]: dense = dy (output grid), gathered = x (input grid)
+                dwp = ops.conv_wgrad(dy, x, ops.KIND_CONV_K4S2, 16)
+            dweight = ops.unpack_conv_wgrad(dwp, weight.shape)
+        if ctx.needs_input_grad[0]:
+            NB, H, W, _ = x.shape
+            if ctx.transposed:   # dgrad of ConvT == strided conv over dy with weights [Cin][tap][Cout]
+                wpd = ctx.cache.get((ctx.key, "dgrad"), weight, lambda: ops.pack_conv_weight(weight.detach(), 0))
+                dx = ops.conv_fwd(dy, wpd, None, ops.KIND_CONV_K4S2, H, W)
+            else:                # dgrad of Conv == 4-phase transposed conv over dy with weights [Cin][tap][Cout]
+                wpd = ctx.cache.get((ctx.key, "dgrad"), weight, lambda: ops.pack_conv_weight(weight.detach(), 1))
+                dx = ops.conv_fwd(dy, wpd, None, ops.KIND_CONVT_K4S2, H, W)
+        if not ctx.needs_input_grad[2]:
+            dbias = None
+        return dx, dweight, dbias, dgamma, dbeta, None, None, None, None, None, None
+
+
+class LinearToNHWC(torch.autograd.Function):
+    """z (B, K) fp32 -> act(Linear(z)).view(B, C, bw, bw) delivered as NHWC bf16 (B, bw, bw, C).
+    Reference: models/dcgan.py:32,50-51 (ReLU) and models/acgan.py:49-50 (no activation)."""
+
+    @staticmethod
+    def forward(ctx, z, weight, bias, bw, act, cache, key):
+        B, K = z.shape
+        O = weight.shape[0]
+        HW = bw * bw
+        C = O // HW
+        Kp = (K + 7) // 8 * 8
+        zb = ops.pack_matrix(z.detach().contiguous(), B, K, B, Kp, K, 1)
+        wp = cache.get((key, "fwd"), weight, lambda: ops.pack_matrix(weight.detach(), O, K, O, Kp, K, 1, perm=HW))
+        # bias in NHWC-flatten order: dst[(s % HW)*C + s // HW] = bias[s]
+        bp = cache.get((key, "bias"), bias, lambda: ops.unpack_matrix(bias.detach(), (O,), O, 1, 1, 1, 1, perm=C))
+        a = ops.conv_fwd(zb.view(B, 1, 1, Kp), wp, bp, ops.KIND_CONV_K1S1, 1, 1, act)
+        ctx.save_for_backward(zb, a, weight)
+        ctx.dims = (B, K, O, HW, C, Kp, act)
+        return a.view(B, bw, bw, C)
+
+    @staticmethod
+    def backward(ctx, da):
+        zb, a, weight = ctx.saved_tensors
+        B, K, O, HW, C, Kp, act = ctx.dims
+        da = da.contiguous().view(B, 1, 1, O)
+        dy = ops.act_bwd(da, a, act) if act != ops.ACT_NONE else da
+        dweight = dbias = None
+        if ctx.needs_input_grad[1]:
+            dwp = ops.conv_wgrad(dy, zb.view(B, 1, 1, Kp), ops.KIND_CONV_K1S1, 1)  # [O][1][Kp], rows in NHWC order
+            dweight = ops.unpack_matrix(dwp.view(O, Kp), weight.shape, O, K, Kp, K, 1, perm=HW)
+        if ctx.needs_input_grad[2]:
+            db = ops.colsum(dy)
+            dbias = ops.unpack_matrix(db, (O,), O, 1, 1, 1, 1, perm=HW)
+        if ctx.needs_input_grad[0]:
+            raise ops._lib.GpError("gradient w.r.t. the latent input of the first Linear is not implemented")
+        return None, dweight, dbias, None, None, None, None
+
+
+class ImageConv(torch.autograd.Function):
+    """D's first layer: Conv2d(img_dim -> C, k4 s2 p1) + LeakyReLU(0.2) reading the fp32 NCHW image directly.
+    Reference: models/dcgan.py:106-109 (block 0 has no BatchNorm). im2col -> 1-tap tensor-core GEMM (K = 64)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, cache, key):
+        x = x.contiguous()
+        NB, ch, H, W = x.shape
+        Cout = weight.shape[0]
+        col = ops.im2col_k4s2(x.detach())
+        wp = cache.get((key, "fwd"), weight,
+                       lambda: ops.pack_matrix(weight.detach(), Cout, ch * 16, Cout, 64, ch * 16, 1))
+        a = ops.conv_fwd(col, wp, bias.detach(), ops.KIND_CONV_K1S1, H // 2, W // 2, act)
+        ctx.save_for_backward(x, weight, a)
+        ctx.misc = (act, cache, key)
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        x, weight, a = ctx.saved_tensors
+        act, cache, key = ctx.misc
+        NB, ch, H, W = x.shape
+        Cout = weight.shape[0]
+        dy = ops.act_bwd(da.contiguous(), a, act) if act != ops.ACT_NONE else da.contiguous()
+        dweight = dbias = dx = None
+        if ctx.needs_input_grad[1]:
+            col = ops.im2col_k4s2(x)
+            dwp = ops.conv_wgrad(dy, col, ops.KIND_CONV_K1S1, 1)  # [Cout][1][64]
+            dweight = ops.unpack_matrix(dwp.view(Cout, 64), weight.shape, Cout, ch * 16, 64, ch * 16, 1)
+        if ctx.needs_input_grad[2]:
+            dbias = ops.colsum(dy)
+        if ctx.needs_input_grad[0]:
+            # dcol[px][j] = sum_o dy[px][o] * W[o][j]  -> weights [64][Cout] = W^T (rows j >= ch*16 are zero)
+            wpt = cache.get((key, "dgrad"), weight,
+                            lambda: ops.pack_matrix(weight.detach(), ch * 16, Cout, 64, Cout, 1, ch * 16))
+            dcol = ops.conv_fwd(dy, wpt, None, ops.KIND_CONV_K1S1, H // 2, W // 2)
+            dx = ops.col2im_k4s2(dcol, None, ch, ops.ACT_NONE)
+        return dx, dweight, dbias, None, None, None
+
+
+class ImageConvT(torch.autograd.Function):
+    """G's last layer: ConvTranspose2d(C -> img_dim, k4 s2 p1) + Tanh writing the fp32 NCHW image.
+    Reference: models/dcgan.py:41-44. 1-tap tensor-core GEMM (N = 64) -> col2im + bias + tanh."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, cache, key):
+        NB, H, W, Cin = x.shape
+        ch = weight.shape[1]
+        wp = cache.get((key, "fwd"), weight,
+                       lambda: ops.pack_matrix(weight.detach(), ch * 16, Cin, 64, Cin, 1, ch * 16))
+        ycol = ops.conv_fwd(x, wp, None, ops.KIND_CONV_K1S1, H, W)
+        out = ops.col2im_k4s2(ycol, bias.detach(), ch, act)
+        ctx.save_for_backward(x, weight, out)
+        ctx.misc = (act, cache, key)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight, out = ctx.saved_tensors
+        act, cache, key = ctx.misc
+        NB, H, W, Cin = x.shape
+        ch = weight.shape[1]
+        dout = dout.contiguous()
+        # dcol[(n,ih,iw)][(co,kh,kw)] = dpre[n, co, 2ih-1+kh, 2iw-1+kw], dpre = dout * (1 - out^2) fused into the gather
+        dcol = ops.im2col_k4s2(dout, out if act == ops.ACT_TANH else None)
+        dweight = dbias = dx = None
+        if ctx.needs_input_grad[1]:
+            dwp = ops.conv_wgrad(x, dcol, ops.KIND_CONV_K1S1, 1)  # [Cin][1][64]
+            dweight = ops.unpack_matrix(dwp.view(Cin, 64), weight.shape, Cin, ch * 16, 64, ch * 16, 1)
+        if ctx.needs_input_grad[2]:
+            dbias = ops.image_bias_grad(dout, out if act == ops.ACT_TANH else None)
+        if ctx.needs_input_grad[0]:
+            wpd = cache.get((key, "dgrad"), weight,
+                            lambda: ops.pack_matrix(weight.detach(), Cin, ch * 16, Cin, 64, ch * 16, 1))
+            dx = ops.conv_fwd(dcol, wpd, None, ops.KIND_CONV_K1S1, H, W)
+        return dx, dweight, dbias, None, None, None
+
+
+class Head(torch.autograd.Function):
+    """Discriminator head on NHWC bf16 features: out[b][o] = bias[o] + sum_{hw,c} a[b,hw,c] * w[o, c, hw].
+    flatten=False: global sum pooling + Linear (models/dcgan.py:121-122); flatten=True: NCHW flatten + Linear
+    (models/dcgan_specnorm.py:125-126)."""
+
+    @staticmethod
+    def forward(ctx, a, weight, bias, flatten):
+        NB, H, W, C = a.shape
+        O = weight.shape[0]
+        strides = (C * H * W, H * W, 1) if flatten else (C, 1, 0)
+        out = ops.head_fwd(a, weight.detach(), bias.detach() if bias is not None else None, O, *strides)
+        ctx.save_for_backward(a, weight)
+        ctx.strides, ctx.O, ctx.has_bias = strides, O, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        a, weight = ctx.saved_tensors
+        da, dw, db = ops.head_bwd(dout.contiguous(), a, weight.detach(), ctx.O, *ctx.strides,
+                                  need_da=ctx.needs_input_grad[0], need_dw=ctx.needs_input_grad[1], need_db=ctx.has_bias)
+        return da, dw, (db if ctx.has_bias else None), None
+
+
+class GanLossFn(torch.autograd.Function):
+    """GANLoss value + gradient in one fused reduction (utils/criterion.py:30-41)."""
+
+    @staticmethod
+    def forward(ctx, pred, mode, target):
+        loss, dpred = ops.gan_loss(pred.detach().contiguous(), mode, target)
+        ctx.save_for_backward(dpred)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dpred,) = ctx.saved_tensors
+        return dpred * g, None, None

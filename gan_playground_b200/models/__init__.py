@@ -1,0 +1,3 @@
+"""Drop-in nn.Module mirrors of the reference's DCGAN-family networks (same constructors, forward signatures,
+sub-module names and state_dict layout), computing on hand-written sm_100a kernels."""
+from . import dcgan  # noqa: F401

@@ -1,0 +1,267 @@
+"""Thin torch-tensor wrappers over the C-ABI (include/gpb200.h). PyTorch is the host: it owns device memory and the
+current stream; every function here only validates shapes/dtypes, allocates outputs with torch and passes raw pointers.
+No computation happens in Python or in torch ops on this path."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvFwd, ConvWgrad, check
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
+KIND_CONV_K4S2, KIND_CONVT_K4S2, KIND_CONV_K3S1, KIND_CONV_K1S1 = 0, 1, 2, 3
+LOSS_BCE, LOSS_MSE, LOSS_HINGE_REAL, LOSS_HINGE_FAKE, LOSS_NEG_MEAN = 0, 1, 2, 3, 4
+
+_vp, _i, _ll, _f, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_double
+_SIGS = {
+    "gp_conv_fwd": [_vp, _vp],
+    "gp_conv_wgrad": [_vp, _vp],
+    "gp_pack_conv_weight": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "gp_unpack_conv_wgrad": [_vp, _vp, _i, _i, _i, _vp],
+    "gp_pack_matrix": [_vp, _vp, _i, _i, _i, _i, _ll, _ll, _i, _vp, _vp],
+    "gp_unpack_matrix": [_vp, _vp, _i, _i, _i, _ll, _ll, _i, _vp],
+    "gp_bn_stats": [_vp, _ll, _i, _vp, _vp, _vp],
+    "gp_bn_finalize": [_vp, _vp, _d, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "gp_bn_eval_params": [_vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp],
+    "gp_bn_apply_act": [_vp, _vp, _ll, _i, _vp, _vp, _i, _vp],
+    "gp_bn_bwd_reduce": [_vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "gp_bn_bwd_apply": [_vp, _vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _vp],
+    "gp_act_bwd": [_vp, _vp, _vp, _ll, _i, _vp],
+    "gp_colsum": [_vp, _ll, _i, _vp, _vp],
+    "gp_im2col_k4s2": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "gp_col2im_k4s2": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "gp_image_bias_grad": [_vp, _vp, _vp, _i, _i, _i, _vp],
+    "gp_head_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _vp],
+    "gp_head_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _vp],
+    "gp_gan_loss": [_vp, _i, _i, _f, _vp, _vp, _vp],
+}
+_bound = {}
+
+
+def _fn(name):
+    f = _bound.get(name)
+    if f is None:
+        f = getattr(_lib.lib(), name)
+        f.argtypes = _SIGS[name]
+        f.restype = ctypes.c_int
+        _bound[name] = f
+    return f
+
+
+def exported_symbols():
+    """Names of every compute entry point declared in include/gpb200.h (used by the CPU-side ABI test)."""
+    return sorted(_SIGS) + ["gp_version", "gp_last_error", "gp_launch_count"]
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, dtype, name):
+    if not t.is_cuda:
+        raise _lib.GpError("%s must be a CUDA tensor (the hot path has no CPU fallback)" % name)
+    if t.dtype != dtype:
+        raise _lib.GpError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise _lib.GpError("%s must be contiguous" % name)
+
+
+# ------------------------------------------------------------------------------------------------ conv GEMMs
+def conv_fwd(x, wp, bias, kind, Hout, Wout, act=ACT_NONE, stats=None):
+    """x: bf16 (NB, Hin, Win, Cin); wp: bf16 [Nout, taps*Cin]; returns bf16 (NB, Hout, Wout, Nout).
+    stats: optional fp32 [2, Nout] zeroed tensor receiving per-channel sum / sum of squares."""
+    _chk(x, torch.bfloat16, "x")
+    _chk(wp, torch.bfloat16, "wp")
+    NB, Hin, Win, Cin = x.shape
+    Nout = wp.shape[0]
+    out = torch.empty((NB, Hout, Wout, Nout), device=x.device, dtype=torch.bfloat16)
+    if bias is not None:
+        _chk(bias, torch.float32, "bias")
+    p = ConvFwd(_p(x), _p(wp), _p(bias), _p(out), _p(stats[0]) if stats is not None else None,
+                _p(stats[1]) if stats is not None else None, NB, Hin, Win, Cin, Hout, Wout, Nout, kind, act)
+    check(_fn("gp_conv_fwd")(ctypes.addressof(p), _stream()), "gp_conv_fwd")
+    return out
+
+
+def conv_wgrad(dense, gath, kind, taps):
+    """dense: bf16 (NB, Hs, Ws, Cd); gath: bf16 (NB, Hg, Wg, Cg); returns fp32 [Cd, taps, Cg]."""
+    _chk(dense, torch.bfloat16, "dense")
+    _chk(gath, torch.bfloat16, "gath")
+    NB, Hs, Ws, Cd = dense.shape
+    _, Hg, Wg, Cg = gath.shape
+    dw = torch.zeros((Cd, taps, Cg), device=dense.device, dtype=torch.float32)
+    p = ConvWgrad(_p(dense), _p(gath), _p(dw), NB, Hs, Ws, Cd, Hg, Wg, Cg, kind)
+    check(_fn("gp_conv_wgrad")(ctypes.addressof(p), _stream()), "gp_conv_wgrad")
+    return dw
+
+
+# ------------------------------------------------------------------------------------------------ weight staging
+def pack_conv_weight(w, n_dim, inv_scale=None):
+    """w: fp32 (D0, D1, kh, kw) -> bf16 [N, taps*C], (N, C) = (D0, D1) if n_dim == 0 else (D1, D0)."""
+    _chk(w, torch.float32, "w")
+    D0, D1 = w.shape[0], w.shape[1]
+    taps = w.shape[2] * w.shape[3]
+    N, C = (D0, D1) if n_dim == 0 else (D1, D0)
+    dst = torch.empty((N, taps * C), device=w.device, dtype=torch.bfloat16)
+    check(_fn("gp_pack_conv_weight")(_p(w), _p(dst), D0, D1, taps, n_dim, _p(inv_scale), _stream()), "gp_pack_conv_weight")
+    return dst
+
+
+def unpack_conv_wgrad(dwp, shape):
+    """dwp: fp32 [M, taps, N] -> fp32 tensor of `shape` = (M, N, kh, kw)."""
+    _chk(dwp, torch.float32, "dwp")
+    M, taps, N = dwp.shape
+    dst = torch.empty(shape, device=dwp.device, dtype=torch.float32)
+    check(_fn("gp_unpack_conv_wgrad")(_p(dwp), _p(dst), M, N, taps, _stream()), "gp_unpack_conv_wgrad")
+    return dst
+
+
+def pack_matrix(src, R, K, Rpad, ld, s_r, s_k, perm=1, inv_scale=None):
+    """Generic fp32 -> bf16 [Rpad, ld] staging with strides, zero padding and optional NCHW->NHWC row permutation."""
+    _chk(src, torch.float32, "src")
+    dst = torch.empty((Rpad, ld), device=src.device, dtype=torch.bfloat16)
+    check(_fn("gp_pack_matrix")(_p(src), _p(dst), R, K, Rpad, ld, s_r, s_k, perm, _p(inv_scale), _stream()), "gp_pack_matrix")
+    return dst
+
+
+def unpack_matrix(src, out_shape, R, K, ld_src, s_r, s_k, perm=1):
+    _chk(src, torch.float32, "src")
+    dst = torch.zeros(out_shape, device=src.device, dtype=torch.float32)
+    check(_fn("gp_unpack_matrix")(_p(src), _p(dst), R, K, ld_src, s_r, s_k, perm, _stream()), "gp_unpack_matrix")
+    return dst
+
+
+# ------------------------------------------------------------------------------------------------ BatchNorm
+def bn_stats(y):
+    """y: bf16 (..., C) -> fp32 [2, C] (sum, sum of squares)."""
+    _chk(y, torch.bfloat16, "y")
+    C = y.shape[-1]
+    P = y.numel() // C
+    st = torch.zeros((2, C), device=y.device, dtype=torch.float32)
+    check(_fn("gp_bn_stats")(_p(y), P, C, _p(st[0]), _p(st[1]), _stream()), "gp_bn_stats")
+    return st
+
+
+def bn_finalize(st, count, gamma, beta, running_mean, running_var, nbt, eps=1e-5, momentum=0.1):
+    """Returns fp32 [4, C]: mean, rstd, scale, shift. Updates running buffers in place when given."""
+    C = st.shape[1]
+    out = torch.empty((4, C), device=st.device, dtype=torch.float32)
+    check(_fn("gp_bn_finalize")(_p(st[0]), _p(st[1]), float(count), C, eps, momentum, _p(gamma), _p(beta), _p(out[0]),
+                                _p(out[1]), _p(out[2]), _p(out[3]), _p(running_mean), _p(running_var), _p(nbt), _stream()),
+          "gp_bn_finalize")
+    return out
+
+
+def bn_eval_params(running_mean, running_var, gamma, beta, eps=1e-5):
+    """Eval-mode BatchNorm: fp32 [4, C] (mean, rstd, scale, shift) from the running statistics."""
+    C = running_mean.shape[0]
+    out = torch.empty((4, C), device=running_mean.device, dtype=torch.float32)
+    check(_fn("gp_bn_eval_params")(_p(running_mean), _p(running_var), _p(gamma), _p(beta), C, eps, _p(out[0]), _p(out[1]),
+                                   _p(out[2]), _p(out[3]), _stream()), "gp_bn_eval_params")
+    return out
+
+
+def bn_apply_act(y, fin, act):
+    _chk(y, torch.bfloat16, "y")
+    C = y.shape[-1]
+    out = torch.empty_like(y)
+    check(_fn("gp_bn_apply_act")(_p(y), _p(out), y.numel() // C, C, _p(fin[2]), _p(fin[3]), act, _stream()), "gp_bn_apply_act")
+    return out
+
+
+def bn_bwd_reduce(da, y, fin, act):
+    _chk(da, torch.bfloat16, "da")
+    _chk(y, torch.bfloat16, "y")
+    C = y.shape[-1]
+    red = torch.zeros((2, C), device=y.device, dtype=torch.float32)
+    check(_fn("gp_bn_bwd_reduce")(_p(da), _p(y), y.numel() // C, C, _p(fin[2]), _p(fin[3]), _p(fin[0]), _p(fin[1]), act,
+                                  _p(red[0]), _p(red[1]), _stream()), "gp_bn_bwd_reduce")
+    return red
+
+
+def bn_bwd_apply(da, y, fin, red, count, act):
+    C = y.shape[-1]
+    dy = torch.empty_like(y)
+    check(_fn("gp_bn_bwd_apply")(_p(da), _p(y), _p(dy), y.numel() // C, C, _p(fin[2]), _p(fin[3]), _p(fin[0]), _p(fin[1]),
+                                 _p(red[0]), _p(red[1]), float(count), act, _stream()), "gp_bn_bwd_apply")
+    return dy
+
+
+def act_bwd(da, a, act):
+    _chk(da, torch.bfloat16, "da")
+    _chk(a, torch.bfloat16, "a")
+    dy = torch.empty_like(a)
+    check(_fn("gp_act_bwd")(_p(da), _p(a), _p(dy), a.numel(), act, _stream()), "gp_act_bwd")
+    return dy
+
+
+def colsum(x):
+    _chk(x, torch.bfloat16, "x")
+    C = x.shape[-1]
+    out = torch.zeros((C,), device=x.device, dtype=torch.float32)
+    check(_fn("gp_colsum")(_p(x), x.numel() // C, C, _p(out), _stream()), "gp_colsum")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ image layers
+def im2col_k4s2(img, mul=None):
+    """img: fp32 NCHW (NB, ch, Hi, Wi) -> bf16 (NB, Hi/2, Wi/2, 64)."""
+    _chk(img, torch.float32, "img")
+    NB, ch, Hi, Wi = img.shape
+    col = torch.empty((NB, Hi // 2, Wi // 2, 64), device=img.device, dtype=torch.bfloat16)
+    if mul is not None:
+        _chk(mul, torch.float32, "mul")
+    check(_fn("gp_im2col_k4s2")(_p(img), _p(mul), _p(col), NB, ch, Hi, Wi, _stream()), "gp_im2col_k4s2")
+    return col
+
+
+def col2im_k4s2(col, bias, ch, act):
+    """col: bf16 (NB, Ho, Wo, 64) -> fp32 NCHW (NB, ch, 2Ho, 2Wo)."""
+    _chk(col, torch.bfloat16, "col")
+    NB, Ho, Wo, _ = col.shape
+    img = torch.empty((NB, ch, 2 * Ho, 2 * Wo), device=col.device, dtype=torch.float32)
+    check(_fn("gp_col2im_k4s2")(_p(col), _p(bias), _p(img), NB, ch, 2 * Ho, 2 * Wo, act, _stream()), "gp_col2im_k4s2")
+    return img
+
+
+def image_bias_grad(dout, mul=None):
+    _chk(dout, torch.float32, "dout")
+    NB, ch, H, W = dout.shape
+    db = torch.zeros((ch,), device=dout.device, dtype=torch.float32)
+    check(_fn("gp_image_bias_grad")(_p(dout), _p(mul), _p(db), NB, ch, H * W, _stream()), "gp_image_bias_grad")
+    return db
+
+
+# ------------------------------------------------------------------------------------------------ heads / losses
+def head_fwd(a, w, bias, O, s_o, s_c, s_hw):
+    """a: bf16 (NB, H, W, C); returns fp32 (NB, O)."""
+    _chk(a, torch.bfloat16, "a")
+    _chk(w, torch.float32, "w")
+    NB, H, W, C = a.shape
+    out = torch.empty((NB, O), device=a.device, dtype=torch.float32)
+    check(_fn("gp_head_fwd")(_p(a), _p(w), _p(bias), _p(out), NB, H * W, C, O, s_o, s_c, s_hw, _stream()), "gp_head_fwd")
+    return out
+
+
+def head_bwd(dout, a, w, O, s_o, s_c, s_hw, need_da=True, need_dw=True, need_db=True):
+    _chk(dout, torch.float32, "dout")
+    NB, H, W, C = a.shape
+    da = torch.empty_like(a) if need_da else None
+    dw = torch.zeros_like(w) if need_dw else None
+    db = torch.empty((O,), device=a.device, dtype=torch.float32) if (need_db and need_dw) else None
+    check(_fn("gp_head_bwd")(_p(dout), _p(a), _p(w), _p(da), _p(dw), _p(db), NB, H * W, C, O, s_o, s_c, s_hw, _stream()),
+          "gp_head_bwd")
+    return da, dw, db
+
+
+def gan_loss(pred, mode, target):
+    """pred: fp32 (n, ...) -> (loss scalar fp32 tensor, dpred fp32 like pred) in one kernel."""
+    _chk(pred, torch.float32, "pred")
+    loss = torch.empty((), device=pred.device, dtype=torch.float32)
+    dpred = torch.empty_like(pred)
+    check(_fn("gp_gan_loss")(_p(pred), pred.numel(), mode, float(target), _p(loss), _p(dpred), _stream()), "gp_gan_loss")
+    return loss, dpred

@@ -1,0 +1,139 @@
+"""Batch-sharded data parallelism for the adversarial step: one process per GPU, NCCL over NVLink.
+
+The reference has no parallelism at all; the semantics defined here are "N ranks on B/N samples each
+== the single-device reference at global batch B in exact arithmetic":
+  * BatchNorm statistics (sum, sum of squares; and the two backward sums) are all-reduced -> global-batch statistics;
+  * losses are means over the *global* batch, so parameter gradients are averaged (all-reduce sum / world);
+  * parameters, Adam state, SN u/v and running statistics are replicated (broadcast once from rank 0).
+"""
+import contextlib
+import os
+
+import torch
+import torch.distributed as dist
+
+_state = {"enabled": False, "world": 1, "rank": 0, "group": None, "sync_grads": True}
+
+
+def init(backend=None, device=None):
+    """Initialise from torchrun-style environment variables (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        kw = {}
+        if backend == "nccl":
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+    _state.update(enabled=True, world=world, rank=rank)
+    return rank, world
+
+
+def shutdown():
+    if dist.is_initialized():
+        dist.destroy_process_group()
+    _state.update(enabled=False, world=1, rank=0)
+
+
+def world_size():
+    return _state["world"]
+
+
+def rank():
+    return _state["rank"]
+
+
+def enabled():
+    return _state["enabled"] and _state["world"] > 1
+
+
+def all_reduce_sum_(t):
+    """In-place sum over ranks (SyncBN partial sums). No-op on a single rank."""
+    if enabled():
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def broadcast_module(module, src=0):
+    """Replicate parameters and buffers from rank `src` (done once after construction)."""
+    if not enabled():
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src)
+
+
+def shard(t, dim=0):
+    """Rank r's contiguous shard [r*B/N, (r+1)*B/N) of a global-batch tensor."""
+    if not enabled():
+        return t
+    n = t.shape[dim] // _state["world"]
+    return t.narrow(dim, _state["rank"] * n, n)
+
+
+@contextlib.contextmanager
+def no_sync():
+    """Skip gradient all-reduces inside the block (use for the first of several accumulating backwards)."""
+    prev = _state["sync_grads"]
+    _state["sync_grads"] = False
+    try:
+        yield
+    finally:
+        _state["sync_grads"] = prev
+
+
+class GradBucket:
+    """Flat fp32 bucket for one network's gradients: one all-reduce per optimiser step.
+
+    Usage:  bucket = GradBucket(net);  ...backward()...;  bucket.all_reduce_mean();  opt.step()
+    Parameters' .grad become views into the flat buffer so no copy is needed before or after the collective."""
+
+    def __init__(self, module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.views = []
+        off = 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def attach(self):
+        """Point every .grad at its slice of the flat buffer (zeroed). Call instead of optimizer.zero_grad()."""
+        self.flat.zero_()
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def all_reduce_mean(self, async_op=False):
+        if not enabled():
+            return None
+        # a backward may have replaced .grad with a fresh tensor (set_to_none semantics); gather those back
+        for p, v in zip(self.params, self.views):
+            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+                p.grad = v
+        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
+        self.flat.mul_(1.0 / _state["world"])
+        return work
+
+
+def all_reduce_grads_mean(module):
+    """Simple (unbucketed-per-call) variant: average every parameter gradient across ranks."""
+    if not enabled():
+        return
+    grads = [p.grad for p in module.parameters() if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.mul_(1.0 / _state["world"])
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()

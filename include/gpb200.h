@@ -81,6 +81,81 @@ typedef struct {
 } gp_conv_wgrad_t;
 int gp_conv_wgrad(const gp_conv_wgrad_t* p, void* stream);
 
+/* ---- weight staging: fp32 torch-layout parameters -> bf16 GEMM operands (and gradients back).
+ * gp_pack_conv_weight: src (D0, D1, taps) fp32 [Conv2d: (Cout, Cin, kh*kw); ConvTranspose2d: (Cin, Cout, kh*kw)]
+ *   -> dst bf16 [N][tap][C] with (N, C) = (D0, D1) when n_dim == 0, (D1, D0) when n_dim == 1.
+ *   inv_scale (optional device scalar): every element is divided by it — the W / sigma of spectral norm
+ *   (torch:nn/utils/spectral_norm.py:112) fused into the staging pass.
+ * gp_unpack_conv_wgrad: fp32 [M][tap][N] -> fp32 (M, N, tap), i.e. the torch layout of the parameter gradient.
+ * gp_pack_matrix: dst[r][k] = src[map(r)*s_r + k*s_k] / inv_scale for r < R, k < K, zero padding up to [Rpad][ld_dst];
+ *   perm > 1 reorders rows from NCHW-flatten (c*perm + hw) to NHWC-flatten (hw*(R/perm) + c) order
+ *   (the view(B, C, 4, 4) after the generator's Linear, models/dcgan.py:50-51).
+ * gp_unpack_matrix: the inverse mapping for fp32 gradients. */
+int gp_pack_conv_weight(const float* src, void* dst, int D0, int D1, int taps, int n_dim, const float* inv_scale,
+                        void* stream);
+int gp_unpack_conv_wgrad(const float* src, float* dst, int M, int N, int taps, void* stream);
+int gp_pack_matrix(const float* src, void* dst, int R, int K, int Rpad, int ld_dst, long long s_r, long long s_k,
+                   int perm, const float* inv_scale, void* stream);
+int gp_unpack_matrix(const float* src, float* dst, int R, int K, int ld_src, long long s_r, long long s_k, int perm,
+                     void* stream);
+
+/* ---- BatchNorm2d in training mode with fused activation (replaces aten::native_batch_norm(+_backward) and the
+ * in-place ReLU / LeakyReLU that follow it: models/dcgan.py:37-39,107-109). x, y, out, da, dy: bf16 [P][C].
+ * gp_bn_stats     : sum[c] += sum_p x, sumsq[c] += sum_p x^2        (caller zeroes; all-reduce these for SyncBN)
+ * gp_bn_finalize  : mean, rstd (biased variance, eps), scale = gamma*rstd, shift = beta - mean*scale;
+ *                   running_mean/var (unbiased variance, momentum) and num_batches_tracked updated when non-NULL
+ * gp_bn_apply_act : out = act(y*scale + shift)
+ * gp_bn_bwd_reduce: sum_dz[c] += sum dz, sum_dzx[c] += sum dz*xhat with dz = da*act'(y*scale+shift)  (= dbeta, dgamma)
+ * gp_bn_bwd_apply : dy = scale * (dz - sum_dz/count - xhat*sum_dzx/count)
+ * gp_act_bwd      : dy = da * act'(.) given the activation OUTPUT a (layers without BatchNorm)
+ * gp_colsum       : out[c] += sum_p x[p][c]  (bias gradients) */
+int gp_bn_stats(const void* x, long long P, int C, float* sum, float* sumsq, void* stream);
+int gp_bn_finalize(const float* sum, const float* sumsq, double count, int C, float eps, float momentum,
+                   const float* gamma, const float* beta, float* mean, float* rstd, float* scale, float* shift,
+                   float* running_mean, float* running_var, long long* num_batches_tracked, void* stream);
+/* eval mode (module.eval()): mean/rstd/scale/shift from the running statistics */
+int gp_bn_eval_params(const float* running_mean, const float* running_var, const float* gamma, const float* beta, int C,
+                      float eps, float* mean, float* rstd, float* scale, float* shift, void* stream);
+int gp_bn_apply_act(const void* y, void* out, long long P, int C, const float* scale, const float* shift, int act,
+                    void* stream);
+int gp_bn_bwd_reduce(const void* da, const void* y, long long P, int C, const float* scale, const float* shift,
+                     const float* mean, const float* rstd, int act, float* sum_dz, float* sum_dzx, void* stream);
+int gp_bn_bwd_apply(const void* da, const void* y, void* dy, long long P, int C, const float* scale,
+                    const float* shift, const float* mean, const float* rstd, const float* sum_dz,
+                    const float* sum_dzx, double count, int act, void* stream);
+int gp_act_bwd(const void* da, const void* a, void* dy, long long n, int act, void* stream);
+int gp_colsum(const void* x, long long P, int C, float* out, void* stream);
+
+/* ---- the two image-side layers (Cin = img_dim of D's first Conv2d, models/dcgan.py:106; Cout = img_dim of G's last
+ * ConvTranspose2d + Tanh, models/dcgan.py:41-44) as im2col / col2im around a 1-tap tensor-core GEMM.
+ * col is bf16 [NB*(Hi/2)*(Wi/2)][64], column (c*4 + kh)*4 + kw, zero for columns >= ch*16; img is fp32 NCHW (NB, ch, Hi, Wi).
+ * gp_im2col_k4s2: col = im2col(img * (mul ? 1 - mul^2 : 1))   (mul = tanh output -> fused tanh')
+ * gp_col2im_k4s2: img = act(bias[c] + col2im(col)) */
+int gp_im2col_k4s2(const float* img, const float* mul, void* col, int NB, int ch, int Hi, int Wi, void* stream);
+int gp_col2im_k4s2(const void* col, const float* bias, float* img, int NB, int ch, int Hi, int Wi, int act,
+                   void* stream);
+/* dbias[c] += sum dout[n,c,:,:] * (mul ? 1 - mul^2 : 1); dbias fp32 [ch], caller-zeroed */
+int gp_image_bias_grad(const float* dout, const float* mul, float* dbias, int NB, int ch, int HW, void* stream);
+
+/* ---- discriminator heads: out[b][o] = bias[o] + sum_{hw,c} a[b,hw,c] * w[o*s_o + c*s_c + hw*s_hw]
+ * (global sum pooling + Linear, models/dcgan.py:121-122: s_hw = 0; flatten + Linear, models/dcgan_specnorm.py:125-126:
+ * s_c = HW, s_hw = 1; also the projection inner product of models/sngan_projection.py:193-195 with a gathered w).
+ * gp_head_bwd: da (bf16, may be NULL), dw (fp32, caller-zeroed, may be NULL), dbias (fp32 [O], may be NULL). */
+int gp_head_fwd(const void* a, const float* w, const float* bias, float* out, int NB, int HW, int C, int O,
+                long long s_o, long long s_c, long long s_hw, void* stream);
+int gp_head_bwd(const float* dout, const void* a, const float* w, void* da, float* dw, float* dbias, int NB, int HW,
+                int C, int O, long long s_o, long long s_c, long long s_hw, void* stream);
+
+/* ---- GANLoss (utils/criterion.py:30-41): mean loss and d(loss)/d(pred) in one pass.
+ * mode 0: BCE-with-logits vs constant `target`; 1: MSE vs `target`; 2: hinge, real: relu(1-p);
+ * 3: hinge, fake: relu(1+p); 4: generator hinge: -p. */
+#define GP_LOSS_BCE 0
+#define GP_LOSS_MSE 1
+#define GP_LOSS_HINGE_REAL 2
+#define GP_LOSS_HINGE_FAKE 3
+#define GP_LOSS_NEG_MEAN 4
+int gp_gan_loss(const float* pred, int n, int mode, float target, float* loss, float* dpred, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
