@@ -22,7 +22,7 @@ class ConvFwd(ctypes.Structure):
         ("col_sum", c_void_p), ("col_sumsq", c_void_p),
         ("NB", c_int), ("Hin", c_int), ("Win", c_int), ("Cin", c_int),
         ("Hout", c_int), ("Wout", c_int), ("Nout", c_int),
-        ("kind", c_int), ("act", c_int),
+        ("kind", c_int), ("act", c_int), ("residual", c_void_p),
     ]
 
 

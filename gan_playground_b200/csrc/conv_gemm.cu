@@ -84,22 +84,26 @@ static int pick_bn(int n) {
   return 64;
 }
 
-template <int MODE>
-static int launch(const ConvGemmParams& prm, int bn, int num_tiles, cudaStream_t st) {
-  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  if (grid <= 0) return GP_OK;
-#define GP_LAUNCH_BN(BNV)                                                                                        \
-  {                                                                                                              \
-    auto kfn = conv_gemm_kernel<MODE, BNV>;                                                                      \
-    GP_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BNV>::kSmemBytes)); \
-    kfn<<<grid, kNumThreads, GemmCfg<BNV>::kSmemBytes, st>>>(prm);                                               \
+template <int MODE, int BNV, int MTV>
+static int launch_cfg(const ConvGemmParams& prm, int grid, cudaStream_t st) {
+  auto kfn = conv_gemm_kernel<MODE, BNV, MTV>;
+  static bool attr_set = false;  // one flag per template instantiation
+  if (!attr_set) {
+    GP_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BNV, MTV>::kSmemBytes));
+    attr_set = true;
   }
-  if (bn == 256) GP_LAUNCH_BN(256)
-  else if (bn == 128) GP_LAUNCH_BN(128)
-  else GP_LAUNCH_BN(64)
-#undef GP_LAUNCH_BN
+  kfn<<<grid, kNumThreads, GemmCfg<BNV, MTV>::kSmemBytes, st>>>(prm);
   GP_CHECK_LAUNCH();
   return GP_OK;
+}
+
+template <int MODE>
+static int launch(const ConvGemmParams& prm, int bn, int mt, int num_tiles, cudaStream_t st) {
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  if (grid <= 0) return GP_OK;
+  if (bn == 256) return launch_cfg<MODE, 256, 1>(prm, grid, st);
+  if (bn == 128) return mt == 2 ? launch_cfg<MODE, 128, 2>(prm, grid, st) : launch_cfg<MODE, 128, 1>(prm, grid, st);
+  return mt == 2 ? launch_cfg<MODE, 64, 2>(prm, grid, st) : launch_cfg<MODE, 64, 1>(prm, grid, st);
 }
 
 }  // namespace gp
@@ -111,11 +115,23 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
   GP_REQUIRE(a->NB > 0 && a->Cin > 0 && a->Nout > 0, "gp_conv_fwd: empty problem");
   GP_REQUIRE(a->Cin % 8 == 0, "gp_conv_fwd: Cin=%d must be a multiple of 8 (16-byte TMA rows)", a->Cin);
   GP_REQUIRE(a->Nout % 8 == 0, "gp_conv_fwd: Nout=%d must be a multiple of 8", a->Nout);
+  GP_REQUIRE(a->act != GP_ACT_TANH, "gp_conv_fwd: tanh is fused in gp_col2im_k4s2, not in the GEMM epilogue");
+  GP_REQUIRE(a->col_sum == nullptr || a->Nout <= kMaxStatCols, "gp_conv_fwd: fused statistics support Nout <= %d", kMaxStatCols);
   ConvGemmParams prm;
   memset(&prm, 0, sizeof(prm));
   const int Cin = a->Cin;
   int ntaps_total = 0;
   int rc;
+  const int bn = pick_bn(a->Nout);
+  // narrow outputs: two M=128 sub-tiles share one B tile (MT = 2) when that still leaves >= one wave of tiles
+  int mt_sub = 1;
+  {
+    const long long small_px = (a->kind == GP_KIND_CONV_K4S2) ? (long long)a->NB * a->Hout * a->Wout
+                                                              : (long long)a->NB * a->Hin * a->Win;
+    const long long tiles2 = (small_px / (2 * kBlockM)) * ((a->Nout + bn - 1) / bn) * (a->kind == GP_KIND_CONVT_K4S2 ? 4 : 1);
+    if (bn <= 128 && tiles2 >= num_sms()) mt_sub = 2;
+  }
+  const int tile_px = mt_sub * kBlockM;
   const long long inW = Cin, inH = (long long)a->Win * Cin, inN = (long long)a->Hin * a->Win * Cin;
   switch (a->kind) {
     case GP_KIND_CONV_K4S2: {
@@ -124,7 +140,7 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
       prm.Ws = a->Wout;
       prm.n_phases = 1;
       prm.taps_per_phase = 16;
-      factor_tile(kBlockM, prm.Hs, prm.Ws, &prm.Nt, &prm.Ht, &prm.Wt);
+      factor_tile(tile_px, prm.Hs, prm.Ws, &prm.Nt, &prm.Ht, &prm.Wt);
       for (int r = 0; r < 2; ++r)
         for (int s = 0; s < 2; ++s) {
           const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(a->in) + ((long long)r * a->Win + s) * Cin;
@@ -154,7 +170,7 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
       prm.Ws = a->Win;
       prm.n_phases = 4;
       prm.taps_per_phase = 4;
-      factor_tile(kBlockM, prm.Hs, prm.Ws, &prm.Nt, &prm.Ht, &prm.Wt);
+      factor_tile(tile_px, prm.Hs, prm.Ws, &prm.Nt, &prm.Ht, &prm.Wt);
       rc = make_map_nhwc(&prm.map_g[0], a->in, Cin, a->Win, a->Hin, a->NB, inW, inH, inN, prm.Wt, prm.Ht, prm.Nt);
       if (rc) return rc;
       for (int i = 1; i < 4; ++i) prm.map_g[i] = prm.map_g[0];
@@ -186,7 +202,7 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
       prm.Ws = a->Win;
       prm.n_phases = 1;
       prm.taps_per_phase = k * k;
-      factor_tile(kBlockM, prm.Hs, prm.Ws, &prm.Nt, &prm.Ht, &prm.Wt);
+      factor_tile(tile_px, prm.Hs, prm.Ws, &prm.Nt, &prm.Ht, &prm.Wt);
       rc = make_map_nhwc(&prm.map_g[0], a->in, Cin, a->Win, a->Hin, a->NB, inW, inH, inN, prm.Wt, prm.Ht, prm.Nt);
       if (rc) return rc;
       for (int i = 1; i < 4; ++i) prm.map_g[i] = prm.map_g[0];
@@ -206,7 +222,6 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
     default:
       return set_error(GP_ERR_UNSUPPORTED, "gp_conv_fwd: unknown kind %d", a->kind);
   }
-  const int bn = pick_bn(a->Nout);
   const long long ktot = (long long)ntaps_total * Cin;  // packed row = every tap of the kernel window
   rc = make_map_2d(&prm.map_w, a->w, ktot, a->Nout, bn);
   if (rc) return rc;
@@ -215,14 +230,15 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
   prm.C = Cin;
   prm.N = a->Nout;
   prm.out = static_cast<__nv_bfloat16*>(a->out);
+  prm.residual = static_cast<const __nv_bfloat16*>(a->residual);
   prm.bias = a->bias;
-  prm.act = a->act;
+  prm.act_slope = a->act == GP_ACT_RELU ? 0.f : (a->act == GP_ACT_LRELU ? 0.2f : 1.f);
   prm.col_sum = a->col_sum;
   prm.col_sumsq = a->col_sumsq;
   GP_REQUIRE((a->col_sum == nullptr) == (a->col_sumsq == nullptr), "gp_conv_fwd: col_sum and col_sumsq go together");
   const int mtiles = ((a->NB + prm.Nt - 1) / prm.Nt) * (prm.Hs / prm.Ht) * (prm.Ws / prm.Wt);
   const int ntn = (a->Nout + bn - 1) / bn;
-  return launch<MODE_FWD>(prm, bn, prm.n_phases * mtiles * ntn, as_stream(stream));
+  return launch<MODE_FWD>(prm, bn, mt_sub, prm.n_phases * mtiles * ntn, as_stream(stream));
 }
 
 extern "C" int gp_conv_wgrad(const gp_conv_wgrad_t* a, void* stream) {
@@ -292,7 +308,8 @@ extern "C" int gp_conv_wgrad(const gp_conv_wgrad_t* a, void* stream) {
   prm.dw = a->dw;
   prm.ldw = ntaps * Cg;
   const int bn = pick_bn(Cg);
-  const int mtiles = (a->Cd + kBlockM - 1) / kBlockM;
+  const int mt_sub = (bn <= 128 && a->Cd >= 2 * kBlockM) ? 2 : 1;  // share the narrow gathered tile between two M=128 MMAs
+  const int mtiles = (a->Cd + mt_sub * kBlockM - 1) / (mt_sub * kBlockM);
   const int ntn = (Cg + bn - 1) / bn;
   const int base_tiles = mtiles * ntaps * ntn;
   prm.kblocks_total = ((a->NB + prm.Nt - 1) / prm.Nt) * (prm.Hs / prm.Ht) * (prm.Ws / prm.Wt);
@@ -305,5 +322,5 @@ extern "C" int gp_conv_wgrad(const gp_conv_wgrad_t* a, void* stream) {
   const int per = (prm.kblocks_total + splits - 1) / splits;
   splits = (prm.kblocks_total + per - 1) / per;
   prm.splits = splits;
-  return launch<MODE_WGRAD>(prm, bn, splits * base_tiles, as_stream(stream));
+  return launch<MODE_WGRAD>(prm, bn, mt_sub, splits * base_tiles, as_stream(stream));
 }

@@ -3,7 +3,7 @@
 // One persistent, warp-specialised kernel template covers every tensor-core contraction of the
 // DCGAN-family step (reference call sites: models/dcgan.py:36,106; models/sngan_projection.py:30-44):
 //
-//   MODE_FWD   out[pix, n] = act( sum_{tap, c} In[gather(pix, tap), c] * Wp[n, tap.koff + c] + bias[n] )
+//   MODE_FWD   out[pix, n] = act( sum_{tap, c} In[gather(pix, tap), c] * Wp[n, tap.koff + c] + bias[n] (+ residual) )
 //              - Conv2d k4s2p1 fprop  / ConvTranspose2d k4s2p1 dgrad : 16 taps, stride-2 gather expressed as
 //                four parity tensor maps (no elementStrides), zero padding = TMA out-of-bounds fill;
 //              - ConvTranspose2d k4s2p1 fprop / Conv2d k4s2p1 dgrad  : 4 output-parity phases x 4 taps, dense
@@ -12,9 +12,11 @@
 //   MODE_WGRAD dW[m, tap.koff + n] += sum_{pix} Dense[pix, m] * Gath[gather(pix, tap), n]
 //              both operands MN-major (channels contiguous in NHWC), split-K over pixels, fp32 atomics.
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer,
-// warps 2..5 = epilogue (tcgen05.ld -> bias/activation -> global). Two TMEM accumulator buffers so the
-// epilogue of tile i overlaps the MMAs of tile i+1.
+// Tile = (MT * 128) x BN: MT = 2 issues two M=128 MMAs per K step that share the B tile, which doubles the
+// arithmetic intensity of narrow (N <= 128) layers. Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM
+// allocator + single-thread tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld -> bias / residual / activation ->
+// global, optional per-channel BatchNorm statistics). Two TMEM accumulator buffers: the epilogue of tile i overlaps
+// the MMAs of tile i+1.
 #pragma once
 #include <cuda_bf16.h>
 #include "sm100_ptx.cuh"
@@ -24,14 +26,16 @@ namespace gp {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // one 128-byte swizzle row of bf16
 constexpr int kUmmaK = 16;
-constexpr int kMaxTaps = 16;
+constexpr int kMaxTaps = 48;
+constexpr int kMaxMaps = 8;
 constexpr int kNumThreads = 192;
+constexpr int kMaxStatCols = 2048;
 
 enum { MODE_FWD = 0, MODE_WGRAD = 1 };
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_TANH = 3 };
 
 struct Tap {
-  int8_t map;  // which gathered-operand tensor map (parity variant)
+  int8_t map;  // which gathered-operand tensor map (parity / hi-lo variant)
   int8_t dh;   // pixel offset on the small grid
   int8_t dw;
   int8_t pad;
@@ -39,22 +43,23 @@ struct Tap {
 };
 
 struct alignas(64) ConvGemmParams {
-  CUtensorMap map_g[4];  // gathered operand (FWD: A; WGRAD: B)
-  CUtensorMap map_d;     // WGRAD: dense operand (A)
-  CUtensorMap map_w;     // FWD: packed weights [N][Ktot] (B)
+  CUtensorMap map_g[kMaxMaps];  // gathered operand (FWD: A; WGRAD: B)
+  CUtensorMap map_d;            // WGRAD: dense operand (A)
+  CUtensorMap map_w;            // FWD: packed weights [N][Ktot] (B)
   Tap taps[kMaxTaps];
   int n_phases, taps_per_phase;
   int NB, Hs, Ws;  // small pixel grid
-  int Nt, Ht, Wt;  // pixel tile factors (product = 128 for FWD, 64 for WGRAD)
+  int Nt, Ht, Wt;  // pixel tile factors (product = MT*128 for FWD, 64 for WGRAD)
   int C;           // FWD: contraction channels per tap
   int N;           // FWD: output channels; WGRAD: channels of the gathered operand (dW columns per tap)
   int M;           // WGRAD: channels of the dense operand (dW rows)
   long long out_sN, out_sH, out_sW;  // FWD: output strides in elements for pixel (n, h, w) of the small grid
   long long phase_off[4];            // FWD: output element offset of each phase
   __nv_bfloat16* out;
+  const __nv_bfloat16* residual;  // optional, same indexing as out
   const float* bias;
-  int act;
-  float* dw;  // WGRAD: fp32 [M][ldw]
+  float act_slope;  // activation as max(v,0) + slope*min(v,0): 1 = identity, 0 = ReLU, 0.2 = LeakyReLU
+  float* dw;        // WGRAD: fp32 [M][ldw]
   int ldw;
   int splits;
   int kblocks_total;  // WGRAD: number of 64-pixel blocks
@@ -62,31 +67,45 @@ struct alignas(64) ConvGemmParams {
   float* col_sumsq;
 };
 
-template <int BN>
+template <int BN, int MT>
 struct GemmCfg {
-  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kABytes = MT * kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
-  static constexpr int kTmemCols = 2 * BN;  // 128 / 256 / 512: all powers of two >= 32
+  static constexpr int kStatBytes = 2 * kMaxStatCols * 4;
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual alignment slack
+  static constexpr int kBudget = 208 * 1024;  // operand ring; + statistics + barriers + alignment slack stays < 227 KB
+  static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
+  static constexpr int kAccCols = MT * BN;      // TMEM columns of one accumulator buffer
+  static constexpr int kTmemCols = 2 * kAccCols;  // 128 / 256 / 512: powers of two >= 32
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStatBytes + kBarBytes + 1024;  // +1024: alignment slack
+  static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM allocation must be a power of two <= 512");
+  static_assert(kStages >= 3, "pipeline too shallow");
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == ACT_RELU) return fmaxf(v, 0.f);
-  if (act == ACT_LRELU) return v > 0.f ? v : 0.2f * v;
-  if (act == ACT_TANH) return tanhf(v);
-  return v;
+// Column sums over the 32 lanes of a warp for 32 per-lane values: butterfly transpose-reduce, 31 shuffles.
+// On return lane l holds in v[0] the sum over lanes of the original v[l].
+__device__ __forceinline__ void warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = upper ? v[i] : v[i + n / 2];
+      const float keep = upper ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
 }
 
-template <int MODE, int BN>
+template <int MODE, int BN, int MT>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  float* s_stat = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStatBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -94,9 +113,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool do_stats = (MODE == MODE_FWD) && p.col_sum != nullptr;
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.map_g[i]);
+    tma_prefetch_desc(&p.map_g[0]);
     tma_prefetch_desc(MODE == MODE_FWD ? &p.map_w : &p.map_d);
     for (int i = 0; i < Cfg::kStages; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -111,6 +131,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   if (warp == 1) {
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
+  }
+  if (do_stats) {
+    for (int i = threadIdx.x; i < 2 * p.N; i += blockDim.x) s_stat[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -127,7 +150,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     ksteps_fwd = p.taps_per_phase * cchunks;
     num_tiles = p.n_phases * mtiles * ntiles_n;
   } else {
-    mtiles = (p.M + kBlockM - 1) / kBlockM;
+    mtiles = (p.M + MT * kBlockM - 1) / (MT * kBlockM);
     kb_per_split = (p.kblocks_total + p.splits - 1) / p.splits;
     num_tiles = p.splits * mtiles * p.taps_per_phase * ntiles_n;
   }
@@ -170,8 +193,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
 #pragma unroll
-          for (int i = 0; i < kBlockM / 64; ++i)
-            tma_load_4d(sa + i * 8192, &p.map_d, &full_bar[stage], mt * kBlockM + i * 64, w0, h0, n0);
+          for (int i = 0; i < MT * kBlockM / 64; ++i)
+            tma_load_4d(sa + i * 8192, &p.map_d, &full_bar[stage], mt * MT * kBlockM + i * 64, w0, h0, n0);
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j)
             tma_load_4d(sa + Cfg::kABytes + j * 8192, &p.map_g[t.map], &full_bar[stage], nt * BN + j * 64,
@@ -186,6 +209,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     // K-major: SBO = 8 rows * 128 B. MN-major: SBO = 8 K-rows * 128 B, LBO = 64 K-rows * 128 B (next 64-channel chunk).
     constexpr uint64_t dbase = (MODE == MODE_FWD) ? make_smem_desc_base(0, 1024) : make_smem_desc_base(8192, 1024);
     constexpr uint32_t kadv = (MODE == MODE_FWD) ? (kUmmaK * 2) : (kUmmaK * 128);  // bytes per UMMA_K step
+    constexpr uint32_t a_sub = kBlockM * kBlockK * 2;  // bytes between the MT sub-tiles of A (both modes: 16 KB)
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -202,7 +226,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       }
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
+      const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -210,8 +234,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const uint32_t b_addr = a_addr + Cfg::kABytes;
 #pragma unroll
         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-          umma_bf16(d_tmem, smem_desc(dbase, a_addr + k * kadv), smem_desc(dbase, b_addr + k * kadv), idesc,
-                    (ks | k) != 0);
+          const uint64_t bdesc = smem_desc(dbase, b_addr + k * kadv);
+#pragma unroll
+          for (int mi = 0; mi < MT; ++mi)
+            umma_bf16(d_tmem + mi * BN, smem_desc(dbase, a_addr + mi * a_sub + k * kadv), bdesc, idesc, (ks | k) != 0);
         }
         umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -221,70 +247,97 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   } else if (warp >= 2) {
     // =========================== epilogue (4 warps, one TMEM lane quarter each) ===========================
     const int q = warp & 3;  // warps 2,3,4,5 -> quarters 2,3,0,1
-    const int row = q * 32 + lane;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t tbase = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(q * 32) << 16);
       if constexpr (MODE == MODE_FWD) {
         const int nt = tile % ntiles_n;
         const int mt = (tile / ntiles_n) % mtiles;
         const int ph = tile / (ntiles_n * mtiles);
-        const int w = (mt % wtiles) * p.Wt + row % p.Wt;
-        const int h = ((mt / wtiles) % htiles) * p.Ht + (row / p.Wt) % p.Ht;
-        const int n = (mt / (wtiles * htiles)) * p.Nt + row / (p.Wt * p.Ht);
-        const bool row_ok = n < p.NB;
-        __nv_bfloat16* orow = p.out + p.phase_off[ph] + n * p.out_sN + h * p.out_sH + w * p.out_sW;
+        const int w_t0 = (mt % wtiles) * p.Wt, h_t0 = ((mt / wtiles) % htiles) * p.Ht;
+        const int n_t0 = (mt / (wtiles * htiles)) * p.Nt;
+        const float slope = p.act_slope;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          const int col0 = nt * BN + c * 32;
-          if (col0 >= p.N) break;  // warp-uniform
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c * 32, r);
-          tmem_ld_wait();
-          float v[32];
+        for (int mi = 0; mi < MT; ++mi) {
+          const int row = mi * kBlockM + q * 32 + lane;
+          const int w = w_t0 + row % p.Wt;
+          const int h = h_t0 + (row / p.Wt) % p.Ht;
+          const int n = n_t0 + row / (p.Wt * p.Ht);
+          const bool row_ok = n < p.NB;
+          const long long off = p.phase_off[ph] + n * p.out_sN + h * p.out_sH + w * p.out_sW;
+          __nv_bfloat16* orow = p.out + off;
+          const __nv_bfloat16* rrow = p.residual ? p.residual + off : nullptr;
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) {
+            const int col0 = nt * BN + c * 32;
+            if (col0 >= p.N) break;  // warp-uniform
+            uint32_t r[32];
+            tmem_ld_32x32(tbase + mi * BN + c * 32, r);
+            float v[32];
+            if (p.bias != nullptr) {
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            float b = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.f;
-            v[j] = __uint_as_float(r[j]) + b;
-          }
-          if (p.col_sum != nullptr) {
-            // per-channel sum / sum of squares of the fp32 pre-activation output over this warp's 32 rows
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float s = row_ok ? v[j] : 0.f;
-              float s2 = s * s;
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) {
-                s += __shfl_xor_sync(0xffffffffu, s, o);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+              for (int g = 0; g < 8; ++g) {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (col0 + g * 4 < p.N) b4 = __ldg(bp + g);
+                v[4 * g] = b4.x, v[4 * g + 1] = b4.y, v[4 * g + 2] = b4.z, v[4 * g + 3] = b4.w;
               }
-              if (lane == j && col0 + j < p.N) {
-                atomicAdd(p.col_sum + col0 + j, s);
-                atomicAdd(p.col_sumsq + col0 + j, s2);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
+            if (do_stats) {
+              // per-channel sum / sum of squares of the fp32 pre-activation output: 32 rows of this warp via a
+              // shuffle butterfly, then shared-memory accumulators per CTA (flushed once at kernel end)
+              float s1[32], s2[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                s1[j] = row_ok ? v[j] : 0.f;
+                s2[j] = s1[j] * s1[j];
+              }
+              warp_transpose_sum32(s1, lane);
+              warp_transpose_sum32(s2, lane);
+              if (col0 + lane < p.N) {
+                atomicAdd(&s_stat[col0 + lane], s1[0]);
+                atomicAdd(&s_stat[p.N + col0 + lane], s2[0]);
               }
             }
-          }
-          if (row_ok) {
-            if (col0 + 32 <= p.N) {
-              uint4* dst = reinterpret_cast<uint4*>(orow + col0);
+            if (rrow != nullptr && row_ok) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (col0 + g * 8 < p.N) {
+                  const uint4 rv = *reinterpret_cast<const uint4*>(rrow + col0 + g * 8);
+                  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(h2[e]);
+                    v[g * 8 + 2 * e] += f.x;
+                    v[g * 8 + 2 * e + 1] += f.y;
+                  }
+                }
+              }
+            }
+            if (row_ok) {
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 uint32_t w32[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  __nv_bfloat162 b2 = __floats2bfloat162_rn(apply_act(v[g * 8 + e * 2], p.act),
-                                                            apply_act(v[g * 8 + e * 2 + 1], p.act));
+                  const float a0 = v[g * 8 + 2 * e], a1 = v[g * 8 + 2 * e + 1];
+                  __nv_bfloat162 b2 = __floats2bfloat162_rn(fmaxf(a0, 0.f) + slope * fminf(a0, 0.f),
+                                                            fmaxf(a1, 0.f) + slope * fminf(a1, 0.f));
                   w32[e] = *reinterpret_cast<uint32_t*>(&b2);
                 }
-                dst[g] = make_uint4(w32[0], w32[1], w32[2], w32[3]);
+                if (col0 + g * 8 < p.N)
+                  *reinterpret_cast<uint4*>(orow + col0 + g * 8) = make_uint4(w32[0], w32[1], w32[2], w32[3]);
               }
-            } else {
-              for (int j = 0; j < 32 && col0 + j < p.N; ++j) orow[col0 + j] = __float2bfloat16(apply_act(v[j], p.act));
             }
           }
         }
@@ -292,20 +345,27 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const int nt = tile % ntiles_n;
         const int tp = (tile / ntiles_n) % p.taps_per_phase;
         const int mt = (tile / (ntiles_n * p.taps_per_phase)) % mtiles;
-        const int m = mt * kBlockM + row;
-        const bool row_ok = m < p.M;
-        float* drow = p.dw + static_cast<long long>(m) * p.ldw + p.taps[tp].koff;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          const int col0 = nt * BN + c * 32;
-          if (col0 >= p.N) break;
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c * 32, r);
-          tmem_ld_wait();
-          if (row_ok) {
+        for (int mi = 0; mi < MT; ++mi) {
+          const int m = (mt * MT + mi) * kBlockM + q * 32 + lane;
+          const bool row_ok = m < p.M;
+          float* drow = p.dw + static_cast<long long>(m) * p.ldw + p.taps[tp].koff;
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) {
+            const int col0 = nt * BN + c * 32;
+            if (col0 >= p.N) break;
+            uint32_t r[32];
+            tmem_ld_32x32(tbase + mi * BN + c * 32, r);
+            tmem_ld_wait();
+            if (row_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) atomicAdd(drow + col0 + j, __uint_as_float(r[j]));
+              for (int g = 0; g < 4; ++g) {
+                if (col0 + g * 8 < p.N) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) atomicAdd(drow + col0 + g * 8 + e, __uint_as_float(r[g * 8 + e]));
+                }
+              }
+            }
           }
         }
       }
@@ -316,6 +376,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
 
   tc_fence_before();
   __syncthreads();
+  if (do_stats) {
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+      atomicAdd(p.col_sum + i, s_stat[i]);
+      atomicAdd(p.col_sumsq + i, s_stat[p.N + i]);
+    }
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);

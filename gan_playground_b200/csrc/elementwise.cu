@@ -225,18 +225,30 @@ __global__ void bn_eval_kernel(const float* __restrict__ rm, const float* __rest
 }
 
 // out = act(y * scale[c] + shift[c])
-__global__ void bn_apply_act_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ out, long long n8,
-                                    int C, const float* __restrict__ scale, const float* __restrict__ shift, int act) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)((i * 8) % C);
+// Each thread owns one group of 8 channels (per-channel parameters live in registers) and strides over rows.
+__global__ void bn_apply_act_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ out, long long P,
+                                    int C, const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                    int rows_per_block) {
+  const ColLayout L = col_layout(C);
+  if (!L.active) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[L.g * 8 + j];
+    sh[j] = shift[L.g * 8 + j];
+  }
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > P) r1 = P;
+  for (long long r = r0 + L.rl; r < r1; r += L.lanes) {
     bf16x8 v;
-    v.load(y + i * 8);
+    v.load(y + r * C + L.g * 8);
     float f[8];
     v.unpack(f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = act_fwd(f[j] * __ldg(scale + c0 + j) + __ldg(shift + c0 + j), act);
+    for (int j = 0; j < 8; ++j) f[j] = act_fwd(f[j] * sc[j] + sh[j], act);
     v.pack(f);
-    v.store(out + i * 8);
+    v.store(out + r * C + L.g * 8);
   }
 }
 
@@ -288,25 +300,38 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const 
                                     const float* __restrict__ scale, const float* __restrict__ shift,
                                     const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const float* __restrict__ sum_dz, const float* __restrict__ sum_dzx,
-                                    float inv_count, int act) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)((i * 8) % C);
+                                    float inv_count, int act, int rows_per_block) {
+  const long long P = n8;  // rows
+  const ColLayout L = col_layout(C);
+  if (!L.active) return;
+  // dy = sc*dz - k0 - (y - mu) * k1   with k0 = sc*sum_dz/M, k1 = sc*rstd*sum_dzx/M
+  float sc[8], sh[8], mu[8], k0[8], k1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = L.g * 8 + j;
+    sc[j] = scale[c];
+    sh[j] = shift[c];
+    mu[j] = mean[c];
+    k0[j] = sc[j] * sum_dz[c] * inv_count;
+    k1[j] = sc[j] * rstd[c] * sum_dzx[c] * inv_count;
+  }
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > P) r1 = P;
+  for (long long r = r0 + L.rl; r < r1; r += L.lanes) {
     bf16x8 vy, vd;
-    vy.load(y + i * 8);
-    vd.load(da + i * 8);
+    vy.load(y + r * C + L.g * 8);
+    vd.load(da + r * C + L.g * 8);
     float fy[8], fd[8], o[8];
     vy.unpack(fy);
     vd.unpack(fd);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      const float sc = __ldg(scale + c);  // gamma * rstd
-      const float dz = fd[j] * act_grad(fy[j] * sc + __ldg(shift + c), act);
-      const float xhat = (fy[j] - __ldg(mean + c)) * __ldg(rstd + c);
-      o[j] = sc * (dz - __ldg(sum_dz + c) * inv_count - xhat * __ldg(sum_dzx + c) * inv_count);
+      const float dz = fd[j] * act_grad(fy[j] * sc[j] + sh[j], act);
+      o[j] = sc[j] * dz - k0[j] - (fy[j] - mu[j]) * k1[j];
     }
     vd.pack(o);
-    vd.store(dy + i * 8);
+    vd.store(dy + r * C + L.g * 8);
   }
 }
 
@@ -493,13 +518,15 @@ __global__ void head_bwd_weight_kernel(const float* __restrict__ dout, const __n
                                        long long s_o, long long s_c, long long s_hw) {
   const int o = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // index over HW*C
+  const int bchunk = (NB + gridDim.z - 1) / gridDim.z;
+  const int b0 = blockIdx.z * bchunk, b1 = min(b0 + bchunk, NB);
   if (i < HW * C) {
     const int c = i % C, hw = i / C;
     float acc = 0.f;
-    for (int b = 0; b < NB; ++b) acc += __ldg(dout + (long long)b * O + o) * __bfloat162float(a[((long long)b * HW) * C + i]);
+    for (int b = b0; b < b1; ++b) acc += __ldg(dout + (long long)b * O + o) * __bfloat162float(a[((long long)b * HW) * C + i]);
     atomicAdd(dw + o * s_o + c * s_c + hw * s_hw, acc);
   }
-  if (dbias != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+  if (dbias != nullptr && blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
     float s = 0.f;
     for (int b = 0; b < NB; ++b) s += dout[(long long)b * O + o];
     dbias[o] = s;
@@ -658,10 +685,10 @@ int gp_bn_eval_params(const float* running_mean, const float* running_var, const
 int gp_bn_apply_act(const void* y, void* out, long long P, int C, const float* scale, const float* shift, int act,
                     void* stream) {
   GP_REQUIRE(y && out && scale && shift && P > 0 && C % 8 == 0, "gp_bn_apply_act: bad arguments");
-  const long long n8 = P * C / 8;
-  bn_apply_act_kernel<<<grid_for(n8), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(y),
-                                                                    static_cast<__nv_bfloat16*>(out), n8, C, scale,
-                                                                    shift, act);
+  const ColLaunch L = col_launch(P, C, 0);
+  bn_apply_act_kernel<<<L.grid, L.block, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(y),
+                                                                 static_cast<__nv_bfloat16*>(out), P, C, scale, shift,
+                                                                 act, L.rpb);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -681,10 +708,10 @@ int gp_bn_bwd_apply(const void* da, const void* y, void* dy, long long P, int C,
                     const float* shift, const float* mean, const float* rstd, const float* sum_dz,
                     const float* sum_dzx, double count, int act, void* stream) {
   GP_REQUIRE(da && y && dy && P > 0 && C % 8 == 0 && count > 0, "gp_bn_bwd_apply: bad arguments");
-  const long long n8 = P * C / 8;
-  bn_bwd_apply_kernel<<<grid_for(n8), 256, 0, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(dy), n8,
-      C, scale, shift, mean, rstd, sum_dz, sum_dzx, (float)(1.0 / count), act);
+  const ColLaunch L = col_launch(P, C, 0);
+  bn_bwd_apply_kernel<<<L.grid, L.block, 0, as_stream(stream)>>>(
+      static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(dy), P, C,
+      scale, shift, mean, rstd, sum_dz, sum_dzx, (float)(1.0 / count), act, L.rpb);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -752,7 +779,11 @@ int gp_head_bwd(const float* dout, const void* a, const float* w, void* da, floa
     GP_CHECK_LAUNCH();
   }
   if (dw != nullptr) {
-    dim3 grid((HW * C + 255) / 256, O);
+    int zsplit = (4 * num_sms()) / (((HW * C + 255) / 256) * O);
+    if (zsplit < 1) zsplit = 1;
+    if (zsplit > 32) zsplit = 32;
+    if (zsplit > NB) zsplit = NB;
+    dim3 grid((HW * C + 255) / 256, O, zsplit);
     head_bwd_weight_kernel<<<grid, 256, 0, as_stream(stream)>>>(dout, static_cast<const __nv_bfloat16*>(a), dw, dbias, NB,
                                                                 HW, C, O, s_o, s_c, s_hw);
     GP_CHECK_LAUNCH();

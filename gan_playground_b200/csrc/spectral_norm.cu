@@ -1,0 +1,175 @@
+// Spectral normalisation (torch.nn.utils.spectral_norm, torch:nn/utils/spectral_norm.py:62-114) as GEMV kernels.
+// The weight is used in place, in torch's layout [A][B][T] (fp32):
+//   dim == 0 (Conv2d / Linear / Embedding): W_mat[r = a][c = b*T + t]
+//   dim == 1 (ConvTranspose2d)            : W_mat[r = b][c = a*T + t]
+// One power iteration:  v <- normalize(W^T u);  u <- normalize(W v);  sigma = u . (W v)  (= ||W v|| after the update).
+// HBM-bound: W is read twice per forward (once per GEMV) plus once for the W / sigma staging.
+#include "common.h"
+
+namespace gp {
+
+struct SnLayout {
+  int A, B, T, dim;
+  __device__ __host__ int rows() const { return dim == 0 ? A : B; }
+  __device__ __host__ int cols() const { return dim == 0 ? B * T : A * T; }
+  __device__ __forceinline__ long long addr(int r, int c) const {
+    if (dim == 0) return (long long)r * (B * T) + c;
+    return ((long long)(c / T) * B + r) * T + (c % T);
+  }
+};
+
+__device__ __forceinline__ float block_sum(float v) {
+  __shared__ float red[32];
+  for (int k = 16; k > 0; k >>= 1) v += __shfl_xor_sync(0xffffffffu, v, k);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+  if (threadIdx.x < 32)
+    for (int k = 16; k > 0; k >>= 1) t += __shfl_xor_sync(0xffffffffu, t, k);
+  if (threadIdx.x == 0) red[0] = t;
+  __syncthreads();
+  t = red[0];
+  __syncthreads();
+  return t;
+}
+
+// t1[c] += sum_{r in chunk} W[r][c] * u[r]      grid: (ceil(cols/256), row chunks)
+__global__ void sn_gemv_t_kernel(const float* __restrict__ w, SnLayout L, const float* __restrict__ u,
+                                 float* __restrict__ t1, int rows_per_block) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= L.cols()) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(r0 + rows_per_block, L.rows());
+  float acc = 0.f;
+  for (int r = r0; r < r1; ++r) acc += __ldg(w + L.addr(r, c)) * __ldg(u + r);
+  atomicAdd(t1 + c, acc);
+}
+
+// t2[r] = sum_c W[r][c] * v[c]      grid: rows
+__global__ void sn_gemv_kernel(const float* __restrict__ w, SnLayout L, const float* __restrict__ v,
+                               float* __restrict__ t2) {
+  const int r = blockIdx.x;
+  float acc = 0.f;
+  for (int c = threadIdx.x; c < L.cols(); c += blockDim.x) acc += __ldg(w + L.addr(r, c)) * __ldg(v + c);
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) t2[r] = acc;
+}
+
+// out[i] = t[i] / max(||t||, eps); sigma (optional) = sum t^2 / max(||t||, eps)      single block
+__global__ void sn_normalize_kernel(const float* __restrict__ t, int n, float eps, float* __restrict__ out,
+                                    float* __restrict__ sigma) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += t[i] * t[i];
+  acc = block_sum(acc);
+  const float nrm = fmaxf(sqrtf(acc), eps);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = t[i] / nrm;
+  if (sigma != nullptr && threadIdx.x == 0) *sigma = acc / nrm;
+}
+
+// eval mode: sigma = u . t2      single block
+__global__ void sn_dot_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, float* __restrict__ out) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += a[i] * b[i];
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) *out = acc;
+}
+
+// out = w / sigma
+__global__ void sn_scale_kernel(const float* __restrict__ w, const float* __restrict__ sigma, float* __restrict__ out,
+                                long long n) {
+  const float inv = 1.f / __ldg(sigma);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = w[i] * inv;
+}
+
+// dot += sum g * w_sn
+__global__ void sn_grad_dot_kernel(const float* __restrict__ g, const float* __restrict__ wsn, long long n,
+                                   float* __restrict__ dot) {
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc += g[i] * wsn[i];
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) atomicAdd(dot, acc);
+}
+
+// dW_orig[e] = (g[e] - dot * u[r(e)] * v[c(e)]) / sigma      (gradient through W / sigma with u, v constant)
+__global__ void sn_grad_kernel(const float* __restrict__ g, SnLayout L, const float* __restrict__ u,
+                               const float* __restrict__ v, const float* __restrict__ sigma,
+                               const float* __restrict__ dot, float* __restrict__ out) {
+  const long long n = (long long)L.A * L.B * L.T;
+  const float inv = 1.f / __ldg(sigma), d = __ldg(dot);
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(e % L.T), b = (int)((e / L.T) % L.B), a = (int)(e / ((long long)L.T * L.B));
+    const int r = L.dim == 0 ? a : b;
+    const int c = L.dim == 0 ? b * L.T + t : a * L.T + t;
+    out[e] = (g[e] - d * __ldg(u + r) * __ldg(v + c)) * inv;
+  }
+}
+
+static inline int grid1d(long long n, int block = 256) {
+  long long g = (n + block - 1) / block;
+  const long long cap = (long long)num_sms() * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace gp
+
+using namespace gp;
+
+extern "C" {
+
+// scratch: fp32 [rows + cols] (t2 then t1). training != 0: u, v are updated in place (one power iteration).
+int gp_sn_sigma(const float* w, int A, int B, int T, int dim, float* u, float* v, float eps, int training,
+                float* scratch, float* sigma, void* stream) {
+  GP_REQUIRE(w && u && v && scratch && sigma && A > 0 && B > 0 && T > 0 && (dim == 0 || dim == 1), "gp_sn_sigma: bad arguments");
+  SnLayout L{A, B, T, dim};
+  const int R = L.rows(), Cc = L.cols();
+  float* t2 = scratch;
+  float* t1 = scratch + R;
+  cudaStream_t st = as_stream(stream);
+  if (training) {
+    GP_CHECK_CUDA(cudaMemsetAsync(t1, 0, sizeof(float) * Cc, st));
+    const int rpb = R > 64 ? 64 : R;
+    dim3 grid((Cc + 255) / 256, (R + rpb - 1) / rpb);
+    sn_gemv_t_kernel<<<grid, 256, 0, st>>>(w, L, u, t1, rpb);
+    GP_CHECK_LAUNCH();
+    sn_normalize_kernel<<<1, 1024, 0, st>>>(t1, Cc, eps, v, nullptr);
+    GP_CHECK_LAUNCH();
+    sn_gemv_kernel<<<R, 256, 0, st>>>(w, L, v, t2);
+    GP_CHECK_LAUNCH();
+    sn_normalize_kernel<<<1, 1024, 0, st>>>(t2, R, eps, u, sigma);
+    GP_CHECK_LAUNCH();
+  } else {
+    sn_gemv_kernel<<<R, 256, 0, st>>>(w, L, v, t2);
+    GP_CHECK_LAUNCH();
+    sn_dot_kernel<<<1, 1024, 0, st>>>(u, t2, R, sigma);
+    GP_CHECK_LAUNCH();
+  }
+  return GP_OK;
+}
+
+int gp_sn_scale(const float* w, const float* sigma, float* out, long long n, void* stream) {
+  GP_REQUIRE(w && sigma && out && n > 0, "gp_sn_scale: bad arguments");
+  sn_scale_kernel<<<grid1d(n), 256, 0, as_stream(stream)>>>(w, sigma, out, n);
+  GP_CHECK_LAUNCH();
+  return GP_OK;
+}
+
+// dot: fp32 scalar scratch. out = (g - <g, w_sn> u v^T) / sigma in the layout of w.
+int gp_sn_grad(const float* g, const float* w_sn, int A, int B, int T, int dim, const float* u, const float* v,
+               const float* sigma, float* dot, float* out, void* stream) {
+  GP_REQUIRE(g && w_sn && u && v && sigma && dot && out, "gp_sn_grad: bad arguments");
+  SnLayout L{A, B, T, dim};
+  const long long n = (long long)A * B * T;
+  cudaStream_t st = as_stream(stream);
+  GP_CHECK_CUDA(cudaMemsetAsync(dot, 0, sizeof(float), st));
+  sn_grad_dot_kernel<<<grid1d(n), 256, 0, st>>>(g, w_sn, n, dot);
+  GP_CHECK_LAUNCH();
+  sn_grad_kernel<<<grid1d(n), 256, 0, st>>>(g, L, u, v, sigma, dot, out);
+  GP_CHECK_LAUNCH();
+  return GP_OK;
+}
+
+}  // extern "C"

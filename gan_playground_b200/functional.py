@@ -141,7 +141,7 @@ class LinearToNHWC(torch.autograd.Function):
         wp = cache.get((key, "fwd"), weight, lambda: ops.pack_matrix(weight.detach(), O, K, O, Kp, K, 1, perm=HW))
         # bias in NHWC-flatten order: dst[(s % HW)*C + s // HW] = bias[s]
         bp = cache.get((key, "bias"), bias, lambda: ops.unpack_matrix(bias.detach(), (O,), O, 1, 1, 1, 1, perm=C))
-        a = ops.conv_fwd(zb.view(B, 1, 1, Kp), wp, bp, ops.KIND_CONV_K1S1, 1, 1, act)
+        a = ops.conv_fwd(zb.view(B, 1, 1, Kp), wp, bp, ops.KIND_CONV_K1S1, 1, 1, act, flops=2.0 * B * O * K)
         ctx.save_for_backward(zb, a, weight)
         ctx.dims = (B, K, O, HW, C, Kp, act)
         return a.view(B, bw, bw, C)
@@ -154,7 +154,7 @@ class LinearToNHWC(torch.autograd.Function):
         dy = ops.act_bwd(da, a, act) if act != ops.ACT_NONE else da
         dweight = dbias = None
         if ctx.needs_input_grad[1]:
-            dwp = ops.conv_wgrad(dy, zb.view(B, 1, 1, Kp), ops.KIND_CONV_K1S1, 1)  # [O][1][Kp], rows in NHWC order
+            dwp = ops.conv_wgrad(dy, zb.view(B, 1, 1, Kp), ops.KIND_CONV_K1S1, 1, flops=2.0 * B * O * K)  # [O][1][Kp]
             dweight = ops.unpack_matrix(dwp.view(O, Kp), weight.shape, O, K, Kp, K, 1, perm=HW)
         if ctx.needs_input_grad[2]:
             db = ops.colsum(dy)
@@ -176,7 +176,8 @@ class ImageConv(torch.autograd.Function):
         col = ops.im2col_k4s2(x.detach())
         wp = cache.get((key, "fwd"), weight,
                        lambda: ops.pack_matrix(weight.detach(), Cout, ch * 16, Cout, 64, ch * 16, 1))
-        a = ops.conv_fwd(col, wp, bias.detach(), ops.KIND_CONV_K1S1, H // 2, W // 2, act)
+        a = ops.conv_fwd(col, wp, bias.detach(), ops.KIND_CONV_K1S1, H // 2, W // 2, act,
+                         flops=2.0 * NB * (H // 2) * (W // 2) * Cout * ch * 16)
         ctx.save_for_backward(x, weight, a)
         ctx.misc = (act, cache, key)
         return a
@@ -191,7 +192,8 @@ class ImageConv(torch.autograd.Function):
         dweight = dbias = dx = None
         if ctx.needs_input_grad[1]:
             col = ops.im2col_k4s2(x)
-            dwp = ops.conv_wgrad(dy, col, ops.KIND_CONV_K1S1, 1)  # [Cout][1][64]
+            dwp = ops.conv_wgrad(dy, col, ops.KIND_CONV_K1S1, 1,
+                                 flops=2.0 * NB * (H // 2) * (W // 2) * Cout * ch * 16)  # [Cout][1][64]
             dweight = ops.unpack_matrix(dwp.view(Cout, 64), weight.shape, Cout, ch * 16, 64, ch * 16, 1)
         if ctx.needs_input_grad[2]:
             dbias = ops.colsum(dy)
@@ -199,7 +201,8 @@ class ImageConv(torch.autograd.Function):
             # dcol[px][j] = sum_o dy[px][o] * W[o][j]  -> weights [64][Cout] = W^T (rows j >= ch*16 are zero)
             wpt = cache.get((key, "dgrad"), weight,
                             lambda: ops.pack_matrix(weight.detach(), ch * 16, Cout, 64, Cout, 1, ch * 16))
-            dcol = ops.conv_fwd(dy, wpt, None, ops.KIND_CONV_K1S1, H // 2, W // 2)
+            dcol = ops.conv_fwd(dy, wpt, None, ops.KIND_CONV_K1S1, H // 2, W // 2,
+                               flops=2.0 * NB * (H // 2) * (W // 2) * Cout * ch * 16)
             dx = ops.col2im_k4s2(dcol, None, ch, ops.ACT_NONE)
         return dx, dweight, dbias, None, None, None
 
@@ -214,7 +217,7 @@ class ImageConvT(torch.autograd.Function):
         ch = weight.shape[1]
         wp = cache.get((key, "fwd"), weight,
                        lambda: ops.pack_matrix(weight.detach(), ch * 16, Cin, 64, Cin, 1, ch * 16))
-        ycol = ops.conv_fwd(x, wp, None, ops.KIND_CONV_K1S1, H, W)
+        ycol = ops.conv_fwd(x, wp, None, ops.KIND_CONV_K1S1, H, W, flops=2.0 * NB * H * W * Cin * ch * 16)
         out = ops.col2im_k4s2(ycol, bias.detach(), ch, act)
         ctx.save_for_backward(x, weight, out)
         ctx.misc = (act, cache, key)
@@ -231,14 +234,14 @@ class ImageConvT(torch.autograd.Function):
         dcol = ops.im2col_k4s2(dout, out if act == ops.ACT_TANH else None)
         dweight = dbias = dx = None
         if ctx.needs_input_grad[1]:
-            dwp = ops.conv_wgrad(x, dcol, ops.KIND_CONV_K1S1, 1)  # [Cin][1][64]
+            dwp = ops.conv_wgrad(x, dcol, ops.KIND_CONV_K1S1, 1, flops=2.0 * NB * H * W * Cin * ch * 16)  # [Cin][1][64]
             dweight = ops.unpack_matrix(dwp.view(Cin, 64), weight.shape, Cin, ch * 16, 64, ch * 16, 1)
         if ctx.needs_input_grad[2]:
             dbias = ops.image_bias_grad(dout, out if act == ops.ACT_TANH else None)
         if ctx.needs_input_grad[0]:
             wpd = cache.get((key, "dgrad"), weight,
                             lambda: ops.pack_matrix(weight.detach(), Cin, ch * 16, Cin, 64, ch * 16, 1))
-            dx = ops.conv_fwd(dcol, wpd, None, ops.KIND_CONV_K1S1, H, W)
+            dx = ops.conv_fwd(dcol, wpd, None, ops.KIND_CONV_K1S1, H, W, flops=2.0 * NB * H * W * Cin * ch * 16)
         return dx, dweight, dbias, None, None, None
 
 
@@ -278,3 +281,23 @@ class GanLossFn(torch.autograd.Function):
     def backward(ctx, g):
         (dpred,) = ctx.saved_tensors
         return dpred * g, None, None
+
+
+class SpectralNormFn(torch.autograd.Function):
+    """weight_orig -> weight_orig / sigma with one in-place power iteration on (u, v) per training forward
+    (torch:nn/utils/spectral_norm.py:92-114). dim = 0 for Conv2d / Linear / Embedding, 1 for ConvTranspose2d.
+    Backward differentiates through sigma with u, v constant: dW = (G - <G, W_sn> u v^T) / sigma."""
+
+    @staticmethod
+    def forward(ctx, weight_orig, u, v, dim, training):
+        w = weight_orig.detach().contiguous()
+        sigma = ops.sn_sigma(w, u, v, dim, training)
+        w_sn = ops.sn_scale(w, sigma)
+        ctx.save_for_backward(w_sn, u.clone(), v.clone(), sigma)   # clones: later forwards update u, v in place
+        ctx.dim = dim
+        return w_sn
+
+    @staticmethod
+    def backward(ctx, g):
+        w_sn, u, v, sigma = ctx.saved_tensors
+        return ops.sn_grad(g.contiguous(), w_sn, ctx.dim, u, v, sigma), None, None, None, None

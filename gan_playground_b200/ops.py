@@ -34,6 +34,9 @@ _SIGS = {
     "gp_head_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _vp],
     "gp_head_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _vp],
     "gp_gan_loss": [_vp, _i, _i, _f, _vp, _vp, _vp],
+    "gp_sn_sigma": [_vp, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _vp],
+    "gp_sn_scale": [_vp, _vp, _vp, _ll, _vp],
+    "gp_sn_grad": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
 }
 _bound = {}
 
@@ -71,9 +74,52 @@ def _chk(t, dtype, name):
 
 
 # ------------------------------------------------------------------------------------------------ conv GEMMs
-def conv_fwd(x, wp, bias, kind, Hout, Wout, act=ACT_NONE, stats=None):
+class GemmProfiler:
+    """Times every tensor-core GEMM launch (gp::conv_gemm_kernel) with CUDA events on the launching stream and
+    accumulates its ALGORITHMIC FLOPs — bench.py's roofline numbers come from here (measured live, no profiler)."""
+
+    active = None
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        GemmProfiler.active = self
+        return self
+
+    def __exit__(self, *exc):
+        GemmProfiler.active = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b, _, _ in self.records)
+        fl = sum(f for _, _, f, _ in self.records)
+        return {"ms": ms, "flops": fl, "tflops": fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0, "launches": len(self.records)}
+
+    def per_launch(self):
+        torch.cuda.synchronize()
+        return [(name, a.elapsed_time(b), f) for a, b, f, name in self.records]
+
+
+def _timed(name, flops, fn):
+    prof = GemmProfiler.active
+    if prof is None:
+        return fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    r = fn()
+    b.record()
+    prof.records.append((a, b, flops, name))
+    return r
+
+
+_TAPS_PER_OUT = {KIND_CONV_K4S2: 16, KIND_CONVT_K4S2: 4, KIND_CONV_K3S1: 9, KIND_CONV_K1S1: 1}
+
+
+def conv_fwd(x, wp, bias, kind, Hout, Wout, act=ACT_NONE, stats=None, flops=None, residual=None):
     """x: bf16 (NB, Hin, Win, Cin); wp: bf16 [Nout, taps*Cin]; returns bf16 (NB, Hout, Wout, Nout).
-    stats: optional fp32 [2, Nout] zeroed tensor receiving per-channel sum / sum of squares."""
+    stats: optional fp32 [2, Nout] zeroed tensor receiving per-channel sum / sum of squares.
+    flops: algorithmic FLOPs of this call when they differ from the padded GEMM shape (image layers)."""
     _chk(x, torch.bfloat16, "x")
     _chk(wp, torch.bfloat16, "wp")
     NB, Hin, Win, Cin = x.shape
@@ -82,12 +128,15 @@ def conv_fwd(x, wp, bias, kind, Hout, Wout, act=ACT_NONE, stats=None):
     if bias is not None:
         _chk(bias, torch.float32, "bias")
     p = ConvFwd(_p(x), _p(wp), _p(bias), _p(out), _p(stats[0]) if stats is not None else None,
-                _p(stats[1]) if stats is not None else None, NB, Hin, Win, Cin, Hout, Wout, Nout, kind, act)
-    check(_fn("gp_conv_fwd")(ctypes.addressof(p), _stream()), "gp_conv_fwd")
+                _p(stats[1]) if stats is not None else None, NB, Hin, Win, Cin, Hout, Wout, Nout, kind, act, _p(residual))
+    if flops is None:
+        flops = 2.0 * NB * Hout * Wout * Nout * Cin * _TAPS_PER_OUT[kind]
+    _timed("conv_fwd kind%d %dx%dx%d C%d->%d" % (kind, NB, Hout, Wout, Cin, Nout), flops,
+           lambda: check(_fn("gp_conv_fwd")(ctypes.addressof(p), _stream()), "gp_conv_fwd"))
     return out
 
 
-def conv_wgrad(dense, gath, kind, taps):
+def conv_wgrad(dense, gath, kind, taps, flops=None):
     """dense: bf16 (NB, Hs, Ws, Cd); gath: bf16 (NB, Hg, Wg, Cg); returns fp32 [Cd, taps, Cg]."""
     _chk(dense, torch.bfloat16, "dense")
     _chk(gath, torch.bfloat16, "gath")
@@ -95,7 +144,10 @@ def conv_wgrad(dense, gath, kind, taps):
     _, Hg, Wg, Cg = gath.shape
     dw = torch.zeros((Cd, taps, Cg), device=dense.device, dtype=torch.float32)
     p = ConvWgrad(_p(dense), _p(gath), _p(dw), NB, Hs, Ws, Cd, Hg, Wg, Cg, kind)
-    check(_fn("gp_conv_wgrad")(ctypes.addressof(p), _stream()), "gp_conv_wgrad")
+    if flops is None:
+        flops = 2.0 * NB * Hs * Ws * Cd * Cg * taps
+    _timed("conv_wgrad kind%d %dx%dx%d Cd%d Cg%d" % (kind, NB, Hs, Ws, Cd, Cg), flops,
+           lambda: check(_fn("gp_conv_wgrad")(ctypes.addressof(p), _stream()), "gp_conv_wgrad"))
     return dw
 
 
@@ -265,3 +317,38 @@ def gan_loss(pred, mode, target):
     dpred = torch.empty_like(pred)
     check(_fn("gp_gan_loss")(_p(pred), pred.numel(), mode, float(target), _p(loss), _p(dpred), _stream()), "gp_gan_loss")
     return loss, dpred
+
+
+# ------------------------------------------------------------------------------------------------ spectral norm
+def _sn_dims(w):
+    A, B = w.shape[0], (w.shape[1] if w.dim() > 1 else 1)
+    T = w.numel() // (A * B)
+    return A, B, T
+
+
+def sn_sigma(w, u, v, dim, training, eps=1e-12):
+    """One power iteration (in place on u, v when training) and sigma; returns the fp32 scalar tensor sigma."""
+    _chk(w, torch.float32, "w")
+    _chk(u, torch.float32, "u")
+    _chk(v, torch.float32, "v")
+    A, B, T = _sn_dims(w)
+    scratch = torch.empty((u.numel() + v.numel(),), device=w.device, dtype=torch.float32)
+    sigma = torch.empty((), device=w.device, dtype=torch.float32)
+    check(_fn("gp_sn_sigma")(_p(w), A, B, T, dim, _p(u), _p(v), eps, 1 if training else 0, _p(scratch), _p(sigma), _stream()),
+          "gp_sn_sigma")
+    return sigma
+
+
+def sn_scale(w, sigma):
+    out = torch.empty_like(w)
+    check(_fn("gp_sn_scale")(_p(w), _p(sigma), _p(out), w.numel(), _stream()), "gp_sn_scale")
+    return out
+
+
+def sn_grad(g, w_sn, dim, u, v, sigma):
+    _chk(g, torch.float32, "g")
+    A, B, T = _sn_dims(w_sn)
+    dot = torch.empty((), device=g.device, dtype=torch.float32)
+    out = torch.empty_like(w_sn)
+    check(_fn("gp_sn_grad")(_p(g), _p(w_sn), A, B, T, dim, _p(u), _p(v), _p(sigma), _p(dot), _p(out), _stream()), "gp_sn_grad")
+    return out

@@ -61,7 +61,9 @@ typedef struct {
   int32_t NB, Hin, Win, Cin;
   int32_t Hout, Wout, Nout;
   int32_t kind;
-  int32_t act;
+  int32_t act;            /* GP_ACT_NONE / RELU / LRELU (tanh lives in gp_col2im_k4s2) */
+  const void* residual;   /* optional bf16 tensor with the layout of `out`, added before the activation
+                             (residual blocks of models/sngan_projection.py:66,136); NULL = none */
 } gp_conv_fwd_t;
 int gp_conv_fwd(const gp_conv_fwd_t* p, void* stream);
 
@@ -155,6 +157,21 @@ int gp_head_bwd(const float* dout, const void* a, const float* w, void* da, floa
 #define GP_LOSS_HINGE_FAKE 3
 #define GP_LOSS_NEG_MEAN 4
 int gp_gan_loss(const float* pred, int n, int mode, float target, float* loss, float* dpred, void* stream);
+
+/* ---- spectral normalisation (torch.nn.utils.spectral_norm's pre-forward hook, torch:nn/utils/spectral_norm.py:62-114,
+ * applied at models/dcgan_specnorm.py:37,42,107 and models/sngan_projection.py:110-181) as GEMV kernels.
+ * w: fp32 parameter in torch's layout viewed as [A][B][T]; dim == 0: W_mat[a][b*T+t] (Conv2d/Linear/Embedding),
+ * dim == 1: W_mat[b][a*T+t] (ConvTranspose2d). u: fp32 [rows], v: fp32 [cols].
+ * gp_sn_sigma : training != 0 -> one power iteration in place (v = normalize(W^T u), u = normalize(W v), eps clamp),
+ *               then sigma = u.(W v); training == 0 -> sigma from the stored u, v. scratch: fp32 [rows + cols].
+ * gp_sn_scale : out = w / sigma (the normalised weight handed to the conv / linear kernels)
+ * gp_sn_grad  : gradient through W / sigma with u, v held constant:
+ *               out = (g - <g, w_sn> * u v^T) / sigma, in w's layout; dot: fp32 scalar scratch. */
+int gp_sn_sigma(const float* w, int A, int B, int T, int dim, float* u, float* v, float eps, int training,
+                float* scratch, float* sigma, void* stream);
+int gp_sn_scale(const float* w, const float* sigma, float* out, long long n, void* stream);
+int gp_sn_grad(const float* g, const float* w_sn, int A, int B, int T, int dim, const float* u, const float* v,
+               const float* sigma, float* dot, float* out, void* stream);
 
 #ifdef __cplusplus
 }

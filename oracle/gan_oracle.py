@@ -281,3 +281,80 @@ def dcgan_step_grads(sd_g, sd_d, x_real, z1, z2, labels=(0.9, 0.1, 0.9), mode="v
 def step_flops_dcgan64(batch):
     """Minimal algorithmic FLOPs of one DCGAN-64 step: 9.7994 GFLOP per image."""
     return 9.7994e9 * batch
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU training loop of the reference (used by bench.py's cpu_baseline / --impl reference legs and by trace tests)
+# --------------------------------------------------------------------------------------------------------------
+
+
+def init_dcgan_state(seed=0, ngf=64, ndf=64, res=64, z_dim=100, img_dim=3, bottom_width=4):
+    """Fresh reference-layout state dicts with the reference's 'N02' initialisation (models/dcgan.py:61-69,128-136):
+    N(0, 0.02) on ConvT/Conv/Linear weights, torch defaults (here: zeros) for biases, BN weight 1 / bias 0.
+    (Biases use zeros instead of torch's uniform default: irrelevant for timing, and tests load explicit weights.)"""
+    g = torch.Generator().manual_seed(seed)
+
+    def n02(*shape):
+        return torch.randn(*shape, generator=g) * 0.02
+
+    ga, da = g_arch(ngf)[res], d_arch(ndf, img_dim)[res]
+    sd_g = {"linear.weight": n02(ga["in_channels"][0] * bottom_width ** 2, z_dim),
+            "linear.bias": torch.zeros(ga["in_channels"][0] * bottom_width ** 2)}
+    for i, (ci, co) in enumerate(zip(ga["in_channels"], ga["out_channels"])):
+        p = "blocks.%d." % i
+        sd_g.update({p + "0.weight": n02(ci, co, 4, 4), p + "0.bias": torch.zeros(co), p + "1.weight": torch.ones(co),
+                     p + "1.bias": torch.zeros(co), p + "1.running_mean": torch.zeros(co),
+                     p + "1.running_var": torch.ones(co), p + "1.num_batches_tracked": torch.tensor(0)})
+    sd_g.update({"out_layer.0.weight": n02(ga["out_channels"][-1], img_dim, 4, 4), "out_layer.0.bias": torch.zeros(img_dim)})
+    sd_d = {}
+    for i, (ci, co) in enumerate(zip(da["in_channels"], da["out_channels"])):
+        p = "blocks.%d." % i
+        sd_d.update({p + "0.weight": n02(co, ci, 4, 4), p + "0.bias": torch.zeros(co)})
+        if i != 0:
+            sd_d.update({p + "1.weight": torch.ones(co), p + "1.bias": torch.zeros(co), p + "1.running_mean": torch.zeros(co),
+                         p + "1.running_var": torch.ones(co), p + "1.num_batches_tracked": torch.tensor(0)})
+    sd_d.update({"out_layer.weight": n02(1, da["out_channels"][-1]), "out_layer.bias": torch.zeros(1)})
+    return sd_g, sd_d
+
+
+class CpuDcganTrainer:
+    """The loop body of main_dcgan.py:68-95 on the CPU in fp32: Adam(lr 4e-4 / 1e-4, betas (0.5, 0.999)) (:55-56),
+    GANLoss('vanilla', 0.9, 0.1, 0.9) (:58), D-real / D-fake backward accumulate, G step through D."""
+
+    def __init__(self, sd_g, sd_d, labels=(0.9, 0.1, 0.9), mode="vanilla", lr_g=4e-4, lr_d=1e-4, betas=(0.5, 0.999)):
+        self.pg, self.bg = split_state({k: v.clone() for k, v in sd_g.items()})
+        self.pd, self.bd = split_state({k: v.clone() for k, v in sd_d.items()})
+        for d in (self.pg, self.pd):
+            for v in d.values():
+                v.requires_grad_(True)
+        self.opt_g = torch.optim.Adam(list(self.pg.values()), lr=lr_g, betas=betas)
+        self.opt_d = torch.optim.Adam(list(self.pd.values()), lr=lr_d, betas=betas)
+        self.labels, self.mode = labels, mode
+
+    def _g(self, z):
+        return dcgan_generator({**self.pg, **self.bg}, z, buffers=self.bg)
+
+    def _d(self, x):
+        return dcgan_discriminator({**self.pd, **self.bd}, x, buffers=self.bd)
+
+    def step(self, x, z1, z2):
+        rl, fl, gl = self.labels
+        self.opt_d.zero_grad()
+        out = self._d(x)
+        dx = out.mean().item()
+        l_real = gan_loss(self.mode, out, True, False, rl, fl, gl)
+        l_real.backward()
+        fake = self._g(z1)
+        out = self._d(fake.detach())
+        dgz1 = out.mean().item()
+        l_fake = gan_loss(self.mode, out, False, False, rl, fl, gl)
+        l_fake.backward()
+        self.opt_d.step()
+        self.opt_g.zero_grad()
+        fake = self._g(z2)
+        out = self._d(fake)
+        dgz2 = out.mean().item()
+        l_g = gan_loss(self.mode, out, False, True, rl, fl, gl)
+        l_g.backward()
+        self.opt_g.step()
+        return l_real.item(), l_fake.item(), l_g.item(), dx, dgz1, dgz2

@@ -1,0 +1,150 @@
+"""SN-DCGAN (models/dcgan_specnorm.py) and ACGAN (models/acgan.py) mirrors on the GPU vs golden fixtures from the
+reference and vs the CPU oracle. Spectral-norm buffers (u, v) are fp32 GEMV results: compared at 1e-4."""
+import contextlib
+import io
+import os
+
+import pytest
+import torch
+
+from conftest import load_golden, unpack_grads
+from test_gpu_dcgan import global_cos, quiet, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def test_spectral_norm_kernels_match_torch_hook():
+    """gp_sn_* vs torch.nn.utils.spectral_norm itself (the third-party code the reference calls), Conv2d (dim 0) and
+    ConvTranspose2d (dim 1): sigma-normalised weight, in-place u/v after 3 forwards, and weight_orig gradient."""
+    from gan_playground_b200 import functional as GF
+
+    for ctor, dim in ((lambda: torch.nn.Conv2d(24, 40, 4, 2, 1), 0), (lambda: torch.nn.ConvTranspose2d(24, 40, 4, 2, 1), 1),
+                      (lambda: torch.nn.Linear(96, 1), 0), (lambda: torch.nn.Embedding(10, 64), 0)):
+        torch.manual_seed(0)
+        ref = torch.nn.utils.spectral_norm(ctor()).cuda()
+        mine_w = ref.weight_orig.detach().clone().requires_grad_(True)
+        u, v = ref.weight_u.detach().clone(), ref.weight_v.detach().clone()
+        ref.train()
+        for it in range(3):
+            # run torch's hook (it fires in the module's forward pre-hook) by touching forward on a dummy input
+            hook = next(iter(ref._forward_pre_hooks.values()))
+            hook(ref, None)
+            w_ref = ref.weight
+            w_mine = GF.SpectralNormFn.apply(mine_w, u, v, dim, True)
+            assert torch.allclose(w_mine, w_ref, rtol=1e-4, atol=1e-6), (dim, it)
+        assert torch.allclose(u, ref.weight_u, atol=1e-5) and torch.allclose(v, ref.weight_v, atol=1e-5)
+        g = torch.randn_like(w_ref)
+        (gr,) = torch.autograd.grad(w_ref, ref.weight_orig, g)
+        (gm,) = torch.autograd.grad(w_mine, mine_w, g)
+        assert torch.allclose(gm, gr, rtol=1e-3, atol=1e-5 * gr.abs().max().item())
+        # eval mode: no power iteration, sigma from the stored u, v
+        ref.eval()
+        hook(ref, None)
+        u0 = u.clone()
+        w_eval = GF.SpectralNormFn.apply(mine_w, u, v, dim, False)
+        assert torch.equal(u, u0) and torch.allclose(w_eval, ref.weight, rtol=1e-4, atol=1e-6)
+
+
+def test_sn_dcgan_golden_step():
+    from gan_playground_b200.criterion import GANLoss
+    from gan_playground_b200.models import dcgan_specnorm as M
+
+    fx = load_golden("snd_r32_w4.pt")
+    netG = quiet(lambda: M.Generator(z_dim=fx["z_dim"], ngf=fx["width"], resolution=32)).cuda()
+    netD = quiet(lambda: M.Discriminator(ndf=fx["width"], resolution=32)).cuda()
+    netG.load_state_dict(fx["sd_g"])
+    netD.load_state_dict(fx["sd_d"])
+    crit = GANLoss("hinge").cuda()
+    x, z1, z2 = fx["x"].cuda(), fx["z1"].cuda(), fx["z2"].cuda()
+    out = netD(x)
+    loss = crit(out, True)
+    loss.backward()
+    assert relerr(out, fx["d_real"]) < 2e-2
+    assert abs(loss.item() - fx["loss_real"].item()) < 0.02 * abs(fx["loss_real"].item())
+    assert global_cos(netD.named_parameters(), unpack_grads(fx["d_grads_real"])) > 0.99
+    fake1 = netG(z1)
+    assert relerr(fake1, fx["fake1"]) < 2e-2
+    netD.zero_grad()
+    out = netD(fx["fake1"].cuda())
+    crit(out, False).backward()
+    assert relerr(out, fx["d_fake"]) < 3e-2
+    assert global_cos(netD.named_parameters(), unpack_grads(fx["d_grads_fake"])) > 0.98
+    netG.zero_grad(), netD.zero_grad()
+    loss = crit(netD(netG(z2)), False, True)
+    loss.backward()
+    assert abs(loss.item() - fx["loss_g"].item()) < 0.03 * abs(fx["loss_g"].item()) + 1e-3
+    assert global_cos(netG.named_parameters(), unpack_grads(fx["g_grads"])) > 0.9
+    # u / v after 3 D forwards and 2 G forwards (one in-place power iteration per train-mode forward)
+    for net, key in ((netD, "buf_d_after"), (netG, "buf_g_after")):
+        sd = net.state_dict()
+        for k, v in fx[key].items():
+            if k.endswith(("weight_u", "weight_v")):
+                assert torch.allclose(sd[k].cpu(), v, atol=2e-4), k
+            if k.endswith("num_batches_tracked"):
+                assert int(sd[k]) == int(v)
+    out, hid = netD(x, out_hidden=True)
+    assert hid.shape == (x.shape[0], fx["width"] * 8, 4, 4) and hid.dtype == torch.float32
+
+
+def test_sn_dcgan_width64_vs_oracle():
+    from gan_playground_b200.criterion import GANLoss
+    from gan_playground_b200.models import dcgan_specnorm as M
+    from oracle import gan_oracle as O
+
+    torch.manual_seed(0)
+    netG, netD = quiet(lambda: M.Generator(resolution=32)), quiet(lambda: M.Discriminator(resolution=32))
+    sd_g = {k: v.clone() for k, v in netG.state_dict().items()}
+    sd_d = {k: v.clone() for k, v in netD.state_dict().items()}
+    gen = torch.Generator().manual_seed(1)
+    B = 32
+    x = torch.rand(B, 3, 32, 32, generator=gen) * 2 - 1
+    z1, z2 = torch.randn(B, 100, generator=gen), torch.randn(B, 100, generator=gen)
+    torch.set_num_threads(os.cpu_count())
+    ref = O.dcgan_step_grads(sd_g, sd_d, x, z1, z2, labels=(1.0, 0.0, 1.0), mode="hinge", sn=True, flatten_head=True)
+    netG.cuda(), netD.cuda()
+    crit = GANLoss("hinge").cuda()
+    out = netD(x.cuda())
+    loss = crit(out, True)
+    loss.backward()
+    assert relerr(out, ref["d_real"]) < 1e-2
+    gD = {k: v for k, v in ref["d_grads_real"].items()}
+    assert global_cos(netD.named_parameters(), gD) > 0.999
+    netD.zero_grad()
+    out = netD(ref["fake1"].cuda())
+    crit(out, False).backward()
+    assert relerr(out, ref["d_fake"]) < 2e-2
+    netG.zero_grad(), netD.zero_grad()
+    # the oracle ran D three times and G twice; replay the same number of power iterations before the G step
+    netG(z1.cuda())
+    loss = crit(netD(netG(z2.cuda())), False, True)
+    loss.backward()
+    assert abs(loss.item() - ref["loss_g"].item()) < 0.02 * abs(ref["loss_g"].item()) + 1e-3
+    assert global_cos(netG.named_parameters(), ref["g_grads"]) > 0.99
+
+
+def test_acgan_golden_step():
+    from gan_playground_b200.criterion import GANLoss
+    from gan_playground_b200.models import acgan as M
+
+    fx = load_golden("acgan_r64_w4.pt")
+    netG = quiet(lambda: M.Generator(z_dim=16, ngf=fx["width"], n_class=10)).cuda()
+    netD = quiet(lambda: M.Discriminator(ndf=fx["width"], n_class=10)).cuda()
+    netG.load_state_dict(fx["sd_g"])
+    netD.load_state_dict(fx["sd_d"])
+    crit = GANLoss("vanilla", 0.9, 0.1, 0.9).cuda()
+    mse = torch.nn.MSELoss()
+    x, y, z = fx["x"].cuda(), fx["y"].cuda(), fx["z"].cuda()
+    adv, cls = netD(x)
+    loss = crit(adv, True) + mse(cls, y) * 0.5       # main_acgan.py:95-97
+    loss.backward()
+    assert relerr(adv, fx["d_real"]) < 2e-2 and relerr(cls, fx["d_real_cls"]) < 2e-2
+    assert abs(loss.item() - fx["loss_real"].item()) < 0.02 * abs(fx["loss_real"].item())
+    assert global_cos(netD.named_parameters(), unpack_grads(fx["d_grads_real"])) > 0.99
+    fake = netG(z, y)
+    assert relerr(fake, fx["fake"]) < 2e-2
+    netG.zero_grad(), netD.zero_grad()
+    adv, cls = netD(fake)
+    loss = crit(adv, False, True) + mse(cls, y) * 0.5
+    loss.backward()
+    assert abs(loss.item() - fx["loss_g"].item()) < 0.03 * abs(fx["loss_g"].item())
+    assert global_cos(netG.named_parameters(), unpack_grads(fx["g_grads"])) > 0.85

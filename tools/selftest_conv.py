@@ -65,7 +65,7 @@ def conv_fwd(x_nhwc, w_packed, bias, kind, Hout, Wout, act=0, stats=False):
         ss = torch.zeros(Nout, device="cuda")
     p = _lib.ConvFwd(x_nhwc.data_ptr(), w_packed.data_ptr(), bias.data_ptr() if bias is not None else None,
                      out.data_ptr(), s.data_ptr() if stats else None, ss.data_ptr() if stats else None,
-                     NB, Hin, Win, Cin, Hout, Wout, Nout, KIND[kind], act)
+                     NB, Hin, Win, Cin, Hout, Wout, Nout, KIND[kind], act, None)
     rc = _lib.lib().gp_conv_fwd(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     _lib.check(rc, "gp_conv_fwd")
     torch.cuda.synchronize()
