@@ -70,7 +70,9 @@ __global__ void pack_matrix_kernel(const float* __restrict__ src, __nv_bfloat16*
 
 // conv weight (D0, D1, KH*KW) fp32 -> packed bf16 [N][tap][C] with (N, C) = (D0, D1) if n_dim == 0 else (D1, D0)
 __global__ void pack_conv_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int D0, int D1,
-                                        int taps, int n_dim, const float* __restrict__ inv_scale) {
+                                        int taps, int n_dim_flags, const float* __restrict__ inv_scale) {
+  const int n_dim = n_dim_flags & 1;
+  const bool flip = (n_dim_flags & 2) != 0;  // reversed tap order: dgrad of a stride-1 conv is a conv with the flipped kernel
   const int N = n_dim == 0 ? D0 : D1, C = n_dim == 0 ? D1 : D0;
   const long long total = (long long)N * taps * C;
   const float sc = inv_scale ? 1.f / __ldg(inv_scale) : 1.f;
@@ -79,7 +81,7 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ src, __nv_bflo
     const int t = (int)((i / C) % taps);
     const int n = (int)(i / ((long long)C * taps));
     const int d0 = n_dim == 0 ? n : c, d1 = n_dim == 0 ? c : n;
-    dst[i] = __float2bfloat16(__ldg(src + ((long long)d0 * D1 + d1) * taps + t) * sc);
+    dst[i] = __float2bfloat16(__ldg(src + ((long long)d0 * D1 + d1) * taps + (flip ? taps - 1 - t : t)) * sc);
   }
 }
 
@@ -613,7 +615,7 @@ int gp_unpack_matrix(const float* src, float* dst, int R, int K, int ld_src, lon
 
 int gp_pack_conv_weight(const float* src, void* dst, int D0, int D1, int taps, int n_dim, const float* inv_scale,
                         void* stream) {
-  GP_REQUIRE(src && dst && D0 > 0 && D1 > 0 && taps > 0 && (n_dim == 0 || n_dim == 1), "gp_pack_conv_weight: bad arguments");
+  GP_REQUIRE(src && dst && D0 > 0 && D1 > 0 && taps > 0 && n_dim >= 0 && n_dim <= 3, "gp_pack_conv_weight: bad arguments");
   pack_conv_weight_kernel<<<grid_for((long long)D0 * D1 * taps), 256, 0, as_stream(stream)>>>(
       src, static_cast<__nv_bfloat16*>(dst), D0, D1, taps, n_dim, inv_scale);
   GP_CHECK_LAUNCH();

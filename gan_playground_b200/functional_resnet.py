@@ -1,0 +1,244 @@
+"""Autograd nodes for the SNGAN projection networks (reference: models/sngan_projection.py): stride-1 convs with fused
+residual add, conditional BatchNorm with fused nearest-upsample, pooling / upsampling, the 3-channel image-side layers
+and the projection head. Same conventions as functional.py: NHWC bf16 activations, fp32 torch-layout parameters."""
+import torch
+
+from . import ops, parallel
+from .functional import BN_EPS, BN_MOMENTUM, _bn_backward, _bn_forward
+
+
+class Conv2dNHWC(torch.autograd.Function):
+    """nn.Conv2d(k=3, p=1) / nn.Conv2d(k=1) (+ bias) [+ residual] + activation, no normalisation.
+    Reference: ResGenBlock / ResDisBlock convs c1, c2, c_sc (models/sngan_projection.py:30-44,105-119)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, act, cache, key):
+        NB, H, W, _ = x.shape
+        ksize = weight.shape[2]
+        kind = ops.KIND_CONV_K3S1 if ksize == 3 else ops.KIND_CONV_K1S1
+        wp = cache.get((key, "fwd"), weight, lambda: ops.pack_conv_weight(weight.detach(), 0))
+        a = ops.conv_fwd(x, wp, bias.detach() if bias is not None else None, kind, H, W, act, residual=residual)
+        ctx.save_for_backward(x, weight, a)
+        ctx.misc = (kind, ksize * ksize, act, cache, key, residual is not None, bias is not None)
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        x, weight, a = ctx.saved_tensors
+        kind, taps, act, cache, key, has_res, has_bias = ctx.misc
+        da = da.contiguous()
+        dy = ops.act_bwd(da, a, act) if act != ops.ACT_NONE else da
+        NB, H, W, _ = x.shape
+        dx = dweight = dbias = None
+        if ctx.needs_input_grad[1]:
+            dweight = ops.unpack_conv_wgrad(ops.conv_wgrad(dy, x, kind, taps), weight.shape)
+        if has_bias and ctx.needs_input_grad[2]:
+            dbias = ops.colsum(dy)
+        if ctx.needs_input_grad[0]:
+            # dgrad of a stride-1 conv: the same conv with channels swapped and the tap order reversed
+            wpd = cache.get((key, "dgrad"), weight, lambda: ops.pack_conv_weight(weight.detach(), 1 | 2))
+            dx = ops.conv_fwd(dy, wpd, None, kind, H, W)
+        dres = dy if (has_res and ctx.needs_input_grad[3]) else None
+        return dx, dweight, dbias, dres, None, None, None
+
+
+class BNAct(torch.autograd.Function):
+    """nn.BatchNorm2d (affine) + activation on an existing NHWC tensor (generator's b6 + ReLU, :92-93)."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, bufs, act, training):
+        a, fin, count = _bn_forward(y, gamma.detach(), beta.detach(), bufs, act, training)
+        ctx.save_for_backward(y, fin)
+        ctx.misc = (count, act, training)
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        y, fin = ctx.saved_tensors
+        count, act, training = ctx.misc
+        dy, dgamma, dbeta = _bn_backward(da.contiguous(), y, fin, count, act, training)
+        return dy, dgamma, dbeta, None, None, None
+
+
+class CondBNAct(torch.autograd.Function):
+    """ConditionalBatchNorm2d (models/sngan_projection.py:6-19) + activation [+ nearest x2 upsample (:53)]:
+    batch statistics (synchronised over ranks) -> xhat * embed(y)[:C] + embed(y)[C:] -> act -> upsample, one pass."""
+
+    @staticmethod
+    def forward(ctx, x, emb, labels, bufs, act, upsample, training):
+        C = x.shape[-1]
+        count = (x.numel() // C) * parallel.world_size()
+        rm, rv, nbt = bufs
+        if training:
+            st = ops.bn_stats(x)
+            parallel.all_reduce_sum_(st)
+            fin = ops.bn_finalize(st, count, None, None, rm, rv, nbt, BN_EPS, BN_MOMENTUM)
+        else:
+            fin = ops.bn_eval_params(rm, rv, None, None, BN_EPS)
+        e = emb.detach()
+        out = ops.cbn_apply_act(x, fin, e, labels, act, upsample)
+        ctx.save_for_backward(x, fin, e, labels)
+        ctx.misc = (count, act, upsample, training, emb.shape[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, da):
+        x, fin, e, labels = ctx.saved_tensors
+        count, act, upsample, training, ncls = ctx.misc
+        da = da.contiguous()
+        S, demb = ops.cbn_bwd_reduce(da, x, fin, e, labels, act, upsample, ncls)
+        parallel.all_reduce_sum_(S)
+        if not training:
+            S = torch.zeros_like(S)
+        dx = ops.cbn_bwd_apply(da, x, fin, e, labels, S, count, act, upsample)
+        return dx, demb, None, None, None, None, None
+
+
+class Pool2x(torch.autograd.Function):
+    """F.avg_pool2d(x, 2) (:128,132)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.pool2x(x, 0.25)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.upsample2x(g.contiguous(), 0.25)
+
+
+class Upsample2x(torch.autograd.Function):
+    """F.interpolate(x, scale_factor=2) (nearest) (:60)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.upsample2x(x, 1.0)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.pool2x(g.contiguous(), 1.0)
+
+
+class ReluFn(torch.autograd.Function):
+    """F.relu on a block input whose raw value is still needed by the shortcut (:122)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        a = ops.act_fwd(x, ops.ACT_RELU)
+        ctx.save_for_backward(a)
+        return a
+
+    @staticmethod
+    def backward(ctx, g):
+        (a,) = ctx.saved_tensors
+        return ops.act_bwd(g.contiguous(), a, ops.ACT_RELU)
+
+
+def _center_tap(wsc):
+    """(Cout, ch, 1, 1) 1x1 kernel embedded as the centre tap of a 3x3 kernel: lets the shortcut share c1's im2col."""
+    full = torch.zeros((wsc.shape[0], wsc.shape[1], 3, 3), device=wsc.device, dtype=wsc.dtype)
+    full[:, :, 1, 1] = wsc[:, :, 0, 0]
+    return full
+
+
+class ImageConv3(torch.autograd.Function):
+    """First block of the projection discriminator on the fp32 NCHW image: h1 = relu(c1(x)) (3x3) and s = c_sc(x) (1x1)
+    from ONE im2col (models/sngan_projection.py:156-163; avg-pooling commutes with the sum, so both are produced at
+    full resolution and pooled once after c2). 1-tap tensor-core GEMMs with K = 32."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, wsc, bsc):
+        x = x.contiguous()
+        NB, ch, H, W = x.shape
+        Cout = w1.shape[0]
+        col = ops.im2col_k3s1(x.detach())
+        K = ch * 9
+        wp1 = ops.pack_matrix(w1.detach().contiguous(), Cout, K, Cout, 32, K, 1)
+        wps = ops.pack_matrix(_center_tap(wsc.detach()), Cout, K, Cout, 32, K, 1)
+        fl = 2.0 * NB * H * W * Cout
+        h1 = ops.conv_fwd(col, wp1, b1.detach(), ops.KIND_CONV_K1S1, H, W, ops.ACT_RELU, flops=fl * K)
+        s = ops.conv_fwd(col, wps, bsc.detach(), ops.KIND_CONV_K1S1, H, W, flops=fl * ch)
+        ctx.save_for_backward(x, w1, wsc, h1)
+        return h1, s
+
+    @staticmethod
+    def backward(ctx, dh1, ds):
+        x, w1, wsc, h1 = ctx.saved_tensors
+        NB, ch, H, W = x.shape
+        Cout, K = w1.shape[0], ch * 9
+        dy1 = ops.act_bwd(dh1.contiguous(), h1, ops.ACT_RELU)
+        ds = ds.contiguous()
+        col = ops.im2col_k3s1(x)
+        fl = 2.0 * NB * H * W * Cout
+        dw1 = ops.unpack_matrix(ops.conv_wgrad(dy1, col, ops.KIND_CONV_K1S1, 1, flops=fl * K).view(Cout, 32), w1.shape,
+                                Cout, K, 32, K, 1)
+        dws_full = ops.unpack_matrix(ops.conv_wgrad(ds, col, ops.KIND_CONV_K1S1, 1, flops=fl * ch).view(Cout, 32),
+                                     (Cout, ch, 3, 3), Cout, K, 32, K, 1)
+        dwsc = dws_full[:, :, 1:2, 1:2].contiguous()
+        db1, dbsc = ops.colsum(dy1), ops.colsum(ds)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wt1 = ops.pack_matrix(w1.detach().contiguous(), K, Cout, 32, Cout, 1, K)
+            wts = ops.pack_matrix(_center_tap(wsc.detach()), K, Cout, 32, Cout, 1, K)
+            dcol = ops.conv_fwd(dy1, wt1, None, ops.KIND_CONV_K1S1, H, W, flops=fl * K)
+            dcol = ops.conv_fwd(ds, wts, None, ops.KIND_CONV_K1S1, H, W, residual=dcol, flops=fl * ch)
+            dx = ops.col2im_k3s1(dcol, ch)
+        return dx, dw1, db1, dwsc, dbsc
+
+
+class ImageOut3(torch.autograd.Function):
+    """Last layer of the ResNet generator: tanh(Conv2d(ch -> img_dim, 3x3)) written as the fp32 NCHW image (:95).
+    The GEMM runs with Nout padded to 8 (rows >= img_dim are zero)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        NB, H, W, C = x.shape
+        ch = weight.shape[0]
+        w8 = torch.zeros((8,) + tuple(weight.shape[1:]), device=x.device, dtype=torch.float32)
+        w8[:ch] = weight.detach()
+        b8 = torch.zeros((8,), device=x.device, dtype=torch.float32)
+        b8[:ch] = bias.detach()
+        wp = ops.pack_conv_weight(w8, 0)
+        y8 = ops.conv_fwd(x, wp, b8, ops.KIND_CONV_K3S1, H, W, flops=2.0 * NB * H * W * ch * C * 9)
+        out = ops.nhwc8_to_image(y8, ch, True)
+        ctx.save_for_backward(x, w8, out)
+        ctx.ch = ch
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w8, out = ctx.saved_tensors
+        ch = ctx.ch
+        NB, H, W, C = x.shape
+        dy8 = ops.image_to_nhwc8_grad(dout.contiguous(), out, True)
+        fl = 2.0 * NB * H * W * ch * C * 9
+        dw8 = ops.unpack_conv_wgrad(ops.conv_wgrad(dy8, x, ops.KIND_CONV_K3S1, 9, flops=fl), w8.shape)
+        db8 = ops.colsum(dy8)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wpd = ops.pack_conv_weight(w8, 1 | 2)
+            dx = ops.conv_fwd(dy8, wpd, None, ops.KIND_CONV_K3S1, H, W, flops=fl)
+        return dx, dw8[:ch].contiguous(), db8[:ch].contiguous()
+
+
+class ProjHead(torch.autograd.Function):
+    """relu -> sum over (H, W) -> l6(h) + sum_c l_y(y)_c * h_c (models/sngan_projection.py:190-195)."""
+
+    @staticmethod
+    def forward(ctx, a, w6, b6, Ey, labels):
+        h = ops.relu_sumpool(a)
+        e = Ey.detach().contiguous() if Ey is not None else None
+        out = ops.proj_head_fwd(h, w6.detach().contiguous(), b6.detach(), e, labels)
+        ctx.save_for_backward(a, h, w6, e if e is not None else torch.empty(0, device=a.device), labels
+                              if labels is not None else torch.empty(0, device=a.device))
+        ctx.has_proj = Ey is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        a, h, w6, e, labels = ctx.saved_tensors
+        E = e if ctx.has_proj else None
+        lb = labels if ctx.has_proj else None
+        dh, dw, db, dE = ops.proj_head_bwd(dout.contiguous(), h, w6.detach().contiguous(), E, lb,
+                                           e.shape[0] if ctx.has_proj else 0)
+        da = ops.relu_sumpool_bwd(dh, a)
+        return da, dw.view_as(w6), db, dE, None

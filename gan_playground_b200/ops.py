@@ -352,3 +352,144 @@ def sn_grad(g, w_sn, dim, u, v, sigma):
     out = torch.empty_like(w_sn)
     check(_fn("gp_sn_grad")(_p(g), _p(w_sn), A, B, T, dim, _p(u), _p(v), _p(sigma), _p(dot), _p(out), _stream()), "gp_sn_grad")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ SNGAN projection
+_SIGS.update({
+    "gp_cbn_apply_act": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "gp_cbn_bwd_reduce": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp],
+    "gp_cbn_bwd_apply": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _i, _i, _vp],
+    "gp_upsample2x": [_vp, _vp, _i, _i, _i, _i, _f, _vp],
+    "gp_pool2x": [_vp, _vp, _i, _i, _i, _i, _f, _vp],
+    "gp_act_fwd": [_vp, _vp, _ll, _i, _vp],
+    "gp_im2col_k3s1": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "gp_col2im_k3s1": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "gp_nhwc8_to_image": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "gp_image_to_nhwc8_grad": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "gp_relu_sumpool": [_vp, _vp, _i, _i, _i, _vp],
+    "gp_relu_sumpool_bwd": [_vp, _vp, _vp, _i, _i, _i, _vp],
+    "gp_proj_head_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "gp_proj_head_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+})
+
+
+def cbn_apply_act(y, fin, emb, labels, act, upsample):
+    """y: bf16 (NB, H, W, C); fin: [4, C] from bn_finalize (mean, rstd, ...); emb: fp32 [ncls, 2C] or None."""
+    _chk(y, torch.bfloat16, "y")
+    NB, H, W, C = y.shape
+    s = 2 if upsample else 1
+    out = torch.empty((NB, s * H, s * W, C), device=y.device, dtype=torch.bfloat16)
+    check(_fn("gp_cbn_apply_act")(_p(y), _p(out), NB, H, W, C, _p(fin[0]), _p(fin[1]), _p(emb), _p(labels), act,
+                                  1 if upsample else 0, _stream()), "gp_cbn_apply_act")
+    return out
+
+
+def cbn_bwd_reduce(da, y, fin, emb, labels, act, upsample, n_classes):
+    """Returns (S fp32 [2, C], demb fp32 [ncls, 2C] or None)."""
+    _chk(da, torch.bfloat16, "da")
+    NB, H, W, C = y.shape
+    part = torch.empty((NB, 2, C), device=y.device, dtype=torch.float32)
+    S = torch.empty((2, C), device=y.device, dtype=torch.float32)
+    demb = torch.empty((n_classes, 2 * C), device=y.device, dtype=torch.float32) if emb is not None else None
+    check(_fn("gp_cbn_bwd_reduce")(_p(da), _p(y), NB, H, W, C, _p(fin[0]), _p(fin[1]), _p(emb), _p(labels), act,
+                                   1 if upsample else 0, _p(part), _p(S), _p(demb), n_classes, _stream()), "gp_cbn_bwd_reduce")
+    return S, demb
+
+
+def cbn_bwd_apply(da, y, fin, emb, labels, S, count, act, upsample):
+    NB, H, W, C = y.shape
+    dy = torch.empty_like(y)
+    check(_fn("gp_cbn_bwd_apply")(_p(da), _p(y), _p(dy), NB, H, W, C, _p(fin[0]), _p(fin[1]), _p(emb), _p(labels), _p(S),
+                                  float(count), act, 1 if upsample else 0, _stream()), "gp_cbn_bwd_apply")
+    return dy
+
+
+def upsample2x(x, scale=1.0):
+    _chk(x, torch.bfloat16, "x")
+    NB, H, W, C = x.shape
+    out = torch.empty((NB, 2 * H, 2 * W, C), device=x.device, dtype=torch.bfloat16)
+    check(_fn("gp_upsample2x")(_p(x), _p(out), NB, H, W, C, scale, _stream()), "gp_upsample2x")
+    return out
+
+
+def pool2x(x, scale):
+    _chk(x, torch.bfloat16, "x")
+    NB, H, W, C = x.shape
+    out = torch.empty((NB, H // 2, W // 2, C), device=x.device, dtype=torch.bfloat16)
+    check(_fn("gp_pool2x")(_p(x), _p(out), NB, H // 2, W // 2, C, scale, _stream()), "gp_pool2x")
+    return out
+
+
+def act_fwd(x, act):
+    _chk(x, torch.bfloat16, "x")
+    out = torch.empty_like(x)
+    check(_fn("gp_act_fwd")(_p(x), _p(out), x.numel(), act, _stream()), "gp_act_fwd")
+    return out
+
+
+def im2col_k3s1(img):
+    _chk(img, torch.float32, "img")
+    NB, ch, H, W = img.shape
+    col = torch.empty((NB, H, W, 32), device=img.device, dtype=torch.bfloat16)
+    check(_fn("gp_im2col_k3s1")(_p(img), _p(col), NB, ch, H, W, _stream()), "gp_im2col_k3s1")
+    return col
+
+
+def col2im_k3s1(col, ch):
+    _chk(col, torch.bfloat16, "col")
+    NB, H, W, _ = col.shape
+    img = torch.empty((NB, ch, H, W), device=col.device, dtype=torch.float32)
+    check(_fn("gp_col2im_k3s1")(_p(col), _p(img), NB, ch, H, W, _stream()), "gp_col2im_k3s1")
+    return img
+
+
+def nhwc8_to_image(x, ch, tanh_act):
+    _chk(x, torch.bfloat16, "x")
+    NB, H, W, _ = x.shape
+    img = torch.empty((NB, ch, H, W), device=x.device, dtype=torch.float32)
+    check(_fn("gp_nhwc8_to_image")(_p(x), _p(img), NB, ch, H * W, 1 if tanh_act else 0, _stream()), "gp_nhwc8_to_image")
+    return img
+
+
+def image_to_nhwc8_grad(dout, out, tanh_act):
+    _chk(dout, torch.float32, "dout")
+    NB, ch, H, W = dout.shape
+    dy = torch.empty((NB, H, W, 8), device=dout.device, dtype=torch.bfloat16)
+    check(_fn("gp_image_to_nhwc8_grad")(_p(dout), _p(out), _p(dy), NB, ch, H * W, 1 if tanh_act else 0, _stream()),
+          "gp_image_to_nhwc8_grad")
+    return dy
+
+
+def relu_sumpool(a):
+    _chk(a, torch.bfloat16, "a")
+    NB, H, W, C = a.shape
+    h = torch.empty((NB, C), device=a.device, dtype=torch.float32)
+    check(_fn("gp_relu_sumpool")(_p(a), _p(h), NB, H * W, C, _stream()), "gp_relu_sumpool")
+    return h
+
+
+def relu_sumpool_bwd(dh, a):
+    _chk(dh, torch.float32, "dh")
+    NB, H, W, C = a.shape
+    da = torch.empty_like(a)
+    check(_fn("gp_relu_sumpool_bwd")(_p(dh), _p(a), _p(da), NB, H * W, C, _stream()), "gp_relu_sumpool_bwd")
+    return da
+
+
+def proj_head_fwd(h, w, b, E, labels):
+    _chk(h, torch.float32, "h")
+    NB, C = h.shape
+    out = torch.empty((NB, 1), device=h.device, dtype=torch.float32)
+    check(_fn("gp_proj_head_fwd")(_p(h), _p(w), _p(b), _p(E), _p(labels), _p(out), NB, C, _stream()), "gp_proj_head_fwd")
+    return out
+
+
+def proj_head_bwd(dout, h, w, E, labels, n_classes):
+    NB, C = h.shape
+    dh = torch.empty_like(h)
+    dw = torch.empty((1, C), device=h.device, dtype=torch.float32)
+    db = torch.empty((1,), device=h.device, dtype=torch.float32)
+    dE = torch.empty((n_classes, C), device=h.device, dtype=torch.float32) if E is not None else None
+    check(_fn("gp_proj_head_bwd")(_p(dout), _p(h), _p(w), _p(E), _p(labels), _p(dh), _p(dw), _p(db), _p(dE), NB, C,
+                                  n_classes, _stream()), "gp_proj_head_bwd")
+    return dh, dw, db, dE

@@ -85,7 +85,8 @@ int gp_conv_wgrad(const gp_conv_wgrad_t* p, void* stream);
 
 /* ---- weight staging: fp32 torch-layout parameters -> bf16 GEMM operands (and gradients back).
  * gp_pack_conv_weight: src (D0, D1, taps) fp32 [Conv2d: (Cout, Cin, kh*kw); ConvTranspose2d: (Cin, Cout, kh*kw)]
- *   -> dst bf16 [N][tap][C] with (N, C) = (D0, D1) when n_dim == 0, (D1, D0) when n_dim == 1.
+ *   -> dst bf16 [N][tap][C] with (N, C) = (D0, D1) when (n_dim & 1) == 0, (D1, D0) when (n_dim & 1) == 1;
+ *   n_dim & 2 reverses the tap order (dgrad of a stride-1 conv = conv with the flipped kernel).
  *   inv_scale (optional device scalar): every element is divided by it — the W / sigma of spectral norm
  *   (torch:nn/utils/spectral_norm.py:112) fused into the staging pass.
  * gp_unpack_conv_wgrad: fp32 [M][tap][N] -> fp32 (M, N, tap), i.e. the torch layout of the parameter gradient.
@@ -172,6 +173,45 @@ int gp_sn_sigma(const float* w, int A, int B, int T, int dim, float* u, float* v
 int gp_sn_scale(const float* w, const float* sigma, float* out, long long n, void* stream);
 int gp_sn_grad(const float* g, const float* w_sn, int A, int B, int T, int dim, const float* u, const float* v,
                const float* sigma, float* dot, float* out, void* stream);
+
+/* ---- SNGAN projection networks (models/sngan_projection.py).
+ * Conditional BatchNorm (:6-19): BatchNorm2d(affine=False) statistics come from gp_bn_stats / gp_bn_finalize
+ * (gamma = beta = NULL); the per-sample scale / shift are gathered from the embedding table
+ * emb fp32 [n_classes][2C] (gamma = emb[label][0:C], beta = emb[label][C:2C]) inside these kernels. emb == NULL: plain
+ * non-affine normalisation. upsample != 0 fuses F.interpolate(scale_factor=2) (nearest, :53) into the write (forward)
+ * and the 2x2 gradient sum into the read (backward): out / da then live on the (2H, 2W) grid.
+ *   gp_cbn_apply_act : out = act(xhat * gamma[n] + beta[n])
+ *   gp_cbn_bwd_reduce: part fp32 [NB][2][C] scratch; S fp32 [2][C] = (sum gamma*dz, sum gamma*dz*xhat) (all-reduce for
+ *                      SyncBN); demb fp32 [n_classes][2C] = embedding gradient (may be NULL)
+ *   gp_cbn_bwd_apply : dy = rstd * (gamma[n]*dz - S0/count - xhat*S1/count) */
+int gp_cbn_apply_act(const void* y, void* out, int NB, int H, int W, int C, const float* mean, const float* rstd,
+                     const float* emb, const long long* labels, int act, int upsample, void* stream);
+int gp_cbn_bwd_reduce(const void* da, const void* y, int NB, int H, int W, int C, const float* mean, const float* rstd,
+                      const float* emb, const long long* labels, int act, int upsample, float* part, float* S,
+                      float* demb, int n_classes, void* stream);
+int gp_cbn_bwd_apply(const void* da, const void* y, void* dy, int NB, int H, int W, int C, const float* mean,
+                     const float* rstd, const float* emb, const long long* labels, const float* S, double count, int act,
+                     int upsample, void* stream);
+/* nearest x2 upsampling / 2x2 sum pooling with a scale (F.interpolate :53,60; F.avg_pool2d :128,132 = pool with 0.25;
+ * each is the other's gradient). gp_pool2x: (Hout, Wout) is the pooled size. gp_act_fwd: out = act(in) (F.relu :122). */
+int gp_upsample2x(const void* in, void* out, int NB, int H, int W, int C, float scale, void* stream);
+int gp_pool2x(const void* in, void* out, int NB, int Hout, int Wout, int C, float scale, void* stream);
+int gp_act_fwd(const void* in, void* out, long long n, int act, void* stream);
+/* 3x3 image-side layers (first conv of the discriminator :141-148, last conv + tanh of the generator :80,95):
+ * col bf16 [NB*H*W][32], column (c*3+kh)*3+kw; NHWC-8 bf16 <-> NCHW fp32 image with fused tanh / tanh'. */
+int gp_im2col_k3s1(const float* img, void* col, int NB, int ch, int H, int W, void* stream);
+int gp_col2im_k3s1(const void* col, float* img, int NB, int ch, int H, int W, void* stream);
+int gp_nhwc8_to_image(const void* in, float* img, int NB, int ch, int HW, int tanh_act, void* stream);
+int gp_image_to_nhwc8_grad(const float* dout, const float* out, void* dy, int NB, int ch, int HW, int tanh_act,
+                           void* stream);
+/* projection head (:190-195): h = sum_hw relu(a) (fp32 [NB][C]); out[n] = b + sum_c h[n][c] * (w[c] + E[label[n]][c])
+ * — the Linear l6 and the embedding inner product as one warp-level GEMV. Backward: dh, dw [C], db [1], dE [n_classes][C]. */
+int gp_relu_sumpool(const void* a, float* h, int NB, int HW, int C, void* stream);
+int gp_relu_sumpool_bwd(const float* dh, const void* a, void* da, int NB, int HW, int C, void* stream);
+int gp_proj_head_fwd(const float* h, const float* w, const float* b, const float* E, const long long* labels, float* out,
+                     int NB, int C, void* stream);
+int gp_proj_head_bwd(const float* dout, const float* h, const float* w, const float* E, const long long* labels,
+                     float* dh, float* dw, float* db, float* dE, int NB, int C, int n_classes, void* stream);
 
 #ifdef __cplusplus
 }
