@@ -111,7 +111,7 @@ static int launch(const ConvGemmParams& prm, int bn, int mt, int num_tiles, cuda
 using namespace gp;
 
 extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
-  GP_REQUIRE(a != nullptr && a->in && a->w && a->out, "gp_conv_fwd: null pointer");
+  GP_REQUIRE(a != nullptr && a->in && a->w && (a->out || a->out_f32), "gp_conv_fwd: null pointer");
   GP_REQUIRE(a->NB > 0 && a->Cin > 0 && a->Nout > 0, "gp_conv_fwd: empty problem");
   GP_REQUIRE(a->Cin % 8 == 0, "gp_conv_fwd: Cin=%d must be a multiple of 8 (16-byte TMA rows)", a->Cin);
   GP_REQUIRE(a->Nout % 8 == 0, "gp_conv_fwd: Nout=%d must be a multiple of 8", a->Nout);
@@ -132,6 +132,7 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
     if (bn <= 128 && tiles2 >= num_sms()) mt_sub = 2;
   }
   const int tile_px = mt_sub * kBlockM;
+  const int n_halves = a->in_lo != nullptr ? 2 : 1;  // bf16x3: hi and lo halves of the activation operand
   const long long inW = Cin, inH = (long long)a->Win * Cin, inN = (long long)a->Hin * a->Win * Cin;
   switch (a->kind) {
     case GP_KIND_CONV_K4S2: {
@@ -141,13 +142,15 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
       prm.n_phases = 1;
       prm.taps_per_phase = 16;
       factor_tile(tile_px, prm.Hs, prm.Ws, &prm.Nt, &prm.Ht, &prm.Wt);
-      for (int r = 0; r < 2; ++r)
-        for (int s = 0; s < 2; ++s) {
-          const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(a->in) + ((long long)r * a->Win + s) * Cin;
-          rc = make_map_nhwc(&prm.map_g[r * 2 + s], base, Cin, a->Win / 2, a->Hin / 2, a->NB, 2 * inW, 2 * inH, inN,
-                             prm.Wt, prm.Ht, prm.Nt);
-          if (rc) return rc;
-        }
+      for (int half = 0; half < n_halves; ++half)
+        for (int r = 0; r < 2; ++r)
+          for (int s = 0; s < 2; ++s) {
+            const __nv_bfloat16* base =
+                static_cast<const __nv_bfloat16*>(half ? a->in_lo : a->in) + ((long long)r * a->Win + s) * Cin;
+            rc = make_map_nhwc(&prm.map_g[half * 4 + r * 2 + s], base, Cin, a->Win / 2, a->Hin / 2, a->NB, 2 * inW,
+                               2 * inH, inN, prm.Wt, prm.Ht, prm.Nt);
+            if (rc) return rc;
+          }
       for (int kh = 0; kh < 4; ++kh)
         for (int kw = 0; kw < 4; ++kw) {
           int r, dh, s, dw;
@@ -171,9 +174,11 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
       prm.n_phases = 4;
       prm.taps_per_phase = 4;
       factor_tile(tile_px, prm.Hs, prm.Ws, &prm.Nt, &prm.Ht, &prm.Wt);
-      rc = make_map_nhwc(&prm.map_g[0], a->in, Cin, a->Win, a->Hin, a->NB, inW, inH, inN, prm.Wt, prm.Ht, prm.Nt);
-      if (rc) return rc;
-      for (int i = 1; i < 4; ++i) prm.map_g[i] = prm.map_g[0];
+      for (int half = 0; half < n_halves; ++half) {
+        rc = make_map_nhwc(&prm.map_g[half * 4], half ? a->in_lo : a->in, Cin, a->Win, a->Hin, a->NB, inW, inH, inN,
+                           prm.Wt, prm.Ht, prm.Nt);
+        if (rc) return rc;
+      }
       // output row oh = 2*ih - 1 + kh. Phase ph = oh & 1: ph=0 -> (kh=1, ih=i), (kh=3, ih=i-1); ph=1 -> (kh=0, ih=i+1), (kh=2, ih=i)
       static const int kk[2][2] = {{1, 3}, {0, 2}};
       static const int dd[2][2] = {{0, -1}, {1, 0}};
@@ -203,9 +208,11 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
       prm.n_phases = 1;
       prm.taps_per_phase = k * k;
       factor_tile(tile_px, prm.Hs, prm.Ws, &prm.Nt, &prm.Ht, &prm.Wt);
-      rc = make_map_nhwc(&prm.map_g[0], a->in, Cin, a->Win, a->Hin, a->NB, inW, inH, inN, prm.Wt, prm.Ht, prm.Nt);
-      if (rc) return rc;
-      for (int i = 1; i < 4; ++i) prm.map_g[i] = prm.map_g[0];
+      for (int half = 0; half < n_halves; ++half) {
+        rc = make_map_nhwc(&prm.map_g[half * 4], half ? a->in_lo : a->in, Cin, a->Win, a->Hin, a->NB, inW, inH, inN,
+                           prm.Wt, prm.Ht, prm.Nt);
+        if (rc) return rc;
+      }
       for (int kh = 0; kh < k; ++kh)
         for (int kw = 0; kw < k; ++kw) {
           Tap& t = prm.taps[ntaps_total++];
@@ -223,13 +230,31 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
       return set_error(GP_ERR_UNSUPPORTED, "gp_conv_fwd: unknown kind %d", a->kind);
   }
   const long long ktot = (long long)ntaps_total * Cin;  // packed row = every tap of the kernel window
-  rc = make_map_2d(&prm.map_w, a->w, ktot, a->Nout, bn);
+  if (n_halves == 2) {
+    // bf16x3 (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo) as three K "taps" per real tap: the lo activation maps are 4..7 and
+    // the lo weights are the second half [ktot, 2*ktot) of each packed row.
+    GP_REQUIRE(3 * ntaps_total <= kMaxTaps, "gp_conv_fwd: too many taps for the bf16x3 mode");
+    Tap tmp[kMaxTaps];
+    for (int i = 0; i < ntaps_total; ++i) tmp[i] = prm.taps[i];
+    for (int i = 0; i < ntaps_total; ++i) {
+      Tap hh = tmp[i], lh = tmp[i], hl = tmp[i];
+      lh.map = (int8_t)(tmp[i].map + 4);
+      hl.koff = tmp[i].koff + (int32_t)ktot;
+      prm.taps[3 * i] = hh;
+      prm.taps[3 * i + 1] = lh;
+      prm.taps[3 * i + 2] = hl;
+    }
+    prm.taps_per_phase *= 3;
+  }
+  rc = make_map_2d(&prm.map_w, a->w, n_halves * ktot, a->Nout, bn);
   if (rc) return rc;
   prm.map_d = prm.map_g[0];
   prm.NB = a->NB;
   prm.C = Cin;
   prm.N = a->Nout;
   prm.out = static_cast<__nv_bfloat16*>(a->out);
+  prm.out_lo = static_cast<__nv_bfloat16*>(a->out_lo);
+  prm.out_f32 = a->out_f32;
   prm.residual = static_cast<const __nv_bfloat16*>(a->residual);
   prm.bias = a->bias;
   prm.act_slope = a->act == GP_ACT_RELU ? 0.f : (a->act == GP_ACT_LRELU ? 0.2f : 1.f);

@@ -56,6 +56,8 @@ struct alignas(64) ConvGemmParams {
   long long out_sN, out_sH, out_sW;  // FWD: output strides in elements for pixel (n, h, w) of the small grid
   long long phase_off[4];            // FWD: output element offset of each phase
   __nv_bfloat16* out;
+  __nv_bfloat16* out_lo;          // optional: low half of a hi/lo bf16 pair (out = hi, out_lo = bf16(v - hi))
+  float* out_f32;                 // optional: store fp32 instead of bf16 (pre-BatchNorm outputs of the bf16x3 mode)
   const __nv_bfloat16* residual;  // optional, same indexing as out
   const float* bias;
   float act_slope;  // activation as max(v,0) + slope*min(v,0): 1 = identity, 0 = ReLU, 0.2 = LeakyReLU
@@ -324,19 +326,31 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 }
               }
             }
-            if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f) + slope * fminf(v[j], 0.f);
+            if (row_ok && p.out_f32 != nullptr) {
+              float4* dst = reinterpret_cast<float4*>(p.out_f32 + off + col0);
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                if (col0 + g * 4 < p.N) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+            } else if (row_ok) {
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
-                uint32_t w32[4];
+                uint32_t w32[4], l32[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const float a0 = v[g * 8 + 2 * e], a1 = v[g * 8 + 2 * e + 1];
-                  __nv_bfloat162 b2 = __floats2bfloat162_rn(fmaxf(a0, 0.f) + slope * fminf(a0, 0.f),
-                                                            fmaxf(a1, 0.f) + slope * fminf(a1, 0.f));
-                  w32[e] = *reinterpret_cast<uint32_t*>(&b2);
+                  const __nv_bfloat162 b2 = __floats2bfloat162_rn(a0, a1);
+                  w32[e] = *reinterpret_cast<const uint32_t*>(&b2);
+                  const float2 hf = __bfloat1622float2(b2);
+                  const __nv_bfloat162 l2 = __floats2bfloat162_rn(a0 - hf.x, a1 - hf.y);
+                  l32[e] = *reinterpret_cast<const uint32_t*>(&l2);
                 }
-                if (col0 + g * 8 < p.N)
+                if (col0 + g * 8 < p.N) {
                   *reinterpret_cast<uint4*>(orow + col0 + g * 8) = make_uint4(w32[0], w32[1], w32[2], w32[3]);
+                  if (p.out_lo != nullptr)
+                    *reinterpret_cast<uint4*>(p.out_lo + off + col0 + g * 8) = make_uint4(l32[0], l32[1], l32[2], l32[3]);
+                }
               }
             }
           }

@@ -2,10 +2,14 @@
 (conv / conv-transpose [+ BatchNorm] + activation, the first Linear, the image-side layers, the heads, the loss) whose
 forward and backward are sequences of C-ABI kernel calls (ops.py). Activations between nodes are NHWC bf16 tensors;
 parameters stay fp32 nn.Parameters in torch's layout and receive fp32 gradients, so torch.optim.Adam and
-state_dict()/torch.save work unchanged."""
+state_dict()/torch.save work unchanged.
+
+Precision modes (config.py): in "bf16x3" every activation travels as a hi/lo bf16 pair — node outputs are
+(a_hi, a_lo) with a_lo non-differentiable, and the next node takes (x, x_lo); autograd only ever sees the hi tensor
+(gradients are w.r.t. the real-valued activation). In "bf16" the lo half is None."""
 import torch
 
-from . import ops, parallel
+from . import config, ops, parallel
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
@@ -33,31 +37,51 @@ class WeightCache:
         self._d.clear()
 
 
+def with_lo(fn, h, *args):
+    """Apply a node to an activation that may carry its low half as the `_gp_lo` attribute; re-attach the output's."""
+    out = fn.apply(h, getattr(h, "_gp_lo", None), *args)
+    if isinstance(out, tuple):
+        a, lo = out
+        if lo is not None:
+            a._gp_lo = lo
+        return a
+    return out
+
+
 def _bn_forward(y, gamma, beta, bufs, act, training=True):
-    """y: bf16 NHWC pre-BN conv output. Returns (a, fin[4,C], count).
+    """y: pre-BN conv output, NHWC bf16 (fp32 in bf16x3 mode). Returns (a, a_lo, fin[4,C], count).
     training: batch statistics (all-reduced over ranks) + running-stat update, as nn.BatchNorm2d.train();
     eval: normalise with the running statistics."""
     C = y.shape[-1]
     count = (y.numel() // C) * parallel.world_size()
     rm, rv, nbt = bufs if bufs is not None else (None, None, None)
+    f32 = y.dtype == torch.float32
     if training or rm is None:
-        st = ops.bn_stats(y)
+        st = ops.bn_stats_f32(y) if f32 else ops.bn_stats(y)
         parallel.all_reduce_sum_(st)
         fin = ops.bn_finalize(st, count, gamma, beta, rm, rv, nbt, BN_EPS, BN_MOMENTUM)
     else:
         fin = ops.bn_eval_params(rm, rv, gamma, beta, BN_EPS)
-    a = ops.bn_apply_act(y, fin, act)
-    return a, fin, count
+    if f32:
+        a, a_lo = ops.bn_apply_act_split(y, fin, act)
+    else:
+        a, a_lo = ops.bn_apply_act(y, fin, act), None
+    return a, a_lo, fin, count
 
 
 def _bn_backward(da, y, fin, count, act, training=True):
     """Returns (dy, dgamma, dbeta)."""
-    red = ops.bn_bwd_reduce(da, y, fin, act)
+    f32 = y.dtype == torch.float32
+    red = ops.bn_bwd_reduce_f32(da, y, fin, act) if f32 else ops.bn_bwd_reduce(da, y, fin, act)
     parallel.all_reduce_sum_(red)
     # eval mode: statistics are constants, so the two batch-coupling terms vanish
-    dy = ops.bn_bwd_apply(da, y, fin, red if training else torch.zeros_like(red), count, act)
-    # dbeta = sum dz, dgamma = sum dz * xhat: local shares are red / world after the all-reduce made them global;
-    # parameter gradients are averaged over ranks later, so hand back the global sums divided by world.
+    red_used = red if training else torch.zeros_like(red)
+    if f32:
+        dy = ops.bn_bwd_apply_f32(da, y, fin, red_used, count, act)
+    else:
+        dy = ops.bn_bwd_apply(da, y, fin, red_used, count, act)
+    # dbeta = sum dz, dgamma = sum dz * xhat. After the all-reduce `red` holds global sums of rank-local-mean-loss
+    # gradients; parameter gradients are averaged over ranks later, so hand back global / world.
     w = parallel.world_size()
     dgamma, dbeta = red[1], red[0]
     if w > 1:
@@ -70,32 +94,40 @@ class ConvBlock(torch.autograd.Function):
     Reference: models/dcgan.py:35-40 (G blocks) and :104-110 (D blocks)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, gamma, beta, bufs, transposed, act, cache, key, training=True):
+    def forward(ctx, x, x_lo, weight, bias, gamma, beta, bufs, transposed, act, cache, key, training=True):
         NB, H, W, Cin = x.shape
+        x3 = config.x3()
+        n_dim = 1 if transposed else 0
         if transposed:
-            Cout = weight.shape[1]
-            wp = cache.get((key, "fwd"), weight, lambda: ops.pack_conv_weight(weight.detach(), 1))
             Ho, Wo, kind = 2 * H, 2 * W, ops.KIND_CONVT_K4S2
         else:
-            Cout = weight.shape[0]
-            wp = cache.get((key, "fwd"), weight, lambda: ops.pack_conv_weight(weight.detach(), 0))
             Ho, Wo, kind = H // 2, W // 2, ops.KIND_CONV_K4S2
         has_bn = gamma is not None or bufs is not None
-        y = ops.conv_fwd(x, wp, bias.detach() if bias is not None else None, kind, Ho, Wo,
-                         ops.ACT_NONE if has_bn else act)
+        b = bias.detach() if bias is not None else None
+        if x3:
+            wp = cache.get((key, "fwd3"), weight, lambda: ops.split_conv_weight(weight.detach(), n_dim))
+            if x_lo is None:
+                x_lo = torch.zeros_like(x)
+            y = ops.conv_fwd(x, wp, b, kind, Ho, Wo, ops.ACT_NONE if has_bn else act, x_lo=x_lo,
+                             out_mode="f32" if has_bn else "split")
+        else:
+            wp = cache.get((key, "fwd"), weight, lambda: ops.pack_conv_weight(weight.detach(), n_dim))
+            y = ops.conv_fwd(x, wp, b, kind, Ho, Wo, ops.ACT_NONE if has_bn else act)
         ctx.transposed, ctx.act, ctx.has_bn, ctx.cache, ctx.key = transposed, act, has_bn, cache, key
         if has_bn:
-            a, fin, count = _bn_forward(y, gamma.detach() if gamma is not None else None,
-                                        beta.detach() if beta is not None else None, bufs, act, training)
+            a, a_lo, fin, count = _bn_forward(y, gamma.detach() if gamma is not None else None,
+                                              beta.detach() if beta is not None else None, bufs, act, training)
             ctx.count, ctx.training = count, training
             ctx.save_for_backward(x, weight, y, fin)
         else:
-            a = y
+            a, a_lo = y if x3 else (y, None)
             ctx.save_for_backward(x, weight, a)
-        return a
+        if a_lo is not None:
+            ctx.mark_non_differentiable(a_lo)
+        return a, a_lo
 
     @staticmethod
-    def backward(ctx, da):
+    def backward(ctx, da, _unused=None):
         da = da.contiguous()
         if ctx.has_bn:
             x, weight, y, fin = ctx.saved_tensors
@@ -107,7 +139,7 @@ class ConvBlock(torch.autograd.Function):
             dgamma = dbeta = None
             dbias = ops.colsum(dy)
         dweight = dx = None
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[2]:
             if ctx.transposed:   # dW[Cin][tap][Cout]: dense = x (input grid), gathered = dy (output grid)
                 dwp = ops.conv_wgrad(x, dy, ops.KIND_CONV_K4S2, 16)
             else:                # dW[Cout][tap][Cin]: dense = dy (output grid), gathered = x (input grid)
@@ -121,9 +153,9 @@ class ConvBlock(torch.autograd.Function):
             else:                # dgrad of Conv == 4-phase transposed conv over dy with weights [Cin][tap][Cout]
                 wpd = ctx.cache.get((ctx.key, "dgrad"), weight, lambda: ops.pack_conv_weight(weight.detach(), 1))
                 dx = ops.conv_fwd(dy, wpd, None, ops.KIND_CONVT_K4S2, H, W)
-        if not ctx.needs_input_grad[2]:
+        if not ctx.needs_input_grad[3]:
             dbias = None
-        return dx, dweight, dbias, dgamma, dbeta, None, None, None, None, None, None
+        return dx, None, dweight, dbias, dgamma, dbeta, None, None, None, None, None, None
 
 
 class LinearToNHWC(torch.autograd.Function):
@@ -137,17 +169,29 @@ class LinearToNHWC(torch.autograd.Function):
         HW = bw * bw
         C = O // HW
         Kp = (K + 7) // 8 * 8
-        zb = ops.pack_matrix(z.detach().contiguous(), B, K, B, Kp, K, 1)
-        wp = cache.get((key, "fwd"), weight, lambda: ops.pack_matrix(weight.detach(), O, K, O, Kp, K, 1, perm=HW))
+        zc = z.detach().contiguous()
         # bias in NHWC-flatten order: dst[(s % HW)*C + s // HW] = bias[s]
         bp = cache.get((key, "bias"), bias, lambda: ops.unpack_matrix(bias.detach(), (O,), O, 1, 1, 1, 1, perm=C))
-        a = ops.conv_fwd(zb.view(B, 1, 1, Kp), wp, bp, ops.KIND_CONV_K1S1, 1, 1, act, flops=2.0 * B * O * K)
+        fl = 2.0 * B * O * K
+        if config.x3():
+            zb, z_lo = ops.split_rows(zc, B, K, Kp, K, 1)
+            wp = cache.get((key, "fwd3"), weight,
+                           lambda: ops.split_weight_matrix(weight.detach(), O, K, O, Kp, K, 1, perm=HW))
+            a, a_lo = ops.conv_fwd(zb.view(B, 1, 1, Kp), wp, bp, ops.KIND_CONV_K1S1, 1, 1, act, flops=fl,
+                                   x_lo=z_lo.view(B, 1, 1, Kp), out_mode="split")
+            a_lo = a_lo.view(B, bw, bw, C)
+        else:
+            zb = ops.pack_matrix(zc, B, K, B, Kp, K, 1)
+            wp = cache.get((key, "fwd"), weight, lambda: ops.pack_matrix(weight.detach(), O, K, O, Kp, K, 1, perm=HW))
+            a, a_lo = ops.conv_fwd(zb.view(B, 1, 1, Kp), wp, bp, ops.KIND_CONV_K1S1, 1, 1, act, flops=fl), None
         ctx.save_for_backward(zb, a, weight)
         ctx.dims = (B, K, O, HW, C, Kp, act)
-        return a.view(B, bw, bw, C)
+        if a_lo is not None:
+            ctx.mark_non_differentiable(a_lo)
+        return a.view(B, bw, bw, C), a_lo
 
     @staticmethod
-    def backward(ctx, da):
+    def backward(ctx, da, _unused=None):
         zb, a, weight = ctx.saved_tensors
         B, K, O, HW, C, Kp, act = ctx.dims
         da = da.contiguous().view(B, 1, 1, O)
@@ -164,6 +208,13 @@ class LinearToNHWC(torch.autograd.Function):
         return None, dweight, dbias, None, None, None, None
 
 
+def linear_to_nhwc(z, weight, bias, bw, act, cache, key):
+    a, lo = LinearToNHWC.apply(z, weight, bias, bw, act, cache, key)
+    if lo is not None:
+        a._gp_lo = lo
+    return a
+
+
 class ImageConv(torch.autograd.Function):
     """D's first layer: Conv2d(img_dim -> C, k4 s2 p1) + LeakyReLU(0.2) reading the fp32 NCHW image directly.
     Reference: models/dcgan.py:106-109 (block 0 has no BatchNorm). im2col -> 1-tap tensor-core GEMM (K = 64)."""
@@ -173,27 +224,35 @@ class ImageConv(torch.autograd.Function):
         x = x.contiguous()
         NB, ch, H, W = x.shape
         Cout = weight.shape[0]
-        col = ops.im2col_k4s2(x.detach())
-        wp = cache.get((key, "fwd"), weight,
-                       lambda: ops.pack_matrix(weight.detach(), Cout, ch * 16, Cout, 64, ch * 16, 1))
-        a = ops.conv_fwd(col, wp, bias.detach(), ops.KIND_CONV_K1S1, H // 2, W // 2, act,
-                         flops=2.0 * NB * (H // 2) * (W // 2) * Cout * ch * 16)
+        fl = 2.0 * NB * (H // 2) * (W // 2) * Cout * ch * 16
+        if config.x3():
+            col, col_lo = ops.im2col_k4s2_split(x.detach())
+            wp = cache.get((key, "fwd3"), weight,
+                           lambda: ops.split_weight_matrix(weight.detach(), Cout, ch * 16, Cout, 64, ch * 16, 1))
+            a, a_lo = ops.conv_fwd(col, wp, bias.detach(), ops.KIND_CONV_K1S1, H // 2, W // 2, act, flops=fl,
+                                   x_lo=col_lo, out_mode="split")
+            ctx.mark_non_differentiable(a_lo)
+        else:
+            col = ops.im2col_k4s2(x.detach())
+            wp = cache.get((key, "fwd"), weight,
+                           lambda: ops.pack_matrix(weight.detach(), Cout, ch * 16, Cout, 64, ch * 16, 1))
+            a, a_lo = ops.conv_fwd(col, wp, bias.detach(), ops.KIND_CONV_K1S1, H // 2, W // 2, act, flops=fl), None
         ctx.save_for_backward(x, weight, a)
         ctx.misc = (act, cache, key)
-        return a
+        return a, a_lo
 
     @staticmethod
-    def backward(ctx, da):
+    def backward(ctx, da, _unused=None):
         x, weight, a = ctx.saved_tensors
         act, cache, key = ctx.misc
         NB, ch, H, W = x.shape
         Cout = weight.shape[0]
+        fl = 2.0 * NB * (H // 2) * (W // 2) * Cout * ch * 16
         dy = ops.act_bwd(da.contiguous(), a, act) if act != ops.ACT_NONE else da.contiguous()
         dweight = dbias = dx = None
         if ctx.needs_input_grad[1]:
             col = ops.im2col_k4s2(x)
-            dwp = ops.conv_wgrad(dy, col, ops.KIND_CONV_K1S1, 1,
-                                 flops=2.0 * NB * (H // 2) * (W // 2) * Cout * ch * 16)  # [Cout][1][64]
+            dwp = ops.conv_wgrad(dy, col, ops.KIND_CONV_K1S1, 1, flops=fl)  # [Cout][1][64]
             dweight = ops.unpack_matrix(dwp.view(Cout, 64), weight.shape, Cout, ch * 16, 64, ch * 16, 1)
         if ctx.needs_input_grad[2]:
             dbias = ops.colsum(dy)
@@ -201,10 +260,16 @@ class ImageConv(torch.autograd.Function):
             # dcol[px][j] = sum_o dy[px][o] * W[o][j]  -> weights [64][Cout] = W^T (rows j >= ch*16 are zero)
             wpt = cache.get((key, "dgrad"), weight,
                             lambda: ops.pack_matrix(weight.detach(), ch * 16, Cout, 64, Cout, 1, ch * 16))
-            dcol = ops.conv_fwd(dy, wpt, None, ops.KIND_CONV_K1S1, H // 2, W // 2,
-                               flops=2.0 * NB * (H // 2) * (W // 2) * Cout * ch * 16)
+            dcol = ops.conv_fwd(dy, wpt, None, ops.KIND_CONV_K1S1, H // 2, W // 2, flops=fl)
             dx = ops.col2im_k4s2(dcol, None, ch, ops.ACT_NONE)
         return dx, dweight, dbias, None, None, None
+
+
+def image_conv(x, weight, bias, act, cache, key):
+    a, lo = ImageConv.apply(x, weight, bias, act, cache, key)
+    if lo is not None:
+        a._gp_lo = lo
+    return a
 
 
 class ImageConvT(torch.autograd.Function):
@@ -212,13 +277,22 @@ class ImageConvT(torch.autograd.Function):
     Reference: models/dcgan.py:41-44. 1-tap tensor-core GEMM (N = 64) -> col2im + bias + tanh."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act, cache, key):
+    def forward(ctx, x, x_lo, weight, bias, act, cache, key):
         NB, H, W, Cin = x.shape
         ch = weight.shape[1]
-        wp = cache.get((key, "fwd"), weight,
-                       lambda: ops.pack_matrix(weight.detach(), ch * 16, Cin, 64, Cin, 1, ch * 16))
-        ycol = ops.conv_fwd(x, wp, None, ops.KIND_CONV_K1S1, H, W, flops=2.0 * NB * H * W * Cin * ch * 16)
-        out = ops.col2im_k4s2(ycol, bias.detach(), ch, act)
+        fl = 2.0 * NB * H * W * Cin * ch * 16
+        if config.x3():
+            wp = cache.get((key, "fwd3"), weight,
+                           lambda: ops.split_weight_matrix(weight.detach(), ch * 16, Cin, 64, Cin, 1, ch * 16))
+            if x_lo is None:
+                x_lo = torch.zeros_like(x)
+            ycol = ops.conv_fwd(x, wp, None, ops.KIND_CONV_K1S1, H, W, flops=fl, x_lo=x_lo, out_mode="f32")
+            out = ops.col2im_k4s2_f32(ycol, bias.detach(), ch, act)
+        else:
+            wp = cache.get((key, "fwd"), weight,
+                           lambda: ops.pack_matrix(weight.detach(), ch * 16, Cin, 64, Cin, 1, ch * 16))
+            ycol = ops.conv_fwd(x, wp, None, ops.KIND_CONV_K1S1, H, W, flops=fl)
+            out = ops.col2im_k4s2(ycol, bias.detach(), ch, act)
         ctx.save_for_backward(x, weight, out)
         ctx.misc = (act, cache, key)
         return out
@@ -229,20 +303,21 @@ class ImageConvT(torch.autograd.Function):
         act, cache, key = ctx.misc
         NB, H, W, Cin = x.shape
         ch = weight.shape[1]
+        fl = 2.0 * NB * H * W * Cin * ch * 16
         dout = dout.contiguous()
         # dcol[(n,ih,iw)][(co,kh,kw)] = dpre[n, co, 2ih-1+kh, 2iw-1+kw], dpre = dout * (1 - out^2) fused into the gather
         dcol = ops.im2col_k4s2(dout, out if act == ops.ACT_TANH else None)
         dweight = dbias = dx = None
-        if ctx.needs_input_grad[1]:
-            dwp = ops.conv_wgrad(x, dcol, ops.KIND_CONV_K1S1, 1, flops=2.0 * NB * H * W * Cin * ch * 16)  # [Cin][1][64]
-            dweight = ops.unpack_matrix(dwp.view(Cin, 64), weight.shape, Cin, ch * 16, 64, ch * 16, 1)
         if ctx.needs_input_grad[2]:
+            dwp = ops.conv_wgrad(x, dcol, ops.KIND_CONV_K1S1, 1, flops=fl)  # [Cin][1][64]
+            dweight = ops.unpack_matrix(dwp.view(Cin, 64), weight.shape, Cin, ch * 16, 64, ch * 16, 1)
+        if ctx.needs_input_grad[3]:
             dbias = ops.image_bias_grad(dout, out if act == ops.ACT_TANH else None)
         if ctx.needs_input_grad[0]:
             wpd = cache.get((key, "dgrad"), weight,
                             lambda: ops.pack_matrix(weight.detach(), Cin, ch * 16, Cin, 64, ch * 16, 1))
-            dx = ops.conv_fwd(dcol, wpd, None, ops.KIND_CONV_K1S1, H, W, flops=2.0 * NB * H * W * Cin * ch * 16)
-        return dx, dweight, dbias, None, None, None
+            dx = ops.conv_fwd(dcol, wpd, None, ops.KIND_CONV_K1S1, H, W, flops=fl)
+        return dx, None, dweight, dbias, None, None, None
 
 
 class Head(torch.autograd.Function):
@@ -251,11 +326,15 @@ class Head(torch.autograd.Function):
     (models/dcgan_specnorm.py:125-126)."""
 
     @staticmethod
-    def forward(ctx, a, weight, bias, flatten):
+    def forward(ctx, a, a_lo, weight, bias, flatten):
         NB, H, W, C = a.shape
         O = weight.shape[0]
         strides = (C * H * W, H * W, 1) if flatten else (C, 1, 0)
-        out = ops.head_fwd(a, weight.detach(), bias.detach() if bias is not None else None, O, *strides)
+        b = bias.detach() if bias is not None else None
+        if a_lo is not None:
+            out = ops.head_fwd_split(a, a_lo, weight.detach(), b, O, *strides)
+        else:
+            out = ops.head_fwd(a, weight.detach(), b, O, *strides)
         ctx.save_for_backward(a, weight)
         ctx.strides, ctx.O, ctx.has_bias = strides, O, bias is not None
         return out
@@ -264,8 +343,8 @@ class Head(torch.autograd.Function):
     def backward(ctx, dout):
         a, weight = ctx.saved_tensors
         da, dw, db = ops.head_bwd(dout.contiguous(), a, weight.detach(), ctx.O, *ctx.strides,
-                                  need_da=ctx.needs_input_grad[0], need_dw=ctx.needs_input_grad[1], need_db=ctx.has_bias)
-        return da, dw, (db if ctx.has_bias else None), None
+                                  need_da=ctx.needs_input_grad[0], need_dw=ctx.needs_input_grad[2], need_db=ctx.has_bias)
+        return da, None, dw, (db if ctx.has_bias else None), None
 
 
 class GanLossFn(torch.autograd.Function):

@@ -47,7 +47,7 @@ class BNAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, y, gamma, beta, bufs, act, training):
-        a, fin, count = _bn_forward(y, gamma.detach(), beta.detach(), bufs, act, training)
+        a, _, fin, count = _bn_forward(y, gamma.detach(), beta.detach(), bufs, act, training)
         ctx.save_for_backward(y, fin)
         ctx.misc = (count, act, training)
         return a

@@ -38,8 +38,8 @@ class Generator(_dcgan.Generator):
     def forward(self, z, y):
         require_cuda(z, "acgan.Generator")
         zy = torch.cat([z, y], 1)   # host-side glue on a (B, z_dim + n_class) tensor, as upstream
-        h = GF.LinearToNHWC.apply(zy, self.linear.weight, self.linear.bias, self.bottom_width, ops.ACT_NONE,
-                                  self._gp_cache, "linear")
+        h = GF.linear_to_nhwc(zy, self.linear.weight, self.linear.bias, self.bottom_width, ops.ACT_NONE,
+                              self._gp_cache, "linear")
         return self._trunk(h)
 
 
@@ -64,6 +64,6 @@ class Discriminator(_dcgan.Discriminator):
     def forward(self, x):
         require_cuda(x, "acgan.Discriminator")
         h = self._features(x)
-        out = GF.Head.apply(h, self.out_layer.weight, self.out_layer.bias, False)
-        out_aux = GF.Head.apply(h, self.out_aux.weight, self.out_aux.bias, False)
+        out = GF.with_lo(GF.Head, h, self.out_layer.weight, self.out_layer.bias, False)
+        out_aux = GF.with_lo(GF.Head, h, self.out_aux.weight, self.out_aux.bias, False)
         return out, out_aux

@@ -45,15 +45,15 @@ class Generator(nn.Module):
     def _trunk(self, h):
         for i, block in enumerate(self.blocks):
             conv, bn = block[0], block[1]
-            h = GF.ConvBlock.apply(h, conv.weight, conv.bias, bn.weight, bn.bias, bn_buffers(bn), True, ops.ACT_RELU,
-                                   self._gp_cache, "blocks.%d" % i, self.training)
+            h = GF.with_lo(GF.ConvBlock, h, conv.weight, conv.bias, bn.weight, bn.bias, bn_buffers(bn), True,
+                           ops.ACT_RELU, self._gp_cache, "blocks.%d" % i, self.training)
         last = self.out_layer[0]
-        return GF.ImageConvT.apply(h, last.weight, last.bias, ops.ACT_TANH, self._gp_cache, "out_layer")
+        return GF.with_lo(GF.ImageConvT, h, last.weight, last.bias, ops.ACT_TANH, self._gp_cache, "out_layer")
 
     def forward(self, z):
         require_cuda(z, "dcgan.Generator")
-        h = GF.LinearToNHWC.apply(z, self.linear.weight, self.linear.bias, self.bottom_width, ops.ACT_RELU,
-                                  self._gp_cache, "linear")
+        h = GF.linear_to_nhwc(z, self.linear.weight, self.linear.bias, self.bottom_width, ops.ACT_RELU,
+                              self._gp_cache, "linear")
         return self._trunk(h)
 
 
@@ -82,14 +82,14 @@ class Discriminator(nn.Module):
 
     def _features(self, x):
         first = self.blocks[0][0]
-        h = GF.ImageConv.apply(x, first.weight, first.bias, ops.ACT_LRELU, self._gp_cache, "blocks.0")
+        h = GF.image_conv(x, first.weight, first.bias, ops.ACT_LRELU, self._gp_cache, "blocks.0")
         for i in range(1, len(self.blocks)):
             conv, bn = self.blocks[i][0], self.blocks[i][1]
-            h = GF.ConvBlock.apply(h, conv.weight, conv.bias, bn.weight, bn.bias, bn_buffers(bn), False, ops.ACT_LRELU,
-                                   self._gp_cache, "blocks.%d" % i, self.training)
+            h = GF.with_lo(GF.ConvBlock, h, conv.weight, conv.bias, bn.weight, bn.bias, bn_buffers(bn), False,
+                           ops.ACT_LRELU, self._gp_cache, "blocks.%d" % i, self.training)
         return h
 
     def forward(self, x):
         require_cuda(x, "dcgan.Discriminator")
         h = self._features(x)
-        return GF.Head.apply(h, self.out_layer.weight, self.out_layer.bias, False)
+        return GF.with_lo(GF.Head, h, self.out_layer.weight, self.out_layer.bias, False)

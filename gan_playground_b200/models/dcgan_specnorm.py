@@ -48,16 +48,16 @@ class Generator(nn.Module):
 
     def forward(self, z):
         require_cuda(z, "dcgan_specnorm.Generator")
-        h = GF.LinearToNHWC.apply(z, self.linear.weight, self.linear.bias, self.bottom_width, ops.ACT_RELU,
-                                  self._gp_cache, "linear")
+        h = GF.linear_to_nhwc(z, self.linear.weight, self.linear.bias, self.bottom_width, ops.ACT_RELU,
+                              self._gp_cache, "linear")
         for i, block in enumerate(self.blocks):
             conv, bn = block[0], block[1]
             w = sn_weight(conv, 1, self.training)
-            h = GF.ConvBlock.apply(h, w, conv.bias, bn.weight, bn.bias, bn_buffers(bn), True, ops.ACT_RELU,
-                                   self._gp_cache, "blocks.%d" % i, self.training)
+            h = GF.with_lo(GF.ConvBlock, h, w, conv.bias, bn.weight, bn.bias, bn_buffers(bn), True, ops.ACT_RELU,
+                           self._gp_cache, "blocks.%d" % i, self.training)
         last = self.out_layer[0]
-        return GF.ImageConvT.apply(h, sn_weight(last, 1, self.training), last.bias, ops.ACT_TANH, self._gp_cache,
-                                   "out_layer")
+        return GF.with_lo(GF.ImageConvT, h, sn_weight(last, 1, self.training), last.bias, ops.ACT_TANH, self._gp_cache,
+                          "out_layer")
 
 
 class Discriminator(nn.Module):
@@ -84,13 +84,12 @@ class Discriminator(nn.Module):
     def forward(self, x, out_hidden=False):
         require_cuda(x, "dcgan_specnorm.Discriminator")
         first = self.blocks[0][0]
-        h = GF.ImageConv.apply(x, sn_weight(first, 0, self.training), first.bias, ops.ACT_LRELU, self._gp_cache,
-                               "blocks.0")
+        h = GF.image_conv(x, sn_weight(first, 0, self.training), first.bias, ops.ACT_LRELU, self._gp_cache, "blocks.0")
         for i in range(1, len(self.blocks)):
             conv, bn = self.blocks[i][0], self.blocks[i][1]
-            h = GF.ConvBlock.apply(h, sn_weight(conv, 0, self.training), conv.bias, bn.weight, bn.bias,
-                                   bn_buffers(bn), False, ops.ACT_LRELU, self._gp_cache, "blocks.%d" % i, self.training)
-        out = GF.Head.apply(h, self.out_layer.weight, self.out_layer.bias, True)
+            h = GF.with_lo(GF.ConvBlock, h, sn_weight(conv, 0, self.training), conv.bias, bn.weight, bn.bias,
+                           bn_buffers(bn), False, ops.ACT_LRELU, self._gp_cache, "blocks.%d" % i, self.training)
+        out = GF.with_lo(GF.Head, h, self.out_layer.weight, self.out_layer.bias, True)
         if out_hidden:
             # upstream hands back the NCHW fp32 feature map; this is a layout change at the API boundary only
             return out, h.permute(0, 3, 1, 2).float()

@@ -112,7 +112,7 @@ class ResNetGenerator(nn.Module):
 
     def forward(self, z, y):
         require_cuda(z, "sngan_projection.ResNetGenerator")
-        h = GF.LinearToNHWC.apply(z, self.l1.weight, self.l1.bias, self.bottom_width, ops.ACT_NONE, self._gp_cache, "l1")
+        h = GF.linear_to_nhwc(z, self.l1.weight, self.l1.bias, self.bottom_width, ops.ACT_NONE, self._gp_cache, "l1")
         if y is not None:
             y = y.contiguous()
         for block in (self.block2, self.block3, self.block4, self.block5):

@@ -116,23 +116,40 @@ def _timed(name, flops, fn):
 _TAPS_PER_OUT = {KIND_CONV_K4S2: 16, KIND_CONVT_K4S2: 4, KIND_CONV_K3S1: 9, KIND_CONV_K1S1: 1}
 
 
-def conv_fwd(x, wp, bias, kind, Hout, Wout, act=ACT_NONE, stats=None, flops=None, residual=None):
+def conv_fwd(x, wp, bias, kind, Hout, Wout, act=ACT_NONE, stats=None, flops=None, residual=None, x_lo=None,
+             out_mode="bf16"):
     """x: bf16 (NB, Hin, Win, Cin); wp: bf16 [Nout, taps*Cin]; returns bf16 (NB, Hout, Wout, Nout).
     stats: optional fp32 [2, Nout] zeroed tensor receiving per-channel sum / sum of squares.
-    flops: algorithmic FLOPs of this call when they differ from the padded GEMM shape (image layers)."""
+    flops: algorithmic FLOPs of this call when they differ from the padded GEMM shape (image layers).
+    bf16x3 mode: x_lo = low halves of x and wp = [Nout, 2*taps*Cin] (hi | lo).
+    out_mode: "bf16" -> bf16 tensor; "split" -> (hi, lo) bf16 pair; "f32" -> fp32 tensor."""
     _chk(x, torch.bfloat16, "x")
     _chk(wp, torch.bfloat16, "wp")
     NB, Hin, Win, Cin = x.shape
     Nout = wp.shape[0]
-    out = torch.empty((NB, Hout, Wout, Nout), device=x.device, dtype=torch.bfloat16)
+    shape = (NB, Hout, Wout, Nout)
+    out = out_lo = out_f32 = None
+    if out_mode == "f32":
+        out_f32 = torch.empty(shape, device=x.device, dtype=torch.float32)
+    else:
+        out = torch.empty(shape, device=x.device, dtype=torch.bfloat16)
+        if out_mode == "split":
+            out_lo = torch.empty(shape, device=x.device, dtype=torch.bfloat16)
     if bias is not None:
         _chk(bias, torch.float32, "bias")
+    if x_lo is not None:
+        _chk(x_lo, torch.bfloat16, "x_lo")
     p = ConvFwd(_p(x), _p(wp), _p(bias), _p(out), _p(stats[0]) if stats is not None else None,
-                _p(stats[1]) if stats is not None else None, NB, Hin, Win, Cin, Hout, Wout, Nout, kind, act, _p(residual))
+                _p(stats[1]) if stats is not None else None, NB, Hin, Win, Cin, Hout, Wout, Nout, kind, act, _p(residual),
+                _p(x_lo), _p(out_lo), _p(out_f32))
     if flops is None:
         flops = 2.0 * NB * Hout * Wout * Nout * Cin * _TAPS_PER_OUT[kind]
-    _timed("conv_fwd kind%d %dx%dx%d C%d->%d" % (kind, NB, Hout, Wout, Cin, Nout), flops,
-           lambda: check(_fn("gp_conv_fwd")(ctypes.addressof(p), _stream()), "gp_conv_fwd"))
+    _timed("conv_fwd kind%d %dx%dx%d C%d->%d%s" % (kind, NB, Hout, Wout, Cin, Nout, " x3" if x_lo is not None else ""),
+           flops, lambda: check(_fn("gp_conv_fwd")(ctypes.addressof(p), _stream()), "gp_conv_fwd"))
+    if out_mode == "f32":
+        return out_f32
+    if out_mode == "split":
+        return out, out_lo
     return out
 
 
@@ -493,3 +510,106 @@ def proj_head_bwd(dout, h, w, E, labels, n_classes):
     check(_fn("gp_proj_head_bwd")(_p(dout), _p(h), _p(w), _p(E), _p(labels), _p(dh), _p(dw), _p(db), _p(dE), NB, C,
                                   n_classes, _stream()), "gp_proj_head_bwd")
     return dh, dw, db, dE
+
+
+# ------------------------------------------------------------------------------------------------ bf16x3 precision mode
+_SIGS.update({
+    "gp_split_matrix": [_vp, _vp, _i, _i, _i, _i, _i, _ll, _ll, _i, _ll, _vp],
+    "gp_split_conv_weight": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "gp_bn_stats_f32": [_vp, _ll, _i, _vp, _vp, _vp],
+    "gp_bn_apply_act_split": [_vp, _vp, _vp, _ll, _i, _vp, _vp, _i, _vp],
+    "gp_bn_bwd_reduce_f32": [_vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "gp_bn_bwd_apply_f32": [_vp, _vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _vp],
+    "gp_im2col_k4s2_split": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "gp_col2im_k4s2_f32": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "gp_head_fwd_split": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _vp],
+})
+
+
+def split_rows(src, R, K, Kp, s_r, s_k, perm=1):
+    """fp32 matrix -> (hi, lo) bf16 pair, each [R, Kp] (activation-side operand of a bf16x3 GEMM)."""
+    _chk(src, torch.float32, "src")
+    dst = torch.empty((2, R, Kp), device=src.device, dtype=torch.bfloat16)
+    check(_fn("gp_split_matrix")(_p(src), _p(dst), R, K, R, Kp, Kp, s_r, s_k, perm, R * Kp, _stream()), "gp_split_matrix")
+    return dst[0], dst[1]
+
+
+def split_weight_matrix(src, R, K, Rpad, Kp, s_r, s_k, perm=1):
+    """fp32 matrix -> bf16 [Rpad, 2*Kp]: hi block | lo block per row (weight-side operand of a bf16x3 GEMM)."""
+    _chk(src, torch.float32, "src")
+    dst = torch.empty((Rpad, 2 * Kp), device=src.device, dtype=torch.bfloat16)
+    check(_fn("gp_split_matrix")(_p(src), _p(dst), R, K, Rpad, 2 * Kp, Kp, s_r, s_k, perm, Kp, _stream()), "gp_split_matrix")
+    return dst
+
+
+def split_conv_weight(w, n_dim):
+    """w fp32 (D0, D1, kh, kw) -> bf16 [N, 2*taps*C] (hi | lo)."""
+    _chk(w, torch.float32, "w")
+    D0, D1 = w.shape[0], w.shape[1]
+    taps = w.shape[2] * w.shape[3]
+    N, C = (D0, D1) if n_dim == 0 else (D1, D0)
+    dst = torch.empty((N, 2 * taps * C), device=w.device, dtype=torch.bfloat16)
+    check(_fn("gp_split_conv_weight")(_p(w), _p(dst), D0, D1, taps, n_dim, _stream()), "gp_split_conv_weight")
+    return dst
+
+
+def bn_stats_f32(y):
+    _chk(y, torch.float32, "y")
+    C = y.shape[-1]
+    st = torch.zeros((2, C), device=y.device, dtype=torch.float32)
+    check(_fn("gp_bn_stats_f32")(_p(y), y.numel() // C, C, _p(st[0]), _p(st[1]), _stream()), "gp_bn_stats_f32")
+    return st
+
+
+def bn_apply_act_split(y, fin, act):
+    _chk(y, torch.float32, "y")
+    C = y.shape[-1]
+    hi = torch.empty(y.shape, device=y.device, dtype=torch.bfloat16)
+    lo = torch.empty(y.shape, device=y.device, dtype=torch.bfloat16)
+    check(_fn("gp_bn_apply_act_split")(_p(y), _p(hi), _p(lo), y.numel() // C, C, _p(fin[2]), _p(fin[3]), act, _stream()),
+          "gp_bn_apply_act_split")
+    return hi, lo
+
+
+def bn_bwd_reduce_f32(da, y, fin, act):
+    _chk(da, torch.bfloat16, "da")
+    _chk(y, torch.float32, "y")
+    C = y.shape[-1]
+    red = torch.zeros((2, C), device=y.device, dtype=torch.float32)
+    check(_fn("gp_bn_bwd_reduce_f32")(_p(da), _p(y), y.numel() // C, C, _p(fin[2]), _p(fin[3]), _p(fin[0]), _p(fin[1]), act,
+                                      _p(red[0]), _p(red[1]), _stream()), "gp_bn_bwd_reduce_f32")
+    return red
+
+
+def bn_bwd_apply_f32(da, y, fin, red, count, act):
+    C = y.shape[-1]
+    dy = torch.empty(y.shape, device=y.device, dtype=torch.bfloat16)
+    check(_fn("gp_bn_bwd_apply_f32")(_p(da), _p(y), _p(dy), y.numel() // C, C, _p(fin[2]), _p(fin[3]), _p(fin[0]), _p(fin[1]),
+                                     _p(red[0]), _p(red[1]), float(count), act, _stream()), "gp_bn_bwd_apply_f32")
+    return dy
+
+
+def im2col_k4s2_split(img):
+    _chk(img, torch.float32, "img")
+    NB, ch, Hi, Wi = img.shape
+    col = torch.empty((2, NB, Hi // 2, Wi // 2, 64), device=img.device, dtype=torch.bfloat16)
+    check(_fn("gp_im2col_k4s2_split")(_p(img), _p(col[0]), _p(col[1]), NB, ch, Hi, Wi, _stream()), "gp_im2col_k4s2_split")
+    return col[0], col[1]
+
+
+def col2im_k4s2_f32(col, bias, ch, act):
+    _chk(col, torch.float32, "col")
+    NB, Ho, Wo, _ = col.shape
+    img = torch.empty((NB, ch, 2 * Ho, 2 * Wo), device=col.device, dtype=torch.float32)
+    check(_fn("gp_col2im_k4s2_f32")(_p(col), _p(bias), _p(img), NB, ch, 2 * Ho, 2 * Wo, act, _stream()), "gp_col2im_k4s2_f32")
+    return img
+
+
+def head_fwd_split(a_hi, a_lo, w, bias, O, s_o, s_c, s_hw):
+    _chk(a_hi, torch.bfloat16, "a_hi")
+    _chk(a_lo, torch.bfloat16, "a_lo")
+    NB, H, W, C = a_hi.shape
+    out = torch.empty((NB, O), device=a_hi.device, dtype=torch.float32)
+    check(_fn("gp_head_fwd_split")(_p(a_hi), _p(a_lo), _p(w), _p(bias), _p(out), NB, H * W, C, O, s_o, s_c, s_hw, _stream()),
+          "gp_head_fwd_split")
+    return out

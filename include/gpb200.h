@@ -64,6 +64,10 @@ typedef struct {
   int32_t act;            /* GP_ACT_NONE / RELU / LRELU (tanh lives in gp_col2im_k4s2) */
   const void* residual;   /* optional bf16 tensor with the layout of `out`, added before the activation
                              (residual blocks of models/sngan_projection.py:66,136); NULL = none */
+  /* bf16x3 forward precision mode (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, fp32 accumulate): */
+  const void* in_lo;      /* low halves of the input (same layout as `in`); then w is [Nout][2][taps][Cin] (hi | lo) */
+  void* out_lo;           /* optional: also write bf16(v - bf16(v)) here (hi/lo output pair)                        */
+  float* out_f32;         /* optional: write fp32 here instead of bf16 `out` (pre-BatchNorm outputs)                */
 } gp_conv_fwd_t;
 int gp_conv_fwd(const gp_conv_fwd_t* p, void* stream);
 
@@ -212,6 +216,29 @@ int gp_proj_head_fwd(const float* h, const float* w, const float* b, const float
                      int NB, int C, void* stream);
 int gp_proj_head_bwd(const float* dout, const float* h, const float* w, const float* E, const long long* labels,
                      float* dh, float* dw, float* db, float* dE, int NB, int C, int n_classes, void* stream);
+
+/* ---- "bf16x3" forward precision mode: the forward GEMMs consume hi/lo bf16 pairs
+ * (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo) and pre-BatchNorm outputs stay fp32; these kernels produce / consume those formats.
+ * gp_split_matrix     : like gp_pack_matrix, writing hi at dst[r*ld + k] and lo at dst[lo_off + r*ld + k] (k < width)
+ * gp_split_conv_weight: like gp_pack_conv_weight, dst bf16 [N][2][taps][C] (hi block | lo block per row)
+ * gp_bn_*_f32 / _split : the BatchNorm kernels above with y in fp32 and the activation written as a hi/lo pair
+ * gp_im2col_k4s2_split / gp_col2im_k4s2_f32 / gp_head_fwd_split: image-side layers and head on those formats. */
+int gp_split_matrix(const float* src, void* dst, int R, int K, int Rpad, int ld, int width, long long s_r, long long s_k,
+                    int perm, long long lo_off, void* stream);
+int gp_split_conv_weight(const float* src, void* dst, int D0, int D1, int taps, int n_dim, void* stream);
+int gp_bn_stats_f32(const float* y, long long P, int C, float* sum, float* sumsq, void* stream);
+int gp_bn_apply_act_split(const float* y, void* out_hi, void* out_lo, long long P, int C, const float* scale,
+                          const float* shift, int act, void* stream);
+int gp_bn_bwd_reduce_f32(const void* da, const float* y, long long P, int C, const float* scale, const float* shift,
+                         const float* mean, const float* rstd, int act, float* sum_dz, float* sum_dzx, void* stream);
+int gp_bn_bwd_apply_f32(const void* da, const float* y, void* dy, long long P, int C, const float* scale,
+                        const float* shift, const float* mean, const float* rstd, const float* sum_dz,
+                        const float* sum_dzx, double count, int act, void* stream);
+int gp_im2col_k4s2_split(const float* img, void* col_hi, void* col_lo, int NB, int ch, int Hi, int Wi, void* stream);
+int gp_col2im_k4s2_f32(const float* col, const float* bias, float* img, int NB, int ch, int Hi, int Wi, int act,
+                       void* stream);
+int gp_head_fwd_split(const void* a_hi, const void* a_lo, const float* w, const float* bias, float* out, int NB, int HW,
+                      int C, int O, long long s_o, long long s_c, long long s_hw, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,81 @@
+"""The two forward precision modes against the fp32 CPU oracle at the BASELINE width (DCGAN-64, ngf=ndf=64, batch 32),
+with BASELINE.json's north_star bars: per-boundary activation max-rel-error <= 1e-2, gradient cosine >= 0.999, losses
+within 2 %.  "bf16x3" (default) must meet all of them; "bf16" is the fast mode whose G-step cosine is bounded near 0.97
+by forward operand rounding — its thresholds document what it reaches."""
+import os
+
+import pytest
+import torch
+
+from test_gpu_dcgan import global_cos, quiet, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def reference_step():
+    from gan_playground_b200.models import dcgan
+    from oracle import gan_oracle as O
+
+    torch.manual_seed(0)
+    netG, netD = quiet(lambda: dcgan.Generator()), quiet(lambda: dcgan.Discriminator())
+    sd_g = {k: v.clone() for k, v in netG.state_dict().items()}
+    sd_d = {k: v.clone() for k, v in netD.state_dict().items()}
+    gen = torch.Generator().manual_seed(1)
+    B = 32
+    x = torch.rand(B, 3, 64, 64, generator=gen) * 2 - 1
+    z1, z2 = torch.randn(B, 100, generator=gen), torch.randn(B, 100, generator=gen)
+    torch.set_num_threads(os.cpu_count())
+    ref = O.dcgan_step_grads(sd_g, sd_d, x, z1, z2)
+    return sd_g, sd_d, x, z1, z2, ref
+
+
+BARS = {
+    #            act    cos D-real  cos D-fake  cos G-step
+    "bf16x3": (1e-2, 0.999, 0.999, 0.999),
+    "bf16": (2e-2, 0.999, 0.99, 0.95),
+}
+
+
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+def test_dcgan64_step_meets_precision_bars(mode, reference_step):
+    from gan_playground_b200 import config
+    from gan_playground_b200.criterion import GANLoss
+    from gan_playground_b200.models import dcgan
+
+    sd_g, sd_d, x, z1, z2, ref = reference_step
+    act_bar, c_real, c_fake, c_g = BARS[mode]
+    prev = config.precision()
+    config.set_precision(mode)
+    try:
+        netG, netD = quiet(lambda: dcgan.Generator()).cuda(), quiet(lambda: dcgan.Discriminator()).cuda()
+        netG.load_state_dict(sd_g), netD.load_state_dict(sd_d)
+        crit = GANLoss("vanilla", 0.9, 0.1, 0.9).cuda()
+        out = netD(x.cuda())
+        loss = crit(out, True)
+        loss.backward()
+        e1 = relerr(out, ref["d_real"])
+        g1 = global_cos(netD.named_parameters(), ref["d_grads_real"])
+        l1 = abs(loss.item() - ref["loss_real"].item()) / ref["loss_real"].item()
+        fake = netG(z1.cuda())
+        e2 = relerr(fake, ref["fake1"])
+        netD.zero_grad()
+        out = netD(fake.detach())
+        lf = crit(out, False)
+        lf.backward()
+        e3 = relerr(out, ref["d_fake"])
+        g2 = global_cos(netD.named_parameters(), ref["d_grads_fake"])
+        netG.zero_grad(), netD.zero_grad()
+        out = netD(netG(z2.cuda()))
+        lg = crit(out, False, True)
+        lg.backward()
+        e4 = relerr(out, ref["d_g"])
+        g3 = global_cos(netG.named_parameters(), ref["g_grads"])
+        l3 = abs(lg.item() - ref["loss_g"].item()) / ref["loss_g"].item()
+        print("\n[%s] act err: D(x) %.2e  G(z) %.2e  D(G(z1)) %.2e  D(G(z2)) %.2e | cos: D-real %.6f  D-fake %.6f  G-step %.6f"
+              " | loss rel: %.2e %.2e" % (mode, e1, e2, e3, e4, g1, g2, g3, l1, l3))
+        assert max(e1, e2, e3, e4) < act_bar
+        assert g1 > c_real and g2 > c_fake and g3 > c_g
+        assert l1 < 0.02 and l3 < 0.02
+    finally:
+        config.set_precision(prev)
