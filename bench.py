@@ -144,13 +144,15 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: global batch 1024 sharded over ranks; weak: 1024 images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of one CUDA graph replay per step")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
     args.warmup = max(args.warmup, 3)
 
-    from gan_playground_b200 import _lib, ops, parallel
+    from gan_playground_b200 import _lib, config, ops, parallel
     from gan_playground_b200.criterion import GANLoss
+    from gan_playground_b200.engine import DcganStep
     from gan_playground_b200.models import dcgan
 
     rank, world = parallel.init()
@@ -170,42 +172,21 @@ def main():
         netD = dcgan.Discriminator().to(dev)
     parallel.broadcast_module(netG)
     parallel.broadcast_module(netD)
-    optG = torch.optim.Adam(netG.parameters(), lr=4e-4, betas=(0.5, 0.999))
-    optD = torch.optim.Adam(netD.parameters(), lr=1e-4, betas=(0.5, 0.999))
+    use_graph = not args.no_graph
+    optG = torch.optim.Adam(netG.parameters(), lr=4e-4, betas=(0.5, 0.999), capturable=use_graph)
+    optD = torch.optim.Adam(netD.parameters(), lr=1e-4, betas=(0.5, 0.999), capturable=use_graph)
     crit = GANLoss('vanilla', target_real_label=0.9, target_fake_label=0.1, target_fake_G_label=0.9).to(dev)
     netG.train(), netD.train()
-    bucketD, bucketG = parallel.GradBucket(netD), parallel.GradBucket(netG)
+    # loop body of main_dcgan.py:68-95 (+ DP gradient all-reduce before each optimiser step), eager or as one CUDA graph
+    runner = DcganStep(netG, netD, crit, optG, optD, per_gpu, Z_DIM, dev, use_graph=use_graph)
 
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     x_dev = torch.rand(per_gpu, 3, 64, 64, device=dev, generator=gen) * 2 - 1
     x_host = x_dev.cpu().pin_memory()
     z_host = torch.randn(2, per_gpu, Z_DIM).pin_memory()
 
-    def step(inputs, z1=None, z2=None):
-        """Loop body of main_dcgan.py:68-95 (+ the DP gradient all-reduce before each optimiser step)."""
-        bucketD.attach()                                       # optD.zero_grad()
-        outD = netD(inputs)
-        Dx = outD.mean().item()
-        lossD_real = crit(outD, True)
-        lossD_real.backward()
-        z = z1 if z1 is not None else torch.randn(per_gpu, Z_DIM, device=dev)
-        outG = netG(z)
-        outD = netD(outG.detach())
-        Dgz1 = outD.mean().item()
-        lossD_fake = crit(outD, False)
-        lossD_fake.backward()
-        bucketD.all_reduce_mean()
-        optD.step()
-        bucketG.attach()                                       # optG.zero_grad()
-        z = z2 if z2 is not None else torch.randn(per_gpu, Z_DIM, device=dev)
-        outG = netG(z)
-        outD = netD(outG)
-        Dgz2 = outD.mean().item()
-        lossG = crit(outD, False, True)
-        lossG.backward()
-        bucketG.all_reduce_mean()
-        optG.step()
-        return lossD_real, lossD_fake, lossG, Dx, Dgz1, Dgz2
+    def step(inputs):
+        return runner.step(inputs)
 
     def barrier():
         if world > 1:
@@ -233,32 +214,33 @@ def main():
         time.sleep(0.5)
     for _ in range(args.warmup):
         step(x_dev)
-    l0 = _lib.launch_count()
     total_ms = timed(lambda: step(x_dev), args.steps)
-    launches = _lib.launch_count() - l0
     ms_per_step = total_ms / args.steps
 
     # ---- end-to-end: inputs start in pinned host memory, results are read back on the host, every step
     last = {}
 
     def e2e_step():
+        # the step's images come from pinned host memory every step; its six logged scalars go back to the host
         xin = x_host.to(dev, non_blocking=True)
-        zz = z_host.to(dev, non_blocking=True)
-        r = step(xin, zz[0], zz[1])
-        last["losses"] = (r[0].item(), r[1].item(), r[2].item())
+        r = step(xin)
+        last["losses"] = tuple(r[:3])
 
     for _ in range(2):
         e2e_step()
     e2e_ms = timed(e2e_step, args.steps) / args.steps
     clocks = sampler.stop() if rank == 0 else None
-    h2d = x_host.numel() * 4 + z_host.numel() * 4
-    d2h = 6 * 4  # three .item() means + three loss scalars
+    h2d = x_host.numel() * 4
+    d2h = 6 * 4  # three D-output means + three loss scalars
 
     # ---- roofline of the dominant kernel family: tcgen05 implicit-GEMM convs, timed per launch with CUDA events
+    # (one eager step: same kernels as the graph replays, launched one by one so they can be bracketed by events)
     prof = ops.GemmProfiler()
+    l0 = _lib.launch_count()
     with prof:
-        step(x_dev)
+        runner.step_eager(x_dev)
     torch.cuda.synchronize()
+    launches = (_lib.launch_count() - l0) * args.steps   # own kernels per step x timed steps
     gemm = prof.summary()
     peaks, peaks_src = load_peaks()
     peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
@@ -276,7 +258,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": global_batch, "per_gpu_batch": per_gpu,
-                       "parallelism": "dp%d" % world,
+                       "parallelism": "dp%d" % world, "precision": config.precision(), "cuda_graph": use_graph,
                        "l2": "no flush needed: per-step working set (~3.4 GB of activations at 1024 img/GPU) >> 126 MB L2"},
             "steps_per_sec": 1e3 / ms_per_step,
             "tflops_minimal_step": FLOPS_PER_IMG * global_batch / (ms_per_step * 1e-3) / 1e12,

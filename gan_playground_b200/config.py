@@ -29,3 +29,17 @@ def set_precision(p):
 
 def x3():
     return _precision == "bf16x3"
+
+
+# BatchNorm batch statistics accumulated in the GEMM epilogue from the fp32 accumulators (one fewer pass over the conv
+# output per BN layer). GP_FUSED_STATS=0 falls back to the standalone statistics kernel.
+_fused_stats = os.environ.get("GP_FUSED_STATS", "1") != "0"
+
+
+def fused_stats():
+    return _fused_stats
+
+
+def set_fused_stats(on):
+    global _fused_stats
+    _fused_stats = bool(on)

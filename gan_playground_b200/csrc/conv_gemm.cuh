@@ -375,8 +375,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 if (col0 + g * 8 < p.N) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) atomicAdd(drow + col0 + g * 8 + e, __uint_as_float(r[g * 8 + e]));
+                  // 16-byte vector reductions (red.global.add.v4.f32): 4x fewer L2 atomic transactions than scalar
+                  red_add_v4(drow + col0 + g * 8, r[g * 8], r[g * 8 + 1], r[g * 8 + 2], r[g * 8 + 3]);
+                  red_add_v4(drow + col0 + g * 8 + 4, r[g * 8 + 4], r[g * 8 + 5], r[g * 8 + 6], r[g * 8 + 7]);
                 }
               }
             }

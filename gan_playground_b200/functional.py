@@ -48,16 +48,17 @@ def with_lo(fn, h, *args):
     return out
 
 
-def _bn_forward(y, gamma, beta, bufs, act, training=True):
+def _bn_forward(y, gamma, beta, bufs, act, training=True, st=None):
     """y: pre-BN conv output, NHWC bf16 (fp32 in bf16x3 mode). Returns (a, a_lo, fin[4,C], count).
     training: batch statistics (all-reduced over ranks) + running-stat update, as nn.BatchNorm2d.train();
-    eval: normalise with the running statistics."""
+    eval: normalise with the running statistics. st: [2, C] sums already produced by the conv epilogue."""
     C = y.shape[-1]
     count = (y.numel() // C) * parallel.world_size()
     rm, rv, nbt = bufs if bufs is not None else (None, None, None)
     f32 = y.dtype == torch.float32
     if training or rm is None:
-        st = ops.bn_stats_f32(y) if f32 else ops.bn_stats(y)
+        if st is None:
+            st = ops.bn_stats_f32(y) if f32 else ops.bn_stats(y)
         parallel.all_reduce_sum_(st)
         fin = ops.bn_finalize(st, count, gamma, beta, rm, rv, nbt, BN_EPS, BN_MOMENTUM)
     else:
@@ -104,19 +105,25 @@ class ConvBlock(torch.autograd.Function):
             Ho, Wo, kind = H // 2, W // 2, ops.KIND_CONV_K4S2
         has_bn = gamma is not None or bufs is not None
         b = bias.detach() if bias is not None else None
+        ctx.set_materialize_grads(False)
+        # BatchNorm batch statistics come out of the GEMM epilogue (fp32 accumulators), not from a second pass over y
+        Cout = weight.shape[1] if transposed else weight.shape[0]
+        st = None
+        if has_bn and training and config.fused_stats() and Cout <= 2048:
+            st = torch.zeros((2, Cout), device=x.device, dtype=torch.float32)
         if x3:
             wp = cache.get((key, "fwd3"), weight, lambda: ops.split_conv_weight(weight.detach(), n_dim))
             if x_lo is None:
                 x_lo = torch.zeros_like(x)
-            y = ops.conv_fwd(x, wp, b, kind, Ho, Wo, ops.ACT_NONE if has_bn else act, x_lo=x_lo,
+            y = ops.conv_fwd(x, wp, b, kind, Ho, Wo, ops.ACT_NONE if has_bn else act, stats=st, x_lo=x_lo,
                              out_mode="f32" if has_bn else "split")
         else:
             wp = cache.get((key, "fwd"), weight, lambda: ops.pack_conv_weight(weight.detach(), n_dim))
-            y = ops.conv_fwd(x, wp, b, kind, Ho, Wo, ops.ACT_NONE if has_bn else act)
+            y = ops.conv_fwd(x, wp, b, kind, Ho, Wo, ops.ACT_NONE if has_bn else act, stats=st)
         ctx.transposed, ctx.act, ctx.has_bn, ctx.cache, ctx.key = transposed, act, has_bn, cache, key
         if has_bn:
             a, a_lo, fin, count = _bn_forward(y, gamma.detach() if gamma is not None else None,
-                                              beta.detach() if beta is not None else None, bufs, act, training)
+                                              beta.detach() if beta is not None else None, bufs, act, training, st)
             ctx.count, ctx.training = count, training
             ctx.save_for_backward(x, weight, y, fin)
         else:
@@ -128,6 +135,8 @@ class ConvBlock(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, da, _unused=None):
+        if da is None:
+            return (None,) * 12
         da = da.contiguous()
         if ctx.has_bn:
             x, weight, y, fin = ctx.saved_tensors
@@ -169,6 +178,7 @@ class LinearToNHWC(torch.autograd.Function):
         HW = bw * bw
         C = O // HW
         Kp = (K + 7) // 8 * 8
+        ctx.set_materialize_grads(False)
         zc = z.detach().contiguous()
         # bias in NHWC-flatten order: dst[(s % HW)*C + s // HW] = bias[s]
         bp = cache.get((key, "bias"), bias, lambda: ops.unpack_matrix(bias.detach(), (O,), O, 1, 1, 1, 1, perm=C))
@@ -192,6 +202,8 @@ class LinearToNHWC(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, da, _unused=None):
+        if da is None:
+            return (None,) * 7
         zb, a, weight = ctx.saved_tensors
         B, K, O, HW, C, Kp, act = ctx.dims
         da = da.contiguous().view(B, 1, 1, O)
@@ -225,6 +237,7 @@ class ImageConv(torch.autograd.Function):
         NB, ch, H, W = x.shape
         Cout = weight.shape[0]
         fl = 2.0 * NB * (H // 2) * (W // 2) * Cout * ch * 16
+        ctx.set_materialize_grads(False)
         if config.x3():
             col, col_lo = ops.im2col_k4s2_split(x.detach())
             wp = cache.get((key, "fwd3"), weight,
@@ -237,21 +250,21 @@ class ImageConv(torch.autograd.Function):
             wp = cache.get((key, "fwd"), weight,
                            lambda: ops.pack_matrix(weight.detach(), Cout, ch * 16, Cout, 64, ch * 16, 1))
             a, a_lo = ops.conv_fwd(col, wp, bias.detach(), ops.KIND_CONV_K1S1, H // 2, W // 2, act, flops=fl), None
-        ctx.save_for_backward(x, weight, a)
-        ctx.misc = (act, cache, key)
+        ctx.save_for_backward(col, weight, a)   # the im2col buffer (hi half) is kept for wgrad instead of rebuilt
+        ctx.misc = (act, cache, key, (NB, ch, H, W))
         return a, a_lo
 
     @staticmethod
     def backward(ctx, da, _unused=None):
-        x, weight, a = ctx.saved_tensors
-        act, cache, key = ctx.misc
-        NB, ch, H, W = x.shape
+        if da is None:
+            return (None,) * 6
+        col, weight, a = ctx.saved_tensors
+        act, cache, key, (NB, ch, H, W) = ctx.misc
         Cout = weight.shape[0]
         fl = 2.0 * NB * (H // 2) * (W // 2) * Cout * ch * 16
         dy = ops.act_bwd(da.contiguous(), a, act) if act != ops.ACT_NONE else da.contiguous()
         dweight = dbias = dx = None
         if ctx.needs_input_grad[1]:
-            col = ops.im2col_k4s2(x)
             dwp = ops.conv_wgrad(dy, col, ops.KIND_CONV_K1S1, 1, flops=fl)  # [Cout][1][64]
             dweight = ops.unpack_matrix(dwp.view(Cout, 64), weight.shape, Cout, ch * 16, 64, ch * 16, 1)
         if ctx.needs_input_grad[2]:
