@@ -98,8 +98,7 @@ static int launch_cfg(const ConvGemmParams& prm, int grid, cudaStream_t st) {
 }
 
 template <int MODE>
-static int launch(const ConvGemmParams& prm, int bn, int mt, int num_tiles, cudaStream_t st) {
-  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+static int launch(const ConvGemmParams& prm, int bn, int mt, int grid, cudaStream_t st) {
   if (grid <= 0) return GP_OK;
   if (bn == 256) return launch_cfg<MODE, 256, 1>(prm, grid, st);
   if (bn == 128) return mt == 2 ? launch_cfg<MODE, 128, 2>(prm, grid, st) : launch_cfg<MODE, 128, 1>(prm, grid, st);
@@ -263,7 +262,8 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
   GP_REQUIRE((a->col_sum == nullptr) == (a->col_sumsq == nullptr), "gp_conv_fwd: col_sum and col_sumsq go together");
   const int mtiles = ((a->NB + prm.Nt - 1) / prm.Nt) * (prm.Hs / prm.Ht) * (prm.Ws / prm.Wt);
   const int ntn = (a->Nout + bn - 1) / bn;
-  return launch<MODE_FWD>(prm, bn, mt_sub, prm.n_phases * mtiles * ntn, as_stream(stream));
+  const int num_tiles = prm.n_phases * mtiles * ntn;
+  return launch<MODE_FWD>(prm, bn, mt_sub, num_tiles < num_sms() ? num_tiles : num_sms(), as_stream(stream));
 }
 
 extern "C" int gp_conv_wgrad(const gp_conv_wgrad_t* a, void* stream) {
@@ -347,5 +347,10 @@ extern "C" int gp_conv_wgrad(const gp_conv_wgrad_t* a, void* stream) {
   const int per = (prm.kblocks_total + splits - 1) / splits;
   splits = (prm.kblocks_total + per - 1) / per;
   prm.splits = splits;
-  return launch<MODE_WGRAD>(prm, bn, mt_sub, splits * base_tiles, as_stream(stream));
+  // Whole tiles round-robin, the K ranges of the last partial wave cut evenly over all CTAs (WorkPlan in conv_gemm.cuh):
+  // every SM gets the same number of K steps, so the grid is always the full machine unless the problem is tiny.
+  const long long total_ksteps = (long long)base_tiles * prm.kblocks_total;
+  int grid = num_sms();
+  if (total_ksteps < 4LL * grid) grid = (int)((total_ksteps + 3) / 4);
+  return launch<MODE_WGRAD>(prm, bn, mt_sub, grid, as_stream(stream));
 }

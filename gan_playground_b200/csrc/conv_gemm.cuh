@@ -75,14 +75,17 @@ struct GemmCfg {
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStatBytes = 2 * kMaxStatCols * 4;
+  static constexpr int kBiasBytes = 2 * 256 * 4;  // double-buffered bias slice of the current / next tile
   static constexpr int kBarBytes = 256;
-  static constexpr int kBudget = 208 * 1024;  // operand ring; + statistics + barriers + alignment slack stays < 227 KB
+  static constexpr int kBudget = 204 * 1024;  // operand ring; + statistics + bias + barriers + alignment slack < 227 KB
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kAccCols = MT * BN;      // TMEM columns of one accumulator buffer
   static constexpr int kTmemCols = 2 * kAccCols;  // 128 / 256 / 512: powers of two >= 32
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStatBytes + kBarBytes + 1024;  // +1024: alignment slack
+  static constexpr int kChunks = MT * (BN / 32);  // 32-column TMEM loads per accumulator buffer and epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStatBytes + kBiasBytes + kBarBytes + 1024;  // +1024: alignment slack
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM allocation must be a power of two <= 512");
   static_assert(kStages >= 3, "pipeline too shallow");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };
 
 // Column sums over the 32 lanes of a warp for 32 per-lane values: butterfly transpose-reduce, 31 shuffles.
@@ -100,6 +103,58 @@ __device__ __forceinline__ void warp_transpose_sum32(float (&v)[32], int lane) {
   }
 }
 
+// One unit of work of a persistent CTA: an output tile and (WGRAD) the range of 64-pixel K blocks it accumulates.
+struct WorkItem {
+  int tile;
+  int kb0, kb1;
+};
+
+// Work distribution.
+//   FWD  : tiles are dealt round-robin (tile = blockIdx.x + it * gridDim.x).
+//   WGRAD: T = splits * base_tiles tiles ordered split-major (so concurrently running CTAs sweep the same pixel range
+//          and share operand tiles in L2). The first floor(T / G) * G tiles are dealt round-robin as whole tiles; the
+//          K ranges of the remaining R < G tiles are cut into G equal pieces (each CTA gets <= 2 segments), so every
+//          SM executes the same number of MMA K steps — no partial last wave ("hybrid stream-K"); the fp32 atomic
+//          epilogue makes partial tiles free of extra bookkeeping.
+struct WorkPlan {
+  int num_items;
+  int nfull, rem_tiles, base_tiles, per, kblocks_total;
+  int num_tiles;
+
+  template <int MODE>
+  __device__ __forceinline__ WorkItem item(int it) const {
+    WorkItem w;
+    const int G = gridDim.x;
+    if constexpr (MODE == MODE_FWD) {
+      w.tile = blockIdx.x + it * G;
+      w.kb0 = 0;
+      w.kb1 = 1;
+    } else {
+      if (it < nfull) {
+        w.tile = blockIdx.x + it * G;
+        const int sp = w.tile / base_tiles;
+        w.kb0 = sp * per;
+        w.kb1 = min(w.kb0 + per, kblocks_total);
+      } else {
+        const int j = it - nfull;
+        const long long tot = (long long)rem_tiles * per;
+        const long long r0 = tot * blockIdx.x / G, r1 = tot * (blockIdx.x + 1) / G;
+        const int t = (int)(r0 / per) + j;                       // remainder tile touched by segment j
+        const long long lo = j == 0 ? r0 : (long long)t * per;
+        const long long hi = min(r1, (long long)(t + 1) * per);
+        w.tile = nfull * G + t;
+        const int sp = w.tile / base_tiles;
+        w.kb0 = sp * per + (int)(lo - (long long)t * per);
+        w.kb1 = hi > lo ? min(sp * per + (int)(hi - (long long)t * per), kblocks_total) : w.kb0;
+        if (w.kb1 < w.kb0) w.kb1 = w.kb0;
+      }
+    }
+    return w;
+  }
+};
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 template <int MODE, int BN, int MT>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using Cfg = GemmCfg<BN, MT>;
@@ -107,7 +162,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   float* s_stat = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStatBytes);
+  float* s_bias = s_stat + 2 * kMaxStatCols;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStatBytes + Cfg::kBiasBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -145,23 +201,32 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   // ---- tile bookkeeping shared by all roles
   const int wtiles = p.Ws / p.Wt, htiles = p.Hs / p.Ht;
   const int ntiles_n = (p.N + BN - 1) / BN;
-  int num_tiles, ksteps_fwd = 0, cchunks = 0, mtiles = 0, kb_per_split = 0;
+  int ksteps_fwd = 0, cchunks = 0, mtiles = 0;
+  WorkPlan plan;
   if constexpr (MODE == MODE_FWD) {
     mtiles = ((p.NB + p.Nt - 1) / p.Nt) * htiles * wtiles;
     cchunks = (p.C + kBlockK - 1) / kBlockK;
     ksteps_fwd = p.taps_per_phase * cchunks;
-    num_tiles = p.n_phases * mtiles * ntiles_n;
+    plan.num_tiles = p.n_phases * mtiles * ntiles_n;
+    plan.num_items = plan.num_tiles > (int)blockIdx.x ? (plan.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   } else {
     mtiles = (p.M + MT * kBlockM - 1) / (MT * kBlockM);
-    kb_per_split = (p.kblocks_total + p.splits - 1) / p.splits;
-    num_tiles = p.splits * mtiles * p.taps_per_phase * ntiles_n;
+    plan.base_tiles = mtiles * p.taps_per_phase * ntiles_n;
+    plan.kblocks_total = p.kblocks_total;
+    plan.per = (p.kblocks_total + p.splits - 1) / p.splits;
+    plan.num_tiles = p.splits * plan.base_tiles;
+    plan.nfull = plan.num_tiles / gridDim.x;
+    plan.rem_tiles = plan.num_tiles - plan.nfull * gridDim.x;
+    plan.num_items = plan.nfull + (plan.rem_tiles > 0 ? 2 : 0);
   }
 
   if (warp == 0 && lane == 0) {
     // =========================== TMA producer ===========================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int it = 0; it < plan.num_items; ++it) {
+      const WorkItem wk = plan.template item<MODE>(it);
+      const int tile = wk.tile;
       if constexpr (MODE == MODE_FWD) {
         const int nt = tile % ntiles_n;
         const int mt = (tile / ntiles_n) % mtiles;
@@ -183,11 +248,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const int nt = tile % ntiles_n;
         const int tp = (tile / ntiles_n) % p.taps_per_phase;
         const int mt = (tile / (ntiles_n * p.taps_per_phase)) % mtiles;
-        const int sp = tile / (ntiles_n * p.taps_per_phase * mtiles);
         const Tap t = p.taps[tp];
-        const int kb0 = sp * kb_per_split;
-        const int kb1 = min(kb0 + kb_per_split, p.kblocks_total);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
           const int w0 = (kb % wtiles) * p.Wt;
           const int h0 = ((kb / wtiles) % htiles) * p.Ht;
           const int n0 = (kb / (wtiles * htiles)) * p.Nt;
@@ -214,18 +276,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     constexpr uint32_t a_sub = kBlockM * kBlockK * 2;  // bytes between the MT sub-tiles of A (both modes: 16 KB)
     int stage = 0;
     uint32_t phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      int ksteps;
-      if constexpr (MODE == MODE_FWD) {
-        ksteps = ksteps_fwd;
-      } else {
-        const int sp = tile / (ntiles_n * p.taps_per_phase * mtiles);
-        const int kb0 = sp * kb_per_split;
-        ksteps = min(kb0 + kb_per_split, p.kblocks_total) - kb0;
-      }
+    int na = 0;  // accumulator buffers handed to the epilogue so far
+    for (int it = 0; it < plan.num_items; ++it) {
+      const WorkItem wk = plan.template item<MODE>(it);
+      const int ksteps = (MODE == MODE_FWD) ? ksteps_fwd : wk.kb1 - wk.kb0;
+      if (ksteps <= 0) continue;
+      const int acc = na & 1;
+      const uint32_t acc_phase = (na >> 1) & 1;
+      ++na;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
@@ -249,13 +307,50 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   } else if (warp >= 2) {
     // =========================== epilogue (4 warps, one TMEM lane quarter each) ===========================
     const int q = warp & 3;  // warps 2,3,4,5 -> quarters 2,3,0,1
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+    const int et = threadIdx.x - 64;  // 0..127
+    const bool has_bias = (MODE == MODE_FWD) && p.bias != nullptr;
+    constexpr int kBiasPerThread = (BN + 127) / 128;
+    // bias slice of a tile -> registers (issued one tile ahead) -> shared memory (double buffered)
+    auto fetch_bias = [&](int tile, float (&b)[kBiasPerThread]) {
+      const int nt = tile % ntiles_n;
+#pragma unroll
+      for (int k = 0; k < kBiasPerThread; ++k) {
+        const int idx = k * 128 + et, col = nt * BN + idx;
+        b[k] = (idx < BN && col < p.N) ? __ldg(p.bias + col) : 0.f;
+      }
+    };
+    auto put_bias = [&](int buf, const float (&b)[kBiasPerThread]) {
+#pragma unroll
+      for (int k = 0; k < kBiasPerThread; ++k) {
+        const int idx = k * 128 + et;
+        if (idx < BN) s_bias[buf * 256 + idx] = b[k];
+      }
+    };
+    if (has_bias && plan.num_items > 0) {
+      float b0[kBiasPerThread];
+      fetch_bias(blockIdx.x, b0);
+      put_bias(0, b0);
+      epi_bar_sync();
+    }
+    int na = 0;
+    for (int it = 0; it < plan.num_items; ++it) {
+      const WorkItem wk = plan.template item<MODE>(it);
+      if (MODE == MODE_WGRAD && wk.kb1 <= wk.kb0) continue;
+      const int tile = wk.tile;
+      const int acc = na & 1;
+      const uint32_t acc_phase = (na >> 1) & 1;
+      ++na;
+      float bnext[kBiasPerThread];
+      const bool more = it + 1 < plan.num_items;
+      if (has_bias && more) fetch_bias(tile + gridDim.x, bnext);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t tbase = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(q * 32) << 16);
+      // 32-column chunks in the order (column chunk c, sub-tile mi). The loop stays rolled (a fully unrolled epilogue
+      // overflows the instruction cache); the TMEM load of the next chunk is issued as soon as the current one has
+      // been copied out of its registers, so it is in flight while the chunk is processed.
+      uint32_t r[32];
+      tmem_ld_32x32(tbase, r);
       if constexpr (MODE == MODE_FWD) {
         const int nt = tile % ntiles_n;
         const int mt = (tile / ntiles_n) % mtiles;
@@ -263,55 +358,64 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const int w_t0 = (mt % wtiles) * p.Wt, h_t0 = ((mt / wtiles) % htiles) * p.Ht;
         const int n_t0 = (mt / (wtiles * htiles)) * p.Nt;
         const float slope = p.act_slope;
-#pragma unroll 1
+        const uint32_t sb = smem_u32(s_bias) + (it & 1) * 1024;
+        long long off[MT];
+        bool row_ok[MT];
+#pragma unroll
         for (int mi = 0; mi < MT; ++mi) {
           const int row = mi * kBlockM + q * 32 + lane;
           const int w = w_t0 + row % p.Wt;
           const int h = h_t0 + (row / p.Wt) % p.Ht;
           const int n = n_t0 + row / (p.Wt * p.Ht);
-          const bool row_ok = n < p.NB;
-          const long long off = p.phase_off[ph] + n * p.out_sN + h * p.out_sH + w * p.out_sW;
-          __nv_bfloat16* orow = p.out + off;
-          const __nv_bfloat16* rrow = p.residual ? p.residual + off : nullptr;
+          row_ok[mi] = n < p.NB;
+          off[mi] = p.phase_off[ph] + n * p.out_sN + h * p.out_sH + w * p.out_sW;
+        }
+        const int nchunks = min(BN / 32, (p.N - nt * BN + 31) / 32);  // partial last column tile
 #pragma unroll 1
-          for (int c = 0; c < BN / 32; ++c) {
-            const int col0 = nt * BN + c * 32;
-            if (col0 >= p.N) break;  // warp-uniform
-            uint32_t r[32];
-            tmem_ld_32x32(tbase + mi * BN + c * 32, r);
+        for (int c = 0; c < nchunks; ++c) {
+          const int col0 = nt * BN + c * 32;
+          float s1[32], s2[32];
+#pragma unroll
+          for (int mi = 0; mi < MT; ++mi) {
             float v[32];
-            if (p.bias != nullptr) {
-              const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+            tmem_ld_wait_regs(r);
+            if (has_bias) {
 #pragma unroll
               for (int g = 0; g < 8; ++g) {
-                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (col0 + g * 4 < p.N) b4 = __ldg(bp + g);
-                v[4 * g] = b4.x, v[4 * g + 1] = b4.y, v[4 * g + 2] = b4.z, v[4 * g + 3] = b4.w;
+                const float4 b4 = lds_f32x4(sb + (c * 32 + 4 * g) * 4);  // same address for every lane: broadcast
+                v[4 * g] = b4.x + __uint_as_float(r[4 * g]);
+                v[4 * g + 1] = b4.y + __uint_as_float(r[4 * g + 1]);
+                v[4 * g + 2] = b4.z + __uint_as_float(r[4 * g + 2]);
+                v[4 * g + 3] = b4.w + __uint_as_float(r[4 * g + 3]);
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
             }
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
+            // next chunk: (c, mi + 1) or (c + 1, 0)
+            if (mi + 1 < MT) tmem_ld_32x32(tbase + (mi + 1) * BN + c * 32, r);
+            else if (c + 1 < nchunks) tmem_ld_32x32(tbase + (c + 1) * 32, r);
             if (do_stats) {
-              // per-channel sum / sum of squares of the fp32 pre-activation output: 32 rows of this warp via a
-              // shuffle butterfly, then shared-memory accumulators per CTA (flushed once at kernel end)
-              float s1[32], s2[32];
+              // per-channel sum / sum of squares of the fp32 pre-activation output: the MT rows of a thread are added
+              // first, then the 32 rows of the warp via a shuffle butterfly, then shared-memory accumulators per CTA
+              // (flushed once at kernel end)
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                s1[j] = row_ok ? v[j] : 0.f;
-                s2[j] = s1[j] * s1[j];
+                const float x = row_ok[mi] ? v[j] : 0.f;
+                s1[j] = (mi == 0 ? 0.f : s1[j]) + x;
+                s2[j] = (mi == 0 ? 0.f : s2[j]) + x * x;
               }
-              warp_transpose_sum32(s1, lane);
-              warp_transpose_sum32(s2, lane);
-              if (col0 + lane < p.N) {
-                atomicAdd(&s_stat[col0 + lane], s1[0]);
-                atomicAdd(&s_stat[p.N + col0 + lane], s2[0]);
+              if (mi == MT - 1) {
+                warp_transpose_sum32(s1, lane);
+                warp_transpose_sum32(s2, lane);
+                if (col0 + lane < p.N) {
+                  atomicAdd(&s_stat[col0 + lane], s1[0]);
+                  atomicAdd(&s_stat[p.N + col0 + lane], s2[0]);
+                }
               }
             }
-            if (rrow != nullptr && row_ok) {
+            if (p.residual != nullptr && row_ok[mi]) {
+              const __nv_bfloat16* rrow = p.residual + off[mi];
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 if (col0 + g * 8 < p.N) {
@@ -326,30 +430,41 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 }
               }
             }
+            // activation as max(v, slope * v): slope 1 = identity, 0 = ReLU, 0.2 = LeakyReLU
+            if (slope != 1.f) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f) + slope * fminf(v[j], 0.f);
-            if (row_ok && p.out_f32 != nullptr) {
-              float4* dst = reinterpret_cast<float4*>(p.out_f32 + off + col0);
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], slope * v[j]);
+            }
+            if (row_ok[mi]) {
+              if (p.out_f32 != nullptr) {
+                float4* dst = reinterpret_cast<float4*>(p.out_f32 + off[mi] + col0);
 #pragma unroll
-              for (int g = 0; g < 8; ++g)
-                if (col0 + g * 4 < p.N) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-            } else if (row_ok) {
+                for (int g = 0; g < 8; ++g)
+                  if (col0 + g * 4 < p.N) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+              } else {
+                __nv_bfloat16* orow = p.out + off[mi] + col0;
+                uint32_t w32[16];
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                uint32_t w32[4], l32[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float a0 = v[g * 8 + 2 * e], a1 = v[g * 8 + 2 * e + 1];
-                  const __nv_bfloat162 b2 = __floats2bfloat162_rn(a0, a1);
+                for (int e = 0; e < 16; ++e) {
+                  const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
                   w32[e] = *reinterpret_cast<const uint32_t*>(&b2);
-                  const float2 hf = __bfloat1622float2(b2);
-                  const __nv_bfloat162 l2 = __floats2bfloat162_rn(a0 - hf.x, a1 - hf.y);
-                  l32[e] = *reinterpret_cast<const uint32_t*>(&l2);
                 }
-                if (col0 + g * 8 < p.N) {
-                  *reinterpret_cast<uint4*>(orow + col0 + g * 8) = make_uint4(w32[0], w32[1], w32[2], w32[3]);
-                  if (p.out_lo != nullptr)
-                    *reinterpret_cast<uint4*>(p.out_lo + off + col0 + g * 8) = make_uint4(l32[0], l32[1], l32[2], l32[3]);
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                  if (col0 + g * 8 < p.N)
+                    *reinterpret_cast<uint4*>(orow + g * 8) = make_uint4(w32[4 * g], w32[4 * g + 1], w32[4 * g + 2], w32[4 * g + 3]);
+                if (p.out_lo != nullptr) {
+                  __nv_bfloat16* lrow = p.out_lo + off[mi] + col0;
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) {
+                    const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w32[e]));
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+                    w32[e] = *reinterpret_cast<const uint32_t*>(&l2);
+                  }
+#pragma unroll
+                  for (int g = 0; g < 4; ++g)
+                    if (col0 + g * 8 < p.N)
+                      *reinterpret_cast<uint4*>(lrow + g * 8) = make_uint4(w32[4 * g], w32[4 * g + 1], w32[4 * g + 2], w32[4 * g + 3]);
                 }
               }
             }
@@ -359,33 +474,34 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const int nt = tile % ntiles_n;
         const int tp = (tile / ntiles_n) % p.taps_per_phase;
         const int mt = (tile / (ntiles_n * p.taps_per_phase)) % mtiles;
+        const int nchunks = min(BN / 32, (p.N - nt * BN + 31) / 32);
 #pragma unroll 1
-        for (int mi = 0; mi < MT; ++mi) {
-          const int m = (mt * MT + mi) * kBlockM + q * 32 + lane;
-          const bool row_ok = m < p.M;
-          float* drow = p.dw + static_cast<long long>(m) * p.ldw + p.taps[tp].koff;
-#pragma unroll 1
-          for (int c = 0; c < BN / 32; ++c) {
-            const int col0 = nt * BN + c * 32;
-            if (col0 >= p.N) break;
-            uint32_t r[32];
-            tmem_ld_32x32(tbase + mi * BN + c * 32, r);
-            tmem_ld_wait();
-            if (row_ok) {
+        for (int c = 0; c < nchunks; ++c) {
+          const int col0 = nt * BN + c * 32;
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                if (col0 + g * 8 < p.N) {
-                  // 16-byte vector reductions (red.global.add.v4.f32): 4x fewer L2 atomic transactions than scalar
-                  red_add_v4(drow + col0 + g * 8, r[g * 8], r[g * 8 + 1], r[g * 8 + 2], r[g * 8 + 3]);
-                  red_add_v4(drow + col0 + g * 8 + 4, r[g * 8 + 4], r[g * 8 + 5], r[g * 8 + 6], r[g * 8 + 7]);
-                }
+          for (int mi = 0; mi < MT; ++mi) {
+            uint32_t v[32];
+            tmem_ld_wait_regs(r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = r[j];
+            if (mi + 1 < MT) tmem_ld_32x32(tbase + (mi + 1) * BN + c * 32, r);
+            else if (c + 1 < nchunks) tmem_ld_32x32(tbase + (c + 1) * 32, r);
+            const int m = (mt * MT + mi) * kBlockM + q * 32 + lane;
+            if (m < p.M) {
+              float* drow = p.dw + static_cast<long long>(m) * p.ldw + p.taps[tp].koff + col0;
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                // 16-byte vector reductions (red.global.add.v4.f32): 4x fewer L2 atomic transactions than scalar
+                if (col0 + g * 4 < p.N) red_add_v4(drow + g * 4, v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
               }
             }
           }
         }
       }
+      if (has_bias && more) put_bias((it + 1) & 1, bnext);
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
+      if (has_bias) epi_bar_sync();
     }
   }
 

@@ -3,46 +3,10 @@
 // All activations are NHWC bf16 viewed as [P pixels][C channels]; reductions accumulate in fp32.
 #include <cuda_bf16.h>
 
+#include "bn_stream.cuh"
 #include "common.h"
 
 namespace gp {
-
-__device__ __forceinline__ float act_fwd(float v, int act) {
-  if (act == GP_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == GP_ACT_LRELU) return v > 0.f ? v : 0.2f * v;
-  if (act == GP_ACT_TANH) return tanhf(v);
-  return v;
-}
-// derivative w.r.t. the pre-activation z, given z (ReLU / LeakyReLU only need its sign)
-__device__ __forceinline__ float act_grad(float z, int act) {
-  if (act == GP_ACT_RELU) return z > 0.f ? 1.f : 0.f;
-  if (act == GP_ACT_LRELU) return z > 0.f ? 1.f : 0.2f;
-  if (act == GP_ACT_TANH) {
-    float t = tanhf(z);
-    return 1.f - t * t;
-  }
-  return 1.f;
-}
-
-struct bf16x8 {
-  uint4 raw;
-  __device__ __forceinline__ void load(const __nv_bfloat16* p) { raw = *reinterpret_cast<const uint4*>(p); }
-  __device__ __forceinline__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = raw; }
-  __device__ __forceinline__ void unpack(float (&f)[8]) const {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float2 t = __bfloat1622float2(h[i]);
-      f[2 * i] = t.x;
-      f[2 * i + 1] = t.y;
-    }
-  }
-  __device__ __forceinline__ void pack(const float (&f)[8]) {
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-  }
-};
 
 // ------------------------------------------------------------------------------------------------ packing
 // dst[r][k] (bf16, row length ld_dst) = scale * src[map(r) * s_r + k * s_k] for r < R, k < K; zero elsewhere.
@@ -68,32 +32,68 @@ __global__ void pack_matrix_kernel(const float* __restrict__ src, __nv_bfloat16*
   }
 }
 
-// conv weight (D0, D1, KH*KW) fp32 -> packed bf16 [N][tap][C] with (N, C) = (D0, D1) if n_dim == 0 else (D1, D0)
-__global__ void pack_conv_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int D0, int D1,
-                                        int taps, int n_dim_flags, const float* __restrict__ inv_scale) {
-  const int n_dim = n_dim_flags & 1;
-  const bool flip = (n_dim_flags & 2) != 0;  // reversed tap order: dgrad of a stride-1 conv is a conv with the flipped kernel
-  const int N = n_dim == 0 ? D0 : D1, C = n_dim == 0 ? D1 : D0;
-  const long long total = (long long)N * taps * C;
+// conv weight (D0, D1, taps) fp32 -> packed bf16 rows [N][tap][C], (N, C) = (D0, D1) if n_dim == 0 else (D1, D0).
+// Row n starts at dst + n*ld; with lo != nullptr the rounding residuals go to the same position of `lo` (bf16x3
+// weight operand, hi block | lo block per row). Both kernels transpose through shared memory so that global reads
+// are contiguous runs of the source and global writes are contiguous runs of C.
+constexpr int kPackCT = 64;  // channels per tile (n_dim == 0)
+__global__ void pack_conv_weight_n0_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                           __nv_bfloat16* __restrict__ lo, int N, int C, int taps, long long ld,
+                                           int flip, const float* __restrict__ inv_scale) {
+  extern __shared__ float s_tile[];  // [kPackCT][taps + 1]
+  const int n = blockIdx.y, c0 = blockIdx.x * kPackCT;
+  const int ct = min(kPackCT, C - c0);
   const float sc = inv_scale ? 1.f / __ldg(inv_scale) : 1.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const int t = (int)((i / C) % taps);
-    const int n = (int)(i / ((long long)C * taps));
-    const int d0 = n_dim == 0 ? n : c, d1 = n_dim == 0 ? c : n;
-    dst[i] = __float2bfloat16(__ldg(src + ((long long)d0 * D1 + d1) * taps + (flip ? taps - 1 - t : t)) * sc);
+  const float* sp = src + ((long long)n * C + c0) * taps;  // contiguous ct*taps floats
+  for (int i = threadIdx.x; i < ct * taps; i += blockDim.x) s_tile[(i / taps) * (taps + 1) + i % taps] = __ldg(sp + i) * sc;
+  __syncthreads();
+  for (int j = threadIdx.x; j < taps * ct; j += blockDim.x) {
+    const int t = j / ct, c = j % ct;
+    const float v = s_tile[c * (taps + 1) + (flip ? taps - 1 - t : t)];
+    const __nv_bfloat16 h = __float2bfloat16(v);
+    const long long o = (long long)n * ld + (long long)t * C + c0 + c;
+    dst[o] = h;
+    if (lo != nullptr) lo[o] = __float2bfloat16(v - __bfloat162float(h));
+  }
+}
+constexpr int kPackC1 = 32, kPackN1 = 8;  // tile of the n_dim == 1 variant: 32 source rows (C) x 8 output rows (N)
+__global__ void pack_conv_weight_n1_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                           __nv_bfloat16* __restrict__ lo, int N, int C, int taps, long long ld,
+                                           int flip, const float* __restrict__ inv_scale) {
+  extern __shared__ float s_tile[];  // [kPackC1][kPackN1 * taps + 1]
+  const int c0 = blockIdx.x * kPackC1, n0 = blockIdx.y * kPackN1;
+  const int ct = min(kPackC1, C - c0), nt = min(kPackN1, N - n0);
+  const int run = nt * taps, pitch = kPackN1 * taps + 1;
+  const float sc = inv_scale ? 1.f / __ldg(inv_scale) : 1.f;
+  for (int i = threadIdx.x; i < ct * run; i += blockDim.x) {
+    const int c = i / run, rem = i % run;
+    s_tile[c * pitch + rem] = __ldg(src + ((long long)(c0 + c) * N + n0) * taps + rem) * sc;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < run * ct; j += blockDim.x) {
+    const int c = j % ct, q = j / ct;  // q = n_local * taps + t
+    const int nl = q / taps, t = q % taps;
+    const float v = s_tile[c * pitch + nl * taps + (flip ? taps - 1 - t : t)];
+    const __nv_bfloat16 h = __float2bfloat16(v);
+    const long long o = (long long)(n0 + nl) * ld + (long long)t * C + c0 + c;
+    dst[o] = h;
+    if (lo != nullptr) lo[o] = __float2bfloat16(v - __bfloat162float(h));
   }
 }
 
-// packed fp32 gradient [M][tap][N] -> torch layout (M, N, tap) fp32
+// packed fp32 gradient [M][tap][N] -> torch layout (M, N, tap) fp32, tile = one m x 64 n, transposed through smem
+constexpr int kUnpackNT = 64;
 __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int M, int N, int taps) {
-  const long long total = (long long)M * N * taps;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int t = (int)(i % taps);
-    const int n = (int)((i / taps) % N);
-    const int m = (int)(i / ((long long)taps * N));
-    dst[i] = src[((long long)m * taps + t) * N + n];
+  extern __shared__ float s_tile[];  // [taps][kUnpackNT + 1]
+  const int m = blockIdx.y, n0 = blockIdx.x * kUnpackNT;
+  const int nt = min(kUnpackNT, N - n0);
+  for (int i = threadIdx.x; i < taps * nt; i += blockDim.x) {
+    const int t = i / nt, n = i % nt;
+    s_tile[t * (kUnpackNT + 1) + n] = src[((long long)m * taps + t) * N + n0 + n];
   }
+  __syncthreads();
+  float* dp = dst + ((long long)m * N + n0) * taps;  // contiguous nt*taps floats
+  for (int j = threadIdx.x; j < nt * taps; j += blockDim.x) dp[j] = s_tile[(j % taps) * (kUnpackNT + 1) + j / taps];
 }
 
 // fp32 [Rpad][ld_src] (gradient of a packed matrix) -> dst[map(r) * s_r + k * s_k] for r < R, k < K (inverse of pack_matrix)
@@ -112,78 +112,7 @@ __global__ void unpack_matrix_kernel(const float* __restrict__ src, float* __res
 }
 
 // ------------------------------------------------------------------------------------------------ BatchNorm
-// Column-reduction thread layout shared by bn_stats / bn_bwd_reduce / colsum: a block of 256 threads covers
-// (C/8 column groups) x (256 / (C/8) row lanes) when C/8 divides 256, else grid.y tiles the column groups.
-// Partial sums are combined in shared memory first (one global atomic per channel per block).
-struct ColLayout {
-  int g, rl, lanes;
-  bool active;
-};
-__device__ __forceinline__ ColLayout col_layout(int C) {
-  ColLayout L;
-  const int cgs = C / 8;
-  if (cgs <= (int)blockDim.x && gridDim.y == 1) {
-    L.g = threadIdx.x % cgs;
-    L.lanes = blockDim.x / cgs;
-    L.rl = threadIdx.x / cgs;
-    L.active = L.rl < L.lanes;
-  } else {
-    L.g = blockIdx.y * blockDim.x + threadIdx.x;
-    L.lanes = 1;
-    L.rl = 0;
-    L.active = L.g < cgs;
-  }
-  return L;
-}
-// smem: NQ * cols floats, cols = number of channels covered by this block.
-template <int NQ>
-__device__ __forceinline__ void col_flush(const ColLayout& L, int C, float (&acc)[NQ][8], float* const (&out)[NQ]) {
-  extern __shared__ float s_red[];
-  const int cgs = C / 8;
-  const bool tiled = !(cgs <= (int)blockDim.x && gridDim.y == 1);
-  const int cols = tiled ? blockDim.x * 8 : C;
-  const int base = tiled ? blockIdx.y * blockDim.x * 8 : 0;
-  for (int i = threadIdx.x; i < NQ * cols; i += blockDim.x) s_red[i] = 0.f;
-  __syncthreads();
-  if (L.active) {
-#pragma unroll
-    for (int q = 0; q < NQ; ++q)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(&s_red[q * cols + L.g * 8 + i - base], acc[q][i]);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < NQ * cols; i += blockDim.x) {
-    const int q = i / cols, c = base + i % cols;
-    if (c < C) atomicAdd(out[q] + c, s_red[i]);
-  }
-}
-
-// Per-channel sum and sum of squares over P rows.
-__global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, float* __restrict__ sum,
-                                float* __restrict__ sumsq, int rows_per_block) {
-  const ColLayout L = col_layout(C);
-  float acc[2][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
-  long long r1 = r0 + rows_per_block;
-  if (r1 > P) r1 = P;
-  if (L.active) {
-    for (long long r = r0 + L.rl; r < r1; r += L.lanes) {
-      bf16x8 v;
-      v.load(x + r * C + L.g * 8);
-      float f[8];
-      v.unpack(f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        acc[0][i] += f[i];
-        acc[1][i] += f[i] * f[i];
-      }
-    }
-  }
-  float* const outs[2] = {sum, sumsq};
-  col_flush<2>(L, C, acc, outs);
-}
+// (statistics / apply / backward kernels: bn_stream.cuh)
 
 // mean / rstd / fused scale & shift, running statistics (torch: aten::native_batch_norm semantics:
 // biased variance to normalise, unbiased into running_var, momentum 0.1, num_batches_tracked += 1).
@@ -226,122 +155,11 @@ __global__ void bn_eval_kernel(const float* __restrict__ rm, const float* __rest
   shift[c] = b - rm[c] * g * r;
 }
 
-// out = act(y * scale[c] + shift[c])
-// Each thread owns one group of 8 channels (per-channel parameters live in registers) and strides over rows.
-__global__ void bn_apply_act_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ out, long long P,
-                                    int C, const float* __restrict__ scale, const float* __restrict__ shift, int act,
-                                    int rows_per_block) {
-  const ColLayout L = col_layout(C);
-  if (!L.active) return;
-  float sc[8], sh[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sc[j] = scale[L.g * 8 + j];
-    sh[j] = shift[L.g * 8 + j];
-  }
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
-  long long r1 = r0 + rows_per_block;
-  if (r1 > P) r1 = P;
-  for (long long r = r0 + L.rl; r < r1; r += L.lanes) {
-    bf16x8 v;
-    v.load(y + r * C + L.g * 8);
-    float f[8];
-    v.unpack(f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = act_fwd(f[j] * sc[j] + sh[j], act);
-    v.pack(f);
-    v.store(out + r * C + L.g * 8);
-  }
-}
-
-// Backward reduction: sum_dz[c] = sum dz, sum_dzx[c] = sum dz * xhat, with z = y*scale+shift, dz = da*act'(z),
-// xhat = (y - mean) * rstd.   Same thread layout as bn_stats_kernel.
-__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ y,
-                                     long long P, int C, const float* __restrict__ scale,
-                                     const float* __restrict__ shift, const float* __restrict__ mean,
-                                     const float* __restrict__ rstd, int act, float* __restrict__ sum_dz,
-                                     float* __restrict__ sum_dzx, int rows_per_block) {
-  const ColLayout L = col_layout(C);
-  float acc[2][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
-  if (L.active) {
-    float sc[8], sh[8], mu[8], rs[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      sc[i] = scale[L.g * 8 + i];
-      sh[i] = shift[L.g * 8 + i];
-      mu[i] = mean[L.g * 8 + i];
-      rs[i] = rstd[L.g * 8 + i];
-    }
-    const long long r0 = (long long)blockIdx.x * rows_per_block;
-    long long r1 = r0 + rows_per_block;
-    if (r1 > P) r1 = P;
-    for (long long r = r0 + L.rl; r < r1; r += L.lanes) {
-      bf16x8 vy, vd;
-      vy.load(y + r * C + L.g * 8);
-      vd.load(da + r * C + L.g * 8);
-      float fy[8], fd[8];
-      vy.unpack(fy);
-      vd.unpack(fd);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float dz = fd[i] * act_grad(fy[i] * sc[i] + sh[i], act);
-        acc[0][i] += dz;
-        acc[1][i] += dz * (fy[i] - mu[i]) * rs[i];
-      }
-    }
-  }
-  float* const outs[2] = {sum_dz, sum_dzx};
-  col_flush<2>(L, C, acc, outs);
-}
-
-// dy = gamma*rstd * (dz - sum_dz/M - xhat * sum_dzx/M)
-__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ y,
-                                    __nv_bfloat16* __restrict__ dy, long long n8, int C,
-                                    const float* __restrict__ scale, const float* __restrict__ shift,
-                                    const float* __restrict__ mean, const float* __restrict__ rstd,
-                                    const float* __restrict__ sum_dz, const float* __restrict__ sum_dzx,
-                                    float inv_count, int act, int rows_per_block) {
-  const long long P = n8;  // rows
-  const ColLayout L = col_layout(C);
-  if (!L.active) return;
-  // dy = sc*dz - k0 - (y - mu) * k1   with k0 = sc*sum_dz/M, k1 = sc*rstd*sum_dzx/M
-  float sc[8], sh[8], mu[8], k0[8], k1[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = L.g * 8 + j;
-    sc[j] = scale[c];
-    sh[j] = shift[c];
-    mu[j] = mean[c];
-    k0[j] = sc[j] * sum_dz[c] * inv_count;
-    k1[j] = sc[j] * rstd[c] * sum_dzx[c] * inv_count;
-  }
-  const long long r0 = (long long)blockIdx.x * rows_per_block;
-  long long r1 = r0 + rows_per_block;
-  if (r1 > P) r1 = P;
-  for (long long r = r0 + L.rl; r < r1; r += L.lanes) {
-    bf16x8 vy, vd;
-    vy.load(y + r * C + L.g * 8);
-    vd.load(da + r * C + L.g * 8);
-    float fy[8], fd[8], o[8];
-    vy.unpack(fy);
-    vd.unpack(fd);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float dz = fd[j] * act_grad(fy[j] * sc[j] + sh[j], act);
-      o[j] = sc[j] * dz - k0[j] - (fy[j] - mu[j]) * k1[j];
-    }
-    vd.pack(o);
-    vd.store(dy + r * C + L.g * 8);
-  }
-}
-
 // dy = da * act'(a)   (activation applied directly on the conv output: a has the sign of the pre-activation)
 __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ a,
                                __nv_bfloat16* __restrict__ dy, long long n8, int act) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
-    bf16x8 va, vd;
+    Vec8<__nv_bfloat16> va, vd;
     va.load(a + i * 8);
     vd.load(da + i * 8);
     float fa[8], fd[8];
@@ -354,80 +172,96 @@ __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_
       else gr = act_grad(fa[j], act);
       fd[j] *= gr;
     }
-    vd.pack(fd);
-    vd.store(dy + i * 8);
+    store8_bf16(dy + i * 8, nullptr, fd);
   }
 }
 
-// column sums of a bf16 [P][C] matrix into fp32 (bias gradients)
-__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, float* __restrict__ out,
-                              int rows_per_block) {
-  const ColLayout L = col_layout(C);
-  float acc[1][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[0][i] = 0.f;
-  if (L.active) {
-    const long long r0 = (long long)blockIdx.x * rows_per_block;
-    long long r1 = r0 + rows_per_block;
-    if (r1 > P) r1 = P;
-    for (long long r = r0 + L.rl; r < r1; r += L.lanes) {
-      bf16x8 v;
-      v.load(x + r * C + L.g * 8);
-      float f[8];
-      v.unpack(f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[0][i] += f[i];
-    }
-  }
-  float* const outs[1] = {out};
-  col_flush<1>(L, C, acc, outs);
-}
+}  // namespace gp
+
+namespace gp {
 
 // ------------------------------------------------------------------------------------------------ image layers
 // im2col of a k4 s2 p1 window over an NCHW fp32 image with `ch` (<= 4) channels:
 //   col[(n, oh, ow)][(c*4 + kh)*4 + kw] = img[n, c, 2oh-1+kh, 2ow-1+kw] * (mul ? 1 - mul[same]^2 : 1); columns >= ch*16 are 0.
 // Used for D's first conv (models/dcgan.py:106, Cin = img_dim) and for the gradient of G's last ConvT + Tanh
-// (models/dcgan.py:41-44): `mul` is then the tanh output, fusing tanh'.
+// (models/dcgan.py:41-44): `mul` is then the tanh output, fusing tanh'. col_lo (optional) receives the bf16 rounding
+// residuals (bf16x3 operand pair).
+// One block = one image x kIm2colRows output rows: the 2*rows+2 input rows of every channel are staged in shared memory
+// with float4 loads, then every thread emits 16-byte column groups (8 groups = one 128-byte col row per pixel).
+constexpr int kIm2colRows = 4;
 __global__ void im2col_k4s2_kernel(const float* __restrict__ img, const float* __restrict__ mul,
-                                   __nv_bfloat16* __restrict__ col, int NB, int ch, int Hi, int Wi) {
+                                   __nv_bfloat16* __restrict__ col, __nv_bfloat16* __restrict__ col_lo, int NB, int ch,
+                                   int Hi, int Wi) {
+  extern __shared__ float s_img[];  // [ch][2*kIm2colRows + 2][Wi]
+  constexpr int kInRows = 2 * kIm2colRows + 2;
   const int Ho = Hi / 2, Wo = Wi / 2;
-  const long long total = (long long)NB * Ho * Wo * 8;  // 8 groups of 8 columns per pixel
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % 8);
-    const long long p = i / 8;
-    const int ow = (int)(p % Wo), oh = (int)((p / Wo) % Ho), n = (int)(p / ((long long)Wo * Ho));
+  const int n = blockIdx.y, oh0 = blockIdx.x * kIm2colRows;
+  const int w4 = Wi / 4;
+  for (int i = threadIdx.x; i < ch * kInRows * w4; i += blockDim.x) {
+    const int q = i % w4, rr = (i / w4) % kInRows, c = i / (w4 * kInRows);
+    const int ih = 2 * oh0 - 1 + rr;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ih >= 0 && ih < Hi) {
+      const long long off = (((long long)n * ch + c) * Hi + ih) * Wi + 4 * q;
+      v = __ldg(reinterpret_cast<const float4*>(img + off));
+      if (mul != nullptr) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(mul + off));
+        v.x *= 1.f - t.x * t.x, v.y *= 1.f - t.y * t.y, v.z *= 1.f - t.z * t.z, v.w *= 1.f - t.w * t.w;
+      }
+    }
+    *reinterpret_cast<float4*>(s_img + (c * kInRows + rr) * Wi + 4 * q) = v;
+  }
+  __syncthreads();
+  const int rows = min(kIm2colRows, Ho - oh0);
+  for (int i = threadIdx.x; i < rows * Wo * 8; i += blockDim.x) {
+    const int g = i & 7, ow = (i >> 3) % Wo, ol = (i >> 3) / Wo;
+    const int c = g >> 1;
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int col_idx = g * 8 + j;
-      const int c = col_idx / 16, kh = (col_idx / 4) % 4, kw = col_idx % 4;
-      const int ih = 2 * oh - 1 + kh, iw = 2 * ow - 1 + kw;
-      float v = 0.f;
-      if (c < ch && ih >= 0 && ih < Hi && iw >= 0 && iw < Wi) {
-        const long long off = (((long long)n * ch + c) * Hi + ih) * Wi + iw;
-        v = __ldg(img + off);
-        if (mul != nullptr) {
-          const float t = __ldg(mul + off);
-          v *= 1.f - t * t;
-        }
-      }
-      f[j] = v;
+      const int kh = (g & 1) * 2 + (j >> 2), kw = j & 3;
+      const int iw = 2 * ow - 1 + kw;
+      f[j] = (c < ch && iw >= 0 && iw < Wi) ? s_img[(c * kInRows + 2 * ol + kh) * Wi + iw] : 0.f;
     }
-    bf16x8 o;
-    o.pack(f);
-    o.store(col + i * 8);
+    const long long o = ((((long long)n * Ho + oh0 + ol) * Wo + ow) * 8 + g) * 8;
+    store8_bf16(col + o, col_lo ? col_lo + o : nullptr, f);
   }
 }
 
 // col2im (transpose of the above): img[n, c, ih, iw] = act( bias[c] + sum_{(oh,kh): 2oh-1+kh = ih} sum_{(ow,kw)} col[(n,oh,ow)][(c*4+kh)*4+kw] )
-// Used for G's last ConvT (+Tanh) forward and for the image gradient of D's first conv.
-__global__ void col2im_k4s2_kernel(const __nv_bfloat16* __restrict__ col, const float* __restrict__ bias,
-                                   float* __restrict__ img, int NB, int ch, int Hi, int Wi, int act) {
+// Used for G's last ConvT (+Tanh) forward and for the image gradient of D's first conv. TC = bf16 or fp32 col.
+// One block = one image x kCol2imRows image rows: the rows/2 + 2 col rows they gather from are staged in shared
+// memory with 16-byte loads (only the ch*16 live columns), then one thread per output pixel.
+constexpr int kCol2imRows = 8;
+template <typename TC>
+__global__ void col2im_k4s2_kernel(const TC* __restrict__ col, const float* __restrict__ bias, float* __restrict__ img,
+                                   int NB, int ch, int Hi, int Wi, int act) {
+  extern __shared__ float s_col[];  // [kCol2imRows/2 + 2][Wo][ch*16 + 1]
+  constexpr int kColRows = kCol2imRows / 2 + 2;
   const int Ho = Hi / 2, Wo = Wi / 2;
-  const long long total = (long long)NB * ch * Hi * Wi;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int iw = (int)(i % Wi), ih = (int)((i / Wi) % Hi);
-    const int c = (int)((i / ((long long)Wi * Hi)) % ch), n = (int)(i / ((long long)Wi * Hi * ch));
+  const int n = blockIdx.y, ih0 = blockIdx.x * kCol2imRows;
+  const int oh_base = ih0 / 2 - 1;
+  const int live = ch * 16, pitch = live + 1, groups = live / 8;
+  for (int i = threadIdx.x; i < kColRows * Wo * groups; i += blockDim.x) {
+    const int g = i % groups, ow = (i / groups) % Wo, r = i / (groups * Wo);
+    const int oh = oh_base + r;
+    float f[8];
+    if (oh >= 0 && oh < Ho) {
+      Vec8<TC> v;
+      v.load(col + (((long long)n * Ho + oh) * Wo + ow) * 64 + g * 8);
+      v.unpack(f);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_col[(r * Wo + ow) * pitch + g * 8 + j] = f[j];
+  }
+  __syncthreads();
+  const int rows = min(kCol2imRows, Hi - ih0);
+  for (int i = threadIdx.x; i < ch * rows * Wi; i += blockDim.x) {
+    const int iw = i % Wi, il = (i / Wi) % rows, c = i / (Wi * rows);
+    const int ih = ih0 + il;
     float acc = bias ? __ldg(bias + c) : 0.f;
     // ih = 2*oh - 1 + kh  ->  kh in {(ih+1)&1, (ih+1)&1 + 2}
 #pragma unroll
@@ -435,17 +269,16 @@ __global__ void col2im_k4s2_kernel(const __nv_bfloat16* __restrict__ col, const 
       const int kh = ((ih + 1) & 1) + 2 * a;
       const int oh2 = ih + 1 - kh;
       if (oh2 < 0 || oh2 >= 2 * Ho) continue;
-      const int oh = oh2 / 2;
+      const int r = oh2 / 2 - oh_base;
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
         const int kw = ((iw + 1) & 1) + 2 * b;
         const int ow2 = iw + 1 - kw;
         if (ow2 < 0 || ow2 >= 2 * Wo) continue;
-        const int ow = ow2 / 2;
-        acc += __bfloat162float(col[(((long long)n * Ho + oh) * Wo + ow) * 64 + (c * 4 + kh) * 4 + kw]);
+        acc += s_col[(r * Wo + ow2 / 2) * pitch + (c * 4 + kh) * 4 + kw];
       }
     }
-    img[i] = act_fwd(acc, act);
+    img[(((long long)n * ch + c) * Hi + ih) * Wi + iw] = act_fwd(acc, act);
   }
 }
 
@@ -476,17 +309,34 @@ __global__ void image_bias_grad_kernel(const float* __restrict__ dout, const flo
 }
 
 // ------------------------------------------------------------------------------------------------ heads
-// out[b][o] = bias[o] + sum_{hw, c} a[b, hw, c] * w[o*s_o + c*s_c + hw*s_hw]
+// out[b][o] = bias[o] + sum_{hw, c} (a + a_lo)[b, hw, c] * w[o*s_o + c*s_c + hw*s_hw]
 // (sum-pool + Linear: s_hw = 0, models/dcgan.py:121-122; flatten + Linear: s_c = HW, s_hw = 1, dcgan_specnorm.py:125-126)
-__global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w,
-                                const float* __restrict__ bias, float* __restrict__ out, int HW, int C, int O,
-                                long long s_o, long long s_c, long long s_hw) {
+// One block per (b, o); threads read 8 channels (16 bytes) at a time. a_lo: optional low halves (bf16x3 mode).
+__global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ a_lo,
+                                const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
+                                int HW, int C, int O, long long s_o, long long s_c, long long s_hw) {
   const int b = blockIdx.x, o = blockIdx.y;
   float acc = 0.f;
-  const __nv_bfloat16* ab = a + (long long)b * HW * C;
-  for (int i = threadIdx.x; i < HW * C; i += blockDim.x) {
-    const int c = i % C, hw = i / C;
-    acc += __bfloat162float(ab[i]) * __ldg(w + o * s_o + c * s_c + hw * s_hw);
+  const long long base = (long long)b * HW * C;
+  const float* wo = w + o * s_o;
+  const int c8 = C / 8;
+  for (int i = threadIdx.x; i < HW * c8; i += blockDim.x) {
+    const int c = (i % c8) * 8, hw = i / c8;
+    Vec8<__nv_bfloat16> v;
+    v.load(a + base + (long long)i * 8);
+    float f[8];
+    v.unpack(f);
+    if (a_lo != nullptr) {
+      Vec8<__nv_bfloat16> vl;
+      vl.load(a_lo + base + (long long)i * 8);
+      float fl[8];
+      vl.unpack(fl);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += fl[j];
+    }
+    const float* wp = wo + c * s_c + hw * s_hw;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += f[j] * __ldg(wp + j * s_c);
   }
   __shared__ float red[32];
   for (int k = 16; k > 0; k >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, k);
@@ -499,34 +349,74 @@ __global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ a, const float
   }
 }
 
-// da[b, hw, c] = sum_o dout[b][o] * w[o, c, hw]
+// da[b, hw, c] = sum_o dout[b][o] * w[o, c, hw]      (one thread per 8 channels)
 __global__ void head_bwd_data_kernel(const float* __restrict__ dout, const float* __restrict__ w,
                                      __nv_bfloat16* __restrict__ da, int NB, int HW, int C, int O, long long s_o,
                                      long long s_c, long long s_hw) {
-  const long long total = (long long)NB * HW * C;
+  const int c8 = C / 8;
+  const long long total = (long long)NB * HW * c8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C), hw = (int)((i / C) % HW);
-    const long long b = i / ((long long)C * HW);
-    float acc = 0.f;
-    for (int o = 0; o < O; ++o) acc += __ldg(dout + b * O + o) * __ldg(w + o * s_o + c * s_c + hw * s_hw);
-    da[i] = __float2bfloat16(acc);
+    const int c = (int)(i % c8) * 8, hw = (int)((i / c8) % HW);
+    const int b = (int)(i / ((long long)c8 * HW));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int o = 0; o < O; ++o) {
+      const float d = __ldg(dout + (long long)b * O + o);
+      const float* wp = w + o * s_o + c * s_c + hw * s_hw;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += d * __ldg(wp + j * s_c);
+    }
+    store8_bf16(da + i * 8, nullptr, acc);
   }
 }
 
 // dw[o, c, hw] (+)= sum_b dout[b][o] * a[b, hw, c]  (sum-pool: s_hw = 0 so the hw terms accumulate); dbias[o] = sum_b dout[b][o]
-// One block per (c-chunk, o); dw must be zeroed by the caller.
+// One thread per (8-channel group, hw) x batch chunk (grid.z); dw must be zeroed by the caller.
 __global__ void head_bwd_weight_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ a,
                                        float* __restrict__ dw, float* __restrict__ dbias, int NB, int HW, int C, int O,
                                        long long s_o, long long s_c, long long s_hw) {
   const int o = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // index over HW*C
+  const int c8 = C / 8;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // index over HW * C/8
   const int bchunk = (NB + gridDim.z - 1) / gridDim.z;
   const int b0 = blockIdx.z * bchunk, b1 = min(b0 + bchunk, NB);
-  if (i < HW * C) {
-    const int c = i % C, hw = i / C;
-    float acc = 0.f;
-    for (int b = b0; b < b1; ++b) acc += __ldg(dout + (long long)b * O + o) * __bfloat162float(a[((long long)b * HW) * C + i]);
-    atomicAdd(dw + o * s_o + c * s_c + hw * s_hw, acc);
+  if (i < HW * c8) {
+    const int c = (i % c8) * 8, hw = i / c8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const __nv_bfloat16* ap = a + (long long)i * 8;
+    const long long sb = (long long)HW * C;
+    int b = b0;
+    for (; b + 4 <= b1; b += 4) {
+      Vec8<__nv_bfloat16> v[4];
+      float d[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        v[u].load(ap + (b + u) * sb);
+        d[u] = __ldg(dout + (long long)(b + u) * O + o);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        v[u].unpack(f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += d[u] * f[j];
+      }
+    }
+    for (; b < b1; ++b) {
+      Vec8<__nv_bfloat16> v;
+      v.load(ap + b * sb);
+      float f[8];
+      v.unpack(f);
+      const float d = __ldg(dout + (long long)b * O + o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += d * f[j];
+    }
+    float* wp = dw + o * s_o + c * s_c + hw * s_hw;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(wp + j * s_c, acc[j]);
   }
   if (dbias != nullptr && blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
     float s = 0.f;
@@ -581,12 +471,21 @@ static inline int grid_for(long long n, int block = 256, int max_blocks = 148 * 
   return (int)g;
 }
 
-// choose rows-per-block for the column-reduction kernels so the grid is ~8 blocks per SM
-static inline int rows_per_block_for(long long P) {
-  long long target_blocks = (long long)num_sms() * 8;
-  long long rpb = (P + target_blocks - 1) / target_blocks;
-  if (rpb < 32) rpb = 32;
-  return (int)rpb;
+// fp32 (D0, D1, taps) -> bf16 rows [N][tap][C] at pitch ld, optional residual block `lo` (see the kernels above)
+static int launch_pack_conv_weight(const float* src, __nv_bfloat16* dst, __nv_bfloat16* lo, int D0, int D1, int taps,
+                                   int n_dim_flags, long long ld, const float* inv_scale, cudaStream_t st) {
+  const int n_dim = n_dim_flags & 1, flip = (n_dim_flags >> 1) & 1;
+  if (n_dim == 0) {
+    dim3 grid((D1 + kPackCT - 1) / kPackCT, D0);
+    pack_conv_weight_n0_kernel<<<grid, 256, (size_t)kPackCT * (taps + 1) * sizeof(float), st>>>(src, dst, lo, D0, D1, taps,
+                                                                                             ld, flip, inv_scale);
+  } else {
+    dim3 grid((D0 + kPackC1 - 1) / kPackC1, (D1 + kPackN1 - 1) / kPackN1);
+    pack_conv_weight_n1_kernel<<<grid, 256, (size_t)kPackC1 * (kPackN1 * taps + 1) * sizeof(float), st>>>(
+        src, dst, lo, D1, D0, taps, ld, flip, inv_scale);
+  }
+  GP_CHECK_LAUNCH();
+  return GP_OK;
 }
 
 }  // namespace gp
@@ -616,50 +515,36 @@ int gp_unpack_matrix(const float* src, float* dst, int R, int K, int ld_src, lon
 int gp_pack_conv_weight(const float* src, void* dst, int D0, int D1, int taps, int n_dim, const float* inv_scale,
                         void* stream) {
   GP_REQUIRE(src && dst && D0 > 0 && D1 > 0 && taps > 0 && n_dim >= 0 && n_dim <= 3, "gp_pack_conv_weight: bad arguments");
-  pack_conv_weight_kernel<<<grid_for((long long)D0 * D1 * taps), 256, 0, as_stream(stream)>>>(
-      src, static_cast<__nv_bfloat16*>(dst), D0, D1, taps, n_dim, inv_scale);
-  GP_CHECK_LAUNCH();
-  return GP_OK;
+  GP_REQUIRE(taps <= 64, "gp_pack_conv_weight: at most 64 taps");
+  const int C = (n_dim & 1) == 0 ? D1 : D0;
+  return launch_pack_conv_weight(src, static_cast<__nv_bfloat16*>(dst), nullptr, D0, D1, taps, n_dim,
+                                 (long long)taps * C, inv_scale, as_stream(stream));
+}
+
+// bf16x3 weight operand: rows [N][2][taps][C] = hi block | lo block (rounding residuals)
+int gp_split_conv_weight(const float* src, void* dst, int D0, int D1, int taps, int n_dim, void* stream) {
+  GP_REQUIRE(src && dst && D0 > 0 && D1 > 0 && taps > 0 && (n_dim == 0 || n_dim == 1), "gp_split_conv_weight: bad arguments");
+  GP_REQUIRE(taps <= 64, "gp_split_conv_weight: at most 64 taps");
+  const int C = n_dim == 0 ? D1 : D0;
+  __nv_bfloat16* hi = static_cast<__nv_bfloat16*>(dst);
+  return launch_pack_conv_weight(src, hi, hi + (long long)taps * C, D0, D1, taps, n_dim, 2LL * taps * C, nullptr,
+                                 as_stream(stream));
 }
 
 int gp_unpack_conv_wgrad(const float* src, float* dst, int M, int N, int taps, void* stream) {
-  GP_REQUIRE(src && dst && M > 0 && N > 0 && taps > 0, "gp_unpack_conv_wgrad: bad arguments");
-  unpack_conv_wgrad_kernel<<<grid_for((long long)M * N * taps), 256, 0, as_stream(stream)>>>(src, dst, M, N, taps);
+  GP_REQUIRE(src && dst && M > 0 && N > 0 && taps > 0 && taps <= 64, "gp_unpack_conv_wgrad: bad arguments");
+  dim3 grid((N + kUnpackNT - 1) / kUnpackNT, M);
+  unpack_conv_wgrad_kernel<<<grid, 256, (size_t)taps * (kUnpackNT + 1) * sizeof(float), as_stream(stream)>>>(src, dst, M,
+                                                                                                          N, taps);
   GP_CHECK_LAUNCH();
   return GP_OK;
-}
-
-// launch geometry of the column-reduction kernels
-struct ColLaunch {
-  dim3 grid;
-  int block;
-  size_t smem;
-  int rpb;
-};
-static ColLaunch col_launch(long long P, int C, int nq) {
-  ColLaunch L;
-  L.rpb = rows_per_block_for(P);
-  const int gx = (int)((P + L.rpb - 1) / L.rpb);
-  const int cgs = C / 8;
-  if (cgs <= 256 && 256 % cgs == 0) {
-    L.grid = dim3(gx, 1);
-    L.block = 256;
-    L.smem = (size_t)nq * C * sizeof(float);
-  } else {
-    L.block = 128;
-    int gy = (cgs + 127) / 128;
-    if (gy < 2) gy = 2;  // gridDim.y > 1 selects the tiled layout inside the kernels
-    L.grid = dim3(gx, gy);
-    L.smem = (size_t)nq * 128 * 8 * sizeof(float);
-  }
-  return L;
 }
 
 int gp_bn_stats(const void* x, long long P, int C, float* sum, float* sumsq, void* stream) {
   GP_REQUIRE(x && sum && sumsq && P > 0 && C > 0 && C % 8 == 0, "gp_bn_stats: bad arguments (C %% 8 == 0 required)");
   const ColLaunch L = col_launch(P, C, 2);
-  bn_stats_kernel<<<L.grid, L.block, L.smem, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(x), P, C, sum, sumsq,
-                                                                  L.rpb);
+  col_stats_kernel<__nv_bfloat16, true><<<L.grid, L.block, L.smem, as_stream(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), P, C, sum, sumsq, L.rpb);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -688,9 +573,8 @@ int gp_bn_apply_act(const void* y, void* out, long long P, int C, const float* s
                     void* stream) {
   GP_REQUIRE(y && out && scale && shift && P > 0 && C % 8 == 0, "gp_bn_apply_act: bad arguments");
   const ColLaunch L = col_launch(P, C, 0);
-  bn_apply_act_kernel<<<L.grid, L.block, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(y),
-                                                                 static_cast<__nv_bfloat16*>(out), P, C, scale, shift,
-                                                                 act, L.rpb);
+  bn_apply_kernel<__nv_bfloat16><<<L.grid, L.block, 0, as_stream(stream)>>>(
+      static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(out), nullptr, P, C, scale, shift, act, L.rpb);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -699,7 +583,7 @@ int gp_bn_bwd_reduce(const void* da, const void* y, long long P, int C, const fl
                      const float* mean, const float* rstd, int act, float* sum_dz, float* sum_dzx, void* stream) {
   GP_REQUIRE(da && y && sum_dz && sum_dzx && P > 0 && C % 8 == 0, "gp_bn_bwd_reduce: bad arguments");
   const ColLaunch L = col_launch(P, C, 2);
-  bn_bwd_reduce_kernel<<<L.grid, L.block, L.smem, as_stream(stream)>>>(
+  bn_bwd_reduce_kernel<__nv_bfloat16><<<L.grid, L.block, L.smem, as_stream(stream)>>>(
       static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), P, C, scale, shift, mean, rstd, act,
       sum_dz, sum_dzx, L.rpb);
   GP_CHECK_LAUNCH();
@@ -711,7 +595,7 @@ int gp_bn_bwd_apply(const void* da, const void* y, void* dy, long long P, int C,
                     const float* sum_dzx, double count, int act, void* stream) {
   GP_REQUIRE(da && y && dy && P > 0 && C % 8 == 0 && count > 0, "gp_bn_bwd_apply: bad arguments");
   const ColLaunch L = col_launch(P, C, 0);
-  bn_bwd_apply_kernel<<<L.grid, L.block, 0, as_stream(stream)>>>(
+  bn_bwd_apply_kernel<__nv_bfloat16><<<L.grid, L.block, 0, as_stream(stream)>>>(
       static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(dy), P, C,
       scale, shift, mean, rstd, sum_dz, sum_dzx, (float)(1.0 / count), act, L.rpb);
   GP_CHECK_LAUNCH();
@@ -730,28 +614,61 @@ int gp_act_bwd(const void* da, const void* a, void* dy, long long n, int act, vo
 int gp_colsum(const void* x, long long P, int C, float* out, void* stream) {
   GP_REQUIRE(x && out && P > 0 && C % 8 == 0, "gp_colsum: bad arguments");
   const ColLaunch L = col_launch(P, C, 1);
-  colsum_kernel<<<L.grid, L.block, L.smem, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(x), P, C, out, L.rpb);
+  col_stats_kernel<__nv_bfloat16, false><<<L.grid, L.block, L.smem, as_stream(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), P, C, out, nullptr, L.rpb);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
 
-int gp_im2col_k4s2(const float* img, const float* mul, void* col, int NB, int ch, int Hi, int Wi, void* stream) {
-  GP_REQUIRE(img && col && NB > 0 && ch > 0 && ch <= 4 && Hi % 2 == 0 && Wi % 2 == 0, "gp_im2col_k4s2: bad arguments");
-  const long long total = (long long)NB * (Hi / 2) * (Wi / 2) * 8;
-  im2col_k4s2_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(img, mul, static_cast<__nv_bfloat16*>(col), NB, ch,
-                                                                     Hi, Wi);
+}  // extern "C"
+
+static int launch_im2col(const float* img, const float* mul, void* col, void* col_lo, int NB, int ch, int Hi, int Wi,
+                         void* stream) {
+  GP_REQUIRE(img && col && NB > 0 && ch > 0 && ch <= 4 && Hi % 2 == 0 && Wi % 8 == 0, "gp_im2col_k4s2: bad arguments (Wi %% 8 == 0)");
+  const size_t smem = (size_t)ch * (2 * kIm2colRows + 2) * Wi * sizeof(float);
+  GP_REQUIRE(smem <= 48 * 1024, "gp_im2col_k4s2: image rows too wide (Wi=%d)", Wi);
+  dim3 grid((Hi / 2 + kIm2colRows - 1) / kIm2colRows, NB);
+  im2col_k4s2_kernel<<<grid, 256, smem, as_stream(stream)>>>(img, mul, static_cast<__nv_bfloat16*>(col),
+                                                             static_cast<__nv_bfloat16*>(col_lo), NB, ch, Hi, Wi);
   GP_CHECK_LAUNCH();
   return GP_OK;
+}
+
+template <typename TC>
+static int launch_col2im(const TC* col, const float* bias, float* img, int NB, int ch, int Hi, int Wi, int act,
+                         void* stream) {
+  GP_REQUIRE(img && col && NB > 0 && ch > 0 && ch <= 4 && Hi % 2 == 0 && Wi % 2 == 0, "gp_col2im_k4s2: bad arguments");
+  const size_t smem = (size_t)(kCol2imRows / 2 + 2) * (Wi / 2) * (ch * 16 + 1) * sizeof(float);
+  auto kfn = col2im_k4s2_kernel<TC>;
+  if (smem > 48 * 1024) {
+    GP_REQUIRE(smem <= 200 * 1024, "gp_col2im_k4s2: image rows too wide (Wi=%d)", Wi);
+    GP_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  dim3 grid((Hi + kCol2imRows - 1) / kCol2imRows, NB);
+  kfn<<<grid, 256, smem, as_stream(stream)>>>(col, bias, img, NB, ch, Hi, Wi, act);
+  GP_CHECK_LAUNCH();
+  return GP_OK;
+}
+
+extern "C" {
+
+int gp_im2col_k4s2(const float* img, const float* mul, void* col, int NB, int ch, int Hi, int Wi, void* stream) {
+  return launch_im2col(img, mul, col, nullptr, NB, ch, Hi, Wi, stream);
+}
+
+int gp_im2col_k4s2_split(const float* img, void* col_hi, void* col_lo, int NB, int ch, int Hi, int Wi, void* stream) {
+  GP_REQUIRE(col_lo != nullptr, "gp_im2col_k4s2_split: null pointer");
+  return launch_im2col(img, nullptr, col_hi, col_lo, NB, ch, Hi, Wi, stream);
 }
 
 int gp_col2im_k4s2(const void* col, const float* bias, float* img, int NB, int ch, int Hi, int Wi, int act,
                    void* stream) {
-  GP_REQUIRE(img && col && NB > 0 && ch > 0 && ch <= 4 && Hi % 2 == 0 && Wi % 2 == 0, "gp_col2im_k4s2: bad arguments");
-  const long long total = (long long)NB * ch * Hi * Wi;
-  col2im_k4s2_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(col), bias, img,
-                                                                     NB, ch, Hi, Wi, act);
-  GP_CHECK_LAUNCH();
-  return GP_OK;
+  return launch_col2im(static_cast<const __nv_bfloat16*>(col), bias, img, NB, ch, Hi, Wi, act, stream);
+}
+
+int gp_col2im_k4s2_f32(const float* col, const float* bias, float* img, int NB, int ch, int Hi, int Wi, int act,
+                       void* stream) {
+  return launch_col2im(col, bias, img, NB, ch, Hi, Wi, act, stream);
 }
 
 int gp_image_bias_grad(const float* dout, const float* mul, float* dbias, int NB, int ch, int HW, void* stream) {
@@ -764,9 +681,20 @@ int gp_image_bias_grad(const float* dout, const float* mul, float* dbias, int NB
 
 int gp_head_fwd(const void* a, const float* w, const float* bias, float* out, int NB, int HW, int C, int O,
                 long long s_o, long long s_c, long long s_hw, void* stream) {
-  GP_REQUIRE(a && w && out && NB > 0 && HW > 0 && C > 0 && O > 0, "gp_head_fwd: bad arguments");
+  GP_REQUIRE(a && w && out && NB > 0 && HW > 0 && C > 0 && C % 8 == 0 && O > 0, "gp_head_fwd: bad arguments");
   dim3 grid(NB, O);
-  head_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(a), w, bias, out, HW, C, O,
+  head_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(a), nullptr, w, bias, out, HW, C,
+                                                       O, s_o, s_c, s_hw);
+  GP_CHECK_LAUNCH();
+  return GP_OK;
+}
+
+int gp_head_fwd_split(const void* a_hi, const void* a_lo, const float* w, const float* bias, float* out, int NB, int HW,
+                      int C, int O, long long s_o, long long s_c, long long s_hw, void* stream) {
+  GP_REQUIRE(a_hi && a_lo && w && out && NB > 0 && HW > 0 && C > 0 && C % 8 == 0 && O > 0, "gp_head_fwd_split: bad arguments");
+  dim3 grid(NB, O);
+  head_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(a_hi),
+                                                       static_cast<const __nv_bfloat16*>(a_lo), w, bias, out, HW, C, O,
                                                        s_o, s_c, s_hw);
   GP_CHECK_LAUNCH();
   return GP_OK;
@@ -774,19 +702,20 @@ int gp_head_fwd(const void* a, const float* w, const float* bias, float* out, in
 
 int gp_head_bwd(const float* dout, const void* a, const float* w, void* da, float* dw, float* dbias, int NB, int HW,
                 int C, int O, long long s_o, long long s_c, long long s_hw, void* stream) {
-  GP_REQUIRE(dout && a && w && NB > 0 && HW > 0 && C > 0 && O > 0, "gp_head_bwd: bad arguments");
+  GP_REQUIRE(dout && a && w && NB > 0 && HW > 0 && C > 0 && C % 8 == 0 && O > 0, "gp_head_bwd: bad arguments");
   if (da != nullptr) {
-    head_bwd_data_kernel<<<grid_for((long long)NB * HW * C), 256, 0, as_stream(stream)>>>(
+    head_bwd_data_kernel<<<grid_for((long long)NB * HW * (C / 8)), 256, 0, as_stream(stream)>>>(
         dout, w, static_cast<__nv_bfloat16*>(da), NB, HW, C, O, s_o, s_c, s_hw);
     GP_CHECK_LAUNCH();
   }
   if (dw != nullptr) {
-    int zsplit = (4 * num_sms()) / (((HW * C + 255) / 256) * O);
+    const int gx = (HW * (C / 8) + 127) / 128;
+    int zsplit = (4 * num_sms()) / (gx * O);
     if (zsplit < 1) zsplit = 1;
-    if (zsplit > 32) zsplit = 32;
+    if (zsplit > 64) zsplit = 64;
     if (zsplit > NB) zsplit = NB;
-    dim3 grid((HW * C + 255) / 256, O, zsplit);
-    head_bwd_weight_kernel<<<grid, 256, 0, as_stream(stream)>>>(dout, static_cast<const __nv_bfloat16*>(a), dw, dbias, NB,
+    dim3 grid(gx, O, zsplit);
+    head_bwd_weight_kernel<<<grid, 128, 0, as_stream(stream)>>>(dout, static_cast<const __nv_bfloat16*>(a), dw, dbias, NB,
                                                                 HW, C, O, s_o, s_c, s_hw);
     GP_CHECK_LAUNCH();
   }

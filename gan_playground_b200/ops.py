@@ -41,6 +41,24 @@ _SIGS = {
 _bound = {}
 
 
+class CallProfiler:
+    """Times EVERY C-ABI call with CUDA events on the launching stream (tools/step_breakdown.py): records
+    (entry point, raw argument tuple, start event, end event). Eager steps only — never active inside a graph capture."""
+
+    active = None
+    note = None   # (label, algorithmic FLOPs) of the next GEMM call, set by conv_fwd / conv_wgrad
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        CallProfiler.active = self
+        return self
+
+    def __exit__(self, *exc):
+        CallProfiler.active = None
+
+
 def _fn(name):
     f = _bound.get(name)
     if f is None:
@@ -48,7 +66,20 @@ def _fn(name):
         f.argtypes = _SIGS[name]
         f.restype = ctypes.c_int
         _bound[name] = f
-    return f
+    prof = CallProfiler.active
+    if prof is None:
+        return f
+
+    def timed(*args):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = f(*args)
+        b.record()
+        prof.records.append((name, args, a, b, CallProfiler.note))
+        CallProfiler.note = None
+        return rc
+
+    return timed
 
 
 def exported_symbols():
@@ -102,6 +133,8 @@ class GemmProfiler:
 
 
 def _timed(name, flops, fn):
+    if CallProfiler.active is not None:
+        CallProfiler.note = (name, flops)
     prof = GemmProfiler.active
     if prof is None:
         return fn()
