@@ -144,6 +144,8 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: global batch 1024 sharded over ranks; weak: 1024 images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH,
+                    help="diagnostics only: the benchmark configuration is the default 1024")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of one CUDA graph replay per step")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -160,7 +162,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
-    per_gpu = GLOBAL_BATCH if args.scaling == "weak" else GLOBAL_BATCH // world
+    per_gpu = args.global_batch if args.scaling == "weak" else args.global_batch // world
     global_batch = per_gpu * world
 
     torch.manual_seed(0)

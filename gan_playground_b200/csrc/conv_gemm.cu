@@ -3,6 +3,9 @@
 
 #include <cudaTypedefs.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.h"
 
 namespace gp {
@@ -84,6 +87,17 @@ static int pick_bn(int n) {
   return 64;
 }
 
+// Experiment hook: GP_TILE_FWD / GP_TILE_WGRAD = "<BN>x<MT>" (e.g. "256x2") overrides the tile-shape heuristics.
+static bool tile_override(const char* var, int* bn, int* mt) {
+  const char* e = getenv(var);
+  int b = 0, m = 0;
+  if (e == nullptr || sscanf(e, "%dx%d", &b, &m) != 2) return false;
+  if ((b != 64 && b != 128 && b != 256) || (m != 1 && m != 2)) return false;
+  *bn = b;
+  *mt = m;
+  return true;
+}
+
 template <int MODE, int BNV, int MTV>
 static int launch_cfg(const ConvGemmParams& prm, int grid, cudaStream_t st) {
   auto kfn = conv_gemm_kernel<MODE, BNV, MTV>;
@@ -100,7 +114,7 @@ static int launch_cfg(const ConvGemmParams& prm, int grid, cudaStream_t st) {
 template <int MODE>
 static int launch(const ConvGemmParams& prm, int bn, int mt, int grid, cudaStream_t st) {
   if (grid <= 0) return GP_OK;
-  if (bn == 256) return launch_cfg<MODE, 256, 1>(prm, grid, st);
+  if (bn == 256) return mt == 2 ? launch_cfg<MODE, 256, 2>(prm, grid, st) : launch_cfg<MODE, 256, 1>(prm, grid, st);
   if (bn == 128) return mt == 2 ? launch_cfg<MODE, 128, 2>(prm, grid, st) : launch_cfg<MODE, 128, 1>(prm, grid, st);
   return mt == 2 ? launch_cfg<MODE, 64, 2>(prm, grid, st) : launch_cfg<MODE, 64, 1>(prm, grid, st);
 }
@@ -121,7 +135,7 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
   const int Cin = a->Cin;
   int ntaps_total = 0;
   int rc;
-  const int bn = pick_bn(a->Nout);
+  int bn = pick_bn(a->Nout);
   // narrow outputs: two M=128 sub-tiles share one B tile (MT = 2) when that still leaves >= one wave of tiles
   int mt_sub = 1;
   {
@@ -129,6 +143,12 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
                                                               : (long long)a->NB * a->Hin * a->Win;
     const long long tiles2 = (small_px / (2 * kBlockM)) * ((a->Nout + bn - 1) / bn) * (a->kind == GP_KIND_CONVT_K4S2 ? 4 : 1);
     if (bn <= 128 && tiles2 >= num_sms()) mt_sub = 2;
+    // 256x256 tiles (single TMEM accumulator buffer, no epilogue overlap) pay off only for long K loops, where the
+    // mainloop is bound by operand traffic from L2 and the exposed epilogue is a few percent (measured: K >= 8192)
+    const int taps_tile = a->kind == GP_KIND_CONV_K4S2 ? 16 : (a->kind == GP_KIND_CONVT_K4S2 ? 4 : (a->kind == GP_KIND_CONV_K3S1 ? 9 : 1));
+    const long long ksteps = (long long)taps_tile * ((a->Cin + kBlockK - 1) / kBlockK) * (a->in_lo != nullptr ? 3 : 1);
+    if (bn == 256 && ksteps >= 128 && tiles2 >= num_sms()) mt_sub = 2;
+    tile_override("GP_TILE_FWD", &bn, &mt_sub);
   }
   const int tile_px = mt_sub * kBlockM;
   const int n_halves = a->in_lo != nullptr ? 2 : 1;  // bf16x3: hi and lo halves of the activation operand
@@ -332,11 +352,17 @@ extern "C" int gp_conv_wgrad(const gp_conv_wgrad_t* a, void* stream) {
   prm.N = Cg;
   prm.dw = a->dw;
   prm.ldw = ntaps * Cg;
-  const int bn = pick_bn(Cg);
-  const int mt_sub = (bn <= 128 && a->Cd >= 2 * kBlockM) ? 2 : 1;  // share the narrow gathered tile between two M=128 MMAs
+  // narrow gathered operand with several taps: tile the flattened (tap, channel) columns so that a 256-wide tile
+  // spans 256 / Cg taps (dW rows are [tap][channel], i.e. contiguous in that index)
+  prm.wg_flat = (Cg % 64 == 0 && ntaps > 1 && Cg < 256) ? 1 : 0;
+  int bn = pick_bn(prm.wg_flat ? ntaps * Cg : Cg);
+  // two M=128 sub-tiles share the gathered tile whenever dW has >= 256 rows: the wgrad mainloop is bound by operand
+  // traffic from L2 (48 KB per 128x256x64 MMA block), a 256-row tile moves 1.5x fewer bytes per FLOP
+  int mt_sub = a->Cd >= 2 * kBlockM ? 2 : 1;
+  tile_override("GP_TILE_WGRAD", &bn, &mt_sub);
   const int mtiles = (a->Cd + mt_sub * kBlockM - 1) / (mt_sub * kBlockM);
-  const int ntn = (Cg + bn - 1) / bn;
-  const int base_tiles = mtiles * ntaps * ntn;
+  const int ntn = ((prm.wg_flat ? ntaps * Cg : Cg) + bn - 1) / bn;
+  const int base_tiles = mtiles * (prm.wg_flat ? 1 : ntaps) * ntn;
   prm.kblocks_total = ((a->NB + prm.Nt - 1) / prm.Nt) * (prm.Hs / prm.Ht) * (prm.Ws / prm.Wt);
   // split-K over pixel blocks: aim for >= 2 waves of tiles, but keep >= 8 k-blocks per split.
   int splits = (2 * num_sms() + base_tiles - 1) / base_tiles;

@@ -13,7 +13,7 @@
 //              both operands MN-major (channels contiguous in NHWC), split-K over pixels, fp32 atomics.
 //
 // Tile = (MT * 128) x BN: MT = 2 issues two M=128 MMAs per K step that share the B tile, which doubles the
-// arithmetic intensity of narrow (N <= 128) layers. Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM
+// arithmetic intensity against L2 / shared memory (256-row tiles). Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM
 // allocator + single-thread tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld -> bias / residual / activation ->
 // global, optional per-channel BatchNorm statistics). Two TMEM accumulator buffers: the epilogue of tile i overlaps
 // the MMAs of tile i+1.
@@ -65,6 +65,8 @@ struct alignas(64) ConvGemmParams {
   int ldw;
   int splits;
   int kblocks_total;  // WGRAD: number of 64-pixel blocks
+  int wg_flat;        // WGRAD: dW columns are tiled over the flattened (tap, channel) index (needs N % 64 == 0), so one
+                      // tile can span several taps of a narrow gathered operand; 0 = one tap per tile
   float* col_sum;     // optional fused per-channel statistics of the (pre-activation) output
   float* col_sumsq;
 };
@@ -80,7 +82,10 @@ struct GemmCfg {
   static constexpr int kBudget = 204 * 1024;  // operand ring; + statistics + bias + barriers + alignment slack < 227 KB
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kAccCols = MT * BN;      // TMEM columns of one accumulator buffer
-  static constexpr int kTmemCols = 2 * kAccCols;  // 128 / 256 / 512: powers of two >= 32
+  // two accumulator buffers (epilogue of tile i overlaps the MMAs of tile i+1) when they fit the 512 TMEM columns;
+  // the 256x256 tile uses all of TMEM for one buffer and trades that overlap for 1.5x less operand traffic per FLOP
+  static constexpr int kAccBufs = 2 * kAccCols <= 512 ? 2 : 1;
+  static constexpr int kTmemCols = kAccBufs * kAccCols;  // 128 / 256 / 512: powers of two >= 32
   static constexpr int kChunks = MT * (BN / 32);  // 32-column TMEM loads per accumulator buffer and epilogue warp
   static constexpr int kSmemBytes = kStages * kStageBytes + kStatBytes + kBiasBytes + kBarBytes + 1024;  // +1024: alignment slack
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM allocation must be a power of two <= 512");
@@ -200,7 +205,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
 
   // ---- tile bookkeeping shared by all roles
   const int wtiles = p.Ws / p.Wt, htiles = p.Hs / p.Ht;
-  const int ntiles_n = (p.N + BN - 1) / BN;
+  // WGRAD: dW columns seen by the tiler (all taps side by side when wg_flat) and tile slots per column tile
+  const int ncols = (MODE == MODE_WGRAD && p.wg_flat) ? p.ldw : p.N;
+  const int tap_slots = (MODE == MODE_WGRAD && p.wg_flat) ? 1 : p.taps_per_phase;
+  const int ntiles_n = (ncols + BN - 1) / BN;
   int ksteps_fwd = 0, cchunks = 0, mtiles = 0;
   WorkPlan plan;
   if constexpr (MODE == MODE_FWD) {
@@ -211,7 +219,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     plan.num_items = plan.num_tiles > (int)blockIdx.x ? (plan.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   } else {
     mtiles = (p.M + MT * kBlockM - 1) / (MT * kBlockM);
-    plan.base_tiles = mtiles * p.taps_per_phase * ntiles_n;
+    plan.base_tiles = mtiles * tap_slots * ntiles_n;
     plan.kblocks_total = p.kblocks_total;
     plan.per = (p.kblocks_total + p.splits - 1) / p.splits;
     plan.num_tiles = p.splits * plan.base_tiles;
@@ -246,9 +254,24 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         }
       } else {
         const int nt = tile % ntiles_n;
-        const int tp = (tile / ntiles_n) % p.taps_per_phase;
-        const int mt = (tile / (ntiles_n * p.taps_per_phase)) % mtiles;
-        const Tap t = p.taps[tp];
+        const int tp = (tile / ntiles_n) % tap_slots;
+        const int mt = (tile / (ntiles_n * tap_slots)) % mtiles;
+        // 64-column chunks of the gathered operand: (tap, first channel) of each; columns past the end read channel
+        // N, which TMA zero-fills
+        Tap tj[BN / 64];
+        int chj[BN / 64];
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j) {
+          const int col = nt * BN + j * 64;
+          if (p.wg_flat) {
+            const int tap = col / p.N;
+            tj[j] = p.taps[tap < p.taps_per_phase ? tap : 0];
+            chj[j] = tap < p.taps_per_phase ? col % p.N : p.N;
+          } else {
+            tj[j] = p.taps[tp];
+            chj[j] = col;
+          }
+        }
         for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
           const int w0 = (kb % wtiles) * p.Wt;
           const int h0 = ((kb / wtiles) % htiles) * p.Ht;
@@ -261,8 +284,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             tma_load_4d(sa + i * 8192, &p.map_d, &full_bar[stage], mt * MT * kBlockM + i * 64, w0, h0, n0);
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j)
-            tma_load_4d(sa + Cfg::kABytes + j * 8192, &p.map_g[t.map], &full_bar[stage], nt * BN + j * 64,
-                        w0 + t.dw, h0 + t.dh, n0);
+            tma_load_4d(sa + Cfg::kABytes + j * 8192, &p.map_g[tj[j].map], &full_bar[stage], chj[j], w0 + tj[j].dw,
+                        h0 + tj[j].dh, n0);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -281,8 +304,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       const WorkItem wk = plan.template item<MODE>(it);
       const int ksteps = (MODE == MODE_FWD) ? ksteps_fwd : wk.kb1 - wk.kb0;
       if (ksteps <= 0) continue;
-      const int acc = na & 1;
-      const uint32_t acc_phase = (na >> 1) & 1;
+      const int acc = na % Cfg::kAccBufs;
+      const uint32_t acc_phase = (na / Cfg::kAccBufs) & 1;
       ++na;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
@@ -337,8 +360,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       const WorkItem wk = plan.template item<MODE>(it);
       if (MODE == MODE_WGRAD && wk.kb1 <= wk.kb0) continue;
       const int tile = wk.tile;
-      const int acc = na & 1;
-      const uint32_t acc_phase = (na >> 1) & 1;
+      const int acc = na % Cfg::kAccBufs;
+      const uint32_t acc_phase = (na / Cfg::kAccBufs) & 1;
       ++na;
       float bnext[kBiasPerThread];
       const bool more = it + 1 < plan.num_items;
@@ -472,9 +495,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         }
       } else {
         const int nt = tile % ntiles_n;
-        const int tp = (tile / ntiles_n) % p.taps_per_phase;
-        const int mt = (tile / (ntiles_n * p.taps_per_phase)) % mtiles;
-        const int nchunks = min(BN / 32, (p.N - nt * BN + 31) / 32);
+        const int tp = (tile / ntiles_n) % tap_slots;
+        const int mt = (tile / (ntiles_n * tap_slots)) % mtiles;
+        const int nchunks = min(BN / 32, (ncols - nt * BN + 31) / 32);
+        const int col_base = p.wg_flat ? 0 : p.taps[tp].koff;  // dW row = [tap][channel]: flat columns are contiguous
 #pragma unroll 1
         for (int c = 0; c < nchunks; ++c) {
           const int col0 = nt * BN + c * 32;
@@ -488,11 +512,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             else if (c + 1 < nchunks) tmem_ld_32x32(tbase + (c + 1) * 32, r);
             const int m = (mt * MT + mi) * kBlockM + q * 32 + lane;
             if (m < p.M) {
-              float* drow = p.dw + static_cast<long long>(m) * p.ldw + p.taps[tp].koff + col0;
+              float* drow = p.dw + static_cast<long long>(m) * p.ldw + col_base + col0;
 #pragma unroll
               for (int g = 0; g < 8; ++g) {
                 // 16-byte vector reductions (red.global.add.v4.f32): 4x fewer L2 atomic transactions than scalar
-                if (col0 + g * 4 < p.N) red_add_v4(drow + g * 4, v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                if (col0 + g * 4 < ncols) red_add_v4(drow + g * 4, v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
               }
             }
           }

@@ -81,6 +81,83 @@ __global__ void pack_conv_weight_n1_kernel(const float* __restrict__ src, __nv_b
   }
 }
 
+// ---- 16-tap (4x4 kernel) fast paths: 16-byte global accesses on both sides of the shared-memory transpose.
+// n_dim == 0: one block = one output row n x 128 channels: reads 128*16 contiguous floats, writes 16 runs of 128 bf16.
+constexpr int kPack16C = 128;
+__global__ void __launch_bounds__(256) pack_conv_weight16_n0_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                                    __nv_bfloat16* __restrict__ lo, int N, int C, long long ld,
+                                                                    const float* __restrict__ inv_scale) {
+  __shared__ float s_tile[kPack16C * 17];  // [c][16 taps + 1 pad]
+  const int n = blockIdx.y, c0 = blockIdx.x * kPack16C;  // C % 128 == 0 on this path
+  const float sc = inv_scale ? 1.f / __ldg(inv_scale) : 1.f;
+  const float4* sp = reinterpret_cast<const float4*>(src + ((long long)n * C + c0) * 16);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int i = threadIdx.x + k * 256;  // float4 index: c = i / 4, taps 4*(i%4)..+3
+    const float4 v = __ldg(sp + i);
+    float* d = s_tile + (i >> 2) * 17 + (i & 3) * 4;
+    d[0] = v.x * sc, d[1] = v.y * sc, d[2] = v.z * sc, d[3] = v.w * sc;
+  }
+  __syncthreads();
+  // thread -> (tap t, group of 8 channels)
+  const int t = threadIdx.x >> 4, g = threadIdx.x & 15;
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = s_tile[(g * 8 + j) * 17 + t];
+  const long long o = (long long)n * ld + (long long)t * C + c0 + g * 8;
+  store8_bf16(dst + o, lo ? lo + o : nullptr, f);
+}
+// n_dim == 1: one block = 32 source rows (channels c) x 8 output rows n: reads 32 runs of 128 floats, writes
+// 8*16 runs of 32 bf16.
+__global__ void __launch_bounds__(256) pack_conv_weight16_n1_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                                    __nv_bfloat16* __restrict__ lo, int N, int C, long long ld,
+                                                                    const float* __restrict__ inv_scale) {
+  __shared__ float s_tile[32 * 129];  // [c][8 n x 16 taps + 1 pad]
+  const int c0 = blockIdx.x * 32, n0 = blockIdx.y * 8;  // C % 32 == 0, N % 8 == 0 on this path
+  const float sc = inv_scale ? 1.f / __ldg(inv_scale) : 1.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = threadIdx.x + k * 256;  // float4 index over [32 c][32 float4]
+    const int c = i >> 5, q = i & 31;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + ((long long)(c0 + c) * N + n0) * 16) + q);
+    float* d = s_tile + c * 129 + q * 4;
+    d[0] = v.x * sc, d[1] = v.y * sc, d[2] = v.z * sc, d[3] = v.w * sc;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int i = threadIdx.x + k * 256;  // (n_local*16 + t) * 4 + channel group of 8
+    const int g = i & 3, q = i >> 2;      // q = n_local * 16 + t
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = s_tile[(g * 8 + j) * 129 + q];
+    const long long o = (long long)(n0 + (q >> 4)) * ld + (long long)(q & 15) * C + c0 + g * 8;
+    store8_bf16(dst + o, lo ? lo + o : nullptr, f);
+  }
+}
+// packed gradient [M][16][N] -> (M, N, 16): one block = one m x 64 n
+__global__ void __launch_bounds__(256) unpack_conv_wgrad16_kernel(const float* __restrict__ src, float* __restrict__ dst, int M,
+                                                                  int N) {
+  __shared__ float s_tile[16 * 65];  // [t][64 n + 1 pad]
+  const int m = blockIdx.y, n0 = blockIdx.x * 64;  // N % 64 == 0 on this path
+  {
+    const int t = threadIdx.x >> 4, q = threadIdx.x & 15;  // 16 taps x 16 float4
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + ((long long)m * 16 + t) * N + n0) + q);
+    float* d = s_tile + t * 65 + q * 4;
+    d[0] = v.x, d[1] = v.y, d[2] = v.z, d[3] = v.w;
+  }
+  __syncthreads();
+  {
+    const int n = threadIdx.x >> 2, tq = threadIdx.x & 3;  // 64 n x 4 float4 of taps
+    float4 v;
+    v.x = s_tile[(tq * 4 + 0) * 65 + n];
+    v.y = s_tile[(tq * 4 + 1) * 65 + n];
+    v.z = s_tile[(tq * 4 + 2) * 65 + n];
+    v.w = s_tile[(tq * 4 + 3) * 65 + n];
+    reinterpret_cast<float4*>(dst + ((long long)m * N + n0 + n) * 16)[tq] = v;
+  }
+}
+
 // packed fp32 gradient [M][tap][N] -> torch layout (M, N, tap) fp32, tile = one m x 64 n, transposed through smem
 constexpr int kUnpackNT = 64;
 __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int M, int N, int taps) {
@@ -475,7 +552,12 @@ static inline int grid_for(long long n, int block = 256, int max_blocks = 148 * 
 static int launch_pack_conv_weight(const float* src, __nv_bfloat16* dst, __nv_bfloat16* lo, int D0, int D1, int taps,
                                    int n_dim_flags, long long ld, const float* inv_scale, cudaStream_t st) {
   const int n_dim = n_dim_flags & 1, flip = (n_dim_flags >> 1) & 1;
-  if (n_dim == 0) {
+  const int N = n_dim == 0 ? D0 : D1, C = n_dim == 0 ? D1 : D0;
+  if (taps == 16 && !flip && n_dim == 0 && C % kPack16C == 0) {
+    pack_conv_weight16_n0_kernel<<<dim3(C / kPack16C, N), 256, 0, st>>>(src, dst, lo, N, C, ld, inv_scale);
+  } else if (taps == 16 && !flip && n_dim == 1 && C % 32 == 0 && N % 8 == 0) {
+    pack_conv_weight16_n1_kernel<<<dim3(C / 32, N / 8), 256, 0, st>>>(src, dst, lo, N, C, ld, inv_scale);
+  } else if (n_dim == 0) {
     dim3 grid((D1 + kPackCT - 1) / kPackCT, D0);
     pack_conv_weight_n0_kernel<<<grid, 256, (size_t)kPackCT * (taps + 1) * sizeof(float), st>>>(src, dst, lo, D0, D1, taps,
                                                                                              ld, flip, inv_scale);
@@ -533,6 +615,11 @@ int gp_split_conv_weight(const float* src, void* dst, int D0, int D1, int taps, 
 
 int gp_unpack_conv_wgrad(const float* src, float* dst, int M, int N, int taps, void* stream) {
   GP_REQUIRE(src && dst && M > 0 && N > 0 && taps > 0 && taps <= 64, "gp_unpack_conv_wgrad: bad arguments");
+  if (taps == 16 && N % 64 == 0) {
+    unpack_conv_wgrad16_kernel<<<dim3(N / 64, M), 256, 0, as_stream(stream)>>>(src, dst, M, N);
+    GP_CHECK_LAUNCH();
+    return GP_OK;
+  }
   dim3 grid((N + kUnpackNT - 1) / kUnpackNT, M);
   unpack_conv_wgrad_kernel<<<grid, 256, (size_t)taps * (kUnpackNT + 1) * sizeof(float), as_stream(stream)>>>(src, dst, M,
                                                                                                           N, taps);

@@ -15,7 +15,7 @@ from gan_playground_b200 import ops
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=1024)
-    ap.add_argument("--cases", default="img_fwd,img_dgrad,d1_fwd,d1_fwd_stats,g2_fwd_stats,d3_fwd,d2_wgrad,d3_wgrad,d1_wgrad")
+    ap.add_argument("--cases", default="img_fwd,img_dgrad,d1_fwd,d1_fwd_stats,d2_fwd,d3_fwd,g0_fwd,g1_fwd,g2_fwd,g2_fwd_stats,d1_wgrad,d2_wgrad,d3_wgrad")
     ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
     B = args.batch
@@ -37,6 +37,10 @@ def main():
                                                  stats=torch.zeros(2, 256, device=dev))
     cases["g2_fwd_stats"] = lambda: ops.conv_fwd(X["a256_16"], W["g2"], Bv[128], ops.KIND_CONVT_K4S2, 32, 32,
                                                  stats=torch.zeros(2, 128, device=dev))
+    cases["d2_fwd"] = lambda: ops.conv_fwd(X["a256_16"], W["d2"], Bv[512], ops.KIND_CONV_K4S2, 8, 8)
+    cases["g0_fwd"] = lambda: ops.conv_fwd(X["a1024_4"], W["g0"], Bv[512], ops.KIND_CONVT_K4S2, 8, 8)
+    cases["g1_fwd"] = lambda: ops.conv_fwd(X["a512_8"], W["g1"], Bv[256], ops.KIND_CONVT_K4S2, 16, 16)
+    cases["g2_fwd"] = lambda: ops.conv_fwd(X["a256_16"], W["g2"], Bv[128], ops.KIND_CONVT_K4S2, 32, 32)
     cases["d3_fwd"] = lambda: ops.conv_fwd(X["a512_8"], W["d3"], Bv[1024], ops.KIND_CONV_K4S2, 4, 4)
     cases["d1_wgrad"] = lambda: ops.conv_wgrad(X["a256_16"], X["a128"], ops.KIND_CONV_K4S2, 16)
     cases["d2_wgrad"] = lambda: ops.conv_wgrad(X["a512_8"], X["a256_16"], ops.KIND_CONV_K4S2, 16)
@@ -45,8 +49,9 @@ def main():
     X = {"col": act(B, 32, 32, 64), "a128": act(B, 32, 32, 128), "a256_16": act(B, 16, 16, 256),
          "a512_8": act(B, 8, 8, 512), "a1024_4": act(B, 4, 4, 1024)}
     W = {"img": wt(128, 64), "imgT": wt(64, 128), "d1": wt(256, 16 * 128), "g2": wt(128, 16 * 256),
-         "d3": wt(1024, 16 * 512)}
-    Bv = {n: torch.randn(n, device=dev) * 0.1 for n in (128, 256, 1024)}
+         "d3": wt(1024, 16 * 512),
+         "d2": wt(512, 16 * 256), "g0": wt(512, 16 * 1024), "g1": wt(256, 16 * 512)}
+    Bv = {n: torch.randn(n, device=dev) * 0.1 for n in (128, 256, 512, 1024)}
 
     for name in args.cases.split(","):
         fn = cases[name]
