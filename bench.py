@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH,
                     help="diagnostics only: the benchmark configuration is the default 1024")
+    ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam + flat gradient buckets instead of optim.FusedAdam")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of one CUDA graph replay per step")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -155,13 +156,17 @@ def main():
     from gan_playground_b200 import _lib, config, ops, parallel
     from gan_playground_b200.criterion import GANLoss
     from gan_playground_b200.engine import DcganStep
+    from gan_playground_b200.optim import FusedAdam
     from gan_playground_b200.models import dcgan
 
     rank, world = parallel.init()
+    peer_sync = False
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
+    if world > 1:
+        peer_sync = parallel.init_peer_sync(dev)   # SyncBN sums over NVLink peer memory (falls back to NCCL)
     per_gpu = args.global_batch if args.scaling == "weak" else args.global_batch // world
     global_batch = per_gpu * world
 
@@ -175,8 +180,12 @@ def main():
     parallel.broadcast_module(netG)
     parallel.broadcast_module(netD)
     use_graph = not args.no_graph
-    optG = torch.optim.Adam(netG.parameters(), lr=4e-4, betas=(0.5, 0.999), capturable=use_graph)
-    optD = torch.optim.Adam(netD.parameters(), lr=1e-4, betas=(0.5, 0.999), capturable=use_graph)
+    if args.torch_adam:   # the optimiser the reference scripts build themselves (main_dcgan.py:55-56)
+        optG = torch.optim.Adam(netG.parameters(), lr=4e-4, betas=(0.5, 0.999), capturable=use_graph)
+        optD = torch.optim.Adam(netD.parameters(), lr=1e-4, betas=(0.5, 0.999), capturable=use_graph)
+    else:                 # same update as one kernel per network over flat buffers (+ ZeRO-1 sharding across ranks)
+        optG = FusedAdam(netG.parameters(), lr=4e-4, betas=(0.5, 0.999), shard=world > 1)
+        optD = FusedAdam(netD.parameters(), lr=1e-4, betas=(0.5, 0.999), shard=world > 1)
     crit = GANLoss('vanilla', target_real_label=0.9, target_fake_label=0.1, target_fake_G_label=0.9).to(dev)
     netG.train(), netD.train()
     # loop body of main_dcgan.py:68-95 (+ DP gradient all-reduce before each optimiser step), eager or as one CUDA graph
@@ -261,6 +270,9 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": global_batch, "per_gpu_batch": per_gpu,
                        "parallelism": "dp%d" % world, "precision": config.precision(), "cuda_graph": use_graph,
+                       "optimizer": "torch.optim.Adam" if args.torch_adam else "FusedAdam(flat%s)" % (", zero1" if world > 1 else ""),
+                       "syncbn": "n/a (1 rank)" if world == 1 else ("one-shot NVLink peer exchange fused with the statistics finalize"
+                                                                   if peer_sync else "NCCL all-reduce"),
                        "l2": "no flush needed: per-step working set (~3.4 GB of activations at 1024 img/GPU) >> 126 MB L2"},
             "steps_per_sec": 1e3 / ms_per_step,
             "tflops_minimal_step": FLOPS_PER_IMG * global_batch / (ms_per_step * 1e-3) / 1e12,
@@ -272,6 +284,14 @@ def main():
             cb = cpu_reference(64, 2, 1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        # Tearing down an NCCL communicator while CUDA graphs that captured its kernels are alive can block forever
+        # (seen at N=8: the JSON line was out, destroy_process_group() never returned). All ranks are past their last
+        # collective here, so drain the device and leave without the destructor path.
+        torch.cuda.synchronize()
+        os._exit(0)
     parallel.shutdown()
 
 

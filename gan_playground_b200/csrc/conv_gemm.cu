@@ -135,19 +135,32 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
   const int Cin = a->Cin;
   int ntaps_total = 0;
   int rc;
-  int bn = pick_bn(a->Nout);
-  // narrow outputs: two M=128 sub-tiles share one B tile (MT = 2) when that still leaves >= one wave of tiles
-  int mt_sub = 1;
+  // Tile shape: the candidate (BN, MT) with the smallest estimated time = waves x tile MACs x relative cost per MAC.
+  // Costs are measured ratios on B200 (tools/prof_gemm.py): 128x256 is the reference; 256x256 (no epilogue overlap)
+  // wins only for long K loops; narrower tiles move more operand bytes per FLOP but fill the 148 SMs at small batch.
+  int bn = 0, mt_sub = 1;
   {
     const long long small_px = (a->kind == GP_KIND_CONV_K4S2) ? (long long)a->NB * a->Hout * a->Wout
                                                               : (long long)a->NB * a->Hin * a->Win;
-    const long long tiles2 = (small_px / (2 * kBlockM)) * ((a->Nout + bn - 1) / bn) * (a->kind == GP_KIND_CONVT_K4S2 ? 4 : 1);
-    if (bn <= 128 && tiles2 >= num_sms()) mt_sub = 2;
-    // 256x256 tiles (single TMEM accumulator buffer, no epilogue overlap) pay off only for long K loops, where the
-    // mainloop is bound by operand traffic from L2 and the exposed epilogue is a few percent (measured: K >= 8192)
+    const int phases = a->kind == GP_KIND_CONVT_K4S2 ? 4 : 1;
     const int taps_tile = a->kind == GP_KIND_CONV_K4S2 ? 16 : (a->kind == GP_KIND_CONVT_K4S2 ? 4 : (a->kind == GP_KIND_CONV_K3S1 ? 9 : 1));
     const long long ksteps = (long long)taps_tile * ((a->Cin + kBlockK - 1) / kBlockK) * (a->in_lo != nullptr ? 3 : 1);
-    if (bn == 256 && ksteps >= 128 && tiles2 >= num_sms()) mt_sub = 2;
+    static const struct { int bn, mt; double cost; } cand[] = {
+        {256, 1, 1.00}, {256, 2, 0.92}, {128, 2, 1.15}, {128, 1, 1.35}, {64, 2, 1.7}, {64, 1, 2.2}};
+    double best = 0;
+    for (const auto& c : cand) {
+      if (c.bn > 64 && c.bn / 2 >= a->Nout) continue;            // more than half of the tile would be padding
+      if (c.bn == 256 && c.mt == 2 && ksteps < 128) continue;   // exposed epilogue not amortised
+      const long long tiles = phases * ((small_px + c.mt * kBlockM - 1) / (c.mt * kBlockM)) * ((a->Nout + c.bn - 1) / c.bn);
+      const long long waves = (tiles + num_sms() - 1) / num_sms();
+      // short K loops: the per-tile epilogue and pipeline fill are not hidden; charge them as extra K steps
+      const double t = (double)waves * c.mt * c.bn * c.cost * (double)(ksteps + 6);
+      if (bn == 0 || t < best) {
+        best = t;
+        bn = c.bn;
+        mt_sub = c.mt;
+      }
+    }
     tile_override("GP_TILE_FWD", &bn, &mt_sub);
   }
   const int tile_px = mt_sub * kBlockM;
@@ -364,8 +377,10 @@ extern "C" int gp_conv_wgrad(const gp_conv_wgrad_t* a, void* stream) {
   const int ntn = ((prm.wg_flat ? ntaps * Cg : Cg) + bn - 1) / bn;
   const int base_tiles = mtiles * (prm.wg_flat ? 1 : ntaps) * ntn;
   prm.kblocks_total = ((a->NB + prm.Nt - 1) / prm.Nt) * (prm.Hs / prm.Ht) * (prm.Ws / prm.Wt);
-  // split-K over pixel blocks: aim for >= 2 waves of tiles, but keep >= 8 k-blocks per split.
-  int splits = (2 * num_sms() + base_tiles - 1) / base_tiles;
+  // split-K over pixel blocks. The hybrid stream-K schedule balances any tile count, so splits are only there to keep
+  // the pixel range swept by one wave of CTAs small enough for its operand tiles to be shared in L2 (~192 K blocks
+  // per split); every extra split costs one more fp32 atomic pass over dW.
+  int splits = (prm.kblocks_total + 191) / 192;
   const int max_splits = prm.kblocks_total / 8 > 0 ? prm.kblocks_total / 8 : 1;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;

@@ -12,6 +12,7 @@ networks are cleared before capture so the staging kernels are part of the graph
 import torch
 
 from . import parallel
+from .optim import FusedAdam
 
 
 def _clear_caches(*nets):
@@ -26,7 +27,10 @@ class DcganStep:
     def __init__(self, netG, netD, criterion, optG, optD, batch, z_dim, device, use_graph=False, warmup=3):
         self.netG, self.netD, self.crit, self.optG, self.optD = netG, netD, criterion, optG, optD
         self.batch, self.z_dim, self.dev = batch, z_dim, device
-        self.bucketD, self.bucketG = parallel.GradBucket(netD), parallel.GradBucket(netG)
+        # FusedAdam owns flat parameter / gradient buffers and does the gradient collective itself; any other optimiser
+        # (torch.optim.Adam as in the reference scripts) gets a flat gradient bucket per network for the all-reduce
+        self.bucketD = None if isinstance(optD, FusedAdam) else parallel.GradBucket(netD)
+        self.bucketG = None if isinstance(optG, FusedAdam) else parallel.GradBucket(netG)
         self.use_graph = use_graph
         self.graph = None
         self.x_static = torch.zeros(batch, netD.img_dim, netD.resolution, netD.resolution, device=device)
@@ -38,7 +42,7 @@ class DcganStep:
     # ---- the loop body; `log(i, t)` receives the six scalars as 0-dim device tensors
     def _body(self, inputs, z1, z2, log):
         netG, netD, crit = self.netG, self.netD, self.crit
-        self.bucketD.attach()                                    # optD.zero_grad()
+        self._zero(self.optD, self.bucketD)                      # optD.zero_grad()
         outD = netD(inputs)
         log(3, outD.mean())
         lossD_real = crit(outD, True)
@@ -48,17 +52,28 @@ class DcganStep:
         log(4, outD.mean())
         lossD_fake = crit(outD, False)
         lossD_fake.backward()
-        self.bucketD.all_reduce_mean()
-        self.optD.step()
-        self.bucketG.attach()                                    # optG.zero_grad()
+        self._step(self.optD, self.bucketD)                      # (gradient all-reduce +) optD.step()
+        self._zero(self.optG, self.bucketG)                      # optG.zero_grad()
         outG = netG(z2)
         outD = netD(outG)
         log(5, outD.mean())
         lossG = crit(outD, False, True)
         lossG.backward()
-        self.bucketG.all_reduce_mean()
-        self.optG.step()
+        self._step(self.optG, self.bucketG)                      # (gradient all-reduce +) optG.step()
         log(0, lossD_real.detach()), log(1, lossD_fake.detach()), log(2, lossG.detach())
+
+    @staticmethod
+    def _zero(opt, bucket):
+        if bucket is None:
+            opt.zero_grad()
+        else:
+            bucket.attach()
+
+    @staticmethod
+    def _step(opt, bucket):
+        if bucket is not None:
+            bucket.all_reduce_mean()
+        opt.step()
 
     def _noise(self):
         return torch.randn(self.batch, self.z_dim, device=self.dev), torch.randn(self.batch, self.z_dim, device=self.dev)

@@ -25,7 +25,9 @@ class WeightCache:
     def get(self, key, param, make):
         if not param.is_leaf:  # derived weight (e.g. W / sigma of spectral norm): new tensor every forward
             return make()
-        ver = param._version
+        # _version: bumped by torch in-place updates (torch.optim.Adam); _gp_epoch: bumped by optim.FusedAdam, whose
+        # kernel updates the storage behind autograd's back
+        ver = (param._version, getattr(param, "_gp_epoch", 0))
         ent = self._d.get(key)
         if ent is not None and ent[0] == ver and ent[1] == param.data_ptr():
             return ent[2]
@@ -59,8 +61,13 @@ def _bn_forward(y, gamma, beta, bufs, act, training=True, st=None):
     if training or rm is None:
         if st is None:
             st = ops.bn_stats_f32(y) if f32 else ops.bn_stats(y)
-        parallel.all_reduce_sum_(st)
-        fin = ops.bn_finalize(st, count, gamma, beta, rm, rv, nbt, BN_EPS, BN_MOMENTUM)
+        ctx = parallel.peer_ctx() if parallel.enabled() else None
+        if ctx is not None and 2 * C <= ops.PEER_MAX_FLOATS:
+            # SyncBN: one-shot NVLink exchange of the partial sums fused with the finalize (one launch, no NCCL)
+            fin = ops.bn_finalize_peer(ctx, st, count, gamma, beta, rm, rv, nbt, BN_EPS, BN_MOMENTUM)
+        else:
+            parallel.all_reduce_sum_(st)
+            fin = ops.bn_finalize(st, count, gamma, beta, rm, rv, nbt, BN_EPS, BN_MOMENTUM)
     else:
         fin = ops.bn_eval_params(rm, rv, gamma, beta, BN_EPS)
     if f32:

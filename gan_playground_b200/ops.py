@@ -84,7 +84,7 @@ def _fn(name):
 
 def exported_symbols():
     """Names of every compute entry point declared in include/gpb200.h (used by the CPU-side ABI test)."""
-    return sorted(_SIGS) + ["gp_version", "gp_last_error", "gp_launch_count"]
+    return sorted(_SIGS) + ["gp_version", "gp_last_error", "gp_launch_count", "gp_peer_buffer_bytes"]
 
 
 def _p(t):
@@ -645,4 +645,64 @@ def head_fwd_split(a_hi, a_lo, w, bias, O, s_o, s_c, s_hw):
     out = torch.empty((NB, O), device=a_hi.device, dtype=torch.float32)
     check(_fn("gp_head_fwd_split")(_p(a_hi), _p(a_lo), _p(w), _p(bias), _p(out), NB, H * W, C, O, s_o, s_c, s_hw, _stream()),
           "gp_head_fwd_split")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ optimiser edge
+_SIGS.update({
+    "gp_adam_flat": [_vp, _vp, _vp, _vp, _ll, _d, _d, _d, _d, _vp, _d, _vp],
+})
+
+
+def adam_flat(p, g, m, v, step, lr, beta1, beta2, eps, grad_scale=1.0):
+    """In-place Adam update of the flat fp32 buffer p (torch.optim.Adam semantics); step: fp32 device scalar holding
+    the number of steps taken so far (not modified here)."""
+    for t, name in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
+        _chk(t, torch.float32, name)
+    check(_fn("gp_adam_flat")(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, _p(step), grad_scale, _stream()),
+          "gp_adam_flat")
+
+
+# ------------------------------------------------------------------------------------------------ SyncBN over peer memory
+class PeerCtx(ctypes.Structure):
+    """gp_peer_t of include/gpb200.h: peer-mapped device pointers of every rank's symmetric buffer."""
+    _fields_ = [("bufs", ctypes.c_void_p * 8), ("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("epoch", ctypes.c_void_p)]
+
+
+_SIGS.update({
+    "gp_peer_allreduce_sum": [_vp, _vp, _i, _vp],
+    "gp_bn_finalize_peer": [_vp, _vp, _d, _i, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+})
+PEER_MAX_FLOATS = 4096
+
+
+def peer_buffer_bytes():
+    f = _lib.lib().gp_peer_buffer_bytes
+    f.restype = ctypes.c_longlong
+    return int(f())
+
+
+def make_peer_ctx(buffer_ptrs, rank, epoch_tensor):
+    ctx = PeerCtx()
+    for i, ptr in enumerate(buffer_ptrs):
+        ctx.bufs[i] = int(ptr)
+    ctx.world, ctx.rank, ctx.epoch = len(buffer_ptrs), rank, epoch_tensor.data_ptr()
+    return ctx
+
+
+def peer_allreduce_sum_(ctx, t):
+    """In-place sum over ranks of a small contiguous fp32 tensor (<= 4096 elements): one kernel, no NCCL."""
+    _chk(t, torch.float32, "t")
+    check(_fn("gp_peer_allreduce_sum")(ctypes.addressof(ctx), _p(t), t.numel(), _stream()), "gp_peer_allreduce_sum")
+    return t
+
+
+def bn_finalize_peer(ctx, st, count, gamma, beta, running_mean, running_var, nbt, eps=1e-5, momentum=0.1):
+    """bn_finalize with the cross-rank exchange of st = [sum | sumsq] fused in; st ends up holding the global sums."""
+    _chk(st, torch.float32, "st")
+    C = st.shape[1]
+    out = torch.empty((4, C), device=st.device, dtype=torch.float32)
+    check(_fn("gp_bn_finalize_peer")(ctypes.addressof(ctx), _p(st), float(count), C, eps, momentum, _p(gamma), _p(beta),
+                                     _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]), _p(running_mean), _p(running_var),
+                                     _p(nbt), _stream()), "gp_bn_finalize_peer")
     return out

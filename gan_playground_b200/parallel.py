@@ -8,6 +8,7 @@ The reference has no parallelism at all; the semantics define
 """
 import contextlib
 import os
+import sys
 
 import torch
 import torch.distributed as dist
@@ -38,7 +39,7 @@ def init(backend=None, device=None):
 def shutdown():
     if dist.is_initialized():
         dist.destroy_process_group()
-    _state.update(enabled=False, world=1, rank=0)
+    _state.update(enabled=False, world=1, rank=0, peer=None)
 
 
 def world_size():
@@ -53,11 +54,88 @@ def enabled():
     return _state["enabled"] and _state["world"] > 1
 
 
+def sync_grads():
+    """False inside `no_sync()` (gradient exchange skipped for an accumulating backward)."""
+    return _state["sync_grads"]
+
+
+def init_peer_sync(device=None):
+    """Set up the one-shot NVLink exchange used for the SyncBN reductions (csrc/peer_sync.cu): a symmetric buffer per
+    rank, mapped into every peer through torch's symmetric-memory rendezvous (plumbing only: the exchange itself is our
+    kernel). Returns True when active; on any failure (no peer access, > 8 ranks, GP_PEER_SYNC=0) the SyncBN sums keep
+    going through NCCL all-reduce."""
+    if not enabled() or _state.get("peer") is not None:
+        return _state.get("peer") is not None
+    if os.environ.get("GP_PEER_SYNC", "1") == "0" or dist.get_backend() != "nccl" or _state["world"] > 8:
+        return False
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import ops
+
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        n = ops.peer_buffer_bytes() // 4
+        buf = symm_mem.empty(n, dtype=torch.float32, device=dev)
+        buf.zero_()
+        torch.cuda.synchronize()
+        hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ok = torch.tensor([1 if len(ptrs) == _state["world"] and all(ptrs) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() != 1:
+            return False
+        _state["peer"] = {"ctx": ops.make_peer_ctx(ptrs, _state["rank"], epoch), "buf": buf, "hdl": hdl, "epoch": epoch}
+        return True
+    except Exception as exc:  # noqa: BLE001 — any rendezvous problem means "use NCCL", never a crash
+        if _state["rank"] == 0:
+            print("gan_playground_b200.parallel: peer SyncBN exchange unavailable (%s); using NCCL all-reduce" % (exc,),
+                  file=sys.stderr)
+        return False
+
+
+def peer_ctx():
+    """The peer-exchange context (ops.PeerCtx) or None when SyncBN sums go through NCCL."""
+    p = _state.get("peer")
+    return None if p is None else p["ctx"]
+
+
 def all_reduce_sum_(t):
     """In-place sum over ranks (SyncBN partial sums). No-op on a single rank."""
     if enabled():
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ctx = peer_ctx()
+        if ctx is not None and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() <= 4096:
+            from . import ops
+
+            ops.peer_allreduce_sum_(ctx, t)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
+
+
+def reduce_scatter_sum_(flat, lo, hi):
+    """flat[lo:hi] (this rank's slice) <- sum over ranks of flat[lo:hi]; the rest of `flat` is left unspecified.
+    NCCL: one in-place reduce-scatter. gloo (CPU tests) has no reduce-scatter: all-reduce the whole buffer."""
+    if not enabled():
+        return
+    if dist.get_backend() == "nccl":
+        dist.reduce_scatter_tensor(flat[lo:hi], flat, op=dist.ReduceOp.SUM)
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+
+
+def all_gather_(flat, lo, hi):
+    """Every rank's flat[lo:hi] slice -> the full `flat` on every rank (in place)."""
+    if not enabled():
+        return
+    if dist.get_backend() == "nccl":
+        dist.all_gather_into_tensor(flat, flat[lo:hi])
+    else:
+        parts = [torch.empty(hi - lo, dtype=flat.dtype, device=flat.device) for _ in range(_state["world"])]
+        dist.all_gather(parts, flat[lo:hi].clone())
+        flat.copy_(torch.cat(parts))
 
 
 def broadcast_module(module, src=0):

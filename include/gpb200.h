@@ -240,6 +240,34 @@ int gp_col2im_k4s2_f32(const float* col, const float* bias, float* img, int NB, 
 int gp_head_fwd_split(const void* a_hi, const void* a_lo, const float* w, const float* bias, float* out, int NB, int HW,
                       int C, int O, long long s_o, long long s_c, long long s_hw, void* stream);
 
+/* ---- SyncBN over NVLink peer memory (the reference has no parallelism; batch-sharded data parallelism
+ * needs global-batch BatchNorm statistics, 15 forward + 12 backward reductions of <= 8 KB per DCGAN-64 step).
+ * One-shot all-reduce: every rank pushes its partial sums into a slot of every peer's symmetric buffer, waits on
+ * sequence-numbered flags and adds the slots in rank order (bit-identical totals on all ranks); one launch, no NCCL.
+ * gp_peer_t: bufs[r] = device pointer (valid in THIS process) to rank r's buffer of gp_peer_buffer_bytes() bytes,
+ * zero-initialised before first use; epoch = this rank's call counter (uint32 in device memory, zero-initialised).
+ * All ranks must issue the same sequence of gp_peer_* calls. n <= 4096 floats.
+ * gp_bn_finalize_peer = that exchange on st = (sum[C] | sumsq[C]) fused with gp_bn_finalize. */
+typedef struct {
+  void* bufs[8];
+  int32_t world, rank;
+  void* epoch;
+} gp_peer_t;
+long long gp_peer_buffer_bytes(void);
+int gp_peer_allreduce_sum(const gp_peer_t* peer, float* data, int n, void* stream);
+int gp_bn_finalize_peer(const gp_peer_t* peer, float* st, double count, int C, float eps, float momentum,
+                        const float* gamma, const float* beta, float* mean, float* rstd, float* scale, float* shift,
+                        float* running_mean, float* running_var, long long* num_batches_tracked, void* stream);
+
+/* ---- optimiser edge: Adam with the literals of main_dcgan.py:55-56 / main_sngan.py:55-56
+ * (torch.optim.Adam, no weight decay, no amsgrad) over FLAT fp32 buffers — one launch per network:
+ *   m += (g*grad_scale - m)*(1-beta1); v = beta2*v + (1-beta2)*(g*grad_scale)^2;
+ *   p -= lr/(1-beta1^t) * m / (sqrt(v)/sqrt(1-beta2^t) + eps),  t = *step + 1
+ * step: device scalar (fp32) = steps taken before this call (the caller increments it; graph-capturable);
+ * grad_scale: 1/world_size of data-parallel averaging folded into the gradient read. n % 4 == 0, 16-byte aligned. */
+int gp_adam_flat(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2,
+                 double eps, const float* step, double grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

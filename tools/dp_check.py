@@ -48,6 +48,9 @@ def main():
     rank, world = parallel.init()
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
+    peer = parallel.init_peer_sync(dev)
+    if rank == 0:
+        print("SyncBN exchange: %s" % ("one-shot NVLink peer kernel" if peer else "NCCL all-reduce"))
     B = 64
     torch.manual_seed(0)
     with contextlib.redirect_stdout(io.StringIO()):
@@ -69,15 +72,55 @@ def main():
     parallel._state["world"] = 1
     netG.load_state_dict(sdG), netD.load_state_dict(sdD)
     losses1, gD1, gG1 = step(netG, netD, crit, x, z1, z2, False)
+
+    # ---- full optimiser steps: engine.DcganStep + FusedAdam (ZeRO-1 sharded over the ranks) vs one device
+    from gan_playground_b200.engine import DcganStep
+    from gan_playground_b200.optim import FusedAdam
+
+    def train(n_steps, dp):
+        parallel._state["enabled"], parallel._state["world"] = dp, (world if dp else 1)
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            nG, nD = dcgan.Generator(ngf=32).to(dev), dcgan.Discriminator(ndf=32).to(dev)
+        nG.load_state_dict(sdG), nD.load_state_dict(sdD)
+        oG = FusedAdam(nG.parameters(), lr=4e-4, betas=(0.5, 0.999), shard=dp)
+        oD = FusedAdam(nD.parameters(), lr=1e-4, betas=(0.5, 0.999), shard=dp)
+        b = B // world if dp else B
+        run = DcganStep(nG, nD, crit, oG, oD, b, 100, dev, use_graph=False)
+        out = []
+        for i in range(n_steps):
+            xi, zi = (x.roll(i, 0), torch.stack([z1.roll(i, 0), z2.roll(i, 0)]))
+            if dp:
+                xi, zi = parallel.shard(xi), parallel.shard(zi, 1)
+            out.append(run.step_eager(xi.contiguous(), zi.contiguous())[:3])
+        return out, {("G." + k): v.detach().clone() for k, v in nG.state_dict().items()} | \
+            {("D." + k): v.detach().clone() for k, v in nD.state_dict().items()}
+
+    tr_dp, sd_dp = train(3, True)
+    tr_1, sd_1 = train(3, False)
+    parallel._state["enabled"], parallel._state["world"] = True, world
+    # Adam normalises every element's step to ~lr, so element-wise weight differences amplify rounding noise wherever a
+    # gradient is near zero; compare the UPDATE DIRECTION of the conv / linear weights instead (global cosine)
+    sd0 = {("G." + k): v for k, v in sdG.items()} | {("D." + k): v for k, v in sdD.items()}
+    keys = [k for k in sd_1 if sd_1[k].dim() >= 2]
+    upd_cos = cos({k: sd_dp[k] - sd0[k] for k in keys}, {k: sd_1[k] - sd0[k] for k in keys})
+    ldp = torch.tensor(tr_dp[-1], device=dev)
+    torch.distributed.all_reduce(ldp)
+    ldp /= world
     if rank == 0:
         print("world %d: DP mean losses %s vs single-device %s" % (world, [round(v, 5) for v in lt.tolist()],
                                                                    [round(v, 5) for v in losses1]))
         print("D grad cosine DP vs single: %.6f   G grad cosine: %.6f" % (cos(gD, gD1), cos(gG, gG1)))
         print("running_mean max abs diff: %.3e" % (rmD - netD.blocks[1][1].running_mean).abs().max().item())
         ok = cos(gD, gD1) > 0.999 and cos(gG, gG1) > 0.99 and all(abs(a - b) < 0.01 * abs(b) + 1e-3 for a, b in zip(lt.tolist(), losses1))
+        print("3 optimiser steps, ZeRO-1 FusedAdam on %d ranks vs one device: step-3 losses %s vs %s; weight-update cosine %.5f"
+              % (world, [round(v, 4) for v in ldp.tolist()], [round(v, 4) for v in tr_1[-1]], upd_cos))
+        ok = ok and upd_cos > 0.98 and all(abs(a - b) < 0.03 * abs(b) + 1e-3 for a, b in zip(ldp.tolist(), tr_1[-1]))
         print("DP_CHECK", "OK" if ok else "FAIL")
+    sys.stdout.flush()
     torch.distributed.barrier()
-    torch.distributed.destroy_process_group()
+    torch.cuda.synchronize()
+    os._exit(0)
 
 
 if __name__ == "__main__":
