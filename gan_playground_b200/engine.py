@@ -24,7 +24,7 @@ def _clear_caches(*nets):
 
 
 class DcganStep:
-    def __init__(self, netG, netD, criterion, optG, optD, batch, z_dim, device, use_graph=False, warmup=3):
+    def __init__(self, netG, netD, criterion, optG, optD, batch, z_dim, device, use_graph=False, warmup=3, overlap=True):
         self.netG, self.netD, self.crit, self.optG, self.optD = netG, netD, criterion, optG, optD
         self.batch, self.z_dim, self.dev = batch, z_dim, device
         # FusedAdam owns flat parameter / gradient buffers and does the gradient collective itself; any other optimiser
@@ -38,6 +38,8 @@ class DcganStep:
         self.scalars = torch.zeros(6, device=device)   # lossD_real, lossD_fake, lossG, D(x), D(G(z))1, D(G(z))2
         self.fixed_z = False
         self._warmup = warmup
+        self.overlap = overlap
+        self._side = torch.cuda.Stream(device=device) if device.type == "cuda" else None
 
     # ---- the loop body; `log(i, t)` receives the six scalars as 0-dim device tensors
     def _body(self, inputs, z1, z2, log):
@@ -52,9 +54,20 @@ class DcganStep:
         log(4, outD.mean())
         lossD_fake = crit(outD, False)
         lossD_fake.backward()
-        self._step(self.optD, self.bucketD)                      # (gradient all-reduce +) optD.step()
-        self._zero(self.optG, self.bucketG)                      # optG.zero_grad()
-        outG = netG(z2)
+        if parallel.enabled() and self.overlap:
+            # D's gradient exchange + update run on a side stream while the generator forward of the G step (which does
+            # not read D) runs on the main one; D's forward below waits for the join
+            cur = torch.cuda.current_stream()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                self._step(self.optD, self.bucketD)
+            self._zero(self.optG, self.bucketG)
+            outG = netG(z2)
+            cur.wait_stream(self._side)
+        else:
+            self._step(self.optD, self.bucketD)                  # (gradient all-reduce +) optD.step()
+            self._zero(self.optG, self.bucketG)                  # optG.zero_grad()
+            outG = netG(z2)
         outD = netD(outG)
         log(5, outD.mean())
         lossG = crit(outD, False, True)

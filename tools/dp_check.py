@@ -104,6 +104,12 @@ def main():
     sd0 = {("G." + k): v for k, v in sdG.items()} | {("D." + k): v for k, v in sdD.items()}
     keys = [k for k in sd_1 if sd_1[k].dim() >= 2]
     upd_cos = cos({k: sd_dp[k] - sd0[k] for k in keys}, {k: sd_1[k] - sd0[k] for k in keys})
+    # replicas must stay bit-identical: every rank applied the same all-gathered parameters
+    flat = torch.cat([sd_dp[k].float().reshape(-1) for k in sorted(sd_dp) if sd_dp[k].dtype.is_floating_point])
+    hi, lo = flat.clone(), flat.clone()
+    torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+    torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+    replica_diff = (hi - lo).abs().max().item()
     ldp = torch.tensor(tr_dp[-1], device=dev)
     torch.distributed.all_reduce(ldp)
     ldp /= world
@@ -115,7 +121,10 @@ def main():
         ok = cos(gD, gD1) > 0.999 and cos(gG, gG1) > 0.99 and all(abs(a - b) < 0.01 * abs(b) + 1e-3 for a, b in zip(lt.tolist(), losses1))
         print("3 optimiser steps, ZeRO-1 FusedAdam on %d ranks vs one device: step-3 losses %s vs %s; weight-update cosine %.5f"
               % (world, [round(v, 4) for v in ldp.tolist()], [round(v, 4) for v in tr_1[-1]], upd_cos))
-        ok = ok and upd_cos > 0.98 and all(abs(a - b) < 0.03 * abs(b) + 1e-3 for a, b in zip(ldp.tolist(), tr_1[-1]))
+        print("replica max |difference| across ranks after 3 steps: %.3e (must be 0)" % replica_diff)
+        # (Adam turns near-zero gradient elements into +-lr steps, so bf16-level gradient differences flip a few percent
+        # of the update signs: the cosine is informative, the losses and the replica identity are the check)
+        ok = ok and replica_diff == 0.0 and upd_cos > 0.9 and all(abs(a - b) < 0.01 * abs(b) + 1e-3 for a, b in zip(ldp.tolist(), tr_1[-1]))
         print("DP_CHECK", "OK" if ok else "FAIL")
     sys.stdout.flush()
     torch.distributed.barrier()
