@@ -148,7 +148,9 @@ class ConvBlock(torch.autograd.Function):
         if ctx.has_bn:
             x, weight, y, fin = ctx.saved_tensors
             dy, dgamma, dbeta = _bn_backward(da, y, fin, ctx.count, ctx.act, ctx.training)
-            dbias = torch.zeros(dy.shape[-1], device=dy.device, dtype=torch.float32)  # analytically zero before BN
+            # a bias in front of BatchNorm has an analytically zero gradient (the reference's is fp32 rounding noise,
+            # SURVEY.md §2.2): hand autograd no tensor at all instead of a zero fill plus an accumulation pass
+            dbias = None
         else:
             x, weight, a = ctx.saved_tensors
             dy = ops.act_bwd(da, a, ctx.act) if ctx.act != ops.ACT_NONE else da

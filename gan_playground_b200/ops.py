@@ -232,7 +232,7 @@ def pack_matrix(src, R, K, Rpad, ld, s_r, s_k, perm=1, inv_scale=None):
 
 def unpack_matrix(src, out_shape, R, K, ld_src, s_r, s_k, perm=1):
     _chk(src, torch.float32, "src")
-    dst = torch.zeros(out_shape, device=src.device, dtype=torch.float32)
+    dst = torch.empty(out_shape, device=src.device, dtype=torch.float32)   # every element of out_shape is written
     check(_fn("gp_unpack_matrix")(_p(src), _p(dst), R, K, ld_src, s_r, s_k, perm, _stream()), "gp_unpack_matrix")
     return dst
 
