@@ -185,6 +185,55 @@ class ImageConv3(torch.autograd.Function):
         return dx, dw1, db1, dwsc, dbsc
 
 
+class BlurPool(torch.autograd.Function):
+    """BlurPool2d(filt_size=3, reflect, stride) on NHWC bf16 (models/ops.py:7-47; dcgan_blur.py:41 stride 1, :116 stride 2)."""
+
+    @staticmethod
+    def forward(ctx, x, stride):
+        ctx.dims = (x.shape[1], x.shape[2], stride)
+        return ops.blur3x3_fwd(x, stride)
+
+    @staticmethod
+    def backward(ctx, g):
+        H, W, stride = ctx.dims
+        return ops.blur3x3_bwd(g.contiguous(), H, W, stride), None
+
+
+class ImageConv3Act(torch.autograd.Function):
+    """Conv2d(img_dim -> C, 3x3, p=1) + activation reading the fp32 NCHW image (first block of the dcgan_blur
+    discriminator, models/dcgan_blur.py:111-115): im2col (K = 32) -> 1-tap tensor-core GEMM with fused bias + act."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, cache, key):
+        x = x.contiguous()
+        NB, ch, H, W = x.shape
+        Cout, K = weight.shape[0], ch * 9
+        col = ops.im2col_k3s1(x.detach())
+        wp = cache.get((key, "fwd"), weight, lambda: ops.pack_matrix(weight.detach().contiguous(), Cout, K, Cout, 32, K, 1))
+        a = ops.conv_fwd(col, wp, bias.detach(), ops.KIND_CONV_K1S1, H, W, act, flops=2.0 * NB * H * W * Cout * K)
+        ctx.save_for_backward(col, weight, a)
+        ctx.misc = (act, cache, key, (NB, ch, H, W))
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        col, weight, a = ctx.saved_tensors
+        act, cache, key, (NB, ch, H, W) = ctx.misc
+        Cout, K = weight.shape[0], ch * 9
+        fl = 2.0 * NB * H * W * Cout * K
+        dy = ops.act_bwd(da.contiguous(), a, act) if act != ops.ACT_NONE else da.contiguous()
+        dweight = dbias = dx = None
+        if ctx.needs_input_grad[1]:
+            dweight = ops.unpack_matrix(ops.conv_wgrad(dy, col, ops.KIND_CONV_K1S1, 1, flops=fl).view(Cout, 32),
+                                        weight.shape, Cout, K, 32, K, 1)
+        if ctx.needs_input_grad[2]:
+            dbias = ops.colsum(dy)
+        if ctx.needs_input_grad[0]:
+            wt = cache.get((key, "dgrad"), weight, lambda: ops.pack_matrix(weight.detach().contiguous(), K, Cout, 32, Cout, 1, K))
+            dx = ops.col2im_k3s1(ops.conv_fwd(dy, wt, None, ops.KIND_CONV_K1S1, H, W, flops=fl), ch)
+        return dx, dweight, dbias, None, None, None
+
+
 class ImageOut3(torch.autograd.Function):
     """Last layer of the ResNet generator: tanh(Conv2d(ch -> img_dim, 3x3)) written as the fp32 NCHW image (:95).
     The GEMM runs with Nout padded to 8 (rows >= img_dim are zero)."""

@@ -706,3 +706,28 @@ def bn_finalize_peer(ctx, st, count, gamma, beta, running_mean, running_var, nbt
                                      _p(out[0]), _p(out[1]), _p(out[2]), _p(out[3]), _p(running_mean), _p(running_var),
                                      _p(nbt), _stream()), "gp_bn_finalize_peer")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ BlurPool2d (dcgan_blur)
+_SIGS.update({
+    "gp_blur3x3_fwd": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "gp_blur3x3_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+})
+
+
+def blur3x3_fwd(x, stride):
+    """x: bf16 (NB, H, W, C) -> reflect-padded [1,2,1]x[1,2,1]/16 depth-wise blur at `stride` (models/ops.py:7-47)."""
+    _chk(x, torch.bfloat16, "x")
+    NB, H, W, C = x.shape
+    out = torch.empty((NB, (H - 1) // stride + 1, (W - 1) // stride + 1, C), device=x.device, dtype=torch.bfloat16)
+    check(_fn("gp_blur3x3_fwd")(_p(x), _p(out), NB, H, W, C, stride, _stream()), "gp_blur3x3_fwd")
+    return out
+
+
+def blur3x3_bwd(dout, H, W, stride):
+    """Adjoint of blur3x3_fwd: dout on the output grid -> gradient on the (H, W) input grid."""
+    _chk(dout, torch.bfloat16, "dout")
+    NB, _, _, C = dout.shape
+    din = torch.empty((NB, H, W, C), device=dout.device, dtype=torch.bfloat16)
+    check(_fn("gp_blur3x3_bwd")(_p(dout), _p(din), NB, H, W, C, stride, _stream()), "gp_blur3x3_bwd")
+    return din

@@ -240,6 +240,13 @@ int gp_col2im_k4s2_f32(const float* col, const float* bias, float* img, int NB, 
 int gp_head_fwd_split(const void* a_hi, const void* a_lo, const float* w, const float* bias, float* out, int NB, int HW,
                       int C, int O, long long s_o, long long s_c, long long s_hw, void* stream);
 
+/* ---- BlurPool2d(filt_size=3, pad_type='reflect', stride 1 | 2) of models/ops.py:7-47, the anti-aliasing filter of
+ * models/dcgan_blur.py:41,116 (the networks main_dcgan.py:52-53 instantiates): reflection pad 1 + depth-wise 3x3
+ * outer([1,2,1],[1,2,1])/16 on NHWC bf16 (NB, H, W, C) -> (NB, (H-1)/stride+1, (W-1)/stride+1, C); _bwd is its adjoint
+ * (dout on the output grid -> din on the (H, W) grid). */
+int gp_blur3x3_fwd(const void* in, void* out, int NB, int H, int W, int C, int stride, void* stream);
+int gp_blur3x3_bwd(const void* dout, void* din, int NB, int H, int W, int C, int stride, void* stream);
+
 /* ---- SyncBN over NVLink peer memory (the reference has no parallelism; batch-sharded data parallelism
  * needs global-batch BatchNorm statistics, 15 forward + 12 backward reductions of <= 8 KB per DCGAN-64 step).
  * One-shot all-reduce: every rank pushes its partial sums into a slot of every peer's symmetric buffer, waits on

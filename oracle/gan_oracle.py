@@ -148,6 +148,56 @@ def dcgan_discriminator(sd, x, *, sn=False, acgan=False, flatten_head=False, tra
 
 
 # --------------------------------------------------------------------------------------------------------------
+# dcgan_blur (models/dcgan_blur.py + models/ops.py::BlurPool2d) — what main_dcgan.py:52-53 instantiates
+# --------------------------------------------------------------------------------------------------------------
+
+
+def blurpool2d(x, stride):
+    """BlurPool2d(filt_size=3, pad_type='reflect'). Reference: models/ops.py:7-47 — reflection pad 1 on every side,
+    then a depth-wise 3x3 convolution with the fixed kernel outer([1,2,1],[1,2,1]) / 16 at the given stride."""
+    a = torch.tensor([1.0, 2.0, 1.0], dtype=x.dtype)
+    filt = (a[:, None] * a[None, :]) / 16.0
+    c = x.shape[1]
+    return F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), filt[None, None].repeat(c, 1, 1, 1), stride=stride, groups=c)
+
+
+def dcgan_blur_generator(sd, z, *, bottom_width=4, training=True, buffers=None):
+    """Generator.forward of models/dcgan_blur.py:53-60: relu(linear(z)) -> view -> [Upsample x2 (nearest) ->
+    Conv3x3 s1 p1 -> BlurPool2d(stride 1) -> BN -> LeakyReLU(0.2)]* -> Conv3x3 -> Tanh (blocks at :37-45, out :46-49)."""
+    h = F.relu(F.linear(z, sd["linear.weight"], sd["linear.bias"]))
+    h = h.view(h.size(0), -1, bottom_width, bottom_width)
+    i = 0
+    while ("blocks.%d.1.bias" % i) in sd:
+        p = "blocks.%d." % i
+        h = F.interpolate(h, scale_factor=2)
+        h = F.conv2d(h, sd[p + "1.weight"], sd[p + "1.bias"], stride=1, padding=1)
+        h = blurpool2d(h, 1)
+        h = F.leaky_relu(batch_norm_train(h, sd[p + "3.weight"], sd[p + "3.bias"], buffers, p + "3."), 0.2)
+        i += 1
+    h = F.conv2d(h, sd["out_layer.0.weight"], sd["out_layer.0.bias"], stride=1, padding=1)
+    return torch.tanh(h)
+
+
+def dcgan_blur_discriminator(sd, x, *, training=True, buffers=None):
+    """Discriminator.forward of models/dcgan_blur.py:124-131: [Conv3x3 s1 p1 (+BN from block 1) -> LeakyReLU(0.2) ->
+    BlurPool2d(stride 2) except after the last block]* -> sum over (H, W) -> Linear (blocks at :108-118)."""
+    h = x
+    n_blocks = 0
+    while ("blocks.%d.0.bias" % n_blocks) in sd:
+        n_blocks += 1
+    for i in range(n_blocks):
+        p = "blocks.%d." % i
+        h = F.conv2d(h, sd[p + "0.weight"], sd[p + "0.bias"], stride=1, padding=1)
+        if i != 0:
+            h = batch_norm_train(h, sd[p + "1.weight"], sd[p + "1.bias"], buffers, p + "1.")
+        h = F.leaky_relu(h, 0.2)
+        if i < n_blocks - 1:
+            h = blurpool2d(h, 2)
+    h = h.sum(dim=(2, 3))
+    return F.linear(h, sd["out_layer.weight"], sd["out_layer.bias"])
+
+
+# --------------------------------------------------------------------------------------------------------------
 # SNGAN projection (models/sngan_projection.py)
 # --------------------------------------------------------------------------------------------------------------
 
@@ -254,6 +304,16 @@ def dcgan_step_grads(sd_g, sd_d, x_real, z1, z2, labels=(0.9, 0.1, 0.9), mode="v
     rl, fl, gl = labels
     g_kw = {k: v for k, v in net_kw.items() if k in ("sn", "bottom_width")}
     d_kw = {k: v for k, v in net_kw.items() if k in ("sn", "flatten_head")}
+    if net_kw.get("blur"):   # models/dcgan_blur.py instead of models/dcgan.py
+        g_kw = {k: v for k, v in net_kw.items() if k == "bottom_width"}
+        d_kw = {}
+        return _step_grads(dcgan_blur_generator, dcgan_blur_discriminator, g_kw, d_kw, sd_g, sd_d, x_real, z1, z2,
+                           labels, mode)
+    return _step_grads(dcgan_generator, dcgan_discriminator, g_kw, d_kw, sd_g, sd_d, x_real, z1, z2, labels, mode)
+
+
+def _step_grads(dcgan_generator, dcgan_discriminator, g_kw, d_kw, sd_g, sd_d, x_real, z1, z2, labels, mode):
+    rl, fl, gl = labels
     pg = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd_g.items()}
     pd = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() else v.clone()) for k, v in sd_d.items()}
     out = {}

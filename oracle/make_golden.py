@@ -3,6 +3,7 @@ container only (the GPU box has no /root/reference). Also cross-checks oracle/ga
 reference on the same inputs (max abs difference printed; must be ~1e-6 or below).
 
     python oracle/make_golden.py            # writes tests/golden/
+    python oracle/make_golden.py dcgan_blur_r32_w8.pt   # only the named fixtures (+ the key lists)
 """
 import json
 import os
@@ -28,6 +29,28 @@ def ref_modules():
         m = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(m)
         mods[name] = m
+    # models/dcgan_blur.py does `from models.ops import BlurPool2d`: give it the REFERENCE's models/ops.py (not this
+    # repository's `models` shim) while it is being imported
+    import types
+
+    spec = importlib.util.spec_from_file_location("ref_models_ops", os.path.join(REF, "models", "ops.py"))
+    ref_ops = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_ops)
+    saved = {k: sys.modules.get(k) for k in ("models", "models.ops")}
+    pkg = types.ModuleType("models")
+    pkg.ops, pkg.__path__ = ref_ops, []
+    sys.modules["models"], sys.modules["models.ops"] = pkg, ref_ops
+    try:
+        spec = importlib.util.spec_from_file_location("ref_models_dcgan_blur", os.path.join(REF, "models", "dcgan_blur.py"))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        mods["dcgan_blur"] = m
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
     spec = importlib.util.spec_from_file_location("ref_criterion", os.path.join(REF, "utils", "criterion.py"))
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
@@ -109,6 +132,8 @@ def dcgan_like_fixture(mods, modname, res, width, batch, mode, labels, seed, z_d
 
     # ---- cross-check the oracle restatement on the same inputs
     kw = dict(sn=(modname == "dcgan_specnorm"), flatten_head=(modname == "dcgan_specnorm"))
+    if modname == "dcgan_blur":
+        kw = dict(blur=True)
     og = {k: v.clone() for k, v in sd_g0.items()}
     od = {k: v.clone() for k, v in sd_d0.items()}
     r = O.dcgan_step_grads(og, od, x, z1, z2, labels=labels, mode=mode, **kw)
@@ -291,6 +316,10 @@ def key_lists(mods):
         out["sngan_projection.SNResNetProjectionDiscriminator"] = desc(mods["sngan_projection"].SNResNetProjectionDiscriminator(n_classes=10))
         out["acgan.Generator"] = desc(mods["acgan"].Generator())
         out["acgan.Discriminator"] = desc(mods["acgan"].Discriminator())
+        out["dcgan_blur.Generator"] = desc(mods["dcgan_blur"].Generator())
+        out["dcgan_blur.Discriminator"] = desc(mods["dcgan_blur"].Discriminator())
+        out["dcgan_blur.Generator@32"] = desc(mods["dcgan_blur"].Generator(resolution=32))
+        out["dcgan_blur.Discriminator@32"] = desc(mods["dcgan_blur"].Discriminator(resolution=32))
         # RNG-order parity: first weights of a seed-0 construction
         torch.manual_seed(0)
         g = mods["dcgan"].Generator(ngf=8, resolution=32)
@@ -317,12 +346,16 @@ def main():
         "dcgan_r32_w4.pt": lambda: dcgan_like_fixture(mods, "dcgan", 32, 4, 8, "vanilla", (0.9, 0.1, 0.9), 0, z_dim=100),
         "dcgan_r64_w4.pt": lambda: dcgan_like_fixture(mods, "dcgan", 64, 4, 2, "vanilla", (0.9, 0.1, 0.9), 1, z_dim=16),
         "snd_r32_w4.pt": lambda: dcgan_like_fixture(mods, "dcgan_specnorm", 32, 4, 8, "hinge", (1.0, 0.0, 1.0), 2, z_dim=16),
+        "dcgan_blur_r32_w8.pt": lambda: dcgan_like_fixture(mods, "dcgan_blur", 32, 8, 4, "vanilla", (0.9, 0.1, 0.9), 6, z_dim=16),
         "dcgan_trace_r32_w4.pt": lambda: dcgan_trace_fixture(mods, 32, 4, 8, 20, 3),
         "sngan_proj_ch8.pt": lambda: sngan_fixture(mods, 8, 2, 4),
         "acgan_r64_w4.pt": lambda: acgan_fixture(mods, 4, 2, 5),
         "ganloss.pt": lambda: ganloss_fixture(mods),
     }
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]   # optional: fixture file names to (re)generate
     for name, fn in fixtures.items():
+        if only and name not in only:
+            continue
         fx = fn()
         path = os.path.join(OUT, name)
         torch.save(fx, path)

@@ -27,6 +27,45 @@ def test_state_dict_layout_matches_reference(name, ctor, capsys):
     assert describe(ctor()) == KEYS[name]
 
 
+@pytest.mark.parametrize("name,res", [("dcgan_blur.Generator", 64), ("dcgan_blur.Discriminator", 64),
+                                      ("dcgan_blur.Generator@32", 32), ("dcgan_blur.Discriminator@32", 32)])
+def test_dcgan_blur_state_dict_layout_matches_reference(name, res, capsys):
+    """models/dcgan_blur.py (what main_dcgan.py:52-53 instantiates): same keys / shapes / dtypes, incl. the `filt` buffers."""
+    from gan_playground_b200.models import dcgan_blur
+
+    net = dcgan_blur.Generator(resolution=res) if "Generator" in name else dcgan_blur.Discriminator(resolution=res)
+    assert describe(net) == KEYS[name]
+
+
+def test_dcgan_blur_same_seed_construction_matches_reference_fixture(capsys):
+    """The golden fixture holds the reference's seed-6 state_dicts: the mirror built from the same seed is identical
+    (same torch layers in the same order; G's init touches only Linear, as upstream)."""
+    from conftest import load_golden
+    from gan_playground_b200.models import dcgan_blur
+
+    fx = load_golden("dcgan_blur_r32_w8.pt")
+    torch.manual_seed(6)
+    g = dcgan_blur.Generator(z_dim=fx["z_dim"], ngf=fx["width"], resolution=fx["res"])
+    d = dcgan_blur.Discriminator(ndf=fx["width"], resolution=fx["res"])
+    for net, sd in ((g, fx["sd_g"]), (d, fx["sd_d"])):
+        mine = net.state_dict()
+        assert list(mine.keys()) == list(sd.keys())
+        assert all(torch.equal(mine[k], sd[k]) for k in sd)
+    with pytest.raises(KeyError):
+        dcgan_blur.Generator(resolution=48)
+
+
+def test_root_level_shims_export_dcgan_blur_and_blurpool():
+    """main_dcgan.py:11 does `from models import dcgan, dcgan_specnorm, dcgan_blur`; dcgan_blur.py:5 `from models.ops import BlurPool2d`."""
+    import importlib
+
+    m = importlib.import_module("models.dcgan_blur")
+    o = importlib.import_module("models.ops")
+    assert hasattr(m, "Generator") and hasattr(m, "Discriminator") and hasattr(o, "BlurPool2d")
+    b = o.BlurPool2d(channels=8, stride=1)
+    assert b.filt.shape == (8, 1, 3, 3) and abs(b.filt.sum().item() - 8.0) < 1e-6
+
+
 def test_same_seed_gives_same_weights_as_reference(capsys):
     probe = KEYS["seed0_probe"]
     torch.manual_seed(0)
