@@ -31,6 +31,27 @@ def x3():
     return _precision == "bf16x3"
 
 
+class precision_scope:
+    """`with precision_scope("bf16"): out = netD(x)` — run the forward passes issued inside the block in the given
+    mode (their backward follows the formats the forward saved). Used by engine.DcganStep for the real-image
+    discriminator pass: plain bf16 operands already give D-real gradient cosine 0.9999 and logits within 6e-3 of the
+    fp32 reference (tests/test_gpu_precision.py), so the 3-MMA forward is spent only on passes that see generated images."""
+
+    def __init__(self, p):
+        if p not in _VALID:
+            raise ValueError("precision must be one of %s" % (_VALID,))
+        self.p = p
+
+    def __enter__(self):
+        global _precision
+        self.prev = _precision
+        _precision = self.p
+
+    def __exit__(self, *exc):
+        global _precision
+        _precision = self.prev
+
+
 # BatchNorm batch statistics accumulated in the GEMM epilogue from the fp32 accumulators (one fewer pass over the conv
 # output per BN layer). GP_FUSED_STATS=0 falls back to the standalone statistics kernel.
 _fused_stats = os.environ.get("GP_FUSED_STATS", "1") != "0"

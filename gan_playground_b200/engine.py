@@ -11,7 +11,7 @@ Requirements for graph mode: optimisers built with `capturable=True`; fixed batc
 networks are cleared before capture so the staging kernels are part of the graph."""
 import torch
 
-from . import parallel
+from . import config, parallel
 from .optim import FusedAdam
 
 
@@ -24,7 +24,8 @@ def _clear_caches(*nets):
 
 
 class DcganStep:
-    def __init__(self, netG, netD, criterion, optG, optD, batch, z_dim, device, use_graph=False, warmup=3, overlap=True):
+    def __init__(self, netG, netD, criterion, optG, optD, batch, z_dim, device, use_graph=False, warmup=3, overlap=True,
+                 mixed_precision=True):
         self.netG, self.netD, self.crit, self.optG, self.optD = netG, netD, criterion, optG, optD
         self.batch, self.z_dim, self.dev = batch, z_dim, device
         # FusedAdam owns flat parameter / gradient buffers and does the gradient collective itself; any other optimiser
@@ -39,13 +40,16 @@ class DcganStep:
         self.fixed_z = False
         self._warmup = warmup
         self.overlap = overlap
+        # mixed forward precision: the real-image D pass needs no 3-MMA forward (config.precision_scope)
+        self.real_precision = "bf16" if (mixed_precision and config.x3()) else None
         self._side = torch.cuda.Stream(device=device) if device.type == "cuda" else None
 
     # ---- the loop body; `log(i, t)` receives the six scalars as 0-dim device tensors
     def _body(self, inputs, z1, z2, log):
         netG, netD, crit = self.netG, self.netD, self.crit
         self._zero(self.optD, self.bucketD)                      # optD.zero_grad()
-        outD = netD(inputs)
+        with config.precision_scope(self.real_precision or config.precision()):
+            outD = netD(inputs)
         log(3, outD.mean())
         lossD_real = crit(outD, True)
         lossD_real.backward()

@@ -29,15 +29,9 @@ def D_arch(ndf=64, img_dim=3):
             for r, (i, o) in plan.items()}
 
 
-class _bf16_mode:
+def _bf16_mode():
     """The dcgan_blur nodes implement the plain bf16 operand mode only."""
-
-    def __enter__(self):
-        self.prev = config.precision()
-        config.set_precision("bf16")
-
-    def __exit__(self, *exc):
-        config.set_precision(self.prev)
+    return config.precision_scope("bf16")
 
 
 class Generator(nn.Module):

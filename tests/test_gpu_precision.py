@@ -79,3 +79,36 @@ def test_dcgan64_step_meets_precision_bars(mode, reference_step):
         assert l1 < 0.02 and l3 < 0.02
     finally:
         config.set_precision(prev)
+
+
+def test_mixed_policy_real_pass_in_bf16_meets_the_bars(reference_step):
+    """engine.DcganStep's policy: the real-image discriminator pass runs plain bf16 operands
+    (config.precision_scope("bf16")), every pass that sees generated images runs bf16x3. The real pass alone and the
+    accumulated D gradient of the step (real + fake, what optD.step() consumes) must both meet the north_star bars."""
+    from gan_playground_b200 import config
+    from gan_playground_b200.criterion import GANLoss
+    from gan_playground_b200.models import dcgan
+
+    sd_g, sd_d, x, z1, z2, ref = reference_step
+    prev = config.precision()
+    config.set_precision("bf16x3")
+    try:
+        netG, netD = quiet(lambda: dcgan.Generator()).cuda(), quiet(lambda: dcgan.Discriminator()).cuda()
+        netG.load_state_dict(sd_g), netD.load_state_dict(sd_d)
+        crit = GANLoss("vanilla", 0.9, 0.1, 0.9).cuda()
+        with config.precision_scope("bf16"):
+            out = netD(x.cuda())
+        assert config.precision() == "bf16x3"
+        loss = crit(out, True)
+        loss.backward()
+        e1 = relerr(out, ref["d_real"])
+        g1 = global_cos(netD.named_parameters(), ref["d_grads_real"])
+        out = netD(netG(z1.cuda()).detach())
+        crit(out, False).backward()                      # accumulates onto the real-pass gradients
+        both = {k: ref["d_grads_real"][k] + ref["d_grads_fake"][k] for k in ref["d_grads_real"]}
+        g12 = global_cos(netD.named_parameters(), both)
+        print("\n[mixed] D(x) act err %.2e | cos: D-real (bf16 pass) %.6f  D real+fake accumulated %.6f" % (e1, g1, g12))
+        assert e1 < 1e-2 and g1 > 0.999 and g12 > 0.999
+        assert abs(loss.item() - ref["loss_real"].item()) < 0.02 * ref["loss_real"].item()
+    finally:
+        config.set_precision(prev)
