@@ -331,9 +331,13 @@ struct ColLaunch {
   size_t smem;
   int rpb;
 };
-static inline ColLaunch col_launch(long long P, int C, int nq) {
+static inline ColLaunch col_launch(long long P, int C, int nq, int blocks_per_sm = 8) {
   ColLaunch L;
-  long long rpb = (P + (long long)num_sms() * 8 - 1) / ((long long)num_sms() * 8);
+  // blocks_per_sm: 8 for the light kernels (statistics, column sums); the BatchNorm backward reduction keeps ~128
+  // registers per thread, so 2 resident blocks per SM is all it gets — one wave of them, with 4x fewer per-block
+  // flushes (shared-memory + global atomics per channel) than a finer split
+  const long long blocks = (long long)num_sms() * blocks_per_sm;
+  long long rpb = (P + blocks - 1) / blocks;
   if (rpb < 32) rpb = 32;
   L.rpb = (int)rpb;
   const int gx = (int)((P + L.rpb - 1) / L.rpb);

@@ -495,10 +495,18 @@ __global__ void head_bwd_weight_kernel(const float* __restrict__ dout, const __n
 #pragma unroll
     for (int j = 0; j < 8; ++j) atomicAdd(wp + j * s_c, acc[j]);
   }
-  if (dbias != nullptr && blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
+  if (dbias != nullptr && blockIdx.x == 0 && blockIdx.z == 0) {  // dbias[o] = sum_b dout[b][o]: block-wide reduction
     float s = 0.f;
-    for (int b = 0; b < NB; ++b) s += dout[(long long)b * O + o];
-    dbias[o] = s;
+    for (int b = threadIdx.x; b < NB; b += blockDim.x) s += __ldg(dout + (long long)b * O + o);
+    __shared__ float red[32];
+    for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+      for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+      if (threadIdx.x == 0) dbias[o] = s;
+    }
   }
 }
 
@@ -669,7 +677,7 @@ int gp_bn_apply_act(const void* y, void* out, long long P, int C, const float* s
 int gp_bn_bwd_reduce(const void* da, const void* y, long long P, int C, const float* scale, const float* shift,
                      const float* mean, const float* rstd, int act, float* sum_dz, float* sum_dzx, void* stream) {
   GP_REQUIRE(da && y && sum_dz && sum_dzx && P > 0 && C % 8 == 0, "gp_bn_bwd_reduce: bad arguments");
-  const ColLaunch L = col_launch(P, C, 2);
+  const ColLaunch L = col_launch(P, C, 2, 2);
   bn_bwd_reduce_kernel<__nv_bfloat16><<<L.grid, L.block, L.smem, as_stream(stream)>>>(
       static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), P, C, scale, shift, mean, rstd, act,
       sum_dz, sum_dzx, L.rpb);

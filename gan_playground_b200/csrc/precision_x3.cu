@@ -75,7 +75,7 @@ int gp_bn_apply_act_split(const float* y, void* out_hi, void* out_lo, long long 
 int gp_bn_bwd_reduce_f32(const void* da, const float* y, long long P, int C, const float* scale, const float* shift,
                          const float* mean, const float* rstd, int act, float* sum_dz, float* sum_dzx, void* stream) {
   GP_REQUIRE(da && y && sum_dz && sum_dzx && P > 0 && C % 8 == 0, "gp_bn_bwd_reduce_f32: bad arguments");
-  const ColLaunch L = col_launch(P, C, 2);
+  const ColLaunch L = col_launch(P, C, 2, 2);
   bn_bwd_reduce_kernel<float><<<L.grid, L.block, L.smem, as_stream(stream)>>>(
       static_cast<const __nv_bfloat16*>(da), y, P, C, scale, shift, mean, rstd, act, sum_dz, sum_dzx, L.rpb);
   GP_CHECK_LAUNCH();
