@@ -98,15 +98,15 @@ static bool tile_override(const char* var, int* bn, int* mt) {
   return true;
 }
 
-template <int MODE, int BNV, int MTV>
+template <int MODE, int BNV, int MTV, bool X3V = false>
 static int launch_cfg(const ConvGemmParams& prm, int grid, cudaStream_t st) {
-  auto kfn = conv_gemm_kernel<MODE, BNV, MTV>;
+  auto kfn = conv_gemm_kernel<MODE, BNV, MTV, X3V>;
   static bool attr_set = false;  // one flag per template instantiation
   if (!attr_set) {
-    GP_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BNV, MTV>::kSmemBytes));
+    GP_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BNV, MTV, X3V>::kSmemBytes));
     attr_set = true;
   }
-  kfn<<<grid, kNumThreads, GemmCfg<BNV, MTV>::kSmemBytes, st>>>(prm);
+  kfn<<<grid, kNumThreads, GemmCfg<BNV, MTV, X3V>::kSmemBytes, st>>>(prm);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -117,6 +117,14 @@ static int launch(const ConvGemmParams& prm, int bn, int mt, int grid, cudaStrea
   if (bn == 256) return mt == 2 ? launch_cfg<MODE, 256, 2>(prm, grid, st) : launch_cfg<MODE, 256, 1>(prm, grid, st);
   if (bn == 128) return mt == 2 ? launch_cfg<MODE, 128, 2>(prm, grid, st) : launch_cfg<MODE, 128, 1>(prm, grid, st);
   return mt == 2 ? launch_cfg<MODE, 64, 2>(prm, grid, st) : launch_cfg<MODE, 64, 1>(prm, grid, st);
+}
+
+// bf16x3 forward: hi and lo tiles of both operands per stage (no 256x256 variant: its stage would be 128 KB)
+static int launch_fwd_x3(const ConvGemmParams& prm, int bn, int mt, int grid, cudaStream_t st) {
+  if (grid <= 0) return GP_OK;
+  if (bn == 256) return launch_cfg<MODE_FWD, 256, 1, true>(prm, grid, st);
+  if (bn == 128) return mt == 2 ? launch_cfg<MODE_FWD, 128, 2, true>(prm, grid, st) : launch_cfg<MODE_FWD, 128, 1, true>(prm, grid, st);
+  return mt == 2 ? launch_cfg<MODE_FWD, 64, 2, true>(prm, grid, st) : launch_cfg<MODE_FWD, 64, 1, true>(prm, grid, st);
 }
 
 }  // namespace gp
@@ -150,7 +158,7 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
     double best = 0;
     for (const auto& c : cand) {
       if (c.bn > 64 && c.bn / 2 >= a->Nout) continue;            // more than half of the tile would be padding
-      if (c.bn == 256 && c.mt == 2 && ksteps < 128) continue;   // exposed epilogue not amortised
+      if (c.bn == 256 && c.mt == 2 && (ksteps < 128 || a->in_lo != nullptr)) continue;  // exposed epilogue not amortised; no bf16x3 variant
       const long long tiles = phases * ((small_px + c.mt * kBlockM - 1) / (c.mt * kBlockM)) * ((a->Nout + c.bn - 1) / c.bn);
       const long long waves = (tiles + num_sms() - 1) / num_sms();
       // short K loops: the per-tile epilogue and pipeline fill are not hidden; charge them as extra K steps
@@ -263,20 +271,9 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
   }
   const long long ktot = (long long)ntaps_total * Cin;  // packed row = every tap of the kernel window
   if (n_halves == 2) {
-    // bf16x3 (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo) as three K "taps" per real tap: the lo activation maps are 4..7 and
-    // the lo weights are the second half [ktot, 2*ktot) of each packed row.
-    GP_REQUIRE(3 * ntaps_total <= kMaxTaps, "gp_conv_fwd: too many taps for the bf16x3 mode");
-    Tap tmp[kMaxTaps];
-    for (int i = 0; i < ntaps_total; ++i) tmp[i] = prm.taps[i];
-    for (int i = 0; i < ntaps_total; ++i) {
-      Tap hh = tmp[i], lh = tmp[i], hl = tmp[i];
-      lh.map = (int8_t)(tmp[i].map + 4);
-      hl.koff = tmp[i].koff + (int32_t)ktot;
-      prm.taps[3 * i] = hh;
-      prm.taps[3 * i + 1] = lh;
-      prm.taps[3 * i + 2] = hl;
-    }
-    prm.taps_per_phase *= 3;
+    // bf16x3 (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo): the lo activation maps are map_g[4..7], the lo weights are the second
+    // half [ktot, 2*ktot) of each packed row; the kernel loads hi and lo tiles of both operands into one stage
+    prm.lo_koff = (int)ktot;
   }
   rc = make_map_2d(&prm.map_w, a->w, n_halves * ktot, a->Nout, bn);
   if (rc) return rc;
@@ -296,7 +293,9 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
   const int mtiles = ((a->NB + prm.Nt - 1) / prm.Nt) * (prm.Hs / prm.Ht) * (prm.Ws / prm.Wt);
   const int ntn = (a->Nout + bn - 1) / bn;
   const int num_tiles = prm.n_phases * mtiles * ntn;
-  return launch<MODE_FWD>(prm, bn, mt_sub, num_tiles < num_sms() ? num_tiles : num_sms(), as_stream(stream));
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  if (n_halves == 2) return launch_fwd_x3(prm, bn, mt_sub, grid, as_stream(stream));
+  return launch<MODE_FWD>(prm, bn, mt_sub, grid, as_stream(stream));
 }
 
 extern "C" int gp_conv_wgrad(const gp_conv_wgrad_t* a, void* stream) {

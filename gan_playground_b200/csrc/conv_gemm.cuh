@@ -65,17 +65,21 @@ struct alignas(64) ConvGemmParams {
   int ldw;
   int splits;
   int kblocks_total;  // WGRAD: number of 64-pixel blocks
+  int lo_koff;        // FWD, bf16x3 kernels: K offset of the lo block inside a packed weight row [hi taps | lo taps]
   int wg_flat;        // WGRAD: dW columns are tiled over the flattened (tap, channel) index (needs N % 64 == 0), so one
                       // tile can span several taps of a narrow gathered operand; 0 = one tap per tile
   float* col_sum;     // optional fused per-channel statistics of the (pre-activation) output
   float* col_sumsq;
 };
 
-template <int BN, int MT>
+// X3 = bf16x3 forward (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo): one pipeline stage holds the hi AND lo tiles of both
+// operands — 4 tile loads feed 3 MMA blocks, i.e. 1/3 fewer operand bytes from L2 per MMA than issuing the three
+// products as separate K steps (the 128x256 mainloop is bound by L2->SM traffic, not by the tensor pipe).
+template <int BN, int MT, bool X3 = false>
 struct GemmCfg {
-  static constexpr int kABytes = MT * kBlockM * kBlockK * 2;
-  static constexpr int kBBytes = BN * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kABytes = MT * kBlockM * kBlockK * 2;   // one A tile (hi or lo)
+  static constexpr int kBBytes = BN * kBlockK * 2;             // one B tile (hi or lo)
+  static constexpr int kStageBytes = (X3 ? 2 : 1) * (kABytes + kBBytes);
   static constexpr int kStatBytes = 2 * kMaxStatCols * 4;
   static constexpr int kBiasBytes = 2 * 256 * 4;  // double-buffered bias slice of the current / next tile
   static constexpr int kBarBytes = 256;
@@ -89,7 +93,7 @@ struct GemmCfg {
   static constexpr int kChunks = MT * (BN / 32);  // 32-column TMEM loads per accumulator buffer and epilogue warp
   static constexpr int kSmemBytes = kStages * kStageBytes + kStatBytes + kBiasBytes + kBarBytes + 1024;  // +1024: alignment slack
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM allocation must be a power of two <= 512");
-  static_assert(kStages >= 3, "pipeline too shallow");
+  static_assert(kStages >= (X3 ? 2 : 3), "pipeline too shallow");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };
 
@@ -160,9 +164,10 @@ struct WorkPlan {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int MODE, int BN, int MT>
+template <int MODE, int BN, int MT, bool X3 = false>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using Cfg = GemmCfg<BN, MT>;
+  static_assert(!(X3 && MODE == MODE_WGRAD), "bf16x3 applies to the forward GEMMs only");
+  using Cfg = GemmCfg<BN, MT, X3>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -248,8 +253,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_4d(sa, &p.map_g[t.map], &full_bar[stage], c0, w0 + t.dw, h0 + t.dh, n0);
-          tma_load_2d(sa + Cfg::kABytes, &p.map_w, &full_bar[stage], t.koff + c0, nt * BN);
+          if constexpr (X3) {  // stage = [A_hi | A_lo | B_hi | B_lo]; the lo activation maps are map_g[4..7]
+            tma_load_4d(sa, &p.map_g[t.map], &full_bar[stage], c0, w0 + t.dw, h0 + t.dh, n0);
+            tma_load_4d(sa + Cfg::kABytes, &p.map_g[t.map + 4], &full_bar[stage], c0, w0 + t.dw, h0 + t.dh, n0);
+            tma_load_2d(sa + 2 * Cfg::kABytes, &p.map_w, &full_bar[stage], t.koff + c0, nt * BN);
+            tma_load_2d(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &p.map_w, &full_bar[stage], p.lo_koff + t.koff + c0, nt * BN);
+          } else {
+            tma_load_4d(sa, &p.map_g[t.map], &full_bar[stage], c0, w0 + t.dw, h0 + t.dh, n0);
+            tma_load_2d(sa + Cfg::kABytes, &p.map_w, &full_bar[stage], t.koff + c0, nt * BN);
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       } else {
@@ -314,13 +326,29 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint32_t b_addr = a_addr + Cfg::kABytes;
+        if constexpr (X3) {
+          const uint32_t a_lo = a_addr + Cfg::kABytes, b_hi = a_addr + 2 * Cfg::kABytes, b_lo = b_hi + Cfg::kBBytes;
 #pragma unroll
-        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-          const uint64_t bdesc = smem_desc(dbase, b_addr + k * kadv);
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t bh = smem_desc(dbase, b_hi + k * kadv), bl = smem_desc(dbase, b_lo + k * kadv);
 #pragma unroll
-          for (int mi = 0; mi < MT; ++mi)
-            umma_bf16(d_tmem + mi * BN, smem_desc(dbase, a_addr + mi * a_sub + k * kadv), bdesc, idesc, (ks | k) != 0);
+            for (int mi = 0; mi < MT; ++mi) {
+              const uint64_t ah = smem_desc(dbase, a_addr + mi * a_sub + k * kadv);
+              const uint64_t al = smem_desc(dbase, a_lo + mi * a_sub + k * kadv);
+              umma_bf16(d_tmem + mi * BN, ah, bh, idesc, (ks | k) != 0);  // x_hi * w_hi
+              umma_bf16(d_tmem + mi * BN, al, bh, idesc, 1u);             // x_lo * w_hi
+              umma_bf16(d_tmem + mi * BN, ah, bl, idesc, 1u);             // x_hi * w_lo
+            }
+          }
+        } else {
+          const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t bdesc = smem_desc(dbase, b_addr + k * kadv);
+#pragma unroll
+            for (int mi = 0; mi < MT; ++mi)
+              umma_bf16(d_tmem + mi * BN, smem_desc(dbase, a_addr + mi * a_sub + k * kadv), bdesc, idesc, (ks | k) != 0);
+          }
         }
         umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
