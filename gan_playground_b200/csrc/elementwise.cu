@@ -310,52 +310,65 @@ __global__ void im2col_k4s2_kernel(const float* __restrict__ img, const float* _
 // One block = one image x kCol2imRows image rows: the rows/2 + 2 col rows they gather from are staged in shared
 // memory with 16-byte loads (only the ch*16 live columns), then one thread per output pixel.
 constexpr int kCol2imRows = 8;
-template <typename TC>
-__global__ void col2im_k4s2_kernel(const TC* __restrict__ col, const float* __restrict__ bias, float* __restrict__ img,
-                                   int NB, int ch, int Hi, int Wi, int act) {
-  extern __shared__ float s_col[];  // [kCol2imRows/2 + 2][Wo][ch*16 + 1]
+template <typename TC, int CH>
+__global__ void __launch_bounds__(256) col2im_k4s2_kernel(const TC* __restrict__ col, const float* __restrict__ bias,
+                                                          float* __restrict__ img, int NB, int Hi, int Wi, int act) {
+  extern __shared__ float s_col[];  // [kCol2imRows/2 + 2][Wo][CH*16 + 1]
   constexpr int kColRows = kCol2imRows / 2 + 2;
+  constexpr int live = CH * 16, pitch = live + 1, groups = live / 8;
   const int Ho = Hi / 2, Wo = Wi / 2;
   const int n = blockIdx.y, ih0 = blockIdx.x * kCol2imRows;
   const int oh_base = ih0 / 2 - 1;
-  const int live = ch * 16, pitch = live + 1, groups = live / 8;
-  for (int i = threadIdx.x; i < kColRows * Wo * groups; i += blockDim.x) {
-    const int g = i % groups, ow = (i / groups) % Wo, r = i / (groups * Wo);
+  // staging: (ow, 8-column group) pairs of one col row per iteration; divisions are by compile-time constants
+  for (int r = 0; r < kColRows; ++r) {
     const int oh = oh_base + r;
-    float f[8];
-    if (oh >= 0 && oh < Ho) {
-      Vec8<TC> v;
-      v.load(col + (((long long)n * Ho + oh) * Wo + ow) * 64 + g * 8);
-      v.unpack(f);
-    } else {
+    const bool row_ok = oh >= 0 && oh < Ho;
+    const TC* crow = col + ((long long)n * Ho + (row_ok ? oh : 0)) * Wo * 64;
+    for (int i = threadIdx.x; i < Wo * groups; i += 256) {
+      const int ow = i / groups, g = i % groups;
+      float f[8];
+      if (row_ok) {
+        Vec8<TC> v;
+        v.load(crow + ow * 64 + g * 8);
+        v.unpack(f);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = 0.f;
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      }
+      float* d = s_col + (r * Wo + ow) * pitch + g * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = f[j];
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s_col[(r * Wo + ow) * pitch + g * 8 + j] = f[j];
   }
   __syncthreads();
-  const int rows = min(kCol2imRows, Hi - ih0);
-  for (int i = threadIdx.x; i < ch * rows * Wi; i += blockDim.x) {
-    const int iw = i % Wi, il = (i / Wi) % rows, c = i / (Wi * rows);
+  // one thread per output pixel: x = threadIdx.x % 64 (+64k), (channel, row) pairs strided by threadIdx.x / 64
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  for (int cr = ty; cr < CH * kCol2imRows; cr += 4) {
+    const int c = cr / kCol2imRows, il = cr % kCol2imRows;
     const int ih = ih0 + il;
-    float acc = bias ? __ldg(bias + c) : 0.f;
+    if (ih >= Hi) continue;
+    const float b0 = bias ? __ldg(bias + c) : 0.f;
     // ih = 2*oh - 1 + kh  ->  kh in {(ih+1)&1, (ih+1)&1 + 2}
+    const int kh0 = (ih + 1) & 1;
+    for (int iw = tx; iw < Wi; iw += 64) {
+      const int kw0 = (iw + 1) & 1;
+      float acc = b0;
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      const int kh = ((ih + 1) & 1) + 2 * a;
-      const int oh2 = ih + 1 - kh;
-      if (oh2 < 0 || oh2 >= 2 * Ho) continue;
-      const int r = oh2 / 2 - oh_base;
+      for (int a = 0; a < 2; ++a) {
+        const int kh = kh0 + 2 * a;
+        const int oh2 = ih + 1 - kh;
+        if (oh2 < 0 || oh2 >= 2 * Ho) continue;
+        const int r = oh2 / 2 - oh_base;
 #pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const int kw = ((iw + 1) & 1) + 2 * b;
-        const int ow2 = iw + 1 - kw;
-        if (ow2 < 0 || ow2 >= 2 * Wo) continue;
-        acc += s_col[(r * Wo + ow2 / 2) * pitch + (c * 4 + kh) * 4 + kw];
+        for (int bb = 0; bb < 2; ++bb) {
+          const int kw = kw0 + 2 * bb;
+          const int ow2 = iw + 1 - kw;
+          if (ow2 < 0 || ow2 >= 2 * Wo) continue;
+          acc += s_col[(r * Wo + ow2 / 2) * pitch + (c * 4 + kh) * 4 + kw];
+        }
       }
+      img[(((long long)n * CH + c) * Hi + ih) * Wi + iw] = act_fwd(acc, act);
     }
-    img[(((long long)n * ch + c) * Hi + ih) * Wi + iw] = act_fwd(acc, act);
   }
 }
 
@@ -507,6 +520,81 @@ __global__ void head_bwd_weight_kernel(const float* __restrict__ dout, const __n
       for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
       if (threadIdx.x == 0) dbias[o] = s;
     }
+  }
+}
+
+// Sum-pool head (s_hw == 0, models/dcgan.py:121-122): every spatial position adds into the same dw[o][c], so the
+// reduction over (batch chunk, hw) is done in registers and across the 8 warps of the block in shared memory before one
+// atomic per channel per block. Block = 8 warps x (32 lanes x 8 channels); warp w takes samples b0 + w, b0 + w + 8, ...
+__global__ void __launch_bounds__(256) head_bwd_weight_pool_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ a,
+                                                                   float* __restrict__ dw, int NB, int HW, int C, int O,
+                                                                   long long s_o, long long s_c) {
+  __shared__ float s_acc[8][256];
+  const int o = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = (blockIdx.x * 32 + lane) * 8;
+  const int bchunk = (NB + gridDim.z - 1) / gridDim.z;
+  const int b0 = blockIdx.z * bchunk, b1 = min(b0 + bchunk, NB);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c < C) {
+    for (int b = b0 + warp; b < b1; b += 8) {
+      const float d = __ldg(dout + (long long)b * O + o);
+      const __nv_bfloat16* ap = a + (long long)b * HW * C + c;
+      float t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = 0.f;
+      int hw = 0;
+      for (; hw + 4 <= HW; hw += 4) {
+        Vec8<__nv_bfloat16> v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u].load(ap + (long long)(hw + u) * C);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float f[8];
+          v[u].unpack(f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t[j] += f[j];
+        }
+      }
+      for (; hw < HW; ++hw) {
+        Vec8<__nv_bfloat16> v;
+        v.load(ap + (long long)hw * C);
+        float f[8];
+        v.unpack(f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] += f[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += d * t[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s_acc[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  {
+    const int i = threadIdx.x;  // channel slot within the block
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += s_acc[w][i];
+    const int cc = blockIdx.x * 256 + i;
+    if (cc < C) atomicAdd(dw + o * s_o + cc * s_c, v);
+  }
+}
+
+// dbias[o] = sum_b dout[b][o]   (one block per output)
+__global__ void head_bias_grad_kernel(const float* __restrict__ dout, float* __restrict__ dbias, int NB, int O) {
+  const int o = blockIdx.x;
+  float s = 0.f;
+  for (int b = threadIdx.x; b < NB; b += blockDim.x) s += __ldg(dout + (long long)b * O + o);
+  __shared__ float red[32];
+  for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+    if (threadIdx.x == 0) dbias[o] = s;
   }
 }
 
@@ -729,20 +817,30 @@ static int launch_im2col(const float* img, const float* mul, void* col, void* co
   return GP_OK;
 }
 
-template <typename TC>
-static int launch_col2im(const TC* col, const float* bias, float* img, int NB, int ch, int Hi, int Wi, int act,
-                         void* stream) {
-  GP_REQUIRE(img && col && NB > 0 && ch > 0 && ch <= 4 && Hi % 2 == 0 && Wi % 2 == 0, "gp_col2im_k4s2: bad arguments");
-  const size_t smem = (size_t)(kCol2imRows / 2 + 2) * (Wi / 2) * (ch * 16 + 1) * sizeof(float);
-  auto kfn = col2im_k4s2_kernel<TC>;
+template <typename TC, int CH>
+static int launch_col2im_ch(const TC* col, const float* bias, float* img, int NB, int Hi, int Wi, int act, cudaStream_t st) {
+  const size_t smem = (size_t)(kCol2imRows / 2 + 2) * (Wi / 2) * (CH * 16 + 1) * sizeof(float);
+  auto kfn = col2im_k4s2_kernel<TC, CH>;
   if (smem > 48 * 1024) {
     GP_REQUIRE(smem <= 200 * 1024, "gp_col2im_k4s2: image rows too wide (Wi=%d)", Wi);
     GP_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   dim3 grid((Hi + kCol2imRows - 1) / kCol2imRows, NB);
-  kfn<<<grid, 256, smem, as_stream(stream)>>>(col, bias, img, NB, ch, Hi, Wi, act);
+  kfn<<<grid, 256, smem, st>>>(col, bias, img, NB, Hi, Wi, act);
   GP_CHECK_LAUNCH();
   return GP_OK;
+}
+template <typename TC>
+static int launch_col2im(const TC* col, const float* bias, float* img, int NB, int ch, int Hi, int Wi, int act,
+                         void* stream) {
+  GP_REQUIRE(img && col && NB > 0 && ch > 0 && ch <= 4 && Hi % 2 == 0 && Wi % 2 == 0, "gp_col2im_k4s2: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  switch (ch) {
+    case 1: return launch_col2im_ch<TC, 1>(col, bias, img, NB, Hi, Wi, act, st);
+    case 2: return launch_col2im_ch<TC, 2>(col, bias, img, NB, Hi, Wi, act, st);
+    case 3: return launch_col2im_ch<TC, 3>(col, bias, img, NB, Hi, Wi, act, st);
+    default: return launch_col2im_ch<TC, 4>(col, bias, img, NB, Hi, Wi, act, st);
+  }
 }
 
 extern "C" {
@@ -803,7 +901,19 @@ int gp_head_bwd(const float* dout, const void* a, const float* w, void* da, floa
         dout, w, static_cast<__nv_bfloat16*>(da), NB, HW, C, O, s_o, s_c, s_hw);
     GP_CHECK_LAUNCH();
   }
-  if (dw != nullptr) {
+  if (dw != nullptr && s_hw == 0) {
+    const int gx = (C + 255) / 256;
+    int zsplit = (4 * num_sms()) / (gx * O);
+    if (zsplit < 1) zsplit = 1;
+    if (zsplit > NB) zsplit = NB;
+    head_bwd_weight_pool_kernel<<<dim3(gx, O, zsplit), 256, 0, as_stream(stream)>>>(dout, static_cast<const __nv_bfloat16*>(a),
+                                                                                 dw, NB, HW, C, O, s_o, s_c);
+    GP_CHECK_LAUNCH();
+    if (dbias != nullptr) {
+      head_bias_grad_kernel<<<O, 256, 0, as_stream(stream)>>>(dout, dbias, NB, O);
+      GP_CHECK_LAUNCH();
+    }
+  } else if (dw != nullptr) {
     const int gx = (HW * (C / 8) + 127) / 128;
     int zsplit = (4 * num_sms()) / (gx * O);
     if (zsplit < 1) zsplit = 1;
