@@ -87,7 +87,8 @@ def test_dcgan_step_fused_adam_matches_torch_adam():
         sd.update({"D." + k: v.detach().clone() for k, v in netD.state_dict().items()})
         out.append((losses, sd))
     # step 1 starts from identical weights: its losses agree to rounding; step 2 has seen one Adam update each
-    assert max(abs(x - y) for x, y in zip(out[0][0][0], out[1][0][0])) < 1e-4, (out[0][0][0], out[1][0][0])
+    assert max(abs(x - y) for x, y in zip(out[0][0][0][:2], out[1][0][0][:2])) < 1e-4, (out[0][0][0], out[1][0][0])
+    assert max(abs(x - y) for x, y in zip(out[0][0][0], out[1][0][0])) < 5e-3, (out[0][0][0], out[1][0][0])  # G step: after optD.step()
     assert max(abs(x - y) for x, y in zip(out[0][0][1], out[1][0][1])) < 2e-2, (out[0][0][1], out[1][0][1])
     # The split-K fp32 atomics of wgrad make gradients differ in the last bits from run to run; Adam turns a near-zero
     # gradient element's sign into a +-lr step, so isolated elements may differ by a few lr per step
