@@ -33,6 +33,8 @@ def main():
     cases["img_fwd"] = lambda: ops.conv_fwd(X["col"], W["img"], Bv[128], ops.KIND_CONV_K1S1, 32, 32, ops.ACT_LRELU)
     cases["img_dgrad"] = lambda: ops.conv_fwd(X["a128"], W["imgT"], None, ops.KIND_CONV_K1S1, 32, 32)
     cases["d1_fwd"] = lambda: ops.conv_fwd(X["a128"], W["d1"], Bv[256], ops.KIND_CONV_K4S2, 16, 16)
+    cases["d1_fwd_x3"] = lambda: ops.conv_fwd(X["a128"], W["d1x3"], Bv[256], ops.KIND_CONV_K4S2, 16, 16, x_lo=X["a128_lo"],
+                                              out_mode="f32", stats=torch.zeros(2, 256, device=dev))
     cases["d1_fwd_stats"] = lambda: ops.conv_fwd(X["a128"], W["d1"], Bv[256], ops.KIND_CONV_K4S2, 16, 16,
                                                  stats=torch.zeros(2, 256, device=dev))
     cases["g2_fwd_stats"] = lambda: ops.conv_fwd(X["a256_16"], W["g2"], Bv[128], ops.KIND_CONVT_K4S2, 32, 32,
@@ -48,7 +50,8 @@ def main():
 
     X = {"col": act(B, 32, 32, 64), "a128": act(B, 32, 32, 128), "a256_16": act(B, 16, 16, 256),
          "a512_8": act(B, 8, 8, 512), "a1024_4": act(B, 4, 4, 1024)}
-    W = {"img": wt(128, 64), "imgT": wt(64, 128), "d1": wt(256, 16 * 128), "g2": wt(128, 16 * 256),
+    X["a128_lo"] = (X["a128"].float() * 2.0 ** -9).to(torch.bfloat16)
+    W = {"d1x3": wt(256, 2 * 16 * 128), "img": wt(128, 64), "imgT": wt(64, 128), "d1": wt(256, 16 * 128), "g2": wt(128, 16 * 256),
          "d3": wt(1024, 16 * 512),
          "d2": wt(512, 16 * 256), "g0": wt(512, 16 * 1024), "g1": wt(256, 16 * 512)}
     Bv = {n: torch.randn(n, device=dev) * 0.1 for n in (128, 256, 512, 1024)}
