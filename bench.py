@@ -255,8 +255,19 @@ def main():
     gemm = prof.summary()
     peaks, peaks_src = load_peaks()
     peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    # DRAM bytes moved by the same 53 GEMM launches of one step, from the committed ncu launch list of this command
+    # (profiles/ncu_gemm_traffic.json; only valid for the configuration it was captured on)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_gemm_traffic.json")))
+        if world == 1 and tj.get("global_batch") == global_batch and tj.get("precision", "").startswith(config.precision()) \
+                and (" (real" in tj.get("precision", "")) == bool(runner.real_precision):
+            traffic, traffic_src = tj["dram_bytes_per_step_gemm"], tj["source"]
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {"bound": "tensor", "achieved": gemm["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": gemm["tflops"] / peak_tf, "traffic": None,
+                "frac": gemm["tflops"] / peak_tf, "traffic": traffic, "traffic_unit": "bytes of DRAM traffic per step (all GEMM launches)",
+                "traffic_source": traffic_src,
                 "kernel": "gp::conv_gemm_kernel<MODE,BN> (all %d launches of one step)" % gemm["launches"],
                 "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peaks_src,
                 "gemm_ms_per_step": gemm["ms"], "gemm_share_of_step": gemm["ms"] / ms_per_step,
