@@ -7,8 +7,10 @@ side stream after a warm-up, the six logged scalars (losses, D(x), D(G(z))) are 
 graph and read back once per step. Graph replay removes the per-launch host overhead (~250 launches per step), which
 is what bounds small per-GPU batches (strong scaling at 128 images/GPU).
 
-Requirements for graph mode: optimisers built with `capturable=True`; fixed batch size; the weight-staging caches of the
-networks are cleared before capture so the staging kernels are part of the graph."""
+Requirements for graph mode: torch optimisers built with `capturable=True` (FusedAdam is capturable as is); fixed batch
+size. The weight-staging caches of the networks are cleared before capture so the staging kernels are part of the graph,
+and the warm-up steps capture needs are undone afterwards (parameters, BatchNorm buffers and optimiser state are restored
+in place), so the first replay is the first training step."""
 import torch
 
 from . import config, parallel
@@ -106,7 +108,44 @@ class DcganStep:
         self._body(inputs, z1, z2, log)
         return vals
 
+    # ---- capture must not train: the warm-up steps run real optimiser steps, so everything they touch is restored
+    def _snapshot(self):
+        snap = {"nets": [{k: v.detach().clone() for k, v in n.state_dict().items()} for n in (self.netG, self.netD)], "opts": []}
+        for opt in (self.optG, self.optD):
+            if isinstance(opt, FusedAdam):
+                snap["opts"].append([None if st is None else {k: st[k].clone() for k in ("m", "v", "step")} for st in opt._flat])
+            else:
+                snap["opts"].append({id(p): {k: v.clone() for k, v in stt.items() if torch.is_tensor(v)}
+                                     for p, stt in opt.state.items()})
+        return snap
+
+    @torch.no_grad()
+    def _restore(self, snap):
+        for net, sd in zip((self.netG, self.netD), snap["nets"]):
+            cur = net.state_dict()
+            for k, v in sd.items():
+                cur[k].copy_(v)                      # in place: parameters stay views of the flat optimiser buffers
+        for opt, saved in zip((self.optG, self.optD), snap["opts"]):
+            if isinstance(opt, FusedAdam):
+                for st, sv in zip(opt._flat, saved):
+                    if st is not None:
+                        for k in ("m", "v", "step"):
+                            st[k].copy_(sv[k])
+                for group in opt.param_groups:
+                    for p in group["params"]:
+                        p._gp_epoch = getattr(p, "_gp_epoch", 0) + 1
+            else:
+                for p, stt in opt.state.items():     # in place too: the captured graph references these tensors
+                    old = saved.get(id(p))
+                    for k, v in stt.items():
+                        if torch.is_tensor(v):
+                            if old is not None and k in old:
+                                v.copy_(old[k])
+                            else:
+                                v.zero_()            # state created by the warm-up: back to torch.optim.Adam's initial zeros
+
     def _capture(self):
+        snap = self._snapshot()
         _clear_caches(self.netG, self.netD)
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream())
@@ -132,6 +171,8 @@ class DcganStep:
         with torch.cuda.graph(g):
             body()
         self.graph = g
+        self._restore(snap)
+        torch.cuda.synchronize()
 
     def step(self, inputs, z=None):
         """One training step. Returns [lossD_real, lossD_fake, lossG, D(x), D(G(z))_1, D(G(z))_2] as Python floats."""
@@ -145,4 +186,6 @@ class DcganStep:
         if z is not None:
             self.z_static.copy_(z, non_blocking=True)
         self.graph.replay()
+        # the replay updated the weights behind Python's back: operand copies cached by earlier eager calls are stale
+        _clear_caches(self.netG, self.netD)
         return self.scalars.tolist()      # one device->host read per step
