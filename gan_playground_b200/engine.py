@@ -13,7 +13,7 @@ and the warm-up steps capture needs are undone afterwards (parameters, BatchNorm
 in place), so the first replay is the first training step."""
 import torch
 
-from . import config, parallel
+from . import config, ops, parallel
 from .optim import FusedAdam
 
 
@@ -42,6 +42,8 @@ class DcganStep:
         self.fixed_z = False
         self._warmup = warmup
         self.overlap = overlap
+        self.arena = ops.ZeroArena(device)
+        self._d_params = [p for p in netD.parameters() if p.requires_grad]
         # mixed forward precision: the real-image D pass needs no 3-MMA forward (config.precision_scope)
         self.real_precision = "bf16" if (mixed_precision and config.x3()) else None
         self._side = torch.cuda.Stream(device=device) if device.type == "cuda" else None
@@ -49,6 +51,14 @@ class DcganStep:
     # ---- the loop body; `log(i, t)` receives the six scalars as 0-dim device tensors
     def _body(self, inputs, z1, z2, log):
         netG, netD, crit = self.netG, self.netD, self.crit
+        self.arena.begin()                                       # one memset for every zero-initialised workspace
+        ops.ZeroArena.active = self.arena
+        try:
+            self._body_steps(netG, netD, crit, inputs, z1, z2, log)
+        finally:
+            ops.ZeroArena.active = None
+
+    def _body_steps(self, netG, netD, crit, inputs, z1, z2, log):
         self._zero(self.optD, self.bucketD)                      # optD.zero_grad()
         with config.precision_scope(self.real_precision or config.precision()):
             outD = netD(inputs)
@@ -74,10 +84,18 @@ class DcganStep:
             self._step(self.optD, self.bucketD)                  # (gradient all-reduce +) optD.step()
             self._zero(self.optG, self.bucketG)                  # optG.zero_grad()
             outG = netG(z2)
-        outD = netD(outG)
-        log(5, outD.mean())
-        lossG = crit(outD, False, True)
-        lossG.backward()
+        # G step: D only relays the gradient to G. The reference also computes D's weight gradients here and throws
+        # them away at the next optD.zero_grad() (main_dcgan.py:68,87-94; SURVEY.md §8d "minimal step"): skip them
+        for p in self._d_params:
+            p.requires_grad_(False)
+        try:
+            outD = netD(outG)
+            log(5, outD.mean())
+            lossG = crit(outD, False, True)
+            lossG.backward()
+        finally:
+            for p in self._d_params:
+                p.requires_grad_(True)
         self._step(self.optG, self.bucketG)                      # (gradient all-reduce +) optG.step()
         log(0, lossD_real.detach()), log(1, lossD_fake.detach()), log(2, lossG.detach())
 

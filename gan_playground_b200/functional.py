@@ -77,8 +77,8 @@ def _bn_forward(y, gamma, beta, bufs, act, training=True, st=None):
     return a, a_lo, fin, count
 
 
-def _bn_backward(da, y, fin, count, act, training=True):
-    """Returns (dy, dgamma, dbeta)."""
+def _bn_backward(da, y, fin, count, act, training=True, need_affine=True):
+    """Returns (dy, dgamma, dbeta); dgamma / dbeta are None when the affine parameters need no gradient."""
     f32 = y.dtype == torch.float32
     red = ops.bn_bwd_reduce_f32(da, y, fin, act) if f32 else ops.bn_bwd_reduce(da, y, fin, act)
     parallel.all_reduce_sum_(red)
@@ -90,6 +90,8 @@ def _bn_backward(da, y, fin, count, act, training=True):
         dy = ops.bn_bwd_apply(da, y, fin, red_used, count, act)
     # dbeta = sum dz, dgamma = sum dz * xhat. After the all-reduce `red` holds global sums of rank-local-mean-loss
     # gradients; parameter gradients are averaged over ranks later, so hand back global / world.
+    if not need_affine:
+        return dy, None, None
     w = parallel.world_size()
     dgamma, dbeta = red[1], red[0]
     if w > 1:
@@ -117,7 +119,7 @@ class ConvBlock(torch.autograd.Function):
         Cout = weight.shape[1] if transposed else weight.shape[0]
         st = None
         if has_bn and training and config.fused_stats() and Cout <= 2048:
-            st = torch.zeros((2, Cout), device=x.device, dtype=torch.float32)
+            st = ops.zeros((2, Cout), x.device)
         if x3:
             wp = cache.get((key, "fwd3"), weight, lambda: ops.split_conv_weight(weight.detach(), n_dim))
             if x_lo is None:
@@ -147,7 +149,8 @@ class ConvBlock(torch.autograd.Function):
         da = da.contiguous()
         if ctx.has_bn:
             x, weight, y, fin = ctx.saved_tensors
-            dy, dgamma, dbeta = _bn_backward(da, y, fin, ctx.count, ctx.act, ctx.training)
+            dy, dgamma, dbeta = _bn_backward(da, y, fin, ctx.count, ctx.act, ctx.training,
+                                             need_affine=ctx.needs_input_grad[4] or ctx.needs_input_grad[5])
             # a bias in front of BatchNorm has an analytically zero gradient (the reference's is fp32 rounding noise,
             # SURVEY.md §2.2): hand autograd no tensor at all instead of a zero fill plus an accumulation pass
             dbias = None

@@ -104,6 +104,51 @@ def _chk(t, dtype, name):
         raise _lib.GpError("%s must be contiguous" % name)
 
 
+# ------------------------------------------------------------------------------------------------ zeroed workspaces
+class ZeroArena:
+    """One memset per training step instead of ~100 small fills: the zero-initialised fp32 workspaces the kernels
+    accumulate into (split-K weight gradients, BatchNorm partial sums, bias-gradient sums) are carved out of one buffer
+    that `begin()` clears at the start of a step. Slices are valid until the next `begin()`, which every consumer on the
+    training path satisfies (the sums are finalised / unpacked / accumulated into .grad within the same step).
+    Only engine.DcganStep activates it (parameters there always own a .grad view, so autograd never adopts a slice as
+    .grad); everywhere else `zeros()` is torch.zeros."""
+
+    active = None
+
+    def __init__(self, device):
+        self.dev, self.buf, self.off, self.need = device, None, 0, 0
+
+    def begin(self):
+        if self.buf is None or self.need > self.buf.numel():
+            if self.need:
+                self.buf = torch.zeros(int(self.need * 1.05) + 1024, device=self.dev, dtype=torch.float32)
+        elif self.off:
+            self.buf[:self.off].zero_()
+        self.off, self.need = 0, 0
+
+    def take(self, numel):
+        n = (numel + 63) // 64 * 64          # 256-byte granules keep every slice aligned for 16-byte vector atomics
+        self.need += n
+        if self.buf is None or self.off + n > self.buf.numel():
+            return None
+        t = self.buf[self.off:self.off + numel]
+        self.off += n
+        return t
+
+
+def zeros(shape, device):
+    """fp32 zeros: a slice of the active ZeroArena when there is one, else torch.zeros."""
+    a = ZeroArena.active
+    if a is not None:
+        n = 1
+        for d in shape:
+            n *= d
+        t = a.take(n)
+        if t is not None:
+            return t.view(shape)
+    return torch.zeros(shape, device=device, dtype=torch.float32)
+
+
 # ------------------------------------------------------------------------------------------------ conv GEMMs
 class GemmProfiler:
     """Times every tensor-core GEMM launch (gp::conv_gemm_kernel) with CUDA events on the launching stream and
@@ -192,7 +237,7 @@ def conv_wgrad(dense, gath, kind, taps, flops=None):
     _chk(gath, torch.bfloat16, "gath")
     NB, Hs, Ws, Cd = dense.shape
     _, Hg, Wg, Cg = gath.shape
-    dw = torch.zeros((Cd, taps, Cg), device=dense.device, dtype=torch.float32)
+    dw = zeros((Cd, taps, Cg), dense.device)
     p = ConvWgrad(_p(dense), _p(gath), _p(dw), NB, Hs, Ws, Cd, Hg, Wg, Cg, kind)
     if flops is None:
         flops = 2.0 * NB * Hs * Ws * Cd * Cg * taps
@@ -243,7 +288,7 @@ def bn_stats(y):
     _chk(y, torch.bfloat16, "y")
     C = y.shape[-1]
     P = y.numel() // C
-    st = torch.zeros((2, C), device=y.device, dtype=torch.float32)
+    st = zeros((2, C), y.device)
     check(_fn("gp_bn_stats")(_p(y), P, C, _p(st[0]), _p(st[1]), _stream()), "gp_bn_stats")
     return st
 
@@ -279,7 +324,7 @@ def bn_bwd_reduce(da, y, fin, act):
     _chk(da, torch.bfloat16, "da")
     _chk(y, torch.bfloat16, "y")
     C = y.shape[-1]
-    red = torch.zeros((2, C), device=y.device, dtype=torch.float32)
+    red = zeros((2, C), y.device)
     check(_fn("gp_bn_bwd_reduce")(_p(da), _p(y), y.numel() // C, C, _p(fin[2]), _p(fin[3]), _p(fin[0]), _p(fin[1]), act,
                                   _p(red[0]), _p(red[1]), _stream()), "gp_bn_bwd_reduce")
     return red
@@ -304,7 +349,7 @@ def act_bwd(da, a, act):
 def colsum(x):
     _chk(x, torch.bfloat16, "x")
     C = x.shape[-1]
-    out = torch.zeros((C,), device=x.device, dtype=torch.float32)
+    out = zeros((C,), x.device)
     check(_fn("gp_colsum")(_p(x), x.numel() // C, C, _p(out), _stream()), "gp_colsum")
     return out
 
@@ -333,7 +378,7 @@ def col2im_k4s2(col, bias, ch, act):
 def image_bias_grad(dout, mul=None):
     _chk(dout, torch.float32, "dout")
     NB, ch, H, W = dout.shape
-    db = torch.zeros((ch,), device=dout.device, dtype=torch.float32)
+    db = zeros((ch,), dout.device)
     check(_fn("gp_image_bias_grad")(_p(dout), _p(mul), _p(db), NB, ch, H * W, _stream()), "gp_image_bias_grad")
     return db
 
@@ -353,7 +398,7 @@ def head_bwd(dout, a, w, O, s_o, s_c, s_hw, need_da=True, need_dw=True, need_db=
     _chk(dout, torch.float32, "dout")
     NB, H, W, C = a.shape
     da = torch.empty_like(a) if need_da else None
-    dw = torch.zeros_like(w) if need_dw else None
+    dw = zeros(tuple(w.shape), w.device) if need_dw else None
     db = torch.empty((O,), device=a.device, dtype=torch.float32) if (need_db and need_dw) else None
     check(_fn("gp_head_bwd")(_p(dout), _p(a), _p(w), _p(da), _p(dw), _p(db), NB, H * W, C, O, s_o, s_c, s_hw, _stream()),
           "gp_head_bwd")
@@ -589,7 +634,7 @@ def split_conv_weight(w, n_dim):
 def bn_stats_f32(y):
     _chk(y, torch.float32, "y")
     C = y.shape[-1]
-    st = torch.zeros((2, C), device=y.device, dtype=torch.float32)
+    st = zeros((2, C), y.device)
     check(_fn("gp_bn_stats_f32")(_p(y), y.numel() // C, C, _p(st[0]), _p(st[1]), _stream()), "gp_bn_stats_f32")
     return st
 
@@ -608,7 +653,7 @@ def bn_bwd_reduce_f32(da, y, fin, act):
     _chk(da, torch.bfloat16, "da")
     _chk(y, torch.float32, "y")
     C = y.shape[-1]
-    red = torch.zeros((2, C), device=y.device, dtype=torch.float32)
+    red = zeros((2, C), y.device)
     check(_fn("gp_bn_bwd_reduce_f32")(_p(da), _p(y), y.numel() // C, C, _p(fin[2]), _p(fin[3]), _p(fin[0]), _p(fin[1]), act,
                                       _p(red[0]), _p(red[1]), _stream()), "gp_bn_bwd_reduce_f32")
     return red
