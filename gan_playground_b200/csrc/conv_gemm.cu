@@ -127,25 +127,11 @@ static int launch_fwd_x3(const ConvGemmParams& prm, int bn, int mt, int grid, cu
   return mt == 2 ? launch_cfg<MODE_FWD, 64, 2, true>(prm, grid, st) : launch_cfg<MODE_FWD, 64, 1, true>(prm, grid, st);
 }
 
-}  // namespace gp
-
-using namespace gp;
-
-extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
-  GP_REQUIRE(a != nullptr && a->in && a->w && (a->out || a->out_f32), "gp_conv_fwd: null pointer");
-  GP_REQUIRE(a->NB > 0 && a->Cin > 0 && a->Nout > 0, "gp_conv_fwd: empty problem");
-  GP_REQUIRE(a->Cin % 8 == 0, "gp_conv_fwd: Cin=%d must be a multiple of 8 (16-byte TMA rows)", a->Cin);
-  GP_REQUIRE(a->Nout % 8 == 0, "gp_conv_fwd: Nout=%d must be a multiple of 8", a->Nout);
-  GP_REQUIRE(a->act != GP_ACT_TANH, "gp_conv_fwd: tanh is fused in gp_col2im_k4s2, not in the GEMM epilogue");
-  GP_REQUIRE(a->col_sum == nullptr || a->Nout <= kMaxStatCols, "gp_conv_fwd: fused statistics support Nout <= %d", kMaxStatCols);
-  ConvGemmParams prm;
-  memset(&prm, 0, sizeof(prm));
-  const int Cin = a->Cin;
-  int ntaps_total = 0;
-  int rc;
-  // Tile shape: the candidate (BN, MT) with the smallest estimated time = waves x tile MACs x relative cost per MAC.
-  // Costs are measured ratios on B200 (tools/prof_gemm.py): 128x256 is the reference; 256x256 (no epilogue overlap)
-  // wins only for long K loops; narrower tiles move more operand bytes per FLOP but fill the 148 SMs at small batch.
+// Tile shape of a forward / dgrad call: the candidate (BN, MT) with the smallest estimated time = waves x tile MACs x
+// relative cost per MAC. Costs are measured ratios on B200 (tools/prof_gemm.py): 128x256 is the reference; 256x256 (no
+// epilogue overlap) wins only for long K loops; narrower tiles move more operand bytes per FLOP but fill the 148 SMs at
+// small batch.
+static void choose_fwd_tile(const gp_conv_fwd_t* a, int* bn_out, int* mt_out) {
   int bn = 0, mt_sub = 1;
   {
     const long long small_px = (a->kind == GP_KIND_CONV_K4S2) ? (long long)a->NB * a->Hout * a->Wout
@@ -171,6 +157,28 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
     }
     tile_override("GP_TILE_FWD", &bn, &mt_sub);
   }
+  *bn_out = bn;
+  *mt_out = mt_sub;
+}
+
+}  // namespace gp
+
+using namespace gp;
+
+extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
+  GP_REQUIRE(a != nullptr && a->in && a->w && (a->out || a->out_f32), "gp_conv_fwd: null pointer");
+  GP_REQUIRE(a->NB > 0 && a->Cin > 0 && a->Nout > 0, "gp_conv_fwd: empty problem");
+  GP_REQUIRE(a->Cin % 8 == 0, "gp_conv_fwd: Cin=%d must be a multiple of 8 (16-byte TMA rows)", a->Cin);
+  GP_REQUIRE(a->Nout % 8 == 0, "gp_conv_fwd: Nout=%d must be a multiple of 8", a->Nout);
+  GP_REQUIRE(a->act != GP_ACT_TANH, "gp_conv_fwd: tanh is fused in gp_col2im_k4s2, not in the GEMM epilogue");
+  GP_REQUIRE(a->col_sum == nullptr || a->Nout <= kMaxStatCols, "gp_conv_fwd: fused statistics support Nout <= %d", kMaxStatCols);
+  ConvGemmParams prm;
+  memset(&prm, 0, sizeof(prm));
+  const int Cin = a->Cin;
+  int ntaps_total = 0;
+  int rc;
+  int bn = 0, mt_sub = 1;
+  choose_fwd_tile(a, &bn, &mt_sub);
   const int tile_px = mt_sub * kBlockM;
   const int n_halves = a->in_lo != nullptr ? 2 : 1;  // bf16x3: hi and lo halves of the activation operand
   const long long inW = Cin, inH = (long long)a->Win * Cin, inN = (long long)a->Hin * a->Win * Cin;
@@ -296,6 +304,15 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   if (n_halves == 2) return launch_fwd_x3(prm, bn, mt_sub, grid, as_stream(stream));
   return launch<MODE_FWD>(prm, bn, mt_sub, grid, as_stream(stream));
+}
+
+extern "C" int gp_conv_fwd_plan(const gp_conv_fwd_t* a, int* bn, int* mt, int* tiles) {
+  GP_REQUIRE(a != nullptr && bn && mt && tiles && a->NB > 0 && a->Cin > 0 && a->Nout > 0, "gp_conv_fwd_plan: bad arguments");
+  choose_fwd_tile(a, bn, mt);
+  const long long small_px = (a->kind == GP_KIND_CONV_K4S2) ? (long long)a->NB * a->Hout * a->Wout : (long long)a->NB * a->Hin * a->Win;
+  const int phases = a->kind == GP_KIND_CONVT_K4S2 ? 4 : 1;
+  *tiles = (int)(phases * ((small_px + *mt * kBlockM - 1) / (*mt * kBlockM)) * ((a->Nout + *bn - 1) / *bn));
+  return GP_OK;
 }
 
 extern "C" int gp_conv_wgrad(const gp_conv_wgrad_t* a, void* stream) {

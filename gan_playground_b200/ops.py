@@ -84,7 +84,7 @@ def _fn(name):
 
 def exported_symbols():
     """Names of every compute entry point declared in include/gpb200.h (used by the CPU-side ABI test)."""
-    return sorted(_SIGS) + ["gp_version", "gp_last_error", "gp_launch_count", "gp_peer_buffer_bytes"]
+    return sorted(_SIGS) + ["gp_version", "gp_last_error", "gp_launch_count", "gp_peer_buffer_bytes", "gp_conv_fwd_plan"]
 
 
 def _p(t):
@@ -229,6 +229,18 @@ def conv_fwd(x, wp, bias, kind, Hout, Wout, act=ACT_NONE, stats=None, flops=None
     if out_mode == "split":
         return out, out_lo
     return out
+
+
+def conv_fwd_plan(NB, Hin, Win, Cin, Hout, Wout, Nout, kind, x3=False):
+    """(BN, MT, tiles) gp_conv_fwd would choose for this shape (host-side cost model; runs without a GPU)."""
+    p = ConvFwd(None, None, None, None, None, None, NB, Hin, Win, Cin, Hout, Wout, Nout, kind, 0, None,
+                1 if x3 else None, None, None)
+    bn, mt, tiles = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    f = _lib.lib().gp_conv_fwd_plan
+    f.argtypes = [_vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    f.restype = ctypes.c_int
+    check(f(ctypes.addressof(p), ctypes.byref(bn), ctypes.byref(mt), ctypes.byref(tiles)), "gp_conv_fwd_plan")
+    return bn.value, mt.value, tiles.value
 
 
 def conv_wgrad(dense, gath, kind, taps, flops=None):

@@ -70,6 +70,9 @@ typedef struct {
   float* out_f32;         /* optional: write fp32 here instead of bf16 `out` (pre-BatchNorm outputs)                */
 } gp_conv_fwd_t;
 int gp_conv_fwd(const gp_conv_fwd_t* p, void* stream);
+/* Host-only: the tile shape gp_conv_fwd would use for this problem (BN in {64,128,256} output columns, MT in {1,2}
+ * 128-row sub-tiles) and the resulting number of output tiles. No pointers are dereferenced, nothing is launched. */
+int gp_conv_fwd_plan(const gp_conv_fwd_t* p, int* bn, int* mt, int* tiles);
 
 /* ---- weight gradient (the wgrad half of aten::convolution_backward).
  *   dw[m, tap, n] += sum_pixels dense[pix, m] * gath[gather(pix, tap), n]

@@ -142,3 +142,23 @@ def test_parameters_are_fp32_leaf_params_usable_by_adam():
     torch.optim.Adam(ps, lr=4e-4, betas=(0.5, 0.999))
     # only reference keys are in the state dict (the weight cache is not serialised)
     assert not any("cache" in k for k in g.state_dict())
+
+
+def test_forward_tile_cost_model_fills_the_machine(built_lib):
+    """Host-side tile selection of gp_conv_fwd (no GPU needed): full-batch DCGAN-64 layers get the 256-wide tiles,
+    the long-K layer the 256x256 one, narrow outputs 256-row tiles, and 128-image shards (8-GPU strong scaling) the
+    narrower tiles that still give every SM work."""
+    from gan_playground_b200 import ops
+
+    K4, CT, K1 = ops.KIND_CONV_K4S2, ops.KIND_CONVT_K4S2, ops.KIND_CONV_K1S1
+    assert ops.conv_fwd_plan(1024, 32, 32, 128, 16, 16, 256, K4) == (256, 1, 2048)       # D block 1
+    assert ops.conv_fwd_plan(1024, 8, 8, 512, 4, 4, 1024, K4) == (256, 2, 256)           # D block 3: K = 8192
+    assert ops.conv_fwd_plan(1024, 8, 8, 512, 4, 4, 1024, K4, x3=True)[:2] == (256, 1)   # no 256x256 bf16x3 variant
+    assert ops.conv_fwd_plan(1024, 16, 16, 256, 32, 32, 128, CT) == (128, 2, 4096)       # G block 2: N = 128
+    assert ops.conv_fwd_plan(1024, 32, 32, 64, 32, 32, 128, K1)[:2] == (128, 2)          # image-side GEMM
+    bn, mt, tiles = ops.conv_fwd_plan(128, 8, 8, 512, 4, 4, 1024, K4)                    # D block 3 at 128 images
+    assert (bn, mt) == (128, 1) and 100 <= tiles <= 148
+    for shape in ((128, 32, 32, 128, 16, 16, 256, K4), (128, 4, 4, 1024, 8, 8, 512, CT), (16, 16, 16, 64, 8, 8, 64, K4)):
+        bn, mt, tiles = ops.conv_fwd_plan(*shape)
+        assert bn in (64, 128, 256) and mt in (1, 2) and tiles >= 1
+        assert bn // 2 < shape[6] or bn == 64                                            # never mostly padding
