@@ -418,3 +418,99 @@ class CpuDcganTrainer:
         l_g.backward()
         self.opt_g.step()
         return l_real.item(), l_fake.item(), l_g.item(), dx, dgz1, dgz2
+
+
+class _CpuTrainer:
+    """Shared plumbing of the CPU loop restatements: parameters become leaves, buffers are updated in place."""
+
+    def __init__(self, sd_g, sd_d, lr_g, lr_d, betas):
+        self.pg, self.bg = split_state({k: v.clone() for k, v in sd_g.items()})
+        self.pd, self.bd = split_state({k: v.clone() for k, v in sd_d.items()})
+        for d in (self.pg, self.pd):
+            for v in d.values():
+                v.requires_grad_(True)
+        self.opt_g = torch.optim.Adam(list(self.pg.values()), lr=lr_g, betas=betas)
+        self.opt_d = torch.optim.Adam(list(self.pd.values()), lr=lr_d, betas=betas)
+
+    def state_dicts(self):
+        """(generator, discriminator) state in the reference's state_dict layout (detached copies)."""
+        return ({k: v.detach().clone() for k, v in {**self.pg, **self.bg}.items()},
+                {k: v.detach().clone() for k, v in {**self.pd, **self.bd}.items()})
+
+
+class CpuSnganTrainer(_CpuTrainer):
+    """The loop body of main_sngan.py:65-100 on the CPU in fp32: Adam(lr 2e-4, betas (0, 0.999)) on both nets (:54-55,
+    argparse defaults :20-21), GANLoss('hinge') (:57); ONE generator forward per iteration — the G step (:92-99) re-uses
+    the graph of the fake batch the discriminator was just trained on and runs only when `i % n_disc_update == 0`."""
+
+    def __init__(self, sd_g, sd_d, n_disc_update=5, bottom_width=4, lr=2e-4, betas=(0.0, 0.999)):
+        super().__init__(sd_g, sd_d, lr, lr, betas)
+        self.n_disc_update, self.bottom_width = n_disc_update, bottom_width
+        self.i = 0
+
+    def _d(self, x, y):
+        sd = {**self.pd, **self.bd}
+        return sngan_discriminator(sd, x, y)          # u / v buffers advance in place (shared tensors)
+
+    def step(self, x, y, z, c):
+        """Returns (lossD_real, lossD_fake, lossG or None, D(x), D(G(z))_1, D(G(z))_2 or None)."""
+        self.opt_d.zero_grad()
+        out = self._d(x, y)
+        dx = out.mean().item()
+        l_real = gan_loss("hinge", out, True)
+        l_real.backward()
+        fake = sngan_generator({**self.pg, **self.bg}, z, c, bottom_width=self.bottom_width, buffers=self.bg)
+        out = self._d(fake.detach(), c)
+        dgz1 = out.mean().item()
+        l_fake = gan_loss("hinge", out, False)
+        l_fake.backward()
+        self.opt_d.step()
+        l_g = dgz2 = None
+        if self.i % self.n_disc_update == 0:
+            self.opt_g.zero_grad()
+            out = self._d(fake, c)
+            dgz2 = out.mean().item()
+            l_g = gan_loss("hinge", out, False, True)
+            l_g.backward()
+            self.opt_g.step()
+            l_g = l_g.item()
+        self.i += 1
+        return l_real.item(), l_fake.item(), l_g, dx, dgz1, dgz2
+
+
+class CpuAcganTrainer(_CpuTrainer):
+    """The loop body of main_acgan.py:84-133 on the CPU in fp32: Adam(lr 4e-4 / 1e-4, betas (0.5, 0.999)) (:59-60),
+    adversarial GANLoss('vanilla', 0.9, 0.1, 0.9) (:62) plus 0.5 x MSELoss between the auxiliary head and the float
+    attribute vector (:64,95-97,114-116,129-131). The fake batch is conditioned on the real batch's labels (:106-107);
+    one generator forward per iteration (the G step re-uses outG, :123); D(x) / D(G(z)) are sigmoid means (:94,112,127)."""
+
+    def __init__(self, sd_g, sd_d, labels=(0.9, 0.1, 0.9), lr_g=4e-4, lr_d=1e-4, betas=(0.5, 0.999), aux_weight=0.5):
+        super().__init__(sd_g, sd_d, lr_g, lr_d, betas)
+        self.labels, self.aux_weight = labels, aux_weight
+
+    def _d(self, x):
+        return dcgan_discriminator({**self.pd, **self.bd}, x, acgan=True, buffers=self.bd)
+
+    def step(self, x, y, z):
+        """Returns (lossD_adv, lossD_aux, lossG_adv, lossG_aux, D(x), D(G(z))_1, D(G(z))_2) — the seven numbers of the
+        reference's progress line (:136-137)."""
+        rl, fl, gl = self.labels
+        self.opt_d.zero_grad()
+        adv, cls = self._d(x)
+        dx = torch.sigmoid(adv).mean().item()
+        l_real_adv, l_real_aux = gan_loss("vanilla", adv, True, False, rl, fl, gl), F.mse_loss(cls, y)
+        (l_real_adv + l_real_aux * self.aux_weight).backward()
+        fake = dcgan_generator({**self.pg, **self.bg}, z, y, acgan=True, buffers=self.bg)
+        adv, cls = self._d(fake.detach())
+        dgz1 = torch.sigmoid(adv).mean().item()
+        l_fake_adv, l_fake_aux = gan_loss("vanilla", adv, False, False, rl, fl, gl), F.mse_loss(cls, y)
+        (l_fake_adv + l_fake_aux * self.aux_weight).backward()
+        self.opt_d.step()
+        self.opt_g.zero_grad()
+        adv, cls = self._d(fake)
+        dgz2 = torch.sigmoid(adv).mean().item()
+        l_g_adv, l_g_aux = gan_loss("vanilla", adv, False, True, rl, fl, gl), F.mse_loss(cls, y)
+        (l_g_adv + l_g_aux * self.aux_weight).backward()
+        self.opt_g.step()
+        return ((l_real_adv + l_fake_adv).item(), (l_real_aux + l_fake_aux).item(), l_g_adv.item(), l_g_aux.item(),
+                dx, dgz1, dgz2)

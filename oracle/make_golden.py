@@ -278,6 +278,126 @@ def acgan_fixture(mods, width, batch, seed):
     return fx
 
 
+def sngan_loop_data(seed, steps, batch, z_dim, n_class=10):
+    """Deterministic data stream of the main_sngan loop fixture, regenerated by the tests from the seed."""
+    gen = torch.Generator().manual_seed(seed + 11)
+    xs = torch.rand(steps, batch, 3, 32, 32, generator=gen) * 2 - 1
+    ys = torch.randint(n_class, (steps, batch), generator=gen)
+    zs = torch.randn(steps, batch, z_dim, generator=gen)
+    cs = torch.randint(n_class, (steps, batch), generator=gen)
+    return xs, ys, zs, cs
+
+
+def sngan_loop_fixture(mods, ch, batch, steps, seed, n_disc_update=2, z_dim=16):
+    """`steps` iterations of main_sngan.py:65-100 (Adam lr 2e-4, betas (0, 0.999): argparse defaults :19-21; hinge loss;
+    the G step every `n_disc_update` iterations re-using the fake batch's graph) on the unmodified reference."""
+    M = mods["sngan_projection"]
+    torch.manual_seed(seed)
+    netG = M.ResNetGenerator(ch=ch, dim_z=z_dim, bottom_width=2, img_dim=3, n_classes=10)
+    netD = M.SNResNetProjectionDiscriminator(ch=ch, n_classes=10, img_dim=3)
+    crit = mods["criterion"].GANLoss("hinge")
+    optG = torch.optim.Adam(netG.parameters(), lr=2e-4, betas=(0.0, 0.999))
+    optD = torch.optim.Adam(netD.parameters(), lr=2e-4, betas=(0.0, 0.999))
+    netG.train(), netD.train()
+    sd_g0, sd_d0 = clone_sd(netG), clone_sd(netD)
+    xs, ys, zs, cs = sngan_loop_data(seed, steps, batch, z_dim)
+    trace = []
+    for i in range(steps):
+        optD.zero_grad()
+        outD = netD(xs[i], ys[i])
+        Dx = outD.mean().item()
+        lossD_real = crit(outD, True)
+        lossD_real.backward()
+        outG = netG(zs[i], cs[i])
+        outD = netD(outG.detach(), cs[i])
+        Dgz1 = outD.mean().item()
+        lossD_fake = crit(outD, False)
+        lossD_fake.backward()
+        optD.step()
+        row = [lossD_real.item(), lossD_fake.item(), float("nan"), Dx, Dgz1, float("nan")]
+        if i % n_disc_update == 0:
+            optG.zero_grad()
+            outD = netD(outG, cs[i])
+            row[5] = outD.mean().item()
+            lossG = crit(outD, False, True)
+            lossG.backward()
+            optG.step()
+            row[2] = lossG.item()
+        trace.append(row)
+    fx = {"sd_g": sd_g0, "sd_d": sd_d0, "seed": seed, "steps": steps, "batch": batch, "z_dim": z_dim, "ch": ch,
+          "n_disc_update": n_disc_update, "trace": torch.tensor(trace), "x0_probe": xs[0, 0, 0, 0, :4].clone(),
+          "buf_g_after": buffers_of(netG), "buf_d_after": buffers_of(netD),
+          "g_l1_w_after": netG.state_dict()["l1.weight"][:4].clone(),
+          "d_l6_w_after": netD.state_dict()["l6.weight_orig"].clone()}
+    tr = O.CpuSnganTrainer(sd_g0, sd_d0, n_disc_update=n_disc_update, bottom_width=2)
+    ot = []
+    for i in range(steps):
+        r = tr.step(xs[i], ys[i], zs[i], cs[i])
+        ot.append([float("nan") if v is None else v for v in r])
+    d = (torch.tensor(ot) - fx["trace"])
+    print("[sngan loop ch%d] oracle trainer vs reference over %d steps: max |d| %.2e" % (ch, steps, d[~d.isnan()].abs().max()))
+    return fx
+
+
+def acgan_loop_data(seed, steps, batch, z_dim, n_class=10):
+    gen = torch.Generator().manual_seed(seed + 13)
+    xs = torch.rand(steps, batch, 3, 64, 64, generator=gen) * 2 - 1
+    ys = torch.randint(0, 2, (steps, batch, n_class), generator=gen).float()   # CelebA-style float attribute vectors
+    zs = torch.randn(steps, batch, z_dim, generator=gen)
+    return xs, ys, zs
+
+
+def acgan_loop_fixture(mods, width, batch, steps, seed, z_dim=16):
+    """`steps` iterations of main_acgan.py:84-133 (Adam lr 4e-4 / 1e-4, betas (0.5, 0.999): :59-60; vanilla GANLoss with
+    0.9 / 0.1 / 0.9 labels + 0.5 x MSELoss on the auxiliary head) on the unmodified reference."""
+    M = mods["acgan"]
+    torch.manual_seed(seed)
+    netG = M.Generator(z_dim=z_dim, ngf=width, n_class=10)
+    netD = M.Discriminator(ndf=width, n_class=10)
+    criterion_adv = mods["criterion"].GANLoss("vanilla", 0.9, 0.1, 0.9)
+    criterion_aux = torch.nn.MSELoss()
+    optG = torch.optim.Adam(netG.parameters(), lr=4e-4, betas=(0.5, 0.999))
+    optD = torch.optim.Adam(netD.parameters(), lr=1e-4, betas=(0.5, 0.999))
+    netG.train(), netD.train()
+    sd_g0, sd_d0 = clone_sd(netG), clone_sd(netD)
+    xs, ys, zs = acgan_loop_data(seed, steps, batch, z_dim)
+    trace = []
+    for i in range(steps):
+        img_real, lbl_real = xs[i], ys[i]
+        optD.zero_grad()
+        outD_adv, outD_cls = netD(img_real)
+        Dx = torch.sigmoid(outD_adv).mean().item()
+        lossD_real_adv = criterion_adv(outD_adv, True)
+        lossD_real_aux = criterion_aux(outD_cls, lbl_real)
+        (lossD_real_adv + lossD_real_aux * 0.5).backward()
+        c = lbl_real.float()
+        outG = netG(zs[i], c)
+        outD_adv, outD_cls = netD(outG.detach())
+        Dgz1 = torch.sigmoid(outD_adv).mean().item()
+        lossD_fake_adv = criterion_adv(outD_adv, False)
+        lossD_fake_aux = criterion_aux(outD_cls, c)
+        (lossD_fake_adv + lossD_fake_aux * 0.5).backward()
+        optD.step()
+        optG.zero_grad()
+        outD_adv, outD_cls = netD(outG)
+        Dgz2 = torch.sigmoid(outD_adv).mean().item()
+        lossG_adv = criterion_adv(outD_adv, False, True)
+        lossG_aux = criterion_aux(outD_cls, c)
+        (lossG_adv + lossG_aux * 0.5).backward()
+        optG.step()
+        trace.append([(lossD_real_adv + lossD_fake_adv).item(), (lossD_real_aux + lossD_fake_aux).item(),
+                      lossG_adv.item(), lossG_aux.item(), Dx, Dgz1, Dgz2])
+    fx = {"sd_g": sd_g0, "sd_d": sd_d0, "seed": seed, "steps": steps, "batch": batch, "z_dim": z_dim, "width": width,
+          "trace": torch.tensor(trace), "x0_probe": xs[0, 0, 0, 0, :4].clone(),
+          "buf_g_after": buffers_of(netG), "buf_d_after": buffers_of(netD),
+          "g_linear_w_after": netG.state_dict()["linear.weight"][:4].clone(),
+          "d_aux_w_after": netD.state_dict()["out_aux.weight"].clone()}
+    tr = O.CpuAcganTrainer(sd_g0, sd_d0)
+    ot = torch.tensor([tr.step(xs[i], ys[i], zs[i]) for i in range(steps)])
+    print("[acgan loop w%d] oracle trainer vs reference over %d steps: max |d| %.2e" % (width, steps, (ot - fx["trace"]).abs().max()))
+    return fx
+
+
 def ganloss_fixture(mods):
     G = mods["criterion"].GANLoss
     gen = torch.Generator().manual_seed(5)
@@ -351,6 +471,8 @@ def main():
         "sngan_proj_ch8.pt": lambda: sngan_fixture(mods, 8, 2, 4),
         "acgan_r64_w4.pt": lambda: acgan_fixture(mods, 4, 2, 5),
         "ganloss.pt": lambda: ganloss_fixture(mods),
+        "sngan_loop_ch8.pt": lambda: sngan_loop_fixture(mods, 8, 8, 12, 8),
+        "acgan_loop_r64_w4.pt": lambda: acgan_loop_fixture(mods, 4, 8, 12, 9),
     }
     only = [a for a in sys.argv[1:] if not a.startswith("-")]   # optional: fixture file names to (re)generate
     for name, fn in fixtures.items():

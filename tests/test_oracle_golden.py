@@ -105,6 +105,52 @@ def test_cpu_trainer_reproduces_reference_loss_trace():
     assert int(tr.bg["blocks.0.1.num_batches_tracked"]) == 40
 
 
+def test_cpu_sngan_trainer_reproduces_reference_loop():
+    """12 iterations of main_sngan.py:65-100 (n_disc_update=2: the G step runs on even iterations only and re-uses the
+    fake batch's graph) against the unmodified reference's trace. The first iterations agree to rounding; later ones
+    drift as Adam amplifies rounding-level gradient differences (bar: the north_star's 2 %)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from make_golden import sngan_loop_data
+
+    fx = load_golden("sngan_loop_ch8.pt")
+    xs, ys, zs, cs = sngan_loop_data(fx["seed"], fx["steps"], fx["batch"], fx["z_dim"])
+    assert torch.equal(xs[0, 0, 0, 0, :4], fx["x0_probe"])
+    tr = O.CpuSnganTrainer(fx["sd_g"], fx["sd_d"], n_disc_update=fx["n_disc_update"], bottom_width=2)
+    rows = [tr.step(xs[i], ys[i], zs[i], cs[i]) for i in range(fx["steps"])]
+    for i, row in enumerate(rows):
+        assert (row[2] is None) == (i % fx["n_disc_update"] != 0) == bool(torch.isnan(fx["trace"][i, 2]))
+    got = torch.tensor([[float("nan") if v is None else v for v in row] for row in rows])
+    ok = ~torch.isnan(fx["trace"])
+    assert torch.equal(ok, ~torch.isnan(got))
+    assert (got[:2] - fx["trace"][:2])[ok[:2]].abs().max() < 1e-4
+    assert ((got - fx["trace"])[ok].abs() <= 0.02 * fx["trace"][ok].abs() + 2e-3).all()
+    sd_g, sd_d = tr.state_dicts()
+    # bookkeeping: D ran 2 forwards per iteration + 1 per G step, G one forward per iteration
+    assert int(sd_g["b6.num_batches_tracked"]) == int(fx["buf_g_after"]["b6.num_batches_tracked"]) == fx["steps"]
+    assert torch.allclose(sd_d["l6.weight_u"], fx["buf_d_after"]["l6.weight_u"], atol=2e-3)
+    assert torch.allclose(sd_g["l1.weight"][:4], fx["g_l1_w_after"], atol=5e-4)
+
+
+def test_cpu_acgan_trainer_reproduces_reference_loop():
+    """12 iterations of main_acgan.py:84-133 (adversarial BCE + 0.5 x MSE on the auxiliary head, fake batch conditioned
+    on the real labels, one generator forward per iteration) against the unmodified reference's seven logged numbers."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from make_golden import acgan_loop_data
+
+    fx = load_golden("acgan_loop_r64_w4.pt")
+    xs, ys, zs = acgan_loop_data(fx["seed"], fx["steps"], fx["batch"], fx["z_dim"])
+    assert torch.equal(xs[0, 0, 0, 0, :4], fx["x0_probe"])
+    tr = O.CpuAcganTrainer(fx["sd_g"], fx["sd_d"])
+    got = torch.tensor([tr.step(xs[i], ys[i], zs[i]) for i in range(fx["steps"])])
+    assert got.shape == fx["trace"].shape == (fx["steps"], 7)
+    assert (got[:2] - fx["trace"][:2]).abs().max() < 1e-4
+    assert ((got - fx["trace"]).abs() <= 0.02 * fx["trace"].abs() + 2e-3).all()
+    sd_g, sd_d = tr.state_dicts()
+    assert int(sd_d["blocks.1.1.num_batches_tracked"]) == int(fx["buf_d_after"]["blocks.1.1.num_batches_tracked"]) == 3 * fx["steps"]
+    assert int(sd_g["blocks.0.1.num_batches_tracked"]) == int(fx["buf_g_after"]["blocks.0.1.num_batches_tracked"]) == fx["steps"]
+    assert torch.allclose(sd_d["out_aux.weight"], fx["d_aux_w_after"], atol=5e-4)
+
+
 @pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="live reference only exists in the build container")
 def test_oracle_matches_live_reference_full_width():
     import importlib.util
