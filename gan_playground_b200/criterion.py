@@ -26,14 +26,40 @@ class GANLoss(nn.Module):
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
         self._host_labels = (float(self.real_label), float(self.fake_label), float(self.fake_G_label))
 
-    def forward(self, prediction, is_real, is_generator=False):
-        if not prediction.is_cuda:
-            raise GpError("GANLoss: prediction is on %s — CUDA only, no CPU fallback" % prediction.device)
+    def _mode_target(self, is_real, is_generator):
         r, f, g = self._host_labels
         if self.gan_mode in ('vanilla', 'lsgan'):
             target = r if is_real else (g if is_generator else f)
-            mode = ops.LOSS_BCE if self.gan_mode == 'vanilla' else ops.LOSS_MSE
-        else:
-            target = 0.0
-            mode = ops.LOSS_HINGE_REAL if is_real else (ops.LOSS_NEG_MEAN if is_generator else ops.LOSS_HINGE_FAKE)
+            return (ops.LOSS_BCE if self.gan_mode == 'vanilla' else ops.LOSS_MSE), target
+        return (ops.LOSS_HINGE_REAL if is_real else (ops.LOSS_NEG_MEAN if is_generator else ops.LOSS_HINGE_FAKE)), 0.0
+
+    def forward(self, prediction, is_real, is_generator=False):
+        if not prediction.is_cuda:
+            raise GpError("GANLoss: prediction is on %s — CUDA only, no CPU fallback" % prediction.device)
+        mode, target = self._mode_target(is_real, is_generator)
         return GF.GanLossFn.apply(prediction, mode, target)
+
+
+class ACGANLoss(nn.Module):
+    """The objective of the reference's main_acgan.py as one fused kernel (gp_acgan_loss):
+    `criterion_adv(outD_adv, is_real, is_generator) + aux_weight * nn.MSELoss()(outD_cls, labels)` (:95-97,114-116,
+    129-131) evaluated on the packed two-head logits of `acgan.Discriminator.packed_logits`.
+
+    forward(...) returns a 4-vector [adversarial term, auxiliary term, adv + aux_weight * aux, mean sigmoid(adv)] —
+    element 2 is what the script back-propagates, elements 0 / 1 / 3 are the numbers it logs. The script itself keeps
+    working unchanged with `GANLoss` + `torch.nn.MSELoss` on `Discriminator.forward`'s pair; this class is the fused
+    route `engine.AcganStep` takes."""
+
+    ADV, AUX, TOTAL, SIGMOID_MEAN = 0, 1, 2, 3
+
+    def __init__(self, criterion_adv, aux_weight=0.5):
+        super().__init__()
+        if not isinstance(criterion_adv, GANLoss):
+            raise TypeError("ACGANLoss wraps a GANLoss, got %s" % type(criterion_adv).__name__)
+        self.criterion_adv, self.aux_weight = criterion_adv, float(aux_weight)
+
+    def forward(self, packed_logits, labels, is_real, is_generator=False):
+        if not packed_logits.is_cuda:
+            raise GpError("ACGANLoss: logits are on %s — CUDA only, no CPU fallback" % packed_logits.device)
+        mode, target = self.criterion_adv._mode_target(is_real, is_generator)
+        return GF.AcganLossFn.apply(packed_logits, labels, mode, target, self.aux_weight)

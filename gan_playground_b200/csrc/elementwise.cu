@@ -601,39 +601,86 @@ __global__ void head_bias_grad_kernel(const float* __restrict__ dout, float* __r
 // ------------------------------------------------------------------------------------------------ losses
 // GANLoss (utils/criterion.py:30-41), value and d(loss)/d(pred) in one pass; single block.
 // mode 0: BCE-with-logits vs constant target; 1: MSE vs constant target; 2: hinge real relu(1-p); 3: hinge fake relu(1+p); 4: -p
+__device__ __forceinline__ void gan_loss_term(int mode, float x, float target, float& l, float& d) {
+  if (mode == 0) {
+    l = fmaxf(x, 0.f) - x * target + log1pf(expf(-fabsf(x)));
+    d = 1.f / (1.f + expf(-x)) - target;
+  } else if (mode == 1) {
+    l = (x - target) * (x - target);
+    d = 2.f * (x - target);
+  } else if (mode == 2) {
+    l = fmaxf(1.f - x, 0.f);
+    d = (1.f - x) > 0.f ? -1.f : 0.f;
+  } else if (mode == 3) {
+    l = fmaxf(1.f + x, 0.f);
+    d = (1.f + x) > 0.f ? 1.f : 0.f;
+  } else {
+    l = -x;
+    d = -1.f;
+  }
+}
+
+// sum over the (single) block; the result is valid in thread 0. `red` is 32 floats of shared memory.
+__device__ __forceinline__ float block_sum(float acc, float* red) {
+  for (int k = 16; k > 0; k >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, k);
+  __syncthreads();                       // `red` may still be read by a previous call
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  acc = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+  if (threadIdx.x < 32)
+    for (int k = 16; k > 0; k >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, k);
+  return acc;
+}
+
 __global__ void gan_loss_kernel(const float* __restrict__ pred, int n, int mode, float target, float inv_n,
                                 float* __restrict__ loss, float* __restrict__ dpred) {
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float x = pred[i];
     float l, d;
-    if (mode == 0) {
-      l = fmaxf(x, 0.f) - x * target + log1pf(expf(-fabsf(x)));
-      d = 1.f / (1.f + expf(-x)) - target;
-    } else if (mode == 1) {
-      l = (x - target) * (x - target);
-      d = 2.f * (x - target);
-    } else if (mode == 2) {
-      l = fmaxf(1.f - x, 0.f);
-      d = (1.f - x) > 0.f ? -1.f : 0.f;
-    } else if (mode == 3) {
-      l = fmaxf(1.f + x, 0.f);
-      d = (1.f + x) > 0.f ? 1.f : 0.f;
-    } else {
-      l = -x;
-      d = -1.f;
-    }
+    gan_loss_term(mode, pred[i], target, l, d);
     acc += l;
     dpred[i] = d * inv_n;
   }
   __shared__ float red[32];
-  for (int k = 16; k > 0; k >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, k);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    acc = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-    for (int k = 16; k > 0; k >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, k);
-    if (threadIdx.x == 0) *loss = acc * inv_n;
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) *loss = acc * inv_n;
+}
+
+// ACGAN objective (main_acgan.py:95-97,114-116,129-131) on the packed two-head logits [NB][1 + K] (column 0 = the
+// adversarial logit, columns 1..K = the auxiliary head): GANLoss term on column 0 + aux_weight * MSELoss(mean over NB*K)
+// against the float label vectors, plus mean(sigmoid(adv)) — the D(x) / D(G(z)) number the script prints (:94,112,127).
+// out[0] = adversarial term, out[1] = auxiliary term (unweighted), out[2] = adv + aux_weight * aux, out[3] = sigmoid mean;
+// dlogits = d out[2] / d logits in the packed layout. Single block.
+__global__ void acgan_loss_kernel(const float* __restrict__ logits, const float* __restrict__ labels, int NB, int K,
+                                  int mode, float target, float aux_weight, float* __restrict__ out,
+                                  float* __restrict__ dlogits) {
+  const int ld = K + 1;
+  const float inv_nb = 1.f / (float)NB, inv_aux = 1.f / ((float)NB * (float)K);
+  float s_adv = 0.f, s_aux = 0.f, s_sig = 0.f;
+  for (int i = threadIdx.x; i < NB * ld; i += blockDim.x) {
+    const int b = i / ld, j = i - b * ld;
+    const float x = logits[i];
+    if (j == 0) {
+      float l, d;
+      gan_loss_term(mode, x, target, l, d);
+      s_adv += l;
+      s_sig += 1.f / (1.f + expf(-x));
+      dlogits[i] = d * inv_nb;
+    } else {
+      const float e = x - labels[b * K + (j - 1)];
+      s_aux += e * e;
+      dlogits[i] = 2.f * e * inv_aux * aux_weight;
+    }
+  }
+  __shared__ float red[32];
+  s_adv = block_sum(s_adv, red);
+  s_aux = block_sum(s_aux, red);
+  s_sig = block_sum(s_sig, red);
+  if (threadIdx.x == 0) {
+    out[0] = s_adv * inv_nb;
+    out[1] = s_aux * inv_aux;
+    out[2] = s_adv * inv_nb + aux_weight * (s_aux * inv_aux);
+    out[3] = s_sig * inv_nb;
   }
 }
 
@@ -930,6 +977,16 @@ int gp_head_bwd(const float* dout, const void* a, const float* w, void* da, floa
 int gp_gan_loss(const float* pred, int n, int mode, float target, float* loss, float* dpred, void* stream) {
   GP_REQUIRE(pred && loss && dpred && n > 0 && mode >= 0 && mode <= 4, "gp_gan_loss: bad arguments");
   gan_loss_kernel<<<1, 256, 0, as_stream(stream)>>>(pred, n, mode, target, 1.f / (float)n, loss, dpred);
+  GP_CHECK_LAUNCH();
+  return GP_OK;
+}
+
+int gp_acgan_loss(const float* logits, const float* labels, int NB, int K, int mode, float target, float aux_weight,
+                  float* out4, float* dlogits, void* stream) {
+  GP_REQUIRE(logits && labels && out4 && dlogits && NB > 0 && K > 0 && mode >= 0 && mode <= 4 &&
+                 (long long)NB * (K + 1) < (1ll << 30),
+             "gp_acgan_loss: bad arguments");
+  acgan_loss_kernel<<<1, 256, 0, as_stream(stream)>>>(logits, labels, NB, K, mode, target, aux_weight, out4, dlogits);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }

@@ -1,19 +1,25 @@
-"""Step driver for the adversarial loop of the reference's main_dcgan.py:68-95.
+"""Step drivers for the adversarial loops of the reference's training scripts:
 
-`DcganStep` runs exactly that loop body (D-real backward, D-fake backward on G(z).detach(), optD.step, G step through D,
-optG.step) either eagerly — one launch per kernel, three host reads per step like the reference's `.item()` calls — or
-as ONE CUDA graph replay per step: the whole step (forward, autograd backward, NCCL all-reduces, Adam) is captured on a
-side stream after a warm-up, the six logged scalars (losses, D(x), D(G(z))) are written to a device buffer inside the
-graph and read back once per step. Graph replay removes the per-launch host overhead (~250 launches per step), which
-is what bounds small per-GPU batches (strong scaling at 128 images/GPU).
+* `DcganStep` — main_dcgan.py:68-95 (two generator forwards per iteration),
+* `SnganStep` — main_sngan.py:65-100 (class-conditional, ONE generator forward whose graph the G step re-uses, G step
+  only every `n_disc_update` iterations),
+* `AcganStep` — main_acgan.py:84-133 (two-head discriminator, adversarial + 0.5 x MSE auxiliary objective).
+
+Each runs exactly the script's loop body (D-real backward, D-fake backward on G(z).detach(), optD.step, G step through
+D, optG.step) either eagerly — one launch per kernel, host reads of the logged scalars like the reference's `.item()`
+calls — or as ONE CUDA graph replay per step: the whole step (forward, autograd backward, NCCL collectives, Adam) is
+captured on a side stream after a warm-up, the logged scalars are written to a device buffer inside the graph and read
+back once per step. Graph replay removes the per-launch host overhead (~250 launches per step), which is what bounds
+small per-GPU batches (strong scaling at 128 images/GPU).
 
 Requirements for graph mode: torch optimisers built with `capturable=True` (FusedAdam is capturable as is); fixed batch
 size. The weight-staging caches of the networks are cleared before capture so the staging kernels are part of the graph,
-and the warm-up steps capture needs are undone afterwards (parameters, BatchNorm buffers and optimiser state are restored
-in place), so the first replay is the first training step."""
+and the warm-up steps capture needs are undone afterwards (parameters, BatchNorm / spectral-norm buffers and optimiser
+state are restored in place), so the first replay is the first training step."""
 import torch
 
 from . import config, ops, parallel
+from .criterion import ACGANLoss
 from .optim import FusedAdam
 
 
@@ -25,79 +31,51 @@ def _clear_caches(*nets):
                 c.clear()
 
 
-class DcganStep:
-    def __init__(self, netG, netD, criterion, optG, optD, batch, z_dim, device, use_graph=False, warmup=3, overlap=True,
-                 mixed_precision=True):
-        self.netG, self.netD, self.crit, self.optG, self.optD = netG, netD, criterion, optG, optD
-        self.batch, self.z_dim, self.dev = batch, z_dim, device
+class _AdversarialStep:
+    """Shared machinery: gradient buckets / flat optimisers, the zero arena, eager stepping, graph capture + replay.
+    A subclass supplies
+      N_SCALARS                    how many numbers its script logs per iteration,
+      _data_static / _noise_static lists of device tensors a replay reads its inputs from,
+      _draw_noise()                fresh on-device noise when the caller supplies none,
+      _loop(data, noise, log, i)   the script's loop body; `log(j, t)` receives logged scalar j as a 0-dim device tensor,
+      _graph_key(i)                which captured variant iteration i replays (scripts whose body depends on `i`)."""
+
+    N_SCALARS = 6
+
+    def __init__(self, netG, netD, optG, optD, batch, device, use_graph=False, warmup=3, overlap=True):
+        self.netG, self.netD, self.optG, self.optD = netG, netD, optG, optD
+        self.batch, self.dev = batch, device
         # FusedAdam owns flat parameter / gradient buffers and does the gradient collective itself; any other optimiser
         # (torch.optim.Adam as in the reference scripts) gets a flat gradient bucket per network for the all-reduce
         self.bucketD = None if isinstance(optD, FusedAdam) else parallel.GradBucket(netD)
         self.bucketG = None if isinstance(optG, FusedAdam) else parallel.GradBucket(netG)
         self.use_graph = use_graph
-        self.graph = None
-        self.x_static = torch.zeros(batch, netD.img_dim, netD.resolution, netD.resolution, device=device)
-        self.z_static = torch.zeros(2, batch, z_dim, device=device)
-        self.scalars = torch.zeros(6, device=device)   # lossD_real, lossD_fake, lossG, D(x), D(G(z))1, D(G(z))2
-        self.fixed_z = False
+        self.graphs = {}
+        self.scalars = torch.zeros(self.N_SCALARS, device=device)
+        self.fixed_noise = False
+        self.iteration = 0
         self._warmup = warmup
         self.overlap = overlap
         self.arena = ops.ZeroArena(device)
         self._d_params = [p for p in netD.parameters() if p.requires_grad]
-        # mixed forward precision: the real-image D pass needs no 3-MMA forward (config.precision_scope)
-        self.real_precision = "bf16" if (mixed_precision and config.x3()) else None
         self._side = torch.cuda.Stream(device=device) if device.type == "cuda" else None
 
-    # ---- the loop body; `log(i, t)` receives the six scalars as 0-dim device tensors
-    def _body(self, inputs, z1, z2, log):
-        netG, netD, crit = self.netG, self.netD, self.crit
-        self.arena.begin()                                       # one memset for every zero-initialised workspace
+    # kept for callers that look at the single-variant graph (DcganStep / AcganStep)
+    @property
+    def graph(self):
+        return next(iter(self.graphs.values()), None)
+
+    def _graph_key(self, i):
+        return 0
+
+    # ---- one loop body inside the zero arena (one memset for every zero-initialised workspace of the step)
+    def _body(self, data, noise, log, i):
+        self.arena.begin()
         ops.ZeroArena.active = self.arena
         try:
-            self._body_steps(netG, netD, crit, inputs, z1, z2, log)
+            self._loop(data, noise, log, i)
         finally:
             ops.ZeroArena.active = None
-
-    def _body_steps(self, netG, netD, crit, inputs, z1, z2, log):
-        self._zero(self.optD, self.bucketD)                      # optD.zero_grad()
-        with config.precision_scope(self.real_precision or config.precision()):
-            outD = netD(inputs)
-        log(3, outD.mean())
-        lossD_real = crit(outD, True)
-        lossD_real.backward()
-        outG = netG(z1)
-        outD = netD(outG.detach())
-        log(4, outD.mean())
-        lossD_fake = crit(outD, False)
-        lossD_fake.backward()
-        if parallel.enabled() and self.overlap:
-            # D's gradient exchange + update run on a side stream while the generator forward of the G step (which does
-            # not read D) runs on the main one; D's forward below waits for the join
-            cur = torch.cuda.current_stream()
-            self._side.wait_stream(cur)
-            with torch.cuda.stream(self._side):
-                self._step(self.optD, self.bucketD)
-            self._zero(self.optG, self.bucketG)
-            outG = netG(z2)
-            cur.wait_stream(self._side)
-        else:
-            self._step(self.optD, self.bucketD)                  # (gradient all-reduce +) optD.step()
-            self._zero(self.optG, self.bucketG)                  # optG.zero_grad()
-            outG = netG(z2)
-        # G step: D only relays the gradient to G. The reference also computes D's weight gradients here and throws
-        # them away at the next optD.zero_grad() (main_dcgan.py:68,87-94; SURVEY.md §8d "minimal step"): skip them
-        for p in self._d_params:
-            p.requires_grad_(False)
-        try:
-            outD = netD(outG)
-            log(5, outD.mean())
-            lossG = crit(outD, False, True)
-            lossG.backward()
-        finally:
-            for p in self._d_params:
-                p.requires_grad_(True)
-        self._step(self.optG, self.bucketG)                      # (gradient all-reduce +) optG.step()
-        log(0, lossD_real.detach()), log(1, lossD_fake.detach()), log(2, lossG.detach())
 
     @staticmethod
     def _zero(opt, bucket):
@@ -112,18 +90,47 @@ class DcganStep:
             bucket.all_reduce_mean()
         opt.step()
 
-    def _noise(self):
-        return torch.randn(self.batch, self.z_dim, device=self.dev), torch.randn(self.batch, self.z_dim, device=self.dev)
+    def _d_step_then(self, g_work):
+        """optD.step() (with its gradient exchange), then `g_work()` — generator-side work that does not read D. Under
+        data parallelism D's exchange + update run on a side stream while `g_work` runs on the main one; whatever reads D
+        next waits for the join."""
+        if parallel.enabled() and self.overlap:
+            cur = torch.cuda.current_stream()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                self._step(self.optD, self.bucketD)
+            out = g_work()
+            cur.wait_stream(self._side)
+            return out
+        self._step(self.optD, self.bucketD)
+        return g_work()
 
-    def step_eager(self, inputs, z=None):
-        """Reference-faithful: every logged scalar is read on the host as soon as it exists (`.item()`)."""
-        vals = [0.0] * 6
+    class _frozen_d:
+        """G step: D only relays the gradient to G. The reference also computes D's weight gradients there and throws
+        them away at the next optD.zero_grad() (main_dcgan.py:68,87-94; SURVEY.md §8d "minimal step"): skip them."""
 
-        def log(i, t):
-            vals[i] = t.item()
+        def __init__(self, params):
+            self.params = params
 
-        z1, z2 = (z[0], z[1]) if z is not None else self._noise()
-        self._body(inputs, z1, z2, log)
+        def __enter__(self):
+            for p in self.params:
+                p.requires_grad_(False)
+
+        def __exit__(self, *exc):
+            for p in self.params:
+                p.requires_grad_(True)
+
+    # ---- eager: every logged scalar is read on the host as soon as it exists, like the reference's `.item()` calls
+    def _run_eager(self, data, noise):
+        vals = [float("nan")] * self.N_SCALARS
+
+        def log(j, t):
+            vals[j] = t.item()
+
+        if noise is None:
+            noise = self._draw_noise()
+        self._body(data, noise, log, self.iteration)
+        self.iteration += 1
         return vals
 
     # ---- capture must not train: the warm-up steps run real optimiser steps, so everything they touch is restored
@@ -162,22 +169,19 @@ class DcganStep:
                             else:
                                 v.zero_()            # state created by the warm-up: back to torch.optim.Adam's initial zeros
 
-    def _capture(self):
+    def _capture(self, key, i):
         snap = self._snapshot()
         _clear_caches(self.netG, self.netD)
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream())
         scal = self.scalars
 
-        def log(i, t):
-            scal[i].copy_(t)
+        def log(j, t):
+            scal[j].copy_(t)
 
         def body():
-            if self.fixed_z:
-                z1, z2 = self.z_static[0], self.z_static[1]
-            else:
-                z1, z2 = self._noise()
-            self._body(self.x_static, z1, z2, log)
+            noise = self._noise_static if self.fixed_noise else self._draw_noise()
+            self._body(self._data_static, noise, log, i)
 
         with torch.cuda.stream(s):
             for _ in range(self._warmup):
@@ -188,22 +192,206 @@ class DcganStep:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             body()
-        self.graph = g
+        self.graphs[key] = g
         self._restore(snap)
         torch.cuda.synchronize()
 
-    def step(self, inputs, z=None):
-        """One training step. Returns [lossD_real, lossD_fake, lossG, D(x), D(G(z))_1, D(G(z))_2] as Python floats."""
+    def _run(self, data, noise):
+        """One training step. Returns the script's logged scalars as Python floats (NaN for a number the script does
+        not produce on this iteration)."""
         if not self.use_graph:
-            return self.step_eager(inputs, z)
-        if self.graph is None:
-            self.fixed_z = z is not None
-            self._capture()
-        if inputs.data_ptr() != self.x_static.data_ptr():
-            self.x_static.copy_(inputs, non_blocking=True)
-        if z is not None:
-            self.z_static.copy_(z, non_blocking=True)
-        self.graph.replay()
+            return self._run_eager(data, noise)
+        i = self.iteration
+        key = self._graph_key(i)
+        if not self.graphs:
+            self.fixed_noise = noise is not None
+        elif self.fixed_noise != (noise is not None):
+            raise ValueError("graph mode: either every step supplies its noise or none does (captured with %s)"
+                             % ("caller-supplied noise" if self.fixed_noise else "on-device noise"))
+        if key not in self.graphs:
+            self._capture(key, i)
+        for st, t in zip(self._data_static, data):
+            if t.data_ptr() != st.data_ptr():
+                st.copy_(t, non_blocking=True)
+        if noise is not None:
+            for st, t in zip(self._noise_static, noise):
+                st.copy_(t, non_blocking=True)
+        if len(self.graphs) > 1:
+            self.scalars.fill_(float("nan"))     # a variant that skips the G step leaves those entries untouched
+        self.graphs[key].replay()
+        self.iteration += 1
         # the replay updated the weights behind Python's back: operand copies cached by earlier eager calls are stale
         _clear_caches(self.netG, self.netD)
         return self.scalars.tolist()      # one device->host read per step
+
+
+class DcganStep(_AdversarialStep):
+    """main_dcgan.py:68-95. Logged scalars: [lossD_real, lossD_fake, lossG, D(x), D(G(z))_1, D(G(z))_2]."""
+
+    def __init__(self, netG, netD, criterion, optG, optD, batch, z_dim, device, use_graph=False, warmup=3, overlap=True,
+                 mixed_precision=True):
+        super().__init__(netG, netD, optG, optD, batch, device, use_graph, warmup, overlap)
+        self.crit, self.z_dim = criterion, z_dim
+        self.x_static = torch.zeros(batch, netD.img_dim, netD.resolution, netD.resolution, device=device)
+        self.z_static = torch.zeros(2, batch, z_dim, device=device)
+        self._data_static = [self.x_static]
+        self._noise_static = [self.z_static[0], self.z_static[1]]
+        # mixed forward precision: the real-image D pass needs no 3-MMA forward (config.precision_scope)
+        self.real_precision = "bf16" if (mixed_precision and config.x3()) else None
+
+    def _draw_noise(self):
+        return torch.randn(self.batch, self.z_dim, device=self.dev), torch.randn(self.batch, self.z_dim, device=self.dev)
+
+    def _loop(self, data, noise, log, i):
+        netG, netD, crit = self.netG, self.netD, self.crit
+        (inputs,), (z1, z2) = data, noise
+        self._zero(self.optD, self.bucketD)                      # optD.zero_grad()
+        with config.precision_scope(self.real_precision or config.precision()):
+            outD = netD(inputs)
+        log(3, outD.mean())
+        lossD_real = crit(outD, True)
+        lossD_real.backward()
+        outG = netG(z1)
+        outD = netD(outG.detach())
+        log(4, outD.mean())
+        lossD_fake = crit(outD, False)
+        lossD_fake.backward()
+
+        def g_forward():
+            self._zero(self.optG, self.bucketG)                  # optG.zero_grad()
+            return netG(z2)
+
+        outG = self._d_step_then(g_forward)                      # (gradient all-reduce +) optD.step()
+        with self._frozen_d(self._d_params):
+            outD = netD(outG)
+            log(5, outD.mean())
+            lossG = crit(outD, False, True)
+            lossG.backward()
+        self._step(self.optG, self.bucketG)                      # (gradient all-reduce +) optG.step()
+        log(0, lossD_real.detach()), log(1, lossD_fake.detach()), log(2, lossG.detach())
+
+    def step_eager(self, inputs, z=None):
+        """Reference-faithful: every logged scalar is read on the host as soon as it exists (`.item()`)."""
+        return self._run_eager([inputs], None if z is None else (z[0], z[1]))
+
+    def step(self, inputs, z=None):
+        """One training step. Returns [lossD_real, lossD_fake, lossG, D(x), D(G(z))_1, D(G(z))_2] as Python floats."""
+        return self._run([inputs], None if z is None else (z[0], z[1]))
+
+
+class SnganStep(_AdversarialStep):
+    """main_sngan.py:65-100: class-conditional hinge GAN. The generator runs ONCE per iteration — the G step (:92-99)
+    sends the batch the discriminator was just trained on through the updated D again and back-propagates into the
+    generator graph of :82 — and only when `i % n_disc_update == 0` (`--n_disc_update`, default 5, :24).
+    Logged scalars: [lossD_real, lossD_fake, lossG, D(x), D(G(z))_1, D(G(z))_2]; entries 2 and 5 are NaN on iterations
+    without a G step (the script keeps printing its stale values there).
+    Graph mode captures two variants (with / without the G step) and replays the one iteration `i` needs."""
+
+    def __init__(self, netG, netD, criterion, optG, optD, batch, z_dim, device, n_classes=10, n_disc_update=5,
+                 resolution=32, use_graph=False, warmup=3, overlap=True):
+        super().__init__(netG, netD, optG, optD, batch, device, use_graph, warmup, overlap)
+        if n_disc_update < 1:
+            raise ValueError("n_disc_update must be >= 1")
+        self.crit, self.z_dim, self.n_classes, self.n_disc_update = criterion, z_dim, n_classes, int(n_disc_update)
+        img_dim = netD.block1.c1.in_channels
+        self.x_static = torch.zeros(batch, img_dim, resolution, resolution, device=device)
+        self.y_static = torch.zeros(batch, dtype=torch.long, device=device)
+        self.z_static = torch.zeros(batch, z_dim, device=device)
+        self.c_static = torch.zeros(batch, dtype=torch.long, device=device)
+        self._data_static = [self.x_static, self.y_static]
+        self._noise_static = [self.z_static, self.c_static]
+
+    def _graph_key(self, i):
+        return int(i % self.n_disc_update == 0)
+
+    def _draw_noise(self):
+        return (torch.randn(self.batch, self.z_dim, device=self.dev),
+                torch.randint(self.n_classes, (self.batch,), device=self.dev))
+
+    def _loop(self, data, noise, log, i):
+        netG, netD, crit = self.netG, self.netD, self.crit
+        (img_real, lbl_real), (z, c) = data, noise
+        g_step = i % self.n_disc_update == 0
+        self._zero(self.optD, self.bucketD)
+        outD = netD(img_real, lbl_real)
+        log(3, outD.mean())
+        lossD_real = crit(outD, True)
+        lossD_real.backward()
+        outG = netG(z, c)
+        outD = netD(outG.detach(), c)
+        log(4, outD.mean())
+        lossD_fake = crit(outD, False)
+        lossD_fake.backward()
+        self._step(self.optD, self.bucketD)      # the G step reads the updated D right away: nothing to overlap with
+        log(0, lossD_real.detach()), log(1, lossD_fake.detach())
+        if g_step:
+            self._zero(self.optG, self.bucketG)
+            with self._frozen_d(self._d_params):
+                outD = netD(outG, c)
+                log(5, outD.mean())
+                lossG = crit(outD, False, True)
+                lossG.backward()
+            self._step(self.optG, self.bucketG)
+            log(2, lossG.detach())
+
+    def step_eager(self, img_real, lbl_real, z=None, c=None):
+        return self._run_eager([img_real, lbl_real], None if z is None else (z, c))
+
+    def step(self, img_real, lbl_real, z=None, c=None):
+        """One iteration. Returns [lossD_real, lossD_fake, lossG, D(x), D(G(z))_1, D(G(z))_2] (NaN where not produced)."""
+        return self._run([img_real, lbl_real], None if z is None else (z, c))
+
+
+class AcganStep(_AdversarialStep):
+    """main_acgan.py:84-133: two-head discriminator, objective `criterion_adv + 0.5 * MSELoss(aux head, labels)` on the
+    real batch, on G(z, labels).detach() and — for the generator — on the same fake batch again (one generator forward
+    per iteration, :107,123). Both heads come from one pass over the features and each of the three objectives is one
+    fused value+gradient kernel (criterion.ACGANLoss on acgan.Discriminator.packed_logits).
+    Logged scalars, in the order of the script's progress line (:136-137):
+    [lossD_adv, lossD_aux, lossG_adv, lossG_aux, D(x), D(G(z))_1, D(G(z))_2] (the D(.) numbers are sigmoid means)."""
+
+    N_SCALARS = 7
+
+    def __init__(self, netG, netD, criterion_adv, optG, optD, batch, z_dim, device, n_class=10, aux_weight=0.5,
+                 use_graph=False, warmup=3, overlap=True):
+        super().__init__(netG, netD, optG, optD, batch, device, use_graph, warmup, overlap)
+        self.crit = criterion_adv if isinstance(criterion_adv, ACGANLoss) else ACGANLoss(criterion_adv, aux_weight)
+        self.z_dim, self.n_class = z_dim, n_class
+        self.x_static = torch.zeros(batch, netD.img_dim, netD.resolution, netD.resolution, device=device)
+        self.y_static = torch.zeros(batch, n_class, device=device)
+        self.z_static = torch.zeros(batch, z_dim, device=device)
+        self._data_static = [self.x_static, self.y_static]
+        self._noise_static = [self.z_static]
+
+    def _draw_noise(self):
+        return (torch.randn(self.batch, self.z_dim, device=self.dev),)
+
+    def _loop(self, data, noise, log, i):
+        netG, netD, crit = self.netG, self.netD, self.crit
+        (img_real, lbl_real), (z,) = data, noise
+        self._zero(self.optD, self.bucketD)
+        real = crit(netD.packed_logits(img_real), lbl_real, True)
+        real[crit.TOTAL].backward()
+        log(4, real[crit.SIGMOID_MEAN].detach())
+        c = lbl_real
+        outG = netG(z, c)
+        fake = crit(netD.packed_logits(outG.detach()), c, False)
+        fake[crit.TOTAL].backward()
+        log(5, fake[crit.SIGMOID_MEAN].detach())
+        self._step(self.optD, self.bucketD)
+        d_terms = (real + fake).detach()         # lossD_adv = real_adv + fake_adv, lossD_aux likewise (:119-120)
+        log(0, d_terms[crit.ADV]), log(1, d_terms[crit.AUX])
+        self._zero(self.optG, self.bucketG)
+        with self._frozen_d(self._d_params):
+            gen = crit(netD.packed_logits(outG), c, False, True)
+            gen[crit.TOTAL].backward()
+        self._step(self.optG, self.bucketG)
+        gen = gen.detach()
+        log(2, gen[crit.ADV]), log(3, gen[crit.AUX]), log(6, gen[crit.SIGMOID_MEAN])
+
+    def step_eager(self, img_real, lbl_real, z=None):
+        return self._run_eager([img_real, lbl_real], None if z is None else (z,))
+
+    def step(self, img_real, lbl_real, z=None):
+        """One iteration. Returns [lossD_adv, lossD_aux, lossG_adv, lossG_aux, D(x), D(G(z))_1, D(G(z))_2]."""
+        return self._run([img_real, lbl_real], None if z is None else (z,))

@@ -23,7 +23,10 @@ class WeightCache:
         self._d = {}
 
     def get(self, key, param, make):
-        if not param.is_leaf:  # derived weight (e.g. W / sigma of spectral norm): new tensor every forward
+        # only real parameters are cached. A derived weight (W / sigma of spectral norm) is a new tensor every forward;
+        # under no_grad / frozen parameters it is even a *leaf* with version 0 whose address the allocator may hand out
+        # again next forward, so neither is_leaf nor (version, data_ptr) can tell two of them apart
+        if not isinstance(param, torch.nn.Parameter) or not param.is_leaf:
             return make()
         # _version: bumped by torch in-place updates (torch.optim.Adam); _gp_epoch: bumped by optim.FusedAdam, whose
         # kernel updates the storage behind autograd's back
@@ -370,6 +373,55 @@ class Head(torch.autograd.Function):
         da, dw, db = ops.head_bwd(dout.contiguous(), a, weight.detach(), ctx.O, *ctx.strides,
                                   need_da=ctx.needs_input_grad[0], need_dw=ctx.needs_input_grad[2], need_db=ctx.has_bias)
         return da, None, dw, (db if ctx.has_bias else None), None
+
+
+class PackedHeads(torch.autograd.Function):
+    """Both heads of the ACGAN discriminator (out_layer, out_aux: models/acgan.py:122-126) in ONE pass over the
+    features: the two Linear weights are stacked into one (O1 + O2, C) head operand, the result is the packed logits
+    (NB, O1 + O2), and one backward pass produces the feature gradient and both weight / bias gradients."""
+
+    @staticmethod
+    def forward(ctx, a, a_lo, w1, b1, w2, b2, flatten):
+        NB, H, W, C = a.shape
+        O1, O2 = w1.shape[0], w2.shape[0]
+        w = torch.cat([w1.detach(), w2.detach()], 0)    # (O1 + O2, C) fp32, a few tens of KB
+        b = torch.cat([b1.detach(), b2.detach()], 0)
+        strides = (C * H * W, H * W, 1) if flatten else (C, 1, 0)
+        if a_lo is not None:
+            out = ops.head_fwd_split(a, a_lo, w, b, O1 + O2, *strides)
+        else:
+            out = ops.head_fwd(a, w, b, O1 + O2, *strides)
+        ctx.save_for_backward(a, w)
+        ctx.strides, ctx.O1, ctx.O2 = strides, O1, O2
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        a, w = ctx.saved_tensors
+        O1, O2 = ctx.O1, ctx.O2
+        need_w = any(ctx.needs_input_grad[2:6])
+        da, dw, db = ops.head_bwd(dout.contiguous(), a, w, O1 + O2, *ctx.strides,
+                                  need_da=ctx.needs_input_grad[0], need_dw=need_w, need_db=need_w)
+        if not need_w:
+            return da, None, None, None, None, None, None
+        return da, None, dw[:O1], db[:O1], dw[O1:], db[O1:], None
+
+
+class AcganLossFn(torch.autograd.Function):
+    """main_acgan.py:95-97,114-116,129-131 on the packed logits: returns the 4-vector [adversarial term, auxiliary MSE
+    term, adv + aux_weight * aux, mean sigmoid(adv)]; only element 2 (the quantity the script calls .backward() on)
+    carries a gradient, produced by the same kernel."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, mode, target, aux_weight):
+        out4, dlogits = ops.acgan_loss(logits.detach().contiguous(), labels.contiguous(), mode, target, aux_weight)
+        ctx.save_for_backward(dlogits)
+        return out4
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * g[2], None, None, None, None
 
 
 class GanLossFn(torch.autograd.Function):

@@ -1,6 +1,7 @@
 """ACGAN generator / discriminator: API mirror of the reference's models/acgan.py on B200 kernels.
 Differences from dcgan: the generator's Linear consumes cat[z, y] and has NO ReLU (reference: models/acgan.py:32,49-50);
-the discriminator has a second Linear head `out_aux` and returns (out, out_aux) (:112-126)."""
+the discriminator has a second Linear head `out_aux` and returns (out, out_aux) (:112-126) — here both heads are one
+pass over the features (functional.PackedHeads)."""
 import torch
 import torch.nn as nn
 
@@ -61,9 +62,16 @@ class Discriminator(_dcgan.Discriminator):
         if not skip_init:
             self.init_weights()
 
-    def forward(self, x):
+    def packed_logits(self, x):
+        """(B, output_dim + n_class) fp32: column block 0 = out_layer, block 1 = out_aux — both heads from one pass over
+        the features (functional.PackedHeads). `forward` returns its two column blocks; the fused ACGAN objective
+        (criterion.ACGANLoss) consumes it whole."""
         require_cuda(x, "acgan.Discriminator")
         h = self._features(x)
-        out = GF.with_lo(GF.Head, h, self.out_layer.weight, self.out_layer.bias, False)
-        out_aux = GF.with_lo(GF.Head, h, self.out_aux.weight, self.out_aux.bias, False)
-        return out, out_aux
+        return GF.with_lo(GF.PackedHeads, h, self.out_layer.weight, self.out_layer.bias, self.out_aux.weight,
+                          self.out_aux.bias, False)
+
+    def forward(self, x):
+        p = self.packed_logits(x)
+        od = self.out_layer.out_features
+        return p[:, :od], p[:, od:]

@@ -34,6 +34,7 @@ _SIGS = {
     "gp_head_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _vp],
     "gp_head_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _vp],
     "gp_gan_loss": [_vp, _i, _i, _f, _vp, _vp, _vp],
+    "gp_acgan_loss": [_vp, _vp, _i, _i, _i, _f, _f, _vp, _vp, _vp],
     "gp_sn_sigma": [_vp, _i, _i, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _vp],
     "gp_sn_scale": [_vp, _vp, _vp, _ll, _vp],
     "gp_sn_grad": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -424,6 +425,22 @@ def gan_loss(pred, mode, target):
     dpred = torch.empty_like(pred)
     check(_fn("gp_gan_loss")(_p(pred), pred.numel(), mode, float(target), _p(loss), _p(dpred), _stream()), "gp_gan_loss")
     return loss, dpred
+
+
+def acgan_loss(logits, labels, mode, target, aux_weight):
+    """logits: fp32 (NB, 1 + K) packed two-head output, labels: fp32 (NB, K) -> (out4, dlogits): out4 = [adversarial
+    term, auxiliary MSE term, adv + aux_weight * aux, mean sigmoid(adv)], dlogits = d out4[2] / d logits. One kernel."""
+    _chk(logits, torch.float32, "logits")
+    _chk(labels, torch.float32, "labels")
+    NB, K = labels.shape
+    if tuple(logits.shape) != (NB, K + 1):
+        raise _lib.GpError("acgan_loss: logits %s do not match labels %s (+1 adversarial column)"
+                           % (tuple(logits.shape), tuple(labels.shape)))
+    out4 = torch.empty((4,), device=logits.device, dtype=torch.float32)
+    dlogits = torch.empty_like(logits)
+    check(_fn("gp_acgan_loss")(_p(logits), _p(labels), NB, K, mode, float(target), float(aux_weight), _p(out4), _p(dlogits),
+                               _stream()), "gp_acgan_loss")
+    return out4, dlogits
 
 
 # ------------------------------------------------------------------------------------------------ spectral norm

@@ -166,6 +166,14 @@ int gp_head_bwd(const float* dout, const void* a, const float* w, void* da, floa
 #define GP_LOSS_NEG_MEAN 4
 int gp_gan_loss(const float* pred, int n, int mode, float target, float* loss, float* dpred, void* stream);
 
+/* ---- ACGAN objective (main_acgan.py:95-97,114-116,129-131: criterion_adv(outD_adv, ...) + 0.5 * MSELoss(outD_cls, c))
+ * on the packed two-head logits fp32 [NB][1 + K] (column 0: out_layer, columns 1..K: out_aux, models/acgan.py:122-126)
+ * and the float label vectors fp32 [NB][K]; value and gradient in one pass.
+ * out4 = { GANLoss term (mode / target as gp_gan_loss), MSE term (mean over NB*K, unweighted), term0 + aux_weight*term1,
+ *          mean(sigmoid(column 0)) — the D(x) / D(G(z)) print of :94,112,127 };  dlogits = d out4[2] / d logits. */
+int gp_acgan_loss(const float* logits, const float* labels, int NB, int K, int mode, float target, float aux_weight,
+                  float* out4, float* dlogits, void* stream);
+
 /* ---- spectral normalisation (torch.nn.utils.spectral_norm's pre-forward hook, torch:nn/utils/spectral_norm.py:62-114,
  * applied at models/dcgan_specnorm.py:37,42,107 and models/sngan_projection.py:110-181) as GEMV kernels.
  * w: fp32 parameter in torch's layout viewed as [A][B][T]; dim == 0: W_mat[a][b*T+t] (Conv2d/Linear/Embedding),
