@@ -131,7 +131,7 @@ def test_acgan_step_tracks_the_oracle_loop():
     dev0, dev, c = rel(got[0], ref[0]).max().item(), rel(got, ref).max().item(), rel(ctl, ref).max().item()
     print("\nACGAN loop, %d steps: first step %.3f%%, all steps %.3f%% (fp32 1e-6-perturbation control %.3f%%)"
           % (steps, 100 * dev0, 100 * dev, 100 * c))
-    assert dev0 < 0.02                    # teacher-forced: identical weights
+    assert dev0 < 0.005                   # teacher-forced: identical weights (measured 8e-5 in bf16x3)
     assert dev < max(0.03, 3 * c)
     # bookkeeping of the loop: D saw 3 forwards per iteration, G one; the auxiliary head moved like the oracle's
     assert int(netD.blocks[1][1].num_batches_tracked) == 3 * steps and int(netG.blocks[0][1].num_batches_tracked) == steps
@@ -222,7 +222,7 @@ def test_sngan_step_tracks_the_oracle_loop():
           % (steps, 100 * dl0, 100 * dl, 100 * cl, 100 * dm, scale, 100 * cm))
     assert dl0 < 0.02
     assert dl < max(0.02, 3 * cl)
-    assert dm < max(0.15, 3 * cm)
+    assert dm < max(0.05, 3 * cm)       # measured 3e-3
     # one generator forward per iteration, spectral-norm vectors advanced 2 or 3 times per iteration like the oracle's
     assert int(netG.b6.num_batches_tracked) == steps
     u_ref = tr.bd["l6.weight_u"]
