@@ -398,6 +398,63 @@ def acgan_loop_fixture(mods, width, batch, steps, seed, z_dim=16):
     return fx
 
 
+def checkpoint_fixture(mods, seed=12):
+    """A checkpoint exactly as the reference writes it (save_model, main_dcgan.py:107-123 / main_sngan.py:107-123:
+    {'state_dict': {'generator', 'discriminator'}, 'optimizer': {'generator', 'discriminator'}, 'epoch'}) after two
+    optimiser steps, for dcgan (res 32, width 4) and the SNGAN projection pair (ch 4) — so the mirrors can be checked to
+    load it, continue from it and write the same layout back. The losses of the NEXT iteration on the reference are stored
+    as the resume check."""
+    out = {}
+    M = mods["dcgan"]
+    torch.manual_seed(seed)
+    netG, netD = M.Generator(z_dim=16, ngf=4, resolution=32), M.Discriminator(ndf=4, resolution=32)
+    crit = mods["criterion"].GANLoss("vanilla", 0.9, 0.1, 0.9)
+    optG = torch.optim.Adam(netG.parameters(), lr=4e-4, betas=(0.5, 0.999))
+    optD = torch.optim.Adam(netD.parameters(), lr=1e-4, betas=(0.5, 0.999))
+    xs, zs = trace_data(seed, 3, 8, 32, 16)
+
+    def it(i):
+        optD.zero_grad()
+        l1 = crit(netD(xs[i]), True)
+        l1.backward()
+        l2 = crit(netD(netG(zs[i, 0]).detach()), False)
+        l2.backward()
+        optD.step()
+        optG.zero_grad()
+        l3 = crit(netD(netG(zs[i, 1])), False, True)
+        l3.backward()
+        optG.step()
+        return [l1.item(), l2.item(), l3.item()]
+
+    it(0), it(1)
+    out["dcgan"] = {"checkpoint": {"state_dict": {"generator": clone_sd(netG), "discriminator": clone_sd(netD)},
+                                   "optimizer": {"generator": optG.state_dict(), "discriminator": optD.state_dict()},
+                                   "epoch": 0},
+                    "seed": seed, "next_losses": it(2)}
+    S = mods["sngan_projection"]
+    torch.manual_seed(seed + 1)
+    sG = S.ResNetGenerator(ch=4, dim_z=16, bottom_width=2, img_dim=3, n_classes=10)
+    sD = S.SNResNetProjectionDiscriminator(ch=4, n_classes=10, img_dim=3)
+    oG = torch.optim.Adam(sG.parameters(), lr=2e-4, betas=(0.0, 0.999))
+    oD = torch.optim.Adam(sD.parameters(), lr=2e-4, betas=(0.0, 0.999))
+    hinge = mods["criterion"].GANLoss("hinge")
+    x, y, z, c = (t[0] for t in sngan_loop_data(seed, 1, 4, 16))
+    oD.zero_grad()
+    hinge(sD(x, y), True).backward()
+    fake = sG(z, c)
+    hinge(sD(fake.detach(), c), False).backward()
+    oD.step()
+    oG.zero_grad()
+    hinge(sD(fake, c), False, True).backward()
+    oG.step()
+    out["sngan"] = {"checkpoint": {"state_dict": {"generator": clone_sd(sG), "discriminator": clone_sd(sD)},
+                                   "optimizer": {"generator": oG.state_dict(), "discriminator": oD.state_dict()},
+                                   "epoch": 0}}
+    import copy
+
+    return copy.deepcopy(out)
+
+
 def ganloss_fixture(mods):
     G = mods["criterion"].GANLoss
     gen = torch.Generator().manual_seed(5)
@@ -471,6 +528,7 @@ def main():
         "sngan_proj_ch8.pt": lambda: sngan_fixture(mods, 8, 2, 4),
         "acgan_r64_w4.pt": lambda: acgan_fixture(mods, 4, 2, 5),
         "ganloss.pt": lambda: ganloss_fixture(mods),
+        "checkpoint_ref_layout.pt": lambda: checkpoint_fixture(mods),
         "sngan_loop_ch8.pt": lambda: sngan_loop_fixture(mods, 8, 8, 12, 8),
         "acgan_loop_r64_w4.pt": lambda: acgan_loop_fixture(mods, 4, 8, 12, 9),
     }

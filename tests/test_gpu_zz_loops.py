@@ -248,3 +248,48 @@ def test_sngan_graph_variants_replay_the_eager_loop():
                 assert abs(x - y) < 5e-2, (i, j, a, b)
     assert int(gE.b6.num_batches_tracked) == int(gG.b6.num_batches_tracked) == steps
     assert torch.allclose(dE.l6.weight_u, dG.l6.weight_u, atol=5e-2)
+
+
+# ------------------------------------------------------------------------------------------------ checkpoints
+@pytest.mark.parametrize("fused", [False, True])
+def test_gpu_training_resumes_from_the_reference_checkpoint(fused):
+    """Mirrors + optimiser (torch.optim.Adam as in the scripts, or optim.FusedAdam) restored from the reference's
+    checkpoint run the reference's next iteration: same three losses (<= 2 %, the north_star bar)."""
+    import os
+    import sys
+
+    from conftest import ROOT
+    from gan_playground_b200.criterion import GANLoss
+    from gan_playground_b200.engine import DcganStep
+    from gan_playground_b200.optim import FusedAdam
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from make_golden import trace_data
+
+    from conftest import load_golden
+    from test_checkpoint_compat import _pairs
+
+    fx = load_golden("checkpoint_ref_layout.pt")
+    netG, netD, ck = _pairs(fx)["dcgan"]
+    netG.load_state_dict(ck["state_dict"]["generator"])
+    netD.load_state_dict(ck["state_dict"]["discriminator"])
+    netG.cuda(), netD.cuda()
+    if fused:
+        optG = FusedAdam(netG.parameters(), lr=4e-4, betas=(0.5, 0.999))
+        optD = FusedAdam(netD.parameters(), lr=1e-4, betas=(0.5, 0.999))
+    else:
+        optG = torch.optim.Adam(netG.parameters(), lr=4e-4, betas=(0.5, 0.999))
+        optD = torch.optim.Adam(netD.parameters(), lr=1e-4, betas=(0.5, 0.999))
+    optG.load_state_dict(ck["optimizer"]["generator"])
+    optD.load_state_dict(ck["optimizer"]["discriminator"])
+    if fused:   # same layout out as in
+        sd = optG.state_dict()
+        ref = ck["optimizer"]["generator"]
+        assert sorted(sd["state"]) == sorted(ref["state"])
+        for i, e in ref["state"].items():
+            assert torch.allclose(sd["state"][i]["exp_avg"].cpu(), e["exp_avg"]) and float(sd["state"][i]["step"]) == float(e["step"])
+    xs, zs = trace_data(fx["dcgan"]["seed"], 3, 8, 32, 16)
+    run = DcganStep(netG, netD, GANLoss("vanilla", 0.9, 0.1, 0.9).cuda(), optG, optD, 8, 16, torch.device("cuda", 0))
+    got = run.step(xs[2].cuda(), zs[2].cuda())[:3]
+    print("resumed iteration (fused=%s): ours %s vs reference %s" % (fused, got, fx["dcgan"]["next_losses"]))
+    assert got == pytest.approx(fx["dcgan"]["next_losses"], rel=2e-2, abs=2e-3)
