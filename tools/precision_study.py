@@ -1,0 +1,293 @@
+"""CPU emulation of the forward-precision policies of the DCGAN-64 step (no GPU needed): which operand / storage
+roundings cost the north_star gradient-cosine bar, and what is the cheapest policy that keeps it?
+
+The real kernels differ from the fp32 reference only through bf16 roundings:
+  operands   conv / linear GEMMs read bf16 tiles; the `bf16x3` mode reads hi+lo pairs of BOTH operands (3 MMAs);
+  y storage  the pre-BatchNorm conv output is stored bf16 (`bf16`) or fp32 (`bf16x3`); batch statistics always come
+             from the fp32 accumulators;
+  a storage  post-activation tensors are stored as one bf16 (`bf16`) or a hi+lo pair (`bf16x3`);
+  backward   always single bf16: da / dy tensors are bf16, dgrad reads (dy, W_hi), wgrad reads (dy, x_hi), fp32 accumulate.
+This script restates those roundings on fp32 CPU tensors (custom autograd nodes with explicit backward operands) for a
+per-layer POLICY = (x bits, w bits, y storage, a storage), calibrates the two shipped modes against the numbers measured
+on the B200 (tests/test_gpu_precision.py), and then scores cheaper candidates with the same metrics:
+activation max-rel-error and the D-real / D-fake / G-step global gradient cosines against the fp32 oracle.
+
+    python tools/precision_study.py [--batch 32] [--only name,name] [--sweep]      # a few seconds per policy
+
+It is an analysis tool (imports oracle/: test infrastructure); nothing in the product path depends on it."""
+import argparse
+import contextlib
+import io
+import os
+import sys
+import time
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import gan_oracle as O  # noqa: E402
+
+EPS = 1e-5
+
+
+def q(x):
+    return x.bfloat16().float()
+
+
+def split16(x):
+    hi = q(x)
+    return hi + q(x - hi)
+
+
+def operand(x, fmt):
+    """GEMM operand formats: 8 = one bf16, 16 = bf16 hi + bf16 lo, "h" = one fp16 (11 significant bits, narrower range:
+    values below 6e-8 flush), "hh" = fp16 hi + fp16 lo."""
+    if fmt == 8:
+        return q(x)
+    if fmt == 16:
+        return split16(x)
+    hi = x.half().float()
+    return hi if fmt == "h" else hi + (x - hi).half().float()
+
+
+def ste(x, xq):
+    """value xq, gradient of x"""
+    return x + (xq - x).detach()
+
+
+class RoundGrad(torch.autograd.Function):
+    """identity whose incoming gradient is stored as bf16 (the da / dy tensors between nodes)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return q(g)
+
+
+class ConvEmu(torch.autograd.Function):
+    """conv / conv-transpose (k4 s2 p1) or linear with operand precisions (xbits, wbits) in {8, 16}; backward with single
+    bf16 operands: dx = dgrad(q(dy), q(w)), dw = wgrad(q(dy), q(x)) in fp32 accumulation."""
+
+    @staticmethod
+    def forward(ctx, x, w, kind, xbits, wbits):
+        X, W = operand(x, xbits), operand(w, wbits)
+        ctx.kind = kind
+        ctx.save_for_backward(q(x), q(w))
+        return ConvEmu.op(X, W, kind)
+
+    @staticmethod
+    def op(X, W, kind):
+        if kind == "conv":
+            return F.conv2d(X, W, None, stride=2, padding=1)
+        if kind == "convT":
+            return F.conv_transpose2d(X, W, None, stride=2, padding=1)
+        return F.linear(X, W)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xh, wh = ctx.saved_tensors
+        with torch.enable_grad():
+            xh = xh.detach().requires_grad_(True)
+            wh = wh.detach().requires_grad_(True)
+            y = ConvEmu.op(xh, wh, ctx.kind)
+            dx, dw = torch.autograd.grad(y, (xh, wh), q(dy))
+        return dx, dw, None, None, None
+
+
+def conv_emu(x, w, b, kind, pol):
+    y = ConvEmu.apply(x, w, kind, pol["x"], pol["w"])
+    if b is not None:
+        y = y + (b[None, :, None, None] if y.dim() == 4 else b)
+    return y
+
+
+def store_act(a, pol):
+    """post-activation storage (hi or hi+lo) + bf16 gradient storage on the way back"""
+    aq = operand(a, pol["a"])
+    return RoundGrad.apply(ste(a, aq))
+
+
+def bn_act(y, gamma, beta, act, pol):
+    """BatchNorm(train) + activation as the kernels do it: statistics from the fp32 accumulators, normalisation applied to
+    the STORED y (bf16 or fp32); the incoming gradient of y is stored as bf16."""
+    mean = y.mean(dim=(0, 2, 3))
+    var = y.var(dim=(0, 2, 3), unbiased=False)
+    ys = RoundGrad.apply(ste(y, q(y)) if pol["y"] == "bf16" else y)
+    xhat = (ys - mean[None, :, None, None]) * torch.rsqrt(var[None, :, None, None] + EPS)
+    z = xhat * gamma[None, :, None, None] + beta[None, :, None, None]
+    return store_act(F.relu(z) if act == "relu" else F.leaky_relu(z, 0.2), pol)
+
+
+def convT_image(x, w, b, pol):
+    """last generator layer: 1-tap GEMM per kernel tap into a column buffer (bf16 in `bf16`, fp32 in `bf16x3`), then
+    col2im + bias + tanh in fp32"""
+    if pol["col"] == "f32":
+        return torch.tanh(conv_emu(x, w, b, "convT", pol))
+    out = None
+    for kh in range(4):
+        for kw in range(4):
+            m = torch.zeros_like(w)
+            m[:, :, kh, kw] = 1.0
+            part = ConvEmu.apply(x, w * m, "convT", pol["x"], pol["w"])
+            part = RoundGrad.apply(ste(part, q(part)))          # the bf16 column buffer (zeros stay zeros)
+            out = part if out is None else out + part
+    return torch.tanh(out + b[None, :, None, None])
+
+
+def generator(sd, z, P):
+    h = F.relu(conv_emu(z, sd["linear.weight"], sd["linear.bias"], "linear", P["g_lin"]))
+    h = store_act(h, P["g_lin"]).view(h.size(0), -1, 4, 4)
+    i = 0
+    while ("blocks.%d.0.bias" % i) in sd:
+        p, pol = "blocks.%d." % i, P["g%d" % i]
+        y = conv_emu(h, sd[p + "0.weight"], sd[p + "0.bias"], "convT", pol)
+        h = bn_act(y, sd[p + "1.weight"], sd[p + "1.bias"], "relu", pol)
+        i += 1
+    return convT_image(h, sd["out_layer.0.weight"], sd["out_layer.0.bias"], P["g_out"])
+
+
+def discriminator(sd, x, P):
+    h, i = x, 0
+    while ("blocks.%d.0.bias" % i) in sd:
+        p, pol = "blocks.%d." % i, P["d%d" % i]
+        y = conv_emu(h, sd[p + "0.weight"], sd[p + "0.bias"], "conv", pol)
+        if (p + "1.weight") in sd:
+            h = bn_act(y, sd[p + "1.weight"], sd[p + "1.bias"], "lrelu", pol)
+        else:
+            h = store_act(F.leaky_relu(y, 0.2), pol)
+        i += 1
+    return F.linear(h.sum(dim=(2, 3)), sd["out_layer.weight"], sd["out_layer.bias"])
+
+
+LAYERS = ["g_lin", "g0", "g1", "g2", "g_out", "d0", "d1", "d2", "d3"]
+BF16 = dict(x=8, w=8, y="bf16", a=8, col="bf16")
+X3 = dict(x=16, w=16, y="f32", a=16, col="f32")
+
+
+def policy(base, **over):
+    P = {k: dict(base) for k in LAYERS}
+    for k, v in over.items():
+        for layer in (LAYERS if k == "all" else [k]):
+            P[layer] = dict(P[layer], **v)
+    return P
+
+
+def mmas(P, fake_passes_only=True):
+    """relative forward MMA work of the generated-image passes (bf16 = 1.0), weighting every layer equally (the DCGAN-64
+    layers have equal FLOPs, the image-side ones are negligible)"""
+    big = ["g0", "g1", "g2", "d1", "d2", "d3"]
+    n = {8: 1, "h": 1, 16: 2, "hh": 2}
+    return sum(n[P[k]["x"]] * n[P[k]["w"]] - (n[P[k]["x"]] * n[P[k]["w"]] == 4) for k in big) / len(big)
+
+
+POLICIES = {
+    "bf16": policy(BF16),
+    "bf16x3": policy(X3),
+    # which single ingredient matters?
+    "bf16 + y fp32": policy(BF16, all=dict(y="f32")),
+    "bf16 + y fp32 + a hi/lo": policy(BF16, all=dict(y="f32", a=16, col="f32")),
+    "x 16 only (2 MMA), y fp32, a hi/lo": policy(X3, all=dict(w=8)),
+    "w 16 only (2 MMA), y fp32": policy(BF16, all=dict(w=16, y="f32", col="f32")),
+    # x3 only where it matters?
+    "x3 in D only": policy(BF16, d0=X3, d1=X3, d2=X3, d3=X3, g_out=dict(a=16, col="f32")),
+    "x3 in G only": policy(X3, d0=BF16, d1=BF16, d2=BF16, d3=BF16),
+    # fp16 forward operands (tcgen05 kind::f16 takes either): 11 significant bits in ONE MMA; backward stays bf16
+    "fp16 operands (1 MMA), y fp32, a fp16": policy(BF16, all=dict(x="h", w="h", y="f32", a="h", col="f32")),
+    "fp16 operands (1 MMA), y bf16, a fp16": policy(BF16, all=dict(x="h", w="h", y="bf16", a="h", col="f32")),
+    "fp16 x, fp16 hi+lo w (2 MMA), y fp32": policy(BF16, all=dict(x="h", w="hh", y="f32", a="h", col="f32")),
+    "fp16 hi+lo x, fp16 w (2 MMA), y fp32": policy(BF16, all=dict(x="hh", w="h", y="f32", a="hh", col="f32")),
+    "fp16x3 (3 MMA), y fp32": policy(BF16, all=dict(x="hh", w="hh", y="f32", a="hh", col="f32")),
+}
+
+
+def cos(ga, gb, skip_prebn_of):
+    num = da = db = 0.0
+    for k, r in gb.items():
+        if k.endswith(".0.bias") and k.replace(".0.bias", ".1.weight") in skip_prebn_of:
+            continue
+        g = ga[k].double()
+        r = r.double()
+        num += (g * r).sum().item()
+        da += (g * g).sum().item()
+        db += (r * r).sum().item()
+    return num / (da ** 0.5 * db ** 0.5 + 1e-30)
+
+
+def relerr(a, b):
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+def run(P, sd_g, sd_d, x, z1, z2, ref):
+    pg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd_g.items()}
+    pd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd_d.items()}
+    dl = [k for k, v in pd.items() if torch.is_tensor(v) and v.requires_grad]
+    gl = [k for k, v in pg.items() if torch.is_tensor(v) and v.requires_grad]
+    out = {}
+    d_real = discriminator(pd, x, P)
+    gr = torch.autograd.grad(O.gan_loss("vanilla", d_real, True, False, 0.9, 0.1, 0.9), [pd[k] for k in dl], allow_unused=True)
+    out["act D(x)"] = relerr(d_real.detach(), ref["d_real"])
+    out["cos D-real"] = cos({k: g for k, g in zip(dl, gr) if g is not None}, ref["d_grads_real"], pd)
+    with torch.no_grad():
+        fake1 = generator(pg, z1, P)
+    out["act G(z)"] = relerr(fake1, ref["fake1"])
+    d_fake = discriminator(pd, fake1, P)
+    gf = torch.autograd.grad(O.gan_loss("vanilla", d_fake, False, False, 0.9, 0.1, 0.9), [pd[k] for k in dl], allow_unused=True)
+    out["act D(G(z))"] = relerr(d_fake.detach(), ref["d_fake"])
+    out["cos D-fake"] = cos({k: g for k, g in zip(dl, gf) if g is not None}, ref["d_grads_fake"], pd)
+    d_g = discriminator(pd, generator(pg, z2, P), P)
+    gg = torch.autograd.grad(O.gan_loss("vanilla", d_g, False, True, 0.9, 0.1, 0.9), [pg[k] for k in gl], allow_unused=True)
+    out["cos G-step"] = cos({k: g for k, g in zip(gl, gg) if g is not None}, ref["g_grads"], pg)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--width", type=int, default=64)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--sweep", action="store_true", help="per-layer sensitivity: one layer fp16 1-MMA / rest bf16x3 and back")
+    args = ap.parse_args()
+    from gan_playground_b200.models import dcgan
+
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        netG, netD = dcgan.Generator(ngf=args.width), dcgan.Discriminator(ndf=args.width)
+    sd_g = {k: v.clone() for k, v in netG.state_dict().items()}
+    sd_d = {k: v.clone() for k, v in netD.state_dict().items()}
+    gen = torch.Generator().manual_seed(1)
+    B = args.batch
+    x = torch.rand(B, 3, 64, 64, generator=gen) * 2 - 1
+    z1, z2 = torch.randn(B, 100, generator=gen), torch.randn(B, 100, generator=gen)
+    ref = O.dcgan_step_grads(sd_g, sd_d, x, z1, z2)
+    print("DCGAN-64 width %d batch %d (same seeds as tests/test_gpu_precision.py); measured on the B200: bf16 -> act 6.2e-3 /"
+          " 1.3e-2 / 1.3e-2, cos 0.999911 / 0.9938 / 0.9707;  bf16x3 -> act 1.2e-5 / 2.5e-5 / 2.6e-5, cos 1.000000 /"
+          " 0.999977 / 0.999893" % (args.width, B))
+    print("%-40s %5s | %9s %9s %9s | %9s %9s %9s" % ("policy (emulated)", "MMAs", "D(x)", "G(z)", "D(G(z))", "cos Dreal",
+                                                    "cos Dfake", "cos Gstep"))
+    for name, P in POLICIES.items():
+        if args.only and name not in args.only.split(","):
+            continue
+        t = time.time()
+        r = run(P, sd_g, sd_d, x, z1, z2, ref)
+        print("%-40s %5.2f | %9.2e %9.2e %9.2e | %9.6f %9.6f %9.6f   (%.0f s)" % (
+            name, mmas(P), r["act D(x)"], r["act G(z)"], r["act D(G(z))"], r["cos D-real"], r["cos D-fake"],
+            r["cos G-step"], time.time() - t), flush=True)
+    if args.sweep:
+        H = dict(x="h", w="h", y="f32", a="h", col="f32")
+        for title, make in (("one layer fp16 1-MMA, rest bf16x3", lambda L: policy(X3, **{L: H})),
+                            ("one layer bf16x3, rest fp16 1-MMA", lambda L: policy(BF16, all=H, **{L: X3}))):
+            print(title + ":")
+            for L in LAYERS:
+                r = run(make(L), sd_g, sd_d, x, z1, z2, ref)
+                print("  %-6s cos D-fake %.6f  G-step %.6f" % (L, r["cos D-fake"], r["cos G-step"]), flush=True)
+
+
+if __name__ == "__main__":
+    main()
