@@ -297,7 +297,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": global_batch, "per_gpu_batch": per_gpu,
-                       "parallelism": "dp%d" % world, "precision": config.precision() + (" (real-image D pass: bf16)" if runner.real_precision else ""),
+                       "parallelism": "dp%d" % world, "precision": config.precision() + (" (real-image D pass: bf16)" if runner.real_precision else "") + (" (D-fake chain: %s)" % runner.fake_precision if runner.fake_precision else ""),
                        "cuda_graph": use_graph,
                        "optimizer": "torch.optim.Adam" if args.torch_adam else "FusedAdam(flat%s)" % (", zero1" if world > 1 else ""),
                        "syncbn": "n/a (1 rank)" if world == 1 else ("one-shot NVLink peer exchange fused with the statistics finalize"

@@ -24,6 +24,7 @@ class ConvFwd(ctypes.Structure):
         ("Hout", c_int), ("Wout", c_int), ("Nout", c_int),
         ("kind", c_int), ("act", c_int), ("residual", c_void_p),
         ("in_lo", c_void_p), ("out_lo", c_void_p), ("out_f32", c_void_p),
+        ("flags", c_int),
     ]
 
 

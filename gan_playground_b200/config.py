@@ -5,12 +5,16 @@ precision:
             and pre-BatchNorm outputs are stored in fp32: fp32-class forward activations on bf16 tensor cores, needed for
             the north_star gradient-cosine bar (>= 0.999 on the G step). Backward GEMMs stay single bf16.
   "bf16"   — single bf16 operands everywhere, bf16 activation storage: ~1.6x faster, G-step gradient cosine ~0.97.
+  "fp16"   — ONE MMA on fp16 operands (11 significant bits; tcgen05 kind::f16 takes fp16 as well as bf16), fp32
+            pre-BatchNorm storage, activations stored twice: bf16 (what the backward GEMMs read — the backward stays bf16,
+            fp16 would underflow its 1e-8-scale gradients) and fp16 (the next forward operand). Emulated cosines
+            (tools/precision_study.py): D-real 0.99999, D-fake 0.9993, G-step 0.9968 — good for every pass except the G step.
 Select with gan_playground_b200.config.set_precision(...) or the GP_PRECISION environment variable.
 Only the DCGAN-family nodes (dcgan / acgan / dcgan_specnorm) implement bf16x3 so far; the ResNet nodes run "bf16".
 """
 import os
 
-_VALID = ("bf16", "bf16x3")
+_VALID = ("bf16", "bf16x3", "fp16")
 _precision = os.environ.get("GP_PRECISION", "bf16x3")
 if _precision not in _VALID:
     raise ValueError("GP_PRECISION must be one of %s" % (_VALID,))
@@ -29,6 +33,10 @@ def set_precision(p):
 
 def x3():
     return _precision == "bf16x3"
+
+
+def fp16():
+    return _precision == "fp16"
 
 
 class precision_scope:

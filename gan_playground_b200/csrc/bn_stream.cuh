@@ -9,6 +9,7 @@
 // one global atomic per channel per block.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.h"
 
@@ -78,6 +79,20 @@ __device__ __forceinline__ void store8_bf16(__nv_bfloat16* hi, __nv_bfloat16* lo
   }
   *reinterpret_cast<uint4*>(hi) = rh;
   if (lo != nullptr) *reinterpret_cast<uint4*>(lo) = rl;
+}
+
+// store 8 fp32 values as bf16 (backward operand) and as fp16 (operand of the next forward GEMM in the "fp16" mode)
+__device__ __forceinline__ void store8_bf16_f16(__nv_bfloat16* b, __half* h, const float (&f)[8]) {
+  uint4 rb, rh;
+  __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&rb);
+  __half2* ph = reinterpret_cast<__half2*>(&rh);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    pb[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    ph[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  }
+  *reinterpret_cast<uint4*>(b) = rb;
+  *reinterpret_cast<uint4*>(h) = rh;
 }
 
 constexpr int kRowsInFlight = 4;
@@ -180,7 +195,8 @@ __global__ void col_stats_kernel(const TY* __restrict__ x, long long P, int C, f
 }
 
 // out (bf16 hi [+ lo]) = act(y * scale[c] + shift[c])
-template <typename TY>
+// LOH: out_lo is an fp16 copy of the value instead of the bf16 rounding residual
+template <typename TY, bool LOH = false>
 __global__ void bn_apply_kernel(const TY* __restrict__ y, __nv_bfloat16* __restrict__ out_hi,
                                 __nv_bfloat16* __restrict__ out_lo, long long P, int C, const float* __restrict__ scale,
                                 const float* __restrict__ shift, int act, int rows_per_block) {
@@ -210,7 +226,10 @@ __global__ void bn_apply_kernel(const TY* __restrict__ y, __nv_bfloat16* __restr
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = act_fwd(f[j] * sc[j] + sh[j], act);
         const long long off = ru * C + L.g * 8;
-        store8_bf16(out_hi + off, out_lo ? out_lo + off : nullptr, f);
+        if constexpr (LOH)
+          store8_bf16_f16(out_hi + off, reinterpret_cast<__half*>(out_lo) + off, f);
+        else
+          store8_bf16(out_hi + off, out_lo ? out_lo + off : nullptr, f);
       }
     }
   }

@@ -19,6 +19,7 @@
 // the MMAs of tile i+1.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "sm100_ptx.cuh"
 
 namespace gp {
@@ -70,7 +71,11 @@ struct alignas(64) ConvGemmParams {
                       // tile can span several taps of a narrow gathered operand; 0 = one tap per tile
   float* col_sum;     // optional fused per-channel statistics of the (pre-activation) output
   float* col_sumsq;
+  int fmt_flags;      // FWD: kFmtInF16 = both operands are fp16 (tcgen05 kind::f16 takes fp16 or bf16: only the instruction
+                      // descriptor changes, tiles are 2-byte elements either way); kFmtLoF16 = out_lo receives fp16(v), the
+                      // single-MMA operand copy of the "fp16" forward mode, instead of the bf16 rounding residual
 };
+constexpr int kFmtInF16 = 1, kFmtLoF16 = 2;
 
 // X3 = bf16x3 forward (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo): one pipeline stage holds the hi AND lo tiles of both
 // operands — 4 tile loads feed 3 MMA blocks, i.e. 1/3 fewer operand bytes from L2 per MMA than issuing the three
@@ -304,7 +309,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     }
   } else if (warp == 1 && lane == 0) {
     // =========================== MMA issuer (one thread) ===========================
-    constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BN, MODE == MODE_WGRAD, MODE == MODE_WGRAD);
+    // a_format / b_format (bits [7,10) / [10,13)): 1 = BF16, 0 = F16
+    const uint32_t idesc = make_idesc_bf16(kBlockM, BN, MODE == MODE_WGRAD, MODE == MODE_WGRAD) &
+                           ~((MODE == MODE_FWD && (p.fmt_flags & kFmtInF16)) ? ((1u << 7) | (1u << 10)) : 0u);
     // K-major: SBO = 8 rows * 128 B. MN-major: SBO = 8 K-rows * 128 B, LBO = 64 K-rows * 128 B (next 64-channel chunk).
     constexpr uint64_t dbase = (MODE == MODE_FWD) ? make_smem_desc_base(0, 1024) : make_smem_desc_base(8192, 1024);
     constexpr uint32_t kadv = (MODE == MODE_FWD) ? (kUmmaK * 2) : (kUmmaK * 128);  // bytes per UMMA_K step
@@ -506,11 +513,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                     *reinterpret_cast<uint4*>(orow + g * 8) = make_uint4(w32[4 * g], w32[4 * g + 1], w32[4 * g + 2], w32[4 * g + 3]);
                 if (p.out_lo != nullptr) {
                   __nv_bfloat16* lrow = p.out_lo + off[mi] + col0;
+                  if (p.fmt_flags & kFmtLoF16) {
 #pragma unroll
-                  for (int e = 0; e < 16; ++e) {
-                    const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w32[e]));
-                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
-                    w32[e] = *reinterpret_cast<const uint32_t*>(&l2);
+                    for (int e = 0; e < 16; ++e) {
+                      const __half2 h2 = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                      w32[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                    }
+                  } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                      const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w32[e]));
+                      const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+                      w32[e] = *reinterpret_cast<const uint32_t*>(&l2);
+                    }
                   }
 #pragma unroll
                   for (int g = 0; g < 4; ++g)

@@ -5,6 +5,7 @@
 // for fp32 y, and the hi/lo staging of plain matrices. (Conv-weight / im2col / col2im / head variants share their
 // kernels with the bf16 mode and live in elementwise.cu; the GEMM side is conv_gemm.cuh with extra K taps.)
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "bn_stream.cuh"
 #include "common.h"
@@ -31,6 +32,29 @@ __global__ void split_matrix_kernel(const float* __restrict__ src, __nv_bfloat16
     const __nv_bfloat16 hi = __float2bfloat16(v);
     dst[(long long)r * ld + k] = hi;
     dst[lo_off + (long long)r * ld + k] = __float2bfloat16(v - __bfloat162float(hi));
+  }
+}
+
+// out[r*ld_out + k] = fp16(hi[r*ld_in + k] + lo[r*ld_in + k]): the single-MMA fp16 operand from a hi/lo bf16 pair
+// (hi + lo carries ~16 significant bits, so the double rounding is below fp16's own). 8 columns per thread.
+__global__ void pair_to_f16_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                   long long ld_in, __half* __restrict__ out, long long ld_out, long long rows, int cols8) {
+  const long long total = rows * cols8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols8;
+    const int k = (int)(i % cols8) * 8;
+    const uint4 vh = *reinterpret_cast<const uint4*>(hi + r * ld_in + k);
+    const uint4 vl = *reinterpret_cast<const uint4*>(lo + r * ld_in + k);
+    const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&vh);
+    const __nv_bfloat162* pl = reinterpret_cast<const __nv_bfloat162*>(&vl);
+    uint4 o;
+    __half2* po = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = __bfloat1622float2(ph[j]), b = __bfloat1622float2(pl[j]);
+      po[j] = __floats2half2_rn(a.x + b.x, a.y + b.y);
+    }
+    *reinterpret_cast<uint4*>(out + r * ld_out + k) = o;
   }
 }
 
@@ -68,6 +92,33 @@ int gp_bn_apply_act_split(const float* y, void* out_hi, void* out_lo, long long 
   bn_apply_kernel<float><<<L.grid, L.block, 0, as_stream(stream)>>>(y, static_cast<__nv_bfloat16*>(out_hi),
                                                                     static_cast<__nv_bfloat16*>(out_lo), P, C, scale,
                                                                     shift, act, L.rpb);
+  GP_CHECK_LAUNCH();
+  return GP_OK;
+}
+
+int gp_pair_to_f16(const void* hi, const void* lo, long long ld_in, void* out, long long ld_out, long long rows, int cols,
+                   void* stream) {
+  GP_REQUIRE(hi && lo && out && rows > 0 && cols > 0 && cols % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 &&
+                 ld_in >= cols && ld_out >= cols,
+             "gp_pair_to_f16: bad arguments (cols and pitches must be multiples of 8)");
+  GP_REQUIRE(((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+             "gp_pair_to_f16: pointers must be 16-byte aligned");
+  long long g = (rows * (cols / 8) + 255) / 256;
+  if (g > (long long)num_sms() * 16) g = (long long)num_sms() * 16;
+  x3::pair_to_f16_kernel<<<(int)g, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(hi),
+                                                                static_cast<const __nv_bfloat16*>(lo), ld_in,
+                                                                static_cast<__half*>(out), ld_out, rows, cols / 8);
+  GP_CHECK_LAUNCH();
+  return GP_OK;
+}
+
+int gp_bn_apply_act_pair(const float* y, void* out_bf16, void* out_f16, long long P, int C, const float* scale,
+                         const float* shift, int act, void* stream) {
+  GP_REQUIRE(y && out_bf16 && out_f16 && scale && shift && P > 0 && C % 8 == 0, "gp_bn_apply_act_pair: bad arguments");
+  const ColLaunch L = col_launch(P, C, 0);
+  bn_apply_kernel<float, true><<<L.grid, L.block, 0, as_stream(stream)>>>(y, static_cast<__nv_bfloat16*>(out_bf16),
+                                                                          static_cast<__nv_bfloat16*>(out_f16), P, C, scale,
+                                                                          shift, act, L.rpb);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }

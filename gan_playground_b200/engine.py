@@ -16,6 +16,8 @@ Requirements for graph mode: torch optimisers built with `capturable=True` (Fuse
 size. The weight-staging caches of the networks are cleared before capture so the staging kernels are part of the graph,
 and the warm-up steps capture needs are undone afterwards (parameters, BatchNorm / spectral-norm buffers and optimiser
 state are restored in place), so the first replay is the first training step."""
+import os
+
 import torch
 
 from . import config, ops, parallel
@@ -229,15 +231,20 @@ class DcganStep(_AdversarialStep):
     """main_dcgan.py:68-95. Logged scalars: [lossD_real, lossD_fake, lossG, D(x), D(G(z))_1, D(G(z))_2]."""
 
     def __init__(self, netG, netD, criterion, optG, optD, batch, z_dim, device, use_graph=False, warmup=3, overlap=True,
-                 mixed_precision=True):
+                 mixed_precision=True, fake_precision=None):
         super().__init__(netG, netD, optG, optD, batch, device, use_graph, warmup, overlap)
         self.crit, self.z_dim = criterion, z_dim
         self.x_static = torch.zeros(batch, netD.img_dim, netD.resolution, netD.resolution, device=device)
         self.z_static = torch.zeros(2, batch, z_dim, device=device)
         self._data_static = [self.x_static]
         self._noise_static = [self.z_static[0], self.z_static[1]]
-        # mixed forward precision: the real-image D pass needs no 3-MMA forward (config.precision_scope)
+        # mixed forward precision (config.precision_scope): only the G step needs the 3-MMA forward. The real-image D pass
+        # meets every parity bar with plain bf16 operands; the D-fake chain G(z1) -> D(G(z1).detach()) with single-MMA
+        # fp16 operands (opt-in through GP_FAKE_PRECISION=fp16 / fake_precision= until its GPU parity run is recorded)
         self.real_precision = "bf16" if (mixed_precision and config.x3()) else None
+        if fake_precision is None:
+            fake_precision = os.environ.get("GP_FAKE_PRECISION", "") or None
+        self.fake_precision = fake_precision if (mixed_precision and config.x3()) else None
 
     def _draw_noise(self):
         return torch.randn(self.batch, self.z_dim, device=self.dev), torch.randn(self.batch, self.z_dim, device=self.dev)
@@ -251,8 +258,9 @@ class DcganStep(_AdversarialStep):
         log(3, outD.mean())
         lossD_real = crit(outD, True)
         lossD_real.backward()
-        outG = netG(z1)
-        outD = netD(outG.detach())
+        with config.precision_scope(self.fake_precision or config.precision()):
+            outG = netG(z1)
+            outD = netD(outG.detach())
         log(4, outD.mean())
         lossD_fake = crit(outD, False)
         lossD_fake.backward()

@@ -6,7 +6,9 @@ state_dict()/torch.save work unchanged.
 
 Precision modes (config.py): in "bf16x3" every activation travels as a hi/lo bf16 pair — node outputs are
 (a_hi, a_lo) with a_lo non-differentiable, and the next node takes (x, x_lo); autograd only ever sees the hi tensor
-(gradients are w.r.t. the real-valued activation). In "bf16" the lo half is None."""
+(gradients are w.r.t. the real-valued activation). In "bf16" the lo half is None. In "fp16" the companion tensor is an
+fp16 COPY of the activation (dtype torch.float16 tells it apart from a bf16 lo half): forward GEMMs read it as their
+single-MMA operand, everything on the backward side reads the bf16 tensor."""
 import torch
 
 from . import config, ops, parallel
@@ -53,7 +55,14 @@ def with_lo(fn, h, *args):
     return out
 
 
-def _bn_forward(y, gamma, beta, bufs, act, training=True, st=None):
+def _f16_operand(x, x_lo):
+    """The fp16 forward operand of an activation: its fp16 companion, or (input produced in another mode) a cast."""
+    if x_lo is not None and x_lo.dtype == torch.float16:
+        return x_lo
+    return x.to(torch.float16) if x_lo is None else (x.float() + x_lo.float()).to(torch.float16)
+
+
+def _bn_forward(y, gamma, beta, bufs, act, training=True, st=None, pair=False):
     """y: pre-BN conv output, NHWC bf16 (fp32 in bf16x3 mode). Returns (a, a_lo, fin[4,C], count).
     training: batch statistics (all-reduced over ranks) + running-stat update, as nn.BatchNorm2d.train();
     eval: normalise with the running statistics. st: [2, C] sums already produced by the conv epilogue."""
@@ -74,7 +83,7 @@ def _bn_forward(y, gamma, beta, bufs, act, training=True, st=None):
     else:
         fin = ops.bn_eval_params(rm, rv, gamma, beta, BN_EPS)
     if f32:
-        a, a_lo = ops.bn_apply_act_split(y, fin, act)
+        a, a_lo = ops.bn_apply_act_pair(y, fin, act) if pair else ops.bn_apply_act_split(y, fin, act)
     else:
         a, a_lo = ops.bn_apply_act(y, fin, act), None
     return a, a_lo, fin, count
@@ -107,9 +116,10 @@ class ConvBlock(torch.autograd.Function):
     Reference: models/dcgan.py:35-40 (G blocks) and :104-110 (D blocks)."""
 
     @staticmethod
-    def forward(ctx, x, x_lo, weight, bias, gamma, beta, bufs, transposed, act, cache, key, training=True):
+    def forward(ctx, x, x_lo, weight, bias, gamma, beta, bufs, transposed, act, cache, key, training=True,
+                feeds_head=False):
         NB, H, W, Cin = x.shape
-        x3 = config.x3()
+        x3, fp16 = config.x3(), config.fp16()
         n_dim = 1 if transposed else 0
         if transposed:
             Ho, Wo, kind = 2 * H, 2 * W, ops.KIND_CONVT_K4S2
@@ -125,21 +135,28 @@ class ConvBlock(torch.autograd.Function):
             st = ops.zeros((2, Cout), x.device)
         if x3:
             wp = cache.get((key, "fwd3"), weight, lambda: ops.split_conv_weight(weight.detach(), n_dim))
-            if x_lo is None:
+            if x_lo is None or x_lo.dtype != torch.bfloat16:   # produced by a bf16 / fp16 pass: no low half to add
                 x_lo = torch.zeros_like(x)
             y = ops.conv_fwd(x, wp, b, kind, Ho, Wo, ops.ACT_NONE if has_bn else act, stats=st, x_lo=x_lo,
                              out_mode="f32" if has_bn else "split")
+        elif fp16:
+            # one MMA on fp16 operands; the output pair is (bf16, fp16) — or a (hi, lo) bf16 pair when the head, which is
+            # not a GEMM, consumes it
+            wp = cache.get((key, "fwdh"), weight, lambda: ops.conv_weight_f16(weight.detach(), n_dim))
+            y = ops.conv_fwd(_f16_operand(x, x_lo), wp, b, kind, Ho, Wo, ops.ACT_NONE if has_bn else act, stats=st,
+                             fp16_in=True, out_mode="f32" if has_bn else ("split" if feeds_head else "pair"))
         else:
             wp = cache.get((key, "fwd"), weight, lambda: ops.pack_conv_weight(weight.detach(), n_dim))
             y = ops.conv_fwd(x, wp, b, kind, Ho, Wo, ops.ACT_NONE if has_bn else act, stats=st)
         ctx.transposed, ctx.act, ctx.has_bn, ctx.cache, ctx.key = transposed, act, has_bn, cache, key
         if has_bn:
             a, a_lo, fin, count = _bn_forward(y, gamma.detach() if gamma is not None else None,
-                                              beta.detach() if beta is not None else None, bufs, act, training, st)
+                                              beta.detach() if beta is not None else None, bufs, act, training, st,
+                                              pair=fp16 and not feeds_head)
             ctx.count, ctx.training = count, training
             ctx.save_for_backward(x, weight, y, fin)
         else:
-            a, a_lo = y if x3 else (y, None)
+            a, a_lo = y if (x3 or fp16) else (y, None)
             ctx.save_for_backward(x, weight, a)
         if a_lo is not None:
             ctx.mark_non_differentiable(a_lo)
@@ -148,7 +165,7 @@ class ConvBlock(torch.autograd.Function):
     @staticmethod
     def backward(ctx, da, _unused=None):
         if da is None:
-            return (None,) * 12
+            return (None,) * 13
         da = da.contiguous()
         if ctx.has_bn:
             x, weight, y, fin = ctx.saved_tensors
@@ -179,7 +196,7 @@ class ConvBlock(torch.autograd.Function):
                 dx = ops.conv_fwd(dy, wpd, None, ops.KIND_CONVT_K4S2, H, W)
         if not ctx.needs_input_grad[3]:
             dbias = None
-        return dx, None, dweight, dbias, dgamma, dbeta, None, None, None, None, None, None
+        return dx, None, dweight, dbias, dgamma, dbeta, None, None, None, None, None, None, None
 
 
 class LinearToNHWC(torch.autograd.Function):
@@ -204,6 +221,14 @@ class LinearToNHWC(torch.autograd.Function):
                            lambda: ops.split_weight_matrix(weight.detach(), O, K, O, Kp, K, 1, perm=HW))
             a, a_lo = ops.conv_fwd(zb.view(B, 1, 1, Kp), wp, bp, ops.KIND_CONV_K1S1, 1, 1, act, flops=fl,
                                    x_lo=z_lo.view(B, 1, 1, Kp), out_mode="split")
+            a_lo = a_lo.view(B, bw, bw, C)
+        elif config.fp16():
+            zb, z_lo = ops.split_rows(zc, B, K, Kp, K, 1)          # zb (bf16) is what wgrad reads
+            zh = ops.pair_to_f16(zb, z_lo, B, Kp, Kp)
+            wp = cache.get((key, "fwdh"), weight,
+                           lambda: ops.weight_matrix_f16(weight.detach(), O, K, O, Kp, K, 1, perm=HW))
+            a, a_lo = ops.conv_fwd(zh.view(B, 1, 1, Kp), wp, bp, ops.KIND_CONV_K1S1, 1, 1, act, flops=fl, fp16_in=True,
+                                   out_mode="pair")
             a_lo = a_lo.view(B, bw, bw, C)
         else:
             zb = ops.pack_matrix(zc, B, K, B, Kp, K, 1)
@@ -259,6 +284,14 @@ class ImageConv(torch.autograd.Function):
                            lambda: ops.split_weight_matrix(weight.detach(), Cout, ch * 16, Cout, 64, ch * 16, 1))
             a, a_lo = ops.conv_fwd(col, wp, bias.detach(), ops.KIND_CONV_K1S1, H // 2, W // 2, act, flops=fl,
                                    x_lo=col_lo, out_mode="split")
+            ctx.mark_non_differentiable(a_lo)
+        elif config.fp16():
+            col, col_lo = ops.im2col_k4s2_split(x.detach())        # col (bf16) is kept for wgrad
+            colh = ops.pair_to_f16(col, col_lo, col.numel() // 64, 64, 64).view(col.shape)
+            wp = cache.get((key, "fwdh"), weight,
+                           lambda: ops.weight_matrix_f16(weight.detach(), Cout, ch * 16, Cout, 64, ch * 16, 1))
+            a, a_lo = ops.conv_fwd(colh, wp, bias.detach(), ops.KIND_CONV_K1S1, H // 2, W // 2, act, flops=fl,
+                                   fp16_in=True, out_mode="pair")
             ctx.mark_non_differentiable(a_lo)
         else:
             col = ops.im2col_k4s2(x.detach())
@@ -316,6 +349,12 @@ class ImageConvT(torch.autograd.Function):
                 x_lo = torch.zeros_like(x)
             ycol = ops.conv_fwd(x, wp, None, ops.KIND_CONV_K1S1, H, W, flops=fl, x_lo=x_lo, out_mode="f32")
             out = ops.col2im_k4s2_f32(ycol, bias.detach(), ch, act)
+        elif config.fp16():
+            wp = cache.get((key, "fwdh"), weight,
+                           lambda: ops.weight_matrix_f16(weight.detach(), ch * 16, Cin, 64, Cin, 1, ch * 16))
+            ycol = ops.conv_fwd(_f16_operand(x, x_lo), wp, None, ops.KIND_CONV_K1S1, H, W, flops=fl, fp16_in=True,
+                                out_mode="f32")
+            out = ops.col2im_k4s2_f32(ycol, bias.detach(), ch, act)
         else:
             wp = cache.get((key, "fwd"), weight,
                            lambda: ops.pack_matrix(weight.detach(), ch * 16, Cin, 64, Cin, 1, ch * 16))
@@ -359,6 +398,8 @@ class Head(torch.autograd.Function):
         O = weight.shape[0]
         strides = (C * H * W, H * W, 1) if flatten else (C, 1, 0)
         b = bias.detach() if bias is not None else None
+        if a_lo is not None and a_lo.dtype != torch.bfloat16:   # an fp16 operand copy is not a low half
+            a_lo = None
         if a_lo is not None:
             out = ops.head_fwd_split(a, a_lo, weight.detach(), b, O, *strides)
         else:
@@ -387,6 +428,8 @@ class PackedHeads(torch.autograd.Function):
         w = torch.cat([w1.detach(), w2.detach()], 0)    # (O1 + O2, C) fp32, a few tens of KB
         b = torch.cat([b1.detach(), b2.detach()], 0)
         strides = (C * H * W, H * W, 1) if flatten else (C, 1, 0)
+        if a_lo is not None and a_lo.dtype != torch.bfloat16:
+            a_lo = None
         if a_lo is not None:
             out = ops.head_fwd_split(a, a_lo, w, b, O1 + O2, *strides)
         else:

@@ -86,7 +86,7 @@ class Discriminator(nn.Module):
         for i in range(1, len(self.blocks)):
             conv, bn = self.blocks[i][0], self.blocks[i][1]
             h = GF.with_lo(GF.ConvBlock, h, conv.weight, conv.bias, bn.weight, bn.bias, bn_buffers(bn), False,
-                           ops.ACT_LRELU, self._gp_cache, "blocks.%d" % i, self.training)
+                           ops.ACT_LRELU, self._gp_cache, "blocks.%d" % i, self.training, i == len(self.blocks) - 1)
         return h
 
     def forward(self, x):

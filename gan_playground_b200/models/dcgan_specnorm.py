@@ -88,7 +88,8 @@ class Discriminator(nn.Module):
         for i in range(1, len(self.blocks)):
             conv, bn = self.blocks[i][0], self.blocks[i][1]
             h = GF.with_lo(GF.ConvBlock, h, sn_weight(conv, 0, self.training), conv.bias, bn.weight, bn.bias,
-                           bn_buffers(bn), False, ops.ACT_LRELU, self._gp_cache, "blocks.%d" % i, self.training)
+                           bn_buffers(bn), False, ops.ACT_LRELU, self._gp_cache, "blocks.%d" % i, self.training,
+                           i == len(self.blocks) - 1)
         out = GF.with_lo(GF.Head, h, self.out_layer.weight, self.out_layer.bias, True)
         if out_hidden:
             # upstream hands back the NCHW fp32 feature map; this is a layout change at the API boundary only

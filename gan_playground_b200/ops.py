@@ -195,15 +195,23 @@ def _timed(name, flops, fn):
 _TAPS_PER_OUT = {KIND_CONV_K4S2: 16, KIND_CONVT_K4S2: 4, KIND_CONV_K3S1: 9, KIND_CONV_K1S1: 1}
 
 
+CONV_IN_F16, CONV_LO_F16 = 1, 2
+
+
 def conv_fwd(x, wp, bias, kind, Hout, Wout, act=ACT_NONE, stats=None, flops=None, residual=None, x_lo=None,
-             out_mode="bf16"):
+             out_mode="bf16", fp16_in=False):
     """x: bf16 (NB, Hin, Win, Cin); wp: bf16 [Nout, taps*Cin]; returns bf16 (NB, Hout, Wout, Nout).
     stats: optional fp32 [2, Nout] zeroed tensor receiving per-channel sum / sum of squares.
     flops: algorithmic FLOPs of this call when they differ from the padded GEMM shape (image layers).
     bf16x3 mode: x_lo = low halves of x and wp = [Nout, 2*taps*Cin] (hi | lo).
-    out_mode: "bf16" -> bf16 tensor; "split" -> (hi, lo) bf16 pair; "f32" -> fp32 tensor."""
-    _chk(x, torch.bfloat16, "x")
-    _chk(wp, torch.bfloat16, "wp")
+    fp16 mode: fp16_in=True, x and wp are fp16 (one MMA; same layouts as the bf16 operands, x_lo must be None).
+    out_mode: "bf16" -> bf16 tensor; "split" -> (hi, lo) bf16 pair; "f32" -> fp32 tensor; "pair" -> (bf16, fp16) copies
+    of the same value (backward operand, next forward operand of the fp16 mode)."""
+    op_dtype = torch.float16 if fp16_in else torch.bfloat16
+    _chk(x, op_dtype, "x")
+    _chk(wp, op_dtype, "wp")
+    if fp16_in and x_lo is not None:
+        raise _lib.GpError("conv_fwd: fp16 operands run as one MMA (x_lo must be None)")
     NB, Hin, Win, Cin = x.shape
     Nout = wp.shape[0]
     shape = (NB, Hout, Wout, Nout)
@@ -214,20 +222,24 @@ def conv_fwd(x, wp, bias, kind, Hout, Wout, act=ACT_NONE, stats=None, flops=None
         out = torch.empty(shape, device=x.device, dtype=torch.bfloat16)
         if out_mode == "split":
             out_lo = torch.empty(shape, device=x.device, dtype=torch.bfloat16)
+        elif out_mode == "pair":
+            out_lo = torch.empty(shape, device=x.device, dtype=torch.float16)
+    flags = (CONV_IN_F16 if fp16_in else 0) | (CONV_LO_F16 if out_mode == "pair" else 0)
     if bias is not None:
         _chk(bias, torch.float32, "bias")
     if x_lo is not None:
         _chk(x_lo, torch.bfloat16, "x_lo")
     p = ConvFwd(_p(x), _p(wp), _p(bias), _p(out), _p(stats[0]) if stats is not None else None,
                 _p(stats[1]) if stats is not None else None, NB, Hin, Win, Cin, Hout, Wout, Nout, kind, act, _p(residual),
-                _p(x_lo), _p(out_lo), _p(out_f32))
+                _p(x_lo), _p(out_lo), _p(out_f32), flags)
     if flops is None:
         flops = 2.0 * NB * Hout * Wout * Nout * Cin * _TAPS_PER_OUT[kind]
-    _timed("conv_fwd kind%d %dx%dx%d C%d->%d%s" % (kind, NB, Hout, Wout, Cin, Nout, " x3" if x_lo is not None else ""),
+    _timed("conv_fwd kind%d %dx%dx%d C%d->%d%s" % (kind, NB, Hout, Wout, Cin, Nout,
+                                                    " x3" if x_lo is not None else (" fp16" if fp16_in else "")),
            flops, lambda: check(_fn("gp_conv_fwd")(ctypes.addressof(p), _stream()), "gp_conv_fwd"))
     if out_mode == "f32":
         return out_f32
-    if out_mode == "split":
+    if out_mode in ("split", "pair"):
         return out, out_lo
     return out
 
@@ -625,6 +637,8 @@ _SIGS.update({
     "gp_split_conv_weight": [_vp, _vp, _i, _i, _i, _i, _vp],
     "gp_bn_stats_f32": [_vp, _ll, _i, _vp, _vp, _vp],
     "gp_bn_apply_act_split": [_vp, _vp, _vp, _ll, _i, _vp, _vp, _i, _vp],
+    "gp_bn_apply_act_pair": [_vp, _vp, _vp, _ll, _i, _vp, _vp, _i, _vp],
+    "gp_pair_to_f16": [_vp, _vp, _ll, _vp, _ll, _ll, _i, _vp],
     "gp_bn_bwd_reduce_f32": [_vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
     "gp_bn_bwd_apply_f32": [_vp, _vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _vp],
     "gp_im2col_k4s2_split": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
@@ -694,6 +708,41 @@ def bn_bwd_apply_f32(da, y, fin, red, count, act):
     check(_fn("gp_bn_bwd_apply_f32")(_p(da), _p(y), _p(dy), y.numel() // C, C, _p(fin[2]), _p(fin[3]), _p(fin[0]), _p(fin[1]),
                                      _p(red[0]), _p(red[1]), float(count), act, _stream()), "gp_bn_bwd_apply_f32")
     return dy
+
+
+def pair_to_f16(hi, lo, rows, cols, ld_in, out=None):
+    """fp16(hi + lo) of a hi/lo bf16 pair stored with row pitch ld_in -> fp16 [rows, cols] (the single-MMA operand of the
+    fp16 mode). hi / lo may be views into one staging buffer (e.g. the hi | lo halves of a packed weight row)."""
+    if hi.dtype != torch.bfloat16 or lo.dtype != torch.bfloat16 or not hi.is_cuda:
+        raise _lib.GpError("pair_to_f16: hi / lo must be CUDA bf16 tensors")
+    if out is None:
+        out = torch.empty((rows, cols), device=hi.device, dtype=torch.float16)
+    check(_fn("gp_pair_to_f16")(_p(hi), _p(lo), ld_in, _p(out), cols, rows, cols, _stream()), "gp_pair_to_f16")
+    return out
+
+
+def conv_weight_f16(w, n_dim):
+    """w fp32 (D0, D1, kh, kw) -> fp16 [N, taps*C] (same row layout as pack_conv_weight)."""
+    wp = split_conv_weight(w, n_dim)                     # [N, 2*K]: hi block | lo block per row
+    K = wp.shape[1] // 2
+    return pair_to_f16(wp, wp[:, K:], wp.shape[0], K, 2 * K)
+
+
+def weight_matrix_f16(src, R, K, Rpad, Kp, s_r, s_k, perm=1):
+    """fp32 matrix -> fp16 [Rpad, Kp] (same arguments as split_weight_matrix / pack_matrix)."""
+    wp = split_weight_matrix(src, R, K, Rpad, Kp, s_r, s_k, perm)
+    return pair_to_f16(wp, wp[:, Kp:], Rpad, Kp, 2 * Kp)
+
+
+def bn_apply_act_pair(y, fin, act):
+    """act(y * scale + shift) stored as (bf16, fp16) copies of the same value."""
+    _chk(y, torch.float32, "y")
+    C = y.shape[-1]
+    b = torch.empty(y.shape, device=y.device, dtype=torch.bfloat16)
+    h = torch.empty(y.shape, device=y.device, dtype=torch.float16)
+    check(_fn("gp_bn_apply_act_pair")(_p(y), _p(b), _p(h), y.numel() // C, C, _p(fin[2]), _p(fin[3]), act, _stream()),
+          "gp_bn_apply_act_pair")
+    return b, h
 
 
 def im2col_k4s2_split(img):

@@ -68,7 +68,12 @@ typedef struct {
   const void* in_lo;      /* low halves of the input (same layout as `in`); then w is [Nout][2][taps][Cin] (hi | lo) */
   void* out_lo;           /* optional: also write bf16(v - bf16(v)) here (hi/lo output pair)                        */
   float* out_f32;         /* optional: write fp32 here instead of bf16 `out` (pre-BatchNorm outputs)                */
+  /* "fp16" forward precision mode (ONE MMA on fp16 operands: 11 significant bits instead of bf16's 8): */
+  int32_t flags;          /* GP_CONV_IN_F16: `in` and `w` hold fp16 (same layouts; in_lo must be NULL);
+                             GP_CONV_LO_F16: out_lo receives fp16(v) — the next layer's operand — instead of the residual */
 } gp_conv_fwd_t;
+#define GP_CONV_IN_F16 1
+#define GP_CONV_LO_F16 2
 int gp_conv_fwd(const gp_conv_fwd_t* p, void* stream);
 /* Host-only: the tile shape gp_conv_fwd would use for this problem (BN in {64,128,256} output columns, MT in {1,2}
  * 128-row sub-tiles) and the resulting number of output tiles. No pointers are dereferenced, nothing is launched. */
@@ -234,6 +239,14 @@ int gp_proj_head_bwd(const float* dout, const float* h, const float* w, const fl
  * gp_split_conv_weight: like gp_pack_conv_weight, dst bf16 [N][2][taps][C] (hi block | lo block per row)
  * gp_bn_*_f32 / _split : the BatchNorm kernels above with y in fp32 and the activation written as a hi/lo pair
  * gp_im2col_k4s2_split / gp_col2im_k4s2_f32 / gp_head_fwd_split: image-side layers and head on those formats. */
+/* "fp16" mode staging: out[r*ld_out + k] = fp16(hi[r*ld_in + k] + lo[r*ld_in + k]) for r < rows, k < cols — turns any
+ * hi/lo bf16 pair produced by the kernels above (weights, im2col columns, latent rows) into the single fp16 operand.
+ * gp_bn_apply_act_pair: gp_bn_apply_act_split with the second output = fp16(v) (operand of the next forward GEMM) next to
+ * the bf16(v) the backward GEMMs read. */
+int gp_pair_to_f16(const void* hi, const void* lo, long long ld_in, void* out, long long ld_out, long long rows, int cols,
+                   void* stream);
+int gp_bn_apply_act_pair(const float* y, void* out_bf16, void* out_f16, long long P, int C, const float* scale,
+                         const float* shift, int act, void* stream);
 int gp_split_matrix(const float* src, void* dst, int R, int K, int Rpad, int ld, int width, long long s_r, long long s_k,
                     int perm, long long lo_off, void* stream);
 int gp_split_conv_weight(const float* src, void* dst, int D0, int D1, int taps, int n_dim, void* stream);

@@ -34,10 +34,12 @@ BARS = {
     #            act    cos D-real  cos D-fake  cos G-step
     "bf16x3": (1e-2, 0.999, 0.999, 0.999),
     "bf16": (2e-2, 0.999, 0.99, 0.95),
+    # one MMA on fp16 operands: meets every bar except the G step's (emulated 0.99677, tools/precision_study.py)
+    "fp16": (5e-3, 0.999, 0.999, 0.99),
 }
 
 
-@pytest.mark.parametrize("mode", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("mode", ["bf16x3", "bf16", "fp16"])
 def test_dcgan64_step_meets_precision_bars(mode, reference_step):
     from gan_playground_b200 import config
     from gan_playground_b200.criterion import GANLoss
@@ -110,5 +112,53 @@ def test_mixed_policy_real_pass_in_bf16_meets_the_bars(reference_step):
         print("\n[mixed] D(x) act err %.2e | cos: D-real (bf16 pass) %.6f  D real+fake accumulated %.6f" % (e1, g1, g12))
         assert e1 < 1e-2 and g1 > 0.999 and g12 > 0.999
         assert abs(loss.item() - ref["loss_real"].item()) < 0.02 * ref["loss_real"].item()
+    finally:
+        config.set_precision(prev)
+
+
+def test_fp16_fake_chain_policy_meets_the_bars(reference_step):
+    """engine.DcganStep(fake_precision="fp16"): the D-fake chain G(z1) -> D(G(z1).detach()) runs ONE MMA on fp16 operands,
+    the real pass plain bf16, only the G step bf16x3. What optD.step() consumes — the accumulated real + fake D gradient —
+    and the D-fake pass alone must meet the north_star bars; the G step is untouched by the policy."""
+    from gan_playground_b200 import config
+    from gan_playground_b200.criterion import GANLoss
+    from gan_playground_b200.models import dcgan
+
+    sd_g, sd_d, x, z1, z2, ref = reference_step
+    prev = config.precision()
+    config.set_precision("bf16x3")
+    try:
+        netG, netD = quiet(lambda: dcgan.Generator()).cuda(), quiet(lambda: dcgan.Discriminator()).cuda()
+        netG.load_state_dict(sd_g), netD.load_state_dict(sd_d)
+        crit = GANLoss("vanilla", 0.9, 0.1, 0.9).cuda()
+        with config.precision_scope("bf16"):
+            out = netD(x.cuda())
+        crit(out, True).backward()
+        g_real = {k: p.grad.detach().clone() for k, p in netD.named_parameters() if p.grad is not None}
+        with config.precision_scope("fp16"):
+            fake = netG(z1.cuda())
+            out = netD(fake.detach())
+        lf = crit(out, False)
+        lf.backward()                                     # accumulates onto the real-pass gradients
+        e2, e3 = relerr(fake, ref["fake1"]), relerr(out, ref["d_fake"])
+        both = {k: ref["d_grads_real"][k] + ref["d_grads_fake"][k] for k in ref["d_grads_real"]}
+        g12 = global_cos(netD.named_parameters(), both)
+        only_fake = {k: p.grad.detach() - g_real[k] for k, p in netD.named_parameters() if k in g_real}
+
+        class _P:   # global_cos reads .grad
+            def __init__(self, g):
+                self.grad = g
+        g2 = global_cos({k: _P(v) for k, v in only_fake.items()}.items(), ref["d_grads_fake"])
+        l2 = abs(lf.item() - ref["loss_fake"].item()) / ref["loss_fake"].item()
+        print("\n[fp16 fake chain] act err G(z) %.2e D(G(z)) %.2e | cos: D-fake %.6f  D real+fake accumulated %.6f | loss rel %.2e"
+              % (e2, e3, g2, g12, l2))
+        assert max(e2, e3) < 1e-2 and g2 > 0.999 and g12 > 0.999 and l2 < 0.02
+        # the G step afterwards runs in the global bf16x3 mode on the same nets (fp16-staged weights do not leak into it)
+        netG.zero_grad(), netD.zero_grad()
+        out = netD(netG(z2.cuda()))
+        crit(out, False, True).backward()
+        g3 = global_cos(netG.named_parameters(), ref["g_grads"])
+        print("[fp16 fake chain] G step after it (bf16x3): cos %.6f" % g3)
+        assert g3 > 0.999
     finally:
         config.set_precision(prev)
