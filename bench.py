@@ -274,11 +274,12 @@ def main():
     peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     # DRAM bytes moved by the same 53 GEMM launches of one step, from the committed ncu launch list of this command
     # (profiles/ncu_gemm_traffic.json; only valid for the configuration it was captured on)
+    precision_label = config.precision() + (" (real-image D pass: bf16)" if runner.real_precision else "") + \
+        (" (D-fake chain: %s)" % runner.fake_precision if runner.fake_precision else "")
     traffic, traffic_src = None, None
     try:
         tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_gemm_traffic.json")))
-        if world == 1 and tj.get("global_batch") == global_batch and tj.get("precision", "").startswith(config.precision()) \
-                and (" (real" in tj.get("precision", "")) == bool(runner.real_precision):
+        if world == 1 and tj.get("global_batch") == global_batch and tj.get("precision", "") == precision_label:
             traffic, traffic_src = tj["dram_bytes_per_step_gemm"], tj["source"]
     except (OSError, ValueError, KeyError):
         pass
@@ -297,7 +298,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": global_batch, "per_gpu_batch": per_gpu,
-                       "parallelism": "dp%d" % world, "precision": config.precision() + (" (real-image D pass: bf16)" if runner.real_precision else "") + (" (D-fake chain: %s)" % runner.fake_precision if runner.fake_precision else ""),
+                       "parallelism": "dp%d" % world, "precision": precision_label,
                        "cuda_graph": use_graph,
                        "optimizer": "torch.optim.Adam" if args.torch_adam else "FusedAdam(flat%s)" % (", zero1" if world > 1 else ""),
                        "syncbn": "n/a (1 rank)" if world == 1 else ("one-shot NVLink peer exchange fused with the statistics finalize"
