@@ -49,6 +49,8 @@ def operand(x, fmt):
         return q(x)
     if fmt == 16:
         return split16(x)
+    if fmt == "h+8":               # storage of an activation whose consumers split it themselves: ~16+ bits
+        fmt = "hh"
     hi = x.half().float()
     return hi if fmt == "h" else hi + (x - hi).half().float()
 
@@ -70,15 +72,34 @@ class RoundGrad(torch.autograd.Function):
         return q(g)
 
 
+def q8(x):
+    """e4m3 with a per-tensor power-of-two scale that puts the largest magnitude near the top of the format's range (a
+    separate accumulator / block scale would undo it exactly); 4 significant bits."""
+    m = x.abs().max().item()
+    if m == 0.0:
+        return x
+    s = 2.0 ** (8 - int(torch.ceil(torch.log2(torch.tensor(m))).item()))      # max |x| * s in (128, 256]
+    return (x * s).to(torch.float8_e4m3fn).float() / s
+
+
+def product(X, W, op, fmt):
+    """fmt "h+8": main product on fp16 operands + the two first-order correction products x_lo*w_hi and x_hi*w_lo on
+    e4m3 operands (kind::f8f6f4 runs at twice the 16-bit rate, so the three products cost two 16-bit MMAs)."""
+    xh, wh = X.half().float(), W.half().float()
+    return op(xh, wh) + op(q8(X - xh), q8(wh)) + op(q8(xh), q8(W - wh))
+
+
 class ConvEmu(torch.autograd.Function):
     """conv / conv-transpose (k4 s2 p1) or linear with operand precisions (xbits, wbits) in {8, 16}; backward with single
     bf16 operands: dx = dgrad(q(dy), q(w)), dw = wgrad(q(dy), q(x)) in fp32 accumulation."""
 
     @staticmethod
     def forward(ctx, x, w, kind, xbits, wbits):
-        X, W = operand(x, xbits), operand(w, wbits)
         ctx.kind = kind
         ctx.save_for_backward(q(x), q(w))
+        if xbits == "h+8":
+            return product(x, w, lambda a, b: ConvEmu.op(a, b, kind), xbits)
+        X, W = operand(x, xbits), operand(w, wbits)
         return ConvEmu.op(X, W, kind)
 
     @staticmethod
@@ -183,7 +204,8 @@ def mmas(P, fake_passes_only=True):
     layers have equal FLOPs, the image-side ones are negligible)"""
     big = ["g0", "g1", "g2", "d1", "d2", "d3"]
     n = {8: 1, "h": 1, 16: 2, "hh": 2}
-    return sum(n[P[k]["x"]] * n[P[k]["w"]] - (n[P[k]["x"]] * n[P[k]["w"]] == 4) for k in big) / len(big)
+    return sum(2 if P[k]["x"] == "h+8" else n[P[k]["x"]] * n[P[k]["w"]] - (n[P[k]["x"]] * n[P[k]["w"]] == 4)
+               for k in big) / len(big)
 
 
 POLICIES = {
@@ -203,6 +225,8 @@ POLICIES = {
     "fp16 x, fp16 hi+lo w (2 MMA), y fp32": policy(BF16, all=dict(x="h", w="hh", y="f32", a="h", col="f32")),
     "fp16 hi+lo x, fp16 w (2 MMA), y fp32": policy(BF16, all=dict(x="hh", w="h", y="f32", a="hh", col="f32")),
     "fp16x3 (3 MMA), y fp32": policy(BF16, all=dict(x="hh", w="hh", y="f32", a="hh", col="f32")),
+    # main product fp16 + both correction products on e4m3 operands at the doubled fp8 rate (2 MMA-equivalents)
+    "fp16 + 2 x e4m3 corrections (2 MMA-eq)": policy(BF16, all=dict(x="h+8", w="h+8", y="f32", a="h+8", col="f32")),
 }
 
 
