@@ -487,12 +487,20 @@ def key_lists(mods):
         out["dcgan.Discriminator"] = desc(mods["dcgan"].Discriminator())
         out["dcgan.Generator@32"] = desc(mods["dcgan"].Generator(resolution=32))
         out["dcgan.Discriminator@32"] = desc(mods["dcgan"].Discriminator(resolution=32))
+        out["dcgan.Generator@128"] = desc(mods["dcgan"].Generator(ngf=8, resolution=128))
+        out["dcgan.Discriminator@128"] = desc(mods["dcgan"].Discriminator(ndf=8, resolution=128))
+        out["dcgan_specnorm.Generator"] = desc(mods["dcgan_specnorm"].Generator(ngf=8))
+        out["dcgan_specnorm.Discriminator"] = desc(mods["dcgan_specnorm"].Discriminator(ndf=8))
         out["dcgan_specnorm.Generator@32"] = desc(mods["dcgan_specnorm"].Generator(resolution=32))
         out["dcgan_specnorm.Discriminator@32"] = desc(mods["dcgan_specnorm"].Discriminator(resolution=32))
         out["sngan_projection.ResNetGenerator"] = desc(mods["sngan_projection"].ResNetGenerator(n_classes=10, bottom_width=2))
         out["sngan_projection.SNResNetProjectionDiscriminator"] = desc(mods["sngan_projection"].SNResNetProjectionDiscriminator(n_classes=10))
         out["acgan.Generator"] = desc(mods["acgan"].Generator())
         out["acgan.Discriminator"] = desc(mods["acgan"].Discriminator())
+        out["acgan.Generator@32c5"] = desc(mods["acgan"].Generator(ngf=8, resolution=32, n_class=5))
+        out["acgan.Discriminator@32c5"] = desc(mods["acgan"].Discriminator(ndf=8, resolution=32, n_class=5))
+        out["sngan_projection.ResNetGenerator@uncond"] = desc(mods["sngan_projection"].ResNetGenerator(ch=8, n_classes=0))
+        out["sngan_projection.SNResNetProjectionDiscriminator@uncond"] = desc(mods["sngan_projection"].SNResNetProjectionDiscriminator(ch=8, n_classes=0))
         out["dcgan_blur.Generator"] = desc(mods["dcgan_blur"].Generator())
         out["dcgan_blur.Discriminator"] = desc(mods["dcgan_blur"].Discriminator())
         out["dcgan_blur.Generator@32"] = desc(mods["dcgan_blur"].Generator(resolution=32))

@@ -27,6 +27,35 @@ def test_state_dict_layout_matches_reference(name, ctor, capsys):
     assert describe(ctor()) == KEYS[name]
 
 
+def _family_ctors():
+    from gan_playground_b200.models import acgan, dcgan_specnorm, sngan_projection as S
+
+    return {
+        "dcgan.Generator@128": lambda: dcgan.Generator(ngf=8, resolution=128),
+        "dcgan.Discriminator@128": lambda: dcgan.Discriminator(ndf=8, resolution=128),
+        "dcgan_specnorm.Generator": lambda: dcgan_specnorm.Generator(ngf=8),
+        "dcgan_specnorm.Discriminator": lambda: dcgan_specnorm.Discriminator(ndf=8),
+        "dcgan_specnorm.Generator@32": lambda: dcgan_specnorm.Generator(resolution=32),
+        "dcgan_specnorm.Discriminator@32": lambda: dcgan_specnorm.Discriminator(resolution=32),
+        "sngan_projection.ResNetGenerator": lambda: S.ResNetGenerator(n_classes=10, bottom_width=2),
+        "sngan_projection.SNResNetProjectionDiscriminator": lambda: S.SNResNetProjectionDiscriminator(n_classes=10),
+        "sngan_projection.ResNetGenerator@uncond": lambda: S.ResNetGenerator(ch=8, n_classes=0),
+        "sngan_projection.SNResNetProjectionDiscriminator@uncond": lambda: S.SNResNetProjectionDiscriminator(ch=8, n_classes=0),
+        "acgan.Generator": lambda: acgan.Generator(),
+        "acgan.Discriminator": lambda: acgan.Discriminator(),
+        "acgan.Generator@32c5": lambda: acgan.Generator(ngf=8, resolution=32, n_class=5),
+        "acgan.Discriminator@32c5": lambda: acgan.Discriminator(ndf=8, resolution=32, n_class=5),
+    }
+
+
+@pytest.mark.parametrize("name", sorted(_family_ctors()))
+def test_state_dict_layout_of_every_family_matches_reference(name, capsys):
+    """Keys, shapes and dtypes in state_dict() order for the other constructors / variants of SURVEY.md §8b: resolution 128,
+    spectral-norm nets (weight_orig / weight_u / weight_v), the projection pair with and without classes, ACGAN with a
+    non-default class count."""
+    assert describe(_family_ctors()[name]()) == KEYS[name]
+
+
 @pytest.mark.parametrize("name,res", [("dcgan_blur.Generator", 64), ("dcgan_blur.Discriminator", 64),
                                       ("dcgan_blur.Generator@32", 32), ("dcgan_blur.Discriminator@32", 32)])
 def test_dcgan_blur_state_dict_layout_matches_reference(name, res, capsys):
