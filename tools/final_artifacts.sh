@@ -7,6 +7,8 @@ timeout 600 python -m pytest tests -q -m gpu > $O/final_pytest_gpu.log 2>&1; ech
 timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > $O/final_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $O/final_smoke.log
 timeout 300 python bench.py --steps 20 --warmup 5 > $O/final_bench_n1_bf16x3.json 2> $O/final_bench_n1_bf16x3.err; echo "bench x3 rc=$?"
 GP_PRECISION=bf16 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $O/final_bench_n1_bf16.json 2> $O/final_bench_n1_bf16.err; echo "bench bf16 rc=$?"
+GP_FAKE_PRECISION=bf16x3 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $O/final_bench_n1_bf16x3_all_fake_passes.json 2> /dev/null; echo "bench x3-everywhere rc=$?"
+timeout 200 python tools/bench_loops.py --steps 20 --warmup 5 > $O/final_bench_loops.jsonl 2> /dev/null; echo "bench loops rc=$?"
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $O/final_bench_reference.json 2> $O/final_bench_reference.err; echo "reference arm rc=$?"
 for p in bf16x3 bf16; do timeout 120 python tools/step_breakdown.py --batch 1024 --precision $p --gemms --out $O/final_breakdown_${p}.log > /dev/null 2>&1; done
 timeout 120 python tools/prof_gemm.py --reps 10 > $O/final_gemm_microbench.log 2>&1

@@ -35,6 +35,10 @@ def main():
     cases["d1_fwd"] = lambda: ops.conv_fwd(X["a128"], W["d1"], Bv[256], ops.KIND_CONV_K4S2, 16, 16)
     cases["d1_fwd_x3"] = lambda: ops.conv_fwd(X["a128"], W["d1x3"], Bv[256], ops.KIND_CONV_K4S2, 16, 16, x_lo=X["a128_lo"],
                                               out_mode="f32", stats=torch.zeros(2, 256, device=dev))
+    # the same layer on fp16 operands (one MMA, fp32 output + fused statistics): the "fp16" forward mode
+    cases["d1_fwd_f16"] = lambda: ops.conv_fwd(X["a128"].to(torch.float16), W["d1"].to(torch.float16), Bv[256],
+                                               ops.KIND_CONV_K4S2, 16, 16, fp16_in=True, out_mode="f32",
+                                               stats=torch.zeros(2, 256, device=dev))
     cases["d1_fwd_stats"] = lambda: ops.conv_fwd(X["a128"], W["d1"], Bv[256], ops.KIND_CONV_K4S2, 16, 16,
                                                  stats=torch.zeros(2, 256, device=dev))
     cases["g2_fwd_stats"] = lambda: ops.conv_fwd(X["a256_16"], W["g2"], Bv[128], ops.KIND_CONVT_K4S2, 32, 32,
