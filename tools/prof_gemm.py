@@ -36,7 +36,7 @@ def main():
     cases["d1_fwd_x3"] = lambda: ops.conv_fwd(X["a128"], W["d1x3"], Bv[256], ops.KIND_CONV_K4S2, 16, 16, x_lo=X["a128_lo"],
                                               out_mode="f32", stats=torch.zeros(2, 256, device=dev))
     # the same layer on fp16 operands (one MMA, fp32 output + fused statistics): the "fp16" forward mode
-    cases["d1_fwd_f16"] = lambda: ops.conv_fwd(X["a128"].to(torch.float16), W["d1"].to(torch.float16), Bv[256],
+    cases["d1_fwd_f16"] = lambda: ops.conv_fwd(X["a128_h"], W["d1_h"], Bv[256],
                                                ops.KIND_CONV_K4S2, 16, 16, fp16_in=True, out_mode="f32",
                                                stats=torch.zeros(2, 256, device=dev))
     cases["d1_fwd_stats"] = lambda: ops.conv_fwd(X["a128"], W["d1"], Bv[256], ops.KIND_CONV_K4S2, 16, 16,
@@ -58,6 +58,7 @@ def main():
     W = {"d1x3": wt(256, 2 * 16 * 128), "img": wt(128, 64), "imgT": wt(64, 128), "d1": wt(256, 16 * 128), "g2": wt(128, 16 * 256),
          "d3": wt(1024, 16 * 512),
          "d2": wt(512, 16 * 256), "g0": wt(512, 16 * 1024), "g1": wt(256, 16 * 512)}
+    X["a128_h"], W["d1_h"] = X["a128"].to(torch.float16), W["d1"].to(torch.float16)
     Bv = {n: torch.randn(n, device=dev) * 0.1 for n in (128, 256, 512, 1024)}
 
     for name in args.cases.split(","):
