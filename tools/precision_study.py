@@ -270,13 +270,81 @@ def run(P, sd_g, sd_d, x, z1, z2, ref):
     return out
 
 
+def trace(args):
+    """200-step loss traces (loop of main_dcgan.py:68-95 with Adam, as tests/test_gpu_trace.py: width 16, 32x32, batch 32)
+    under EMULATED per-pass precision policies against the fp32 oracle, with the fp32 1e-6-perturbation control — the
+    protocol of SURVEY.md §7.3: 200-step mean and 50-step moving average within 2 %, early point-wise deviation against
+    the control. `mixed` is engine.DcganStep's policy: real pass bf16, D-fake chain fp16 (1 MMA), G step bf16x3."""
+    from gan_playground_b200.models import dcgan
+
+    STEPS, B, RES, W = args.steps, 32, 32, 16
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        netG, netD = dcgan.Generator(ngf=W, resolution=RES), dcgan.Discriminator(ndf=W, resolution=RES)
+    sd_g = {k: v.clone() for k, v in netG.state_dict().items()}
+    sd_d = {k: v.clone() for k, v in netD.state_dict().items()}
+    gen = torch.Generator().manual_seed(11)
+    xs = torch.rand(STEPS, B, 3, RES, RES, generator=gen) * 2 - 1
+    zs = torch.randn(STEPS, 2, B, 100, generator=gen)
+
+    def run_oracle(perturb):
+        tr = O.CpuDcganTrainer(sd_g, sd_d)
+        return torch.tensor([tr.step(xs[i] + (perturb if i == 0 else 0.0), zs[i, 0], zs[i, 1])[:3] for i in range(STEPS)])
+
+    def run_emulated(p_real, p_fake, p_g):
+        pg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd_g.items()}
+        pd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd_d.items()}
+        og = torch.optim.Adam([v for v in pg.values() if v.requires_grad], lr=4e-4, betas=(0.5, 0.999))
+        od = torch.optim.Adam([v for v in pd.values() if v.requires_grad], lr=1e-4, betas=(0.5, 0.999))
+        loss = lambda p, real, g=False: O.gan_loss("vanilla", p, real, g, 0.9, 0.1, 0.9)
+        out = []
+        for i in range(STEPS):
+            od.zero_grad()
+            l1 = loss(discriminator(pd, xs[i], p_real), True)
+            l1.backward()
+            with torch.no_grad():
+                fake = generator(pg, zs[i, 0], p_fake)
+            l2 = loss(discriminator(pd, fake, p_fake), False)
+            l2.backward()
+            od.step()
+            og.zero_grad()
+            l3 = loss(discriminator(pd, generator(pg, zs[i, 1], p_g), p_g), False, True)
+            l3.backward()
+            og.step()
+            out.append([l1.item(), l2.item(), l3.item()])
+        return torch.tensor(out)
+
+    def moving_avg(t, k=min(50, STEPS)):
+        c = torch.cumsum(torch.cat([torch.zeros(1, t.shape[1]), t]), 0)
+        return (c[k:] - c[:-k]) / k
+
+    rel = lambda a, b: ((a - b).abs() / b.abs().clamp_min(1e-6)).max().item()
+    ref, ctl = run_oracle(0.0), run_oracle(1e-6)
+    H = dict(x="h", w="h", y="f32", a="h", col="f32")
+    runs = {"fp32 control (1e-6 perturbation)": ctl,
+            "mixed: real bf16 / fake chain fp16 / G step bf16x3": run_emulated(policy(BF16), policy(BF16, all=H), policy(X3)),
+            "bf16x3 on every pass": run_emulated(policy(X3), policy(X3), policy(X3)),
+            "bf16 on every pass": run_emulated(policy(BF16), policy(BF16), policy(BF16))}
+    print("%d-step loss traces vs the fp32 oracle, max over (lossD_real, lossD_fake, lossG) of the relative deviation" % STEPS)
+    print("%-52s %10s %14s %16s %12s" % ("run (emulated roundings)", "mean", "50-step avg", "first 20 steps", "all steps"))
+    for name, t in runs.items():
+        print("%-52s %9.3f%% %13.3f%% %15.3f%% %11.3f%%" % (
+            name, 100 * rel(t.mean(0), ref.mean(0)), 100 * rel(moving_avg(t), moving_avg(ref)),
+            100 * rel(t[:20], ref[:20]), 100 * rel(t, ref)), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--width", type=int, default=64)
     ap.add_argument("--only", default="")
     ap.add_argument("--sweep", action="store_true", help="per-layer sensitivity: one layer fp16 1-MMA / rest bf16x3 and back")
+    ap.add_argument("--trace", action="store_true", help="200-step loss traces under the per-pass policies instead of the one-step study")
+    ap.add_argument("--steps", type=int, default=200)
     args = ap.parse_args()
+    torch.set_num_threads(os.cpu_count())
+    if args.trace:
+        return trace(args)
     from gan_playground_b200.models import dcgan
 
     torch.set_num_threads(os.cpu_count())
