@@ -26,8 +26,10 @@ def algorithmic_bytes(name, a):
         return a[1] * a[2] * 4
     if name == "gp_bn_apply_act":
         return a[2] * a[3] * 4
-    if name == "gp_bn_apply_act_split":
+    if name in ("gp_bn_apply_act_split", "gp_bn_apply_act_pair"):
         return a[3] * a[4] * 8
+    if name == "gp_pair_to_f16":      # (hi, lo, ld_in, out, ld_out, rows, cols): two bf16 reads + one fp16 write
+        return a[5] * a[6] * 6
     if name == "gp_bn_bwd_reduce":
         return a[2] * a[3] * 4
     if name == "gp_bn_bwd_reduce_f32":
