@@ -362,9 +362,14 @@ class AcganStep(_AdversarialStep):
     N_SCALARS = 7
 
     def __init__(self, netG, netD, criterion_adv, optG, optD, batch, z_dim, device, n_class=10, aux_weight=0.5,
-                 use_graph=False, warmup=3, overlap=True):
+                 use_graph=False, warmup=3, overlap=True, mixed_precision=False):
         super().__init__(netG, netD, optG, optD, batch, device, use_graph, warmup, overlap)
         self.crit = criterion_adv if isinstance(criterion_adv, ACGANLoss) else ACGANLoss(criterion_adv, aux_weight)
+        # per-pass forward precision as in DcganStep — OPT-IN here (not yet measured on the GPU for this loop): real pass
+        # bf16, D's pass over the detached fake batch single-MMA fp16; the one generator forward feeds the G step, so it
+        # and the G step's D pass stay in the global mode
+        mixed = mixed_precision and config.x3()
+        self.real_precision, self.fake_precision = ("bf16", "fp16") if mixed else (None, None)
         self.z_dim, self.n_class = z_dim, n_class
         self.x_static = torch.zeros(batch, netD.img_dim, netD.resolution, netD.resolution, device=device)
         self.y_static = torch.zeros(batch, n_class, device=device)
@@ -379,12 +384,14 @@ class AcganStep(_AdversarialStep):
         netG, netD, crit = self.netG, self.netD, self.crit
         (img_real, lbl_real), (z,) = data, noise
         self._zero(self.optD, self.bucketD)
-        real = crit(netD.packed_logits(img_real), lbl_real, True)
+        with config.precision_scope(self.real_precision or config.precision()):
+            real = crit(netD.packed_logits(img_real), lbl_real, True)
         real[crit.TOTAL].backward()
         log(4, real[crit.SIGMOID_MEAN].detach())
         c = lbl_real
         outG = netG(z, c)
-        fake = crit(netD.packed_logits(outG.detach()), c, False)
+        with config.precision_scope(self.fake_precision or config.precision()):
+            fake = crit(netD.packed_logits(outG.detach()), c, False)
         fake[crit.TOTAL].backward()
         log(5, fake[crit.SIGMOID_MEAN].detach())
         self._step(self.optD, self.bucketD)

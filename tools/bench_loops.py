@@ -87,12 +87,14 @@ def cfg5(dev, batch):
     netD = quiet(lambda: M.Discriminator(ndf=64, n_class=10)).to(dev)
     oG = FusedAdam(netG.parameters(), lr=4e-4, betas=(0.5, 0.999))
     oD = FusedAdam(netD.parameters(), lr=1e-4, betas=(0.5, 0.999))
-    run = AcganStep(netG, netD, GANLoss("vanilla", 0.9, 0.1, 0.9).to(dev), oG, oD, batch, 100, dev, use_graph=True)
+    run = AcganStep(netG, netD, GANLoss("vanilla", 0.9, 0.1, 0.9).to(dev), oG, oD, batch, 100, dev, use_graph=True,
+                    mixed_precision=MIXED["acgan"])
     x = torch.rand(batch, 3, 64, 64, device=dev) * 2 - 1
     y = torch.randint(0, 2, (batch, 10), device=dev).float()
     return (lambda: run.step(x, y)), 8.979e9, "ACGAN 64x64 two-head, main_acgan loop"
 
 
+MIXED = {"acgan": False}      # --acgan-mixed: AcganStep's opt-in per-pass precision policy (real bf16 / D-fake fp16)
 CONFIGS = {"cfg3": (cfg3, 512), "cfg4": (cfg4, 256), "cfg5": (cfg5, 512)}
 
 
@@ -102,7 +104,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--only", default="")
     ap.add_argument("--batch", type=int, default=0, help="override the per-configuration batch")
+    ap.add_argument("--acgan-mixed", action="store_true", help="cfg5 with AcganStep(mixed_precision=True)")
     args = ap.parse_args()
+    MIXED["acgan"] = args.acgan_mixed
     from gan_playground_b200 import _lib, config
 
     dev = torch.device("cuda", 0)
@@ -117,7 +121,8 @@ def main():
             ms, last = timed(step, args.steps, max(args.warmup, 3))
             print(json.dumps({"config": name, "workload": what, "batch": batch, "ms_per_step": ms,
                               "images_per_sec": batch / ms * 1e3, "steps_per_sec": 1e3 / ms,
-                              "tflops_minimal_step": flops_img * batch / ms * 1e-9, "precision": config.precision(),
+                              "tflops_minimal_step": flops_img * batch / ms * 1e-9,
+                              "precision": config.precision() + (" (mixed per-pass policy)" if name == "cfg5" and args.acgan_mixed else ""),
                               "cuda_graph": True, "steps": args.steps, "gpu_launches_incl_capture": _lib.launch_count() - l0,
                               "last_logged": last}), flush=True)
         except Exception as e:  # keep going: the other configurations are independent
