@@ -4,6 +4,7 @@
 set -u
 O=gpurun_out
 timeout 600 python -m pytest tests -q -m gpu > $O/final_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 $O/final_pytest_gpu.log
+GP_EXTENDED_TESTS=1 timeout 300 python -m pytest tests/test_gpu_trace.py -q -s > $O/final_pytest_gpu_extended.log 2>&1; echo "extended rc=$?"; grep -i "engine mixed\|passed\|failed" $O/final_pytest_gpu_extended.log
 timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > $O/final_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $O/final_smoke.log
 timeout 300 python bench.py --steps 20 --warmup 5 > $O/final_bench_n1_bf16x3.json 2> $O/final_bench_n1_bf16x3.err; echo "bench x3 rc=$?"
 GP_PRECISION=bf16 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $O/final_bench_n1_bf16.json 2> $O/final_bench_n1_bf16.err; echo "bench bf16 rc=$?"
