@@ -244,7 +244,9 @@ class DcganStep(_AdversarialStep):
         # tests/test_gpu_precision.py). GP_FAKE_PRECISION / fake_precision= override ("bf16x3" = no special case).
         self.real_precision = "bf16" if (mixed_precision and config.x3()) else None
         if fake_precision is None:
-            fake_precision = os.environ.get("GP_FAKE_PRECISION", "") or "fp16"
+            # default only for the family it was measured on (models/dcgan.py nets); SN-DCGAN / others keep the global mode
+            measured = all(type(n).__module__.endswith("models.dcgan") for n in (netG, netD))
+            fake_precision = os.environ.get("GP_FAKE_PRECISION", "") or ("fp16" if measured else "bf16x3")
         self.fake_precision = fake_precision if (mixed_precision and config.x3() and fake_precision != "bf16x3") else None
 
     def _draw_noise(self):
