@@ -270,6 +270,76 @@ def run(P, sd_g, sd_d, x, z1, z2, ref):
     return out
 
 
+def acgan_study(args):
+    """The same one-step study for the ACGAN loop (main_acgan.py:84-133: one generator forward per iteration, adversarial
+    BCE + 0.5 x MSE on the auxiliary head): does AcganStep's opt-in per-pass policy — real pass bf16, D's pass over the
+    DETACHED fake batch fp16 (1 MMA), generator forward and G step bf16x3 — keep the bars? Reported per pass and for the
+    accumulated real + fake discriminator gradient that optD.step() consumes."""
+    from gan_playground_b200.models import acgan
+
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        netG, netD = acgan.Generator(ngf=args.width, n_class=10), acgan.Discriminator(ndf=args.width, n_class=10)
+    sd_g = {k: v.clone() for k, v in netG.state_dict().items()}
+    sd_d = {k: v.clone() for k, v in netD.state_dict().items()}
+    gen = torch.Generator().manual_seed(1)
+    B = args.batch
+    x = torch.rand(B, 3, 64, 64, generator=gen) * 2 - 1
+    y = torch.randint(0, 2, (B, 10), generator=gen).float()
+    z = torch.randn(B, 100, generator=gen)
+
+    def gen_emu(sd, z, y, P):
+        h = store_act(conv_emu(torch.cat([z, y], 1), sd["linear.weight"], sd["linear.bias"], "linear", P["g_lin"]), P["g_lin"])
+        h = h.view(h.size(0), -1, 4, 4)
+        for i in range(3):
+            p, pol = "blocks.%d." % i, P["g%d" % i]
+            h = bn_act(conv_emu(h, sd[p + "0.weight"], sd[p + "0.bias"], "convT", pol), sd[p + "1.weight"], sd[p + "1.bias"],
+                       "relu", pol)
+        return convT_image(h, sd["out_layer.0.weight"], sd["out_layer.0.bias"], P["g_out"])
+
+    def dis_emu(sd, x, P):
+        h = store_act(F.leaky_relu(conv_emu(x, sd["blocks.0.0.weight"], sd["blocks.0.0.bias"], "conv", P["d0"]), 0.2), P["d0"])
+        for i in range(1, 4):
+            p, pol = "blocks.%d." % i, P["d%d" % i]
+            h = bn_act(conv_emu(h, sd[p + "0.weight"], sd[p + "0.bias"], "conv", pol), sd[p + "1.weight"], sd[p + "1.bias"],
+                       "lrelu", pol)
+        h = h.sum(dim=(2, 3))
+        return F.linear(h, sd["out_layer.weight"], sd["out_layer.bias"]), F.linear(h, sd["out_aux.weight"], sd["out_aux.bias"])
+
+    def objective(adv, cls, real, g=False):
+        return O.gan_loss("vanilla", adv, real, g, 0.9, 0.1, 0.9) + 0.5 * F.mse_loss(cls, y)
+
+    def leaves(sd):
+        return {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+
+    def grads(loss, p):
+        ks = [k for k, v in p.items() if torch.is_tensor(v) and v.requires_grad]
+        return {k: g for k, g in zip(ks, torch.autograd.grad(loss, [p[k] for k in ks], allow_unused=True)) if g is not None}
+
+    def step(p_real, p_gen, p_fake, p_g, exact=False):
+        pg, pd = leaves(sd_g), leaves(sd_d)
+        G = (lambda z: O.dcgan_generator(pg, z, y, acgan=True)) if exact else (lambda z: gen_emu(pg, z, y, p_gen))
+        D = (lambda x, P: O.dcgan_discriminator(pd, x, acgan=True)) if exact else (lambda x, P: dis_emu(pd, x, P))
+        g_real = grads(objective(*D(x, p_real), True), pd)
+        fake = G(z)
+        g_fake = grads(objective(*D(fake.detach(), p_fake), False), pd)
+        g_gen = grads(objective(*D(fake, p_g), False, True), pg)
+        return g_real, g_fake, g_gen, pd, pg
+
+    ref = step(None, None, None, None, exact=True)
+    H = dict(x="h", w="h", y="f32", a="h", col="f32")
+    print("ACGAN-64 width %d batch %d, emulated: gradient cosines against the fp32 oracle" % (args.width, B))
+    print("%-58s %9s %9s %9s %9s" % ("policy", "D-real", "D-fake", "D r+f", "G-step"))
+    for name, pol in (("bf16x3 on every pass", (policy(X3),) * 4),
+                      ("mixed: real bf16 / D(fake.detach()) fp16 / G, G step bf16x3", (policy(BF16), policy(X3), policy(BF16, all=H), policy(X3))),
+                      ("bf16 on every pass", (policy(BF16),) * 4)):
+        r = step(*pol)
+        both = {k: r[0][k] + r[1][k] for k in r[0]}
+        both_ref = {k: ref[0][k] + ref[1][k] for k in ref[0]}
+        print("%-58s %9.6f %9.6f %9.6f %9.6f" % (name, cos(r[0], ref[0], r[3]), cos(r[1], ref[1], r[3]),
+                                                 cos(both, both_ref, r[3]), cos(r[2], ref[2], r[4])), flush=True)
+
+
 def trace(args):
     """200-step loss traces (loop of main_dcgan.py:68-95 with Adam, as tests/test_gpu_trace.py: width 16, 32x32, batch 32)
     under EMULATED per-pass precision policies against the fp32 oracle, with the fp32 1e-6-perturbation control — the
@@ -341,10 +411,13 @@ def main():
     ap.add_argument("--sweep", action="store_true", help="per-layer sensitivity: one layer fp16 1-MMA / rest bf16x3 and back")
     ap.add_argument("--trace", action="store_true", help="200-step loss traces under the per-pass policies instead of the one-step study")
     ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--acgan", action="store_true", help="the one-step study for the main_acgan.py loop and AcganStep's opt-in policy")
     args = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     if args.trace:
         return trace(args)
+    if args.acgan:
+        return acgan_study(args)
     from gan_playground_b200.models import dcgan
 
     torch.set_num_threads(os.cpu_count())
