@@ -12,7 +12,7 @@ per-layer POLICY = (x bits, w bits, y storage, a storage), calibrates the two sh
 on the B200 (tests/test_gpu_precision.py), and then scores cheaper candidates with the same metrics:
 activation max-rel-error and the D-real / D-fake / G-step global gradient cosines against the fp32 oracle.
 
-    python tools/precision_study.py [--batch 32] [--only name,name] [--sweep]      # a few seconds per policy
+    python tools/precision_study.py [--batch 32] [--only substring|substring] [--sweep]      # a few seconds per policy
 
 It is an analysis tool (imports oracle/: test infrastructure); nothing in the product path depends on it."""
 import argparse
@@ -139,7 +139,7 @@ def bn_act(y, gamma, beta, act, pol):
     the STORED y (bf16 or fp32); the incoming gradient of y is stored as bf16."""
     mean = y.mean(dim=(0, 2, 3))
     var = y.var(dim=(0, 2, 3), unbiased=False)
-    ys = RoundGrad.apply(ste(y, q(y)) if pol["y"] == "bf16" else y)
+    ys = RoundGrad.apply(ste(y, q(y)) if pol["y"] == "bf16" else (ste(y, y.half().float()) if pol["y"] == "f16" else y))
     xhat = (ys - mean[None, :, None, None]) * torch.rsqrt(var[None, :, None, None] + EPS)
     z = xhat * gamma[None, :, None, None] + beta[None, :, None, None]
     return store_act(F.relu(z) if act == "relu" else F.leaky_relu(z, 0.2), pol)
@@ -225,6 +225,7 @@ POLICIES = {
     "fp16 x, fp16 hi+lo w (2 MMA), y fp32": policy(BF16, all=dict(x="h", w="hh", y="f32", a="h", col="f32")),
     "fp16 hi+lo x, fp16 w (2 MMA), y fp32": policy(BF16, all=dict(x="hh", w="h", y="f32", a="hh", col="f32")),
     "fp16x3 (3 MMA), y fp32": policy(BF16, all=dict(x="hh", w="hh", y="f32", a="hh", col="f32")),
+    "fp16 operands (1 MMA), y fp16, a fp16": policy(BF16, all=dict(x="h", w="h", y="f16", a="h", col="f32")),
     # main product fp16 + both correction products on e4m3 operands at the doubled fp8 rate (2 MMA-equivalents)
     "fp16 + 2 x e4m3 corrections (2 MMA-eq)": policy(BF16, all=dict(x="h+8", w="h+8", y="f32", a="h+8", col="f32")),
 }
@@ -407,7 +408,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--width", type=int, default=64)
-    ap.add_argument("--only", default="")
+    ap.add_argument("--only", default="", help="policies whose name contains one of these |-separated substrings")
     ap.add_argument("--sweep", action="store_true", help="per-layer sensitivity: one layer fp16 1-MMA / rest bf16x3 and back")
     ap.add_argument("--trace", action="store_true", help="200-step loss traces under the per-pass policies instead of the one-step study")
     ap.add_argument("--steps", type=int, default=200)
@@ -437,7 +438,7 @@ def main():
     print("%-40s %5s | %9s %9s %9s | %9s %9s %9s" % ("policy (emulated)", "MMAs", "D(x)", "G(z)", "D(G(z))", "cos Dreal",
                                                     "cos Dfake", "cos Gstep"))
     for name, P in POLICIES.items():
-        if args.only and name not in args.only.split(","):
+        if args.only and not any(tok in name for tok in args.only.split("|")):
             continue
         t = time.time()
         r = run(P, sd_g, sd_d, x, z1, z2, ref)
