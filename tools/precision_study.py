@@ -108,6 +108,10 @@ class ConvEmu(torch.autograd.Function):
             return F.conv2d(X, W, None, stride=2, padding=1)
         if kind == "convT":
             return F.conv_transpose2d(X, W, None, stride=2, padding=1)
+        if kind == "c3":
+            return F.conv2d(X, W, None, stride=1, padding=1)
+        if kind == "c1":
+            return F.conv2d(X, W, None)
         return F.linear(X, W)
 
     @staticmethod
@@ -341,6 +345,120 @@ def acgan_study(args):
                                                  cos(both, both_ref, r[3]), cos(r[2], ref[2], r[4])), flush=True)
 
 
+def sngan_study(args):
+    """One-step study for the SNGAN projection pair (models/sngan_projection.py, loop of main_sngan.py:65-100; cfg 4:
+    ch 64, 32x32, bottom_width 2, 10 classes). The ResNet nodes (functional_resnet.py) have no BatchNorm between most
+    convs, so every conv output is STORED in the activation format and feeds the next GEMM directly: one policy =
+    (operand format, storage format) for all layers. Which one do the nodes need to meet the bars?"""
+    from gan_playground_b200.models import sngan_projection as M
+
+    torch.manual_seed(0)
+    ch, B = args.width, args.batch
+    with contextlib.redirect_stdout(io.StringIO()):
+        netG = M.ResNetGenerator(ch=ch, dim_z=128, bottom_width=2, img_dim=3, n_classes=10)
+        netD = M.SNResNetProjectionDiscriminator(ch=ch, n_classes=10, img_dim=3)
+    sd_g = {k: v.clone() for k, v in netG.state_dict().items()}
+    sd_d = {k: v.clone() for k, v in netD.state_dict().items()}
+    gen = torch.Generator().manual_seed(1)
+    x = torch.rand(B, 3, 32, 32, generator=gen) * 2 - 1
+    y = torch.randint(10, (B,), generator=gen)
+    z = torch.randn(B, 128, generator=gen)
+    c = torch.randint(10, (B,), generator=gen)
+
+    def leaves(sd):
+        return {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(("_u", "_v", "running_mean", "running_var"))
+                    else v.clone()) for k, v in sd.items()}
+
+    def st(a, pol):                     # a stored activation (no fp32 copy exists anywhere)
+        return store_act(a, pol)
+
+    def cbn(sd, p, h, lab):
+        mean, var = h.mean(dim=(0, 2, 3)), h.var(dim=(0, 2, 3), unbiased=False)
+        xhat = (h - mean[None, :, None, None]) * torch.rsqrt(var[None, :, None, None] + EPS)
+        e = F.embedding(lab, sd[p + "embed.weight"])
+        C = h.shape[1]
+        return e[:, :C, None, None] * xhat + e[:, C:, None, None]
+
+    def gen_emu(sd, z, lab, pol):
+        h = st(conv_emu(z, sd["l1.weight"], sd["l1.bias"], "linear", pol), pol).view(z.size(0), -1, 2, 2)
+        for b in ("block2.", "block3.", "block4.", "block5."):
+            a = st(F.interpolate(F.relu(cbn(sd, b + "b1.", h, lab)), scale_factor=2), pol)
+            t = st(conv_emu(a, sd[b + "c1.weight"], sd[b + "c1.bias"], "c3", pol), pol)
+            a2 = st(F.relu(cbn(sd, b + "b2.", t, lab)), pol)
+            up = st(F.interpolate(h, scale_factor=2), pol)
+            sc = st(conv_emu(up, sd[b + "c_sc.weight"], sd[b + "c_sc.bias"], "c1", pol), pol)
+            h = st(conv_emu(a2, sd[b + "c2.weight"], sd[b + "c2.bias"], "c3", pol) + sc, pol)
+        mean, var = h.mean(dim=(0, 2, 3)), h.var(dim=(0, 2, 3), unbiased=False)
+        a = (h - mean[None, :, None, None]) * torch.rsqrt(var[None, :, None, None] + EPS)
+        a = st(F.relu(a * sd["b6.weight"][None, :, None, None] + sd["b6.bias"][None, :, None, None]), pol)
+        return torch.tanh(conv_emu(a, sd["l6.weight"], sd["l6.bias"], "c3", dict(pol, col="f32")))
+
+    def snw(sd, p):
+        return O.spectral_norm_weight(sd, p, 0, True, update_buffers=False)
+
+    def dis_emu(sd, x, lab, pol):
+        h1 = st(F.relu(conv_emu(x, snw(sd, "block1.c1."), sd["block1.c1.bias"], "c3", pol)), pol)
+        s = st(conv_emu(x, snw(sd, "block1.c_sc."), sd["block1.c_sc.bias"], "c1", pol), pol)
+        h = st(conv_emu(h1, snw(sd, "block1.c2."), sd["block1.c2.bias"], "c3", pol) + s, pol)
+        h = st(F.avg_pool2d(h, 2), pol)
+        for b in ("block2.", "block3.", "block4.", "block5."):
+            a = st(F.relu(h), pol)
+            t = st(F.relu(conv_emu(a, snw(sd, b + "c1."), sd[b + "c1.bias"], "c3", pol)), pol)
+            sc = st(conv_emu(h, snw(sd, b + "c_sc."), sd[b + "c_sc.bias"], "c1", pol), pol)
+            h = st(conv_emu(t, snw(sd, b + "c2."), sd[b + "c2.bias"], "c3", pol) + sc, pol)
+            h = st(F.avg_pool2d(h, 2), pol)
+        f = F.relu(h).sum(dim=(2, 3))
+        out = F.linear(f, snw(sd, "l6."), sd["l6.bias"])
+        return out + (F.embedding(lab, snw(sd, "l_y.")) * f).sum(dim=1, keepdim=True)
+
+    def grads(loss, p):
+        ks = [k for k, v in p.items() if torch.is_tensor(v) and v.requires_grad]
+        return {k: g for k, g in zip(ks, torch.autograd.grad(loss, [p[k] for k in ks], allow_unused=True)) if g is not None}
+
+    def step(pol):
+        pg, pd = leaves(sd_g), leaves(sd_d)
+        if pol is None:
+            G = lambda: O.sngan_generator(pg, z, c, bottom_width=2)
+            D = lambda xx, lab: O.sngan_discriminator({k: v for k, v in pd.items()}, xx, lab, training=True)
+            # the oracle's hook advances u / v in place; every D call below must see the same u, v as the emulation
+            def D(xx, lab, _pd=pd):
+                keep = {k: v.clone() for k, v in _pd.items() if k.endswith(("_u", "_v"))}
+                out = O.sngan_discriminator(_pd, xx, lab, training=True)
+                for k, v in keep.items():
+                    _pd[k].copy_(v)
+                return out
+        else:
+            G = lambda: gen_emu(pg, z, c, pol)
+            D = lambda xx, lab: dis_emu(pd, xx, lab, pol)
+        d_real = D(x, y)
+        g_real = grads(O.gan_loss("hinge", d_real, True), pd)
+        fake = G()
+        d_fake = D(fake.detach(), c)
+        g_fake = grads(O.gan_loss("hinge", d_fake, False), pd)
+        g_gen = grads(O.gan_loss("hinge", D(fake, c), False, True), pg)
+        return dict(d_real=d_real.detach(), fake=fake.detach(), d_fake=d_fake.detach(), g_real=g_real, g_fake=g_fake,
+                    g_gen=g_gen, pd=pd, pg=pg)
+
+    ref = step(None)
+    print("SNGAN projection ch %d batch %d, 32x32, emulated (operand format, storage format) for every layer" % (ch, B))
+    print("%-44s | %9s %9s %9s | %9s %9s %9s" % ("policy", "D(x)", "G(z)", "D(G(z))", "cos Dreal", "cos Dfake", "cos Gstep"))
+    pols = {"bf16 operands, bf16 storage (today)": dict(x=8, w=8, a=8, col="bf16"),
+            "bf16 operands, hi/lo storage": dict(x=8, w=8, a=16, col="f32"),
+            "fp16 operands (1 MMA), fp16 storage": dict(x="h", w="h", a="h", col="f32"),
+            "fp16 operands (1 MMA), hi/lo storage": dict(x="h", w="h", a="hh", col="f32"),
+            "bf16x3, hi/lo storage": dict(x=16, w=16, a=16, col="f32")}
+    for name, pol in pols.items():
+        if args.only and not any(tok in name for tok in args.only.split("|")):
+            continue
+        t = time.time()
+        r = step(pol)
+        skip = {}      # no analytically-zero bias gradients to exclude here: cosine over every parameter with a gradient
+        print("%-44s | %9.2e %9.2e %9.2e | %9.6f %9.6f %9.6f   (%.0f s)" % (
+            name, relerr(r["d_real"], ref["d_real"]), relerr(r["fake"], ref["fake"]), relerr(r["d_fake"], ref["d_fake"]),
+            cos(r["g_real"], ref["g_real"], skip), cos(r["g_fake"], ref["g_fake"], skip), cos(r["g_gen"], ref["g_gen"], skip),
+            time.time() - t), flush=True)
+
+
 def trace(args):
     """200-step loss traces (loop of main_dcgan.py:68-95 with Adam, as tests/test_gpu_trace.py: width 16, 32x32, batch 32)
     under EMULATED per-pass precision policies against the fp32 oracle, with the fp32 1e-6-perturbation control — the
@@ -412,6 +530,7 @@ def main():
     ap.add_argument("--sweep", action="store_true", help="per-layer sensitivity: one layer fp16 1-MMA / rest bf16x3 and back")
     ap.add_argument("--trace", action="store_true", help="200-step loss traces under the per-pass policies instead of the one-step study")
     ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--sngan", action="store_true", help="the one-step study for the SNGAN projection pair (ResNet nodes)")
     ap.add_argument("--acgan", action="store_true", help="the one-step study for the main_acgan.py loop and AcganStep's opt-in policy")
     args = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
@@ -419,6 +538,8 @@ def main():
         return trace(args)
     if args.acgan:
         return acgan_study(args)
+    if args.sngan:
+        return sngan_study(args)
     from gan_playground_b200.models import dcgan
 
     torch.set_num_threads(os.cpu_count())
