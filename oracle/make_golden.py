@@ -505,6 +505,21 @@ def key_lists(mods):
         out["dcgan_blur.Discriminator"] = desc(mods["dcgan_blur"].Discriminator())
         out["dcgan_blur.Generator@32"] = desc(mods["dcgan_blur"].Generator(resolution=32))
         out["dcgan_blur.Discriminator@32"] = desc(mods["dcgan_blur"].Discriminator(resolution=32))
+        # RNG-order parity of every family: (sum, first element) of every state_dict entry of a seed-7 construction
+        def probes(build):
+            torch.manual_seed(7)
+            nets = build()
+            return [[[k, float(v.double().sum()), float(v.flatten()[0])] for k, v in n.state_dict().items()] for n in nets]
+
+        S, A, N = mods["sngan_projection"], mods["acgan"], mods["dcgan_specnorm"]
+        out["same_seed_probes"] = {
+            "sngan_projection": probes(lambda: (S.ResNetGenerator(ch=8, dim_z=16, bottom_width=2, n_classes=10),
+                                                S.SNResNetProjectionDiscriminator(ch=8, n_classes=10))),
+            "sngan_projection@uncond": probes(lambda: (S.ResNetGenerator(ch=8, dim_z=16, n_classes=0),
+                                                       S.SNResNetProjectionDiscriminator(ch=8, n_classes=0))),
+            "acgan": probes(lambda: (A.Generator(z_dim=16, ngf=8, n_class=10), A.Discriminator(ndf=8, n_class=10))),
+            "dcgan_specnorm": probes(lambda: (N.Generator(z_dim=16, ngf=8, resolution=32), N.Discriminator(ndf=8, resolution=32))),
+        }
         # RNG-order parity: first weights of a seed-0 construction
         torch.manual_seed(0)
         g = mods["dcgan"].Generator(ngf=8, resolution=32)

@@ -191,3 +191,29 @@ def test_forward_tile_cost_model_fills_the_machine(built_lib):
         bn, mt, tiles = ops.conv_fwd_plan(*shape)
         assert bn in (64, 128, 256) and mt in (1, 2) and tiles >= 1
         assert bn // 2 < shape[6] or bn == 64                                            # never mostly padding
+
+
+@pytest.mark.parametrize("family", ["sngan_projection", "sngan_projection@uncond", "acgan", "dcgan_specnorm"])
+def test_same_seed_construction_of_every_family_matches_reference(family, capsys):
+    """The mirrors create their torch parameter holders, apply the initialisers and wrap spectral norm in the reference's
+    order, so a construction under the same seed consumes the same RNG stream: every parameter AND buffer (spectral-norm
+    u / v included) is identical to the unmodified reference's — (sum, first element) probes of each state_dict entry."""
+    from gan_playground_b200.models import acgan, dcgan_specnorm, sngan_projection as S
+
+    build = {
+        "sngan_projection": lambda: (S.ResNetGenerator(ch=8, dim_z=16, bottom_width=2, n_classes=10),
+                                     S.SNResNetProjectionDiscriminator(ch=8, n_classes=10)),
+        "sngan_projection@uncond": lambda: (S.ResNetGenerator(ch=8, dim_z=16, n_classes=0),
+                                            S.SNResNetProjectionDiscriminator(ch=8, n_classes=0)),
+        "acgan": lambda: (acgan.Generator(z_dim=16, ngf=8, n_class=10), acgan.Discriminator(ndf=8, n_class=10)),
+        "dcgan_specnorm": lambda: (dcgan_specnorm.Generator(z_dim=16, ngf=8, resolution=32),
+                                   dcgan_specnorm.Discriminator(ndf=8, resolution=32)),
+    }[family]
+    torch.manual_seed(7)
+    nets = build()
+    want = KEYS["same_seed_probes"][family]
+    for net, probes in zip(nets, want):
+        sd = net.state_dict()
+        assert list(sd.keys()) == [k for k, _, _ in probes]
+        for k, total, first in probes:
+            assert float(sd[k].double().sum()) == total and float(sd[k].flatten()[0]) == first, k
