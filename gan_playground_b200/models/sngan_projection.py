@@ -24,17 +24,37 @@ def _sn(module, training):
     return GF.SpectralNormFn.apply(module.weight_orig, module.weight_u, module.weight_v, 0, training)
 
 
+def _holder(layer, gain=1.0, spectral=False):
+    """Finish a freshly built torch layer the way every layer of this file is finished upstream: xavier-uniform weight
+    (`gain`), zero bias when there is one, optional torch spectral-norm wrapper. The calls happen per layer, in creation
+    order — that order is what makes a same-seed construction consume the reference's RNG stream."""
+    nn.init.xavier_uniform_(layer.weight, gain=gain)
+    if getattr(layer, "bias", None) is not None:
+        nn.init.zeros_(layer.bias)
+    return nn.utils.spectral_norm(layer) if spectral else layer
+
+
+_SQRT2 = 2 ** 0.5
+
+
+def _register(module, layers):
+    """Attach (name, layer) pairs in order: sub-module registration order is the state_dict key order."""
+    for name, layer in layers:
+        setattr(module, name, layer)
+
+
 class ConditionalBatchNorm2d(nn.Module):
     """Parameter holder (reference: models/sngan_projection.py:6-19): BatchNorm2d(affine=False) + Embedding(n, 2C)
     with gamma ~ N(1, 0.02), beta = 0. The computation is fused into GR.CondBNAct by the owning block."""
 
     def __init__(self, num_features, num_classes):
         super().__init__()
-        self.num_features = num_features
-        self.bn = nn.BatchNorm2d(num_features, affine=False)
-        self.embed = nn.Embedding(num_classes, num_features * 2)
-        self.embed.weight.data[:, :num_features].normal_(1, 0.02)
-        self.embed.weight.data[:, num_features:].zero_()
+        C = self.num_features = num_features
+        self.bn = nn.BatchNorm2d(C, affine=False)
+        self.embed = nn.Embedding(num_classes, 2 * C)          # row = [gamma(C) | beta(C)] of one class
+        gamma, beta = self.embed.weight.data.split(C, dim=1)
+        gamma.normal_(1, 0.02)
+        beta.zero_()
 
     def forward(self, x, y, act=ops.ACT_NONE, upsample=False):
         """x: NHWC bf16 feature map (internal layout), y: int64 labels."""
@@ -45,27 +65,19 @@ class ResGenBlock(nn.Module):
     def __init__(self, in_channels, out_channels, hidden_channels=None, ksize=3, pad=1,
                  activation=F.relu, upsample=False, n_classes=0):
         super().__init__()
-        self.activation = activation
-        self.upsample = upsample
-        self.learnable_sc = in_channels != out_channels or upsample
-        hidden_channels = out_channels if hidden_channels is None else hidden_channels
-        self.n_classes = n_classes
-        self.c1 = nn.Conv2d(in_channels, hidden_channels, ksize, padding=pad)
-        nn.init.xavier_uniform_(self.c1.weight, gain=(2 ** 0.5))
-        nn.init.zeros_(self.c1.bias)
-        self.c2 = nn.Conv2d(hidden_channels, out_channels, ksize, padding=pad)
-        nn.init.xavier_uniform_(self.c2.weight, gain=(2 ** 0.5))
-        nn.init.zeros_(self.c2.bias)
-        if n_classes > 0:
-            self.b1 = ConditionalBatchNorm2d(in_channels, n_classes)
-            self.b2 = ConditionalBatchNorm2d(hidden_channels, n_classes)
-        else:
-            self.b1 = nn.BatchNorm2d(in_channels)
-            self.b2 = nn.BatchNorm2d(hidden_channels)
+        hidden = out_channels if hidden_channels is None else hidden_channels
+        self.activation, self.upsample, self.n_classes = activation, upsample, n_classes
+        self.learnable_sc = upsample or in_channels != out_channels
+
+        def norm(C):
+            return ConditionalBatchNorm2d(C, n_classes) if n_classes > 0 else nn.BatchNorm2d(C)
+
+        _register(self, [("c1", _holder(nn.Conv2d(in_channels, hidden, ksize, padding=pad), _SQRT2)),
+                         ("c2", _holder(nn.Conv2d(hidden, out_channels, ksize, padding=pad), _SQRT2)),
+                         ("b1", norm(in_channels)),
+                         ("b2", norm(hidden))])
         if self.learnable_sc:
-            self.c_sc = nn.Conv2d(in_channels, out_channels, 1, padding=0)
-            nn.init.xavier_uniform_(self.c_sc.weight)
-            nn.init.zeros_(self.c_sc.bias)
+            self.c_sc = _holder(nn.Conv2d(in_channels, out_channels, 1))
         self._gp_cache = GF.WeightCache()
 
     def _norm_act(self, bn, h, y, upsample):
@@ -93,21 +105,13 @@ class ResGenBlock(nn.Module):
 class ResNetGenerator(nn.Module):
     def __init__(self, ch=64, dim_z=128, bottom_width=4, img_dim=3, activation=F.relu, n_classes=0):
         super().__init__()
-        self.bottom_width = bottom_width
-        self.activation = activation
-        self.dim_z = dim_z
-        self.n_classes = n_classes
-        self.l1 = nn.Linear(dim_z, (bottom_width ** 2) * ch * 16)
-        nn.init.xavier_uniform_(self.l1.weight)
-        nn.init.zeros_(self.l1.bias)
-        self.block2 = ResGenBlock(ch * 16, ch * 8, activation=activation, upsample=True, n_classes=n_classes)
-        self.block3 = ResGenBlock(ch * 8, ch * 4, activation=activation, upsample=True, n_classes=n_classes)
-        self.block4 = ResGenBlock(ch * 4, ch * 2, activation=activation, upsample=True, n_classes=n_classes)
-        self.block5 = ResGenBlock(ch * 2, ch, activation=activation, upsample=True, n_classes=n_classes)
+        self.bottom_width, self.activation, self.dim_z, self.n_classes = bottom_width, activation, dim_z, n_classes
+        widths = [ch * m for m in (16, 8, 4, 2, 1)]                 # 16ch at the bottom, halved by every block
+        self.l1 = _holder(nn.Linear(dim_z, bottom_width ** 2 * widths[0]))
+        for i, (cin, cout) in enumerate(zip(widths, widths[1:]), start=2):
+            setattr(self, "block%d" % i, ResGenBlock(cin, cout, activation=activation, upsample=True, n_classes=n_classes))
         self.b6 = nn.BatchNorm2d(ch)
-        self.l6 = nn.Conv2d(ch, img_dim, 3, stride=1, padding=1)
-        nn.init.xavier_uniform_(self.l6.weight)
-        nn.init.zeros_(self.l6.bias)
+        self.l6 = _holder(nn.Conv2d(ch, img_dim, 3, stride=1, padding=1))
         self._gp_cache = GF.WeightCache()
 
     def forward(self, z, y):
@@ -125,23 +129,14 @@ class ResDisBlock(nn.Module):
     def __init__(self, in_channels, out_channels, hidden_channels=None, ksize=3, pad=1,
                  activation=F.relu, downsample=False):
         super().__init__()
-        self.activation = activation
-        self.downsample = downsample
-        self.learnable_sc = (in_channels != out_channels) or downsample
-        hidden_channels = in_channels if hidden_channels is None else hidden_channels
-        self.c1 = nn.Conv2d(in_channels, hidden_channels, ksize, padding=pad)
-        nn.init.xavier_uniform_(self.c1.weight, gain=(2 ** 0.5))
-        nn.init.zeros_(self.c1.bias)
-        nn.utils.spectral_norm(self.c1)
-        self.c2 = nn.Conv2d(hidden_channels, out_channels, ksize, padding=pad)
-        nn.init.xavier_uniform_(self.c2.weight, gain=(2 ** 0.5))
-        nn.init.zeros_(self.c2.bias)
-        nn.utils.spectral_norm(self.c2)
+        hidden = in_channels if hidden_channels is None else hidden_channels
+        self.activation, self.downsample = activation, downsample
+        self.learnable_sc = downsample or in_channels != out_channels
+        # one layer at a time — create, initialise, wrap — so the RNG draws interleave as upstream's do
+        for name, cin, cout in (("c1", in_channels, hidden), ("c2", hidden, out_channels)):
+            setattr(self, name, _holder(nn.Conv2d(cin, cout, ksize, padding=pad), _SQRT2, spectral=True))
         if self.learnable_sc:
-            self.c_sc = nn.Conv2d(in_channels, out_channels, 1, padding=0)
-            nn.init.xavier_uniform_(self.c_sc.weight)
-            nn.init.zeros_(self.c_sc.bias)
-            nn.utils.spectral_norm(self.c_sc)
+            self.c_sc = _holder(nn.Conv2d(in_channels, out_channels, 1), spectral=True)
         self._gp_cache = GF.WeightCache()
 
     def forward(self, x):
@@ -161,18 +156,9 @@ class ResDisOptimizedBlock(nn.Module):
     def __init__(self, in_channels, out_channels, ksize=3, pad=1, activation=F.relu):
         super().__init__()
         self.activation = activation
-        self.c1 = nn.Conv2d(in_channels, out_channels, ksize, padding=pad)
-        nn.init.xavier_uniform_(self.c1.weight, gain=(2 ** 0.5))
-        nn.init.zeros_(self.c1.bias)
-        nn.utils.spectral_norm(self.c1)
-        self.c2 = nn.Conv2d(out_channels, out_channels, ksize, padding=pad)
-        nn.init.xavier_uniform_(self.c2.weight, gain=(2 ** 0.5))
-        nn.init.zeros_(self.c2.bias)
-        nn.utils.spectral_norm(self.c2)
-        self.c_sc = nn.Conv2d(in_channels, out_channels, 1, padding=0)
-        nn.init.xavier_uniform_(self.c_sc.weight)
-        nn.init.zeros_(self.c_sc.bias)
-        nn.utils.spectral_norm(self.c_sc)
+        for name, cin, k, gain in (("c1", in_channels, ksize, _SQRT2), ("c2", out_channels, ksize, _SQRT2),
+                                   ("c_sc", in_channels, 1, 1.0)):
+            setattr(self, name, _holder(nn.Conv2d(cin, out_channels, k, padding=pad if k == ksize else 0), gain, spectral=True))
         self._gp_cache = GF.WeightCache()
 
     def forward(self, x):
@@ -188,19 +174,13 @@ class SNResNetProjectionDiscriminator(nn.Module):
     def __init__(self, ch=64, n_classes=0, img_dim=3, activation=F.relu):
         super().__init__()
         self.activation = activation
-        self.block1 = ResDisOptimizedBlock(img_dim, ch)
-        self.block2 = ResDisBlock(ch, ch * 2, activation=activation, downsample=True)
-        self.block3 = ResDisBlock(ch * 2, ch * 4, activation=activation, downsample=True)
-        self.block4 = ResDisBlock(ch * 4, ch * 8, activation=activation, downsample=True)
-        self.block5 = ResDisBlock(ch * 8, ch * 16, activation=activation, downsample=True)
-        self.l6 = nn.Linear(ch * 16, 1)
-        nn.init.xavier_uniform_(self.l6.weight)
-        nn.init.zeros_(self.l6.bias)
-        nn.utils.spectral_norm(self.l6)
-        if n_classes > 0:
-            self.l_y = nn.Embedding(n_classes, ch * 16)
-            nn.init.xavier_uniform_(self.l_y.weight)
-            nn.utils.spectral_norm(self.l_y)
+        widths = [ch * m for m in (1, 2, 4, 8, 16)]                 # doubled by every down-sampling block
+        self.block1 = ResDisOptimizedBlock(img_dim, widths[0])
+        for i, (cin, cout) in enumerate(zip(widths, widths[1:]), start=2):
+            setattr(self, "block%d" % i, ResDisBlock(cin, cout, activation=activation, downsample=True))
+        self.l6 = _holder(nn.Linear(widths[-1], 1), spectral=True)
+        if n_classes > 0:                                           # projection: one spectral-normed embedding row per class
+            self.l_y = _holder(nn.Embedding(n_classes, widths[-1]), spectral=True)
 
     def forward(self, x, y=None):
         require_cuda(x, "sngan_projection.SNResNetProjectionDiscriminator")
