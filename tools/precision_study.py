@@ -345,6 +345,92 @@ def acgan_study(args):
                                                  cos(both, both_ref, r[3]), cos(r[2], ref[2], r[4])), flush=True)
 
 
+def sndcgan_study(args):
+    """One-step study for SN-DCGAN 32x32 with the hinge loss (cfg 3: models/dcgan_specnorm.py through the main_dcgan.py
+    loop): spectral-normed conv weights W / sigma (sigma from fp32 GEMV kernels) are what the GEMMs round."""
+    from gan_playground_b200.models import dcgan_specnorm as M
+
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        netG, netD = M.Generator(ngf=args.width, resolution=32), M.Discriminator(ndf=args.width, resolution=32)
+    sd_g = {k: v.clone() for k, v in netG.state_dict().items()}
+    sd_d = {k: v.clone() for k, v in netD.state_dict().items()}
+    gen = torch.Generator().manual_seed(1)
+    B = args.batch
+    x = torch.rand(B, 3, 32, 32, generator=gen) * 2 - 1
+    z1, z2 = torch.randn(B, 100, generator=gen), torch.randn(B, 100, generator=gen)
+
+    def snw(sd, p, dim):
+        return O.spectral_norm_weight(sd, p, dim, True, update_buffers=False)
+
+    def gen_emu(sd, z, P):
+        h = store_act(F.relu(conv_emu(z, sd["linear.weight"], sd["linear.bias"], "linear", P["g_lin"])), P["g_lin"])
+        h = h.view(h.size(0), -1, 4, 4)
+        for i in range(2):
+            p, pol = "blocks.%d." % i, P["g%d" % i]
+            h = bn_act(conv_emu(h, snw(sd, p + "0.", 1), sd[p + "0.bias"], "convT", pol), sd[p + "1.weight"],
+                       sd[p + "1.bias"], "relu", pol)
+        return convT_image(h, snw(sd, "out_layer.0.", 1), sd["out_layer.0.bias"], P["g_out"])
+
+    def dis_emu(sd, x, P):
+        h = store_act(F.leaky_relu(conv_emu(x, snw(sd, "blocks.0.0.", 0), sd["blocks.0.0.bias"], "conv", P["d0"]), 0.2), P["d0"])
+        for i in range(1, 3):
+            p, pol = "blocks.%d." % i, P["d%d" % i]
+            h = bn_act(conv_emu(h, snw(sd, p + "0.", 0), sd[p + "0.bias"], "conv", pol), sd[p + "1.weight"],
+                       sd[p + "1.bias"], "lrelu", pol)
+        return F.linear(h.flatten(1), sd["out_layer.weight"], sd["out_layer.bias"])
+
+    def leaves(sd):
+        return {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(("_u", "_v", "running_mean", "running_var"))
+                    else v.clone()) for k, v in sd.items()}
+
+    def grads(loss, p):
+        ks = [k for k, v in p.items() if torch.is_tensor(v) and v.requires_grad]
+        return {k: g for k, g in zip(ks, torch.autograd.grad(loss, [p[k] for k in ks], allow_unused=True)) if g is not None}
+
+    def step(p_real, p_fake, p_g):
+        pg, pd = leaves(sd_g), leaves(sd_d)
+        if p_real is None:
+            G = lambda z, P: O.dcgan_generator(dict(pg), z, sn=True, training=True)
+            D = lambda xx, P: O.dcgan_discriminator(dict(pd), xx, sn=True, flatten_head=True, training=True)
+            keep = [{k: v.clone() for k, v in d.items() if k.endswith(("_u", "_v"))} for d in (pg, pd)]
+
+            def restore():      # the oracle's hook advances u / v in place: every pass must start from the same vectors
+                for d, kp in zip((pg, pd), keep):
+                    for k, v in kp.items():
+                        d[k].copy_(v)
+        else:
+            G, D, restore = (lambda z, P: gen_emu(pg, z, P)), (lambda xx, P: dis_emu(pd, xx, P)), (lambda: None)
+        g_real = grads(O.gan_loss("hinge", D(x, p_real), True), pd)
+        restore()
+        with torch.no_grad():
+            fake1 = G(z1, p_fake)
+        restore()
+        g_fake = grads(O.gan_loss("hinge", D(fake1, p_fake), False), pd)
+        restore()
+        fake2 = G(z2, p_g)
+        restore()
+        g_gen = grads(O.gan_loss("hinge", D(fake2, p_g), False, True), pg)
+        restore()
+        return g_real, g_fake, g_gen
+
+    ref = step(None, None, None)
+    H = dict(x="h", w="h", y="f32", a="h", col="f32")
+    print("SN-DCGAN 32x32 width %d batch %d, hinge loss, emulated: gradient cosines against the fp32 oracle" % (args.width, B))
+    print("%-58s %9s %9s %9s %9s" % ("policy (real pass / D-fake chain / G step)", "D-real", "D-fake", "D r+f", "G-step"))
+    for name, pol in (("bf16x3 / bf16x3 / bf16x3", (policy(X3),) * 3),
+                      ("bf16 / bf16x3 / bf16x3 (DcganStep today for this family)", (policy(BF16), policy(X3), policy(X3))),
+                      ("bf16 / fp16 / bf16x3", (policy(BF16), policy(BF16, all=H), policy(X3))),
+                      ("fp16 / fp16 / fp16", (policy(BF16, all=H),) * 3),
+                      ("bf16 / bf16 / bf16", (policy(BF16),) * 3)):
+        r = step(*pol)
+        both = {k: r[0][k] + r[1][k] for k in r[0]}
+        both_ref = {k: ref[0][k] + ref[1][k] for k in ref[0]}
+        nb = {}
+        print("%-58s %9.6f %9.6f %9.6f %9.6f" % (name, cos(r[0], ref[0], nb), cos(r[1], ref[1], nb), cos(both, both_ref, nb),
+                                                 cos(r[2], ref[2], nb)), flush=True)
+
+
 def sngan_study(args):
     """One-step study for the SNGAN projection pair (models/sngan_projection.py, loop of main_sngan.py:65-100; cfg 4:
     ch 64, 32x32, bottom_width 2, 10 classes). The ResNet nodes (functional_resnet.py) have no BatchNorm between most
@@ -530,6 +616,7 @@ def main():
     ap.add_argument("--sweep", action="store_true", help="per-layer sensitivity: one layer fp16 1-MMA / rest bf16x3 and back")
     ap.add_argument("--trace", action="store_true", help="200-step loss traces under the per-pass policies instead of the one-step study")
     ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--sndcgan", action="store_true", help="the one-step study for SN-DCGAN 32x32 with the hinge loss (cfg 3)")
     ap.add_argument("--sngan", action="store_true", help="the one-step study for the SNGAN projection pair (ResNet nodes)")
     ap.add_argument("--acgan", action="store_true", help="the one-step study for the main_acgan.py loop and AcganStep's opt-in policy")
     args = ap.parse_args()
@@ -540,6 +627,8 @@ def main():
         return acgan_study(args)
     if args.sngan:
         return sngan_study(args)
+    if args.sndcgan:
+        return sndcgan_study(args)
     from gan_playground_b200.models import dcgan
 
     torch.set_num_threads(os.cpu_count())
