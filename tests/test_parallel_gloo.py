@@ -136,3 +136,127 @@ def test_single_process_is_a_noop():
     t = torch.ones(3)
     assert parallel.all_reduce_sum_(t) is t
     assert parallel.shard(t) is t
+
+
+# ---- the step drivers under data parallelism (host logic): BatchNorm-free stand-in nets, so that two ranks on half
+# ---- batches with averaged gradients must reproduce the single-process run on the full batch exactly
+def _toy_nets(seed):
+    import torch.nn as nn
+
+    torch.manual_seed(seed)
+
+    class G(nn.Module):
+        def __init__(self, cond):
+            super().__init__()
+            self.fc = nn.Linear(4 + (3 if cond else 0), 3 * 4 * 4)
+            self.cond = cond
+
+        def forward(self, z, y=None):
+            if self.cond:
+                y = y if y.is_floating_point() else torch.nn.functional.one_hot(y, 3).float()
+                z = torch.cat([z, y], 1)
+            return torch.tanh(self.fc(z)).view(-1, 3, 4, 4)
+
+    class D(nn.Module):
+        def __init__(self, heads):
+            super().__init__()
+            self.body = nn.Linear(3 * 4 * 4, 8)
+            self.out = nn.Linear(8, heads)
+            self.img_dim, self.resolution = 3, 4
+            self.block1 = nn.Module()
+            self.block1.c1 = nn.Module()
+            self.block1.c1.in_channels = 3
+
+        def packed_logits(self, x):
+            return self.out(torch.nn.functional.leaky_relu(self.body(x.flatten(1)), 0.2))
+
+        def forward(self, x, y=None):
+            return self.packed_logits(x)[:, :1]
+
+    return G, D
+
+
+def _drive(kind, rank, world, steps=3, B=8):
+    """Run `steps` iterations of one driver on this rank's shard (or on the full batch when world == 1)."""
+    from gan_playground_b200 import engine, parallel
+    from gan_playground_b200.criterion import ACGANLoss, GANLoss
+    from oracle import gan_oracle as O
+
+    G, D = _toy_nets(0)
+    netG, netD = G(kind != "dcgan"), D(4 if kind == "acgan" else 1)
+    parallel.broadcast_module(netG), parallel.broadcast_module(netD)
+    optG = torch.optim.SGD(netG.parameters(), lr=0.1)
+    optD = torch.optim.SGD(netD.parameters(), lr=0.1)
+    gen = torch.Generator().manual_seed(3)
+    xs = torch.rand(steps, B, 3, 4, 4, generator=gen) * 2 - 1
+    zs = torch.randn(steps, 2, B, 4, generator=gen)
+    ys = torch.randint(3, (steps, B), generator=gen)
+    cs = torch.randint(3, (steps, B), generator=gen)
+    yf = torch.randint(0, 2, (steps, B, 3), generator=gen).float()
+    b = B // world
+    sl = slice(rank * b, (rank + 1) * b)
+    dev = torch.device("cpu")
+
+    def crit(pred, is_real, is_generator=False):
+        return O.gan_loss("hinge", pred, is_real, is_generator)
+
+    class CpuACGANLoss(ACGANLoss):
+        def forward(self, packed, labels, is_real, is_generator=False):
+            adv, cls = packed[:, :1], packed[:, 1:]
+            l_adv = O.gan_loss("vanilla", adv, is_real, is_generator, 0.9, 0.1, 0.9)
+            l_aux = torch.nn.functional.mse_loss(cls, labels)
+            return torch.stack([l_adv, l_aux, l_adv + self.aux_weight * l_aux, torch.sigmoid(adv).mean()])
+
+    if kind == "dcgan":
+        run = engine.DcganStep(netG, netD, crit, optG, optD, b, 4, dev, overlap=False)
+        step = lambda i: run.step(xs[i, sl], zs[i, :, sl])
+    elif kind == "sngan":
+        run = engine.SnganStep(netG, netD, crit, optG, optD, b, 4, dev, n_classes=3, n_disc_update=2, resolution=4,
+                               overlap=False)
+        step = lambda i: run.step(xs[i, sl], ys[i, sl], zs[i, 0, sl], cs[i, sl])
+    else:
+        run = engine.AcganStep(netG, netD, CpuACGANLoss(GANLoss("vanilla", 0.9, 0.1, 0.9)), optG, optD, b, 4, dev, n_class=3,
+                               overlap=False)
+        step = lambda i: run.step(xs[i, sl], yf[i, sl], zs[i, 0, sl])
+    for i in range(steps):
+        step(i)
+    return [p.detach().clone() for p in list(netG.parameters()) + list(netD.parameters())]
+
+
+def _driver_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from gan_playground_b200 import parallel
+
+    parallel.init(backend="gloo")
+    out = {kind: [t.tolist() for t in _drive(kind, rank, world)] for kind in ("dcgan", "sngan", "acgan")}   # plain lists:
+    parallel.shutdown()                                                   # tensors in a Queue need the sender alive
+    q.put((rank, out))
+
+
+def test_step_drivers_data_parallel_equals_full_batch_gloo():
+    """engine.DcganStep / SnganStep / AcganStep on 2 gloo ranks (half batch each, gradients averaged through the flat
+    buckets before every optimiser step) == the same driver in one process on the full batch: the mean losses of the
+    scripts make the averaged shard gradients the full-batch gradients. Replicas must also be identical to each other."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    single = {kind: _drive(kind, 0, 1) for kind in ("dcgan", "sngan", "acgan")}
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_driver_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(60)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    for kind, ref in single.items():
+        for a, b0, b1 in zip(ref, got[0][kind], got[1][kind]):
+            assert b0 == b1, kind                                              # replicas stay identical
+            b0 = torch.tensor(b0)
+            assert torch.allclose(a, b0, atol=1e-6, rtol=1e-5), (kind, (a - b0).abs().max())
