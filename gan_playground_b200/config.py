@@ -10,7 +10,8 @@ precision:
             fp16 would underflow its 1e-8-scale gradients) and fp16 (the next forward operand). Emulated cosines
             (tools/precision_study.py): D-real 0.99999, D-fake 0.9993, G-step 0.9968 — good for every pass except the G step.
 Select with gan_playground_b200.config.set_precision(...) or the GP_PRECISION environment variable.
-Only the DCGAN-family nodes (dcgan / acgan / dcgan_specnorm) implement bf16x3 so far; the ResNet nodes run "bf16".
+The DCGAN-family nodes (dcgan / acgan / dcgan_specnorm) implement all three; the ResNet and blur nodes implement "bf16"
+and "fp16" and run the default "bf16x3" as "fp16" (resnet_scope).
 """
 import os
 
@@ -58,6 +59,13 @@ class precision_scope:
     def __exit__(self, *exc):
         global _precision
         _precision = self.prev
+
+
+def resnet_scope():
+    """The scope the ResNet (models/sngan_projection.py) and blur (models/dcgan_blur.py) mirrors run their forward in:
+    those nodes implement "bf16" and "fp16"; the global default "bf16x3" maps to "fp16" — one MMA on 11-bit operands
+    already meets every north_star bar on the projection pair, which has no BatchNorm in D."""
+    return precision_scope("fp16" if _precision in ("bf16x3", "fp16") else "bf16")
 
 
 # BatchNorm batch statistics accumulated in the GEMM epilogue from the fp32 accumulators (one fewer pass over the conv

@@ -4,6 +4,7 @@
 // one thread per output pixel x 8-channel group (16-byte accesses), fp32 accumulation.
 #include <cuda_bf16.h>
 
+#include "act_io.cuh"
 #include "common.h"
 
 namespace gp {
@@ -33,7 +34,9 @@ __device__ __forceinline__ int reflect1(int q, int n) {
 }
 
 // out[n, oh, ow, :] = sum_{kh,kw} w[kh] w[kw] / 16 * in[n, reflect(oh*s + kh), reflect(ow*s + kw), :],  w = (1, 2, 1)
-__global__ void blur3x3_fwd_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int NB, int H,
+// in_comp / out_comp / fmt: companion tensors of the forward precision mode (act_io.cuh)
+__global__ void blur3x3_fwd_kernel(const __nv_bfloat16* __restrict__ in, const void* __restrict__ in_comp,
+                                   __nv_bfloat16* __restrict__ out, void* __restrict__ out_comp, int fmt, int NB, int H,
                                    int W, int C, int s, int Ho, int Wo) {
   const int cgs = C / 8;
   const long long total = (long long)NB * Ho * Wo * cgs;
@@ -52,12 +55,12 @@ __global__ void blur3x3_fwd_kernel(const __nv_bfloat16* __restrict__ in, __nv_bf
         const int iw = reflect1(ow * s + kw, W);
         const float wgt = (kh == 1 ? 2.f : 1.f) * (kw == 1 ? 2.f : 1.f) * (1.f / 16.f);
         float f[8];
-        blur_unpack8(*reinterpret_cast<const uint4*>(in + (((long long)n * H + ih) * W + iw) * C + g * 8), f);
+        load8c(in, in_comp, fmt, (((long long)n * H + ih) * W + iw) * C + g * 8, f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] += wgt * f[j];
       }
     }
-    *reinterpret_cast<uint4*>(out + p * C + g * 8) = blur_pack8(acc);
+    store8c(out, out_comp, fmt, p * C + g * 8, acc);
   }
 }
 
@@ -118,12 +121,15 @@ using namespace gp;
 
 extern "C" {
 
-int gp_blur3x3_fwd(const void* in, void* out, int NB, int H, int W, int C, int stride, void* stream) {
+int gp_blur3x3_fwd(const void* in, const void* in_comp, void* out, void* out_comp, int comp_fmt, int NB, int H, int W,
+                   int C, int stride, void* stream) {
   GP_REQUIRE(in && out && NB > 0 && H >= 2 && W >= 2 && C > 0 && C % 8 == 0 && (stride == 1 || stride == 2),
              "gp_blur3x3_fwd: bad arguments (C %% 8 == 0, H, W >= 2, stride 1 or 2)");
+  GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_blur3x3_fwd: unknown companion format %d", comp_fmt);
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   blur3x3_fwd_kernel<<<blur_grid((long long)NB * Ho * Wo * (C / 8)), 256, 0, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), NB, H, W, C, stride, Ho, Wo);
+      static_cast<const __nv_bfloat16*>(in), in_comp, static_cast<__nv_bfloat16*>(out), out_comp, comp_fmt, NB, H, W, C,
+      stride, Ho, Wo);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }

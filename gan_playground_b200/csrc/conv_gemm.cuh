@@ -76,6 +76,7 @@ struct alignas(64) ConvGemmParams {
                       // single-MMA operand copy of the "fp16" forward mode, instead of the bf16 rounding residual
 };
 constexpr int kFmtInF16 = 1, kFmtLoF16 = 2;
+constexpr int kFmtResF16 = 4;  // FWD: `residual` holds fp16 (the companion of the shortcut activation in the fp16 mode)
 
 // X3 = bf16x3 forward (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo): one pipeline stage holds the hi AND lo tiles of both
 // operands — 4 tile loads feed 3 MMA blocks, i.e. 1/3 fewer operand bytes from L2 per MMA than issuing the three
@@ -474,14 +475,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             }
             if (p.residual != nullptr && row_ok[mi]) {
               const __nv_bfloat16* rrow = p.residual + off[mi];
+              const bool res_f16 = (p.fmt_flags & kFmtResF16) != 0;
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 if (col0 + g * 8 < p.N) {
                   const uint4 rv = *reinterpret_cast<const uint4*>(rrow + col0 + g * 8);
                   const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+                  const __half2* q2 = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
-                    const float2 f = __bfloat1622float2(h2[e]);
+                    const float2 f = res_f16 ? __half22float2(q2[e]) : __bfloat1622float2(h2[e]);
                     v[g * 8 + 2 * e] += f.x;
                     v[g * 8 + 2 * e + 1] += f.y;
                   }

@@ -3,6 +3,7 @@
 // All activations are NHWC bf16 viewed as [P pixels][C channels]; reductions accumulate in fp32.
 #include <cuda_bf16.h>
 
+#include "act_io.cuh"
 #include "bn_stream.cuh"
 #include "common.h"
 
@@ -402,7 +403,7 @@ __global__ void image_bias_grad_kernel(const float* __restrict__ dout, const flo
 // out[b][o] = bias[o] + sum_{hw, c} (a + a_lo)[b, hw, c] * w[o*s_o + c*s_c + hw*s_hw]
 // (sum-pool + Linear: s_hw = 0, models/dcgan.py:121-122; flatten + Linear: s_c = HW, s_hw = 1, dcgan_specnorm.py:125-126)
 // One block per (b, o); threads read 8 channels (16 bytes) at a time. a_lo: optional low halves (bf16x3 mode).
-__global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ a_lo,
+__global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ a, const void* __restrict__ a_comp, int fmt,
                                 const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
                                 int HW, int C, int O, long long s_o, long long s_c, long long s_hw) {
   const int b = blockIdx.x, o = blockIdx.y;
@@ -412,18 +413,8 @@ __global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_
   const int c8 = C / 8;
   for (int i = threadIdx.x; i < HW * c8; i += blockDim.x) {
     const int c = (i % c8) * 8, hw = i / c8;
-    Vec8<__nv_bfloat16> v;
-    v.load(a + base + (long long)i * 8);
     float f[8];
-    v.unpack(f);
-    if (a_lo != nullptr) {
-      Vec8<__nv_bfloat16> vl;
-      vl.load(a_lo + base + (long long)i * 8);
-      float fl[8];
-      vl.unpack(fl);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += fl[j];
-    }
+    load8c(a, a_comp, fmt, base + (long long)i * 8, f);   // most precise view of the features (act_io.cuh)
     const float* wp = wo + c * s_c + hw * s_hw;
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc += f[j] * __ldg(wp + j * s_c);
@@ -923,8 +914,8 @@ int gp_head_fwd(const void* a, const float* w, const float* bias, float* out, in
                 long long s_o, long long s_c, long long s_hw, void* stream) {
   GP_REQUIRE(a && w && out && NB > 0 && HW > 0 && C > 0 && C % 8 == 0 && O > 0, "gp_head_fwd: bad arguments");
   dim3 grid(NB, O);
-  head_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(a), nullptr, w, bias, out, HW, C,
-                                                       O, s_o, s_c, s_hw);
+  head_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(a), nullptr, GP_COMP_NONE, w, bias,
+                                                       out, HW, C, O, s_o, s_c, s_hw);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -933,9 +924,19 @@ int gp_head_fwd_split(const void* a_hi, const void* a_lo, const float* w, const 
                       int C, int O, long long s_o, long long s_c, long long s_hw, void* stream) {
   GP_REQUIRE(a_hi && a_lo && w && out && NB > 0 && HW > 0 && C > 0 && C % 8 == 0 && O > 0, "gp_head_fwd_split: bad arguments");
   dim3 grid(NB, O);
-  head_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(a_hi),
-                                                       static_cast<const __nv_bfloat16*>(a_lo), w, bias, out, HW, C, O,
-                                                       s_o, s_c, s_hw);
+  head_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(a_hi), a_lo, GP_COMP_LO, w, bias,
+                                                       out, HW, C, O, s_o, s_c, s_hw);
+  GP_CHECK_LAUNCH();
+  return GP_OK;
+}
+
+int gp_head_fwd_comp(const void* a, const void* a_comp, int comp_fmt, const float* w, const float* bias, float* out, int NB,
+                     int HW, int C, int O, long long s_o, long long s_c, long long s_hw, void* stream) {
+  GP_REQUIRE(a && w && out && NB > 0 && HW > 0 && C > 0 && C % 8 == 0 && O > 0, "gp_head_fwd_comp: bad arguments");
+  GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_head_fwd_comp: unknown companion format %d", comp_fmt);
+  dim3 grid(NB, O);
+  head_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(a), a_comp, comp_fmt, w, bias, out,
+                                                       HW, C, O, s_o, s_c, s_hw);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }

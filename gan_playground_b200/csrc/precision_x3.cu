@@ -7,6 +7,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include "act_io.cuh"
 #include "bn_stream.cuh"
 #include "common.h"
 
@@ -55,6 +56,75 @@ __global__ void pair_to_f16_kernel(const __nv_bfloat16* __restrict__ hi, const _
       po[j] = __floats2half2_rn(a.x + b.x, a.y + b.y);
     }
     *reinterpret_cast<uint4*>(out + r * ld_out + k) = o;
+  }
+}
+
+// BatchNorm statistics / apply on an activation stored with a companion tensor (act_io.cuh): the nodes that normalise
+// an EXISTING activation instead of a conv's fp32 output (generator's b6 of models/sngan_projection.py:92, every
+// BatchNorm of models/dcgan_blur.py, which follows a BlurPool). Same thread layout as bn_stream.cuh.
+__global__ void col_stats_comp_kernel(const __nv_bfloat16* __restrict__ x, const void* __restrict__ x_comp, int fmt,
+                                      long long P, int C, float* __restrict__ sum, float* __restrict__ sumsq,
+                                      int rows_per_block) {
+  const ColLayout L = col_layout(C);
+  float acc[2][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
+  if (L.active) {
+    const RowRange R = row_range(P, rows_per_block);
+    for (long long r = R.r0 + L.rl; r < R.r1; r += (long long)kRowsInFlight * L.lanes) {
+      float f[kRowsInFlight][8];
+#pragma unroll
+      for (int u = 0; u < kRowsInFlight; ++u) {
+        const long long ru = r + (long long)u * L.lanes;
+        if (ru < R.r1) {
+          load8c(x, x_comp, fmt, ru * C + L.g * 8, f[u]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[u][i] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kRowsInFlight; ++u)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[0][i] += f[u][i];
+          acc[1][i] += f[u][i] * f[u][i];
+        }
+    }
+  }
+  float* const outs[2] = {sum, sumsq};
+  col_flush<2>(L, C, acc, outs);
+}
+
+__global__ void bn_apply_comp_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ y_comp,
+                                     __nv_bfloat16* __restrict__ out, void* __restrict__ out_comp, int fmt, long long P,
+                                     int C, const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                     int rows_per_block) {
+  const ColLayout L = col_layout(C);
+  if (!L.active) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[L.g * 8 + j];
+    sh[j] = shift[L.g * 8 + j];
+  }
+  const RowRange R = row_range(P, rows_per_block);
+  for (long long r = R.r0 + L.rl; r < R.r1; r += (long long)kRowsInFlight * L.lanes) {
+    float f[kRowsInFlight][8];
+#pragma unroll
+    for (int u = 0; u < kRowsInFlight; ++u) {
+      const long long ru = r + (long long)u * L.lanes;
+      if (ru < R.r1) load8c(y, y_comp, fmt, ru * C + L.g * 8, f[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kRowsInFlight; ++u) {
+      const long long ru = r + (long long)u * L.lanes;
+      if (ru < R.r1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[u][j] = act_fwd(f[u][j] * sc[j] + sh[j], act);
+        store8c(out, out_comp, fmt, ru * C + L.g * 8, f[u]);
+      }
+    }
   }
 }
 
@@ -119,6 +189,29 @@ int gp_bn_apply_act_pair(const float* y, void* out_bf16, void* out_f16, long lon
   bn_apply_kernel<float, true><<<L.grid, L.block, 0, as_stream(stream)>>>(y, static_cast<__nv_bfloat16*>(out_bf16),
                                                                           static_cast<__nv_bfloat16*>(out_f16), P, C, scale,
                                                                           shift, act, L.rpb);
+  GP_CHECK_LAUNCH();
+  return GP_OK;
+}
+
+int gp_bn_stats_comp(const void* x, const void* x_comp, int comp_fmt, long long P, int C, float* sum, float* sumsq,
+                     void* stream) {
+  GP_REQUIRE(x && sum && sumsq && P > 0 && C > 0 && C % 8 == 0, "gp_bn_stats_comp: bad arguments (C %% 8 == 0 required)");
+  GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_bn_stats_comp: unknown companion format %d", comp_fmt);
+  const ColLaunch L = col_launch(P, C, 2);
+  x3::col_stats_comp_kernel<<<L.grid, L.block, L.smem, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(x), x_comp,
+                                                                            comp_fmt, P, C, sum, sumsq, L.rpb);
+  GP_CHECK_LAUNCH();
+  return GP_OK;
+}
+
+int gp_bn_apply_act_comp(const void* y, const void* y_comp, void* out, void* out_comp, int comp_fmt, long long P, int C,
+                         const float* scale, const float* shift, int act, void* stream) {
+  GP_REQUIRE(y && out && scale && shift && P > 0 && C % 8 == 0, "gp_bn_apply_act_comp: bad arguments");
+  GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_bn_apply_act_comp: unknown companion format %d", comp_fmt);
+  const ColLaunch L = col_launch(P, C, 0);
+  x3::bn_apply_comp_kernel<<<L.grid, L.block, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(y), y_comp,
+                                                                      static_cast<__nv_bfloat16*>(out), out_comp, comp_fmt,
+                                                                      P, C, scale, shift, act, L.rpb);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }

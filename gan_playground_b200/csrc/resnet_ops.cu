@@ -3,6 +3,7 @@
 // 2x2 pooling / upsampling, 3x3 image-side im2col / col2im, ReLU + global sum pooling, the projection head.
 #include <cuda_bf16.h>
 
+#include "act_io.cuh"
 #include "common.h"
 
 namespace gp {
@@ -39,7 +40,9 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // out[n, (up)h, (up)w, c] = act( (y - mean[c]) * rstd[c] * gamma[n][c] + beta[n][c] ),
 // gamma[n] = emb[label[n]][0:C], beta[n] = emb[label[n]][C:2C]   (models/sngan_projection.py:15-19).
 // emb == NULL: plain non-affine normalisation. grid = (pixel chunks, NB); thread = one 8-channel group x pixel lane.
-__global__ void cbn_apply_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ out, int H, int W,
+// y_comp / out_comp / fmt: companion tensors of the forward precision mode (act_io.cuh).
+__global__ void cbn_apply_kernel(const __nv_bfloat16* __restrict__ y, const void* __restrict__ y_comp,
+                                 __nv_bfloat16* __restrict__ out, void* __restrict__ out_comp, int fmt, int H, int W,
                                  int C, const float* __restrict__ mean, const float* __restrict__ rstd,
                                  const float* __restrict__ emb, const long long* __restrict__ labels, int act, int up,
                                  int px_per_block) {
@@ -60,21 +63,20 @@ __global__ void cbn_apply_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloa
   const int p0 = blockIdx.x * px_per_block, p1 = min(p0 + px_per_block, HW);
   const int oW = up ? 2 * W : W;
   for (int p = p0 + lane; p < p1; p += lanes) {
-    const uint4 raw = *reinterpret_cast<const uint4*>(y + ((long long)n * HW + p) * C + g * 8);
     float f[8];
-    unpack8(raw, f);
+    load8c(y, y_comp, fmt, ((long long)n * HW + p) * C + g * 8, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = r_act_fwd(f[j] * sc[j] + sh[j], act);
-    const uint4 o = pack8(f);
+    const Packed8c o = pack8c(out_comp != nullptr ? fmt : GP_COMP_NONE, f);
     if (up) {
       const int h = p / W, w = p % W;
-      __nv_bfloat16* base = out + (((long long)n * 2 * H + 2 * h) * oW + 2 * w) * C + g * 8;
-      *reinterpret_cast<uint4*>(base) = o;
-      *reinterpret_cast<uint4*>(base + C) = o;
-      *reinterpret_cast<uint4*>(base + (long long)oW * C) = o;
-      *reinterpret_cast<uint4*>(base + (long long)oW * C + C) = o;
+      const long long base = (((long long)n * 2 * H + 2 * h) * oW + 2 * w) * C + g * 8;
+      put8c(out, out_comp, base, o);
+      put8c(out, out_comp, base + C, o);
+      put8c(out, out_comp, base + (long long)oW * C, o);
+      put8c(out, out_comp, base + (long long)oW * C + C, o);
     } else {
-      *reinterpret_cast<uint4*>(out + ((long long)n * HW + p) * C + g * 8) = o;
+      put8c(out, out_comp, ((long long)n * HW + p) * C + g * 8, o);
     }
   }
 }
@@ -224,11 +226,14 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfl
     const long long p = i / cgs;
     const int w = (int)(p % W), h = (int)((p / W) % H);
     const long long n = p / ((long long)W * H);
-    float f[8];
-    unpack8(*reinterpret_cast<const uint4*>(in + p * C + g * 8), f);
+    uint4 o = *reinterpret_cast<const uint4*>(in + p * C + g * 8);
+    if (scale != 1.f) {  // scale == 1: a pure 16-bit copy (also used for fp16 companion tensors)
+      float f[8];
+      unpack8(o, f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] *= scale;
-    const uint4 o = pack8(f);
+      for (int j = 0; j < 8; ++j) f[j] *= scale;
+      o = pack8(f);
+    }
     __nv_bfloat16* base = out + ((n * 2 * H + 2 * h) * (2LL * W) + 2 * w) * C + g * 8;
     *reinterpret_cast<uint4*>(base) = o;
     *reinterpret_cast<uint4*>(base + C) = o;
@@ -238,7 +243,8 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfl
 }
 
 // out[n, h, w, c] = scale * sum_{a,b} in[n, 2h+a, 2w+b, c]      (H, W: output size)
-__global__ void pool2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, long long NB, int H,
+__global__ void pool2x_kernel(const __nv_bfloat16* __restrict__ in, const void* __restrict__ in_comp,
+                              __nv_bfloat16* __restrict__ out, void* __restrict__ out_comp, int fmt, long long NB, int H,
                               int W, int C, float scale) {
   const int cgs = C / 8;
   const long long total = NB * H * W * cgs;
@@ -247,36 +253,38 @@ __global__ void pool2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat1
     const long long p = i / cgs;
     const int w = (int)(p % W), h = (int)((p / W) % H);
     const long long n = p / ((long long)W * H);
-    const __nv_bfloat16* base = in + ((n * 2 * H + 2 * h) * (2LL * W) + 2 * w) * C + g * 8;
+    const long long base = ((n * 2 * H + 2 * h) * (2LL * W) + 2 * w) * C + g * 8;
     float f[8], t[8];
-    unpack8(*reinterpret_cast<const uint4*>(base), f);
-    unpack8(*reinterpret_cast<const uint4*>(base + C), t);
+    load8c(in, in_comp, fmt, base, f);
+    load8c(in, in_comp, fmt, base + C, t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] += t[j];
-    unpack8(*reinterpret_cast<const uint4*>(base + 2LL * W * C), t);
+    load8c(in, in_comp, fmt, base + 2LL * W * C, t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] += t[j];
-    unpack8(*reinterpret_cast<const uint4*>(base + 2LL * W * C + C), t);
+    load8c(in, in_comp, fmt, base + 2LL * W * C + C, t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = (f[j] + t[j]) * scale;
-    *reinterpret_cast<uint4*>(out + p * C + g * 8) = pack8(f);
+    store8c(out, out_comp, fmt, p * C + g * 8, f);
   }
 }
 
-__global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n8, int act) {
+__global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ in, const void* __restrict__ in_comp,
+                               __nv_bfloat16* __restrict__ out, void* __restrict__ out_comp, int fmt, long long n8,
+                               int act) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float f[8];
-    unpack8(*reinterpret_cast<const uint4*>(in + i * 8), f);
+    load8c(in, in_comp, fmt, i * 8, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = r_act_fwd(f[j], act);
-    *reinterpret_cast<uint4*>(out + i * 8) = pack8(f);
+    store8c(out, out_comp, fmt, i * 8, f);
   }
 }
 
 // ---------------------------------------------------------------------------------------- 3x3 image-side layers
 // col[(n,h,w)][(c*3+kh)*3+kw] = img[n, c, h+kh-1, w+kw-1] (zero padded), columns >= ch*9 are zero; col row = 32 bf16.
-__global__ void im2col_k3s1_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ col, int NB, int ch, int H,
-                                   int W) {
+__global__ void im2col_k3s1_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ col,
+                                   void* __restrict__ col_comp, int fmt, int NB, int ch, int H, int W) {
   const long long total = (long long)NB * H * W * 4;  // 4 groups of 8 columns
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(i % 4);
@@ -290,7 +298,7 @@ __global__ void im2col_k3s1_kernel(const float* __restrict__ img, __nv_bfloat16*
       const int ih = h + kh - 1, iw = w + kw - 1;
       f[j] = (c < ch && ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(img + (((long long)n * ch + c) * H + ih) * W + iw) : 0.f;
     }
-    *reinterpret_cast<uint4*>(col + i * 8) = pack8(f);
+    store8c(col, col_comp, fmt, i * 8, f);
   }
 }
 
@@ -318,14 +326,16 @@ __global__ void col2im_k3s1_kernel(const __nv_bfloat16* __restrict__ col, float*
 }
 
 // NHWC bf16 with 8 channels (first `ch` valid) -> NCHW fp32 with optional tanh; and its gradient back.
-__global__ void nhwc8_to_image_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ img, long long NB, int ch,
+// in_f32 != 0: `in` is the fp32 output of the GEMM (the precise modes keep the pre-tanh image out of bf16).
+__global__ void nhwc8_to_image_kernel(const void* __restrict__ in, int in_f32, float* __restrict__ img, long long NB, int ch,
                                       int HW, int tanh_act) {
   const long long total = NB * ch * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long p = i % HW;
     const int c = (int)((i / HW) % ch);
     const long long n = i / ((long long)HW * ch);
-    const float v = __bfloat162float(in[(n * HW + p) * 8 + c]);
+    const long long off = (n * HW + p) * 8 + c;
+    const float v = in_f32 ? static_cast<const float*>(in)[off] : __bfloat162float(static_cast<const __nv_bfloat16*>(in)[off]);
     img[i] = tanh_act ? tanhf(v) : v;
   }
 }
@@ -355,13 +365,22 @@ __global__ void image_to_nhwc8_grad_kernel(const float* __restrict__ dout, const
 
 // ---------------------------------------------------------------------------------------- projection head
 // h[n][c] = sum_hw relu(a[n,hw,c])     (models/sngan_projection.py:190-191)
-__global__ void relu_sumpool_kernel(const __nv_bfloat16* __restrict__ a, float* __restrict__ h, int HW, int C) {
+__global__ void relu_sumpool_kernel(const __nv_bfloat16* __restrict__ a, const void* __restrict__ a_comp, int fmt,
+                                    float* __restrict__ h, int HW, int C) {
   const int n = blockIdx.y;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float acc = 0.f;
-  for (int p = 0; p < HW; ++p) acc += fmaxf(__bfloat162float(a[((long long)n * HW + p) * C + c]), 0.f);
-  h[(long long)n * C + c] = acc;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;  // 8-channel group
+  if (g * 8 >= C) return;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int p = 0; p < HW; ++p) {
+    float f[8];
+    load8c(a, a_comp, fmt, ((long long)n * HW + p) * C + g * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += fmaxf(f[j], 0.f);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) h[(long long)n * C + g * 8 + j] = acc[j];
 }
 __global__ void relu_sumpool_bwd_kernel(const float* __restrict__ dh, const __nv_bfloat16* __restrict__ a,
                                         __nv_bfloat16* __restrict__ da, long long total, int HW, int C) {
@@ -440,15 +459,17 @@ using namespace gp;
 
 extern "C" {
 
-int gp_cbn_apply_act(const void* y, void* out, int NB, int H, int W, int C, const float* mean, const float* rstd,
-                     const float* emb, const long long* labels, int act, int upsample, void* stream) {
+int gp_cbn_apply_act(const void* y, const void* y_comp, void* out, void* out_comp, int comp_fmt, int NB, int H, int W,
+                     int C, const float* mean, const float* rstd, const float* emb, const long long* labels, int act,
+                     int upsample, void* stream) {
   GP_REQUIRE(y && out && mean && rstd && NB > 0 && C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0,
              "gp_cbn_apply_act: bad arguments (C/8 must divide 256)");
+  GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_cbn_apply_act: unknown companion format %d", comp_fmt);
   GP_REQUIRE(emb == nullptr || labels != nullptr, "gp_cbn_apply_act: labels required with an embedding table");
   const CbnLaunch L = cbn_launch(NB, H * W, C);
-  cbn_apply_kernel<<<L.grid, L.block, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(y),
-                                                              static_cast<__nv_bfloat16*>(out), H, W, C, mean, rstd, emb,
-                                                              labels, act, upsample, L.ppb);
+  cbn_apply_kernel<<<L.grid, L.block, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(y), y_comp,
+                                                              static_cast<__nv_bfloat16*>(out), out_comp, comp_fmt, H, W, C,
+                                                              mean, rstd, emb, labels, act, upsample, L.ppb);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -492,26 +513,33 @@ int gp_upsample2x(const void* in, void* out, int NB, int H, int W, int C, float 
   return GP_OK;
 }
 
-int gp_pool2x(const void* in, void* out, int NB, int Hout, int Wout, int C, float scale, void* stream) {
+int gp_pool2x(const void* in, const void* in_comp, void* out, void* out_comp, int comp_fmt, int NB, int Hout, int Wout,
+              int C, float scale, void* stream) {
   GP_REQUIRE(in && out && NB > 0 && C % 8 == 0, "gp_pool2x: bad arguments");
+  GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_pool2x: unknown companion format %d", comp_fmt);
   pool2x_kernel<<<grid1((long long)NB * Hout * Wout * (C / 8)), 256, 0, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), NB, Hout, Wout, C, scale);
+      static_cast<const __nv_bfloat16*>(in), in_comp, static_cast<__nv_bfloat16*>(out), out_comp, comp_fmt, NB, Hout, Wout,
+      C, scale);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
 
-int gp_act_fwd(const void* in, void* out, long long n, int act, void* stream) {
+int gp_act_fwd(const void* in, const void* in_comp, void* out, void* out_comp, int comp_fmt, long long n, int act,
+               void* stream) {
   GP_REQUIRE(in && out && n > 0 && n % 8 == 0, "gp_act_fwd: bad arguments");
-  act_fwd_kernel<<<grid1(n / 8), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(in),
-                                                              static_cast<__nv_bfloat16*>(out), n / 8, act);
+  GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_act_fwd: unknown companion format %d", comp_fmt);
+  act_fwd_kernel<<<grid1(n / 8), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(in), in_comp,
+                                                              static_cast<__nv_bfloat16*>(out), out_comp, comp_fmt, n / 8,
+                                                              act);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
 
-int gp_im2col_k3s1(const float* img, void* col, int NB, int ch, int H, int W, void* stream) {
+int gp_im2col_k3s1(const float* img, void* col, void* col_comp, int comp_fmt, int NB, int ch, int H, int W, void* stream) {
   GP_REQUIRE(img && col && NB > 0 && ch > 0 && ch * 9 <= 32, "gp_im2col_k3s1: bad arguments");
+  GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_im2col_k3s1: unknown companion format %d", comp_fmt);
   im2col_k3s1_kernel<<<grid1((long long)NB * H * W * 4), 256, 0, as_stream(stream)>>>(
-      img, static_cast<__nv_bfloat16*>(col), NB, ch, H, W);
+      img, static_cast<__nv_bfloat16*>(col), col_comp, comp_fmt, NB, ch, H, W);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -524,10 +552,10 @@ int gp_col2im_k3s1(const void* col, float* img, int NB, int ch, int H, int W, vo
   return GP_OK;
 }
 
-int gp_nhwc8_to_image(const void* in, float* img, int NB, int ch, int HW, int tanh_act, void* stream) {
+int gp_nhwc8_to_image(const void* in, int in_f32, float* img, int NB, int ch, int HW, int tanh_act, void* stream) {
   GP_REQUIRE(in && img && NB > 0 && ch > 0 && ch <= 8, "gp_nhwc8_to_image: bad arguments");
-  nhwc8_to_image_kernel<<<grid1((long long)NB * ch * HW), 256, 0, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(in), img, NB, ch, HW, tanh_act);
+  nhwc8_to_image_kernel<<<grid1((long long)NB * ch * HW), 256, 0, as_stream(stream)>>>(in, in_f32, img, NB, ch, HW,
+                                                                                       tanh_act);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -541,10 +569,11 @@ int gp_image_to_nhwc8_grad(const float* dout, const float* out, void* dy, int NB
   return GP_OK;
 }
 
-int gp_relu_sumpool(const void* a, float* h, int NB, int HW, int C, void* stream) {
-  GP_REQUIRE(a && h && NB > 0 && HW > 0 && C > 0, "gp_relu_sumpool: bad arguments");
-  dim3 grid((C + 127) / 128, NB);
-  relu_sumpool_kernel<<<grid, 128, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(a), h, HW, C);
+int gp_relu_sumpool(const void* a, const void* a_comp, int comp_fmt, float* h, int NB, int HW, int C, void* stream) {
+  GP_REQUIRE(a && h && NB > 0 && HW > 0 && C > 0 && C % 8 == 0, "gp_relu_sumpool: bad arguments (C %% 8 == 0)");
+  GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_relu_sumpool: unknown companion format %d", comp_fmt);
+  dim3 grid((C / 8 + 63) / 64, NB);
+  relu_sumpool_kernel<<<grid, 64, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(a), a_comp, comp_fmt, h, HW, C);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }

@@ -62,17 +62,19 @@ def _f16_operand(x, x_lo):
     return x.to(torch.float16) if x_lo is None else (x.float() + x_lo.float()).to(torch.float16)
 
 
-def _bn_forward(y, gamma, beta, bufs, act, training=True, st=None, pair=False):
+def _bn_forward(y, gamma, beta, bufs, act, training=True, st=None, pair=False, comp=None, out_fmt=0):
     """y: pre-BN conv output, NHWC bf16 (fp32 in bf16x3 mode). Returns (a, a_lo, fin[4,C], count).
     training: batch statistics (all-reduced over ranks) + running-stat update, as nn.BatchNorm2d.train();
-    eval: normalise with the running statistics. st: [2, C] sums already produced by the conv epilogue."""
+    eval: normalise with the running statistics. st: [2, C] sums already produced by the conv epilogue.
+    comp / out_fmt: y is an existing activation with a companion tensor (csrc/act_io.cuh) / the companion format to
+    produce (the ResNet and blur nodes, which normalise something other than a conv's fp32 output)."""
     C = y.shape[-1]
     count = (y.numel() // C) * parallel.world_size()
     rm, rv, nbt = bufs if bufs is not None else (None, None, None)
     f32 = y.dtype == torch.float32
     if training or rm is None:
         if st is None:
-            st = ops.bn_stats_f32(y) if f32 else ops.bn_stats(y)
+            st = ops.bn_stats_f32(y) if f32 else (ops.bn_stats_comp(y, comp) if comp is not None else ops.bn_stats(y))
         ctx = parallel.peer_ctx() if parallel.enabled() else None
         if ctx is not None and 2 * C <= ops.PEER_MAX_FLOATS:
             # SyncBN: one-shot NVLink exchange of the partial sums fused with the finalize (one launch, no NCCL)
@@ -84,6 +86,8 @@ def _bn_forward(y, gamma, beta, bufs, act, training=True, st=None, pair=False):
         fin = ops.bn_eval_params(rm, rv, gamma, beta, BN_EPS)
     if f32:
         a, a_lo = ops.bn_apply_act_pair(y, fin, act) if pair else ops.bn_apply_act_split(y, fin, act)
+    elif comp is not None or out_fmt:
+        a, a_lo = ops.bn_apply_act_comp(y, comp, fin, act, out_fmt)
     else:
         a, a_lo = ops.bn_apply_act(y, fin, act), None
     return a, a_lo, fin, count
@@ -398,10 +402,8 @@ class Head(torch.autograd.Function):
         O = weight.shape[0]
         strides = (C * H * W, H * W, 1) if flatten else (C, 1, 0)
         b = bias.detach() if bias is not None else None
-        if a_lo is not None and a_lo.dtype != torch.bfloat16:   # an fp16 operand copy is not a low half
-            a_lo = None
-        if a_lo is not None:
-            out = ops.head_fwd_split(a, a_lo, weight.detach(), b, O, *strides)
+        if a_lo is not None:            # bf16 low half or fp16 copy: read the most precise view of the features
+            out = ops.head_fwd_comp(a, a_lo, weight.detach(), b, O, *strides)
         else:
             out = ops.head_fwd(a, weight.detach(), b, O, *strides)
         ctx.save_for_backward(a, weight)
@@ -428,10 +430,8 @@ class PackedHeads(torch.autograd.Function):
         w = torch.cat([w1.detach(), w2.detach()], 0)    # (O1 + O2, C) fp32, a few tens of KB
         b = torch.cat([b1.detach(), b2.detach()], 0)
         strides = (C * H * W, H * W, 1) if flatten else (C, 1, 0)
-        if a_lo is not None and a_lo.dtype != torch.bfloat16:
-            a_lo = None
         if a_lo is not None:
-            out = ops.head_fwd_split(a, a_lo, w, b, O1 + O2, *strides)
+            out = ops.head_fwd_comp(a, a_lo, w, b, O1 + O2, *strides)
         else:
             out = ops.head_fwd(a, w, b, O1 + O2, *strides)
         ctx.save_for_backward(a, w)

@@ -5,10 +5,9 @@ G: relu(Linear) -> view -> n x [nearest x2 -> Conv3x3 -> BlurPool(stride 1) -> B
 D: n x [Conv3x3 (+BN from block 1) -> LeakyReLU 0.2 (-> BlurPool(stride 2) except after the last block)] -> sum -> Linear
 Same constructor arguments, sub-module indices and state_dict keys (`blocks.i.1.*` conv, `blocks.i.2.filt`, `blocks.i.3.*`
 BN in G; `blocks.i.0.*`, `blocks.i.1.*`, `blocks.i.{2|3}.filt` in D); torch layers are fp32 parameter holders built in the
-reference's order (same RNG stream). These nodes run the plain bf16 operand mode (like the ResNet nodes)."""
+reference's order (same RNG stream). All three forward precision modes of config.py run here (functional_resnet.py)."""
 import torch.nn as nn
 
-from .. import config
 from .. import functional as GF
 from .. import functional_resnet as GR
 from .. import ops
@@ -29,9 +28,12 @@ def D_arch(ndf=64, img_dim=3):
             for r, (i, o) in plan.items()}
 
 
-def _bf16_mode():
-    """The dcgan_blur nodes implement the plain bf16 operand mode only."""
-    return config.precision_scope("bf16")
+def _node(fn, h, *args):
+    return GR.attach(fn.apply(h, GR.comp_of(h), *args))
+
+
+def _conv(h, conv, cache, key):
+    return GR.attach(GR.Conv2dNHWC.apply(h, GR.comp_of(h), conv.weight, conv.bias, None, None, ops.ACT_NONE, cache, key))
 
 
 class Generator(nn.Module):
@@ -58,17 +60,16 @@ class Generator(nn.Module):
 
     def forward(self, z):
         require_cuda(z, "dcgan_blur.Generator")
-        with _bf16_mode():
-            h = GF.linear_to_nhwc(z, self.linear.weight, self.linear.bias, self.bottom_width, ops.ACT_RELU,
-                                  self._gp_cache, "linear")
-            for i, block in enumerate(self.blocks):
-                conv, blur, bn = block[1], block[2], block[3]
-                h = GR.Upsample2x.apply(h)
-                h = GR.Conv2dNHWC.apply(h, conv.weight, conv.bias, None, ops.ACT_NONE, self._gp_cache, "blocks.%d" % i)
-                h = blur.forward_nhwc(h)
-                h = GR.BNAct.apply(h, bn.weight, bn.bias, bn_buffers(bn), ops.ACT_LRELU, self.training)
-            last = self.out_layer[0]
-            return GR.ImageOut3.apply(h, last.weight, last.bias)
+        h = GF.linear_to_nhwc(z, self.linear.weight, self.linear.bias, self.bottom_width, ops.ACT_RELU,
+                              self._gp_cache, "linear")
+        for i, block in enumerate(self.blocks):
+            conv, blur, bn = block[1], block[2], block[3]
+            h = _node(GR.Upsample2x, h)
+            h = _conv(h, conv, self._gp_cache, "blocks.%d" % i)
+            h = blur.forward_nhwc(h)
+            h = _node(GR.BNAct, h, bn.weight, bn.bias, bn_buffers(bn), ops.ACT_LRELU, self.training)
+        last = self.out_layer[0]
+        return GR.ImageOut3.apply(h, GR.comp_of(h), last.weight, last.bias)
 
 
 class Discriminator(nn.Module):
@@ -96,16 +97,15 @@ class Discriminator(nn.Module):
 
     def forward(self, x):
         require_cuda(x, "dcgan_blur.Discriminator")
-        with _bf16_mode():
-            n_blocks = len(self.blocks)
-            for idx, block in enumerate(self.blocks):
-                conv = block[0]
-                if idx == 0:
-                    h = GR.ImageConv3Act.apply(x, conv.weight, conv.bias, ops.ACT_LRELU, self._gp_cache, "blocks.0")
-                else:
-                    bn = block[1]
-                    h = GR.Conv2dNHWC.apply(h, conv.weight, conv.bias, None, ops.ACT_NONE, self._gp_cache, "blocks.%d" % idx)
-                    h = GR.BNAct.apply(h, bn.weight, bn.bias, bn_buffers(bn), ops.ACT_LRELU, self.training)
-                if idx < n_blocks - 1:
-                    h = block[-1].forward_nhwc(h)
-            return GF.Head.apply(h, None, self.out_layer.weight, self.out_layer.bias, False)
+        n_blocks = len(self.blocks)
+        for idx, block in enumerate(self.blocks):
+            conv = block[0]
+            if idx == 0:
+                h = GR.attach(GR.ImageConv3Act.apply(x, conv.weight, conv.bias, ops.ACT_LRELU, self._gp_cache, "blocks.0"))
+            else:
+                bn = block[1]
+                h = _conv(h, conv, self._gp_cache, "blocks.%d" % idx)
+                h = _node(GR.BNAct, h, bn.weight, bn.bias, bn_buffers(bn), ops.ACT_LRELU, self.training)
+            if idx < n_blocks - 1:
+                h = block[-1].forward_nhwc(h)
+        return GF.Head.apply(h, GR.comp_of(h), self.out_layer.weight, self.out_layer.bias, False)

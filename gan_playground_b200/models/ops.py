@@ -34,7 +34,7 @@ class BlurPool2d(nn.Module):
             raise _lib.GpError("BlurPool2d(filt_size=%d, pad_type=%r, stride=%d, pad_off=%d) is not on the B200 hot path; "
                                "only filt_size=3 / reflect / stride 1|2 (models/dcgan_blur.py) is implemented"
                                % (self.filt_size, self.pad_type, self.stride, self.pad_off))
-        return GR.BlurPool.apply(h, self.stride)
+        return GR.attach(GR.BlurPool.apply(h, GR.comp_of(h), self.stride))
 
     def forward(self, inp):
         """Stand-alone use on an NCHW tensor, as in the reference (fp32 in / fp32 out, computed in bf16 NHWC)."""
@@ -42,21 +42,14 @@ class BlurPool2d(nn.Module):
             raise _lib.GpError("BlurPool2d: input is on %s — this implementation runs only on CUDA" % (inp.device,))
         if inp.shape[1] % 8 != 0:
             raise _lib.GpError("BlurPool2d: channels must be a multiple of 8 on the B200 path")
+        from .. import config
+
         h = inp.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
-        return self.forward_nhwc(h).permute(0, 3, 1, 2).to(inp.dtype)
+        with config.precision_scope("bf16"):
+            return self.forward_nhwc(h).permute(0, 3, 1, 2).to(inp.dtype)
 
 
 class BlurPool1d(nn.Module):
     def __init__(self, pad_type='reflect', filt_size=3, stride=2, channels=None, pad_off=0):
         super().__init__()
         raise _lib.GpError("BlurPool1d is not used by any network on the B200 hot path (models/ops.py:61-101 upstream)")
-
-
-def get_pad_layer(pad_type):
-    if pad_type in ['refl', 'reflect']:
-        return nn.ReflectionPad2d
-    if pad_type in ['repl', 'replicate']:
-        return nn.ReplicationPad2d
-    if pad_type == 'zero':
-        return nn.ZeroPad2d
-    print('Pad type [%s] not recognized' % pad_type)

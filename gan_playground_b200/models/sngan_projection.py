@@ -8,10 +8,20 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import config
 from .. import functional as GF
 from .. import functional_resnet as GR
 from .. import ops
 from ._common import bn_buffers, require_cuda
+
+
+def _node(fn, h, *args):
+    """Apply a node to an activation carrying its companion tensor (`_gp_lo`); re-attach the output's."""
+    return GR.attach(fn.apply(h, GR.comp_of(h), *args))
+
+
+def _conv(h, weight, bias, residual, act, cache, key):
+    return GR.attach(GR.Conv2dNHWC.apply(h, GR.comp_of(h), weight, bias, residual, GR.comp_of(residual), act, cache, key))
 
 
 def _act_code(activation):
@@ -58,7 +68,7 @@ class ConditionalBatchNorm2d(nn.Module):
 
     def forward(self, x, y, act=ops.ACT_NONE, upsample=False):
         """x: NHWC bf16 feature map (internal layout), y: int64 labels."""
-        return GR.CondBNAct.apply(x, self.embed.weight, y, bn_buffers(self.bn), act, upsample, self.training)
+        return _node(GR.CondBNAct, x, self.embed.weight, y, bn_buffers(self.bn), act, upsample, self.training)
 
 
 class ResGenBlock(nn.Module):
@@ -84,22 +94,22 @@ class ResGenBlock(nn.Module):
         act = _act_code(self.activation)
         if y is not None:
             return bn(h, y, act=act, upsample=upsample)
-        h = GR.BNAct.apply(h, bn.weight, bn.bias, bn_buffers(bn), act, self.training)
-        return GR.Upsample2x.apply(h) if upsample else h
+        h = _node(GR.BNAct, h, bn.weight, bn.bias, bn_buffers(bn), act, self.training)
+        return _node(GR.Upsample2x, h) if upsample else h
 
     def forward(self, x, y=None):
         """x: NHWC bf16. cBN -> ReLU -> nearest x2 -> c1 -> cBN -> ReLU -> c2, plus shortcut c_sc(nearest x2(x))
         (reference :48-66). The 1x1 shortcut conv commutes with nearest upsampling, so it runs on the small grid."""
         h = self._norm_act(self.b1, x, y, self.upsample)
-        h = GR.Conv2dNHWC.apply(h, self.c1.weight, self.c1.bias, None, ops.ACT_NONE, self._gp_cache, "c1")
+        h = _conv(h, self.c1.weight, self.c1.bias, None, ops.ACT_NONE, self._gp_cache, "c1")
         h = self._norm_act(self.b2, h, y, False)
         if self.learnable_sc:
-            sc = GR.Conv2dNHWC.apply(x, self.c_sc.weight, self.c_sc.bias, None, ops.ACT_NONE, self._gp_cache, "c_sc")
+            sc = _conv(x, self.c_sc.weight, self.c_sc.bias, None, ops.ACT_NONE, self._gp_cache, "c_sc")
             if self.upsample:
-                sc = GR.Upsample2x.apply(sc)
+                sc = _node(GR.Upsample2x, sc)
         else:
             sc = x
-        return GR.Conv2dNHWC.apply(h, self.c2.weight, self.c2.bias, sc, ops.ACT_NONE, self._gp_cache, "c2")
+        return _conv(h, self.c2.weight, self.c2.bias, sc, ops.ACT_NONE, self._gp_cache, "c2")
 
 
 class ResNetGenerator(nn.Module):
@@ -116,13 +126,15 @@ class ResNetGenerator(nn.Module):
 
     def forward(self, z, y):
         require_cuda(z, "sngan_projection.ResNetGenerator")
-        h = GF.linear_to_nhwc(z, self.l1.weight, self.l1.bias, self.bottom_width, ops.ACT_NONE, self._gp_cache, "l1")
-        if y is not None:
-            y = y.contiguous()
-        for block in (self.block2, self.block3, self.block4, self.block5):
-            h = block(h, y)
-        h = GR.BNAct.apply(h, self.b6.weight, self.b6.bias, bn_buffers(self.b6), _act_code(self.activation), self.training)
-        return GR.ImageOut3.apply(h, self.l6.weight, self.l6.bias)
+        with config.resnet_scope():
+            h = GF.linear_to_nhwc(z, self.l1.weight, self.l1.bias, self.bottom_width, ops.ACT_NONE, self._gp_cache, "l1")
+            if y is not None:
+                y = y.contiguous()
+            for block in (self.block2, self.block3, self.block4, self.block5):
+                h = block(h, y)
+            h = _node(GR.BNAct, h, self.b6.weight, self.b6.bias, bn_buffers(self.b6), _act_code(self.activation),
+                      self.training)
+            return GR.ImageOut3.apply(h, GR.comp_of(h), self.l6.weight, self.l6.bias)
 
 
 class ResDisBlock(nn.Module):
@@ -144,12 +156,12 @@ class ResDisBlock(nn.Module):
         Pooling is linear, so the shortcut is added in c2's epilogue and the sum is pooled once."""
         _act_code(self.activation)
         t = self.training
-        h = GR.ReluFn.apply(x)
-        h = GR.Conv2dNHWC.apply(h, _sn(self.c1, t), self.c1.bias, None, ops.ACT_RELU, self._gp_cache, "c1")
-        sc = GR.Conv2dNHWC.apply(x, _sn(self.c_sc, t), self.c_sc.bias, None, ops.ACT_NONE, self._gp_cache, "c_sc") \
+        h = _node(GR.ReluFn, x)
+        h = _conv(h, _sn(self.c1, t), self.c1.bias, None, ops.ACT_RELU, self._gp_cache, "c1")
+        sc = _conv(x, _sn(self.c_sc, t), self.c_sc.bias, None, ops.ACT_NONE, self._gp_cache, "c_sc") \
             if self.learnable_sc else x
-        h = GR.Conv2dNHWC.apply(h, _sn(self.c2, t), self.c2.bias, sc, ops.ACT_NONE, self._gp_cache, "c2")
-        return GR.Pool2x.apply(h) if self.downsample else h
+        h = _conv(h, _sn(self.c2, t), self.c2.bias, sc, ops.ACT_NONE, self._gp_cache, "c2")
+        return _node(GR.Pool2x, h) if self.downsample else h
 
 
 class ResDisOptimizedBlock(nn.Module):
@@ -165,9 +177,10 @@ class ResDisOptimizedBlock(nn.Module):
         """x: fp32 NCHW image. c1 -> relu -> c2 -> avgpool, plus avgpool(c_sc(x)) (reference :156-164)."""
         _act_code(self.activation)
         t = self.training
-        h1, sc = GR.ImageConv3.apply(x, _sn(self.c1, t), self.c1.bias, _sn(self.c_sc, t), self.c_sc.bias)
-        h = GR.Conv2dNHWC.apply(h1, _sn(self.c2, t), self.c2.bias, sc, ops.ACT_NONE, self._gp_cache, "c2")
-        return GR.Pool2x.apply(h)
+        h1, h1c, sc, scc = GR.ImageConv3.apply(x, _sn(self.c1, t), self.c1.bias, _sn(self.c_sc, t), self.c_sc.bias)
+        h1, sc = GR.attach((h1, h1c)), GR.attach((sc, scc))
+        h = _conv(h1, _sn(self.c2, t), self.c2.bias, sc, ops.ACT_NONE, self._gp_cache, "c2")
+        return _node(GR.Pool2x, h)
 
 
 class SNResNetProjectionDiscriminator(nn.Module):
@@ -185,12 +198,14 @@ class SNResNetProjectionDiscriminator(nn.Module):
     def forward(self, x, y=None):
         require_cuda(x, "sngan_projection.SNResNetProjectionDiscriminator")
         _act_code(self.activation)
-        h = self.block1(x)
-        for block in (self.block2, self.block3, self.block4, self.block5):
-            h = block(h)
-        t = self.training
-        Ey = _sn(self.l_y, t) if (y is not None) else None
-        return GR.ProjHead.apply(h, _sn(self.l6, t), self.l6.bias, Ey, y.contiguous() if y is not None else None)
+        with config.resnet_scope():
+            h = self.block1(x)
+            for block in (self.block2, self.block3, self.block4, self.block5):
+                h = block(h)
+            t = self.training
+            Ey = _sn(self.l_y, t) if (y is not None) else None
+            return GR.ProjHead.apply(h, GR.comp_of(h), _sn(self.l6, t), self.l6.bias, Ey,
+                                     y.contiguous() if y is not None else None)
 
 
 if __name__ == "__main__":

@@ -111,8 +111,9 @@ class ZeroArena:
     accumulate into (split-K weight gradients, BatchNorm partial sums, bias-gradient sums) are carved out of one buffer
     that `begin()` clears at the start of a step. Slices are valid until the next `begin()`, which every consumer on the
     training path satisfies (the sums are finalised / unpacked / accumulated into .grad within the same step).
-    Only engine.DcganStep activates it (parameters there always own a .grad view, so autograd never adopts a slice as
-    .grad); everywhere else `zeros()` is torch.zeros."""
+    The three step drivers of engine.py (DcganStep / SnganStep / AcganStep) activate it — their parameters always own a
+    .grad view (FusedAdam / GradBucket), so autograd never adopts a slice as .grad; everywhere else `zeros()` is
+    torch.zeros."""
 
     active = None
 
@@ -195,7 +196,7 @@ def _timed(name, flops, fn):
 _TAPS_PER_OUT = {KIND_CONV_K4S2: 16, KIND_CONVT_K4S2: 4, KIND_CONV_K3S1: 9, KIND_CONV_K1S1: 1}
 
 
-CONV_IN_F16, CONV_LO_F16 = 1, 2
+CONV_IN_F16, CONV_LO_F16, CONV_RES_F16 = 1, 2, 4
 
 
 def conv_fwd(x, wp, bias, kind, Hout, Wout, act=ACT_NONE, stats=None, flops=None, residual=None, x_lo=None,
@@ -225,6 +226,8 @@ def conv_fwd(x, wp, bias, kind, Hout, Wout, act=ACT_NONE, stats=None, flops=None
         elif out_mode == "pair":
             out_lo = torch.empty(shape, device=x.device, dtype=torch.float16)
     flags = (CONV_IN_F16 if fp16_in else 0) | (CONV_LO_F16 if out_mode == "pair" else 0)
+    if residual is not None and residual.dtype == torch.float16:   # the fp16 companion of the shortcut activation
+        flags |= CONV_RES_F16
     if bias is not None:
         _chk(bias, torch.float32, "bias")
     if x_lo is not None:
@@ -492,32 +495,61 @@ def sn_grad(g, w_sn, dim, u, v, sigma):
 
 # ------------------------------------------------------------------------------------------------ SNGAN projection
 _SIGS.update({
-    "gp_cbn_apply_act": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "gp_cbn_apply_act": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "gp_cbn_bwd_reduce": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp],
     "gp_cbn_bwd_apply": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _i, _i, _vp],
     "gp_upsample2x": [_vp, _vp, _i, _i, _i, _i, _f, _vp],
-    "gp_pool2x": [_vp, _vp, _i, _i, _i, _i, _f, _vp],
-    "gp_act_fwd": [_vp, _vp, _ll, _i, _vp],
-    "gp_im2col_k3s1": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "gp_pool2x": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
+    "gp_act_fwd": [_vp, _vp, _vp, _vp, _i, _ll, _i, _vp],
+    "gp_im2col_k3s1": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "gp_col2im_k3s1": [_vp, _vp, _i, _i, _i, _i, _vp],
-    "gp_nhwc8_to_image": [_vp, _vp, _i, _i, _i, _i, _vp],
+    "gp_nhwc8_to_image": [_vp, _i, _vp, _i, _i, _i, _i, _vp],
     "gp_image_to_nhwc8_grad": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
-    "gp_relu_sumpool": [_vp, _vp, _i, _i, _i, _vp],
+    "gp_relu_sumpool": [_vp, _vp, _i, _vp, _i, _i, _i, _vp],
     "gp_relu_sumpool_bwd": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "gp_proj_head_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "gp_proj_head_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
 })
 
 
-def cbn_apply_act(y, fin, emb, labels, act, upsample):
-    """y: bf16 (NB, H, W, C); fin: [4, C] from bn_finalize (mean, rstd, ...); emb: fp32 [ncls, 2C] or None."""
+COMP_NONE, COMP_LO, COMP_F16 = 0, 1, 2
+_COMP_DTYPE = {COMP_LO: torch.bfloat16, COMP_F16: torch.float16}
+
+
+def comp_fmt_of(comp):
+    """Companion format of a companion tensor (act_io.cuh): fp16 = copy of the value, bf16 = low half, None = none."""
+    if comp is None:
+        return COMP_NONE
+    return COMP_F16 if comp.dtype == torch.float16 else COMP_LO
+
+
+def _comp_io(comp, out_fmt, shape, device):
+    """(input companion to pass, kernel format, output companion tensor or None). One format per call: an input
+    companion of another format than the requested output's is dropped (the bf16 tensor alone is read)."""
+    fmt_in = comp_fmt_of(comp)
+    if comp is not None and out_fmt not in (COMP_NONE, fmt_in):
+        comp, fmt_in = None, COMP_NONE
+    fmt = fmt_in or out_fmt
+    out_comp = torch.empty(shape, device=device, dtype=_COMP_DTYPE[out_fmt]) if out_fmt else None
+    return comp, fmt, out_comp
+
+
+def _ret(out, out_comp, out_fmt):
+    return (out, out_comp) if out_fmt else out
+
+
+def cbn_apply_act(y, fin, emb, labels, act, upsample, comp=None, out_fmt=COMP_NONE):
+    """y: bf16 (NB, H, W, C); fin: [4, C] from bn_finalize (mean, rstd, ...); emb: fp32 [ncls, 2C] or None.
+    comp: companion of y; out_fmt != 0: returns (out, out_comp)."""
     _chk(y, torch.bfloat16, "y")
     NB, H, W, C = y.shape
     s = 2 if upsample else 1
-    out = torch.empty((NB, s * H, s * W, C), device=y.device, dtype=torch.bfloat16)
-    check(_fn("gp_cbn_apply_act")(_p(y), _p(out), NB, H, W, C, _p(fin[0]), _p(fin[1]), _p(emb), _p(labels), act,
-                                  1 if upsample else 0, _stream()), "gp_cbn_apply_act")
-    return out
+    shape = (NB, s * H, s * W, C)
+    out = torch.empty(shape, device=y.device, dtype=torch.bfloat16)
+    comp, fmt, out_comp = _comp_io(comp, out_fmt, shape, y.device)
+    check(_fn("gp_cbn_apply_act")(_p(y), _p(comp), _p(out), _p(out_comp), fmt, NB, H, W, C, _p(fin[0]), _p(fin[1]), _p(emb),
+                                  _p(labels), act, 1 if upsample else 0, _stream()), "gp_cbn_apply_act")
+    return _ret(out, out_comp, out_fmt)
 
 
 def cbn_bwd_reduce(da, y, fin, emb, labels, act, upsample, n_classes):
@@ -541,34 +573,43 @@ def cbn_bwd_apply(da, y, fin, emb, labels, S, count, act, upsample):
 
 
 def upsample2x(x, scale=1.0):
-    _chk(x, torch.bfloat16, "x")
+    """Nearest x2. scale == 1 is a pure 16-bit copy, so an fp16 companion tensor goes through the same kernel."""
+    if x.dtype == torch.float16 and scale == 1.0:
+        _chk(x, torch.float16, "x")
+    else:
+        _chk(x, torch.bfloat16, "x")
     NB, H, W, C = x.shape
-    out = torch.empty((NB, 2 * H, 2 * W, C), device=x.device, dtype=torch.bfloat16)
+    out = torch.empty((NB, 2 * H, 2 * W, C), device=x.device, dtype=x.dtype)
     check(_fn("gp_upsample2x")(_p(x), _p(out), NB, H, W, C, scale, _stream()), "gp_upsample2x")
     return out
 
 
-def pool2x(x, scale):
+def pool2x(x, scale, comp=None, out_fmt=COMP_NONE):
     _chk(x, torch.bfloat16, "x")
     NB, H, W, C = x.shape
-    out = torch.empty((NB, H // 2, W // 2, C), device=x.device, dtype=torch.bfloat16)
-    check(_fn("gp_pool2x")(_p(x), _p(out), NB, H // 2, W // 2, C, scale, _stream()), "gp_pool2x")
-    return out
+    shape = (NB, H // 2, W // 2, C)
+    out = torch.empty(shape, device=x.device, dtype=torch.bfloat16)
+    comp, fmt, out_comp = _comp_io(comp, out_fmt, shape, x.device)
+    check(_fn("gp_pool2x")(_p(x), _p(comp), _p(out), _p(out_comp), fmt, NB, H // 2, W // 2, C, scale, _stream()), "gp_pool2x")
+    return _ret(out, out_comp, out_fmt)
 
 
-def act_fwd(x, act):
+def act_fwd(x, act, comp=None, out_fmt=COMP_NONE):
     _chk(x, torch.bfloat16, "x")
     out = torch.empty_like(x)
-    check(_fn("gp_act_fwd")(_p(x), _p(out), x.numel(), act, _stream()), "gp_act_fwd")
-    return out
+    comp, fmt, out_comp = _comp_io(comp, out_fmt, x.shape, x.device)
+    check(_fn("gp_act_fwd")(_p(x), _p(comp), _p(out), _p(out_comp), fmt, x.numel(), act, _stream()), "gp_act_fwd")
+    return _ret(out, out_comp, out_fmt)
 
 
-def im2col_k3s1(img):
+def im2col_k3s1(img, out_fmt=COMP_NONE):
     _chk(img, torch.float32, "img")
     NB, ch, H, W = img.shape
-    col = torch.empty((NB, H, W, 32), device=img.device, dtype=torch.bfloat16)
-    check(_fn("gp_im2col_k3s1")(_p(img), _p(col), NB, ch, H, W, _stream()), "gp_im2col_k3s1")
-    return col
+    shape = (NB, H, W, 32)
+    col = torch.empty(shape, device=img.device, dtype=torch.bfloat16)
+    _, fmt, col_comp = _comp_io(None, out_fmt, shape, img.device)
+    check(_fn("gp_im2col_k3s1")(_p(img), _p(col), _p(col_comp), fmt, NB, ch, H, W, _stream()), "gp_im2col_k3s1")
+    return _ret(col, col_comp, out_fmt)
 
 
 def col2im_k3s1(col, ch):
@@ -580,10 +621,15 @@ def col2im_k3s1(col, ch):
 
 
 def nhwc8_to_image(x, ch, tanh_act):
-    _chk(x, torch.bfloat16, "x")
+    """x: bf16 or fp32 (NB, H, W, 8) -> fp32 NCHW image of the first `ch` channels."""
+    if x.dtype != torch.float32:
+        _chk(x, torch.bfloat16, "x")
+    else:
+        _chk(x, torch.float32, "x")
     NB, H, W, _ = x.shape
     img = torch.empty((NB, ch, H, W), device=x.device, dtype=torch.float32)
-    check(_fn("gp_nhwc8_to_image")(_p(x), _p(img), NB, ch, H * W, 1 if tanh_act else 0, _stream()), "gp_nhwc8_to_image")
+    check(_fn("gp_nhwc8_to_image")(_p(x), 1 if x.dtype == torch.float32 else 0, _p(img), NB, ch, H * W,
+                                   1 if tanh_act else 0, _stream()), "gp_nhwc8_to_image")
     return img
 
 
@@ -596,11 +642,11 @@ def image_to_nhwc8_grad(dout, out, tanh_act):
     return dy
 
 
-def relu_sumpool(a):
+def relu_sumpool(a, comp=None):
     _chk(a, torch.bfloat16, "a")
     NB, H, W, C = a.shape
     h = torch.empty((NB, C), device=a.device, dtype=torch.float32)
-    check(_fn("gp_relu_sumpool")(_p(a), _p(h), NB, H * W, C, _stream()), "gp_relu_sumpool")
+    check(_fn("gp_relu_sumpool")(_p(a), _p(comp), comp_fmt_of(comp), _p(h), NB, H * W, C, _stream()), "gp_relu_sumpool")
     return h
 
 
@@ -639,11 +685,14 @@ _SIGS.update({
     "gp_bn_apply_act_split": [_vp, _vp, _vp, _ll, _i, _vp, _vp, _i, _vp],
     "gp_bn_apply_act_pair": [_vp, _vp, _vp, _ll, _i, _vp, _vp, _i, _vp],
     "gp_pair_to_f16": [_vp, _vp, _ll, _vp, _ll, _ll, _i, _vp],
+    "gp_bn_stats_comp": [_vp, _vp, _i, _ll, _i, _vp, _vp, _vp],
+    "gp_bn_apply_act_comp": [_vp, _vp, _vp, _vp, _i, _ll, _i, _vp, _vp, _i, _vp],
     "gp_bn_bwd_reduce_f32": [_vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
     "gp_bn_bwd_apply_f32": [_vp, _vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _vp],
     "gp_im2col_k4s2_split": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "gp_col2im_k4s2_f32": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "gp_head_fwd_split": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _vp],
+    "gp_head_fwd_comp": [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _vp],
 })
 
 
@@ -710,6 +759,27 @@ def bn_bwd_apply_f32(da, y, fin, red, count, act):
     return dy
 
 
+def bn_stats_comp(x, comp):
+    """Per-channel sum / sum of squares of an activation read through its companion (most precise view)."""
+    _chk(x, torch.bfloat16, "x")
+    C = x.shape[-1]
+    st = zeros((2, C), x.device)
+    check(_fn("gp_bn_stats_comp")(_p(x), _p(comp), comp_fmt_of(comp), x.numel() // C, C, _p(st[0]), _p(st[1]), _stream()),
+          "gp_bn_stats_comp")
+    return st
+
+
+def bn_apply_act_comp(y, comp, fin, act, out_fmt):
+    """act(y * scale + shift) of an activation with a companion; returns (out, out_comp)."""
+    _chk(y, torch.bfloat16, "y")
+    C = y.shape[-1]
+    out = torch.empty_like(y)
+    comp, fmt, out_comp = _comp_io(comp, out_fmt, y.shape, y.device)
+    check(_fn("gp_bn_apply_act_comp")(_p(y), _p(comp), _p(out), _p(out_comp), fmt, y.numel() // C, C, _p(fin[2]), _p(fin[3]),
+                                      act, _stream()), "gp_bn_apply_act_comp")
+    return out, out_comp
+
+
 def pair_to_f16(hi, lo, rows, cols, ld_in, out=None):
     """fp16(hi + lo) of a hi/lo bf16 pair stored with row pitch ld_in -> fp16 [rows, cols] (the single-MMA operand of the
     fp16 mode). hi / lo may be views into one staging buffer (e.g. the hi | lo halves of a packed weight row)."""
@@ -768,6 +838,16 @@ def head_fwd_split(a_hi, a_lo, w, bias, O, s_o, s_c, s_hw):
     out = torch.empty((NB, O), device=a_hi.device, dtype=torch.float32)
     check(_fn("gp_head_fwd_split")(_p(a_hi), _p(a_lo), _p(w), _p(bias), _p(out), NB, H * W, C, O, s_o, s_c, s_hw, _stream()),
           "gp_head_fwd_split")
+    return out
+
+
+def head_fwd_comp(a, comp, w, bias, O, s_o, s_c, s_hw):
+    """head_fwd reading the features through their companion tensor (fp16 copy or bf16 low half)."""
+    _chk(a, torch.bfloat16, "a")
+    NB, H, W, C = a.shape
+    out = torch.empty((NB, O), device=a.device, dtype=torch.float32)
+    check(_fn("gp_head_fwd_comp")(_p(a), _p(comp), comp_fmt_of(comp), _p(w), _p(bias), _p(out), NB, H * W, C, O, s_o, s_c,
+                                  s_hw, _stream()), "gp_head_fwd_comp")
     return out
 
 
@@ -833,18 +913,20 @@ def bn_finalize_peer(ctx, st, count, gamma, beta, running_mean, running_var, nbt
 
 # ------------------------------------------------------------------------------------------------ BlurPool2d (dcgan_blur)
 _SIGS.update({
-    "gp_blur3x3_fwd": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "gp_blur3x3_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "gp_blur3x3_bwd": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
 })
 
 
-def blur3x3_fwd(x, stride):
+def blur3x3_fwd(x, stride, comp=None, out_fmt=COMP_NONE):
     """x: bf16 (NB, H, W, C) -> reflect-padded [1,2,1]x[1,2,1]/16 depth-wise blur at `stride` (models/ops.py:7-47)."""
     _chk(x, torch.bfloat16, "x")
     NB, H, W, C = x.shape
-    out = torch.empty((NB, (H - 1) // stride + 1, (W - 1) // stride + 1, C), device=x.device, dtype=torch.bfloat16)
-    check(_fn("gp_blur3x3_fwd")(_p(x), _p(out), NB, H, W, C, stride, _stream()), "gp_blur3x3_fwd")
-    return out
+    shape = (NB, (H - 1) // stride + 1, (W - 1) // stride + 1, C)
+    out = torch.empty(shape, device=x.device, dtype=torch.bfloat16)
+    comp, fmt, out_comp = _comp_io(comp, out_fmt, shape, x.device)
+    check(_fn("gp_blur3x3_fwd")(_p(x), _p(comp), _p(out), _p(out_comp), fmt, NB, H, W, C, stride, _stream()), "gp_blur3x3_fwd")
+    return _ret(out, out_comp, out_fmt)
 
 
 def blur3x3_bwd(dout, H, W, stride):

@@ -75,7 +75,10 @@ class FusedAdam(torch.optim.Optimizer):
                 p.grad = v
 
     def _collect(self, st):
-        # a backward that ran while .grad was None created a fresh tensor: fold it back into the flat buffer
+        # a backward that ran while .grad was None created a fresh tensor: fold it back into the flat buffer.
+        # NOTE: a parameter that received NO gradient is updated with a zero gradient (its moments decay and it moves by
+        # lr * m / (sqrt(v) + eps)), whereas torch.optim.Adam skips it: FusedAdam requires every parameter to take part
+        # in every step — true for all networks / loops of the hot path (each step back-propagates through the whole net).
         for p, v in zip(st["params"], st["gviews"]):
             g = p.grad
             if g is None:
@@ -110,17 +113,29 @@ class FusedAdam(torch.optim.Optimizer):
         return loss
 
     # ---- torch.optim.Adam-shaped state for checkpoints ------------------------------------------------------------
+    @staticmethod
+    def _torch_adam_group_defaults():
+        """Every key torch.optim.Adam keeps in a param group (weight_decay, amsgrad, maximize, foreach, capturable,
+        differentiable, fused, ... — whatever this torch version has), at the values the reference scripts run with:
+        torch's load_state_dict REPLACES the groups wholesale, so a checkpoint that lacks them breaks the next step()."""
+        d = dict(torch.optim.Adam([torch.zeros(1)]).defaults)
+        d.pop("lr", None), d.pop("betas", None), d.pop("eps", None)
+        return d
+
     def state_dict(self):
-        """Same layout as torch.optim.Adam.state_dict() (per-parameter step / exp_avg / exp_avg_sq); with shard=True the
-        moments of other ranks' slices are zeros (gather the ranks' state dicts to checkpoint a sharded run)."""
+        """Same layout as torch.optim.Adam.state_dict(): per-parameter step (a CPU fp32 scalar, as torch writes it for a
+        non-capturable Adam) / exp_avg / exp_avg_sq, and param groups carrying every torch.optim.Adam key, so the
+        checkpoint loads into the reference scripts' torch.optim.Adam and steps. With shard=True the moments of other
+        ranks' slices are zeros (gather the ranks' state dicts to checkpoint a sharded run)."""
         state, idx = {}, 0
         groups = []
+        extra = self._torch_adam_group_defaults()
         for group, st in zip(self.param_groups, self._flat):
             ids = []
             for p in group["params"]:
                 ids.append(idx)
                 idx += 1
-            groups.append({**{k: v for k, v in group.items() if k != "params"}, "params": ids})
+            groups.append({**extra, **{k: v for k, v in group.items() if k != "params"}, "params": ids})
             if st is None:
                 continue
             full_m = torch.zeros(st["n"], device=st["m"].device)
@@ -129,7 +144,7 @@ class FusedAdam(torch.optim.Optimizer):
             full_v[st["lo"]:st["hi"]] = st["v"]
             pid = {id(p): i for i, p in zip(ids, group["params"])}
             for p, o in zip(st["params"], st["offs"]):
-                state[pid[id(p)]] = {"step": st["step"].clone(), "exp_avg": full_m[o:o + p.numel()].view_as(p).clone(),
+                state[pid[id(p)]] = {"step": st["step"].detach().cpu().clone(), "exp_avg": full_m[o:o + p.numel()].view_as(p).clone(),
                                      "exp_avg_sq": full_v[o:o + p.numel()].view_as(p).clone()}
         return {"state": state, "param_groups": groups}
 
@@ -137,7 +152,7 @@ class FusedAdam(torch.optim.Optimizer):
         idx = 0
         for group, st, g_sd in zip(self.param_groups, self._flat, sd["param_groups"]):
             for k, v in g_sd.items():
-                if k != "params":
+                if k in ("lr", "betas", "eps"):          # the other torch.optim.Adam keys have no meaning here
                     group[k] = v
             ids = list(range(idx, idx + len(group["params"])))
             idx += len(group["params"])

@@ -68,12 +68,16 @@ def init_peer_sync(device=None):
         return _state.get("peer") is not None
     if os.environ.get("GP_PEER_SYNC", "1") == "0" or dist.get_backend() != "nccl" or _state["world"] > 8:
         return False
+    # A rank-local failure (symmetric allocation, rendezvous) is caught into a flag; the decision is then taken by a MIN
+    # all-reduce that EVERY rank reaches, outside the try block — a rank must never fall back on its own while its peers
+    # wait in a barrier or later spin in the peer kernel.
+    from . import ops
+
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    local_ok, why, pending = 1, "", None
     try:
         import torch.distributed._symmetric_memory as symm_mem
 
-        from . import ops
-
-        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
         n = ops.peer_buffer_bytes() // 4
         buf = symm_mem.empty(n, dtype=torch.float32, device=dev)
         buf.zero_()
@@ -82,18 +86,21 @@ def init_peer_sync(device=None):
         ptrs = [int(p) for p in hdl.buffer_ptrs]
         epoch = torch.zeros(1, dtype=torch.int32, device=dev)
         torch.cuda.synchronize()
-        dist.barrier()
-        ok = torch.tensor([1 if len(ptrs) == _state["world"] and all(ptrs) else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if ok.item() != 1:
-            return False
-        _state["peer"] = {"ctx": ops.make_peer_ctx(ptrs, _state["rank"], epoch), "buf": buf, "hdl": hdl, "epoch": epoch}
-        return True
+        if len(ptrs) != _state["world"] or not all(ptrs):
+            local_ok, why = 0, "incomplete peer mapping"
+        else:
+            pending = {"ctx": ops.make_peer_ctx(ptrs, _state["rank"], epoch), "buf": buf, "hdl": hdl, "epoch": epoch}
     except Exception as exc:  # noqa: BLE001 — any rendezvous problem means "use NCCL", never a crash
-        if _state["rank"] == 0:
-            print("gan_playground_b200.parallel: peer SyncBN exchange unavailable (%s); using NCCL all-reduce" % (exc,),
-                  file=sys.stderr)
+        local_ok, why = 0, str(exc)
+    ok = torch.tensor([local_ok], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)         # doubles as the barrier after the buffers were zeroed
+    if ok.item() != 1:
+        if _state["rank"] == 0 or why:
+            print("gan_playground_b200.parallel: peer SyncBN exchange unavailable on rank %d (%s); all ranks use NCCL "
+                  "all-reduce" % (_state["rank"], why or "a peer failed"), file=sys.stderr)
         return False
+    _state["peer"] = pending
+    return True
 
 
 def peer_ctx():
@@ -142,8 +149,13 @@ def broadcast_module(module, src=0):
     """Replicate parameters and buffers from rank `src` (done once after construction)."""
     if not enabled():
         return
-    for t in list(module.parameters()) + list(module.buffers()):
-        dist.broadcast(t.data, src=src)
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t, src=src)       # in place on the parameter itself: bumps ._version for the operand caches
+    for m in module.modules():               # and drop whatever an earlier forward staged from the old values
+        c = getattr(m, "_gp_cache", None)
+        if c is not None:
+            c.clear()
 
 
 def shard(t, dim=0):
@@ -188,7 +200,7 @@ class GradBucket:
         for p, v in zip(self.params, self.views):
             p.grad = v
 
-    def all_reduce_mean(self, async_op=False):
+    def all_reduce_mean(self):
         if not enabled():
             return None
         # a backward may have replaced .grad with a fresh tensor (set_to_none semantics); gather those back
@@ -196,9 +208,9 @@ class GradBucket:
             if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
                 v.copy_(p.grad)
                 p.grad = v
-        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)     # stream-ordered: the scale below runs after it
         self.flat.mul_(1.0 / _state["world"])
-        return work
+        return None
 
 
 def all_reduce_grads_mean(module):

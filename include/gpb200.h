@@ -38,6 +38,15 @@ extern "C" {
 #define GP_KIND_CONV_K3S1 2  /* nn.Conv2d(k=3, s=1, p=1) fprop / dgrad (models/sngan_projection.py:30,33)              */
 #define GP_KIND_CONV_K1S1 3  /* nn.Conv2d(k=1) / nn.Linear as a 1-tap GEMM (models/sngan_projection.py:43; dcgan.py:32) */
 
+/* Companion tensor of an NHWC activation. Every activation has a bf16 tensor — what autograd sees and
+ * every backward kernel / GEMM reads — and, depending on the forward precision mode that produced it, a second tensor of
+ * the same shape: GP_COMP_LO = bf16(value - bf16(value)) ("bf16x3": value = hi + lo), GP_COMP_F16 = fp16(value) ("fp16":
+ * the operand of the next single-MMA forward GEMM). Forward element-wise kernels taking (x, x_comp, ..., comp_fmt) read
+ * the most precise view and write both tensors; a NULL companion pointer = that tensor has none. */
+#define GP_COMP_NONE 0
+#define GP_COMP_LO 1
+#define GP_COMP_F16 2
+
 const char* gp_version(void);
 const char* gp_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
@@ -74,6 +83,7 @@ typedef struct {
 } gp_conv_fwd_t;
 #define GP_CONV_IN_F16 1
 #define GP_CONV_LO_F16 2
+#define GP_CONV_RES_F16 4 /* `residual` holds fp16: the companion of the shortcut activation in the "fp16" mode */
 int gp_conv_fwd(const gp_conv_fwd_t* p, void* stream);
 /* Host-only: the tile shape gp_conv_fwd would use for this problem (BN in {64,128,256} output columns, MT in {1,2}
  * 128-row sub-tiles) and the resulting number of output tiles. No pointers are dereferenced, nothing is launched. */
@@ -204,8 +214,9 @@ int gp_sn_grad(const float* g, const float* w_sn, int A, int B, int T, int dim, 
  *   gp_cbn_bwd_reduce: part fp32 [NB][2][C] scratch; S fp32 [2][C] = (sum gamma*dz, sum gamma*dz*xhat) (all-reduce for
  *                      SyncBN); demb fp32 [n_classes][2C] = embedding gradient (may be NULL)
  *   gp_cbn_bwd_apply : dy = rstd * (gamma[n]*dz - S0/count - xhat*S1/count) */
-int gp_cbn_apply_act(const void* y, void* out, int NB, int H, int W, int C, const float* mean, const float* rstd,
-                     const float* emb, const long long* labels, int act, int upsample, void* stream);
+int gp_cbn_apply_act(const void* y, const void* y_comp, void* out, void* out_comp, int comp_fmt, int NB, int H, int W,
+                     int C, const float* mean, const float* rstd, const float* emb, const long long* labels, int act,
+                     int upsample, void* stream);
 int gp_cbn_bwd_reduce(const void* da, const void* y, int NB, int H, int W, int C, const float* mean, const float* rstd,
                       const float* emb, const long long* labels, int act, int upsample, float* part, float* S,
                       float* demb, int n_classes, void* stream);
@@ -215,18 +226,21 @@ int gp_cbn_bwd_apply(const void* da, const void* y, void* dy, int NB, int H, int
 /* nearest x2 upsampling / 2x2 sum pooling with a scale (F.interpolate :53,60; F.avg_pool2d :128,132 = pool with 0.25;
  * each is the other's gradient). gp_pool2x: (Hout, Wout) is the pooled size. gp_act_fwd: out = act(in) (F.relu :122). */
 int gp_upsample2x(const void* in, void* out, int NB, int H, int W, int C, float scale, void* stream);
-int gp_pool2x(const void* in, void* out, int NB, int Hout, int Wout, int C, float scale, void* stream);
-int gp_act_fwd(const void* in, void* out, long long n, int act, void* stream);
+int gp_pool2x(const void* in, const void* in_comp, void* out, void* out_comp, int comp_fmt, int NB, int Hout, int Wout,
+              int C, float scale, void* stream);
+int gp_act_fwd(const void* in, const void* in_comp, void* out, void* out_comp, int comp_fmt, long long n, int act,
+               void* stream);
 /* 3x3 image-side layers (first conv of the discriminator :141-148, last conv + tanh of the generator :80,95):
- * col bf16 [NB*H*W][32], column (c*3+kh)*3+kw; NHWC-8 bf16 <-> NCHW fp32 image with fused tanh / tanh'. */
-int gp_im2col_k3s1(const float* img, void* col, int NB, int ch, int H, int W, void* stream);
+ * col bf16 [NB*H*W][32], column (c*3+kh)*3+kw; NHWC-8 bf16 <-> NCHW fp32 image with fused tanh / tanh'.
+ * gp_nhwc8_to_image: in_f32 != 0 reads the GEMM's fp32 output (the precise modes keep the pre-tanh image out of bf16). */
+int gp_im2col_k3s1(const float* img, void* col, void* col_comp, int comp_fmt, int NB, int ch, int H, int W, void* stream);
 int gp_col2im_k3s1(const void* col, float* img, int NB, int ch, int H, int W, void* stream);
-int gp_nhwc8_to_image(const void* in, float* img, int NB, int ch, int HW, int tanh_act, void* stream);
+int gp_nhwc8_to_image(const void* in, int in_f32, float* img, int NB, int ch, int HW, int tanh_act, void* stream);
 int gp_image_to_nhwc8_grad(const float* dout, const float* out, void* dy, int NB, int ch, int HW, int tanh_act,
                            void* stream);
 /* projection head (:190-195): h = sum_hw relu(a) (fp32 [NB][C]); out[n] = b + sum_c h[n][c] * (w[c] + E[label[n]][c])
  * — the Linear l6 and the embedding inner product as one warp-level GEMV. Backward: dh, dw [C], db [1], dE [n_classes][C]. */
-int gp_relu_sumpool(const void* a, float* h, int NB, int HW, int C, void* stream);
+int gp_relu_sumpool(const void* a, const void* a_comp, int comp_fmt, float* h, int NB, int HW, int C, void* stream);
 int gp_relu_sumpool_bwd(const float* dh, const void* a, void* da, int NB, int HW, int C, void* stream);
 int gp_proj_head_fwd(const float* h, const float* w, const float* b, const float* E, const long long* labels, float* out,
                      int NB, int C, void* stream);
@@ -243,6 +257,12 @@ int gp_proj_head_bwd(const float* dout, const float* h, const float* w, const fl
  * hi/lo bf16 pair produced by the kernels above (weights, im2col columns, latent rows) into the single fp16 operand.
  * gp_bn_apply_act_pair: gp_bn_apply_act_split with the second output = fp16(v) (operand of the next forward GEMM) next to
  * the bf16(v) the backward GEMMs read. */
+/* BatchNorm statistics / apply on an EXISTING activation with a companion tensor (generator's b6 of
+ * models/sngan_projection.py:92; every BatchNorm of models/dcgan_blur.py, which follows a BlurPool). */
+int gp_bn_stats_comp(const void* x, const void* x_comp, int comp_fmt, long long P, int C, float* sum, float* sumsq,
+                     void* stream);
+int gp_bn_apply_act_comp(const void* y, const void* y_comp, void* out, void* out_comp, int comp_fmt, long long P, int C,
+                         const float* scale, const float* shift, int act, void* stream);
 int gp_pair_to_f16(const void* hi, const void* lo, long long ld_in, void* out, long long ld_out, long long rows, int cols,
                    void* stream);
 int gp_bn_apply_act_pair(const float* y, void* out_bf16, void* out_f16, long long P, int C, const float* scale,
@@ -263,12 +283,16 @@ int gp_col2im_k4s2_f32(const float* col, const float* bias, float* img, int NB, 
                        void* stream);
 int gp_head_fwd_split(const void* a_hi, const void* a_lo, const float* w, const float* bias, float* out, int NB, int HW,
                       int C, int O, long long s_o, long long s_c, long long s_hw, void* stream);
+/* gp_head_fwd on features with a companion tensor of either format (GP_COMP_LO == gp_head_fwd_split) */
+int gp_head_fwd_comp(const void* a, const void* a_comp, int comp_fmt, const float* w, const float* bias, float* out, int NB,
+                     int HW, int C, int O, long long s_o, long long s_c, long long s_hw, void* stream);
 
 /* ---- BlurPool2d(filt_size=3, pad_type='reflect', stride 1 | 2) of models/ops.py:7-47, the anti-aliasing filter of
  * models/dcgan_blur.py:41,116 (the networks main_dcgan.py:52-53 instantiates): reflection pad 1 + depth-wise 3x3
  * outer([1,2,1],[1,2,1])/16 on NHWC bf16 (NB, H, W, C) -> (NB, (H-1)/stride+1, (W-1)/stride+1, C); _bwd is its adjoint
  * (dout on the output grid -> din on the (H, W) grid). */
-int gp_blur3x3_fwd(const void* in, void* out, int NB, int H, int W, int C, int stride, void* stream);
+int gp_blur3x3_fwd(const void* in, const void* in_comp, void* out, void* out_comp, int comp_fmt, int NB, int H, int W,
+                   int C, int stride, void* stream);
 int gp_blur3x3_bwd(const void* dout, void* din, int NB, int H, int W, int C, int stride, void* stream);
 
 /* ---- SyncBN over NVLink peer memory (the reference has no parallelism; batch-sharded data parallelism

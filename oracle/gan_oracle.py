@@ -338,6 +338,62 @@ def _step_grads(dcgan_generator, dcgan_discriminator, g_kw, d_kw, sd_g, sd_d, x_
     return out
 
 
+def _leaves(sd):
+    return {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(
+        ("running_mean", "running_var", "weight_u", "weight_v")) else v.clone()) for k, v in sd.items()}
+
+
+def _grads(loss, p):
+    keys = [k for k, v in p.items() if v.requires_grad]
+    gs = torch.autograd.grad(loss, [p[k] for k in keys], allow_unused=True, retain_graph=True)
+    return {k: g for k, g in zip(keys, gs) if g is not None}
+
+
+def sngan_step_grads(sd_g, sd_d, x_real, y_real, z, c, bottom_width=4):
+    """The three backward passes of one main_sngan.py iteration (:72-99) at FIXED weights (no optimiser step in
+    between): D-real (:73-77), D-fake on G(z, c).detach() (:82-87), G step through D on the SAME fake batch, re-using the
+    generator graph of :82 (:94-98). Hinge losses (:57). Spectral-norm u / v advance once per discriminator forward, as
+    in the script. Returns losses, logits, the fake batch and the per-pass gradients."""
+    pg, pd = _leaves(sd_g), _leaves(sd_d)
+    d_real = sngan_discriminator(pd, x_real, y_real)
+    loss_real = gan_loss("hinge", d_real, True)
+    g_real = _grads(loss_real, pd)
+    fake = sngan_generator(pg, z, c, bottom_width=bottom_width)
+    d_fake = sngan_discriminator(pd, fake.detach(), c)
+    loss_fake = gan_loss("hinge", d_fake, False)
+    g_fake = _grads(loss_fake, pd)
+    d_g = sngan_discriminator(pd, fake, c)
+    loss_g = gan_loss("hinge", d_g, False, True)
+    g_g = _grads(loss_g, pg)
+    return dict(loss_real=loss_real.detach(), loss_fake=loss_fake.detach(), loss_g=loss_g.detach(), d_real=d_real.detach(),
+                d_fake=d_fake.detach(), d_g=d_g.detach(), fake=fake.detach(), d_grads_real=g_real, d_grads_fake=g_fake,
+                g_grads=g_g)
+
+
+def acgan_step_grads(sd_g, sd_d, x_real, y_real, z, labels=(0.9, 0.1, 0.9), aux_weight=0.5):
+    """The three backward passes of one main_acgan.py iteration (:90-131) at FIXED weights: objective
+    criterion_adv + 0.5 * MSELoss(aux head, labels) on the real batch (:95-97), on G(z, y).detach() (:107-116) and, for
+    the generator, on the same fake batch through D (:123-131). Returns losses (the total each pass back-propagates),
+    both heads' outputs, the fake batch and the per-pass gradients."""
+    rl, fl, gl = labels
+    pg, pd = _leaves(sd_g), _leaves(sd_d)
+
+    def objective(x, is_real, is_gen):
+        adv, cls = dcgan_discriminator(pd, x, acgan=True)
+        return gan_loss("vanilla", adv, is_real, is_gen, rl, fl, gl) + aux_weight * F.mse_loss(cls, y_real), adv, cls
+
+    loss_real, adv_r, cls_r = objective(x_real, True, False)
+    g_real = _grads(loss_real, pd)
+    fake = dcgan_generator(pg, z, y_real, acgan=True)
+    loss_fake, adv_f, cls_f = objective(fake.detach(), False, False)
+    g_fake = _grads(loss_fake, pd)
+    loss_g, adv_g, _ = objective(fake, False, True)
+    g_g = _grads(loss_g, pg)
+    return dict(loss_real=loss_real.detach(), loss_fake=loss_fake.detach(), loss_g=loss_g.detach(), d_real=adv_r.detach(),
+                d_real_cls=cls_r.detach(), d_fake=adv_f.detach(), d_fake_cls=cls_f.detach(), d_g=adv_g.detach(),
+                fake=fake.detach(), d_grads_real=g_real, d_grads_fake=g_fake, g_grads=g_g)
+
+
 def step_flops_dcgan64(batch):
     """Minimal algorithmic FLOPs of one DCGAN-64 step: 9.7994 GFLOP per image."""
     return 9.7994e9 * batch

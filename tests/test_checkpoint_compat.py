@@ -89,3 +89,41 @@ def test_oracle_trainer_resumes_from_the_reference_checkpoint():
     xs, zs = trace_data(fx["seed"], 3, 8, 32, 16)
     got = tr.step(xs[2], zs[2, 0], zs[2, 1])[:3]
     assert got == pytest.approx(fx["next_losses"], abs=2e-5)
+
+
+def test_fused_adam_checkpoint_steps_in_torch_adam_and_back():
+    """a checkpoint written by optim.FusedAdam must load into the reference scripts' torch.optim.Adam AND
+    step there (torch's load_state_dict replaces the param groups wholesale, so every torch.optim.Adam group key has to
+    be in the file; `step` is a CPU scalar like torch's own), and the other way round. Host logic only: no kernel runs."""
+    from gan_playground_b200.optim import FusedAdam
+
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 4))
+    ref_opt = torch.optim.Adam(net.parameters(), lr=4e-4, betas=(0.5, 0.999))
+    net(torch.randn(3, 6)).sum().backward()
+    ref_opt.step()                                              # real Adam state: step 1, non-zero moments
+    fused = FusedAdam(net.parameters(), lr=1e-3, betas=(0.9, 0.999))
+    fused.load_state_dict(ref_opt.state_dict())                 # torch -> fused
+    assert fused.param_groups[0]["lr"] == 4e-4 and tuple(fused.param_groups[0]["betas"]) == (0.5, 0.999)
+    sd = fused.state_dict()
+    want = set(torch.optim.Adam([torch.zeros(1)]).param_groups[0]) - {"params"}
+    assert want <= set(sd["param_groups"][0]), "missing torch.optim.Adam group keys: %s" % (want - set(sd["param_groups"][0]))
+    for i, e in ref_opt.state_dict()["state"].items():
+        assert torch.allclose(sd["state"][i]["exp_avg"], e["exp_avg"]) and torch.allclose(sd["state"][i]["exp_avg_sq"], e["exp_avg_sq"])
+        assert sd["state"][i]["step"].device.type == "cpu" and float(sd["state"][i]["step"]) == float(e["step"]) == 1.0
+    # fused -> torch: loads and STEPS (this raised KeyError: 'weight_decay' before the groups carried every key)
+    net2 = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 4))
+    net2.load_state_dict({k: v.clone() for k, v in net.state_dict().items()})
+    opt2 = torch.optim.Adam(net2.parameters(), lr=1.0)
+    opt2.load_state_dict(sd)
+    x = torch.randn(3, 6)
+    net2(x).sum().backward()
+    before = [p.detach().clone() for p in net2.parameters()]
+    opt2.step()
+    assert all(not torch.equal(a, b) for a, b in zip(before, net2.parameters()))
+    # and it moved exactly like the torch optimiser the state came from
+    net.zero_grad()
+    net(x).sum().backward()
+    ref_opt.step()
+    for a, b in zip(net.parameters(), net2.parameters()):
+        assert torch.allclose(a, b, atol=1e-7)
