@@ -9,6 +9,11 @@ from . import ops
 from ._lib import GpError
 
 
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise GpError("%s on %s — CUDA only, no CPU fallback" % (what, t.device))
+
+
 class GANLoss(nn.Module):
     def __init__(self, gan_mode, target_real_label=1.0, target_fake_label=0.0, target_fake_G_label=1.0):
         super().__init__()
@@ -34,8 +39,7 @@ class GANLoss(nn.Module):
         return (ops.LOSS_HINGE_REAL if is_real else (ops.LOSS_NEG_MEAN if is_generator else ops.LOSS_HINGE_FAKE)), 0.0
 
     def forward(self, prediction, is_real, is_generator=False):
-        if not prediction.is_cuda:
-            raise GpError("GANLoss: prediction is on %s — CUDA only, no CPU fallback" % prediction.device)
+        _require_cuda(prediction, "GANLoss: prediction")
         mode, target = self._mode_target(is_real, is_generator)
         return GF.GanLossFn.apply(prediction, mode, target)
 
@@ -59,7 +63,6 @@ class ACGANLoss(nn.Module):
         self.criterion_adv, self.aux_weight = criterion_adv, float(aux_weight)
 
     def forward(self, packed_logits, labels, is_real, is_generator=False):
-        if not packed_logits.is_cuda:
-            raise GpError("ACGANLoss: logits are on %s — CUDA only, no CPU fallback" % packed_logits.device)
+        _require_cuda(packed_logits, "ACGANLoss: logits")
         mode, target = self.criterion_adv._mode_target(is_real, is_generator)
         return GF.AcganLossFn.apply(packed_logits, labels, mode, target, self.aux_weight)

@@ -783,8 +783,10 @@ def bn_apply_act_comp(y, comp, fin, act, out_fmt):
 def pair_to_f16(hi, lo, rows, cols, ld_in, out=None):
     """fp16(hi + lo) of a hi/lo bf16 pair stored with row pitch ld_in -> fp16 [rows, cols] (the single-MMA operand of the
     fp16 mode). hi / lo may be views into one staging buffer (e.g. the hi | lo halves of a packed weight row)."""
-    if hi.dtype != torch.bfloat16 or lo.dtype != torch.bfloat16 or not hi.is_cuda:
-        raise _lib.GpError("pair_to_f16: hi / lo must be CUDA bf16 tensors")
+    for t, name in ((hi, "hi"), (lo, "lo")):       # may be strided views into one staging buffer: no contiguity check
+        if t.dtype != torch.bfloat16:
+            raise _lib.GpError("pair_to_f16: %s must be bf16, got %s" % (name, t.dtype))
+    _chk(hi if hi.is_contiguous() else hi.new_empty(1), torch.bfloat16, "hi")
     if out is None:
         out = torch.empty((rows, cols), device=hi.device, dtype=torch.float16)
     check(_fn("gp_pair_to_f16")(_p(hi), _p(lo), ld_in, _p(out), cols, rows, cols, _stream()), "gp_pair_to_f16")

@@ -31,9 +31,7 @@ def global_cos(named_params, ref, skip=()):
     for k, r in ref.items():
         if k in skip:
             continue
-        g = params[k]
-        g = (g.grad if hasattr(g, "grad") and not isinstance(g, dict) else g)
-        g = g.detach().float().cpu().double()
+        g = params[k].grad.detach().float().cpu().double()
         r = r.double()
         num += (g * r).sum().item()
         da += (g * g).sum().item()
@@ -48,6 +46,13 @@ def prebn_biases(net):
     return [k for k in names if k.endswith(".0.bias") and k.replace(".0.bias", ".1.weight") in names]
 
 
+def prebn_biases_blur_g(net):
+    """dcgan_blur.Generator blocks are [Upsample, Conv, BlurPool, BatchNorm, LeakyReLU]: `blocks.i.1.bias` feeds the
+    BatchNorm `blocks.i.3` through the (linear, bias-preserving) blur."""
+    names = dict(net.named_parameters())
+    return [k for k in names if k.endswith(".1.bias") and k.replace(".1.bias", ".3.weight") in names]
+
+
 def resnet_g_zero_biases(net):
     """ResNetGenerator: every block conv (c1 -> b2; c2 + c_sc -> the next block's b1 / b6) feeds a BatchNorm."""
     return [k for k, _ in net.named_parameters() if k.startswith("block") and k.endswith(("c1.bias", "c2.bias", "c_sc.bias"))]
@@ -57,8 +62,10 @@ class Bars:
     """Collects (kind, name, value) rows for one configuration, prints them, appends them to gpurun_out/parity_table.jsonl
     and asserts the north_star bars on all of them at the end (so a failing row does not hide the others)."""
 
-    def __init__(self, config, act_bar=ACT_BAR, cos_bar=COS_BAR, loss_bar=LOSS_BAR):
-        self.config, self.rows = config, []
+    def __init__(self, config, act_bar=ACT_BAR, cos_bar=COS_BAR, loss_bar=LOSS_BAR, loss_abs=0.0):
+        """loss_abs: absolute scale added to |ref| in the loss rows — for losses that sit near zero (the hinge generator
+        loss -mean D(G(z)) of a fresh network), where a relative error has no meaning; 0 for everything else."""
+        self.config, self.rows, self.loss_abs = config, [], loss_abs
         self.bars = {"act": act_bar, "cos": cos_bar, "loss": loss_bar}
 
     def act(self, name, got, ref):
@@ -69,7 +76,7 @@ class Bars:
 
     def loss(self, name, got, ref):
         got, ref = float(got), float(ref)
-        self.rows.append(("loss", name, abs(got - ref) / (abs(ref) + 1e-12)))
+        self.rows.append(("loss", name, abs(got - ref) / (abs(ref) + self.loss_abs + 1e-12)))
 
     def ok(self, kind, v):
         return v >= self.bars[kind] if kind == "cos" else v <= self.bars[kind]

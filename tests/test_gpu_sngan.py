@@ -37,30 +37,30 @@ def test_sngan_golden_iteration():
     loss = crit(out, True)
     loss.backward()
     print("d_real", relerr(out, fx["d_real"]), loss.item(), fx["loss_real"].item())
-    assert relerr(out, fx["d_real"]) < 3e-2
+    assert relerr(out, fx["d_real"]) < 1e-2
     assert abs(loss.item() - fx["loss_real"].item()) < 0.02 * abs(fx["loss_real"].item()) + 1e-3
     cd = gcos(netD, unpack_grads(fx["d_grads_real"]))
     print("D-real grad cos", cd)
-    assert cd > 0.99
+    assert cd > 0.999
     fake = netG(z, c)
     print("fake", relerr(fake, fx["fake"]))
-    # batch 2 => the first conditional BN normalises over 8 values per channel: bf16 rounding is amplified (4e-2 seen);
-    # the ch=64 / batch-16 oracle test below holds the 2e-2 bar
-    assert fake.shape == (2, 3, 32, 32) and relerr(fake, fx["fake"]) < 8e-2
+    # batch 2 => the first conditional BN normalises over 8 values per channel (rounding is amplified: plain bf16
+    # operands gave 4e-2 here); the default mode's fp16 operands + fp16 activation copies hold the north_star bar
+    assert fake.shape == (2, 3, 32, 32) and relerr(fake, fx["fake"]) < 1e-2
     netD.zero_grad()
     out = netD(fx["fake"].cuda(), c)
     lf = crit(out, False)
     lf.backward()
-    assert relerr(out, fx["d_fake"]) < 3e-2
-    assert gcos(netD, unpack_grads(fx["d_grads_fake"])) > 0.99
+    assert relerr(out, fx["d_fake"]) < 1e-2
+    assert gcos(netD, unpack_grads(fx["d_grads_fake"])) > 0.999
     netG.zero_grad(), netD.zero_grad()
     out = netD(fake, c)                      # main_sngan.py:96 reuses the generator graph of the D-fake step
     lg = crit(out, False, True)
     lg.backward()
-    assert abs(lg.item() - fx["loss_g"].item()) < 0.03 * abs(fx["loss_g"].item()) + 2e-3
+    assert abs(lg.item() - fx["loss_g"].item()) < 0.02 * abs(fx["loss_g"].item()) + 2e-3   # -mean D(G(z)) sits near zero
     cg = gcos(netG, unpack_grads(fx["g_grads"]), skip=zero_grad_biases(netG))
     print("G-step grad cos", cg)
-    assert cg > 0.9
+    assert cg > 0.999
     sd = netD.state_dict()
     for k, v in fx["buf_d_after"].items():
         if k.endswith(("weight_u", "weight_v")):
@@ -103,14 +103,14 @@ def test_sngan_ch64_vs_oracle():
     out = netD(x.cuda(), y.cuda())
     loss = crit(out, True)
     loss.backward()
-    assert relerr(out, ref_out.detach()) < 2e-2
+    assert relerr(out, ref_out.detach()) < 1e-2
     assert abs(loss.item() - ref_loss.item()) < 0.02 * abs(ref_loss.item()) + 1e-3
     assert gcos(netD, ref_g) > 0.999
     fake = netG(z.cuda(), y.cuda())
-    # 13 convs deep with un-normalised residual sums: single-bf16 operands + bf16 storage give 5e-2 max-rel error in a
-    # CPU emulation of the same rounding (oracle with bf16-rounded conv operands/outputs: 5.06e-2); measured 5.2e-2.
-    assert relerr(fake, ref_fake) < 8e-2
-    assert (fake.detach().cpu() - ref_fake).abs().mean() < 1e-2
+    # 13 convs deep with un-normalised residual sums: single-bf16 operands + bf16 storage gave 5.2e-2 (round 1); the
+    # default mode now runs these nodes on fp16 operands with fp16 activation copies
+    print("ch64 G(z) max-rel-err", relerr(fake, ref_fake))
+    assert relerr(fake, ref_fake) < 1e-2
     # unconditional path (y=None) and eval mode run
     netD.eval()
     assert netD(x.cuda()).shape == (B, 1)

@@ -89,8 +89,6 @@ def test_loss_trace_200_steps_within_2_percent():
     assert pt_dev < max(0.02, 3 * pt_ctl)
 
 
-@pytest.mark.skipif(os.environ.get("GP_EXTENDED_TESTS", "0") != "1",
-                    reason="written when no GPU minutes were left to calibrate it: run with GP_EXTENDED_TESTS=1 (round 2)")
 def test_engine_mixed_policy_loss_trace_200_steps():
     """The same 200-step protocol through engine.DcganStep with its per-pass precision policy (real pass bf16, D-fake chain
     single-MMA fp16, G step bf16x3), eager and as CUDA-graph replays. tools/precision_study.py --trace emulates this on the

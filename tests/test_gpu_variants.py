@@ -48,6 +48,7 @@ def test_spectral_norm_kernels_match_torch_hook():
 def test_sn_dcgan_golden_step():
     from gan_playground_b200.criterion import GANLoss
     from gan_playground_b200.models import dcgan_specnorm as M
+    from parity import Bars
 
     fx = load_golden("snd_r32_w4.pt")
     netG = quiet(lambda: M.Generator(z_dim=fx["z_dim"], ngf=fx["width"], resolution=32)).cuda()
@@ -56,24 +57,25 @@ def test_sn_dcgan_golden_step():
     netD.load_state_dict(fx["sd_d"])
     crit = GANLoss("hinge").cuda()
     x, z1, z2 = fx["x"].cuda(), fx["z1"].cuda(), fx["z2"].cuda()
+    bars = Bars("golden snd_r32_w4 (unmodified reference, SN-DCGAN width %d, batch %d)" % (fx["width"], x.shape[0]))
     out = netD(x)
     loss = crit(out, True)
     loss.backward()
-    assert relerr(out, fx["d_real"]) < 2e-2
-    assert abs(loss.item() - fx["loss_real"].item()) < 0.02 * abs(fx["loss_real"].item())
-    assert global_cos(netD.named_parameters(), unpack_grads(fx["d_grads_real"])) > 0.99
+    bars.act("D(x)", out, fx["d_real"]), bars.loss("loss_real", loss.item(), fx["loss_real"])
+    bars.cos("D-real", global_cos(netD.named_parameters(), unpack_grads(fx["d_grads_real"])))
     fake1 = netG(z1)
-    assert relerr(fake1, fx["fake1"]) < 2e-2
+    bars.act("G(z)", fake1, fx["fake1"])
     netD.zero_grad()
     out = netD(fx["fake1"].cuda())
     crit(out, False).backward()
-    assert relerr(out, fx["d_fake"]) < 3e-2
-    assert global_cos(netD.named_parameters(), unpack_grads(fx["d_grads_fake"])) > 0.98
+    bars.act("D(G(z))", out, fx["d_fake"])
+    bars.cos("D-fake", global_cos(netD.named_parameters(), unpack_grads(fx["d_grads_fake"])))
     netG.zero_grad(), netD.zero_grad()
     loss = crit(netD(netG(z2)), False, True)
     loss.backward()
-    assert abs(loss.item() - fx["loss_g"].item()) < 0.03 * abs(fx["loss_g"].item()) + 1e-3
-    assert global_cos(netG.named_parameters(), unpack_grads(fx["g_grads"])) > 0.9
+    assert abs(loss.item() - fx["loss_g"].item()) < 0.02 * abs(fx["loss_g"].item()) + 1e-3   # -mean D(G(z)) sits near zero
+    bars.cos("G-step", global_cos(netG.named_parameters(), unpack_grads(fx["g_grads"])))
+    bars.finish()
     # u / v after 3 D forwards and 2 G forwards (one in-place power iteration per train-mode forward)
     for net, key in ((netD, "buf_d_after"), (netG, "buf_g_after")):
         sd = net.state_dict()
@@ -86,45 +88,10 @@ def test_sn_dcgan_golden_step():
     assert hid.shape == (x.shape[0], fx["width"] * 8, 4, 4) and hid.dtype == torch.float32
 
 
-def test_sn_dcgan_width64_vs_oracle():
-    from gan_playground_b200.criterion import GANLoss
-    from gan_playground_b200.models import dcgan_specnorm as M
-    from oracle import gan_oracle as O
-
-    torch.manual_seed(0)
-    netG, netD = quiet(lambda: M.Generator(resolution=32)), quiet(lambda: M.Discriminator(resolution=32))
-    sd_g = {k: v.clone() for k, v in netG.state_dict().items()}
-    sd_d = {k: v.clone() for k, v in netD.state_dict().items()}
-    gen = torch.Generator().manual_seed(1)
-    B = 32
-    x = torch.rand(B, 3, 32, 32, generator=gen) * 2 - 1
-    z1, z2 = torch.randn(B, 100, generator=gen), torch.randn(B, 100, generator=gen)
-    torch.set_num_threads(os.cpu_count())
-    ref = O.dcgan_step_grads(sd_g, sd_d, x, z1, z2, labels=(1.0, 0.0, 1.0), mode="hinge", sn=True, flatten_head=True)
-    netG.cuda(), netD.cuda()
-    crit = GANLoss("hinge").cuda()
-    out = netD(x.cuda())
-    loss = crit(out, True)
-    loss.backward()
-    assert relerr(out, ref["d_real"]) < 1e-2
-    gD = {k: v for k, v in ref["d_grads_real"].items()}
-    assert global_cos(netD.named_parameters(), gD) > 0.999
-    netD.zero_grad()
-    out = netD(ref["fake1"].cuda())
-    crit(out, False).backward()
-    assert relerr(out, ref["d_fake"]) < 2e-2
-    netG.zero_grad(), netD.zero_grad()
-    # the oracle ran D three times and G twice; replay the same number of power iterations before the G step
-    netG(z1.cuda())
-    loss = crit(netD(netG(z2.cuda())), False, True)
-    loss.backward()
-    assert abs(loss.item() - ref["loss_g"].item()) < 0.02 * abs(ref["loss_g"].item()) + 1e-3
-    assert global_cos(netG.named_parameters(), ref["g_grads"]) > 0.99
-
-
 def test_acgan_golden_step():
     from gan_playground_b200.criterion import GANLoss
     from gan_playground_b200.models import acgan as M
+    from parity import Bars
 
     fx = load_golden("acgan_r64_w4.pt")
     netG = quiet(lambda: M.Generator(z_dim=16, ngf=fx["width"], n_class=10)).cuda()
@@ -134,17 +101,19 @@ def test_acgan_golden_step():
     crit = GANLoss("vanilla", 0.9, 0.1, 0.9).cuda()
     mse = torch.nn.MSELoss()
     x, y, z = fx["x"].cuda(), fx["y"].cuda(), fx["z"].cuda()
+    bars = Bars("golden acgan_r64_w4 (unmodified reference, ACGAN width %d, batch %d)" % (fx["width"], x.shape[0]))
     adv, cls = netD(x)
     loss = crit(adv, True) + mse(cls, y) * 0.5       # main_acgan.py:95-97
     loss.backward()
-    assert relerr(adv, fx["d_real"]) < 2e-2 and relerr(cls, fx["d_real_cls"]) < 2e-2
-    assert abs(loss.item() - fx["loss_real"].item()) < 0.02 * abs(fx["loss_real"].item())
-    assert global_cos(netD.named_parameters(), unpack_grads(fx["d_grads_real"])) > 0.99
+    bars.act("D(x) adv", adv, fx["d_real"]), bars.act("D(x) aux", cls, fx["d_real_cls"])
+    bars.loss("loss_real", loss.item(), fx["loss_real"])
+    bars.cos("D-real", global_cos(netD.named_parameters(), unpack_grads(fx["d_grads_real"])))
     fake = netG(z, y)
-    assert relerr(fake, fx["fake"]) < 2e-2
+    bars.act("G(z,y)", fake, fx["fake"])
     netG.zero_grad(), netD.zero_grad()
     adv, cls = netD(fake)
     loss = crit(adv, False, True) + mse(cls, y) * 0.5
     loss.backward()
-    assert abs(loss.item() - fx["loss_g"].item()) < 0.03 * abs(fx["loss_g"].item())
-    assert global_cos(netG.named_parameters(), unpack_grads(fx["g_grads"])) > 0.85
+    bars.loss("loss_g", loss.item(), fx["loss_g"])
+    bars.cos("G-step", global_cos(netG.named_parameters(), unpack_grads(fx["g_grads"])))
+    bars.finish()

@@ -124,7 +124,7 @@ def test_acgan_step_tracks_the_oracle_loop():
         return torch.tensor([tr.step(xs[i] + (perturb if i == 0 else 0.0), ys[i], zs[i]) for i in range(steps)]), tr
 
     ref, tr = oracle(0.0)
-    ctl, _ = oracle(1e-6)
+    ctl, tr_ctl = oracle(1e-6)
     run = make(B)
     got = torch.tensor([run.step(xs[i].to(DEV), ys[i].to(DEV), zs[i].to(DEV)) for i in range(steps)])
     assert torch.isfinite(got).all() and got.shape == (steps, 7)
@@ -137,9 +137,14 @@ def test_acgan_step_tracks_the_oracle_loop():
     assert int(netD.blocks[1][1].num_batches_tracked) == 3 * steps and int(netG.blocks[0][1].num_batches_tracked) == steps
     upd_ref = (tr.pd["out_aux.weight"].detach() - sd_d["out_aux.weight"]).flatten()
     upd = (netD.out_aux.weight.detach().cpu() - sd_d["out_aux.weight"]).flatten()
+    upd_ctl = (tr_ctl.pd["out_aux.weight"].detach() - sd_d["out_aux.weight"]).flatten()
     cos = torch.nn.functional.cosine_similarity(upd, upd_ref, dim=0).item()
-    print("auxiliary head: cosine of the %d-step weight update vs the oracle's %.4f" % (steps, cos))
-    assert cos > 0.7
+    cos_ctl = torch.nn.functional.cosine_similarity(upd_ctl, upd_ref, dim=0).item()
+    print("auxiliary head: cosine of the %d-step weight update vs the oracle's %.4f (fp32 1e-6-perturbation control %.4f)"
+          % (steps, cos, cos_ctl))
+    # Adam turns every gradient into a +-lr step, so the accumulated update is chaotic even in fp32: the bar is the
+    # fp32 control's own agreement with the oracle (minus 0.02), capped at the north_star cosine
+    assert cos > min(0.999, cos_ctl) - 0.02
 
 
 def test_acgan_graph_replay_is_the_eager_step():

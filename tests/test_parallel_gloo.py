@@ -260,3 +260,46 @@ def test_step_drivers_data_parallel_equals_full_batch_gloo():
             assert b0 == b1, kind                                              # replicas stay identical
             b0 = torch.tensor(b0)
             assert torch.allclose(a, b0, atol=1e-6, rtol=1e-5), (kind, (a - b0).abs().max())
+
+
+def _checkpoint_worker(rank, world, port, q, tmp):
+    """checkpoint.save_model / sample_images under data parallelism: only rank 0 writes, every rank runs the sampling
+    forward (train-mode BatchNorm statistics must stay replicated), the file has the scripts' layout."""
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from gan_playground_b200 import checkpoint, parallel
+
+    parallel.init(backend="gloo")
+    torch.manual_seed(rank)          # different initial replicas on purpose: broadcast makes them equal
+    netG = torch.nn.Sequential(torch.nn.Linear(4, 3 * 4 * 4), torch.nn.Unflatten(1, (3, 4, 4)), torch.nn.BatchNorm2d(3))
+    netD = torch.nn.Linear(5, 1)
+    parallel.broadcast_module(netG), parallel.broadcast_module(netD)
+    optG, optD = torch.optim.Adam(netG.parameters(), lr=1e-3), torch.optim.Adam(netD.parameters(), lr=1e-3)
+    netG(torch.randn(6, 4)).sum().backward()
+    optG.step()
+    netG.train()
+    out = checkpoint.sample_images(netG, torch.ones(8, 4), os.path.join(tmp, "res", "fake.jpg"))
+    assert out.shape == (8, 3, 4, 4) and int(netG[2].num_batches_tracked) == 2      # sampled in train mode on EVERY rank
+    path = checkpoint.save_model((netG, netD), (optG, optD), 0, os.path.join(tmp, "ckpt"))
+    assert path.endswith("checkpoint_001.pth") and os.path.exists(path) and os.path.exists(os.path.join(tmp, "res", "fake.jpg"))
+    q.put((rank, sorted(os.listdir(os.path.join(tmp, "ckpt")))))
+    parallel.shutdown()
+
+
+def test_checkpoint_and_sampling_write_on_rank_zero_only(tmp_path):
+    ctx = mp.get_context("spawn")
+    q, port = ctx.Queue(), _free_port()
+    procs = [ctx.Process(target=_checkpoint_worker, args=(r, 2, port, q, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert sorted(q.get(timeout=5)[1] for _ in range(2)) == [["checkpoint_001.pth"]] * 2
+    ck = torch.load(tmp_path / "ckpt" / "checkpoint_001.pth", weights_only=False)
+    assert sorted(ck) == ["epoch", "optimizer", "state_dict"] and ck["epoch"] == 0
+    assert sorted(ck["state_dict"]) == sorted(ck["optimizer"]) == ["discriminator", "generator"]
+    assert ck["optimizer"]["generator"]["state"][0]["exp_avg"].abs().sum() > 0

@@ -17,6 +17,11 @@ import torch.nn.functional as F
 
 from gan_playground_b200 import _lib
 
+# the references below are torch convolutions on the GPU: they must be TRUE fp32 (torch's default lets cuDNN / cuBLAS use
+# TF32, i.e. 10-bit operands — SURVEY.md D8), or the check would be TF32 judging bf16
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 KIND = {"k4s2": 0, "convt": 1, "k3s1": 2, "k1s1": 3}
 
 
