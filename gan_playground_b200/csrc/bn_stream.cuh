@@ -296,7 +296,16 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const 
                                     __nv_bfloat16* __restrict__ dy, long long P, int C, const float* __restrict__ scale,
                                     const float* __restrict__ shift, const float* __restrict__ mean,
                                     const float* __restrict__ rstd, const float* __restrict__ sum_dz,
-                                    const float* __restrict__ sum_dzx, float inv_count, int act, int rows_per_block) {
+                                    const float* __restrict__ sum_dzx, float inv_count, int act, int rows_per_block,
+                                    float* __restrict__ acc_dbeta, float* __restrict__ acc_dgamma, float acc_scale) {
+  // affine-parameter gradients delivered straight into the parameters' .grad buffers (dbeta = sum dz, dgamma =
+  // sum dz * xhat, times 1 / world under data parallelism): one block does it, no separate accumulation launches
+  if (acc_dbeta != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      acc_dbeta[c] += sum_dz[c] * acc_scale;
+      acc_dgamma[c] += sum_dzx[c] * acc_scale;
+    }
+  }
   const ColLayout L = col_layout(C);
   if (!L.active) return;
   // dy = sc*dz - k0 - (y - mu) * k1   with k0 = sc*sum_dz/M, k1 = sc*rstd*sum_dzx/M

@@ -137,8 +137,9 @@ __global__ void __launch_bounds__(256) pack_conv_weight16_n1_kernel(const float*
   }
 }
 // packed gradient [M][16][N] -> (M, N, 16): one block = one m x 64 n
+// acc != 0: dst += value (the parameter's .grad buffer is the destination: no AccumulateGrad pass afterwards)
 __global__ void __launch_bounds__(256) unpack_conv_wgrad16_kernel(const float* __restrict__ src, float* __restrict__ dst, int M,
-                                                                  int N) {
+                                                                  int N, int acc) {
   __shared__ float s_tile[16 * 65];  // [t][64 n + 1 pad]
   const int m = blockIdx.y, n0 = blockIdx.x * 64;  // N % 64 == 0 on this path
   {
@@ -155,13 +156,19 @@ __global__ void __launch_bounds__(256) unpack_conv_wgrad16_kernel(const float* _
     v.y = s_tile[(tq * 4 + 1) * 65 + n];
     v.z = s_tile[(tq * 4 + 2) * 65 + n];
     v.w = s_tile[(tq * 4 + 3) * 65 + n];
-    reinterpret_cast<float4*>(dst + ((long long)m * N + n0 + n) * 16)[tq] = v;
+    float4* d4 = reinterpret_cast<float4*>(dst + ((long long)m * N + n0 + n) * 16) + tq;
+    if (acc) {
+      const float4 o = *d4;
+      v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
+    }
+    *d4 = v;
   }
 }
 
 // packed fp32 gradient [M][tap][N] -> torch layout (M, N, tap) fp32, tile = one m x 64 n, transposed through smem
 constexpr int kUnpackNT = 64;
-__global__ void unpack_conv_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int M, int N, int taps) {
+__global__ void unpack_conv_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int M, int N, int taps,
+                                         int acc) {
   extern __shared__ float s_tile[];  // [taps][kUnpackNT + 1]
   const int m = blockIdx.y, n0 = blockIdx.x * kUnpackNT;
   const int nt = min(kUnpackNT, N - n0);
@@ -171,12 +178,15 @@ __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ src, float* _
   }
   __syncthreads();
   float* dp = dst + ((long long)m * N + n0) * taps;  // contiguous nt*taps floats
-  for (int j = threadIdx.x; j < nt * taps; j += blockDim.x) dp[j] = s_tile[(j % taps) * (kUnpackNT + 1) + j / taps];
+  for (int j = threadIdx.x; j < nt * taps; j += blockDim.x) {
+    const float v = s_tile[(j % taps) * (kUnpackNT + 1) + j / taps];
+    dp[j] = acc ? dp[j] + v : v;
+  }
 }
 
 // fp32 [Rpad][ld_src] (gradient of a packed matrix) -> dst[map(r) * s_r + k * s_k] for r < R, k < K (inverse of pack_matrix)
 __global__ void unpack_matrix_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int K, int ld_src,
-                                     long long s_r, long long s_k, int perm) {
+                                     long long s_r, long long s_k, int perm, int acc) {
   const long long total = (long long)R * K;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / K), k = (int)(i % K);
@@ -185,7 +195,9 @@ __global__ void unpack_matrix_kernel(const float* __restrict__ src, float* __res
       const int inner = R / perm;
       rs = (r % inner) * perm + r / inner;
     }
-    dst[rs * s_r + k * s_k] = src[(long long)r * ld_src + k];
+    const float v = src[(long long)r * ld_src + k];
+    float* d = dst + rs * s_r + k * s_k;
+    *d = acc ? *d + v : v;
   }
 }
 
@@ -723,7 +735,8 @@ int gp_pack_matrix(const float* src, void* dst, int R, int K, int Rpad, int ld_d
 int gp_unpack_matrix(const float* src, float* dst, int R, int K, int ld_src, long long s_r, long long s_k, int perm,
                      void* stream) {
   GP_REQUIRE(src && dst && R > 0 && K > 0 && ld_src >= K, "gp_unpack_matrix: bad arguments");
-  unpack_matrix_kernel<<<grid_for((long long)R * K), 256, 0, as_stream(stream)>>>(src, dst, R, K, ld_src, s_r, s_k, perm);
+  unpack_matrix_kernel<<<grid_for((long long)R * K), 256, 0, as_stream(stream)>>>(src, dst, R, K, ld_src, s_r, s_k,
+                                                                                  perm & 0x3fffffff, (perm >> 30) & 1);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -748,15 +761,18 @@ int gp_split_conv_weight(const float* src, void* dst, int D0, int D1, int taps, 
 }
 
 int gp_unpack_conv_wgrad(const float* src, float* dst, int M, int N, int taps, void* stream) {
+  // bit 30 of `taps` (GP_UNPACK_ACCUMULATE): dst += value instead of dst = value
+  const int acc = (taps >> 30) & 1;
+  taps &= 0x3fffffff;
   GP_REQUIRE(src && dst && M > 0 && N > 0 && taps > 0 && taps <= 64, "gp_unpack_conv_wgrad: bad arguments");
   if (taps == 16 && N % 64 == 0) {
-    unpack_conv_wgrad16_kernel<<<dim3(N / 64, M), 256, 0, as_stream(stream)>>>(src, dst, M, N);
+    unpack_conv_wgrad16_kernel<<<dim3(N / 64, M), 256, 0, as_stream(stream)>>>(src, dst, M, N, acc);
     GP_CHECK_LAUNCH();
     return GP_OK;
   }
   dim3 grid((N + kUnpackNT - 1) / kUnpackNT, M);
   unpack_conv_wgrad_kernel<<<grid, 256, (size_t)taps * (kUnpackNT + 1) * sizeof(float), as_stream(stream)>>>(src, dst, M,
-                                                                                                          N, taps);
+                                                                                                          N, taps, acc);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -813,12 +829,14 @@ int gp_bn_bwd_reduce(const void* da, const void* y, long long P, int C, const fl
 
 int gp_bn_bwd_apply(const void* da, const void* y, void* dy, long long P, int C, const float* scale,
                     const float* shift, const float* mean, const float* rstd, const float* sum_dz,
-                    const float* sum_dzx, double count, int act, void* stream) {
+                    const float* sum_dzx, double count, int act, float* acc_dbeta, float* acc_dgamma, float acc_scale,
+                    void* stream) {
   GP_REQUIRE(da && y && dy && P > 0 && C % 8 == 0 && count > 0, "gp_bn_bwd_apply: bad arguments");
+  GP_REQUIRE((acc_dbeta == nullptr) == (acc_dgamma == nullptr), "gp_bn_bwd_apply: acc_dbeta and acc_dgamma go together");
   const ColLaunch L = col_launch(P, C, 0);
   bn_bwd_apply_kernel<__nv_bfloat16><<<L.grid, L.block, 0, as_stream(stream)>>>(
       static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(dy), P, C,
-      scale, shift, mean, rstd, sum_dz, sum_dzx, (float)(1.0 / count), act, L.rpb);
+      scale, shift, mean, rstd, sum_dz, sum_dzx, (float)(1.0 / count), act, L.rpb, acc_dbeta, acc_dgamma, acc_scale);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }

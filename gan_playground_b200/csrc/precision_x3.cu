@@ -128,6 +128,107 @@ __global__ void bn_apply_comp_kernel(const __nv_bfloat16* __restrict__ y, const 
   }
 }
 
+// BatchNorm backward with y read through its companion (the SAME value the forward normalised: the activation mask
+// act'(y*scale+shift) and xhat must not be recomputed from the bf16 rounding of y, or near-zero pre-activations flip
+// sides — measured on dcgan_blur: G-step gradient cosine 0.9984 with the bf16 view).
+__global__ void bn_bwd_reduce_comp_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ y,
+                                          const void* __restrict__ y_comp, int fmt, long long P, int C,
+                                          const float* __restrict__ scale, const float* __restrict__ shift,
+                                          const float* __restrict__ mean, const float* __restrict__ rstd, int act,
+                                          float* __restrict__ sum_dz, float* __restrict__ sum_dzx, int rows_per_block) {
+  const ColLayout L = col_layout(C);
+  float acc[2][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
+  if (L.active) {
+    float sc[8], sh[8], mu[8], rs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sc[i] = scale[L.g * 8 + i];
+      sh[i] = shift[L.g * 8 + i];
+      mu[i] = mean[L.g * 8 + i];
+      rs[i] = rstd[L.g * 8 + i];
+    }
+    const RowRange R = row_range(P, rows_per_block);
+    for (long long r = R.r0 + L.rl; r < R.r1; r += (long long)kRowsInFlight * L.lanes) {
+      float fy[kRowsInFlight][8], fd[kRowsInFlight][8];
+#pragma unroll
+      for (int u = 0; u < kRowsInFlight; ++u) {
+        const long long ru = r + (long long)u * L.lanes;
+        if (ru < R.r1) {
+          load8c(y, y_comp, fmt, ru * C + L.g * 8, fy[u]);
+          load8c(da, nullptr, GP_COMP_NONE, ru * C + L.g * 8, fd[u]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) fy[u][i] = fd[u][i] = 0.f;  // da = 0 contributes nothing
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kRowsInFlight; ++u)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float dz = fd[u][i] * act_grad(fy[u][i] * sc[i] + sh[i], act);
+          acc[0][i] += dz;
+          acc[1][i] += dz * (fy[u][i] - mu[i]) * rs[i];
+        }
+    }
+  }
+  float* const outs[2] = {sum_dz, sum_dzx};
+  col_flush<2>(L, C, acc, outs);
+}
+
+__global__ void bn_bwd_apply_comp_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ y,
+                                         const void* __restrict__ y_comp, int fmt, __nv_bfloat16* __restrict__ dy,
+                                         long long P, int C, const float* __restrict__ scale,
+                                         const float* __restrict__ shift, const float* __restrict__ mean,
+                                         const float* __restrict__ rstd, const float* __restrict__ sum_dz,
+                                         const float* __restrict__ sum_dzx, float inv_count, int act, int rows_per_block,
+                                         float* __restrict__ acc_dbeta, float* __restrict__ acc_dgamma, float acc_scale) {
+  if (acc_dbeta != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      acc_dbeta[c] += sum_dz[c] * acc_scale;
+      acc_dgamma[c] += sum_dzx[c] * acc_scale;
+    }
+  }
+  const ColLayout L = col_layout(C);
+  if (!L.active) return;
+  float sc[8], sh[8], mu[8], k0[8], k1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = L.g * 8 + j;
+    sc[j] = scale[c];
+    sh[j] = shift[c];
+    mu[j] = mean[c];
+    k0[j] = sc[j] * sum_dz[c] * inv_count;
+    k1[j] = sc[j] * rstd[c] * sum_dzx[c] * inv_count;
+  }
+  const RowRange R = row_range(P, rows_per_block);
+  for (long long r = R.r0 + L.rl; r < R.r1; r += (long long)kRowsInFlight * L.lanes) {
+    float fy[kRowsInFlight][8], fd[kRowsInFlight][8];
+#pragma unroll
+    for (int u = 0; u < kRowsInFlight; ++u) {
+      const long long ru = r + (long long)u * L.lanes;
+      if (ru < R.r1) {
+        load8c(y, y_comp, fmt, ru * C + L.g * 8, fy[u]);
+        load8c(da, nullptr, GP_COMP_NONE, ru * C + L.g * 8, fd[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kRowsInFlight; ++u) {
+      const long long ru = r + (long long)u * L.lanes;
+      if (ru < R.r1) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dz = fd[u][j] * act_grad(fy[u][j] * sc[j] + sh[j], act);
+          o[j] = sc[j] * dz - k0[j] - (fy[u][j] - mu[j]) * k1[j];
+        }
+        store8_bf16(dy + ru * C + L.g * 8, nullptr, o);
+      }
+    }
+  }
+}
+
 }  // namespace x3
 }  // namespace gp
 
@@ -216,6 +317,35 @@ int gp_bn_apply_act_comp(const void* y, const void* y_comp, void* out, void* out
   return GP_OK;
 }
 
+int gp_bn_bwd_reduce_comp(const void* da, const void* y, const void* y_comp, int comp_fmt, long long P, int C,
+                          const float* scale, const float* shift, const float* mean, const float* rstd, int act,
+                          float* sum_dz, float* sum_dzx, void* stream) {
+  GP_REQUIRE(da && y && sum_dz && sum_dzx && P > 0 && C % 8 == 0, "gp_bn_bwd_reduce_comp: bad arguments");
+  GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_bn_bwd_reduce_comp: unknown companion format %d", comp_fmt);
+  const ColLaunch L = col_launch(P, C, 2, 2);
+  x3::bn_bwd_reduce_comp_kernel<<<L.grid, L.block, L.smem, as_stream(stream)>>>(
+      static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), y_comp, comp_fmt, P, C, scale, shift, mean,
+      rstd, act, sum_dz, sum_dzx, L.rpb);
+  GP_CHECK_LAUNCH();
+  return GP_OK;
+}
+
+int gp_bn_bwd_apply_comp(const void* da, const void* y, const void* y_comp, int comp_fmt, void* dy, long long P, int C,
+                         const float* scale, const float* shift, const float* mean, const float* rstd,
+                         const float* sum_dz, const float* sum_dzx, double count, int act, float* acc_dbeta,
+                         float* acc_dgamma, float acc_scale, void* stream) {
+  GP_REQUIRE(da && y && dy && P > 0 && C % 8 == 0 && count > 0, "gp_bn_bwd_apply_comp: bad arguments");
+  GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_bn_bwd_apply_comp: unknown companion format %d", comp_fmt);
+  GP_REQUIRE((acc_dbeta == nullptr) == (acc_dgamma == nullptr), "gp_bn_bwd_apply_comp: acc_dbeta and acc_dgamma go together");
+  const ColLaunch L = col_launch(P, C, 0);
+  x3::bn_bwd_apply_comp_kernel<<<L.grid, L.block, 0, as_stream(stream)>>>(
+      static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), y_comp, comp_fmt,
+      static_cast<__nv_bfloat16*>(dy), P, C, scale, shift, mean, rstd, sum_dz, sum_dzx, (float)(1.0 / count), act, L.rpb,
+      acc_dbeta, acc_dgamma, acc_scale);
+  GP_CHECK_LAUNCH();
+  return GP_OK;
+}
+
 int gp_bn_bwd_reduce_f32(const void* da, const float* y, long long P, int C, const float* scale, const float* shift,
                          const float* mean, const float* rstd, int act, float* sum_dz, float* sum_dzx, void* stream) {
   GP_REQUIRE(da && y && sum_dz && sum_dzx && P > 0 && C % 8 == 0, "gp_bn_bwd_reduce_f32: bad arguments");
@@ -228,12 +358,14 @@ int gp_bn_bwd_reduce_f32(const void* da, const float* y, long long P, int C, con
 
 int gp_bn_bwd_apply_f32(const void* da, const float* y, void* dy, long long P, int C, const float* scale,
                         const float* shift, const float* mean, const float* rstd, const float* sum_dz,
-                        const float* sum_dzx, double count, int act, void* stream) {
+                        const float* sum_dzx, double count, int act, float* acc_dbeta, float* acc_dgamma, float acc_scale,
+                    void* stream) {
   GP_REQUIRE(da && y && dy && P > 0 && C % 8 == 0 && count > 0, "gp_bn_bwd_apply_f32: bad arguments");
+  GP_REQUIRE((acc_dbeta == nullptr) == (acc_dgamma == nullptr), "gp_bn_bwd_apply_f32: acc_dbeta and acc_dgamma go together");
   const ColLaunch L = col_launch(P, C, 0);
   bn_bwd_apply_kernel<float><<<L.grid, L.block, 0, as_stream(stream)>>>(
       static_cast<const __nv_bfloat16*>(da), y, static_cast<__nv_bfloat16*>(dy), P, C, scale, shift, mean, rstd, sum_dz,
-      sum_dzx, (float)(1.0 / count), act, L.rpb);
+      sum_dzx, (float)(1.0 / count), act, L.rpb, acc_dbeta, acc_dgamma, acc_scale);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }

@@ -104,8 +104,8 @@ __device__ __forceinline__ void load_da(const __nv_bfloat16* __restrict__ da, in
 }
 
 // per-sample sums: part[n][0][c] += sum_hw dz, part[n][1][c] += sum_hw dz * xhat   (dz = da * act'(z))
-__global__ void cbn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ y, int H,
-                                      int W, int C, const float* __restrict__ mean, const float* __restrict__ rstd,
+__global__ void cbn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ y,
+                                      const void* __restrict__ y_comp, int fmt, int H, int W, int C, const float* __restrict__ mean, const float* __restrict__ rstd,
                                       const float* __restrict__ emb, const long long* __restrict__ labels, int act,
                                       int up, float* __restrict__ part, int px_per_block) {
   const int n = blockIdx.y;
@@ -129,7 +129,7 @@ __global__ void cbn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, cons
     const int p0 = blockIdx.x * px_per_block, p1 = min(p0 + px_per_block, HW);
     for (int p = p0 + lane; p < p1; p += lanes) {
       float fy[8], fd[8];
-      unpack8(*reinterpret_cast<const uint4*>(y + ((long long)n * HW + p) * C + g * 8), fy);
+      load8c(y, y_comp, fmt, ((long long)n * HW + p) * C + g * 8, fy);   // the value the forward normalised
       load_da(da, n, p, H, W, C, g, up, fd);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -179,7 +179,8 @@ __global__ void cbn_bwd_finalize_kernel(const float* __restrict__ part, int NB, 
 
 // dy[n,hw,c] = rstd[c] * (gamma[n][c] * dz - S0[c]/M - xhat * S1[c]/M)
 __global__ void cbn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ y,
-                                     __nv_bfloat16* __restrict__ dy, int H, int W, int C,
+                                     const void* __restrict__ y_comp, int fmt, __nv_bfloat16* __restrict__ dy, int H,
+                                     int W, int C,
                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                      const float* __restrict__ emb, const long long* __restrict__ labels,
                                      const float* __restrict__ S, float inv_count, int act, int up, int px_per_block) {
@@ -203,7 +204,7 @@ __global__ void cbn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const
   const int p0 = blockIdx.x * px_per_block, p1 = min(p0 + px_per_block, HW);
   for (int p = p0 + lane; p < p1; p += lanes) {
     float fy[8], fd[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(y + ((long long)n * HW + p) * C + g * 8), fy);
+    load8c(y, y_comp, fmt, ((long long)n * HW + p) * C + g * 8, fy);
     load_da(da, n, p, H, W, C, g, up, fd);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -475,9 +476,10 @@ int gp_cbn_apply_act(const void* y, const void* y_comp, void* out, void* out_com
 }
 
 // part: fp32 [NB][2][C] scratch; S: fp32 [2][C] out; demb: fp32 [ncls][2C] or NULL (both zeroed by this call as needed)
-int gp_cbn_bwd_reduce(const void* da, const void* y, int NB, int H, int W, int C, const float* mean, const float* rstd,
-                      const float* emb, const long long* labels, int act, int upsample, float* part, float* S,
-                      float* demb, int n_classes, void* stream) {
+int gp_cbn_bwd_reduce(const void* da, const void* y, const void* y_comp, int comp_fmt, int NB, int H, int W, int C,
+                      const float* mean, const float* rstd, const float* emb, const long long* labels, int act,
+                      int upsample, float* part, float* S, float* demb, int n_classes, void* stream) {
+  GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_cbn_bwd_reduce: unknown companion format %d", comp_fmt);
   GP_REQUIRE(da && y && part && S && NB > 0 && C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0,
              "gp_cbn_bwd_reduce: bad arguments");
   cudaStream_t st = as_stream(stream);
@@ -485,22 +487,23 @@ int gp_cbn_bwd_reduce(const void* da, const void* y, int NB, int H, int W, int C
   if (demb != nullptr) GP_CHECK_CUDA(cudaMemsetAsync(demb, 0, sizeof(float) * n_classes * 2 * C, st));
   const CbnLaunch L = cbn_launch(NB, H * W, C);
   cbn_bwd_reduce_kernel<<<L.grid, L.block, 2 * C * sizeof(float), st>>>(
-      static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), H, W, C, mean, rstd, emb, labels, act,
-      upsample, part, L.ppb);
+      static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), y_comp, comp_fmt, H, W, C, mean, rstd,
+      emb, labels, act, upsample, part, L.ppb);
   GP_CHECK_LAUNCH();
   cbn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, NB, C, emb, labels, S, demb);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
 
-int gp_cbn_bwd_apply(const void* da, const void* y, void* dy, int NB, int H, int W, int C, const float* mean,
-                     const float* rstd, const float* emb, const long long* labels, const float* S, double count, int act,
-                     int upsample, void* stream) {
+int gp_cbn_bwd_apply(const void* da, const void* y, const void* y_comp, int comp_fmt, void* dy, int NB, int H, int W,
+                     int C, const float* mean, const float* rstd, const float* emb, const long long* labels,
+                     const float* S, double count, int act, int upsample, void* stream) {
+  GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_cbn_bwd_apply: unknown companion format %d", comp_fmt);
   GP_REQUIRE(da && y && dy && S && NB > 0 && C % 8 == 0 && count > 0, "gp_cbn_bwd_apply: bad arguments");
   const CbnLaunch L = cbn_launch(NB, H * W, C);
   cbn_bwd_apply_kernel<<<L.grid, L.block, 0, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(dy), H, W,
-      C, mean, rstd, emb, labels, S, (float)(1.0 / count), act, upsample, L.ppb);
+      static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), y_comp, comp_fmt,
+      static_cast<__nv_bfloat16*>(dy), H, W, C, mean, rstd, emb, labels, S, (float)(1.0 / count), act, upsample, L.ppb);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }

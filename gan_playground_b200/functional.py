@@ -93,26 +93,73 @@ def _bn_forward(y, gamma, beta, bufs, act, training=True, st=None, pair=False, c
     return a, a_lo, fin, count
 
 
-def _bn_backward(da, y, fin, count, act, training=True, need_affine=True):
-    """Returns (dy, dgamma, dbeta); dgamma / dbeta are None when the affine parameters need no gradient."""
+def _bn_backward(da, y, fin, count, act, training=True, need_affine=True, comp=None, affine=None):
+    """Returns (dy, dgamma, dbeta); dgamma / dbeta are None when the affine parameters need no gradient — or when their
+    gradients were delivered straight into the parameters' .grad buffers by the apply kernel (`affine` = (gamma, beta)
+    parameters that own such a buffer, ops.grad_target). comp: companion tensor of y — the backward must see the value
+    the forward normalised, not its bf16 rounding (activation mask, xhat)."""
     f32 = y.dtype == torch.float32
-    red = ops.bn_bwd_reduce_f32(da, y, fin, act) if f32 else ops.bn_bwd_reduce(da, y, fin, act)
+    if f32:
+        red = ops.bn_bwd_reduce_f32(da, y, fin, act)
+    elif comp is not None:
+        red = ops.bn_bwd_reduce_comp(da, y, comp, fin, act)
+    else:
+        red = ops.bn_bwd_reduce(da, y, fin, act)
     parallel.all_reduce_sum_(red)
     # eval mode: statistics are constants, so the two batch-coupling terms vanish
     red_used = red if training else torch.zeros_like(red)
-    if f32:
-        dy = ops.bn_bwd_apply_f32(da, y, fin, red_used, count, act)
-    else:
-        dy = ops.bn_bwd_apply(da, y, fin, red_used, count, act)
     # dbeta = sum dz, dgamma = sum dz * xhat. After the all-reduce `red` holds global sums of rank-local-mean-loss
-    # gradients; parameter gradients are averaged over ranks later, so hand back global / world.
-    if not need_affine:
-        return dy, None, None
+    # gradients; parameter gradients are averaged over ranks later, so what is delivered is global / world.
     w = parallel.world_size()
+    acc = None
+    if need_affine and training and affine is not None:
+        tg, tb = ops.grad_target(affine[0]), ops.grad_target(affine[1])
+        if tg is not None and tb is not None:
+            acc = (tb, tg)
+    if f32:
+        dy = ops.bn_bwd_apply_f32(da, y, fin, red_used, count, act, acc, 1.0 / w)
+    elif comp is not None:
+        dy = ops.bn_bwd_apply_comp(da, y, comp, fin, red_used, count, act, acc, 1.0 / w)
+    else:
+        dy = ops.bn_bwd_apply(da, y, fin, red_used, count, act, acc, 1.0 / w)
+    if not need_affine or acc is not None:
+        return dy, None, None
     dgamma, dbeta = red[1], red[0]
     if w > 1:
         dgamma, dbeta = dgamma / w, dbeta / w
     return dy, dgamma.clone(), dbeta.clone()
+
+
+def _params(*ts):
+    """The nn.Parameter objects among a node's inputs (None for derived tensors such as a spectral-normalised weight):
+    kept on the ctx so that backward can deliver gradients straight into their .grad buffers (ops.grad_target)."""
+    return tuple(t if isinstance(t, torch.nn.Parameter) else None for t in ts)
+
+
+def _deliver_conv_wgrad(dwp, shape, param):
+    """Packed fp32 weight gradient -> the parameter: accumulated straight into param.grad when it owns a buffer (returns
+    None: autograd has nothing left to add), else returned as a fresh tensor in torch's layout."""
+    tgt = ops.grad_target(param)
+    if tgt is not None:
+        ops.unpack_conv_wgrad(dwp, shape, into=tgt)
+        return None
+    return ops.unpack_conv_wgrad(dwp, shape)
+
+
+def _deliver_matrix_grad(src, shape, param, *args, **kw):
+    tgt = ops.grad_target(param)
+    if tgt is not None:
+        ops.unpack_matrix(src, shape, *args, into=tgt, **kw)
+        return None
+    return ops.unpack_matrix(src, shape, *args, **kw)
+
+
+def _deliver_colsum(dy, bias):
+    tgt = ops.grad_target(bias)
+    if tgt is not None:
+        ops.colsum(dy, into=tgt)
+        return None
+    return ops.colsum(dy)
 
 
 class ConvBlock(torch.autograd.Function):
@@ -153,6 +200,7 @@ class ConvBlock(torch.autograd.Function):
             wp = cache.get((key, "fwd"), weight, lambda: ops.pack_conv_weight(weight.detach(), n_dim))
             y = ops.conv_fwd(x, wp, b, kind, Ho, Wo, ops.ACT_NONE if has_bn else act, stats=st)
         ctx.transposed, ctx.act, ctx.has_bn, ctx.cache, ctx.key = transposed, act, has_bn, cache, key
+        ctx.params = _params(weight, bias, gamma, beta)   # the Parameter objects: gradients go straight into their .grad
         if has_bn:
             a, a_lo, fin, count = _bn_forward(y, gamma.detach() if gamma is not None else None,
                                               beta.detach() if beta is not None else None, bufs, act, training, st,
@@ -174,7 +222,8 @@ class ConvBlock(torch.autograd.Function):
         if ctx.has_bn:
             x, weight, y, fin = ctx.saved_tensors
             dy, dgamma, dbeta = _bn_backward(da, y, fin, ctx.count, ctx.act, ctx.training,
-                                             need_affine=ctx.needs_input_grad[4] or ctx.needs_input_grad[5])
+                                             need_affine=ctx.needs_input_grad[4] or ctx.needs_input_grad[5],
+                                             affine=ctx.params[2:4])
             # a bias in front of BatchNorm has an analytically zero gradient (the reference's is fp32 rounding noise,
             # SURVEY.md §2.2): hand autograd no tensor at all instead of a zero fill plus an accumulation pass
             dbias = None
@@ -182,14 +231,14 @@ class ConvBlock(torch.autograd.Function):
             x, weight, a = ctx.saved_tensors
             dy = ops.act_bwd(da, a, ctx.act) if ctx.act != ops.ACT_NONE else da
             dgamma = dbeta = None
-            dbias = ops.colsum(dy)
+            dbias = _deliver_colsum(dy, ctx.params[1]) if ctx.needs_input_grad[3] else None
         dweight = dx = None
         if ctx.needs_input_grad[2]:
             if ctx.transposed:   # dW[Cin][tap][Cout]: dense = x (input grid), gathered = dy (output grid)
                 dwp = ops.conv_wgrad(x, dy, ops.KIND_CONV_K4S2, 16)
             else:                # dW[Cout][tap][Cin]: dense = dy (output grid), gathered = x (input grid)
                 dwp = ops.conv_wgrad(dy, x, ops.KIND_CONV_K4S2, 16)
-            dweight = ops.unpack_conv_wgrad(dwp, weight.shape)
+            dweight = _deliver_conv_wgrad(dwp, weight.shape, ctx.params[0])
         if ctx.needs_input_grad[0]:
             NB, H, W, _ = x.shape
             if ctx.transposed:   # dgrad of ConvT == strided conv over dy with weights [Cin][tap][Cout]
@@ -240,6 +289,7 @@ class LinearToNHWC(torch.autograd.Function):
             a, a_lo = ops.conv_fwd(zb.view(B, 1, 1, Kp), wp, bp, ops.KIND_CONV_K1S1, 1, 1, act, flops=fl), None
         ctx.save_for_backward(zb, a, weight)
         ctx.dims = (B, K, O, HW, C, Kp, act)
+        ctx.params = _params(weight, bias)
         if a_lo is not None:
             ctx.mark_non_differentiable(a_lo)
         return a.view(B, bw, bw, C), a_lo
@@ -255,10 +305,10 @@ class LinearToNHWC(torch.autograd.Function):
         dweight = dbias = None
         if ctx.needs_input_grad[1]:
             dwp = ops.conv_wgrad(dy, zb.view(B, 1, 1, Kp), ops.KIND_CONV_K1S1, 1, flops=2.0 * B * O * K)  # [O][1][Kp]
-            dweight = ops.unpack_matrix(dwp.view(O, Kp), weight.shape, O, K, Kp, K, 1, perm=HW)
+            dweight = _deliver_matrix_grad(dwp.view(O, Kp), weight.shape, ctx.params[0], O, K, Kp, K, 1, perm=HW)
         if ctx.needs_input_grad[2]:
             db = ops.colsum(dy)
-            dbias = ops.unpack_matrix(db, (O,), O, 1, 1, 1, 1, perm=HW)
+            dbias = _deliver_matrix_grad(db, (O,), ctx.params[1], O, 1, 1, 1, 1, perm=HW)
         if ctx.needs_input_grad[0]:
             raise ops._lib.GpError("gradient w.r.t. the latent input of the first Linear is not implemented")
         return None, dweight, dbias, None, None, None, None
@@ -304,6 +354,7 @@ class ImageConv(torch.autograd.Function):
             a, a_lo = ops.conv_fwd(col, wp, bias.detach(), ops.KIND_CONV_K1S1, H // 2, W // 2, act, flops=fl), None
         ctx.save_for_backward(col, weight, a)   # the im2col buffer (hi half) is kept for wgrad instead of rebuilt
         ctx.misc = (act, cache, key, (NB, ch, H, W))
+        ctx.params = _params(weight, bias)
         return a, a_lo
 
     @staticmethod
@@ -318,9 +369,9 @@ class ImageConv(torch.autograd.Function):
         dweight = dbias = dx = None
         if ctx.needs_input_grad[1]:
             dwp = ops.conv_wgrad(dy, col, ops.KIND_CONV_K1S1, 1, flops=fl)  # [Cout][1][64]
-            dweight = ops.unpack_matrix(dwp.view(Cout, 64), weight.shape, Cout, ch * 16, 64, ch * 16, 1)
+            dweight = _deliver_matrix_grad(dwp.view(Cout, 64), weight.shape, ctx.params[0], Cout, ch * 16, 64, ch * 16, 1)
         if ctx.needs_input_grad[2]:
-            dbias = ops.colsum(dy)
+            dbias = _deliver_colsum(dy, ctx.params[1])
         if ctx.needs_input_grad[0]:
             # dcol[px][j] = sum_o dy[px][o] * W[o][j]  -> weights [64][Cout] = W^T (rows j >= ch*16 are zero)
             wpt = cache.get((key, "dgrad"), weight,
@@ -366,6 +417,7 @@ class ImageConvT(torch.autograd.Function):
             out = ops.col2im_k4s2(ycol, bias.detach(), ch, act)
         ctx.save_for_backward(x, weight, out)
         ctx.misc = (act, cache, key)
+        ctx.params = _params(weight, bias)
         return out
 
     @staticmethod
@@ -381,9 +433,12 @@ class ImageConvT(torch.autograd.Function):
         dweight = dbias = dx = None
         if ctx.needs_input_grad[2]:
             dwp = ops.conv_wgrad(x, dcol, ops.KIND_CONV_K1S1, 1, flops=fl)  # [Cin][1][64]
-            dweight = ops.unpack_matrix(dwp.view(Cin, 64), weight.shape, Cin, ch * 16, 64, ch * 16, 1)
+            dweight = _deliver_matrix_grad(dwp.view(Cin, 64), weight.shape, ctx.params[0], Cin, ch * 16, 64, ch * 16, 1)
         if ctx.needs_input_grad[3]:
-            dbias = ops.image_bias_grad(dout, out if act == ops.ACT_TANH else None)
+            tgt = ops.grad_target(ctx.params[1])
+            dbias = ops.image_bias_grad(dout, out if act == ops.ACT_TANH else None, into=tgt)
+            if tgt is not None:
+                dbias = None
         if ctx.needs_input_grad[0]:
             wpd = cache.get((key, "dgrad"), weight,
                             lambda: ops.pack_matrix(weight.detach(), Cin, ch * 16, Cin, 64, ch * 16, 1))

@@ -13,7 +13,8 @@ run all three modes."""
 import torch
 
 from . import config, ops, parallel
-from .functional import BN_EPS, BN_MOMENTUM, _bn_backward, _bn_forward, _f16_operand
+from .functional import (BN_EPS, BN_MOMENTUM, _bn_backward, _bn_forward, _deliver_colsum, _deliver_conv_wgrad,
+                         _f16_operand, _params)
 
 
 def _fmt():
@@ -70,6 +71,7 @@ class Conv2dNHWC(torch.autograd.Function):
             a, a_comp = ops.conv_fwd(x, wp, b, kind, H, W, act, residual=residual), None
         ctx.save_for_backward(x, weight, a)
         ctx.misc = (kind, ksize * ksize, act, cache, key, residual is not None, bias is not None)
+        ctx.params = _params(weight, bias)
         return a, a_comp
 
     @staticmethod
@@ -81,9 +83,9 @@ class Conv2dNHWC(torch.autograd.Function):
         NB, H, W, _ = x.shape
         dx = dweight = dbias = None
         if ctx.needs_input_grad[2]:
-            dweight = ops.unpack_conv_wgrad(ops.conv_wgrad(dy, x, kind, taps), weight.shape)
+            dweight = _deliver_conv_wgrad(ops.conv_wgrad(dy, x, kind, taps), weight.shape, ctx.params[0])
         if has_bias and ctx.needs_input_grad[3]:
-            dbias = ops.colsum(dy)
+            dbias = _deliver_colsum(dy, ctx.params[1])
         if ctx.needs_input_grad[0]:
             # dgrad of a stride-1 conv: the same conv with channels swapped and the tap order reversed
             wpd = cache.get((key, "dgrad"), weight, lambda: ops.pack_conv_weight(weight.detach(), 1 | 2))
@@ -99,17 +101,22 @@ class BNAct(torch.autograd.Function):
     def forward(ctx, y, y_comp, gamma, beta, bufs, act, training):
         a, a_comp, fin, count = _bn_forward(y, gamma.detach(), beta.detach(), bufs, act, training, comp=y_comp,
                                             out_fmt=_fmt())
-        ctx.save_for_backward(y, fin)
+        # the backward normalises the SAME value: keep y's companion (activation mask / xhat from the bf16 rounding of y
+        # cost the dcgan_blur G step 1.6e-3 of gradient cosine)
+        ctx.has_comp = y_comp is not None
+        ctx.save_for_backward(y, fin, *((y_comp,) if y_comp is not None else ()))
         ctx.misc = (count, act, training)
+        ctx.params = _params(gamma, beta)
         if a_comp is not None:
             ctx.mark_non_differentiable(a_comp)
         return a, a_comp
 
     @staticmethod
     def backward(ctx, da, _unused=None):
-        y, fin = ctx.saved_tensors
+        y, fin = ctx.saved_tensors[:2]
+        y_comp = ctx.saved_tensors[2] if ctx.has_comp else None
         count, act, training = ctx.misc
-        dy, dgamma, dbeta = _bn_backward(da.contiguous(), y, fin, count, act, training)
+        dy, dgamma, dbeta = _bn_backward(da.contiguous(), y, fin, count, act, training, comp=y_comp, affine=ctx.params)
         return dy, None, dgamma, dbeta, None, None, None
 
 
@@ -136,7 +143,8 @@ class CondBNAct(torch.autograd.Function):
                 out_comp = None
         else:
             out, out_comp = ops.cbn_apply_act(x, fin, e, labels, act, upsample), None
-        ctx.save_for_backward(x, fin, e, labels)
+        ctx.has_comp = x_comp is not None
+        ctx.save_for_backward(x, fin, e, labels, *((x_comp,) if x_comp is not None else ()))
         ctx.misc = (count, act, upsample, training, emb.shape[0])
         if out_comp is not None:
             ctx.mark_non_differentiable(out_comp)
@@ -144,14 +152,15 @@ class CondBNAct(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, da, _unused=None):
-        x, fin, e, labels = ctx.saved_tensors
+        x, fin, e, labels = ctx.saved_tensors[:4]
+        x_comp = ctx.saved_tensors[4] if ctx.has_comp else None
         count, act, upsample, training, ncls = ctx.misc
         da = da.contiguous()
-        S, demb = ops.cbn_bwd_reduce(da, x, fin, e, labels, act, upsample, ncls)
+        S, demb = ops.cbn_bwd_reduce(da, x, fin, e, labels, act, upsample, ncls, comp=x_comp)
         parallel.all_reduce_sum_(S)
         if not training:
             S = torch.zeros_like(S)
-        dx = ops.cbn_bwd_apply(da, x, fin, e, labels, S, count, act, upsample)
+        dx = ops.cbn_bwd_apply(da, x, fin, e, labels, S, count, act, upsample, comp=x_comp)
         return dx, None, demb, None, None, None, None, None
 
 

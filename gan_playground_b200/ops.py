@@ -25,7 +25,7 @@ _SIGS = {
     "gp_bn_eval_params": [_vp, _vp, _vp, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp],
     "gp_bn_apply_act": [_vp, _vp, _ll, _i, _vp, _vp, _i, _vp],
     "gp_bn_bwd_reduce": [_vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
-    "gp_bn_bwd_apply": [_vp, _vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _vp],
+    "gp_bn_bwd_apply": [_vp, _vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _vp, _vp, _f, _vp],
     "gp_act_bwd": [_vp, _vp, _vp, _ll, _i, _vp],
     "gp_colsum": [_vp, _ll, _i, _vp, _vp],
     "gp_im2col_k4s2": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
@@ -286,12 +286,29 @@ def pack_conv_weight(w, n_dim, inv_scale=None):
     return dst
 
 
-def unpack_conv_wgrad(dwp, shape):
-    """dwp: fp32 [M, taps, N] -> fp32 tensor of `shape` = (M, N, kh, kw)."""
+UNPACK_ACCUMULATE = 1 << 30
+
+
+def grad_target(param):
+    """The parameter's existing .grad buffer when gradients can be delivered straight into it (fp32, contiguous, a leaf
+    that already owns a .grad — the step drivers' flat gradient buffers), else None. The node then returns no tensor
+    for that parameter, so autograd runs no AccumulateGrad pass: `grad += new` happens inside the producing kernel
+    (gradients of the D-real and D-fake passes accumulate, main_dcgan.py:73,84)."""
+    if param is None or not isinstance(param, torch.nn.Parameter) or not param.is_leaf:
+        return None
+    g = param.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != param.shape or not g.is_cuda == param.is_cuda:
+        return None
+    return g
+
+
+def unpack_conv_wgrad(dwp, shape, into=None):
+    """dwp: fp32 [M, taps, N] -> fp32 tensor of `shape` = (M, N, kh, kw); into: accumulate into this tensor instead."""
     _chk(dwp, torch.float32, "dwp")
     M, taps, N = dwp.shape
-    dst = torch.empty(shape, device=dwp.device, dtype=torch.float32)
-    check(_fn("gp_unpack_conv_wgrad")(_p(dwp), _p(dst), M, N, taps, _stream()), "gp_unpack_conv_wgrad")
+    dst = torch.empty(shape, device=dwp.device, dtype=torch.float32) if into is None else into
+    check(_fn("gp_unpack_conv_wgrad")(_p(dwp), _p(dst), M, N, taps | (UNPACK_ACCUMULATE if into is not None else 0),
+                                      _stream()), "gp_unpack_conv_wgrad")
     return dst
 
 
@@ -303,10 +320,11 @@ def pack_matrix(src, R, K, Rpad, ld, s_r, s_k, perm=1, inv_scale=None):
     return dst
 
 
-def unpack_matrix(src, out_shape, R, K, ld_src, s_r, s_k, perm=1):
+def unpack_matrix(src, out_shape, R, K, ld_src, s_r, s_k, perm=1, into=None):
     _chk(src, torch.float32, "src")
-    dst = torch.empty(out_shape, device=src.device, dtype=torch.float32)   # every element of out_shape is written
-    check(_fn("gp_unpack_matrix")(_p(src), _p(dst), R, K, ld_src, s_r, s_k, perm, _stream()), "gp_unpack_matrix")
+    dst = torch.empty(out_shape, device=src.device, dtype=torch.float32) if into is None else into   # every element is written
+    check(_fn("gp_unpack_matrix")(_p(src), _p(dst), R, K, ld_src, s_r, s_k, perm | (UNPACK_ACCUMULATE if into is not None else 0),
+                                  _stream()), "gp_unpack_matrix")
     return dst
 
 
@@ -358,11 +376,13 @@ def bn_bwd_reduce(da, y, fin, act):
     return red
 
 
-def bn_bwd_apply(da, y, fin, red, count, act):
+def bn_bwd_apply(da, y, fin, red, count, act, acc=None, acc_scale=1.0):
+    """acc = (dbeta_grad_buffer, dgamma_grad_buffer): the affine gradients are added into them by the same launch."""
     C = y.shape[-1]
     dy = torch.empty_like(y)
     check(_fn("gp_bn_bwd_apply")(_p(da), _p(y), _p(dy), y.numel() // C, C, _p(fin[2]), _p(fin[3]), _p(fin[0]), _p(fin[1]),
-                                 _p(red[0]), _p(red[1]), float(count), act, _stream()), "gp_bn_bwd_apply")
+                                 _p(red[0]), _p(red[1]), float(count), act, _p(acc[0]) if acc else None,
+                                 _p(acc[1]) if acc else None, float(acc_scale), _stream()), "gp_bn_bwd_apply")
     return dy
 
 
@@ -374,10 +394,11 @@ def act_bwd(da, a, act):
     return dy
 
 
-def colsum(x):
+def colsum(x, into=None):
+    """out[c] (+)= sum over rows; into: an existing fp32 [C] buffer to accumulate into (a bias' .grad)."""
     _chk(x, torch.bfloat16, "x")
     C = x.shape[-1]
-    out = zeros((C,), x.device)
+    out = zeros((C,), x.device) if into is None else into
     check(_fn("gp_colsum")(_p(x), x.numel() // C, C, _p(out), _stream()), "gp_colsum")
     return out
 
@@ -403,10 +424,10 @@ def col2im_k4s2(col, bias, ch, act):
     return img
 
 
-def image_bias_grad(dout, mul=None):
+def image_bias_grad(dout, mul=None, into=None):
     _chk(dout, torch.float32, "dout")
     NB, ch, H, W = dout.shape
-    db = zeros((ch,), dout.device)
+    db = zeros((ch,), dout.device) if into is None else into
     check(_fn("gp_image_bias_grad")(_p(dout), _p(mul), _p(db), NB, ch, H * W, _stream()), "gp_image_bias_grad")
     return db
 
@@ -496,8 +517,8 @@ def sn_grad(g, w_sn, dim, u, v, sigma):
 # ------------------------------------------------------------------------------------------------ SNGAN projection
 _SIGS.update({
     "gp_cbn_apply_act": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp],
-    "gp_cbn_bwd_reduce": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp],
-    "gp_cbn_bwd_apply": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _i, _i, _vp],
+    "gp_cbn_bwd_reduce": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp],
+    "gp_cbn_bwd_apply": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _i, _i, _vp],
     "gp_upsample2x": [_vp, _vp, _i, _i, _i, _i, _f, _vp],
     "gp_pool2x": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
     "gp_act_fwd": [_vp, _vp, _vp, _vp, _i, _ll, _i, _vp],
@@ -552,23 +573,25 @@ def cbn_apply_act(y, fin, emb, labels, act, upsample, comp=None, out_fmt=COMP_NO
     return _ret(out, out_comp, out_fmt)
 
 
-def cbn_bwd_reduce(da, y, fin, emb, labels, act, upsample, n_classes):
-    """Returns (S fp32 [2, C], demb fp32 [ncls, 2C] or None)."""
+def cbn_bwd_reduce(da, y, fin, emb, labels, act, upsample, n_classes, comp=None):
+    """Returns (S fp32 [2, C], demb fp32 [ncls, 2C] or None). comp: companion of y (the forward's view of it)."""
     _chk(da, torch.bfloat16, "da")
     NB, H, W, C = y.shape
     part = torch.empty((NB, 2, C), device=y.device, dtype=torch.float32)
     S = torch.empty((2, C), device=y.device, dtype=torch.float32)
     demb = torch.empty((n_classes, 2 * C), device=y.device, dtype=torch.float32) if emb is not None else None
-    check(_fn("gp_cbn_bwd_reduce")(_p(da), _p(y), NB, H, W, C, _p(fin[0]), _p(fin[1]), _p(emb), _p(labels), act,
-                                   1 if upsample else 0, _p(part), _p(S), _p(demb), n_classes, _stream()), "gp_cbn_bwd_reduce")
+    check(_fn("gp_cbn_bwd_reduce")(_p(da), _p(y), _p(comp), comp_fmt_of(comp), NB, H, W, C, _p(fin[0]), _p(fin[1]), _p(emb),
+                                   _p(labels), act, 1 if upsample else 0, _p(part), _p(S), _p(demb), n_classes, _stream()),
+          "gp_cbn_bwd_reduce")
     return S, demb
 
 
-def cbn_bwd_apply(da, y, fin, emb, labels, S, count, act, upsample):
+def cbn_bwd_apply(da, y, fin, emb, labels, S, count, act, upsample, comp=None):
     NB, H, W, C = y.shape
     dy = torch.empty_like(y)
-    check(_fn("gp_cbn_bwd_apply")(_p(da), _p(y), _p(dy), NB, H, W, C, _p(fin[0]), _p(fin[1]), _p(emb), _p(labels), _p(S),
-                                  float(count), act, 1 if upsample else 0, _stream()), "gp_cbn_bwd_apply")
+    check(_fn("gp_cbn_bwd_apply")(_p(da), _p(y), _p(comp), comp_fmt_of(comp), _p(dy), NB, H, W, C, _p(fin[0]), _p(fin[1]),
+                                  _p(emb), _p(labels), _p(S), float(count), act, 1 if upsample else 0, _stream()),
+          "gp_cbn_bwd_apply")
     return dy
 
 
@@ -688,7 +711,9 @@ _SIGS.update({
     "gp_bn_stats_comp": [_vp, _vp, _i, _ll, _i, _vp, _vp, _vp],
     "gp_bn_apply_act_comp": [_vp, _vp, _vp, _vp, _i, _ll, _i, _vp, _vp, _i, _vp],
     "gp_bn_bwd_reduce_f32": [_vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
-    "gp_bn_bwd_apply_f32": [_vp, _vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _vp],
+    "gp_bn_bwd_apply_f32": [_vp, _vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _vp, _vp, _f, _vp],
+    "gp_bn_bwd_reduce_comp": [_vp, _vp, _vp, _i, _ll, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+    "gp_bn_bwd_apply_comp": [_vp, _vp, _vp, _i, _vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _vp, _vp, _f, _vp],
     "gp_im2col_k4s2_split": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "gp_col2im_k4s2_f32": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "gp_head_fwd_split": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _ll, _vp],
@@ -751,11 +776,33 @@ def bn_bwd_reduce_f32(da, y, fin, act):
     return red
 
 
-def bn_bwd_apply_f32(da, y, fin, red, count, act):
+def bn_bwd_apply_f32(da, y, fin, red, count, act, acc=None, acc_scale=1.0):
     C = y.shape[-1]
     dy = torch.empty(y.shape, device=y.device, dtype=torch.bfloat16)
     check(_fn("gp_bn_bwd_apply_f32")(_p(da), _p(y), _p(dy), y.numel() // C, C, _p(fin[2]), _p(fin[3]), _p(fin[0]), _p(fin[1]),
-                                     _p(red[0]), _p(red[1]), float(count), act, _stream()), "gp_bn_bwd_apply_f32")
+                                     _p(red[0]), _p(red[1]), float(count), act, _p(acc[0]) if acc else None,
+                                     _p(acc[1]) if acc else None, float(acc_scale), _stream()), "gp_bn_bwd_apply_f32")
+    return dy
+
+
+def bn_bwd_reduce_comp(da, y, comp, fin, act):
+    """bn_bwd_reduce with y read through its companion tensor (the value the forward normalised)."""
+    _chk(da, torch.bfloat16, "da")
+    _chk(y, torch.bfloat16, "y")
+    C = y.shape[-1]
+    red = zeros((2, C), y.device)
+    check(_fn("gp_bn_bwd_reduce_comp")(_p(da), _p(y), _p(comp), comp_fmt_of(comp), y.numel() // C, C, _p(fin[2]), _p(fin[3]),
+                                       _p(fin[0]), _p(fin[1]), act, _p(red[0]), _p(red[1]), _stream()), "gp_bn_bwd_reduce_comp")
+    return red
+
+
+def bn_bwd_apply_comp(da, y, comp, fin, red, count, act, acc=None, acc_scale=1.0):
+    C = y.shape[-1]
+    dy = torch.empty_like(y)
+    check(_fn("gp_bn_bwd_apply_comp")(_p(da), _p(y), _p(comp), comp_fmt_of(comp), _p(dy), y.numel() // C, C, _p(fin[2]),
+                                      _p(fin[3]), _p(fin[0]), _p(fin[1]), _p(red[0]), _p(red[1]), float(count), act,
+                                      _p(acc[0]) if acc else None, _p(acc[1]) if acc else None, float(acc_scale), _stream()),
+          "gp_bn_bwd_apply_comp")
     return dy
 
 

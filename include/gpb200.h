@@ -115,7 +115,11 @@ int gp_conv_wgrad(const gp_conv_wgrad_t* p, void* stream);
  * gp_pack_matrix: dst[r][k] = src[map(r)*s_r + k*s_k] / inv_scale for r < R, k < K, zero padding up to [Rpad][ld_dst];
  *   perm > 1 reorders rows from NCHW-flatten (c*perm + hw) to NHWC-flatten (hw*(R/perm) + c) order
  *   (the view(B, C, 4, 4) after the generator's Linear, models/dcgan.py:50-51).
- * gp_unpack_matrix: the inverse mapping for fp32 gradients. */
+ * gp_unpack_matrix: the inverse mapping for fp32 gradients.
+ * GP_UNPACK_ACCUMULATE or-ed into `taps` (gp_unpack_conv_wgrad) / `perm` (gp_unpack_matrix): dst += value instead of
+ * dst = value — the destination is the parameter's existing .grad buffer (gradients of the D-real and D-fake passes
+ * accumulate there, main_dcgan.py:73,84), so no separate accumulation pass runs afterwards. */
+#define GP_UNPACK_ACCUMULATE (1 << 30)
 int gp_pack_conv_weight(const float* src, void* dst, int D0, int D1, int taps, int n_dim, const float* inv_scale,
                         void* stream);
 int gp_unpack_conv_wgrad(const float* src, float* dst, int M, int N, int taps, void* stream);
@@ -145,9 +149,13 @@ int gp_bn_apply_act(const void* y, void* out, long long P, int C, const float* s
                     void* stream);
 int gp_bn_bwd_reduce(const void* da, const void* y, long long P, int C, const float* scale, const float* shift,
                      const float* mean, const float* rstd, int act, float* sum_dz, float* sum_dzx, void* stream);
+/* acc_dbeta / acc_dgamma (optional, both or neither): the affine parameters' gradient buffers (fp32 [C]);
+ * acc_dbeta += sum_dz * acc_scale, acc_dgamma += sum_dzx * acc_scale in the same launch (acc_scale = 1 / world_size) —
+ * the gradient lands in `.grad` without an accumulation pass. */
 int gp_bn_bwd_apply(const void* da, const void* y, void* dy, long long P, int C, const float* scale,
                     const float* shift, const float* mean, const float* rstd, const float* sum_dz,
-                    const float* sum_dzx, double count, int act, void* stream);
+                    const float* sum_dzx, double count, int act, float* acc_dbeta, float* acc_dgamma, float acc_scale,
+                    void* stream);
 int gp_act_bwd(const void* da, const void* a, void* dy, long long n, int act, void* stream);
 int gp_colsum(const void* x, long long P, int C, float* out, void* stream);
 
@@ -217,12 +225,12 @@ int gp_sn_grad(const float* g, const float* w_sn, int A, int B, int T, int dim, 
 int gp_cbn_apply_act(const void* y, const void* y_comp, void* out, void* out_comp, int comp_fmt, int NB, int H, int W,
                      int C, const float* mean, const float* rstd, const float* emb, const long long* labels, int act,
                      int upsample, void* stream);
-int gp_cbn_bwd_reduce(const void* da, const void* y, int NB, int H, int W, int C, const float* mean, const float* rstd,
-                      const float* emb, const long long* labels, int act, int upsample, float* part, float* S,
-                      float* demb, int n_classes, void* stream);
-int gp_cbn_bwd_apply(const void* da, const void* y, void* dy, int NB, int H, int W, int C, const float* mean,
-                     const float* rstd, const float* emb, const long long* labels, const float* S, double count, int act,
-                     int upsample, void* stream);
+int gp_cbn_bwd_reduce(const void* da, const void* y, const void* y_comp, int comp_fmt, int NB, int H, int W, int C,
+                      const float* mean, const float* rstd, const float* emb, const long long* labels, int act,
+                      int upsample, float* part, float* S, float* demb, int n_classes, void* stream);
+int gp_cbn_bwd_apply(const void* da, const void* y, const void* y_comp, int comp_fmt, void* dy, int NB, int H, int W,
+                     int C, const float* mean, const float* rstd, const float* emb, const long long* labels,
+                     const float* S, double count, int act, int upsample, void* stream);
 /* nearest x2 upsampling / 2x2 sum pooling with a scale (F.interpolate :53,60; F.avg_pool2d :128,132 = pool with 0.25;
  * each is the other's gradient). gp_pool2x: (Hout, Wout) is the pooled size. gp_act_fwd: out = act(in) (F.relu :122). */
 int gp_upsample2x(const void* in, void* out, int NB, int H, int W, int C, float scale, void* stream);
@@ -263,6 +271,15 @@ int gp_bn_stats_comp(const void* x, const void* x_comp, int comp_fmt, long long 
                      void* stream);
 int gp_bn_apply_act_comp(const void* y, const void* y_comp, void* out, void* out_comp, int comp_fmt, long long P, int C,
                          const float* scale, const float* shift, int act, void* stream);
+/* backward of the same: y is read through its companion, i.e. exactly the value the forward normalised (the
+ * activation mask and xhat must not come from the bf16 rounding of y) */
+int gp_bn_bwd_reduce_comp(const void* da, const void* y, const void* y_comp, int comp_fmt, long long P, int C,
+                          const float* scale, const float* shift, const float* mean, const float* rstd, int act,
+                          float* sum_dz, float* sum_dzx, void* stream);
+int gp_bn_bwd_apply_comp(const void* da, const void* y, const void* y_comp, int comp_fmt, void* dy, long long P, int C,
+                         const float* scale, const float* shift, const float* mean, const float* rstd,
+                         const float* sum_dz, const float* sum_dzx, double count, int act, float* acc_dbeta,
+                         float* acc_dgamma, float acc_scale, void* stream);
 int gp_pair_to_f16(const void* hi, const void* lo, long long ld_in, void* out, long long ld_out, long long rows, int cols,
                    void* stream);
 int gp_bn_apply_act_pair(const float* y, void* out_bf16, void* out_f16, long long P, int C, const float* scale,
@@ -277,7 +294,8 @@ int gp_bn_bwd_reduce_f32(const void* da, const float* y, long long P, int C, con
                          const float* mean, const float* rstd, int act, float* sum_dz, float* sum_dzx, void* stream);
 int gp_bn_bwd_apply_f32(const void* da, const float* y, void* dy, long long P, int C, const float* scale,
                         const float* shift, const float* mean, const float* rstd, const float* sum_dz,
-                        const float* sum_dzx, double count, int act, void* stream);
+                        const float* sum_dzx, double count, int act, float* acc_dbeta, float* acc_dgamma,
+                        float acc_scale, void* stream);
 int gp_im2col_k4s2_split(const float* img, void* col_hi, void* col_lo, int NB, int ch, int Hi, int Wi, void* stream);
 int gp_col2im_k4s2_f32(const float* col, const float* bias, float* img, int NB, int ch, int Hi, int Wi, int act,
                        void* stream);

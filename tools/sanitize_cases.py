@@ -21,6 +21,10 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 import torch  # noqa: E402
 
+# torch references on the GPU must be true fp32 (the default lets cuDNN / cuBLAS use TF32: 10-bit operands)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 
 def gemm_cases(quick):
     import selftest_conv as st
