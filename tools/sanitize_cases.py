@@ -65,21 +65,26 @@ def mode_cases():
                           fp16_in=True, out_mode="pair")
     eh = (oh.float() - F.relu(ref + res.float())).abs().max().item() / ref.abs().max().item()
     print("bf16x3 k3s1 rel err %.2e | fp16 k3s1 + fp16 residual + relu rel err %.2e" % (e3, eh))
-    ok &= e3 < 1e-4 and eh < 3e-3 and torch.equal(ob, oh.float().bfloat16())
+    ok &= e3 < 1e-4 and eh < 3e-3
+    # the two outputs of a "pair" store are roundings of the same fp32 value
+    ok &= (ob.float() - oh.float()).abs().max().item() <= 2 ** -8 * oh.float().abs().max().item()
     # BatchNorm on an activation with a companion, pooling, blur, upsample
     st = ops.bn_stats_comp(ob, oh)
     fin = ops.bn_finalize(st, NB * H * H, None, None, None, None, None)
     a, ac = ops.bn_apply_act_comp(ob, oh, fin, ops.ACT_LRELU, ops.COMP_F16)
     want = F.leaky_relu(F.batch_norm(oh.float().permute(0, 3, 1, 2), None, None, None, None, True, 0.1, 1e-5), 0.2)
-    ok &= (ac.float().permute(0, 3, 1, 2) - want).abs().max().item() < 5e-3
+    checks = {"x3/fp16 conv": bool(ok)}
+    checks["bn apply (companion)"] = (ac.float().permute(0, 3, 1, 2) - want).abs().max().item() < 5e-3
     p, pc = ops.pool2x(a, 0.25, comp=ac, out_fmt=ops.COMP_F16)
-    ok &= (pc.float().permute(0, 3, 1, 2) - F.avg_pool2d(ac.float().permute(0, 3, 1, 2), 2)).abs().max().item() < 2e-3
+    checks["pool2x"] = (pc.float().permute(0, 3, 1, 2) - F.avg_pool2d(ac.float().permute(0, 3, 1, 2), 2)).abs().max().item() < 2e-3
     bl, blc = ops.blur3x3_fwd(a, 2, comp=ac, out_fmt=ops.COMP_F16)
-    ok &= bl.shape == (NB, H // 2, H // 2, N) and torch.isfinite(blc.float()).all().item()
+    checks["blur"] = bl.shape == (NB, H // 2, H // 2, N) and torch.isfinite(blc.float()).all().item()
     up = ops.upsample2x(ac, 1.0)
-    ok &= up.dtype == torch.float16 and torch.equal(up[:, ::2, ::2], ac)
+    checks["upsample"] = up.dtype == torch.float16 and torch.equal(up[:, ::2, ::2], ac)
     loss, dpred = ops.gan_loss(torch.randn(33, 1, device="cuda"), ops.LOSS_BCE, 0.9)
-    ok &= bool(torch.isfinite(loss).item())
+    checks["loss"] = bool(torch.isfinite(loss).item())
+    print("mode cases:", checks)
+    ok = all(checks.values())
     torch.cuda.synchronize()
     return bool(ok)
 
