@@ -89,7 +89,8 @@ struct GemmCfg {
   static constexpr int kStatBytes = 2 * kMaxStatCols * 4;
   static constexpr int kBiasBytes = 2 * 256 * 4;  // double-buffered bias slice of the current / next tile
   static constexpr int kBarBytes = 256;
-  static constexpr int kBudget = 204 * 1024;  // operand ring; + statistics + bias + barriers + alignment slack < 227 KB
+  static constexpr int kStoreStageBytes = 4 * 2048;  // epilogue store staging: 2 KB per epilogue warp (coalesced stores)
+  static constexpr int kBudget = 196 * 1024;  // operand ring; + statistics + bias + barriers + staging + slack < 227 KB
   static constexpr int kStages = kBudget / kStageBytes > 8 ? 8 : kBudget / kStageBytes;
   static constexpr int kAccCols = MT * BN;      // TMEM columns of one accumulator buffer
   // two accumulator buffers (epilogue of tile i overlaps the MMAs of tile i+1) when they fit the 512 TMEM columns;
@@ -97,7 +98,8 @@ struct GemmCfg {
   static constexpr int kAccBufs = 2 * kAccCols <= 512 ? 2 : 1;
   static constexpr int kTmemCols = kAccBufs * kAccCols;  // 128 / 256 / 512: powers of two >= 32
   static constexpr int kChunks = MT * (BN / 32);  // 32-column TMEM loads per accumulator buffer and epilogue warp
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStatBytes + kBiasBytes + kBarBytes + 1024;  // +1024: alignment slack
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kStatBytes + kBiasBytes + kBarBytes + kStoreStageBytes + 1024;  // +1024: alignment slack
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM allocation must be a power of two <= 512");
   static_assert(kStages >= (X3 ? 2 : 3), "pipeline too shallow");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
@@ -116,6 +118,40 @@ __device__ __forceinline__ void warp_transpose_sum32(float (&v)[32], int lane) {
       v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
     }
   }
+}
+
+// Coalesced epilogue stores. After tcgen05.ld every lane owns one ROW of a 32-row x 64-byte chunk; storing it directly
+// makes each 16-byte store instruction touch 32 different rows (ncu on the K=64 image-side GEMM: 16 of 32 bytes per
+// sector used, the L1/L2 store path is the limiter). Instead the warp transposes the chunk through 2 KB of shared memory:
+// lane l then stores segment (l & 3) of rows (l >> 2) + 8 i, i.e. every instruction writes 8 rows x 64 contiguous bytes
+// (full sectors). Row addresses / validity of the other lanes' rows come by shuffle.
+//   stage: this warp's 2 KB buffer (shared address); seg[4]: the lane's own row as four 16-byte vectors; base +
+//   row_byte_off: global address of the lane's own row; row_ok: that row is inside the tensor; col_lim: number of valid
+//   16-byte segments (partial last column tile).
+__device__ __forceinline__ void store_rows_coalesced(uint32_t stage, const uint4 (&seg)[4], uint8_t* __restrict__ base,
+                                                     long long row_byte_off, bool row_ok, int col_lim, int lane) {
+  // swizzle: 16-byte slot (s ^ ((row >> 1) & 3)) of a 64-byte row -> conflict-free for both the row-wise writes and the
+  // (8 rows x 4 segments) reads
+#pragma unroll
+  for (int sg = 0; sg < 4; ++sg) {
+    const uint32_t a = stage + lane * 64 + ((sg ^ ((lane >> 1) & 3)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(seg[sg].x), "r"(seg[sg].y), "r"(seg[sg].z),
+                 "r"(seg[sg].w)
+                 : "memory");
+  }
+  __syncwarp();
+  const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
+  const int sg = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane >> 2) + 8 * i;
+    const long long off = __shfl_sync(0xffffffffu, row_byte_off, r);
+    uint4 v;
+    const uint32_t a = stage + r * 64 + ((sg ^ ((r >> 1) & 3)) << 4);
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    if (((okmask >> r) & 1u) && sg < col_lim) *reinterpret_cast<uint4*>(base + off + sg * 16) = v;
+  }
+  __syncwarp();  // the buffer is rewritten by the next call
 }
 
 // One unit of work of a persistent CTA: an output tile and (WGRAD) the range of 64-pixel K blocks it accumulates.
@@ -184,6 +220,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* s_store = smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStatBytes + Cfg::kBiasBytes + Cfg::kBarBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -496,45 +533,53 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], slope * v[j]);
             }
-            if (row_ok[mi]) {
-              if (p.out_f32 != nullptr) {
-                float4* dst = reinterpret_cast<float4*>(p.out_f32 + off[mi] + col0);
+            // ---- stores, transposed through this warp's staging buffer so that each instruction writes whole sectors
+            const uint32_t stage = smem_u32(s_store) + (warp - 2) * 2048;
+            if (p.out_f32 != nullptr) {
+              uint8_t* base = reinterpret_cast<uint8_t*>(p.out_f32 + col0);
 #pragma unroll
-                for (int g = 0; g < 8; ++g)
-                  if (col0 + g * 4 < p.N) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-              } else {
-                __nv_bfloat16* orow = p.out + off[mi] + col0;
-                uint32_t w32[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                  const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-                  w32[e] = *reinterpret_cast<const uint32_t*>(&b2);
-                }
+              for (int hlf = 0; hlf < 2; ++hlf) {  // 32 fp32 columns = two 64-byte halves
+                uint4 seg[4];
 #pragma unroll
                 for (int g = 0; g < 4; ++g)
-                  if (col0 + g * 8 < p.N)
-                    *reinterpret_cast<uint4*>(orow + g * 8) = make_uint4(w32[4 * g], w32[4 * g + 1], w32[4 * g + 2], w32[4 * g + 3]);
-                if (p.out_lo != nullptr) {
-                  __nv_bfloat16* lrow = p.out_lo + off[mi] + col0;
-                  if (p.fmt_flags & kFmtLoF16) {
+                  seg[g] = make_uint4(__float_as_uint(v[hlf * 16 + 4 * g]), __float_as_uint(v[hlf * 16 + 4 * g + 1]),
+                                      __float_as_uint(v[hlf * 16 + 4 * g + 2]), __float_as_uint(v[hlf * 16 + 4 * g + 3]));
+                const int lim = (p.N - col0 - hlf * 16 + 3) / 4;  // valid 4-float segments of this half
+                store_rows_coalesced(stage, seg, base + hlf * 64, off[mi] * 4, row_ok[mi], lim, lane);
+              }
+            } else {
+              uint32_t w32[16];
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                      const __half2 h2 = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-                      w32[e] = *reinterpret_cast<const uint32_t*>(&h2);
-                    }
-                  } else {
+              for (int e = 0; e < 16; ++e) {
+                const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                w32[e] = *reinterpret_cast<const uint32_t*>(&b2);
+              }
+              const int lim = (p.N - col0 + 7) / 8;  // valid 8-element segments
+              {
+                uint4 seg[4];
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                      const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w32[e]));
-                      const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
-                      w32[e] = *reinterpret_cast<const uint32_t*>(&l2);
-                    }
+                for (int g = 0; g < 4; ++g) seg[g] = make_uint4(w32[4 * g], w32[4 * g + 1], w32[4 * g + 2], w32[4 * g + 3]);
+                store_rows_coalesced(stage, seg, reinterpret_cast<uint8_t*>(p.out + col0), off[mi] * 2, row_ok[mi], lim, lane);
+              }
+              if (p.out_lo != nullptr) {
+                if (p.fmt_flags & kFmtLoF16) {
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) {
+                    const __half2 h2 = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                    w32[e] = *reinterpret_cast<const uint32_t*>(&h2);
                   }
+                } else {
 #pragma unroll
-                  for (int g = 0; g < 4; ++g)
-                    if (col0 + g * 8 < p.N)
-                      *reinterpret_cast<uint4*>(lrow + g * 8) = make_uint4(w32[4 * g], w32[4 * g + 1], w32[4 * g + 2], w32[4 * g + 3]);
+                  for (int e = 0; e < 16; ++e) {
+                    const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w32[e]));
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+                    w32[e] = *reinterpret_cast<const uint32_t*>(&l2);
+                  }
                 }
+                uint4 seg[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) seg[g] = make_uint4(w32[4 * g], w32[4 * g + 1], w32[4 * g + 2], w32[4 * g + 3]);
+                store_rows_coalesced(stage, seg, reinterpret_cast<uint8_t*>(p.out_lo + col0), off[mi] * 2, row_ok[mi], lim, lane);
               }
             }
           }

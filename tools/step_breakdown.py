@@ -1,4 +1,4 @@
-"""Per-kernel breakdown of one eager DCGAN-64 training step on the GPU: every C-ABI call is bracketed by CUDA events
+"""Per-kernel breakdown of one eager training step of a bench.py configuration on the GPU: every C-ABI call is bracketed by CUDA events
 (ops.CallProfiler); tensor-core GEMMs are reported as algorithmic TFLOP/s per launch, HBM-bound kernels as algorithmic
 GB/s (each input read once + each output written once) against MEASURED_PEAKS.json.
 
@@ -73,36 +73,29 @@ def main():
     ap.add_argument("--precision", default=None)
     ap.add_argument("--gemms", action="store_true", help="list every GEMM launch")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--config", default="cfg2", help="bench.py configuration (cfg2 DCGAN-64, cfg3 SN-DCGAN-32, cfg4 SNGAN "
+                                                     "projection, cfg5 ACGAN-64): same nets / step driver / optimiser as the bench")
     args = ap.parse_args()
     from gan_playground_b200 import config, ops
     if args.precision:
         config.set_precision(args.precision)
-    from gan_playground_b200.criterion import GANLoss
-    from gan_playground_b200.engine import DcganStep
-    from gan_playground_b200.models import dcgan
+    import bench
 
     dev = torch.device("cuda", 0)
-    torch.manual_seed(0)
-    with contextlib.redirect_stdout(io.StringIO()):
-        netG, netD = dcgan.Generator().to(dev), dcgan.Discriminator().to(dev)
-    optG = torch.optim.Adam(netG.parameters(), lr=4e-4, betas=(0.5, 0.999))
-    optD = torch.optim.Adam(netD.parameters(), lr=1e-4, betas=(0.5, 0.999))
-    crit = GANLoss('vanilla', 0.9, 0.1, 0.9).to(dev)
-    runner = DcganStep(netG, netD, crit, optG, optD, args.batch, 100, dev, use_graph=False)
-    x = torch.rand(args.batch, 3, 64, 64, device=dev) * 2 - 1
+    runner, inputs = bench.build_config(args.config, dev, args.batch, 1, False, False)
     for _ in range(3):
-        runner.step_eager(x)
+        runner.step_eager(*inputs)
     torch.cuda.synchronize()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(5):
-        runner.step_eager(x)
+        runner.step_eager(*inputs)
     t1.record()
     torch.cuda.synchronize()
     step_ms = t0.elapsed_time(t1) / 5
     prof = ops.CallProfiler()
     with prof:
-        runner.step_eager(x)
+        runner.step_eager(*inputs)
     torch.cuda.synchronize()
 
     peaks = {"hbm_gbs": 6550.7, "bf16_tflops_sustained": 1361.6}
@@ -126,8 +119,8 @@ def main():
             ent = agg.setdefault(name, [0, 0.0, 0.0, 0.0])
             ent[0] += 1; ent[1] += ms; ent[2] += (b or 0)
     lines = []
-    lines.append("DCGAN-64 batch %d precision %s: eager step %.3f ms (5-step mean); profiled own kernels %.3f ms in %d calls"
-                 % (args.batch, config.precision(), step_ms, tot, len(prof.records)))
+    lines.append("%s batch %d precision %s: eager step %.3f ms (5-step mean); profiled own kernels %.3f ms in %d calls"
+                 % (args.config, args.batch, bench.precision_label(runner), step_ms, tot, len(prof.records)))
     lines.append("%-28s %5s %10s %7s  %s" % ("entry point", "calls", "total us", "share", "achieved (of measured peak)"))
     for k, (n, ms, by, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         if fl:
