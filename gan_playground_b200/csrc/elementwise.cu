@@ -442,6 +442,50 @@ __global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ a, const void*
   }
 }
 
+// Several outputs per sample (ACGAN's packed adversarial + auxiliary heads, models/acgan.py:122-126): ONE pass over the
+// sample's features accumulates all O <= kHeadMaxO outputs (the per-(b, o) kernel above would re-read them O times).
+constexpr int kHeadMaxO = 16;
+__global__ void __launch_bounds__(256) head_fwd_multi_kernel(const __nv_bfloat16* __restrict__ a, const void* __restrict__ a_comp,
+                                                             int fmt, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ out, int HW,
+                                                             int C, int O, long long s_o, long long s_c, long long s_hw) {
+  const int b = blockIdx.x;
+  float acc[kHeadMaxO];
+#pragma unroll
+  for (int o = 0; o < kHeadMaxO; ++o) acc[o] = 0.f;
+  const long long base = (long long)b * HW * C;
+  const int c8 = C / 8;
+  for (int i = threadIdx.x; i < HW * c8; i += blockDim.x) {
+    const int c = (i % c8) * 8, hw = i / c8;
+    float f[8];
+    load8c(a, a_comp, fmt, base + (long long)i * 8, f);
+    const float* wp = w + c * s_c + hw * s_hw;
+#pragma unroll
+    for (int o = 0; o < kHeadMaxO; ++o) {
+      if (o < O) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += f[j] * __ldg(wp + o * s_o + j * s_c);
+        acc[o] += t;
+      }
+    }
+  }
+  __shared__ float red[kHeadMaxO][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 0; o < kHeadMaxO; ++o) {
+    float v = acc[o];
+    for (int k = 16; k > 0; k >>= 1) v += __shfl_xor_sync(0xffffffffu, v, k);
+    if (lane == 0) red[o][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < O) {
+    float v = 0.f;
+    for (int k = 0; k < 8; ++k) v += red[threadIdx.x][k];
+    out[(long long)b * O + threadIdx.x] = v + (bias ? bias[threadIdx.x] : 0.f);
+  }
+}
+
 // da[b, hw, c] = sum_o dout[b][o] * w[o, c, hw]      (one thread per 8 channels)
 __global__ void head_bwd_data_kernel(const float* __restrict__ dout, const float* __restrict__ w,
                                      __nv_bfloat16* __restrict__ da, int NB, int HW, int C, int O, long long s_o,
@@ -582,6 +626,62 @@ __global__ void __launch_bounds__(256) head_bwd_weight_pool_kernel(const float* 
     for (int w = 0; w < 8; ++w) v += s_acc[w][i];
     const int cc = blockIdx.x * 256 + i;
     if (cc < C) atomicAdd(dw + o * s_o + cc * s_c, v);
+  }
+}
+
+// The same for O <= kHeadMaxO outputs at once: the pooled features sum_hw a[b, hw, c] do not depend on o, so one pass
+// over `a` serves every output (grid: channel blocks x batch chunks).
+__global__ void __launch_bounds__(256) head_bwd_weight_pool_multi_kernel(const float* __restrict__ dout,
+                                                                         const __nv_bfloat16* __restrict__ a,
+                                                                         float* __restrict__ dw, int NB, int HW, int C, int O,
+                                                                         long long s_o, long long s_c) {
+  __shared__ float s_acc[8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = (blockIdx.x * 32 + lane) * 8;
+  const int bchunk = (NB + gridDim.y - 1) / gridDim.y;
+  const int b0 = blockIdx.y * bchunk, b1 = min(b0 + bchunk, NB);
+  float acc[kHeadMaxO][8];
+#pragma unroll
+  for (int o = 0; o < kHeadMaxO; ++o)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[o][j] = 0.f;
+  if (c < C) {
+    for (int b = b0 + warp; b < b1; b += 8) {
+      const __nv_bfloat16* ap = a + (long long)b * HW * C + c;
+      float t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = 0.f;
+      for (int hw = 0; hw < HW; ++hw) {
+        Vec8<__nv_bfloat16> v;
+        v.load(ap + (long long)hw * C);
+        float f[8];
+        v.unpack(f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] += f[j];
+      }
+#pragma unroll
+      for (int o = 0; o < kHeadMaxO; ++o) {
+        if (o < O) {
+          const float d = __ldg(dout + (long long)b * O + o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[o][j] += d * t[j];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < kHeadMaxO; ++o) {
+    if (o < O) {   // uniform across the block
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_acc[warp][lane * 8 + j] = acc[o][j];
+      __syncthreads();
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) v += s_acc[w][threadIdx.x];
+      const int cc = blockIdx.x * 256 + threadIdx.x;
+      if (cc < C) atomicAdd(dw + o * s_o + cc * s_c, v);
+      __syncthreads();
+    }
   }
 }
 
@@ -931,6 +1031,12 @@ int gp_image_bias_grad(const float* dout, const float* mul, float* dbias, int NB
 int gp_head_fwd(const void* a, const float* w, const float* bias, float* out, int NB, int HW, int C, int O,
                 long long s_o, long long s_c, long long s_hw, void* stream) {
   GP_REQUIRE(a && w && out && NB > 0 && HW > 0 && C > 0 && C % 8 == 0 && O > 0, "gp_head_fwd: bad arguments");
+  if (O > 1 && O <= kHeadMaxO) {
+    head_fwd_multi_kernel<<<NB, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(a), nullptr, GP_COMP_NONE, w, bias,
+                                                             out, HW, C, O, s_o, s_c, s_hw);
+    GP_CHECK_LAUNCH();
+    return GP_OK;
+  }
   dim3 grid(NB, O);
   head_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(a), nullptr, GP_COMP_NONE, w, bias,
                                                        out, HW, C, O, s_o, s_c, s_hw);
@@ -952,6 +1058,12 @@ int gp_head_fwd_comp(const void* a, const void* a_comp, int comp_fmt, const floa
                      int HW, int C, int O, long long s_o, long long s_c, long long s_hw, void* stream) {
   GP_REQUIRE(a && w && out && NB > 0 && HW > 0 && C > 0 && C % 8 == 0 && O > 0, "gp_head_fwd_comp: bad arguments");
   GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_head_fwd_comp: unknown companion format %d", comp_fmt);
+  if (O > 1 && O <= kHeadMaxO) {   // several heads packed: read the features once for all of them
+    head_fwd_multi_kernel<<<NB, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(a), a_comp, comp_fmt, w, bias, out,
+                                                             HW, C, O, s_o, s_c, s_hw);
+    GP_CHECK_LAUNCH();
+    return GP_OK;
+  }
   dim3 grid(NB, O);
   head_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(a), a_comp, comp_fmt, w, bias, out,
                                                        HW, C, O, s_o, s_c, s_hw);
@@ -967,7 +1079,19 @@ int gp_head_bwd(const float* dout, const void* a, const float* w, void* da, floa
         dout, w, static_cast<__nv_bfloat16*>(da), NB, HW, C, O, s_o, s_c, s_hw);
     GP_CHECK_LAUNCH();
   }
-  if (dw != nullptr && s_hw == 0) {
+  if (dw != nullptr && s_hw == 0 && O > 1 && O <= kHeadMaxO) {
+    const int gx = (C + 255) / 256;
+    int zsplit = (2 * num_sms()) / gx;
+    if (zsplit < 1) zsplit = 1;
+    if (zsplit > (NB + 7) / 8) zsplit = (NB + 7) / 8;
+    head_bwd_weight_pool_multi_kernel<<<dim3(gx, zsplit), 256, 0, as_stream(stream)>>>(
+        dout, static_cast<const __nv_bfloat16*>(a), dw, NB, HW, C, O, s_o, s_c);
+    GP_CHECK_LAUNCH();
+    if (dbias != nullptr) {
+      head_bias_grad_kernel<<<O, 256, 0, as_stream(stream)>>>(dout, dbias, NB, O);
+      GP_CHECK_LAUNCH();
+    }
+  } else if (dw != nullptr && s_hw == 0) {
     const int gx = (C + 255) / 256;
     int zsplit = (4 * num_sms()) / (gx * O);
     if (zsplit < 1) zsplit = 1;
