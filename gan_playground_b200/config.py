@@ -61,6 +61,27 @@ class precision_scope:
         _precision = self.prev
 
 
+# Pre-BatchNorm storage of the single-MMA "fp16" mode: "f32" (4 bytes, default) or "f16" (2 bytes; the statistics still come
+# from the fp32 accumulators). Measured on the B200 (DCGAN-64, batch 1024, D-fake chain in fp16): the 2-byte storage keeps
+# the north_star bars (D-fake cosine 0.99968 at batch 64 / 0.99996 at 1024 vs 0.99973 / 0.99996) but does NOT pay: 16.57
+# vs 16.40 ms per step — the fp32-input BatchNorm kernels are the tuned ones, and the GEMM epilogue is not the limiter
+# there. Kept as an option (GP_FP16_PREBN=f16).
+_fp16_prebn = os.environ.get("GP_FP16_PREBN", "f32")
+if _fp16_prebn not in ("f16", "f32"):
+    raise ValueError("GP_FP16_PREBN must be f16 or f32")
+
+
+def fp16_prebn():
+    return _fp16_prebn
+
+
+def set_fp16_prebn(v):
+    global _fp16_prebn
+    if v not in ("f16", "f32"):
+        raise ValueError("fp16 pre-BatchNorm storage must be f16 or f32")
+    _fp16_prebn = v
+
+
 def resnet_scope():
     """The scope the ResNet (models/sngan_projection.py) and blur (models/dcgan_blur.py) mirrors run their forward in:
     those nodes implement "bf16" and "fp16"; the global default "bf16x3" maps to "fp16" — one MMA on 11-bit operands

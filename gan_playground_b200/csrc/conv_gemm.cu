@@ -297,12 +297,15 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
   prm.act_slope = a->act == GP_ACT_RELU ? 0.f : (a->act == GP_ACT_LRELU ? 0.2f : 1.f);
   prm.col_sum = a->col_sum;
   prm.col_sumsq = a->col_sumsq;
-  GP_REQUIRE((a->flags & ~(GP_CONV_IN_F16 | GP_CONV_LO_F16 | GP_CONV_RES_F16)) == 0, "gp_conv_fwd: unknown flags 0x%x", a->flags);
+  GP_REQUIRE((a->flags & ~(GP_CONV_IN_F16 | GP_CONV_LO_F16 | GP_CONV_RES_F16 | GP_CONV_OUT_F16)) == 0,
+             "gp_conv_fwd: unknown flags 0x%x", a->flags);
+  GP_REQUIRE(!(a->flags & GP_CONV_OUT_F16) || (a->out != nullptr && a->out_lo == nullptr && a->out_f32 == nullptr),
+             "gp_conv_fwd: GP_CONV_OUT_F16 writes a single fp16 tensor to `out`");
   GP_REQUIRE(!(a->flags & GP_CONV_RES_F16) || a->residual != nullptr, "gp_conv_fwd: GP_CONV_RES_F16 needs a residual");
   GP_REQUIRE(!(a->flags & GP_CONV_IN_F16) || a->in_lo == nullptr, "gp_conv_fwd: fp16 operands run as one MMA (in_lo must be NULL)");
   GP_REQUIRE(!(a->flags & GP_CONV_LO_F16) || (a->out_lo != nullptr && a->out != nullptr), "gp_conv_fwd: GP_CONV_LO_F16 needs out and out_lo");
   prm.fmt_flags = ((a->flags & GP_CONV_IN_F16) ? kFmtInF16 : 0) | ((a->flags & GP_CONV_LO_F16) ? kFmtLoF16 : 0) |
-                  ((a->flags & GP_CONV_RES_F16) ? kFmtResF16 : 0);
+                  ((a->flags & GP_CONV_RES_F16) ? kFmtResF16 : 0) | ((a->flags & GP_CONV_OUT_F16) ? kFmtOutF16 : 0);
   GP_REQUIRE((a->col_sum == nullptr) == (a->col_sumsq == nullptr), "gp_conv_fwd: col_sum and col_sumsq go together");
   const int mtiles = ((a->NB + prm.Nt - 1) / prm.Nt) * (prm.Hs / prm.Ht) * (prm.Ws / prm.Wt);
   const int ntn = (a->Nout + bn - 1) / bn;

@@ -77,6 +77,7 @@ struct alignas(64) ConvGemmParams {
 };
 constexpr int kFmtInF16 = 1, kFmtLoF16 = 2;
 constexpr int kFmtResF16 = 4;  // FWD: `residual` holds fp16 (the companion of the shortcut activation in the fp16 mode)
+constexpr int kFmtOutF16 = 8;  // FWD: `out` receives fp16(v) instead of bf16(v) (pre-BatchNorm output of the fp16 mode)
 
 // X3 = bf16x3 forward (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo): one pipeline stage holds the hi AND lo tiles of both
 // operands — 4 tile loads feed 3 MMA blocks, i.e. 1/3 fewer operand bytes from L2 per MMA than issuing the three
@@ -549,10 +550,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               }
             } else {
               uint32_t w32[16];
+              if (p.fmt_flags & kFmtOutF16) {
 #pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-                w32[e] = *reinterpret_cast<const uint32_t*>(&b2);
+                for (int e = 0; e < 16; ++e) {
+                  const __half2 h2 = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                  w32[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                  const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                  w32[e] = *reinterpret_cast<const uint32_t*>(&b2);
+                }
               }
               const int lim = (p.N - col0 + 7) / 8;  // valid 8-element segments
               {

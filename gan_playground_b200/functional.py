@@ -72,6 +72,8 @@ def _bn_forward(y, gamma, beta, bufs, act, training=True, st=None, pair=False, c
     count = (y.numel() // C) * parallel.world_size()
     rm, rv, nbt = bufs if bufs is not None else (None, None, None)
     f32 = y.dtype == torch.float32
+    if y.dtype == torch.float16:          # 2-byte pre-BN storage of the fp16 mode: the tensor is its own fp16 companion;
+        comp, out_fmt = y, ops.COMP_F16   # the activation leaves as a (bf16, fp16) pair (heads read the fp16 copy too)
     if training or rm is None:
         if st is None:
             st = ops.bn_stats_f32(y) if f32 else (ops.bn_stats_comp(y, comp) if comp is not None else ops.bn_stats(y))
@@ -99,6 +101,8 @@ def _bn_backward(da, y, fin, count, act, training=True, need_affine=True, comp=N
     parameters that own such a buffer, ops.grad_target). comp: companion tensor of y — the backward must see the value
     the forward normalised, not its bf16 rounding (activation mask, xhat)."""
     f32 = y.dtype == torch.float32
+    if y.dtype == torch.float16:          # 2-byte pre-BN storage of the fp16 mode (its own companion)
+        comp = y
     if f32:
         red = ops.bn_bwd_reduce_f32(da, y, fin, act)
     elif comp is not None:
@@ -194,8 +198,10 @@ class ConvBlock(torch.autograd.Function):
             # one MMA on fp16 operands; the output pair is (bf16, fp16) — or a (hi, lo) bf16 pair when the head, which is
             # not a GEMM, consumes it
             wp = cache.get((key, "fwdh"), weight, lambda: ops.conv_weight_f16(weight.detach(), n_dim))
+            # pre-BatchNorm output: 2-byte fp16 storage when the statistics come from the epilogue (fp32 accumulators)
+            prebn = "f16" if (st is not None and config.fp16_prebn() == "f16") else "f32"
             y = ops.conv_fwd(_f16_operand(x, x_lo), wp, b, kind, Ho, Wo, ops.ACT_NONE if has_bn else act, stats=st,
-                             fp16_in=True, out_mode="f32" if has_bn else ("split" if feeds_head else "pair"))
+                             fp16_in=True, out_mode=prebn if has_bn else ("split" if feeds_head else "pair"))
         else:
             wp = cache.get((key, "fwd"), weight, lambda: ops.pack_conv_weight(weight.detach(), n_dim))
             y = ops.conv_fwd(x, wp, b, kind, Ho, Wo, ops.ACT_NONE if has_bn else act, stats=st)

@@ -196,7 +196,7 @@ def _timed(name, flops, fn):
 _TAPS_PER_OUT = {KIND_CONV_K4S2: 16, KIND_CONVT_K4S2: 4, KIND_CONV_K3S1: 9, KIND_CONV_K1S1: 1}
 
 
-CONV_IN_F16, CONV_LO_F16, CONV_RES_F16 = 1, 2, 4
+CONV_IN_F16, CONV_LO_F16, CONV_RES_F16, CONV_OUT_F16 = 1, 2, 4, 8
 
 
 def conv_fwd(x, wp, bias, kind, Hout, Wout, act=ACT_NONE, stats=None, flops=None, residual=None, x_lo=None,
@@ -207,7 +207,8 @@ def conv_fwd(x, wp, bias, kind, Hout, Wout, act=ACT_NONE, stats=None, flops=None
     bf16x3 mode: x_lo = low halves of x and wp = [Nout, 2*taps*Cin] (hi | lo).
     fp16 mode: fp16_in=True, x and wp are fp16 (one MMA; same layouts as the bf16 operands, x_lo must be None).
     out_mode: "bf16" -> bf16 tensor; "split" -> (hi, lo) bf16 pair; "f32" -> fp32 tensor; "pair" -> (bf16, fp16) copies
-    of the same value (backward operand, next forward operand of the fp16 mode)."""
+    of the same value (backward operand, next forward operand of the fp16 mode); "f16" -> one fp16 tensor (2-byte
+    pre-BatchNorm storage of the fp16 mode)."""
     op_dtype = torch.float16 if fp16_in else torch.bfloat16
     _chk(x, op_dtype, "x")
     _chk(wp, op_dtype, "wp")
@@ -220,12 +221,13 @@ def conv_fwd(x, wp, bias, kind, Hout, Wout, act=ACT_NONE, stats=None, flops=None
     if out_mode == "f32":
         out_f32 = torch.empty(shape, device=x.device, dtype=torch.float32)
     else:
-        out = torch.empty(shape, device=x.device, dtype=torch.bfloat16)
+        out = torch.empty(shape, device=x.device, dtype=torch.float16 if out_mode == "f16" else torch.bfloat16)
         if out_mode == "split":
             out_lo = torch.empty(shape, device=x.device, dtype=torch.bfloat16)
         elif out_mode == "pair":
             out_lo = torch.empty(shape, device=x.device, dtype=torch.float16)
-    flags = (CONV_IN_F16 if fp16_in else 0) | (CONV_LO_F16 if out_mode == "pair" else 0)
+    flags = (CONV_IN_F16 if fp16_in else 0) | (CONV_LO_F16 if out_mode == "pair" else 0) | \
+        (CONV_OUT_F16 if out_mode == "f16" else 0)
     if residual is not None and residual.dtype == torch.float16:   # the fp16 companion of the shortcut activation
         flags |= CONV_RES_F16
     if bias is not None:
@@ -788,6 +790,8 @@ def bn_bwd_apply_f32(da, y, fin, red, count, act, acc=None, acc_scale=1.0):
 def bn_bwd_reduce_comp(da, y, comp, fin, act):
     """bn_bwd_reduce with y read through its companion tensor (the value the forward normalised)."""
     _chk(da, torch.bfloat16, "da")
+    if y.dtype == torch.float16:
+        y, comp = _as_hi(y)
     _chk(y, torch.bfloat16, "y")
     C = y.shape[-1]
     red = zeros((2, C), y.device)
@@ -797,6 +801,8 @@ def bn_bwd_reduce_comp(da, y, comp, fin, act):
 
 
 def bn_bwd_apply_comp(da, y, comp, fin, red, count, act, acc=None, acc_scale=1.0):
+    if y.dtype == torch.float16:
+        y, comp = _as_hi(y)
     C = y.shape[-1]
     dy = torch.empty_like(y)
     check(_fn("gp_bn_bwd_apply_comp")(_p(da), _p(y), _p(comp), comp_fmt_of(comp), _p(dy), y.numel() // C, C, _p(fin[2]),
@@ -816,8 +822,17 @@ def bn_stats_comp(x, comp):
     return st
 
 
+def _as_hi(y):
+    """A pure-fp16 tensor (2-byte pre-BatchNorm storage of the fp16 mode) handed to a companion-format kernel: it is its
+    own fp16 companion; the bf16 slot gets the same storage and is never read (act_io.cuh: GP_COMP_F16 reads the
+    companion only)."""
+    return (y.view(torch.bfloat16), y) if y.dtype == torch.float16 else (y, None)
+
+
 def bn_apply_act_comp(y, comp, fin, act, out_fmt):
     """act(y * scale + shift) of an activation with a companion; returns (out, out_comp)."""
+    if y.dtype == torch.float16:
+        y, comp = _as_hi(y)
     _chk(y, torch.bfloat16, "y")
     C = y.shape[-1]
     out = torch.empty_like(y)

@@ -84,6 +84,7 @@ typedef struct {
 #define GP_CONV_IN_F16 1
 #define GP_CONV_LO_F16 2
 #define GP_CONV_RES_F16 4 /* `residual` holds fp16: the companion of the shortcut activation in the "fp16" mode */
+#define GP_CONV_OUT_F16 8 /* `out` receives fp16(v) instead of bf16(v): 2-byte pre-BatchNorm storage of the "fp16" mode */
 int gp_conv_fwd(const gp_conv_fwd_t* p, void* stream);
 /* Host-only: the tile shape gp_conv_fwd would use for this problem (BN in {64,128,256} output columns, MT in {1,2}
  * 128-row sub-tiles) and the resulting number of output tiles. No pointers are dereferenced, nothing is launched. */
