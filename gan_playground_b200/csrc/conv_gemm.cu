@@ -119,6 +119,43 @@ static int launch(const ConvGemmParams& prm, int bn, int mt, int grid, cudaStrea
   return mt == 2 ? launch_cfg<MODE, 64, 2>(prm, grid, st) : launch_cfg<MODE, 64, 1>(prm, grid, st);
 }
 
+// CTA-pair forward (tcgen05 cta_group::2): 2 x (128 x 256) tile per cluster of two CTAs (conv_gemm.cuh, GemmCfg C2)
+template <int BNV, bool X3V>
+static int launch_fwd_pair(const ConvGemmParams& prm, int pair_tiles, cudaStream_t st) {
+  auto kfn = conv_gemm_kernel<MODE_FWD, BNV, 1, X3V, true>;
+  using Cfg = GemmCfg<BNV, 1, X3V, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GP_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  int pairs = num_sms() / 2;
+  if (pair_tiles < pairs) pairs = pair_tiles;
+  if (pairs <= 0) return GP_OK;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs, 1, 1);
+  cfg.blockDim = dim3(kNumThreads, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, prm));
+  gp::count_launch();
+  return GP_OK;
+}
+
+// GP_FWD_2CTA=0 disables the CTA-pair variant (1 = on, the default once a layer has enough 128-row tiles)
+static bool pair_enabled() {
+  const char* e = getenv("GP_FWD_2CTA");
+  return e == nullptr || e[0] != '0';
+}
+
 // bf16x3 forward: hi and lo tiles of both operands per stage (no 256x256 variant: its stage would be 128 KB)
 static int launch_fwd_x3(const ConvGemmParams& prm, int bn, int mt, int grid, cudaStream_t st) {
   if (grid <= 0) return GP_OK;
@@ -179,6 +216,23 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
   int rc;
   int bn = 0, mt_sub = 1;
   choose_fwd_tile(a, &bn, &mt_sub);
+  // CTA pair (cta_group::2): for 256-wide column tiles with at least one full wave of pair tiles. Each CTA of the pair
+  // works on its own 128-pixel tile, so the pixel tiling below is the MT = 1 one.
+  bool use_pair = false;
+  long long pair_tiles = 0;
+  // (128-wide column tiles gain nothing from pairing — a lone CTA's 256 x 128 tile already moves the same bytes per FLOP;
+  // measured: G block-2 fprop 333 us paired vs 255 us — so only 256-wide tiles are paired; GP_FWD_2CTA=128 forces them)
+  const char* pe = getenv("GP_FWD_2CTA");
+  const bool pair128 = pe != nullptr && pe[0] == '1' && pe[1] == '2';
+  if ((bn == 256 || (bn == 128 && pair128)) && pair_enabled() && a->Nout % bn == 0) {
+    const int Hs = a->kind == GP_KIND_CONV_K4S2 ? a->Hout : a->Hin, Ws = a->kind == GP_KIND_CONV_K4S2 ? a->Wout : a->Win;
+    int Nt1, Ht1, Wt1;
+    factor_tile(kBlockM, Hs, Ws, &Nt1, &Ht1, &Wt1);
+    const long long m128 = (long long)((a->NB + Nt1 - 1) / Nt1) * (Hs / Ht1) * (Ws / Wt1);
+    pair_tiles = (a->kind == GP_KIND_CONVT_K4S2 ? 4 : 1) * ((m128 + 1) / 2) * (a->Nout / bn);
+    use_pair = pair_tiles >= num_sms() / 2;
+    if (use_pair) mt_sub = 1;
+  }
   const int tile_px = mt_sub * kBlockM;
   const int n_halves = a->in_lo != nullptr ? 2 : 1;  // bf16x3: hi and lo halves of the activation operand
   const long long inW = Cin, inH = (long long)a->Win * Cin, inN = (long long)a->Hin * a->Win * Cin;
@@ -283,7 +337,7 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
     // half [ktot, 2*ktot) of each packed row; the kernel loads hi and lo tiles of both operands into one stage
     prm.lo_koff = (int)ktot;
   }
-  rc = make_map_2d(&prm.map_w, a->w, n_halves * ktot, a->Nout, bn);
+  rc = make_map_2d(&prm.map_w, a->w, n_halves * ktot, a->Nout, use_pair ? bn / 2 : bn);  // a pair CTA loads half the columns
   if (rc) return rc;
   prm.map_d = prm.map_g[0];
   prm.NB = a->NB;
@@ -311,6 +365,13 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
   const int ntn = (a->Nout + bn - 1) / bn;
   const int num_tiles = prm.n_phases * mtiles * ntn;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  if (use_pair) {
+    if (bn == 256)
+      return n_halves == 2 ? launch_fwd_pair<256, true>(prm, (int)pair_tiles, as_stream(stream))
+                           : launch_fwd_pair<256, false>(prm, (int)pair_tiles, as_stream(stream));
+    return n_halves == 2 ? launch_fwd_pair<128, true>(prm, (int)pair_tiles, as_stream(stream))
+                         : launch_fwd_pair<128, false>(prm, (int)pair_tiles, as_stream(stream));
+  }
   if (n_halves == 2) return launch_fwd_x3(prm, bn, mt_sub, grid, as_stream(stream));
   return launch<MODE_FWD>(prm, bn, mt_sub, grid, as_stream(stream));
 }

@@ -82,10 +82,14 @@ constexpr int kFmtOutF16 = 8;  // FWD: `out` receives fp16(v) instead of bf16(v)
 // X3 = bf16x3 forward (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo): one pipeline stage holds the hi AND lo tiles of both
 // operands — 4 tile loads feed 3 MMA blocks, i.e. 1/3 fewer operand bytes from L2 per MMA than issuing the three
 // products as separate K steps (the 128x256 mainloop is bound by L2->SM traffic, not by the tensor pipe).
-template <int BN, int MT, bool X3 = false>
+// C2 = CTA pair (tcgen05 cta_group::2, cluster of two CTAs): one MMA of M = 256 per K step; each CTA stages its own 128
+// rows of A and HALF of the B tile, so per FLOP it moves 1.5x fewer operand bytes into shared memory than a lone 128 x 256
+// CTA (what bounds that mainloop) and, unlike the single-CTA 256 x 256 tile, keeps two accumulator buffers.
+template <int BN, int MT, bool X3 = false, bool C2 = false>
 struct GemmCfg {
+  static_assert(!C2 || ((BN == 256 || BN == 128) && MT == 1), "the CTA-pair variants are the 2 x (128 x {128, 256}) tiles");
   static constexpr int kABytes = MT * kBlockM * kBlockK * 2;   // one A tile (hi or lo)
-  static constexpr int kBBytes = BN * kBlockK * 2;             // one B tile (hi or lo)
+  static constexpr int kBBytes = (C2 ? BN / 2 : BN) * kBlockK * 2;  // one B tile (hi or lo); a pair CTA holds half of it
   static constexpr int kStageBytes = (X3 ? 2 : 1) * (kABytes + kBBytes);
   static constexpr int kStatBytes = 2 * kMaxStatCols * 4;
   static constexpr int kBiasBytes = 2 * 256 * 4;  // double-buffered bias slice of the current / next tile
@@ -173,12 +177,14 @@ struct WorkPlan {
   int nfull, rem_tiles, base_tiles, per, kblocks_total;
   int num_tiles;
 
+  int first, stride;  // FWD: first tile of this CTA (pair) and distance to its next one
+
   template <int MODE>
   __device__ __forceinline__ WorkItem item(int it) const {
     WorkItem w;
     const int G = gridDim.x;
     if constexpr (MODE == MODE_FWD) {
-      w.tile = blockIdx.x + it * G;
+      w.tile = first + it * stride;
       w.kb0 = 0;
       w.kb1 = 1;
     } else {
@@ -207,10 +213,12 @@ struct WorkPlan {
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int MODE, int BN, int MT, bool X3 = false>
+template <int MODE, int BN, int MT, bool X3 = false, bool C2 = false>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   static_assert(!(X3 && MODE == MODE_WGRAD), "bf16x3 applies to the forward GEMMs only");
-  using Cfg = GemmCfg<BN, MT, X3>;
+  static_assert(!(C2 && MODE == MODE_WGRAD), "CTA pairs are used by the forward GEMMs only");
+  using Cfg = GemmCfg<BN, MT, X3, C2>;
+  const uint32_t pair_rank = C2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs), 1 = peer
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -236,13 +244,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], C2 ? 256 : 128);  // pair: the epilogue threads of BOTH CTAs release the leader's buffer
     }
     fence_mbar_init();
   }
+  if constexpr (C2) cluster_sync_all();  // the peer's barriers exist before anything can arrive on them
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (C2) {
+      tmem_alloc_2cta(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   if (do_stats) {
     for (int i = threadIdx.x; i < 2 * p.N; i += blockDim.x) s_stat[i] = 0.f;
@@ -262,10 +276,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   WorkPlan plan;
   if constexpr (MODE == MODE_FWD) {
     mtiles = ((p.NB + p.Nt - 1) / p.Nt) * htiles * wtiles;
+    if constexpr (C2) mtiles = (mtiles + 1) / 2;  // pair tiles: CTA r of the pair owns 128-pixel tile 2 * mt + r
     cchunks = (p.C + kBlockK - 1) / kBlockK;
     ksteps_fwd = p.taps_per_phase * cchunks;
     plan.num_tiles = p.n_phases * mtiles * ntiles_n;
-    plan.num_items = plan.num_tiles > (int)blockIdx.x ? (plan.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    plan.first = C2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    plan.stride = C2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    plan.num_items = plan.num_tiles > plan.first ? (plan.num_tiles - plan.first + plan.stride - 1) / plan.stride : 0;
   } else {
     mtiles = (p.M + MT * kBlockM - 1) / (MT * kBlockM);
     plan.base_tiles = mtiles * tap_slots * ntiles_n;
@@ -286,16 +303,33 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       const int tile = wk.tile;
       if constexpr (MODE == MODE_FWD) {
         const int nt = tile % ntiles_n;
-        const int mt = (tile / ntiles_n) % mtiles;
+        const int mt = C2 ? 2 * ((tile / ntiles_n) % mtiles) + (int)pair_rank : (tile / ntiles_n) % mtiles;
         const int ph = tile / (ntiles_n * mtiles);
         const int w0 = (mt % wtiles) * p.Wt;
         const int h0 = ((mt / wtiles) % htiles) * p.Ht;
-        const int n0 = (mt / (wtiles * htiles)) * p.Nt;
+        const int n0 = (mt / (wtiles * htiles)) * p.Nt;  // a pair tile past the end (odd tile count): all out of bounds
         for (int ks = 0; ks < ksteps_fwd; ++ks) {
           const Tap t = p.taps[ph * p.taps_per_phase + ks / cchunks];
           const int c0 = (ks % cchunks) * kBlockK;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          if constexpr (C2) {
+            // both CTAs' bytes are counted on the leader's barrier, which the leader arms for the pair; this CTA loads
+            // its own rows of A and its half of the B columns
+            if (pair_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            const int brow = nt * BN + (int)pair_rank * (BN / 2);
+            if constexpr (X3) {
+              tma_load_4d_2cta(sa, &p.map_g[t.map], &full_bar[stage], c0, w0 + t.dw, h0 + t.dh, n0);
+              tma_load_4d_2cta(sa + Cfg::kABytes, &p.map_g[t.map + 4], &full_bar[stage], c0, w0 + t.dw, h0 + t.dh, n0);
+              tma_load_2d_2cta(sa + 2 * Cfg::kABytes, &p.map_w, &full_bar[stage], t.koff + c0, brow);
+              tma_load_2d_2cta(sa + 2 * Cfg::kABytes + Cfg::kBBytes, &p.map_w, &full_bar[stage], p.lo_koff + t.koff + c0, brow);
+            } else {
+              tma_load_4d_2cta(sa, &p.map_g[t.map], &full_bar[stage], c0, w0 + t.dw, h0 + t.dh, n0);
+              tma_load_2d_2cta(sa + Cfg::kABytes, &p.map_w, &full_bar[stage], t.koff + c0, brow);
+            }
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           if constexpr (X3) {  // stage = [A_hi | A_lo | B_hi | B_lo]; the lo activation maps are map_g[4..7]
             tma_load_4d(sa, &p.map_g[t.map], &full_bar[stage], c0, w0 + t.dw, h0 + t.dh, n0);
@@ -346,10 +380,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // =========================== MMA issuer (one thread) ===========================
+  } else if (warp == 1 && lane == 0 && pair_rank == 0) {
+    // =========================== MMA issuer (one thread; in a CTA pair: of the leader) ===========================
     // a_format / b_format (bits [7,10) / [10,13)): 1 = BF16, 0 = F16
-    const uint32_t idesc = make_idesc_bf16(kBlockM, BN, MODE == MODE_WGRAD, MODE == MODE_WGRAD) &
+    const uint32_t idesc = make_idesc_bf16(C2 ? 2 * kBlockM : kBlockM, BN, MODE == MODE_WGRAD, MODE == MODE_WGRAD) &
                            ~((MODE == MODE_FWD && (p.fmt_flags & kFmtInF16)) ? ((1u << 7) | (1u << 10)) : 0u);
     // K-major: SBO = 8 rows * 128 B. MN-major: SBO = 8 K-rows * 128 B, LBO = 64 K-rows * 128 B (next 64-channel chunk).
     constexpr uint64_t dbase = (MODE == MODE_FWD) ? make_smem_desc_base(0, 1024) : make_smem_desc_base(8192, 1024);
@@ -381,9 +415,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             for (int mi = 0; mi < MT; ++mi) {
               const uint64_t ah = smem_desc(dbase, a_addr + mi * a_sub + k * kadv);
               const uint64_t al = smem_desc(dbase, a_lo + mi * a_sub + k * kadv);
-              umma_bf16(d_tmem + mi * BN, ah, bh, idesc, (ks | k) != 0);  // x_hi * w_hi
-              umma_bf16(d_tmem + mi * BN, al, bh, idesc, 1u);             // x_lo * w_hi
-              umma_bf16(d_tmem + mi * BN, ah, bl, idesc, 1u);             // x_hi * w_lo
+              if constexpr (C2) {
+                umma_bf16_2cta(d_tmem, ah, bh, idesc, (ks | k) != 0);
+                umma_bf16_2cta(d_tmem, al, bh, idesc, 1u);
+                umma_bf16_2cta(d_tmem, ah, bl, idesc, 1u);
+              } else {
+                umma_bf16(d_tmem + mi * BN, ah, bh, idesc, (ks | k) != 0);  // x_hi * w_hi
+                umma_bf16(d_tmem + mi * BN, al, bh, idesc, 1u);             // x_lo * w_hi
+                umma_bf16(d_tmem + mi * BN, ah, bl, idesc, 1u);             // x_hi * w_lo
+              }
             }
           }
         } else {
@@ -392,14 +432,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             const uint64_t bdesc = smem_desc(dbase, b_addr + k * kadv);
 #pragma unroll
-            for (int mi = 0; mi < MT; ++mi)
-              umma_bf16(d_tmem + mi * BN, smem_desc(dbase, a_addr + mi * a_sub + k * kadv), bdesc, idesc, (ks | k) != 0);
+            for (int mi = 0; mi < MT; ++mi) {
+              if constexpr (C2)
+                umma_bf16_2cta(d_tmem, smem_desc(dbase, a_addr + k * kadv), bdesc, idesc, (ks | k) != 0);
+              else
+                umma_bf16(d_tmem + mi * BN, smem_desc(dbase, a_addr + mi * a_sub + k * kadv), bdesc, idesc, (ks | k) != 0);
+            }
           }
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+        // frees the smem slot (pair: in both CTAs) once these MMAs retire
+        if constexpr (C2) umma_commit_2cta(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&tfull_bar[acc]);  // accumulator ready for the epilogue
+      // accumulator ready for the epilogue (pair: of both CTAs)
+      if constexpr (C2) umma_commit_2cta(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
     }
   } else if (warp >= 2) {
     // =========================== epilogue (4 warps, one TMEM lane quarter each) ===========================
@@ -425,7 +471,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     };
     if (has_bias && plan.num_items > 0) {
       float b0[kBiasPerThread];
-      fetch_bias(blockIdx.x, b0);
+      fetch_bias(plan.first, b0);
       put_bias(0, b0);
       epi_bar_sync();
     }
@@ -439,7 +485,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       ++na;
       float bnext[kBiasPerThread];
       const bool more = it + 1 < plan.num_items;
-      if (has_bias && more) fetch_bias(tile + gridDim.x, bnext);
+      if (has_bias && more) fetch_bias(tile + plan.stride, bnext);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t tbase = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(q * 32) << 16);
@@ -450,7 +496,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       tmem_ld_32x32(tbase, r);
       if constexpr (MODE == MODE_FWD) {
         const int nt = tile % ntiles_n;
-        const int mt = (tile / ntiles_n) % mtiles;
+        const int mt = C2 ? 2 * ((tile / ntiles_n) % mtiles) + (int)pair_rank : (tile / ntiles_n) % mtiles;
         const int ph = tile / (ntiles_n * mtiles);
         const int w_t0 = (mt % wtiles) * p.Wt, h_t0 = ((mt / wtiles) % htiles) * p.Ht;
         const int n_t0 = (mt / (wtiles * htiles)) * p.Nt;
@@ -624,7 +670,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       }
       if (has_bias && more) put_bias((it + 1) & 1, bnext);
       tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
+      if constexpr (C2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]);
       if (has_bias) epi_bar_sync();
     }
   }
@@ -637,9 +683,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       atomicAdd(p.col_sumsq + i, s_stat[p.N + i]);
     }
   }
+  if constexpr (C2) cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the other can still signal it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (C2) tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
