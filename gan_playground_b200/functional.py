@@ -561,3 +561,40 @@ class SpectralNormFn(torch.autograd.Function):
     def backward(ctx, g):
         w_sn, u, v, sigma = ctx.saved_tensors
         return ops.sn_grad(g.contiguous(), w_sn, ctx.dim, u, v, sigma), None, None, None, None
+
+
+class SpectralNormAllFn(torch.autograd.Function):
+    """SpectralNormFn for EVERY spectral-normed weight a forward uses, in five launches instead of ~7 per hook
+    (ops.sn_batched): forward(training, dims, n, w_0..w_{n-1}, u_0.., v_0..) -> (w_sn_0, ..., w_sn_{n-1}). Same semantics
+    per hook as torch.nn.utils.spectral_norm's pre-forward hook (one in-place power iteration in training mode, sigma
+    differentiated with u, v held constant)."""
+
+    @staticmethod
+    def forward(ctx, training, dims, n, *tensors):
+        ws = [t.detach().contiguous() for t in tensors[:n]]
+        us, vs = list(tensors[n:2 * n]), list(tensors[2 * n:3 * n])
+        outs, sigma, keep, offs = ops.sn_batched(ws, us, vs, dims, training)
+        ctx.save_for_backward(sigma, keep, *outs)
+        ctx.meta = (tuple(dims), offs, n)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        sigma, keep = ctx.saved_tensors[:2]
+        w_sns = ctx.saved_tensors[2:]
+        dims, offs, n = ctx.meta
+        gs = [g.contiguous() if (g is not None and ctx.needs_input_grad[3 + i]) else None for i, g in enumerate(gs)]
+        douts = ops.sn_grad_batched(gs, w_sns, sigma, keep, offs, dims)
+        return (None, None, None) + tuple(douts) + (None,) * (2 * n)
+
+
+def spectral_norm_all(modules, dims, training):
+    """{module: W / sigma} for the spectral-normed `modules` (torch.nn.utils.spectral_norm holders: weight_orig, weight_u,
+    weight_v) with one batched call; dims[i] = 0 (Conv2d / Linear / Embedding) or 1 (ConvTranspose2d)."""
+    out = {}
+    for s in range(0, len(modules), ops.SN_MAX):
+        ms, ds = modules[s:s + ops.SN_MAX], tuple(dims[s:s + ops.SN_MAX])
+        res = SpectralNormAllFn.apply(training, ds, len(ms), *[m.weight_orig for m in ms], *[m.weight_u for m in ms],
+                                      *[m.weight_v for m in ms])
+        out.update(zip(ms, res))
+    return out

@@ -8,6 +8,7 @@ are gp_sn_* GEMV kernels (functional.SpectralNormFn). The discriminator head is 
 import torch
 import torch.nn as nn
 
+from .. import config
 from .. import functional as GF
 from .. import ops
 from ._common import bn_buffers, d_channels, g_channels, init_and_count, require_cuda
@@ -21,8 +22,15 @@ def D_arch(ndf=64, img_dim=3):
     return d_channels(ndf, img_dim)
 
 
-def sn_weight(module, dim, training):
+def sn_weight(module, dim, training, table=None):
+    if table is not None:
+        return table[module]
     return GF.SpectralNormFn.apply(module.weight_orig, module.weight_u, module.weight_v, dim, training)
+
+
+def _sn_table(convs, dim, training):
+    """Every spectral-norm hook of one forward in a single batched call (functional.spectral_norm_all)."""
+    return GF.spectral_norm_all(convs, [dim] * len(convs), training) if config.batched_sn() else None
 
 
 class Generator(nn.Module):
@@ -48,15 +56,16 @@ class Generator(nn.Module):
 
     def forward(self, z):
         require_cuda(z, "dcgan_specnorm.Generator")
+        sn = _sn_table([b[0] for b in self.blocks] + [self.out_layer[0]], 1, self.training)
         h = GF.linear_to_nhwc(z, self.linear.weight, self.linear.bias, self.bottom_width, ops.ACT_RELU,
                               self._gp_cache, "linear")
         for i, block in enumerate(self.blocks):
             conv, bn = block[0], block[1]
-            w = sn_weight(conv, 1, self.training)
+            w = sn_weight(conv, 1, self.training, sn)
             h = GF.with_lo(GF.ConvBlock, h, w, conv.bias, bn.weight, bn.bias, bn_buffers(bn), True, ops.ACT_RELU,
                            self._gp_cache, "blocks.%d" % i, self.training)
         last = self.out_layer[0]
-        return GF.with_lo(GF.ImageConvT, h, sn_weight(last, 1, self.training), last.bias, ops.ACT_TANH, self._gp_cache,
+        return GF.with_lo(GF.ImageConvT, h, sn_weight(last, 1, self.training, sn), last.bias, ops.ACT_TANH, self._gp_cache,
                           "out_layer")
 
 
@@ -84,10 +93,11 @@ class Discriminator(nn.Module):
     def forward(self, x, out_hidden=False):
         require_cuda(x, "dcgan_specnorm.Discriminator")
         first = self.blocks[0][0]
-        h = GF.image_conv(x, sn_weight(first, 0, self.training), first.bias, ops.ACT_LRELU, self._gp_cache, "blocks.0")
+        sn = _sn_table([b[0] for b in self.blocks], 0, self.training)
+        h = GF.image_conv(x, sn_weight(first, 0, self.training, sn), first.bias, ops.ACT_LRELU, self._gp_cache, "blocks.0")
         for i in range(1, len(self.blocks)):
             conv, bn = self.blocks[i][0], self.blocks[i][1]
-            h = GF.with_lo(GF.ConvBlock, h, sn_weight(conv, 0, self.training), conv.bias, bn.weight, bn.bias,
+            h = GF.with_lo(GF.ConvBlock, h, sn_weight(conv, 0, self.training, sn), conv.bias, bn.weight, bn.bias,
                            bn_buffers(bn), False, ops.ACT_LRELU, self._gp_cache, "blocks.%d" % i, self.training,
                            i == len(self.blocks) - 1)
         out = GF.with_lo(GF.Head, h, self.out_layer.weight, self.out_layer.bias, True)

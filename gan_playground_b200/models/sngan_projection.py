@@ -30,7 +30,10 @@ def _act_code(activation):
     raise NotImplementedError("only activation=F.relu is implemented on the B200 path (reference default)")
 
 
-def _sn(module, training):
+def _sn(module, training, table=None):
+    """W / sigma of a spectral-normed holder: from the forward's batched table when there is one, else on its own."""
+    if table is not None:
+        return table[module]
     return GF.SpectralNormFn.apply(module.weight_orig, module.weight_u, module.weight_v, 0, training)
 
 
@@ -151,16 +154,20 @@ class ResDisBlock(nn.Module):
             self.c_sc = _holder(nn.Conv2d(in_channels, out_channels, 1), spectral=True)
         self._gp_cache = GF.WeightCache()
 
-    def forward(self, x):
+    def sn_modules(self):
+        return [self.c1, self.c2] + ([self.c_sc] if self.learnable_sc else [])
+
+    def forward(self, x, sn=None):
         """x: NHWC bf16. relu -> c1 -> relu -> c2 (-> avgpool) + shortcut c_sc(x) (-> avgpool) (reference :125-136).
-        Pooling is linear, so the shortcut is added in c2's epilogue and the sum is pooled once."""
+        Pooling is linear, so the shortcut is added in c2's epilogue and the sum is pooled once.
+        sn: {module: W / sigma} when the owning network ran all its spectral-norm hooks in one batched call."""
         _act_code(self.activation)
         t = self.training
         h = _node(GR.ReluFn, x)
-        h = _conv(h, _sn(self.c1, t), self.c1.bias, None, ops.ACT_RELU, self._gp_cache, "c1")
-        sc = _conv(x, _sn(self.c_sc, t), self.c_sc.bias, None, ops.ACT_NONE, self._gp_cache, "c_sc") \
+        h = _conv(h, _sn(self.c1, t, sn), self.c1.bias, None, ops.ACT_RELU, self._gp_cache, "c1")
+        sc = _conv(x, _sn(self.c_sc, t, sn), self.c_sc.bias, None, ops.ACT_NONE, self._gp_cache, "c_sc") \
             if self.learnable_sc else x
-        h = _conv(h, _sn(self.c2, t), self.c2.bias, sc, ops.ACT_NONE, self._gp_cache, "c2")
+        h = _conv(h, _sn(self.c2, t, sn), self.c2.bias, sc, ops.ACT_NONE, self._gp_cache, "c2")
         return _node(GR.Pool2x, h) if self.downsample else h
 
 
@@ -173,13 +180,16 @@ class ResDisOptimizedBlock(nn.Module):
             setattr(self, name, _holder(nn.Conv2d(cin, out_channels, k, padding=pad if k == ksize else 0), gain, spectral=True))
         self._gp_cache = GF.WeightCache()
 
-    def forward(self, x):
+    def sn_modules(self):
+        return [self.c1, self.c2, self.c_sc]
+
+    def forward(self, x, sn=None):
         """x: fp32 NCHW image. c1 -> relu -> c2 -> avgpool, plus avgpool(c_sc(x)) (reference :156-164)."""
         _act_code(self.activation)
         t = self.training
-        h1, h1c, sc, scc = GR.ImageConv3.apply(x, _sn(self.c1, t), self.c1.bias, _sn(self.c_sc, t), self.c_sc.bias)
+        h1, h1c, sc, scc = GR.ImageConv3.apply(x, _sn(self.c1, t, sn), self.c1.bias, _sn(self.c_sc, t, sn), self.c_sc.bias)
         h1, sc = GR.attach((h1, h1c)), GR.attach((sc, scc))
-        h = _conv(h1, _sn(self.c2, t), self.c2.bias, sc, ops.ACT_NONE, self._gp_cache, "c2")
+        h = _conv(h1, _sn(self.c2, t, sn), self.c2.bias, sc, ops.ACT_NONE, self._gp_cache, "c2")
         return _node(GR.Pool2x, h)
 
 
@@ -199,12 +209,16 @@ class SNResNetProjectionDiscriminator(nn.Module):
         require_cuda(x, "sngan_projection.SNResNetProjectionDiscriminator")
         _act_code(self.activation)
         with config.resnet_scope():
-            h = self.block1(x)
-            for block in (self.block2, self.block3, self.block4, self.block5):
-                h = block(h)
             t = self.training
-            Ey = _sn(self.l_y, t) if (y is not None) else None
-            return GR.ProjHead.apply(h, GR.comp_of(h), _sn(self.l6, t), self.l6.bias, Ey,
+            # every spectral-norm hook this forward fires (l_y only when labels are given, as upstream's hooks), batched
+            blocks = (self.block1, self.block2, self.block3, self.block4, self.block5)
+            mods = [m for b in blocks for m in b.sn_modules()] + [self.l6] + ([self.l_y] if y is not None else [])
+            sn = GF.spectral_norm_all(mods, [0] * len(mods), t) if config.batched_sn() else None
+            h = self.block1(x, sn)
+            for block in blocks[1:]:
+                h = block(h, sn)
+            Ey = _sn(self.l_y, t, sn) if (y is not None) else None
+            return GR.ProjHead.apply(h, GR.comp_of(h), _sn(self.l6, t, sn), self.l6.bias, Ey,
                                      y.contiguous() if y is not None else None)
 
 

@@ -516,6 +516,81 @@ def sn_grad(g, w_sn, dim, u, v, sigma):
     return out
 
 
+SN_MAX = 24
+_SIGS.update({"gp_sn_batched": [_vp, _vp], "gp_sn_grad_batched": [_vp, _vp]})
+
+
+class SnBatch(ctypes.Structure):
+    """gp_sn_batch_t of include/gpb200.h."""
+    _fields_ = [(n, ctypes.c_void_p * SN_MAX) for n in ("w", "u", "v", "out", "sigma")] + \
+               [(n, ctypes.c_int32 * SN_MAX) for n in ("A", "B", "T", "dim")] + \
+               [("count", ctypes.c_int32), ("training", ctypes.c_int32), ("eps", ctypes.c_float),
+                ("scratch", ctypes.c_void_p), ("keep", ctypes.c_void_p)]
+
+
+class SnGradBatch(ctypes.Structure):
+    """gp_sn_grad_batch_t of include/gpb200.h."""
+    _fields_ = [(n, ctypes.c_void_p * SN_MAX) for n in ("g", "w_sn", "u", "v", "sigma", "out")] + \
+               [(n, ctypes.c_int32 * SN_MAX) for n in ("A", "B", "T", "dim")] + \
+               [("count", ctypes.c_int32), ("dot", ctypes.c_void_p)]
+
+
+def sn_batched(ws, us, vs, dims, training, eps=1e-12):
+    """Spectral norm of every hook of one forward in five launches. ws / us / vs: lists of fp32 tensors (weight_orig, u,
+    v), dims: 0 | 1 per hook. u, v are advanced in place when training. Returns (w_sn list — views into one flat buffer,
+    sigma fp32 [n], keep fp32 flat buffer of the (u | v) used, offsets of each hook inside keep)."""
+    n = len(ws)
+    if not 0 < n <= SN_MAX:
+        raise _lib.GpError("sn_batched: 1..%d hooks per call, got %d" % (SN_MAX, n))
+    dev = ws[0].device
+    numels = [w.numel() for w in ws]
+    flat = torch.empty(sum((m + 3) // 4 * 4 for m in numels), device=dev, dtype=torch.float32)
+    sigma = torch.empty(n, device=dev, dtype=torch.float32)
+    b = SnBatch()
+    outs, offs, off, pos = [], [], 0, 0
+    for i, (w, u, v, d) in enumerate(zip(ws, us, vs, dims)):
+        _chk(w, torch.float32, "w")
+        _chk(u, torch.float32, "u")
+        _chk(v, torch.float32, "v")
+        A, B, T = _sn_dims(w)
+        o = flat[pos:pos + numels[i]].view(w.shape)
+        pos += (numels[i] + 3) // 4 * 4
+        outs.append(o)
+        b.w[i], b.u[i], b.v[i], b.out[i], b.sigma[i] = _p(w), _p(u), _p(v), _p(o), sigma.data_ptr() + 4 * i
+        b.A[i], b.B[i], b.T[i], b.dim[i] = A, B, T, d
+        offs.append((off, u.numel(), v.numel()))
+        off += u.numel() + v.numel()
+    scratch = torch.empty(off, device=dev, dtype=torch.float32)
+    keep = torch.empty(off, device=dev, dtype=torch.float32)
+    b.count, b.training, b.eps, b.scratch, b.keep = n, 1 if training else 0, eps, _p(scratch), _p(keep)
+    check(_fn("gp_sn_batched")(ctypes.addressof(b), _stream()), "gp_sn_batched")
+    return outs, sigma, keep, offs
+
+
+def sn_grad_batched(gs, w_sns, sigma, keep, offs, dims):
+    """Gradient through W / sigma for every hook that received one (gs[i] may be None). Returns a list (None where gs[i] is)."""
+    n = len(gs)
+    dev = sigma.device
+    b = SnGradBatch()
+    outs = []
+    for i, g in enumerate(gs):
+        if g is None:
+            outs.append(None)
+            continue
+        _chk(g, torch.float32, "g")
+        A, B, T = _sn_dims(w_sns[i])
+        o = torch.empty_like(w_sns[i])
+        off, nu, nv = offs[i]
+        b.g[i], b.w_sn[i], b.out[i] = _p(g), _p(w_sns[i]), _p(o)
+        b.u[i], b.v[i], b.sigma[i] = keep.data_ptr() + 4 * off, keep.data_ptr() + 4 * (off + nu), sigma.data_ptr() + 4 * i
+        b.A[i], b.B[i], b.T[i], b.dim[i] = A, B, T, dims[i]
+        outs.append(o)
+    dot = torch.empty(n, device=dev, dtype=torch.float32)
+    b.count, b.dot = n, _p(dot)
+    check(_fn("gp_sn_grad_batched")(ctypes.addressof(b), _stream()), "gp_sn_grad_batched")
+    return outs
+
+
 # ------------------------------------------------------------------------------------------------ SNGAN projection
 _SIGS.update({
     "gp_cbn_apply_act": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp],

@@ -213,6 +213,38 @@ int gp_sn_scale(const float* w, const float* sigma, float* out, long long n, voi
 int gp_sn_grad(const float* g, const float* w_sn, int A, int B, int T, int dim, const float* u, const float* v,
                const float* sigma, float* dot, float* out, void* stream);
 
+/* Batched over the hooks of one forward (the projection discriminator has 17: models/sngan_projection.py:110-181): the same
+ * semantics as gp_sn_sigma + gp_sn_scale for `count` weights in five launches. scratch: fp32 [sum_i rows_i + cols_i];
+ * keep (optional, same size): receives the (u | v) each hook used in this forward — what gp_sn_grad_batched needs, since
+ * later forwards advance u, v in place. gp_sn_grad_batched: hooks with g[i] == NULL are skipped; dot: fp32 [count]. */
+#define GP_SN_MAX 24
+typedef struct {
+  const float* w[GP_SN_MAX];
+  float* u[GP_SN_MAX];
+  float* v[GP_SN_MAX];
+  float* out[GP_SN_MAX];   /* w / sigma, same layout as w */
+  float* sigma[GP_SN_MAX]; /* fp32 scalars */
+  int32_t A[GP_SN_MAX], B[GP_SN_MAX], T[GP_SN_MAX], dim[GP_SN_MAX];
+  int32_t count;
+  int32_t training;
+  float eps;
+  float* scratch;
+  float* keep;
+} gp_sn_batch_t;
+typedef struct {
+  const float* g[GP_SN_MAX];
+  const float* w_sn[GP_SN_MAX];
+  const float* u[GP_SN_MAX];
+  const float* v[GP_SN_MAX];
+  const float* sigma[GP_SN_MAX];
+  float* out[GP_SN_MAX];
+  int32_t A[GP_SN_MAX], B[GP_SN_MAX], T[GP_SN_MAX], dim[GP_SN_MAX];
+  int32_t count;
+  float* dot;
+} gp_sn_grad_batch_t;
+int gp_sn_batched(const gp_sn_batch_t* p, void* stream);
+int gp_sn_grad_batched(const gp_sn_grad_batch_t* p, void* stream);
+
 /* ---- SNGAN projection networks (models/sngan_projection.py).
  * Conditional BatchNorm (:6-19): BatchNorm2d(affine=False) statistics come from gp_bn_stats / gp_bn_finalize
  * (gamma = beta = NULL); the per-sample scale / shift are gathered from the embedding table

@@ -117,3 +117,47 @@ def test_acgan_golden_step():
     bars.loss("loss_g", loss.item(), fx["loss_g"])
     bars.cos("G-step", global_cos(netG.named_parameters(), unpack_grads(fx["g_grads"])))
     bars.finish()
+
+
+def test_batched_spectral_norm_matches_torch_hooks():
+    """functional.spectral_norm_all — every hook of a forward in one batched call — vs torch.nn.utils.spectral_norm itself on
+    a mixed set of layers (Conv2d 3x3 / 1x1, ConvTranspose2d (dim 1), Linear with a length-1 u, Embedding): W / sigma, the
+    in-place u / v after 3 training forwards, the gradient through sigma (some outputs unused), and eval mode."""
+    from gan_playground_b200 import functional as GF
+
+    ctors = [(lambda: torch.nn.Conv2d(24, 40, 3, 1, 1), 0), (lambda: torch.nn.Conv2d(16, 64, 1), 0),
+             (lambda: torch.nn.ConvTranspose2d(24, 40, 4, 2, 1), 1), (lambda: torch.nn.Linear(96, 1), 0),
+             (lambda: torch.nn.Embedding(10, 64), 0), (lambda: torch.nn.Conv2d(3, 8, 3, 1, 1), 0)]
+    torch.manual_seed(0)
+    refs = [torch.nn.utils.spectral_norm(c()).cuda() for c, _ in ctors]
+    dims = [d for _, d in ctors]
+    mine = [torch.nn.utils.spectral_norm(c()).cuda() for c, _ in ctors]
+    for m, r in zip(mine, refs):
+        m.load_state_dict(r.state_dict())
+    for r in refs:
+        r.train()
+    for it in range(3):
+        for r in refs:
+            next(iter(r._forward_pre_hooks.values()))(r, None)
+        table = GF.spectral_norm_all(mine, dims, True)
+        for m, r in zip(mine, refs):
+            assert torch.allclose(table[m], r.weight, rtol=1e-4, atol=1e-6), (type(r).__name__, it)
+    for m, r in zip(mine, refs):
+        assert torch.allclose(m.weight_u, r.weight_u, atol=1e-5) and torch.allclose(m.weight_v, r.weight_v, atol=1e-5)
+    # gradient through sigma: outputs 0, 2, 3 receive one, the others are unused
+    used = (0, 2, 3)
+    gs = {i: torch.randn_like(refs[i].weight) for i in used}
+    loss_ref = sum((refs[i].weight * gs[i]).sum() for i in used)
+    loss_mine = sum((table[mine[i]] * gs[i]).sum() for i in used)
+    g_ref = torch.autograd.grad(loss_ref, [refs[i].weight_orig for i in used])
+    g_mine = torch.autograd.grad(loss_mine, [mine[i].weight_orig for i in used])
+    for a, b in zip(g_mine, g_ref):
+        assert torch.allclose(a, b, rtol=1e-3, atol=1e-5 * b.abs().max().item())
+    # eval mode: no power iteration
+    u0 = [m.weight_u.clone() for m in mine]
+    for r in refs:
+        r.eval()
+        next(iter(r._forward_pre_hooks.values()))(r, None)
+    table = GF.spectral_norm_all(mine, dims, False)
+    for m, r, u in zip(mine, refs, u0):
+        assert torch.equal(m.weight_u, u) and torch.allclose(table[m], r.weight, rtol=1e-4, atol=1e-6)
