@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], C2 ? 256 : 128);  // pair: the epilogue threads of BOTH CTAs release the leader's buffer
+      mbar_init(&tempty_bar[i], C2 ? 8 : 4);  // one arrival per epilogue warp (pair: of BOTH CTAs, on the leader's barrier)
     }
     fence_mbar_init();
   }
@@ -670,7 +670,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       }
       if (has_bias && more) put_bias((it + 1) & 1, bnext);
       tc_fence_before();
-      if constexpr (C2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]);
+      __syncwarp();  // every lane's TMEM loads of this buffer have completed: one arrival per warp releases it
+      if (lane == 0) {
+        if constexpr (C2) mbar_arrive_leader(&tempty_bar[acc]); else mbar_arrive(&tempty_bar[acc]);
+      }
       if (has_bias) epi_bar_sync();
     }
   }
