@@ -150,6 +150,42 @@ static int launch_fwd_pair(const ConvGemmParams& prm, int pair_tiles, cudaStream
   return GP_OK;
 }
 
+// CTA-pair wgrad: a pair owns a 256 x 256 dW tile (128 rows per CTA), each CTA stages its own 128 dense channels and half
+// of the gathered columns: 32 KB per stage instead of 64 KB (6 stages instead of 3) and two accumulator buffers per CTA
+// where the lone 256 x 256 tile has one.
+static int launch_wgrad_pair(const ConvGemmParams& prm, int grid, cudaStream_t st) {
+  auto kfn = conv_gemm_kernel<MODE_WGRAD, 256, 1, false, true>;
+  using Cfg = GemmCfg<256, 1, false, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GP_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  grid &= ~1;
+  if (grid < 2) grid = 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(kNumThreads, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, prm));
+  gp::count_launch();
+  return GP_OK;
+}
+
+static bool wgrad_pair_enabled() {
+  const char* e = getenv("GP_WGRAD_2CTA");
+  return e != nullptr && e[0] == '1';   // off until validated
+}
+
 // GP_FWD_2CTA=0 disables the CTA-pair variant (1 = on, the default once a layer has enough 128-row tiles)
 static bool pair_enabled() {
   const char* e = getenv("GP_FWD_2CTA");
@@ -479,5 +515,7 @@ extern "C" int gp_conv_wgrad(const gp_conv_wgrad_t* a, void* stream) {
   const long long total_ksteps = (long long)base_tiles * prm.kblocks_total;
   int grid = num_sms();
   if (total_ksteps < 4LL * grid) grid = (int)((total_ksteps + 3) / 4);
+  if (bn == 256 && mt_sub == 2 && grid == num_sms() && wgrad_pair_enabled())
+    return launch_wgrad_pair(prm, grid, as_stream(stream));   // same 256 x 256 tiles, one per CTA pair
   return launch<MODE_WGRAD>(prm, bn, mt_sub, grid, as_stream(stream));
 }

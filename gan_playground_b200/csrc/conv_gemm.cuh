@@ -177,26 +177,26 @@ struct WorkPlan {
   int nfull, rem_tiles, base_tiles, per, kblocks_total;
   int num_tiles;
 
-  int first, stride;  // FWD: first tile of this CTA (pair) and distance to its next one
+  int first, stride;  // index of this CTA (or CTA pair) among the work units and their number
 
   template <int MODE>
   __device__ __forceinline__ WorkItem item(int it) const {
     WorkItem w;
-    const int G = gridDim.x;
+    const int G = stride;  // number of work units running side by side: CTAs, or CTA pairs
     if constexpr (MODE == MODE_FWD) {
       w.tile = first + it * stride;
       w.kb0 = 0;
       w.kb1 = 1;
     } else {
       if (it < nfull) {
-        w.tile = blockIdx.x + it * G;
+        w.tile = first + it * G;
         const int sp = w.tile / base_tiles;
         w.kb0 = sp * per;
         w.kb1 = min(w.kb0 + per, kblocks_total);
       } else {
         const int j = it - nfull;
         const long long tot = (long long)rem_tiles * per;
-        const long long r0 = tot * blockIdx.x / G, r1 = tot * (blockIdx.x + 1) / G;
+        const long long r0 = tot * first / G, r1 = tot * (first + 1) / G;
         const int t = (int)(r0 / per) + j;                       // remainder tile touched by segment j
         const long long lo = j == 0 ? r0 : (long long)t * per;
         const long long hi = min(r1, (long long)(t + 1) * per);
@@ -216,7 +216,6 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 template <int MODE, int BN, int MT, bool X3 = false, bool C2 = false>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   static_assert(!(X3 && MODE == MODE_WGRAD), "bf16x3 applies to the forward GEMMs only");
-  static_assert(!(C2 && MODE == MODE_WGRAD), "CTA pairs are used by the forward GEMMs only");
   using Cfg = GemmCfg<BN, MT, X3, C2>;
   const uint32_t pair_rank = C2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs), 1 = peer
   extern __shared__ uint8_t smem_raw[];
@@ -274,23 +273,24 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   const int ntiles_n = (ncols + BN - 1) / BN;
   int ksteps_fwd = 0, cchunks = 0, mtiles = 0;
   WorkPlan plan;
+  plan.first = C2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  plan.stride = C2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   if constexpr (MODE == MODE_FWD) {
     mtiles = ((p.NB + p.Nt - 1) / p.Nt) * htiles * wtiles;
     if constexpr (C2) mtiles = (mtiles + 1) / 2;  // pair tiles: CTA r of the pair owns 128-pixel tile 2 * mt + r
     cchunks = (p.C + kBlockK - 1) / kBlockK;
     ksteps_fwd = p.taps_per_phase * cchunks;
     plan.num_tiles = p.n_phases * mtiles * ntiles_n;
-    plan.first = C2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    plan.stride = C2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     plan.num_items = plan.num_tiles > plan.first ? (plan.num_tiles - plan.first + plan.stride - 1) / plan.stride : 0;
   } else {
-    mtiles = (p.M + MT * kBlockM - 1) / (MT * kBlockM);
+    // pair: a work unit covers 256 dW rows, CTA r of the pair owns rows [256 mt + 128 r, + 128)
+    mtiles = C2 ? (p.M + 2 * kBlockM - 1) / (2 * kBlockM) : (p.M + MT * kBlockM - 1) / (MT * kBlockM);
     plan.base_tiles = mtiles * tap_slots * ntiles_n;
     plan.kblocks_total = p.kblocks_total;
     plan.per = (p.kblocks_total + p.splits - 1) / p.splits;
     plan.num_tiles = p.splits * plan.base_tiles;
-    plan.nfull = plan.num_tiles / gridDim.x;
-    plan.rem_tiles = plan.num_tiles - plan.nfull * gridDim.x;
+    plan.nfull = plan.num_tiles / plan.stride;
+    plan.rem_tiles = plan.num_tiles - plan.nfull * plan.stride;
     plan.num_items = plan.nfull + (plan.rem_tiles > 0 ? 2 : 0);
   }
 
@@ -348,11 +348,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const int mt = (tile / (ntiles_n * tap_slots)) % mtiles;
         // 64-column chunks of the gathered operand: (tap, first channel) of each; columns past the end read channel
         // N, which TMA zero-fills
-        Tap tj[BN / 64];
-        int chj[BN / 64];
+        constexpr int kBChunks = C2 ? BN / 128 : BN / 64;  // 64-column chunks this CTA stages (a pair CTA: half of them)
+        Tap tj[kBChunks];
+        int chj[kBChunks];
 #pragma unroll
-        for (int j = 0; j < BN / 64; ++j) {
-          const int col = nt * BN + j * 64;
+        for (int j = 0; j < kBChunks; ++j) {
+          const int col = nt * BN + ((C2 ? (int)pair_rank * kBChunks : 0) + j) * 64;
           if (p.wg_flat) {
             const int tap = col / p.N;
             tj[j] = p.taps[tap < p.taps_per_phase ? tap : 0];
@@ -368,14 +369,26 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           const int n0 = (kb / (wtiles * htiles)) * p.Nt;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if constexpr (C2) {
+            if (pair_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            const int m0 = (2 * mt + (int)pair_rank) * kBlockM;
 #pragma unroll
-          for (int i = 0; i < MT * kBlockM / 64; ++i)
-            tma_load_4d(sa + i * 8192, &p.map_d, &full_bar[stage], mt * MT * kBlockM + i * 64, w0, h0, n0);
+            for (int i = 0; i < kBlockM / 64; ++i)
+              tma_load_4d_2cta(sa + i * 8192, &p.map_d, &full_bar[stage], m0 + i * 64, w0, h0, n0);
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_4d(sa + Cfg::kABytes + j * 8192, &p.map_g[tj[j].map], &full_bar[stage], chj[j], w0 + tj[j].dw,
-                        h0 + tj[j].dh, n0);
+            for (int j = 0; j < kBChunks; ++j)
+              tma_load_4d_2cta(sa + Cfg::kABytes + j * 8192, &p.map_g[tj[j].map], &full_bar[stage], chj[j], w0 + tj[j].dw,
+                               h0 + tj[j].dh, n0);
+          } else {
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+#pragma unroll
+            for (int i = 0; i < MT * kBlockM / 64; ++i)
+              tma_load_4d(sa + i * 8192, &p.map_d, &full_bar[stage], mt * MT * kBlockM + i * 64, w0, h0, n0);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_4d(sa + Cfg::kABytes + j * 8192, &p.map_g[tj[j].map], &full_bar[stage], chj[j], w0 + tj[j].dw,
+                          h0 + tj[j].dh, n0);
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -656,7 +669,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             for (int j = 0; j < 32; ++j) v[j] = r[j];
             if (mi + 1 < MT) tmem_ld_32x32(tbase + (mi + 1) * BN + c * 32, r);
             else if (c + 1 < nchunks) tmem_ld_32x32(tbase + (c + 1) * 32, r);
-            const int m = (mt * MT + mi) * kBlockM + q * 32 + lane;
+            const int m = (C2 ? 2 * mt + (int)pair_rank : mt * MT + mi) * kBlockM + q * 32 + lane;
             if (m < p.M) {
               float* drow = p.dw + static_cast<long long>(m) * p.ldw + col_base + col0;
 #pragma unroll
