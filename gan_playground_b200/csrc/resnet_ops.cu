@@ -159,10 +159,13 @@ __global__ void cbn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, cons
 __global__ void cbn_bwd_finalize_kernel(const float* __restrict__ part, int NB, int C, const float* __restrict__ emb,
                                         const long long* __restrict__ labels, float* __restrict__ S,
                                         float* __restrict__ demb) {
+  // grid (channel blocks, sample slices): S is zeroed by the caller and receives one atomic per slice
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  const int per = (NB + gridDim.y - 1) / gridDim.y;
+  const int n0 = blockIdx.y * per, n1 = min(n0 + per, NB);
   float s0 = 0.f, s1 = 0.f;
-  for (int n = 0; n < NB; ++n) {
+  for (int n = n0; n < n1; ++n) {
     const float a = part[(long long)n * 2 * C + c], b = part[(long long)n * 2 * C + C + c];
     const long long lb = emb ? labels[n] : 0;
     const float gm = emb ? emb[lb * 2 * C + c] : 1.f;
@@ -173,8 +176,10 @@ __global__ void cbn_bwd_finalize_kernel(const float* __restrict__ part, int NB, 
       atomicAdd(demb + lb * 2 * C + C + c, a);
     }
   }
-  S[c] = s0;
-  S[C + c] = s1;
+  if (n1 > n0) {
+    atomicAdd(S + c, s0);
+    atomicAdd(S + C + c, s1);
+  }
 }
 
 // dy[n,hw,c] = rstd[c] * (gamma[n][c] * dz - S0[c]/M - xhat * S1[c]/M)
@@ -412,10 +417,13 @@ __global__ void proj_head_bwd_kernel(const float* __restrict__ dout, const float
                                      const long long* __restrict__ labels, float* __restrict__ dh,
                                      float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dE, int NB,
                                      int C) {
+  // grid (channel blocks, sample slices): dw / db are zeroed by the caller and receive one atomic per slice
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  const int per = (NB + gridDim.y - 1) / gridDim.y;
+  const int n0 = blockIdx.y * per, n1 = min(n0 + per, NB);
   float accw = 0.f, accb = 0.f;
-  for (int n = 0; n < NB; ++n) {
+  for (int n = n0; n < n1; ++n) {
     const float d = dout[n];
     const float hv = h[(long long)n * C + c];
     const long long lb = E ? labels[n] : 0;
@@ -424,8 +432,10 @@ __global__ void proj_head_bwd_kernel(const float* __restrict__ dout, const float
     if (dE != nullptr) atomicAdd(dE + lb * C + c, d * hv);
     accb += d;
   }
-  dw[c] = accw;
-  if (c == 0 && db != nullptr) db[0] = accb;
+  if (n1 > n0) {
+    atomicAdd(dw + c, accw);
+    if (c == 0 && db != nullptr) atomicAdd(db, accb);
+  }
 }
 
 static inline int grid1(long long n, int block = 256) {
@@ -435,6 +445,9 @@ static inline int grid1(long long n, int block = 256) {
   if (g < 1) g = 1;
   return (int)g;
 }
+
+// slices of ~16 samples for the per-channel kernels that loop over the batch
+static inline int sample_slices(int NB) { return NB >= 32 ? (NB + 15) / 16 : 1; }
 
 struct CbnLaunch {
   dim3 grid;
@@ -490,7 +503,8 @@ int gp_cbn_bwd_reduce(const void* da, const void* y, const void* y_comp, int com
       static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), y_comp, comp_fmt, H, W, C, mean, rstd,
       emb, labels, act, upsample, part, L.ppb);
   GP_CHECK_LAUNCH();
-  cbn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, NB, C, emb, labels, S, demb);
+  GP_CHECK_CUDA(cudaMemsetAsync(S, 0, sizeof(float) * 2 * C, st));
+  cbn_bwd_finalize_kernel<<<dim3((C + 127) / 128, sample_slices(NB)), 128, 0, st>>>(part, NB, C, emb, labels, S, demb);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -603,7 +617,9 @@ int gp_proj_head_bwd(const float* dout, const float* h, const float* w, const fl
   GP_REQUIRE(dout && h && w && dh && dw && NB > 0 && C > 0, "gp_proj_head_bwd: bad arguments");
   cudaStream_t st = as_stream(stream);
   if (dE != nullptr) GP_CHECK_CUDA(cudaMemsetAsync(dE, 0, sizeof(float) * n_classes * C, st));
-  proj_head_bwd_kernel<<<(C + 127) / 128, 128, 0, st>>>(dout, h, w, E, labels, dh, dw, db, dE, NB, C);
+  GP_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * C, st));
+  if (db != nullptr) GP_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float), st));
+  proj_head_bwd_kernel<<<dim3((C + 127) / 128, sample_slices(NB)), 128, 0, st>>>(dout, h, w, E, labels, dh, dw, db, dE, NB, C);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }

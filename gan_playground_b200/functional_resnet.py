@@ -49,6 +49,7 @@ class Conv2dNHWC(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, x_comp, weight, bias, residual, res_comp, act, cache, key):
+        ctx.set_materialize_grads(False)   # no zero tensors for the companion outputs
         NB, H, W, _ = x.shape
         ksize = weight.shape[2]
         kind = ops.KIND_CONV_K3S1 if ksize == 3 else ops.KIND_CONV_K1S1
@@ -76,6 +77,8 @@ class Conv2dNHWC(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, da, _unused=None):
+        if da is None:
+            return (None,) * 9
         x, weight, a = ctx.saved_tensors
         kind, taps, act, cache, key, has_res, has_bias = ctx.misc
         da = da.contiguous()
@@ -99,6 +102,7 @@ class BNAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, y, y_comp, gamma, beta, bufs, act, training):
+        ctx.set_materialize_grads(False)   # no zero tensors for the companion outputs
         a, a_comp, fin, count = _bn_forward(y, gamma.detach(), beta.detach(), bufs, act, training, comp=y_comp,
                                             out_fmt=_fmt())
         # the backward normalises the SAME value: keep y's companion (activation mask / xhat from the bf16 rounding of y
@@ -113,6 +117,8 @@ class BNAct(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, da, _unused=None):
+        if da is None:
+            return (None,) * 7
         y, fin = ctx.saved_tensors[:2]
         y_comp = ctx.saved_tensors[2] if ctx.has_comp else None
         count, act, training = ctx.misc
@@ -126,6 +132,7 @@ class CondBNAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, x_comp, emb, labels, bufs, act, upsample, training):
+        ctx.set_materialize_grads(False)   # no zero tensors for the companion outputs
         C = x.shape[-1]
         count = (x.numel() // C) * parallel.world_size()
         rm, rv, nbt = bufs
@@ -152,6 +159,8 @@ class CondBNAct(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, da, _unused=None):
+        if da is None:
+            return (None,) * 8
         x, fin, e, labels = ctx.saved_tensors[:4]
         x_comp = ctx.saved_tensors[4] if ctx.has_comp else None
         count, act, upsample, training, ncls = ctx.misc
@@ -169,6 +178,7 @@ class Pool2x(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, x_comp):
+        ctx.set_materialize_grads(False)   # no zero tensors for the companion outputs
         fmt = _fmt()
         if not fmt:
             return ops.pool2x(x, 0.25), None
@@ -178,7 +188,7 @@ class Pool2x(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, _unused=None):
-        return ops.upsample2x(g.contiguous(), 0.25), None
+        return (ops.upsample2x(g.contiguous(), 0.25) if g is not None else None), None
 
 
 class Upsample2x(torch.autograd.Function):
@@ -186,6 +196,7 @@ class Upsample2x(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, x_comp):
+        ctx.set_materialize_grads(False)   # no zero tensors for the companion outputs
         out = ops.upsample2x(x, 1.0)
         if not _fmt() or x_comp is None:
             return out, None
@@ -195,7 +206,7 @@ class Upsample2x(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, _unused=None):
-        return ops.pool2x(g.contiguous(), 1.0), None
+        return (ops.pool2x(g.contiguous(), 1.0) if g is not None else None), None
 
 
 class ReluFn(torch.autograd.Function):
@@ -203,6 +214,7 @@ class ReluFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, x_comp):
+        ctx.set_materialize_grads(False)   # no zero tensors for the companion outputs
         fmt = _fmt()
         if fmt:
             a, a_comp = ops.act_fwd(x, ops.ACT_RELU, comp=x_comp, out_fmt=fmt)
@@ -214,6 +226,8 @@ class ReluFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, _unused=None):
+        if g is None:
+            return None, None
         (a,) = ctx.saved_tensors
         return ops.act_bwd(g.contiguous(), a, ops.ACT_RELU), None
 
@@ -232,6 +246,7 @@ class ImageConv3(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w1, b1, wsc, bsc):
+        ctx.set_materialize_grads(False)   # no zero tensors for the companion outputs
         x = x.contiguous()
         NB, ch, H, W = x.shape
         Cout = w1.shape[0]
@@ -259,8 +274,13 @@ class ImageConv3(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dh1, _u1, ds, _u2):
         x, w1, wsc, h1 = ctx.saved_tensors
+        if dh1 is None and ds is None:
+            return (None,) * 5
         NB, ch, H, W = x.shape
         Cout, K = w1.shape[0], ch * 9
+        # one of the two branches unused by the caller's graph: its gradient is zero
+        dh1 = dh1 if dh1 is not None else torch.zeros_like(h1)
+        ds = ds if ds is not None else torch.zeros_like(h1)
         dy1 = ops.act_bwd(dh1.contiguous(), h1, ops.ACT_RELU)
         ds = ds.contiguous()
         col = ops.im2col_k3s1(x)
@@ -286,6 +306,7 @@ class BlurPool(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, x_comp, stride):
+        ctx.set_materialize_grads(False)   # no zero tensors for the companion outputs
         ctx.dims = (x.shape[1], x.shape[2], stride)
         fmt = _fmt()
         if not fmt:
@@ -296,6 +317,8 @@ class BlurPool(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, _unused=None):
+        if g is None:
+            return None, None, None
         H, W, stride = ctx.dims
         return ops.blur3x3_bwd(g.contiguous(), H, W, stride), None, None
 
@@ -306,6 +329,7 @@ class ImageConv3Act(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, act, cache, key):
+        ctx.set_materialize_grads(False)   # no zero tensors for the companion outputs
         x = x.contiguous()
         NB, ch, H, W = x.shape
         Cout, K = weight.shape[0], ch * 9
@@ -334,6 +358,8 @@ class ImageConv3Act(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, da, _unused=None):
+        if da is None:
+            return (None,) * 6
         col, weight, a = ctx.saved_tensors
         act, cache, key, (NB, ch, H, W) = ctx.misc
         Cout, K = weight.shape[0], ch * 9
