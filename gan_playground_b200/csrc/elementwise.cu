@@ -423,13 +423,41 @@ __global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ a, const void*
   const long long base = (long long)b * HW * C;
   const float* wo = w + o * s_o;
   const int c8 = C / 8;
-  for (int i = threadIdx.x; i < HW * c8; i += blockDim.x) {
-    const int c = (i % c8) * 8, hw = i / c8;
-    float f[8];
-    load8c(a, a_comp, fmt, base + (long long)i * 8, f);   // most precise view of the features (act_io.cuh)
-    const float* wp = wo + c * s_c + hw * s_hw;
+  const int total = HW * c8;
+  if (s_c == 1 && ((s_o | s_hw) & 3) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0) {
+    // channels contiguous in the weight (pooled Linear, or the flatten head with its weight staged as [O][HW][C]):
+    // 16-byte weight loads, four feature groups in flight per thread
+    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {
+      float f[4][8];
+      float4 w0[4], w1[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc += f[j] * __ldg(wp + j * s_c);
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * blockDim.x;
+        if (i < total) {
+          load8c(a, a_comp, fmt, base + (long long)i * 8, f[u]);   // most precise view of the features (act_io.cuh)
+          const float4* wp = reinterpret_cast<const float4*>(wo + (i % c8) * 8 + (long long)(i / c8) * s_hw);
+          w0[u] = __ldg(wp);
+          w1[u] = __ldg(wp + 1);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[u][j] = 0.f;
+          w0[u] = w1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        acc += f[u][0] * w0[u].x + f[u][1] * w0[u].y + f[u][2] * w0[u].z + f[u][3] * w0[u].w + f[u][4] * w1[u].x +
+               f[u][5] * w1[u].y + f[u][6] * w1[u].z + f[u][7] * w1[u].w;
+    }
+  } else {
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const int c = (i % c8) * 8, hw = i / c8;
+      float f[8];
+      load8c(a, a_comp, fmt, base + (long long)i * 8, f);
+      const float* wp = wo + c * s_c + hw * s_hw;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += f[j] * __ldg(wp + j * s_c);
+    }
   }
   __shared__ float red[32];
   for (int k = 16; k > 0; k >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, k);
@@ -492,6 +520,7 @@ __global__ void head_bwd_data_kernel(const float* __restrict__ dout, const float
                                      long long s_c, long long s_hw) {
   const int c8 = C / 8;
   const long long total = (long long)NB * HW * c8;
+  const bool vec = s_c == 1 && ((s_o | s_hw) & 3) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % c8) * 8, hw = (int)((i / c8) % HW);
     const int b = (int)(i / ((long long)c8 * HW));
@@ -501,8 +530,14 @@ __global__ void head_bwd_data_kernel(const float* __restrict__ dout, const float
     for (int o = 0; o < O; ++o) {
       const float d = __ldg(dout + (long long)b * O + o);
       const float* wp = w + o * s_o + c * s_c + hw * s_hw;
+      if (vec) {   // channels contiguous in the weight: two 16-byte loads
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp)), w1 = __ldg(reinterpret_cast<const float4*>(wp) + 1);
+        acc[0] += d * w0.x, acc[1] += d * w0.y, acc[2] += d * w0.z, acc[3] += d * w0.w;
+        acc[4] += d * w1.x, acc[5] += d * w1.y, acc[6] += d * w1.z, acc[7] += d * w1.w;
+      } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += d * __ldg(wp + j * s_c);
+        for (int j = 0; j < 8; ++j) acc[j] += d * __ldg(wp + j * s_c);
+      }
     }
     store8_bf16(da + i * 8, nullptr, acc);
   }

@@ -113,6 +113,8 @@ __global__ void sn_grad_kernel(const float* __restrict__ g, SnLayout L, const fl
 // one by one that is ~7 launches per hook, three forwards per step. These kernels run the SAME five phases for every hook
 // of a forward at once (blockIdx.y = hook; the descriptor table travels by value in the kernel parameters, so a CUDA
 // graph node owns it): Wt u -> normalise v -> W v -> normalise u + sigma -> W / sigma.
+constexpr int kSnRowChunk = 16;  // rows of W per block of the batched W^T u kernel
+
 struct SnBatch {
   const float* w[GP_SN_MAX];
   float* u[GP_SN_MAX];
@@ -131,15 +133,23 @@ struct SnBatch {
 __global__ void snb_gemv_t_kernel(const __grid_constant__ SnBatch b) {
   const int m = blockIdx.y;
   const SnLayout L{b.A[m], b.B[m], b.T[m], b.dim[m]};
-  const int cb = (L.cols() + 255) / 256, rc = (L.rows() + 63) / 64;
+  const int cb = (L.cols() + 255) / 256, rc = (L.rows() + kSnRowChunk - 1) / kSnRowChunk;
   if ((int)blockIdx.x >= cb * rc) return;
   const int c = (blockIdx.x % cb) * 256 + threadIdx.x;
   if (c >= L.cols()) return;
-  const int r0 = (blockIdx.x / cb) * 64, r1 = min(r0 + 64, L.rows());
+  const int r0 = (blockIdx.x / cb) * kSnRowChunk, r1 = min(r0 + kSnRowChunk, L.rows());
   const float* w = b.w[m];
   const float* u = b.u[m];
   float acc = 0.f;
-  for (int r = r0; r < r1; ++r) acc += __ldg(w + L.addr(r, c)) * __ldg(u + r);
+  int r = r0;
+  for (; r + 8 <= r1; r += 8) {   // eight independent loads in flight per thread
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = __ldg(w + L.addr(r + k, c));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += x[k] * __ldg(u + r + k);
+  }
+  for (; r < r1; ++r) acc += __ldg(w + L.addr(r, c)) * __ldg(u + r);
   atomicAdd(b.t1[m] + c, acc);
 }
 
@@ -170,7 +180,25 @@ __global__ void snb_gemv_kernel(const __grid_constant__ SnBatch b) {
   const float* w = b.w[m];
   const float* v = b.v[m];
   float acc = 0.f;
-  for (int c = threadIdx.x; c < L.cols(); c += blockDim.x) acc += __ldg(w + L.addr(r, c)) * __ldg(v + c);
+  const int cols = L.cols();
+  if (L.dim == 0 && (cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(v)) & 15) == 0) {
+    // a row of the matrix is contiguous: 16-byte loads, two per thread in flight
+    const float4* wr = reinterpret_cast<const float4*>(w + (long long)r * cols);
+    const float4* v4 = reinterpret_cast<const float4*>(v);
+    const int n4 = cols >> 2;
+    int c = threadIdx.x;
+    for (; c + (int)blockDim.x < n4; c += 2 * blockDim.x) {
+      const float4 a0 = __ldg(wr + c), a1 = __ldg(wr + c + blockDim.x);
+      const float4 b0 = __ldg(v4 + c), b1 = __ldg(v4 + c + blockDim.x);
+      acc += a0.x * b0.x + a0.y * b0.y + a0.z * b0.z + a0.w * b0.w + a1.x * b1.x + a1.y * b1.y + a1.z * b1.z + a1.w * b1.w;
+    }
+    for (; c < n4; c += blockDim.x) {
+      const float4 a0 = __ldg(wr + c), b0 = __ldg(v4 + c);
+      acc += a0.x * b0.x + a0.y * b0.y + a0.z * b0.z + a0.w * b0.w;
+    }
+  } else {
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) acc += __ldg(w + L.addr(r, c)) * __ldg(v + c);
+  }
   acc = block_sum(acc);
   if (threadIdx.x == 0) b.t2[m][r] = acc;
 }
@@ -337,7 +365,7 @@ int gp_sn_batched(const gp_sn_batch_t* p, void* stream) {
     const long long n = (long long)L.A * L.B * L.T;
     if (n > max_elems) max_elems = n;
     if (L.rows() > max_rows) max_rows = L.rows();
-    const int tb = ((L.cols() + 255) / 256) * ((L.rows() + 63) / 64);
+    const int tb = ((L.cols() + 255) / 256) * ((L.rows() + kSnRowChunk - 1) / kSnRowChunk);
     if (tb > max_tblocks) max_tblocks = tb;
   }
   cudaStream_t st = as_stream(stream);

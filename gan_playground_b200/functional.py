@@ -461,21 +461,31 @@ class Head(torch.autograd.Function):
     def forward(ctx, a, a_lo, weight, bias, flatten):
         NB, H, W, C = a.shape
         O = weight.shape[0]
-        strides = (C * H * W, H * W, 1) if flatten else (C, 1, 0)
+        w = weight.detach()
+        if flatten and H * W > 1:
+            # torch's NCHW flatten order (c, hw) -> the features' own order (hw, c): the kernels then read the weight
+            # with 16-byte loads instead of one 4-byte load per 64-byte stride (a few KB, restaged per call)
+            w = w.view(O, C, H * W).transpose(1, 2).contiguous()
+            strides = (C * H * W, 1, C)
+        else:
+            strides = (C * H * W, H * W, 1) if flatten else (C, 1, 0)
         b = bias.detach() if bias is not None else None
         if a_lo is not None:            # bf16 low half or fp16 copy: read the most precise view of the features
-            out = ops.head_fwd_comp(a, a_lo, weight.detach(), b, O, *strides)
+            out = ops.head_fwd_comp(a, a_lo, w, b, O, *strides)
         else:
-            out = ops.head_fwd(a, weight.detach(), b, O, *strides)
-        ctx.save_for_backward(a, weight)
-        ctx.strides, ctx.O, ctx.has_bias = strides, O, bias is not None
+            out = ops.head_fwd(a, w, b, O, *strides)
+        ctx.save_for_backward(a, w)
+        ctx.strides, ctx.O, ctx.has_bias, ctx.restaged = strides, O, bias is not None, w.shape != weight.shape
+        ctx.wshape = tuple(weight.shape)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        a, weight = ctx.saved_tensors
-        da, dw, db = ops.head_bwd(dout.contiguous(), a, weight.detach(), ctx.O, *ctx.strides,
+        a, w = ctx.saved_tensors
+        da, dw, db = ops.head_bwd(dout.contiguous(), a, w, ctx.O, *ctx.strides,
                                   need_da=ctx.needs_input_grad[0], need_dw=ctx.needs_input_grad[2], need_db=ctx.has_bias)
+        if dw is not None and ctx.restaged:     # [O][HW][C] -> torch's (O, C * HW)
+            dw = dw.transpose(1, 2).reshape(ctx.wshape)
         return da, None, dw, (db if ctx.has_bias else None), None
 
 
