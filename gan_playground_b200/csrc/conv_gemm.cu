@@ -181,6 +181,11 @@ static int launch_wgrad_pair(const ConvGemmParams& prm, int grid, cudaStream_t s
   return GP_OK;
 }
 
+static bool wide_flat_enabled() {
+  const char* e = getenv("GP_WGRAD_WIDE_FLAT");
+  return e == nullptr || e[0] != '0';
+}
+
 static bool wgrad_pair_enabled() {
   const char* e = getenv("GP_WGRAD_2CTA");
   return e != nullptr && e[0] == '1';   // off until validated
@@ -491,6 +496,13 @@ extern "C" int gp_conv_wgrad(const gp_conv_wgrad_t* a, void* stream) {
   // spans 256 / Cg taps (dW rows are [tap][channel], i.e. contiguous in that index)
   prm.wg_flat = (Cg % 64 == 0 && ntaps > 1 && Cg < 256) ? 1 : 0;
   int bn = pick_bn(prm.wg_flat ? ntaps * Cg : Cg);
+  // flattened 3x3 columns (9 * Cg) are never a multiple of 256: a partly empty last 256-wide tile (the producer clamps
+  // its taps, the epilogue masks its columns) still moves fewer operand bytes per FLOP than 128-wide tiles when the
+  // padding stays under ~15 % (Cg = 128: 1152 -> 1280)
+  if (prm.wg_flat && bn == 128 && wide_flat_enabled()) {
+    const int n = ntaps * Cg, padded = (n + 255) / 256 * 256;
+    if (n >= 512 && (padded - n) * 100 <= 15 * n) bn = 256;
+  }
   // two M=128 sub-tiles share the gathered tile whenever dW has >= 256 rows: the wgrad mainloop is bound by operand
   // traffic from L2 (48 KB per 128x256x64 MMA block), a 256-row tile moves 1.5x fewer bytes per FLOP
   int mt_sub = a->Cd >= 2 * kBlockM ? 2 : 1;
