@@ -11,7 +11,7 @@ has() { [[ " $WHAT " == *" $1 "* ]]; }
 
 if has tests; then
   rm -f $O/parity_table.jsonl
-  timeout 1500 python -m pytest tests -q -m gpu -rs --durations=15 > $O/r02_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $O/r02_pytest_gpu.log
+  timeout 1500 python -m pytest tests -q -m gpu -rs -s --durations=15 > $O/r02_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 $O/r02_pytest_gpu.log
   timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > $O/r02_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $O/r02_smoke.log
 fi
 if has bench; then
@@ -41,7 +41,8 @@ if has ncu; then
 fi
 if has sanitize; then
   timeout 200 python tools/sanitize_cases.py --quick > $O/r02_sanitize_plain.log 2>&1; echo "sanitize cases (no tool) rc=$?"
-  timeout 900 compute-sanitizer --tool memcheck --target-processes all --error-exitcode 9 python tools/sanitize_cases.py --quick > $O/r02_sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -3 $O/r02_sanitizer_memcheck.log
-  timeout 900 compute-sanitizer --tool racecheck --target-processes all --error-exitcode 9 python tools/sanitize_cases.py --quick > $O/r02_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -3 $O/r02_sanitizer_racecheck.log
-  timeout 600 compute-sanitizer --tool synccheck --target-processes all --error-exitcode 9 python tools/sanitize_cases.py --quick > $O/r02_sanitizer_synccheck.log 2>&1; echo "synccheck rc=$?"; tail -3 $O/r02_sanitizer_synccheck.log
+  # compute-sanitizer itself is closed on this pool (profiles/r02_compute_sanitizer_closed_on_pool.log)
+  timeout 200 python tools/check_pair.py > $O/r02_check_pair.log 2>&1; echo "check_pair rc=$?"
+  timeout 200 python tools/check_wgrad_pair.py > $O/r02_check_wgrad_pair.log 2>&1; echo "check_wgrad_pair rc=$?"
+  timeout 200 python tools/check_wide_flat_wgrad.py > $O/r02_check_wide_flat_wgrad.log 2>&1; echo "check_wide_flat rc=$?"
 fi
