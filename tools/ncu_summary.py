@@ -11,11 +11,12 @@ _BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
 def short_name(name):
-    m = re.search(r"conv_gemm_kernel<\(int\)(\d+), \(int\)(\d+), \(int\)(\d+)(?:, \(bool\)(\d+))?>", name) or \
-        re.search(r"conv_gemm_kernel<(\d+), (\d+), (\d+)(?:, (\d+))?>", name)
+    m = re.search(r"conv_gemm_kernel<\(int\)(\d+), \(int\)(\d+), \(int\)(\d+)(?:, \(bool\)(\d+))?(?:, \(bool\)(\d+))?>", name) or \
+        re.search(r"conv_gemm_kernel<(\d+), (\d+), (\d+)(?:, (\d+))?(?:, (\d+))?>", name)
     if m:
-        mode, bn, mt, x3 = m.groups()
-        return "gp::conv_gemm_kernel<%s,BN=%s,MT=%s%s>" % ("WGRAD" if mode == "1" else "FWD", bn, mt, ",X3" if x3 == "1" else "")
+        mode, bn, mt, x3, c2 = m.groups()
+        return "gp::conv_gemm_kernel<%s,BN=%s,MT=%s%s%s>" % ("WGRAD" if mode == "1" else "FWD", bn, mt,
+                                                              ",X3" if x3 == "1" else "", ",PAIR" if c2 == "1" else "")
     return re.sub(r"\(.*", "", name)[:70]
 
 
