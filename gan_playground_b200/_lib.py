@@ -25,6 +25,7 @@ class ConvFwd(ctypes.Structure):
         ("kind", c_int), ("act", c_int), ("residual", c_void_p),
         ("in_lo", c_void_p), ("out_lo", c_void_p), ("out_f32", c_void_p),
         ("flags", c_int),
+        ("bwd_src", c_void_p), ("bwd_fin", c_void_p), ("bwd_slope", ctypes.c_float), ("bwd_mode", c_int),
     ]
 
 

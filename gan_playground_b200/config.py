@@ -115,3 +115,22 @@ def fused_stats():
 def set_fused_stats(on):
     global _fused_stats
     _fused_stats = bool(on)
+
+
+# Backward-side epilogue fusion (functional.BwdLink): the data-gradient GEMM of block i+1 applies block i's activation
+# derivative (blocks without BatchNorm) or accumulates block i's BatchNorm-backward sums, instead of a separate pass over
+# dA. Correct (tests/test_gpu_conv_gemm.py: bit-identical dA, sums within 2e-4) but OFF by default — measured on the B200
+# it LOSES: cfg2 15.93 -> 17.24 ms, cfg3 4.11 -> 4.54, cfg5 9.23 -> 9.77 (GP_BWD_FUSION=1 vs 0, same box). The DCGAN
+# data-gradient GEMMs have small K per output element (512-2048), so the extra 2-4 bytes per output element read in the
+# epilogue (y or a, row-strided, latency-exposed with ~250 registers already live) stretch a 55-80 us GEMM by more than
+# the 40-100 us streaming pass it replaces; the standalone passes run at 0.7-0.9 of the HBM peak.
+_bwd_fusion = os.environ.get("GP_BWD_FUSION", "0") == "1"
+
+
+def bwd_fusion():
+    return _bwd_fusion
+
+
+def set_bwd_fusion(on):
+    global _bwd_fusion
+    _bwd_fusion = bool(on)

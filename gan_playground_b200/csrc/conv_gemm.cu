@@ -402,6 +402,23 @@ extern "C" int gp_conv_fwd(const gp_conv_fwd_t* a, void* stream) {
   prm.fmt_flags = ((a->flags & GP_CONV_IN_F16) ? kFmtInF16 : 0) | ((a->flags & GP_CONV_LO_F16) ? kFmtLoF16 : 0) |
                   ((a->flags & GP_CONV_RES_F16) ? kFmtResF16 : 0) | ((a->flags & GP_CONV_OUT_F16) ? kFmtOutF16 : 0);
   GP_REQUIRE((a->col_sum == nullptr) == (a->col_sumsq == nullptr), "gp_conv_fwd: col_sum and col_sumsq go together");
+  GP_REQUIRE(a->bwd_mode >= GP_CONV_BWD_NONE && a->bwd_mode <= GP_CONV_BWD_BN_BF16, "gp_conv_fwd: unknown bwd_mode %d", a->bwd_mode);
+  if (a->bwd_mode != GP_CONV_BWD_NONE) {
+    // this GEMM is a data gradient: plain bf16 output, nothing else fused
+    GP_REQUIRE(a->bwd_src != nullptr && a->out != nullptr && a->out_lo == nullptr && a->out_f32 == nullptr &&
+                   a->bias == nullptr && a->residual == nullptr && a->act == GP_ACT_NONE && a->in_lo == nullptr &&
+                   (a->flags & (GP_CONV_LO_F16 | GP_CONV_OUT_F16)) == 0,
+               "gp_conv_fwd: bwd_mode %d needs bwd_src and a plain bf16 output (no bias / residual / activation / pair)", a->bwd_mode);
+    GP_REQUIRE(a->bwd_slope >= 0.f && a->bwd_slope <= 1.f, "gp_conv_fwd: bwd_slope %g outside [0, 1]", (double)a->bwd_slope);
+    if (a->bwd_mode == GP_CONV_BWD_MASK)
+      GP_REQUIRE(a->col_sum == nullptr, "gp_conv_fwd: GP_CONV_BWD_MASK does not produce statistics");
+    else
+      GP_REQUIRE(a->col_sum != nullptr && a->bwd_fin != nullptr, "gp_conv_fwd: the fused BatchNorm-backward reduction needs col_sum / col_sumsq / bwd_fin");
+    prm.bwd_src = a->bwd_src;
+    prm.bwd_fin = a->bwd_fin;
+    prm.bwd_slope = a->bwd_slope;
+    prm.bwd_mode = a->bwd_mode;
+  }
   const int mtiles = ((a->NB + prm.Nt - 1) / prm.Nt) * (prm.Hs / prm.Ht) * (prm.Ws / prm.Wt);
   const int ntn = (a->Nout + bn - 1) / bn;
   const int num_tiles = prm.n_phases * mtiles * ntn;

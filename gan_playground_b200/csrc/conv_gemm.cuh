@@ -71,6 +71,16 @@ struct alignas(64) ConvGemmParams {
                       // tile can span several taps of a narrow gathered operand; 0 = one tap per tile
   float* col_sum;     // optional fused per-channel statistics of the (pre-activation) output
   float* col_sumsq;
+  // FWD run as the DATA GRADIENT of the next layer (its output is dA of the producing layer): backward work of the
+  // producing layer done in this epilogue.  bwd_mode 1: out = v * act'(a), a = bwd_src (bf16 activation, layout of
+  // out; ReLU / LeakyReLU by sign) — replaces the producer's act_bwd pass.  bwd_mode 2 / 3: BatchNorm-backward
+  // reduction of the producer, col_sum += sum dz, col_sumsq += sum dz * xhat with dz = bf16(v) * act'(scale*y + shift),
+  // xhat = (y - mean) * rstd, y = bwd_src (fp32 for mode 2, bf16 for mode 3), bwd_fin = [mean | rstd | scale | shift][N];
+  // out = v unchanged — replaces the producer's bn_bwd_reduce pass (a second read of dA and y).
+  const void* bwd_src;
+  const float* bwd_fin;
+  float bwd_slope;
+  int bwd_mode;
   int fmt_flags;      // FWD: kFmtInF16 = both operands are fp16 (tcgen05 kind::f16 takes fp16 or bf16: only the instruction
                       // descriptor changes, tiles are 2-byte elements either way); kFmtLoF16 = out_lo receives fp16(v), the
                       // single-MMA operand copy of the "fp16" forward mode, instead of the bf16 rounding residual
@@ -551,15 +561,71 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             // next chunk: (c, mi + 1) or (c + 1, 0)
             if (mi + 1 < MT) tmem_ld_32x32(tbase + (mi + 1) * BN + c * 32, r);
             else if (c + 1 < nchunks) tmem_ld_32x32(tbase + (c + 1) * 32, r);
+            if (p.bwd_mode == 1 && row_ok[mi]) {
+              // activation derivative of the producing layer from the sign of its (bf16) output
+              const __nv_bfloat16* arow = static_cast<const __nv_bfloat16*>(p.bwd_src) + off[mi];
+              const float sl = p.bwd_slope;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (col0 + g * 8 < p.N) {
+                  const uint4 av = *reinterpret_cast<const uint4*>(arow + col0 + g * 8);
+                  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&av);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(h2[e]);
+                    v[g * 8 + 2 * e] *= f.x > 0.f ? 1.f : sl;
+                    v[g * 8 + 2 * e + 1] *= f.y > 0.f ? 1.f : sl;
+                  }
+                }
+              }
+            }
             if (do_stats) {
               // per-channel sum / sum of squares of the fp32 pre-activation output: the MT rows of a thread are added
               // first, then the 32 rows of the warp via a shuffle butterfly, then shared-memory accumulators per CTA
               // (flushed once at kernel end)
+              if (p.bwd_mode >= 2) {
+                // BatchNorm-backward sums of the producing layer instead (see ConvGemmParams::bwd_mode)
+                const float* fin = p.bwd_fin;
+                const float sl = p.bwd_slope;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float x = row_ok[mi] ? v[j] : 0.f;
-                s1[j] = (mi == 0 ? 0.f : s1[j]) + x;
-                s2[j] = (mi == 0 ? 0.f : s2[j]) + x * x;
+                for (int g = 0; g < 8; ++g) {
+                  float y4[4] = {0.f, 0.f, 0.f, 0.f};
+                  float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rs = mu, sc = mu, sh = mu;
+                  const bool on = row_ok[mi] && col0 + g * 4 < p.N;
+                  if (on) {
+                    if (p.bwd_mode == 2) {
+                      const float4 t = *reinterpret_cast<const float4*>(static_cast<const float*>(p.bwd_src) + off[mi] + col0 + g * 4);
+                      y4[0] = t.x, y4[1] = t.y, y4[2] = t.z, y4[3] = t.w;
+                    } else {
+                      const uint2 t = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(p.bwd_src) + off[mi] + col0 + g * 4);
+                      const float2 lo2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+                      const float2 hi2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+                      y4[0] = lo2.x, y4[1] = lo2.y, y4[2] = hi2.x, y4[3] = hi2.y;
+                    }
+                    mu = __ldg(reinterpret_cast<const float4*>(fin + col0 + g * 4));             // same address in every lane
+                    rs = __ldg(reinterpret_cast<const float4*>(fin + p.N + col0 + g * 4));
+                    sc = __ldg(reinterpret_cast<const float4*>(fin + 2 * p.N + col0 + g * 4));
+                    sh = __ldg(reinterpret_cast<const float4*>(fin + 3 * p.N + col0 + g * 4));
+                  }
+                  const float m4[4] = {mu.x, mu.y, mu.z, mu.w}, r4[4] = {rs.x, rs.y, rs.z, rs.w};
+                  const float c4[4] = {sc.x, sc.y, sc.z, sc.w}, h4[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const int j = g * 4 + e;
+                    // the value the apply pass will read back: dA rounded to bf16
+                    const float dav = on ? __bfloat162float(__float2bfloat16_rn(v[j])) : 0.f;
+                    const float dz = dav * (y4[e] * c4[e] + h4[e] > 0.f ? 1.f : sl);
+                    s1[j] = (mi == 0 ? 0.f : s1[j]) + dz;
+                    s2[j] = (mi == 0 ? 0.f : s2[j]) + dz * (y4[e] - m4[e]) * r4[e];
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float x = row_ok[mi] ? v[j] : 0.f;
+                  s1[j] = (mi == 0 ? 0.f : s1[j]) + x;
+                  s2[j] = (mi == 0 ? 0.f : s2[j]) + x * x;
+                }
               }
               if (mi == MT - 1) {
                 warp_transpose_sum32(s1, lane);

@@ -62,6 +62,59 @@ def _f16_operand(x, x_lo):
     return x.to(torch.float16) if x_lo is None else (x.float() + x_lo.float()).to(torch.float16)
 
 
+class BwdLink:
+    """Backward-side coupling of two CONSECUTIVE blocks of a sequential net (created by the model's forward, which knows
+    that the producer's activation has exactly one consumer). The producer describes what its backward starts with —
+    the activation derivative (kind "act": a, act) or the BatchNorm-backward reduction (kind "bn": y, fin, act) — and the
+    consumer's data-gradient GEMM does that work in its epilogue (ops.conv_fwd(bwd=...)): one pass over dA less per layer.
+    The consumer records the dA tensor it produced; the producer uses the fused result only when autograd hands it that
+    very tensor."""
+    __slots__ = ("kind", "a", "y", "fin", "act", "dx", "red")
+
+    def __init__(self):
+        self.kind = self.a = self.y = self.fin = self.act = self.dx = self.red = None
+
+    def offer_act(self, a, act):
+        if config.bwd_fusion() and act in ops._ACT_SLOPE:
+            self.kind, self.a, self.act = "act", a, act
+
+    def offer_bn(self, y, fin, act, training):
+        if (config.bwd_fusion() and training and act in ops._ACT_SLOPE and y.dtype in (torch.float32, torch.bfloat16)
+                and y.shape[-1] <= ops.MAX_STAT_COLS):
+            self.kind, self.y, self.fin, self.act = "bn", y, fin, act
+
+    def conv_bwd_arg(self, shape, device):
+        """The bwd= argument for the consumer's data-gradient GEMM whose output has `shape` (None: nothing to fuse)."""
+        if self.kind == "act" and tuple(self.a.shape) == tuple(shape):
+            return ("mask", self.a, self.act)
+        if self.kind == "bn" and tuple(self.y.shape) == tuple(shape):
+            self.red = ops.zeros((2, shape[-1]), device)
+            return ("bn", self.y, self.fin, self.act, self.red)
+        return None
+
+    def produced(self, dx):
+        self.dx = dx
+
+    def take(self, da):
+        """Producer side: ("act", None) if da already carries the activation derivative, ("bn", red) if the sums of
+        this da are ready, else (None, None). The link is consumed either way."""
+        kind, dx, red = self.kind, self.dx, self.red
+        self.dx = self.red = self.a = self.y = self.fin = None
+        if dx is None:
+            return None, None
+        same = da.data_ptr() == dx.data_ptr() and da.shape == dx.shape
+        if kind == "act":
+            if not same:
+                raise ops._lib.GpError("BwdLink: the activation derivative was fused into one consumer's data gradient, "
+                                       "but the activation has further consumers (build the model without the link)")
+            return "act", None
+        return ("bn", red) if same else (None, None)
+
+
+def _link_bwd(link, shape, device):
+    return link.conv_bwd_arg(shape, device) if link is not None else None
+
+
 def _bn_forward(y, gamma, beta, bufs, act, training=True, st=None, pair=False, comp=None, out_fmt=0):
     """y: pre-BN conv output, NHWC bf16 (fp32 in bf16x3 mode). Returns (a, a_lo, fin[4,C], count).
     training: batch statistics (all-reduced over ranks) + running-stat update, as nn.BatchNorm2d.train();
@@ -95,7 +148,7 @@ def _bn_forward(y, gamma, beta, bufs, act, training=True, st=None, pair=False, c
     return a, a_lo, fin, count
 
 
-def _bn_backward(da, y, fin, count, act, training=True, need_affine=True, comp=None, affine=None):
+def _bn_backward(da, y, fin, count, act, training=True, need_affine=True, comp=None, affine=None, red=None):
     """Returns (dy, dgamma, dbeta); dgamma / dbeta are None when the affine parameters need no gradient — or when their
     gradients were delivered straight into the parameters' .grad buffers by the apply kernel (`affine` = (gamma, beta)
     parameters that own such a buffer, ops.grad_target). comp: companion tensor of y — the backward must see the value
@@ -103,7 +156,9 @@ def _bn_backward(da, y, fin, count, act, training=True, need_affine=True, comp=N
     f32 = y.dtype == torch.float32
     if y.dtype == torch.float16:          # 2-byte pre-BN storage of the fp16 mode (its own companion)
         comp = y
-    if f32:
+    if red is not None:
+        pass            # accumulated by the epilogue of the GEMM that produced da (BwdLink)
+    elif f32:
         red = ops.bn_bwd_reduce_f32(da, y, fin, act)
     elif comp is not None:
         red = ops.bn_bwd_reduce_comp(da, y, comp, fin, act)
@@ -172,8 +227,9 @@ class ConvBlock(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, x_lo, weight, bias, gamma, beta, bufs, transposed, act, cache, key, training=True,
-                feeds_head=False):
+                feeds_head=False, in_link=None, out_link=None):
         NB, H, W, Cin = x.shape
+        ctx.in_link, ctx.out_link = in_link, out_link
         x3, fp16 = config.x3(), config.fp16()
         n_dim = 1 if transposed else 0
         if transposed:
@@ -213,9 +269,13 @@ class ConvBlock(torch.autograd.Function):
                                               pair=fp16 and not feeds_head)
             ctx.count, ctx.training = count, training
             ctx.save_for_backward(x, weight, y, fin)
+            if out_link is not None:
+                out_link.offer_bn(y, fin, act, training)
         else:
             a, a_lo = y if (x3 or fp16) else (y, None)
             ctx.save_for_backward(x, weight, a)
+            if out_link is not None:
+                out_link.offer_act(a, act)
         if a_lo is not None:
             ctx.mark_non_differentiable(a_lo)
         return a, a_lo
@@ -223,19 +283,20 @@ class ConvBlock(torch.autograd.Function):
     @staticmethod
     def backward(ctx, da, _unused=None):
         if da is None:
-            return (None,) * 13
+            return (None,) * 15
         da = da.contiguous()
+        fused, red = ctx.out_link.take(da) if ctx.out_link is not None else (None, None)
         if ctx.has_bn:
             x, weight, y, fin = ctx.saved_tensors
             dy, dgamma, dbeta = _bn_backward(da, y, fin, ctx.count, ctx.act, ctx.training,
                                              need_affine=ctx.needs_input_grad[4] or ctx.needs_input_grad[5],
-                                             affine=ctx.params[2:4])
+                                             affine=ctx.params[2:4], red=red if fused == "bn" else None)
             # a bias in front of BatchNorm has an analytically zero gradient (the reference's is fp32 rounding noise,
             # SURVEY.md §2.2): hand autograd no tensor at all instead of a zero fill plus an accumulation pass
             dbias = None
         else:
             x, weight, a = ctx.saved_tensors
-            dy = ops.act_bwd(da, a, ctx.act) if ctx.act != ops.ACT_NONE else da
+            dy = da if (ctx.act == ops.ACT_NONE or fused == "act") else ops.act_bwd(da, a, ctx.act)
             dgamma = dbeta = None
             dbias = _deliver_colsum(dy, ctx.params[1]) if ctx.needs_input_grad[3] else None
         dweight = dx = None
@@ -247,15 +308,18 @@ class ConvBlock(torch.autograd.Function):
             dweight = _deliver_conv_wgrad(dwp, weight.shape, ctx.params[0])
         if ctx.needs_input_grad[0]:
             NB, H, W, _ = x.shape
+            bwd = _link_bwd(ctx.in_link, x.shape, x.device)   # the producing block's backward work, in this epilogue
             if ctx.transposed:   # dgrad of ConvT == strided conv over dy with weights [Cin][tap][Cout]
                 wpd = ctx.cache.get((ctx.key, "dgrad"), weight, lambda: ops.pack_conv_weight(weight.detach(), 0))
-                dx = ops.conv_fwd(dy, wpd, None, ops.KIND_CONV_K4S2, H, W)
+                dx = ops.conv_fwd(dy, wpd, None, ops.KIND_CONV_K4S2, H, W, bwd=bwd)
             else:                # dgrad of Conv == 4-phase transposed conv over dy with weights [Cin][tap][Cout]
                 wpd = ctx.cache.get((ctx.key, "dgrad"), weight, lambda: ops.pack_conv_weight(weight.detach(), 1))
-                dx = ops.conv_fwd(dy, wpd, None, ops.KIND_CONVT_K4S2, H, W)
+                dx = ops.conv_fwd(dy, wpd, None, ops.KIND_CONVT_K4S2, H, W, bwd=bwd)
+            if bwd is not None:
+                ctx.in_link.produced(dx)
         if not ctx.needs_input_grad[3]:
             dbias = None
-        return dx, None, dweight, dbias, dgamma, dbeta, None, None, None, None, None, None, None
+        return dx, None, dweight, dbias, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 
 class LinearToNHWC(torch.autograd.Function):
@@ -263,8 +327,9 @@ class LinearToNHWC(torch.autograd.Function):
     Reference: models/dcgan.py:32,50-51 (ReLU) and models/acgan.py:49-50 (no activation)."""
 
     @staticmethod
-    def forward(ctx, z, weight, bias, bw, act, cache, key):
+    def forward(ctx, z, weight, bias, bw, act, cache, key, out_link=None):
         B, K = z.shape
+        ctx.out_link = out_link
         O = weight.shape[0]
         HW = bw * bw
         C = O // HW
@@ -298,16 +363,20 @@ class LinearToNHWC(torch.autograd.Function):
         ctx.params = _params(weight, bias)
         if a_lo is not None:
             ctx.mark_non_differentiable(a_lo)
+        if out_link is not None:
+            out_link.offer_act(a.view(B, bw, bw, C), act)
         return a.view(B, bw, bw, C), a_lo
 
     @staticmethod
     def backward(ctx, da, _unused=None):
         if da is None:
-            return (None,) * 7
+            return (None,) * 8
         zb, a, weight = ctx.saved_tensors
         B, K, O, HW, C, Kp, act = ctx.dims
-        da = da.contiguous().view(B, 1, 1, O)
-        dy = ops.act_bwd(da, a, act) if act != ops.ACT_NONE else da
+        da = da.contiguous()
+        fused, _ = ctx.out_link.take(da) if ctx.out_link is not None else (None, None)
+        da = da.view(B, 1, 1, O)
+        dy = da if (act == ops.ACT_NONE or fused == "act") else ops.act_bwd(da, a, act)
         dweight = dbias = None
         if ctx.needs_input_grad[1]:
             dwp = ops.conv_wgrad(dy, zb.view(B, 1, 1, Kp), ops.KIND_CONV_K1S1, 1, flops=2.0 * B * O * K)  # [O][1][Kp]
@@ -317,11 +386,11 @@ class LinearToNHWC(torch.autograd.Function):
             dbias = _deliver_matrix_grad(db, (O,), ctx.params[1], O, 1, 1, 1, 1, perm=HW)
         if ctx.needs_input_grad[0]:
             raise ops._lib.GpError("gradient w.r.t. the latent input of the first Linear is not implemented")
-        return None, dweight, dbias, None, None, None, None
+        return None, dweight, dbias, None, None, None, None, None
 
 
-def linear_to_nhwc(z, weight, bias, bw, act, cache, key):
-    a, lo = LinearToNHWC.apply(z, weight, bias, bw, act, cache, key)
+def linear_to_nhwc(z, weight, bias, bw, act, cache, key, out_link=None):
+    a, lo = LinearToNHWC.apply(z, weight, bias, bw, act, cache, key, out_link)
     if lo is not None:
         a._gp_lo = lo
     return a
@@ -332,12 +401,13 @@ class ImageConv(torch.autograd.Function):
     Reference: models/dcgan.py:106-109 (block 0 has no BatchNorm). im2col -> 1-tap tensor-core GEMM (K = 64)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act, cache, key):
+    def forward(ctx, x, weight, bias, act, cache, key, out_link=None):
         x = x.contiguous()
         NB, ch, H, W = x.shape
         Cout = weight.shape[0]
         fl = 2.0 * NB * (H // 2) * (W // 2) * Cout * ch * 16
         ctx.set_materialize_grads(False)
+        ctx.out_link = out_link
         if config.x3():
             col, col_lo = ops.im2col_k4s2_split(x.detach())
             wp = cache.get((key, "fwd3"), weight,
@@ -361,17 +431,21 @@ class ImageConv(torch.autograd.Function):
         ctx.save_for_backward(col, weight, a)   # the im2col buffer (hi half) is kept for wgrad instead of rebuilt
         ctx.misc = (act, cache, key, (NB, ch, H, W))
         ctx.params = _params(weight, bias)
+        if out_link is not None:
+            out_link.offer_act(a, act)
         return a, a_lo
 
     @staticmethod
     def backward(ctx, da, _unused=None):
         if da is None:
-            return (None,) * 6
+            return (None,) * 7
         col, weight, a = ctx.saved_tensors
         act, cache, key, (NB, ch, H, W) = ctx.misc
         Cout = weight.shape[0]
         fl = 2.0 * NB * (H // 2) * (W // 2) * Cout * ch * 16
-        dy = ops.act_bwd(da.contiguous(), a, act) if act != ops.ACT_NONE else da.contiguous()
+        da = da.contiguous()
+        fused, _ = ctx.out_link.take(da) if ctx.out_link is not None else (None, None)
+        dy = da if (act == ops.ACT_NONE or fused == "act") else ops.act_bwd(da, a, act)
         dweight = dbias = dx = None
         if ctx.needs_input_grad[1]:
             dwp = ops.conv_wgrad(dy, col, ops.KIND_CONV_K1S1, 1, flops=fl)  # [Cout][1][64]
@@ -384,11 +458,11 @@ class ImageConv(torch.autograd.Function):
                             lambda: ops.pack_matrix(weight.detach(), ch * 16, Cout, 64, Cout, 1, ch * 16))
             dcol = ops.conv_fwd(dy, wpt, None, ops.KIND_CONV_K1S1, H // 2, W // 2, flops=fl)
             dx = ops.col2im_k4s2(dcol, None, ch, ops.ACT_NONE)
-        return dx, dweight, dbias, None, None, None
+        return dx, dweight, dbias, None, None, None, None
 
 
-def image_conv(x, weight, bias, act, cache, key):
-    a, lo = ImageConv.apply(x, weight, bias, act, cache, key)
+def image_conv(x, weight, bias, act, cache, key, out_link=None):
+    a, lo = ImageConv.apply(x, weight, bias, act, cache, key, out_link)
     if lo is not None:
         a._gp_lo = lo
     return a
@@ -399,10 +473,11 @@ class ImageConvT(torch.autograd.Function):
     Reference: models/dcgan.py:41-44. 1-tap tensor-core GEMM (N = 64) -> col2im + bias + tanh."""
 
     @staticmethod
-    def forward(ctx, x, x_lo, weight, bias, act, cache, key):
+    def forward(ctx, x, x_lo, weight, bias, act, cache, key, in_link=None):
         NB, H, W, Cin = x.shape
         ch = weight.shape[1]
         fl = 2.0 * NB * H * W * Cin * ch * 16
+        ctx.in_link = in_link
         if config.x3():
             wp = cache.get((key, "fwd3"), weight,
                            lambda: ops.split_weight_matrix(weight.detach(), ch * 16, Cin, 64, Cin, 1, ch * 16))
@@ -448,8 +523,11 @@ class ImageConvT(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             wpd = cache.get((key, "dgrad"), weight,
                             lambda: ops.pack_matrix(weight.detach(), Cin, ch * 16, Cin, 64, ch * 16, 1))
-            dx = ops.conv_fwd(dcol, wpd, None, ops.KIND_CONV_K1S1, H, W, flops=fl)
-        return dx, None, dweight, dbias, None, None, None
+            bwd = _link_bwd(ctx.in_link, x.shape, x.device)
+            dx = ops.conv_fwd(dcol, wpd, None, ops.KIND_CONV_K1S1, H, W, flops=fl, bwd=bwd)
+            if bwd is not None:
+                ctx.in_link.produced(dx)
+        return dx, None, dweight, dbias, None, None, None, None
 
 
 class Head(torch.autograd.Function):

@@ -42,19 +42,24 @@ class Generator(nn.Module):
     def init_weights(self):
         init_and_count(self, (nn.ConvTranspose2d, nn.Linear), "G")
 
-    def _trunk(self, h):
+    def _trunk(self, h, link=None):
+        # a strictly sequential chain: every activation has ONE consumer, so each block's data-gradient GEMM can do the
+        # first backward pass of the block before it (functional.BwdLink)
         for i, block in enumerate(self.blocks):
             conv, bn = block[0], block[1]
+            nxt = GF.BwdLink()
             h = GF.with_lo(GF.ConvBlock, h, conv.weight, conv.bias, bn.weight, bn.bias, bn_buffers(bn), True,
-                           ops.ACT_RELU, self._gp_cache, "blocks.%d" % i, self.training)
+                           ops.ACT_RELU, self._gp_cache, "blocks.%d" % i, self.training, False, link, nxt)
+            link = nxt
         last = self.out_layer[0]
-        return GF.with_lo(GF.ImageConvT, h, last.weight, last.bias, ops.ACT_TANH, self._gp_cache, "out_layer")
+        return GF.with_lo(GF.ImageConvT, h, last.weight, last.bias, ops.ACT_TANH, self._gp_cache, "out_layer", link)
 
     def forward(self, z):
         require_cuda(z, "dcgan.Generator")
+        link = GF.BwdLink()
         h = GF.linear_to_nhwc(z, self.linear.weight, self.linear.bias, self.bottom_width, ops.ACT_RELU,
-                              self._gp_cache, "linear")
-        return self._trunk(h)
+                              self._gp_cache, "linear", link)
+        return self._trunk(h, link)
 
 
 class Discriminator(nn.Module):
@@ -82,11 +87,15 @@ class Discriminator(nn.Module):
 
     def _features(self, x):
         first = self.blocks[0][0]
-        h = GF.image_conv(x, first.weight, first.bias, ops.ACT_LRELU, self._gp_cache, "blocks.0")
+        link = GF.BwdLink()
+        h = GF.image_conv(x, first.weight, first.bias, ops.ACT_LRELU, self._gp_cache, "blocks.0", link)
         for i in range(1, len(self.blocks)):
             conv, bn = self.blocks[i][0], self.blocks[i][1]
+            last = i == len(self.blocks) - 1
+            nxt = None if last else GF.BwdLink()      # the head is not a GEMM: the last block keeps its own reduction
             h = GF.with_lo(GF.ConvBlock, h, conv.weight, conv.bias, bn.weight, bn.bias, bn_buffers(bn), False,
-                           ops.ACT_LRELU, self._gp_cache, "blocks.%d" % i, self.training, i == len(self.blocks) - 1)
+                           ops.ACT_LRELU, self._gp_cache, "blocks.%d" % i, self.training, last, link, nxt)
+            link = nxt
         return h
 
     def forward(self, x):

@@ -57,16 +57,19 @@ class Generator(nn.Module):
     def forward(self, z):
         require_cuda(z, "dcgan_specnorm.Generator")
         sn = _sn_table([b[0] for b in self.blocks] + [self.out_layer[0]], 1, self.training)
+        link = GF.BwdLink()      # sequential chain: see models/dcgan.py
         h = GF.linear_to_nhwc(z, self.linear.weight, self.linear.bias, self.bottom_width, ops.ACT_RELU,
-                              self._gp_cache, "linear")
+                              self._gp_cache, "linear", link)
         for i, block in enumerate(self.blocks):
             conv, bn = block[0], block[1]
             w = sn_weight(conv, 1, self.training, sn)
+            nxt = GF.BwdLink()
             h = GF.with_lo(GF.ConvBlock, h, w, conv.bias, bn.weight, bn.bias, bn_buffers(bn), True, ops.ACT_RELU,
-                           self._gp_cache, "blocks.%d" % i, self.training)
+                           self._gp_cache, "blocks.%d" % i, self.training, False, link, nxt)
+            link = nxt
         last = self.out_layer[0]
         return GF.with_lo(GF.ImageConvT, h, sn_weight(last, 1, self.training, sn), last.bias, ops.ACT_TANH, self._gp_cache,
-                          "out_layer")
+                          "out_layer", link)
 
 
 class Discriminator(nn.Module):
@@ -94,12 +97,17 @@ class Discriminator(nn.Module):
         require_cuda(x, "dcgan_specnorm.Discriminator")
         first = self.blocks[0][0]
         sn = _sn_table([b[0] for b in self.blocks], 0, self.training)
-        h = GF.image_conv(x, sn_weight(first, 0, self.training, sn), first.bias, ops.ACT_LRELU, self._gp_cache, "blocks.0")
+        link = GF.BwdLink()
+        h = GF.image_conv(x, sn_weight(first, 0, self.training, sn), first.bias, ops.ACT_LRELU, self._gp_cache, "blocks.0",
+                          link)
         for i in range(1, len(self.blocks)):
             conv, bn = self.blocks[i][0], self.blocks[i][1]
+            last = i == len(self.blocks) - 1
+            nxt = None if last else GF.BwdLink()
             h = GF.with_lo(GF.ConvBlock, h, sn_weight(conv, 0, self.training, sn), conv.bias, bn.weight, bn.bias,
-                           bn_buffers(bn), False, ops.ACT_LRELU, self._gp_cache, "blocks.%d" % i, self.training,
-                           i == len(self.blocks) - 1)
+                           bn_buffers(bn), False, ops.ACT_LRELU, self._gp_cache, "blocks.%d" % i, self.training, last,
+                           link, nxt)
+            link = nxt
         out = GF.with_lo(GF.Head, h, self.out_layer.weight, self.out_layer.bias, True)
         if out_hidden:
             # upstream hands back the NCHW fp32 feature map; this is a layout change at the API boundary only

@@ -199,8 +199,13 @@ _TAPS_PER_OUT = {KIND_CONV_K4S2: 16, KIND_CONVT_K4S2: 4, KIND_CONV_K3S1: 9, KIND
 CONV_IN_F16, CONV_LO_F16, CONV_RES_F16, CONV_OUT_F16 = 1, 2, 4, 8
 
 
+CONV_BWD_MASK, CONV_BWD_BN_F32, CONV_BWD_BN_BF16 = 1, 2, 3
+MAX_STAT_COLS = 2048     # kMaxStatCols of csrc/conv_gemm.cuh: widest output with epilogue-accumulated column sums
+_ACT_SLOPE = {ACT_RELU: 0.0, ACT_LRELU: 0.2}
+
+
 def conv_fwd(x, wp, bias, kind, Hout, Wout, act=ACT_NONE, stats=None, flops=None, residual=None, x_lo=None,
-             out_mode="bf16", fp16_in=False):
+             out_mode="bf16", fp16_in=False, bwd=None):
     """x: bf16 (NB, Hin, Win, Cin); wp: bf16 [Nout, taps*Cin]; returns bf16 (NB, Hout, Wout, Nout).
     stats: optional fp32 [2, Nout] zeroed tensor receiving per-channel sum / sum of squares.
     flops: algorithmic FLOPs of this call when they differ from the padded GEMM shape (image layers).
@@ -208,7 +213,10 @@ def conv_fwd(x, wp, bias, kind, Hout, Wout, act=ACT_NONE, stats=None, flops=None
     fp16 mode: fp16_in=True, x and wp are fp16 (one MMA; same layouts as the bf16 operands, x_lo must be None).
     out_mode: "bf16" -> bf16 tensor; "split" -> (hi, lo) bf16 pair; "f32" -> fp32 tensor; "pair" -> (bf16, fp16) copies
     of the same value (backward operand, next forward operand of the fp16 mode); "f16" -> one fp16 tensor (2-byte
-    pre-BatchNorm storage of the fp16 mode)."""
+    pre-BatchNorm storage of the fp16 mode).
+    bwd: this GEMM is the data gradient of the next layer and does backward work of the PRODUCING layer in its epilogue
+    (gp_conv_fwd_t::bwd_mode): ("mask", a, act) multiplies the result by act'(a); ("bn", y, fin, act, red) accumulates
+    the BatchNorm-backward sums of the producer into the zeroed fp32 [2, Nout] tensor red."""
     op_dtype = torch.float16 if fp16_in else torch.bfloat16
     _chk(x, op_dtype, "x")
     _chk(wp, op_dtype, "wp")
@@ -234,9 +242,26 @@ def conv_fwd(x, wp, bias, kind, Hout, Wout, act=ACT_NONE, stats=None, flops=None
         _chk(bias, torch.float32, "bias")
     if x_lo is not None:
         _chk(x_lo, torch.bfloat16, "x_lo")
+    bwd_src = bwd_fin = None
+    bwd_slope, bwd_mode = 0.0, 0
+    if bwd is not None:
+        if bwd[0] == "mask":
+            _, bwd_src, bact = bwd
+            _chk(bwd_src, torch.bfloat16, "bwd mask source")
+            bwd_mode = CONV_BWD_MASK
+        else:
+            _, bwd_src, bwd_fin, bact, stats = bwd
+            _chk(bwd_fin, torch.float32, "bwd fin")
+            _chk(stats, torch.float32, "bwd red")
+            if bwd_src.dtype not in (torch.float32, torch.bfloat16) or not bwd_src.is_contiguous():
+                raise _lib.GpError("conv_fwd: the fused BatchNorm-backward reduction reads a contiguous fp32 / bf16 y")
+            bwd_mode = CONV_BWD_BN_F32 if bwd_src.dtype == torch.float32 else CONV_BWD_BN_BF16
+        if tuple(bwd_src.shape) != shape:
+            raise _lib.GpError("conv_fwd: bwd source %s does not have the output's shape %s" % (tuple(bwd_src.shape), shape))
+        bwd_slope = _ACT_SLOPE[bact]
     p = ConvFwd(_p(x), _p(wp), _p(bias), _p(out), _p(stats[0]) if stats is not None else None,
                 _p(stats[1]) if stats is not None else None, NB, Hin, Win, Cin, Hout, Wout, Nout, kind, act, _p(residual),
-                _p(x_lo), _p(out_lo), _p(out_f32), flags)
+                _p(x_lo), _p(out_lo), _p(out_f32), flags, _p(bwd_src), _p(bwd_fin), bwd_slope, bwd_mode)
     if flops is None:
         flops = 2.0 * NB * Hout * Wout * Nout * Cin * _TAPS_PER_OUT[kind]
     _timed("conv_fwd kind%d %dx%dx%d C%d->%d%s" % (kind, NB, Hout, Wout, Cin, Nout,

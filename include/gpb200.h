@@ -80,7 +80,24 @@ typedef struct {
   /* "fp16" forward precision mode (ONE MMA on fp16 operands: 11 significant bits instead of bf16's 8): */
   int32_t flags;          /* GP_CONV_IN_F16: `in` and `w` hold fp16 (same layouts; in_lo must be NULL);
                              GP_CONV_LO_F16: out_lo receives fp16(v) — the next layer's operand — instead of the residual */
+  /* Backward-side fusions for a GEMM that runs as the DATA GRADIENT of the next layer (its output is dA of the layer that
+   * produced its input): work of the PRODUCING layer's backward, which would otherwise start with a pass over dA:
+   *   GP_CONV_BWD_MASK   : out = v * act'(a); bwd_src = a, the producer's bf16 activation (layout of `out`); ReLU /
+   *                        LeakyReLU by sign, bwd_slope = 0 / 0.2. Replaces gp_act_bwd of a block without BatchNorm.
+   *   GP_CONV_BWD_BN_F32 / _BF16: out = v unchanged; col_sum += sum dz, col_sumsq += sum dz * xhat with
+   *                        dz = bf16(v) * act'(scale*y + shift), xhat = (y - mean) * rstd; bwd_src = y, the producer's
+   *                        pre-BatchNorm tensor (fp32 / bf16, layout of `out`); bwd_fin = fp32 [4][Nout]: mean | rstd |
+   *                        scale | shift (the gp_bn_finalize outputs). Replaces gp_bn_bwd_reduce[_f32].
+   * Requires a plain bf16 output: no bias, residual, activation, in_lo, out_lo, out_f32. */
+  const void* bwd_src;
+  const float* bwd_fin;
+  float bwd_slope;
+  int32_t bwd_mode;
 } gp_conv_fwd_t;
+#define GP_CONV_BWD_NONE 0
+#define GP_CONV_BWD_MASK 1
+#define GP_CONV_BWD_BN_F32 2
+#define GP_CONV_BWD_BN_BF16 3
 #define GP_CONV_IN_F16 1
 #define GP_CONV_LO_F16 2
 #define GP_CONV_RES_F16 4 /* `residual` holds fp16: the companion of the shortcut activation in the "fp16" mode */

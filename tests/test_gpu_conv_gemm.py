@@ -78,3 +78,67 @@ def test_full_size_dcgan64_layers_linearity_and_adjoint():
     dx = ops.conv_fwd(dy, wpd, None, ops.KIND_CONVT_K4S2, H, H).float()
     rhs2 = (dx.double() * x1.double()).sum()
     assert abs(lhs - rhs2) / abs(rhs2) < 5e-3, (lhs.item(), rhs2.item())
+
+
+# ------------------------------------------------------------------------------ backward-side epilogue fusion (BwdLink)
+_DGRAD_CASES = [
+    # (kind, NB, Hin, Cin, Nout): the data-gradient GEMM of the NEXT layer; its output (NB, Hout, Wout, Nout) is dA of the
+    # producing layer
+    ("convt", 320, 4, 512, 256),     # CTA-pair kernel (>= 74 pair tiles)
+    ("convt", 24, 8, 256, 128),      # 128-wide tiles, two 128-row sub-tiles
+    ("k4s2", 40, 16, 128, 256),      # dgrad of a ConvTranspose2d block
+    ("k1", 12, 32, 64, 64),          # image-side layer: 64-wide tiles, ragged last row tile
+]
+
+
+def _dgrad_case(kind, NB, Hin, Cin, Nout):
+    from gan_playground_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    dy = (torch.randn(NB, Hin, Hin, Cin, device="cuda", generator=g) * 0.5).bfloat16()
+    if kind == "convt":
+        Hout, k, okind = 2 * Hin, ops.KIND_CONVT_K4S2, 16
+    elif kind == "k4s2":
+        Hout, k, okind = Hin // 2, ops.KIND_CONV_K4S2, 16
+    else:
+        Hout, k, okind = Hin, ops.KIND_CONV_K1S1, 1
+    wp = (torch.randn(Nout, okind * Cin, device="cuda", generator=g) * 0.05).bfloat16()
+    shape = (NB, Hout, Hout, Nout)
+    return ops, dy, wp, k, Hout, shape, g
+
+
+@pytest.mark.parametrize("kind,NB,Hin,Cin,Nout", _DGRAD_CASES)
+@pytest.mark.parametrize("act", ["relu", "lrelu"])
+def test_dgrad_epilogue_applies_the_producers_activation_derivative(kind, NB, Hin, Cin, Nout, act):
+    ops, dy, wp, k, Hout, shape, g = _dgrad_case(kind, NB, Hin, Cin, Nout)
+    a = torch.randn(shape, device="cuda", generator=g).bfloat16()
+    a[0, 0, 0, :8] = 0                                             # the derivative at exactly 0 is the slope
+    code = ops.ACT_RELU if act == "relu" else ops.ACT_LRELU
+    plain = ops.conv_fwd(dy, wp, None, k, Hout, Hout)
+    want = ops.act_bwd(plain, a, code).float()                     # the standalone pass it replaces
+    got = ops.conv_fwd(dy, wp, None, k, Hout, Hout, bwd=("mask", a, code)).float()
+    torch.cuda.synchronize()
+    # one extra bf16 rounding in the two-pass reference (v -> bf16 -> * slope -> bf16)
+    assert torch.allclose(got, want, rtol=2 ** -7, atol=1e-6), (got - want).abs().max().item()
+    pos = a.float() > 0
+    assert torch.equal(got[pos], plain.float()[pos])               # untouched where the activation was active
+
+
+@pytest.mark.parametrize("kind,NB,Hin,Cin,Nout", _DGRAD_CASES)
+@pytest.mark.parametrize("ydtype", [torch.float32, torch.bfloat16])
+def test_dgrad_epilogue_accumulates_the_producers_batchnorm_backward_sums(kind, NB, Hin, Cin, Nout, ydtype):
+    ops, dy, wp, k, Hout, shape, g = _dgrad_case(kind, NB, Hin, Cin, Nout)
+    y = (torch.randn(shape, device="cuda", generator=g) * 1.5 + 0.3).to(ydtype)
+    gamma = torch.rand(Nout, device="cuda", generator=g) + 0.5
+    beta = torch.randn(Nout, device="cuda", generator=g) * 0.2
+    st = ops.bn_stats_f32(y) if ydtype == torch.float32 else ops.bn_stats(y)
+    fin = ops.bn_finalize(st, y.numel() // Nout, gamma, beta, None, None, None)
+    plain = ops.conv_fwd(dy, wp, None, k, Hout, Hout)
+    reduce = ops.bn_bwd_reduce_f32 if ydtype == torch.float32 else ops.bn_bwd_reduce
+    want = reduce(plain, y, fin, ops.ACT_LRELU)                    # the standalone pass it replaces
+    red = torch.zeros(2, Nout, device="cuda")
+    got = ops.conv_fwd(dy, wp, None, k, Hout, Hout, bwd=("bn", y, fin, ops.ACT_LRELU, red))
+    torch.cuda.synchronize()
+    assert torch.equal(got, plain)                                 # dA itself is unchanged
+    scale = want.abs().max(dim=1, keepdim=True).values
+    assert ((red - want).abs() / scale).max().item() < 2e-4, ((red - want).abs() / scale).max().item()

@@ -198,3 +198,35 @@ def test_binding_table_matches_header_prototypes():
                 want = (ctypes.c_longlong if "long long" in p else ctypes.c_double if "double" in p else
                         ctypes.c_float if "float" in p else ctypes.c_int)
                 assert t is want, "%s: parameter `%s` bound as %s" % (name, p, t)
+
+
+def test_backward_links_replace_the_standalone_passes(fake_kernels):
+    """functional.BwdLink (config.bwd_fusion, off by default — it measured slower): with the fusion on, the data-gradient GEMMs take over the activation-derivative pass of the
+    blocks without BatchNorm and the BatchNorm-backward reduction of every block that feeds another GEMM block; only the
+    block in front of the head keeps its own reduction. Off: the standalone kernels run."""
+    from gan_playground_b200 import config
+    from gan_playground_b200.criterion import GANLoss
+    from gan_playground_b200.models import dcgan
+
+    prev = config.bwd_fusion()
+
+    def counts(on):
+        config.set_bwd_fusion(on)
+        try:
+            torch.manual_seed(0)
+            netG = quiet(lambda: dcgan.Generator(z_dim=16, ngf=8, resolution=32))
+            netD = quiet(lambda: dcgan.Discriminator(ndf=8, resolution=32))
+            del fake_kernels[:]
+            missing, wrong = _step(netG, netD, GANLoss("vanilla", 0.9, 0.1, 0.9), (torch.randn(4, 3, 32, 32),),
+                                   (torch.randn(4, 16),))
+            assert not [k for k in missing if not k.endswith(".0.bias")] and not wrong
+            red = sum(fake_kernels.count(k) for k in ("gp_bn_bwd_reduce", "gp_bn_bwd_reduce_f32", "gp_bn_bwd_reduce_comp"))
+            return fake_kernels.count("gp_act_bwd"), red
+        finally:
+            config.set_bwd_fusion(prev)
+
+    act_off, red_off = counts(False)
+    act_on, red_on = counts(True)
+    # resolution 32: D = image block + 2 BN blocks (3 passes), G = linear + 2 BN blocks + image layer (G step only)
+    assert act_off == 3 + 1 and red_off == 3 * 2 + 2          # D block 0 x 3 passes + G's linear; every BN block
+    assert act_on == 0 and red_on == 3 * 1                     # only D's last block (in front of the head) reduces itself
