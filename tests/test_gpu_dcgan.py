@@ -159,3 +159,36 @@ def test_eval_mode_uses_running_statistics():
     b = netG(z[:8])[:4]
     assert int(netG.blocks[0][1].num_batches_tracked) == n
     assert torch.allclose(a, b, atol=1e-2)    # eval output of a sample does not depend on its batch
+
+
+def test_backward_link_fusion_gives_the_same_gradients():
+    """config.bwd_fusion (functional.BwdLink, off by default): the data-gradient GEMMs doing the previous block's
+    activation-derivative / BatchNorm-backward-reduction pass in their epilogue must not change a G step's gradients."""
+    from gan_playground_b200 import config
+    from gan_playground_b200.criterion import GANLoss
+    from gan_playground_b200.models import dcgan
+
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        netG, netD = dcgan.Generator(ngf=32).cuda(), dcgan.Discriminator(ndf=32).cuda()
+    crit = GANLoss("vanilla", 0.9, 0.1, 0.9).cuda()
+    z = torch.randn(32, 100, device="cuda")
+    x = torch.rand(32, 3, 64, 64, device="cuda") * 2 - 1
+    prev = config.bwd_fusion()
+    grads = {}
+    try:
+        for on in (False, True):
+            config.set_bwd_fusion(on)
+            netG.zero_grad(), netD.zero_grad()
+            crit(netD(x), True).backward()
+            crit(netD(netG(z)), False, True).backward()
+            grads[on] = torch.cat([p.grad.flatten() for p in list(netG.parameters()) + list(netD.parameters())
+                                   if p.grad is not None]).clone()
+    finally:
+        config.set_bwd_fusion(prev)
+    a, b = grads[False].double(), grads[True].double()
+    assert a.numel() == b.numel()
+    cos = (a @ b / (a.norm() * b.norm())).item()
+    rel = ((a - b).norm() / a.norm()).item()
+    print("BwdLink fusion on vs off: gradient cosine %.7f, relative difference %.2e" % (cos, rel))
+    assert cos > 0.99999 and rel < 5e-3
