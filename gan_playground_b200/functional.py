@@ -408,6 +408,19 @@ class ImageConv(torch.autograd.Function):
         fl = 2.0 * NB * (H // 2) * (W // 2) * Cout * ch * 16
         ctx.set_materialize_grads(False)
         ctx.out_link = out_link
+        ctx.fused = ops.image_edge_ok(ch, H, W, Cout) and weight.is_contiguous()
+        if ctx.fused:
+            # csrc/image_edge.cu: the column tile lives in shared memory only; the image itself is what wgrad re-reads
+            fmt = ops.COMP_LO if config.x3() else (ops.COMP_F16 if config.fp16() else ops.COMP_NONE)
+            a, a_lo = _timed_edge("image_conv_fwd", fl, lambda: ops.image_conv_fwd(x.detach(), weight.detach(), bias.detach(), act, fmt))
+            if a_lo is not None:
+                ctx.mark_non_differentiable(a_lo)
+            ctx.save_for_backward(x, weight, a)
+            ctx.misc = (act, cache, key, (NB, ch, H, W))
+            ctx.params = _params(weight, bias)
+            if out_link is not None:
+                out_link.offer_act(a, act)
+            return a, a_lo
         if config.x3():
             col, col_lo = ops.im2col_k4s2_split(x.detach())
             wp = cache.get((key, "fwd3"), weight,
@@ -447,18 +460,47 @@ class ImageConv(torch.autograd.Function):
         fused, _ = ctx.out_link.take(da) if ctx.out_link is not None else (None, None)
         dy = da if (act == ops.ACT_NONE or fused == "act") else ops.act_bwd(da, a, act)
         dweight = dbias = dx = None
+        if ctx.fused:
+            x = col  # the fused forward saved the image, not a column buffer
+            if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+                # one pass over dy and the image: weight gradient in torch's layout and the bias gradient (the column
+                # sums of dy, as the constant-1 column of the tile), added straight into the .grad buffers when they exist
+                tw, tb = ops.grad_target(ctx.params[0]), ops.grad_target(ctx.params[1])
+                dw = tw if tw is not None else ops.zeros(tuple(weight.shape), dy.device)
+                db = None
+                if ctx.needs_input_grad[2]:
+                    db = tb if tb is not None else ops.zeros((Cout,), dy.device)
+                _timed_edge("image_conv_wgrad", fl, lambda: ops.image_conv_wgrad(dy, x, None, dw, db))
+                dweight = None if tw is not None else dw
+                dbias = None if (tb is not None or db is None) else db
+            if ctx.needs_input_grad[0]:
+                dx = _image_dgrad(dy, weight, ch, cache, key, H, W, fl)
+            return dx, dweight, dbias, None, None, None, None
         if ctx.needs_input_grad[1]:
             dwp = ops.conv_wgrad(dy, col, ops.KIND_CONV_K1S1, 1, flops=fl)  # [Cout][1][64]
             dweight = _deliver_matrix_grad(dwp.view(Cout, 64), weight.shape, ctx.params[0], Cout, ch * 16, 64, ch * 16, 1)
         if ctx.needs_input_grad[2]:
             dbias = _deliver_colsum(dy, ctx.params[1])
         if ctx.needs_input_grad[0]:
-            # dcol[px][j] = sum_o dy[px][o] * W[o][j]  -> weights [64][Cout] = W^T (rows j >= ch*16 are zero)
-            wpt = cache.get((key, "dgrad"), weight,
-                            lambda: ops.pack_matrix(weight.detach(), ch * 16, Cout, 64, Cout, 1, ch * 16))
-            dcol = ops.conv_fwd(dy, wpt, None, ops.KIND_CONV_K1S1, H // 2, W // 2, flops=fl)
-            dx = ops.col2im_k4s2(dcol, None, ch, ops.ACT_NONE)
+            dx = _image_dgrad(dy, weight, ch, cache, key, H, W, fl)
         return dx, dweight, dbias, None, None, None, None
+
+
+def _timed_edge(name, flops, fn):
+    """The fused image-edge launches are tensor-core launches too: keep them in bench.py's GEMM accounting."""
+    return ops._timed(name, flops, fn)
+
+
+def _image_dgrad(dy, weight, ch, cache, key, H, W, fl):
+    """Image gradient of D's first conv: dx = col2im(dy * W) — fused (csrc/image_edge.cu) when the shape allows."""
+    Cout = weight.shape[0]
+    if ops.image_edge_ok(ch, H, W, Cout, transposed=True) and weight.is_contiguous():
+        return _timed_edge("image_convt_fwd (dgrad)", fl, lambda: ops.image_convt_fwd(dy, None, weight.detach(), None, ch, ops.ACT_NONE))
+    # dcol[px][j] = sum_o dy[px][o] * W[o][j]  -> weights [64][Cout] = W^T (rows j >= ch*16 are zero)
+    wpt = cache.get((key, "dgrad"), weight,
+                    lambda: ops.pack_matrix(weight.detach(), ch * 16, Cout, 64, Cout, 1, ch * 16))
+    dcol = ops.conv_fwd(dy, wpt, None, ops.KIND_CONV_K1S1, H // 2, W // 2, flops=fl)
+    return ops.col2im_k4s2(dcol, None, ch, ops.ACT_NONE)
 
 
 def image_conv(x, weight, bias, act, cache, key, out_link=None):
@@ -478,6 +520,19 @@ class ImageConvT(torch.autograd.Function):
         ch = weight.shape[1]
         fl = 2.0 * NB * H * W * Cin * ch * 16
         ctx.in_link = in_link
+        if ops.image_edge_ok(ch, 2 * H, 2 * W, Cin, transposed=True) and weight.is_contiguous():
+            # csrc/image_edge.cu: GEMM + col2im + bias + tanh in one kernel, the column values stay on the SM
+            if config.x3():
+                xa, xl = x, (x_lo if x_lo is not None else torch.zeros_like(x))
+            elif config.fp16():
+                xa, xl = _f16_operand(x, x_lo), None
+            else:
+                xa, xl = x, None
+            out = _timed_edge("image_convt_fwd", fl, lambda: ops.image_convt_fwd(xa, xl, weight.detach(), bias.detach(), ch, act))
+            ctx.save_for_backward(x, weight, out)
+            ctx.misc = (act, cache, key)
+            ctx.params = _params(weight, bias)
+            return out
         if config.x3():
             wp = cache.get((key, "fwd3"), weight,
                            lambda: ops.split_weight_matrix(weight.detach(), ch * 16, Cin, 64, Cin, 1, ch * 16))
@@ -509,9 +564,26 @@ class ImageConvT(torch.autograd.Function):
         ch = weight.shape[1]
         fl = 2.0 * NB * H * W * Cin * ch * 16
         dout = dout.contiguous()
+        dweight = dbias = dx = None
+        mul = out if act == ops.ACT_TANH else None
+        if ops.image_edge_ok(ch, 2 * H, 2 * W, Cin) and weight.is_contiguous() and ctx.in_link is None:
+            # fused: the column tile of dout * tanh' is rebuilt in shared memory by both kernels instead of stored
+            if ctx.needs_input_grad[2]:
+                tw = ops.grad_target(ctx.params[0])
+                dw = tw if tw is not None else ops.zeros(tuple(weight.shape), x.device)
+                _timed_edge("image_conv_wgrad", fl, lambda: ops.image_conv_wgrad(x, dout, mul, dw))
+                dweight = None if tw is not None else dw
+            if ctx.needs_input_grad[3]:
+                tgt = ops.grad_target(ctx.params[1])
+                dbias = ops.image_bias_grad(dout, mul, into=tgt)
+                if tgt is not None:
+                    dbias = None
+            if ctx.needs_input_grad[0]:
+                dx, _ = _timed_edge("image_conv_fwd (dgrad)", fl,
+                                    lambda: ops.image_conv_fwd(dout, weight.detach(), None, ops.ACT_NONE, ops.COMP_NONE, mul=mul))
+            return dx, None, dweight, dbias, None, None, None, None
         # dcol[(n,ih,iw)][(co,kh,kw)] = dpre[n, co, 2ih-1+kh, 2iw-1+kw], dpre = dout * (1 - out^2) fused into the gather
         dcol = ops.im2col_k4s2(dout, out if act == ops.ACT_TANH else None)
-        dweight = dbias = dx = None
         if ctx.needs_input_grad[2]:
             dwp = ops.conv_wgrad(x, dcol, ops.KIND_CONV_K1S1, 1, flops=fl)  # [Cin][1][64]
             dweight = _deliver_matrix_grad(dwp.view(Cin, 64), weight.shape, ctx.params[0], Cin, ch * 16, 64, ch * 16, 1)

@@ -1015,6 +1015,78 @@ def head_fwd_comp(a, comp, w, bias, O, s_o, s_c, s_hw):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ fused image edge
+_SIGS.update({
+    "gp_image_conv_k4s2_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "gp_image_conv_k4s2_wgrad": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "gp_image_convt_k4s2_fwd": [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+})
+
+
+def image_edge_ok(ch, Hi, Wi, C, transposed=False):
+    """Shapes the fused image-edge kernels (csrc/image_edge.cu) take; anything else goes through im2col / col2im.
+    (Hi, Wi): the IMAGE side; C: channels of the NHWC side. GP_IMAGE_EDGE=0 forces the column-buffer path."""
+    import os
+
+    if os.environ.get("GP_IMAGE_EDGE", "1") == "0" or ch != 3 or Hi % 2 or Wi % 4:
+        return False
+    Ho, Wo = Hi // 2, Wi // 2
+    if Wo > (64 if transposed else 128) or 128 % Wo or (Ho * Wo) % 128:
+        return False
+    return C > 0 and (C % 16 == 0 and C <= 64 if transposed else C % 8 == 0 and C <= 128)
+
+
+def image_conv_fwd(img, w, bias, act, comp_fmt=COMP_NONE, mul=None):
+    """Fused im2col + GEMM of the 4x4 stride-2 conv on the fp32 NCHW image (no column buffer). w: fp32 (Cout, ch, 4, 4)
+    or any contiguous [Cout][ch*16] view. Returns (out bf16 NHWC, companion or None)."""
+    _chk(img, torch.float32, "img")
+    _chk(w, torch.float32, "w")
+    NB, ch, Hi, Wi = img.shape
+    Cout = w.shape[0]
+    shape = (NB, Hi // 2, Wi // 2, Cout)
+    out = torch.empty(shape, device=img.device, dtype=torch.bfloat16)
+    comp = torch.empty(shape, device=img.device, dtype=_COMP_DTYPE[comp_fmt]) if comp_fmt != COMP_NONE else None
+    if bias is not None:
+        _chk(bias, torch.float32, "bias")
+    if mul is not None:
+        _chk(mul, torch.float32, "mul")
+    check(_fn("gp_image_conv_k4s2_fwd")(_p(img), _p(mul), _p(w), _p(bias), _p(out), _p(comp), comp_fmt, NB, ch, Hi, Wi, Cout,
+                                        act, _stream()), "gp_image_conv_k4s2_fwd")
+    return out, comp
+
+
+def image_conv_wgrad(dense, img, mul, dw, dbias=None):
+    """dw[m][j] += sum_px dense[px][m] * im2col(img * (1 - mul^2))[px][j] accumulated into dw (fp32, shape (M, ch, 4, 4));
+    dbias (fp32 [M], optional) += column sums of dense."""
+    _chk(dense, torch.bfloat16, "dense")
+    _chk(img, torch.float32, "img")
+    _chk(dw, torch.float32, "dw")
+    NB, ch, Hi, Wi = img.shape
+    M = dense.shape[-1]
+    check(_fn("gp_image_conv_k4s2_wgrad")(_p(dense), _p(img), _p(mul), _p(dw), _p(dbias), NB, ch, Hi, Wi, M, _stream()),
+          "gp_image_conv_k4s2_wgrad")
+    return dw
+
+
+def image_convt_fwd(x, x_lo, w, bias, ch, act):
+    """Fused GEMM + col2im (+ bias + activation) of the 4x4 stride-2 transposed conv onto the fp32 NCHW image.
+    x: bf16 or fp16 NHWC (NB, Hs, Ws, C); x_lo: bf16 low halves (bf16x3 operands) or None; w: fp32 [C][ch*16]."""
+    if x.dtype == torch.float16:
+        fmt = COMP_F16
+        _chk(x, torch.float16, "x")
+    else:
+        _chk(x, torch.bfloat16, "x")
+        fmt = COMP_LO if x_lo is not None else COMP_NONE
+    if x_lo is not None:
+        _chk(x_lo, torch.bfloat16, "x_lo")
+    _chk(w, torch.float32, "w")
+    NB, Hs, Ws, C = x.shape
+    img = torch.empty((NB, ch, 2 * Hs, 2 * Ws), device=x.device, dtype=torch.float32)
+    check(_fn("gp_image_convt_k4s2_fwd")(_p(x), _p(x_lo), fmt, _p(w), _p(bias), _p(img), NB, Hs, Ws, C, ch, act, _stream()),
+          "gp_image_convt_k4s2_fwd")
+    return img
+
+
 # ------------------------------------------------------------------------------------------------ optimiser edge
 _SIGS.update({
     "gp_adam_flat": [_vp, _vp, _vp, _vp, _ll, _d, _d, _d, _d, _vp, _d, _vp],

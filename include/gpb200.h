@@ -188,6 +188,28 @@ int gp_col2im_k4s2(const void* col, const float* bias, float* img, int NB, int c
 /* dbias[c] += sum dout[n,c,:,:] * (mul ? 1 - mul^2 : 1); dbias fp32 [ch], caller-zeroed */
 int gp_image_bias_grad(const float* dout, const float* mul, float* dbias, int NB, int ch, int HW, void* stream);
 
+/* ---- the same two layers WITHOUT the column buffer: the im2col tile of 128 pixels is built in shared
+ * memory from the fp32 NCHW image rows and consumed by tcgen05.mma in place; ch == 3, Wo = Wi/2 divides 128,
+ * (Hi/2)*(Wi/2) % 128 == 0, channel count % 8 == 0 and <= 128 (other shapes: the im2col / col2im entry points above).
+ * gp_image_conv_k4s2_fwd  (models/dcgan.py:106-109, Conv2d(img_dim, ndf, 4, 2, 1) + LeakyReLU on the image):
+ *   out[px][n] = act(bias[n] + sum_j col[px][j] * w[n][j]), col = im2col(img * (mul ? 1 - mul^2 : 1)) as above,
+ *   w fp32 [Cout][ch*16] = the Conv2d weight in torch's layout; out bf16 NHWC; comp_fmt / out_comp: GP_COMP_NONE (bf16
+ *   operands), GP_COMP_LO (bf16x3 operands, out_comp = bf16 low halves), GP_COMP_F16 (fp16 operands, out_comp = fp16 copy).
+ *   With mul = the tanh output and w = the ConvTranspose2d weight [Cin][ch*16] of models/dcgan.py:41-44 it is that layer's
+ *   data gradient (dx[px][ci] from d(image)).
+ * gp_image_conv_k4s2_wgrad: dw[m][j] += sum_px dense[px][m] * col[px][j] (fp32, torch layout [M][ch*16], accumulated);
+ *   dbias[m] += sum_px dense[px][m] when dbias != NULL. dense bf16 [pixels][M]: dy of D's first conv, or x of G's last
+ *   ConvTranspose2d (then mul = tanh output).
+ * gp_image_convt_k4s2_fwd (models/dcgan.py:41-44, ConvTranspose2d(ngf, img_dim, 4, 2, 1) + Tanh; also the image gradient
+ *   of D's first conv): img = act(bias[c] + col2im(x * w)), x 2-byte NHWC (NB, Hs, Ws, C) in format fmt (GP_COMP_NONE bf16,
+ *   GP_COMP_LO bf16 hi + x_lo, GP_COMP_F16 fp16), w fp32 [C][ch*16], img fp32 NCHW (NB, ch, 2Hs, 2Ws); C % 16 == 0, <= 64. */
+int gp_image_conv_k4s2_fwd(const float* img, const float* mul, const float* w, const float* bias, void* out,
+                           void* out_comp, int comp_fmt, int NB, int ch, int Hi, int Wi, int Cout, int act, void* stream);
+int gp_image_conv_k4s2_wgrad(const void* dense, const float* img, const float* mul, float* dw, float* dbias, int NB,
+                             int ch, int Hi, int Wi, int M, void* stream);
+int gp_image_convt_k4s2_fwd(const void* x, const void* x_lo, int fmt, const float* w, const float* bias, float* img,
+                            int NB, int Hs, int Ws, int C, int ch, int act, void* stream);
+
 /* ---- discriminator heads: out[b][o] = bias[o] + sum_{hw,c} a[b,hw,c] * w[o*s_o + c*s_c + hw*s_hw]
  * (global sum pooling + Linear, models/dcgan.py:121-122: s_hw = 0; flatten + Linear, models/dcgan_specnorm.py:125-126:
  * s_c = HW, s_hw = 1; also the projection inner product of models/sngan_projection.py:193-195 with a gathered w).
