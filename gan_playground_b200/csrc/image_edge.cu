@@ -1,24 +1,32 @@
-// Fused image-edge layers: the 4x4 stride-2 convolution between the fp32 NCHW image and the first / last 64-channel NHWC
-// activation (D's first Conv2d, models/dcgan.py:106-109; the gradient side of G's last ConvTranspose2d + Tanh,
-// models/dcgan.py:41-44) WITHOUT a column buffer in HBM.
-//
-// Both kernels build the im2col tile of 128 output pixels in shared memory straight from the image rows — fp32 -> bf16
-// (or a hi/lo bf16 pair, or fp16), written in the 128-byte-swizzled UMMA layout by plain stores — and feed it to
-// tcgen05.mma with the accumulator in TMEM:
+// Fused image-edge layers: the 4x4 stride-2 convolution between the fp32 NCHW image and the first / last NHWC
+// activation (D's first Conv2d, models/dcgan.py:106-109; G's last ConvTranspose2d + Tanh, models/dcgan.py:41-44, and the
+// gradient side of both) WITHOUT a column buffer in HBM.
 //
 //   gp_image_conv_k4s2_fwd  : out[px][n] = act(bias[n] + sum_j col[px][j] * w[n][j])      col tile = K-major A operand
 //   gp_image_conv_k4s2_wgrad: dw[m][j] += sum_px dense[px][m] * col[px][j]                col tile = MN-major B operand
-//                             (the SAME bytes in shared memory: a 128-byte row per pixel is the contiguous dimension
-//                              of both views)
+//   gp_image_convt_k4s2_fwd : img = act(bias[c] + col2im(x * w))                          col values stay in TMEM / registers
 //   col[px = (n, oh, ow)][j = (c*4 + kh)*4 + kw] = img[n, c, 2oh-1+kh, 2ow-1+kw] * (mul ? 1 - mul[same]^2 : 1)
 //
-// They are HBM-bound (K = 48): per 128-pixel tile the forward reads 7.7 KB of image and writes 16 KB (32 KB with a
-// companion tensor); the round trip of the 128-byte-per-pixel column buffer (written by im2col, re-read by the K = 64
-// GEMM and again by wgrad) is gone. Several small CTAs (128 threads, 36-60 KB of shared memory, 64 TMEM columns) share
-// an SM so that one CTA's image loads overlap another's MMA and stores; within a CTA the next tile's image rows are
-// prefetched into registers while the current tile is processed.
+// All three are HBM-bound (K = 48); what they must avoid is instruction work per byte, so every bulk transfer is a TMA
+// copy and the threads only convert:
+//   * the image rows of a 128-pixel tile arrive as ONE cp.async.bulk.tensor.3d box (Wi + 8 columns from column -4, 2R + 2
+//     rows from row 2*oh0 - 1, 3 channels): padding = TMA out-of-bounds zero fill, so the tile builder has no bounds checks —
+//     per pixel 36 loads, fp32 -> bf16 (or hi/lo pair, or fp16), 6 x STS.128 into the 128-byte-swizzled UMMA layout;
+//   * forward: the bias rides in the MMA (column 48/49 of the K = 64 tile are the constant 1, the weight tile holds the bias
+//     split over them), the epilogue is tcgen05.ld -> LeakyReLU -> pack -> swizzled shared memory -> per-warp TMA STORE
+//     (cp.async.bulk.tensor.2d.global.shared::cta, a ring of two 4 KB slots per warp);
+//   * wgrad: dy tiles arrive by TMA straight in the MN-major operand layout, 3-4 stages deep, one persistent CTA per SM
+//     accumulating dW (and, through a constant-1 column, the bias gradient) in TMEM, flushed once with vector reductions;
+//   * transposed direction: x tiles (128 pixels + one halo row above and below, in the second M = 128 half) arrive by TMA,
+//     the 48 column values of a pixel are read from TMEM by the thread that owns the pixel, horizontal neighbours come by
+//     warp shuffle, vertical neighbours through 9 KB of shared memory, and every thread writes its 2x2x3 output patch.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cudaTypedefs.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.h"
 #include "act_io.cuh"
@@ -28,180 +36,312 @@
 namespace gp {
 
 constexpr int kEdgeThreads = 128;
-constexpr int kEdgePatchFloats = 3072;  // ch * (2R + 2) * Wi <= 3 * (512 + 4 * Wo), Wo <= 128
-constexpr int kEdgePatchVec = kEdgePatchFloats / 4 / kEdgeThreads;  // float4 per thread
-constexpr int kEdgeMaxDenseVec = 16;  // 128 pixels x (M <= 128 channels) bf16 = 2048 16-byte chunks / 128 threads
 
-struct ImageEdgeParams {
-  const float* img;
-  const float* mul;
-  // forward
-  const float* w;     // fp32 [N][ch*16] (torch layout of Conv2d / ConvTranspose2d weights with the image on the ch side)
-  const float* bias;  // fp32 [N] or null
-  __nv_bfloat16* out;
-  void* out_comp;
-  int comp_fmt;
-  float slope;
-  // weight gradient
-  const __nv_bfloat16* dense;
-  float* dw;     // fp32 [M][ch*16], accumulated
-  float* dbias;  // fp32 [M] or null, accumulated (column sums of dense)
-  int NB, Hi, Wi, N;  // N: forward output channels / wgrad dense channels (M)
-  int tiles;
-  int tmem_cols;
-};
+// ------------------------------------------------------------------------------------------------ tensor maps (host)
+static PFN_cuTensorMapEncodeTiled_v12000 edge_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
 
-// geometry of a 128-pixel tile: R = 128 / Wo whole output rows of one image
+// fp32 NCHW image seen as (Wi, Hi, ch * NB); box (Wi + 8, rows, ch), no swizzle. Loaded from (-4, 2*oh0 - 1, n*ch): the
+// innermost start coordinate of a tiled TMA load must be a multiple of 16 bytes (measured on the B200 with
+// tools/probe/tma_probe.cu: start -1 is an illegal instruction, -4 loads with the left columns zero-filled).
+static int make_map_image(CUtensorMap* m, const float* base, int NB, int ch, int Hi, int Wi, int rows) {
+  auto fn = edge_encode_fn();
+  if (fn == nullptr) return set_error(GP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(GP_ERR_INVALID, "image base not 16-byte aligned");
+  cuuint64_t dims[3] = {(cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)ch * NB};
+  cuuint64_t strides[2] = {(cuuint64_t)Wi * 4, (cuuint64_t)Hi * Wi * 4};
+  cuuint32_t box[3] = {(cuuint32_t)(Wi + 8), (cuuint32_t)rows, (cuuint32_t)ch};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(GP_ERR_CUDA, "cuTensorMapEncodeTiled(image %dx%dx%dx%d, %d rows) failed: %d", NB, ch, Hi, Wi, rows, (int)r);
+  return GP_OK;
+}
+
+// 2-byte row-major matrix [P][C]; box (64 columns, box_rows), 128-byte swizzle (loads and stores)
+static int make_map_rows(CUtensorMap* m, const void* base, long long P, int C, int box_rows) {
+  auto fn = edge_encode_fn();
+  if (fn == nullptr) return set_error(GP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(GP_ERR_INVALID, "activation base not 16-byte aligned");
+  cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)P};
+  cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(GP_ERR_CUDA, "cuTensorMapEncodeTiled(rows P=%lld C=%d) failed: %d", P, C, (int)r);
+  return GP_OK;
+}
+
+// 2-byte NHWC (C, W, H, N); box (64 channels, W, bh rows, 1 image), 128-byte swizzle; rows outside the image are zero
+static int make_map_nhwc_rows(CUtensorMap* m, const void* base, int C, int W, int H, int N, int bh) {
+  auto fn = edge_encode_fn();
+  if (fn == nullptr) return set_error(GP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(GP_ERR_INVALID, "activation base not 16-byte aligned");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)W, (cuuint32_t)bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(GP_ERR_CUDA, "cuTensorMapEncodeTiled(nhwc C=%d W=%d H=%d N=%d rows=%d) failed: %d", C, W, H, N, bh, (int)r);
+  return GP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ shared device pieces
+// geometry of a 128-pixel tile: R = 128 / Wo whole output rows of one image; its image patch is [3][2R + 2][Wi + 8] fp32,
+// patch column q = image column q - 4
 struct EdgeGeom {
-  int Ho, Wo, R, rows_in, w4;
+  int Wi, Wo, R, tiles, tiles_per_img;
+  int pitch_b;       // bytes of one patch row: (Wi + 8) * 4
+  int chan_b;        // bytes of one channel of the patch: (2R + 2) * pitch_b
+  int patch_bytes;   // 3 * chan_b: the TMA transaction size
+  int patch_stride;  // patch_bytes rounded up to 128
 };
-__device__ __forceinline__ EdgeGeom edge_geom(const ImageEdgeParams& p) {
+
+static EdgeGeom make_geom(int NB, int Hi, int Wi) {
   EdgeGeom g;
-  g.Ho = p.Hi / 2;
-  g.Wo = p.Wi / 2;
+  g.Wi = Wi, g.Wo = Wi / 2;
   g.R = 128 / g.Wo;
-  g.rows_in = 2 * g.R + 2;
-  g.w4 = p.Wi / 4;
+  g.tiles_per_img = (Hi / 2) * g.Wo / 128;
+  g.tiles = NB * g.tiles_per_img;
+  g.pitch_b = (Wi + 8) * 4;
+  g.chan_b = (2 * g.R + 2) * g.pitch_b;
+  g.patch_bytes = 3 * g.chan_b;
+  g.patch_stride = (g.patch_bytes + 127) & ~127;
   return g;
 }
 
-// the tile's 2R + 2 input rows of every channel -> registers (zero above / below the image), tanh' fused when mul != null.
-// Element i of the flattened [ch][rows_in][Wi / 4] patch goes to thread i % 128.
-template <int CH>
-__device__ __forceinline__ void patch_fetch(const ImageEdgeParams& p, const EdgeGeom& g, int tile, float4 (&pre)[kEdgePatchVec]) {
-  const long long pix0 = (long long)tile * 128;
-  const int n = (int)(pix0 / (g.Ho * g.Wo));
-  const int oh0 = (int)(pix0 % (g.Ho * g.Wo)) / g.Wo;
-  const int total = CH * g.rows_in * g.w4;
-#pragma unroll
-  for (int k = 0; k < kEdgePatchVec; ++k) {
-    const int i = k * kEdgeThreads + threadIdx.x;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < total) {
-      const int q = i % g.w4, rr = (i / g.w4) % g.rows_in, c = i / (g.w4 * g.rows_in);
-      const int ih = 2 * oh0 - 1 + rr;
-      if (ih >= 0 && ih < p.Hi) {
-        const long long off = (((long long)n * CH + c) * p.Hi + ih) * p.Wi + 4 * q;
-        v = __ldg(reinterpret_cast<const float4*>(p.img + off));
-        if (p.mul != nullptr) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(p.mul + off));
-          v.x *= 1.f - t.x * t.x, v.y *= 1.f - t.y * t.y, v.z *= 1.f - t.z * t.z, v.w *= 1.f - t.w * t.w;
-        }
-      }
-    }
-    pre[k] = v;
-  }
+__device__ __forceinline__ float2 lds_f32x2(uint32_t saddr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
+  return v;
 }
-template <int CH>
-__device__ __forceinline__ void patch_store(const EdgeGeom& g, float* s_patch, const float4 (&pre)[kEdgePatchVec]) {
-  const int total = CH * g.rows_in * g.w4;
-#pragma unroll
-  for (int k = 0; k < kEdgePatchVec; ++k) {
-    const int i = k * kEdgeThreads + threadIdx.x;
-    if (i < total) *reinterpret_cast<float4*>(s_patch + 4 * i) = pre[k];
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_u32x4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts_u32x4(uint32_t saddr, const uint4& v) { sts_u32x4(saddr, v.x, v.y, v.z, v.w); }
+
+// Bounded barrier wait that names itself: with GP_EDGE_DEBUG=1 the library maps a small pinned host buffer into every
+// launch and a wait that times out (1 s) records (code, block, thread, parity, aux) there before trapping.
+__device__ __noinline__ void edge_wait_timeout(unsigned int* dbg, uint32_t code, uint32_t parity, uint32_t aux) {
+  if (dbg != nullptr) {
+    dbg[1] = blockIdx.x, dbg[2] = threadIdx.x, dbg[3] = parity, dbg[4] = aux;
+    __threadfence_system();
+    dbg[0] = code;
+    __threadfence_system();
+  }
+  asm volatile("trap;");
+}
+__device__ __forceinline__ void edge_wait(uint64_t* bar, uint32_t parity, unsigned int* dbg, uint32_t code, uint32_t aux = 0) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > 1000000000ull) edge_wait_timeout(dbg, code, parity, aux);
   }
 }
 
-// Row r (one output pixel) of the column tile: 2 * CH 16-byte groups of 8 columns, group gi at byte
-// r * 128 + ((gi ^ (r & 7)) << 4) — the SWIZZLE_128B pattern TMA would produce for a {64 elements, 128 rows} box.
+// issue the patch load(s) of one tile; the caller has armed `bar` with the transaction bytes
+__device__ __forceinline__ void patch_load(const EdgeGeom& g, const CUtensorMap* map, uint32_t dst, uint64_t* bar, int tile) {
+  const int n = tile / g.tiles_per_img;
+  const int oh0 = (tile - n * g.tiles_per_img) * g.R;
+  tma_load_3d(dst, map, bar, -4, 2 * oh0 - 1, n * 3);
+}
+
+// Row r (one output pixel) of the column tile: six 16-byte groups of 8 columns, group gi at byte
+// r * 128 + ((gi ^ (r & 7)) << 4) — the SWIZZLE_128B pattern of a {64 elements, 128 rows} box. Groups 6 and 7 (columns
+// 48..63) are written once by the kernels (constants) and never touched here.
 // FMT: GP_COMP_NONE -> bf16 into t_hi; GP_COMP_LO -> bf16 hi into t_hi and bf16(v - hi) into t_lo; GP_COMP_F16 -> fp16 into t_hi.
-template <int CH, int FMT>
-__device__ __forceinline__ void build_col_row(const EdgeGeom& g, int Wi, const float* s_patch, int r, uint32_t t_hi, uint32_t t_lo) {
-  const int ol = r / g.Wo, ow = r % g.Wo;
+// row_off: byte offset of patch element (row 2*ol, column 2*ow + 3) = image (2*(oh0+ol) - 1, 2*ow - 1); the four taps of a
+// row are read as 4 + 8 + 4 bytes (the middle pair is 8-byte aligned).
+template <int FMT, bool MUL>
+__device__ __forceinline__ void build_col_row(const EdgeGeom& g, uint32_t patch, uint32_t mpatch, uint32_t row_off, int r,
+                                              uint32_t t_hi, uint32_t t_lo) {
 #pragma unroll
-  for (int gi = 0; gi < 2 * CH; ++gi) {
-    const int c = gi >> 1;
+  for (int gi = 0; gi < 6; ++gi) {
+    const uint32_t rel = (uint32_t)(gi >> 1) * g.chan_b + (uint32_t)((gi & 1) * 2) * g.pitch_b + row_off;
     float f[8];
+    {
+      const uint32_t a = patch + rel, a2 = a + g.pitch_b;
+      const float2 m0 = lds_f32x2(a + 4), m1 = lds_f32x2(a2 + 4);
+      f[0] = lds_f32(a), f[1] = m0.x, f[2] = m0.y, f[3] = lds_f32(a + 12);
+      f[4] = lds_f32(a2), f[5] = m1.x, f[6] = m1.y, f[7] = lds_f32(a2 + 12);
+    }
+    if (MUL) {
+      const uint32_t a = mpatch + rel, a2 = a + g.pitch_b;
+      const float2 m0 = lds_f32x2(a + 4), m1 = lds_f32x2(a2 + 4);
+      const float t[8] = {lds_f32(a), m0.x, m0.y, lds_f32(a + 12), lds_f32(a2), m1.x, m1.y, lds_f32(a2 + 12)};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int kh = (gi & 1) * 2 + (j >> 2), kw = j & 3;
-      const int iw = 2 * ow - 1 + kw;
-      f[j] = (iw >= 0 && iw < Wi) ? s_patch[(c * g.rows_in + 2 * ol + kh) * Wi + iw] : 0.f;
+      for (int j = 0; j < 8; ++j) f[j] *= fmaf(-t[j], t[j], 1.f);
     }
     const Packed8c pk = pack8c(FMT, f);
     const uint32_t off = (uint32_t)r * 128u + (uint32_t)((gi ^ (r & 7)) << 4);
     if (FMT == GP_COMP_F16) {
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t_hi + off), "r"(pk.comp.x), "r"(pk.comp.y), "r"(pk.comp.z), "r"(pk.comp.w) : "memory");
+      sts_u32x4(t_hi + off, pk.comp);
     } else {
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t_hi + off), "r"(pk.hi.x), "r"(pk.hi.y), "r"(pk.hi.z), "r"(pk.hi.w) : "memory");
-      if (FMT == GP_COMP_LO)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(t_lo + off), "r"(pk.comp.x), "r"(pk.comp.y), "r"(pk.comp.z), "r"(pk.comp.w) : "memory");
+      sts_u32x4(t_hi + off, pk.hi);
+      if (FMT == GP_COMP_LO) sts_u32x4(t_lo + off, pk.comp);
     }
   }
 }
 
+__device__ __forceinline__ uint32_t bf16_bits(float v) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ float bf16_val(uint32_t b) { return __uint_as_float(b << 16); }
+
 // ------------------------------------------------------------------------------------------------ forward
-// shared memory: [A hi 16 KB | A lo 16 KB (bf16x3) | B hi Npad*128 | B lo (bf16x3) | patch 12 KB | bias | store staging 8 KB | barrier]
-template <int CH, int FMT>
-__global__ void __launch_bounds__(kEdgeThreads, 4) image_conv_fwd_kernel(const __grid_constant__ ImageEdgeParams p) {
+struct EdgeFwdParams {
+  CUtensorMap map_img, map_mul, map_out, map_comp;
+  const float* w;     // fp32 [N][48] (torch layout of Conv2d / ConvTranspose2d weights with the image on the 3-channel side)
+  const float* bias;  // fp32 [N] or null
+  float slope;
+  int N;  // 64 or 128
+  EdgeGeom g;
+  unsigned int* dbg;
+};
+
+// shared memory: [A hi 16 KB | A lo 16 KB (bf16x3) | B hi N*128 | B lo (bf16x3) | store ring 4 warps x 2 x 4 KB |
+//                 patch (| mul patch) | 2 barriers | TMEM slot]
+template <int FMT, bool MUL>
+__global__ void __launch_bounds__(kEdgeThreads) image_conv_fwd_kernel(const __grid_constant__ EdgeFwdParams p) {
   constexpr bool X3 = FMT == GP_COMP_LO;
+  constexpr bool COMP = FMT != GP_COMP_NONE;
+  constexpr int HALVES = X3 ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int Npad = (p.N + 15) & ~15;
-  const int bbytes = Npad * 128;
+  const EdgeGeom g = p.g;
+  const int N = p.N;
+  const int bbytes = N * 128;
   uint8_t* sA = smem;
-  uint8_t* sB = sA + (X3 ? 2 : 1) * 16384;
-  float* s_patch = reinterpret_cast<float*>(sB + (X3 ? 2 : 1) * bbytes);
-  float* s_bias = s_patch + kEdgePatchFloats;
-  uint8_t* s_store = reinterpret_cast<uint8_t*>(s_bias + 160);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(s_store + 8192);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint8_t* sB = sA + HALVES * 16384;
+  uint8_t* sStage = sB + HALVES * bbytes;
+  uint8_t* sPatch = sStage + 32768;
+  uint64_t* bar_patch = reinterpret_cast<uint64_t*>(sPatch + (MUL ? 2 : 1) * g.patch_stride);
+  uint64_t* bar_mma = bar_patch + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const EdgeGeom g = edge_geom(p);
-
-  float4 pre[kEdgePatchVec];
-  int tile = blockIdx.x;
-  if (tile < p.tiles) patch_fetch<CH>(p, g, tile, pre);
+  const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + 16384, b_hi = smem_u32(sB), b_lo = b_hi + (uint32_t)bbytes;
+  const uint32_t patch = smem_u32(sPatch), mpatch = patch + (uint32_t)g.patch_stride;
+  const uint32_t tx_bytes = (uint32_t)g.patch_bytes * (MUL ? 2u : 1u);
 
   if (tid == 0) {
-    mbar_init(bar, 1);
+    tma_prefetch_desc(&p.map_img);
+    tma_prefetch_desc(&p.map_out);
+    if (MUL) tma_prefetch_desc(&p.map_mul);
+    if (COMP) tma_prefetch_desc(&p.map_comp);
+    mbar_init(bar_patch, 1);
+    mbar_init(bar_mma, 1);
     fence_mbar_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_alloc(tmem_slot, (uint32_t)N);
     tmem_relinquish();
   }
-  // weights -> B tile(s): row n = 128 bytes (K = CH*16 live elements), swizzled like the A rows; rows >= N are zero
-  for (int n = tid; n < Npad; n += kEdgeThreads) {
-#pragma unroll
-    for (int gi = 0; gi < 2 * CH; ++gi) {
-      float f[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = n < p.N ? __ldg(p.w + (long long)n * (CH * 16) + gi * 8 + j) : 0.f;
-      const Packed8c pk = pack8c(FMT, f);
-      uint8_t* d = sB + n * 128 + ((gi ^ (n & 7)) << 4);
-      *reinterpret_cast<uint4*>(d) = FMT == GP_COMP_F16 ? pk.comp : pk.hi;
-      if (X3) *reinterpret_cast<uint4*>(d + bbytes) = pk.comp;
-    }
-  }
-  for (int i = tid; i < 160; i += kEdgeThreads) s_bias[i] = (p.bias != nullptr && i < p.N) ? __ldg(p.bias + i) : 0.f;
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  int tile = blockIdx.x;
+  if (tid == 0 && tile < g.tiles) {
+    mbar_expect_tx(bar_patch, tx_bytes);
+    patch_load(g, &p.map_img, patch, bar_patch, tile);
+    if (MUL) patch_load(g, &p.map_mul, mpatch, bar_patch, tile);
+  }
 
-  const uint32_t idesc = make_idesc_bf16(kBlockM, Npad, 0, 0) & ~(FMT == GP_COMP_F16 ? ((1u << 7) | (1u << 10)) : 0u);
+  // constant columns 48..63 of the A tile: (1, 1, 0, ...) in the hi half — they multiply the bias columns of B
+  {
+    const uint32_t one2 = FMT == GP_COMP_F16 ? 0x3C003C00u : 0x3F803F80u;
+    const uint32_t o6 = (uint32_t)tid * 128u + (uint32_t)((6 ^ (tid & 7)) << 4), o7 = (uint32_t)tid * 128u + (uint32_t)((7 ^ (tid & 7)) << 4);
+    sts_u32x4(a_hi + o6, one2, 0u, 0u, 0u);
+    sts_u32x4(a_hi + o7, 0u, 0u, 0u, 0u);
+    if (X3) {
+      sts_u32x4(a_lo + o6, 0u, 0u, 0u, 0u);
+      sts_u32x4(a_lo + o7, 0u, 0u, 0u, 0u);
+    }
+  }
+  // weights -> B tile(s): row n = 128 bytes, swizzled like the A rows; columns 48 / 49 carry the bias split into two
+  // (bf16x3: three) terms, so that 1 * b1 + 1 * b2 (+ 1 * b3) reproduces it to 16 (24) bits in the fp32 accumulator
+  for (int n = tid; n < N; n += kEdgeThreads) {
+    const uint32_t rowb = (uint32_t)n * 128u;
+#pragma unroll
+    for (int gi = 0; gi < 6; ++gi) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w + (long long)n * 48 + gi * 8));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w + (long long)n * 48 + gi * 8 + 4));
+      const float f[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const Packed8c pk = pack8c(FMT, f);
+      const uint32_t off = rowb + (uint32_t)((gi ^ (n & 7)) << 4);
+      sts_u32x4(b_hi + off, FMT == GP_COMP_F16 ? pk.comp : pk.hi);
+      if (X3) sts_u32x4(b_lo + off, pk.comp);
+    }
+    const float b = p.bias != nullptr ? __ldg(p.bias + n) : 0.f;
+    uint32_t w_hi, w_lo = 0u;
+    if (FMT == GP_COMP_F16) {
+      const __half h1 = __float2half_rn(b);
+      const __half h2 = __float2half_rn(b - __half2float(h1));
+      w_hi = (uint32_t)__half_as_ushort(h1) | ((uint32_t)__half_as_ushort(h2) << 16);
+    } else {
+      const uint32_t b1 = bf16_bits(b);
+      const uint32_t b2 = bf16_bits(b - bf16_val(b1));
+      w_hi = b1 | (b2 << 16);
+      if (X3) w_lo = bf16_bits(b - bf16_val(b1) - bf16_val(b2));
+    }
+    const uint32_t o6 = rowb + (uint32_t)((6 ^ (n & 7)) << 4), o7 = rowb + (uint32_t)((7 ^ (n & 7)) << 4);
+    sts_u32x4(b_hi + o6, w_hi, 0u, 0u, 0u);
+    sts_u32x4(b_hi + o7, 0u, 0u, 0u, 0u);
+    if (X3) {
+      sts_u32x4(b_lo + o6, w_lo, 0u, 0u, 0u);
+      sts_u32x4(b_lo + o7, 0u, 0u, 0u, 0u);
+    }
+  }
+
+  const uint32_t idesc = make_idesc_bf16(kBlockM, N, 0, 0) & ~(FMT == GP_COMP_F16 ? ((1u << 7) | (1u << 10)) : 0u);
   constexpr uint64_t dbase = make_smem_desc_base(0, 1024);
-  const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + 16384, b_hi = smem_u32(sB), b_lo = b_hi + (uint32_t)bbytes;
   const float slope = p.slope;
-  const int nch = (p.N + 31) / 32;
-  uint32_t phase = 0;
+  const int nh = N / 64;
+  const uint32_t row_off = (uint32_t)(2 * (tid / g.Wo)) * g.pitch_b + (uint32_t)(2 * (tid % g.Wo) + 3) * 4u;
+  const uint32_t stage_w = smem_u32(sStage) + (uint32_t)warp * 8192u;
+  const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t srow = (uint32_t)lane * 128u;
+  const int sw = lane & 7;
+  uint32_t ph_patch = 0, ph_mma = 0, sidx = 0;
 
-  for (; tile < p.tiles; tile += gridDim.x) {
-    patch_store<CH>(g, s_patch, pre);
-    __syncthreads();
-    const int next = tile + gridDim.x;
-    if (next < p.tiles) patch_fetch<CH>(p, g, next, pre);  // in flight during the MMA and the epilogue
-    build_col_row<CH, FMT>(g, p.Wi, s_patch, tid, a_hi, a_lo);
+  for (; tile < g.tiles; tile += gridDim.x) {
+    edge_wait(bar_patch, ph_patch, p.dbg, 1, (uint32_t)tile);
+    ph_patch ^= 1;
+    build_col_row<FMT, MUL>(g, patch, mpatch, row_off, tid, a_hi, a_lo);
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
+    __syncthreads();  // the A tile (and, the first time, B) is complete; the patch is consumed; TMEM has been drained
     if (tid == 0) {
+      const int next = tile + gridDim.x;
+      if (next < g.tiles) {  // lands during the MMA and the epilogue
+        mbar_expect_tx(bar_patch, tx_bytes);
+        patch_load(g, &p.map_img, patch, bar_patch, next);
+        if (MUL) patch_load(g, &p.map_mul, mpatch, bar_patch, next);
+      }
       tc_fence_after();
 #pragma unroll
-      for (int k = 0; k < CH; ++k) {  // K = CH * 16
+      for (int k = 0; k < 4; ++k) {  // K = 64: 48 image taps + the bias columns
         const uint64_t ah = smem_desc(dbase, a_hi + k * 32), bh = smem_desc(dbase, b_hi + k * 32);
         umma_bf16(tmem_base, ah, bh, idesc, k != 0);
         if (X3) {
@@ -209,136 +349,153 @@ __global__ void __launch_bounds__(kEdgeThreads, 4) image_conv_fwd_kernel(const _
           umma_bf16(tmem_base, ah, smem_desc(dbase, b_lo + k * 32), idesc, 1u);
         }
       }
-      umma_commit(bar);
+      umma_commit(bar_mma);
     }
-    mbar_wait(bar, phase);
-    phase ^= 1;
+    edge_wait(bar_mma, ph_mma, p.dbg, 2, (uint32_t)tile);
+    ph_mma ^= 1;
     tc_fence_after();
-    // epilogue: thread = pixel row; 32-column chunks
-    const long long row_off = ((long long)tile * 128 + tid) * p.N;
-    const uint32_t stage = smem_u32(s_store) + warp * 2048;
+    // epilogue: thread = pixel row; 64 columns at a time -> this warp's 32-row box in shared memory -> TMA store
+    const int row0 = tile * 128 + warp * 32;
 #pragma unroll 1
-    for (int c = 0; c < nch; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, r);
-      tmem_ld_wait_regs(r);
-      float v[32];
+    for (int h = 0; h < nh; ++h) {
+      uint32_t ra[32], rb[32];
+      tmem_ld_32x32(trow + h * 64, ra);
+      tmem_ld_32x32(trow + h * 64 + 32, rb);
+      tmem_ld_wait_regs(ra);
+      tmem_ld_wait_regs(rb);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float x = __uint_as_float(r[j]) + s_bias[c * 32 + j];
-        v[j] = fmaxf(x, slope * x);
+        const float xa = __uint_as_float(ra[j]), xb = __uint_as_float(rb[j]);
+        ra[j] = __float_as_uint(fmaxf(xa, slope * xa));
+        rb[j] = __float_as_uint(fmaxf(xb, slope * xb));
       }
-      const int col0 = c * 32;
-      const int lim = (p.N - col0 + 7) / 8;
-      uint32_t w32[16];
+      uint32_t hw[32];  // bf16 pairs of the 64 columns
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        const __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-        w32[e] = *reinterpret_cast<const uint32_t*>(&b2);
+        const __nv_bfloat162 pa = __floats2bfloat162_rn(__uint_as_float(ra[2 * e]), __uint_as_float(ra[2 * e + 1]));
+        const __nv_bfloat162 pb = __floats2bfloat162_rn(__uint_as_float(rb[2 * e]), __uint_as_float(rb[2 * e + 1]));
+        hw[e] = *reinterpret_cast<const uint32_t*>(&pa);
+        hw[16 + e] = *reinterpret_cast<const uint32_t*>(&pb);
       }
       {
-        uint4 seg[4];
+        const uint32_t slot = stage_w + (sidx & 1u) * 4096u;
+        ++sidx;
+        if (lane == 0) bulk_wait_read<1>();  // the store that used this slot two groups ago has read it
+        __syncwarp();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) seg[q] = make_uint4(w32[4 * q], w32[4 * q + 1], w32[4 * q + 2], w32[4 * q + 3]);
-        store_rows_coalesced(stage, seg, reinterpret_cast<uint8_t*>(p.out + col0), row_off * 2, true, lim, lane);
+        for (int q = 0; q < 8; ++q) sts_u32x4(slot + srow + (uint32_t)((q ^ sw) << 4), hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&p.map_out, slot, h * 64, row0);
+          bulk_commit();
+        }
       }
-      if (p.out_comp != nullptr) {
-        if (p.comp_fmt == GP_COMP_F16) {
+      if (COMP) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const __half2 h2 = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-            w32[e] = *reinterpret_cast<const uint32_t*>(&h2);
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w32[e]));
-            const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
-            w32[e] = *reinterpret_cast<const uint32_t*>(&l2);
+        for (int e = 0; e < 16; ++e) {
+          if (FMT == GP_COMP_F16) {
+            const __half2 pa = __floats2half2_rn(__uint_as_float(ra[2 * e]), __uint_as_float(ra[2 * e + 1]));
+            const __half2 pb = __floats2half2_rn(__uint_as_float(rb[2 * e]), __uint_as_float(rb[2 * e + 1]));
+            hw[e] = *reinterpret_cast<const uint32_t*>(&pa);
+            hw[16 + e] = *reinterpret_cast<const uint32_t*>(&pb);
+          } else {
+            const float2 fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[e]));
+            const float2 fb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[16 + e]));
+            const __nv_bfloat162 pa = __floats2bfloat162_rn(__uint_as_float(ra[2 * e]) - fa.x, __uint_as_float(ra[2 * e + 1]) - fa.y);
+            const __nv_bfloat162 pb = __floats2bfloat162_rn(__uint_as_float(rb[2 * e]) - fb.x, __uint_as_float(rb[2 * e + 1]) - fb.y);
+            hw[e] = *reinterpret_cast<const uint32_t*>(&pa);
+            hw[16 + e] = *reinterpret_cast<const uint32_t*>(&pb);
           }
         }
-        uint4 seg[4];
+        const uint32_t slot = stage_w + (sidx & 1u) * 4096u;
+        ++sidx;
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) seg[q] = make_uint4(w32[4 * q], w32[4 * q + 1], w32[4 * q + 2], w32[4 * q + 3]);
-        store_rows_coalesced(stage, seg, reinterpret_cast<uint8_t*>(static_cast<uint16_t*>(p.out_comp) + col0), row_off * 2, true,
-                             lim, lane);
+        for (int q = 0; q < 8; ++q) sts_u32x4(slot + srow + (uint32_t)((q ^ sw) << 4), hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&p.map_comp, slot, h * 64, row0);
+          bulk_commit();
+        }
       }
     }
-    tc_fence_before();
-    __syncthreads();  // TMEM, the A tile and the patch are free for the next tile
   }
 
+  if (lane == 0) bulk_wait_read<0>();  // the ring must outlive the stores that read it
+  tc_fence_before();
+  __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    tmem_dealloc(tmem_base, (uint32_t)N);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ weight gradient
-// shared memory: [A = dense tile, MN-major: 2 x (128 pixel rows x 128 B) = 32 KB | B = column tile 16 KB | patch 12 KB | barrier]
-// Every CTA accumulates its share of the pixel tiles into ONE 128 x 64 fp32 accumulator in TMEM and adds it to dw once.
-// Column CH*16 of the tile is the constant 1 (when a bias gradient is wanted), so accumulator column CH*16 = sum_px dense.
-template <int CH>
-__global__ void __launch_bounds__(kEdgeThreads, 3) image_conv_wgrad_kernel(const __grid_constant__ ImageEdgeParams p) {
+struct EdgeWgradParams {
+  CUtensorMap map_img, map_mul, map_dense;
+  float* dw;     // fp32 [M][48], accumulated
+  float* dbias;  // fp32 [M] or null, accumulated (column sums of dense)
+  int M;         // 64 or 128
+  EdgeGeom g;
+  unsigned int* dbg;
+};
+
+// shared memory: [STAGES x dense tile (MN-major A: 2 x 128 pixel rows x 128 B = 32 KB) | 2 x column tile (B, 16 KB) |
+//                 STAGES x patch (| mul patch) | barriers | TMEM slot]
+// One persistent CTA per SM walks a contiguous range of tiles: TMA keeps STAGES - 1 tiles in flight, the 128 threads only
+// build the column tile, one thread issues the 8 MMAs (K = the tile's 128 pixels) into ONE 128 x 64 fp32 accumulator in
+// TMEM, which is added to dw once at the end. Column 48 of the column tile is the constant 1 when a bias gradient is
+// wanted, so accumulator column 48 = sum_px dense.
+template <bool MUL, int STAGES>
+__global__ void __launch_bounds__(kEdgeThreads, 1) image_conv_wgrad_kernel(const __grid_constant__ EdgeWgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const EdgeGeom g = p.g;
+  constexpr int NP = MUL ? 2 : 1;
   uint8_t* sA = smem;
-  uint8_t* sB = sA + 32768;
-  float* s_patch = reinterpret_cast<float*>(sB + 16384);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(s_patch + kEdgePatchFloats);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint8_t* sB = sA + STAGES * 32768;
+  uint8_t* sPatch = sB + 2 * 16384;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(sPatch + STAGES * NP * g.patch_stride);
+  uint64_t* bar_done = bar_full + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_done + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const EdgeGeom g = edge_geom(p);
-  const int M = p.N;
-  const int cpr = M / 8;  // 16-byte chunks per dense row
-  const bool want_db = p.dbias != nullptr && CH < 4;
-  const int ncols = CH * 16 + (want_db ? 16 : 0);
+  const int M = p.M;
+  const int nchunk = M / 64;
+  const bool want_db = p.dbias != nullptr;
 
   // contiguous range of tiles for this CTA
-  const int per = (p.tiles + gridDim.x - 1) / gridDim.x;
-  const int t0 = blockIdx.x * per, t1 = min(t0 + per, p.tiles);
-
-  float4 pre[kEdgePatchVec];
-  uint4 dpre[kEdgeMaxDenseVec];
-  auto dense_fetch = [&](int tile) {
-    const uint4* src = reinterpret_cast<const uint4*>(p.dense + (long long)tile * 128 * M);
-#pragma unroll
-    for (int k = 0; k < kEdgeMaxDenseVec; ++k) {
-      const int i = k * kEdgeThreads + tid;
-      if (i < 128 * cpr) dpre[k] = __ldg(src + i);
-    }
-  };
-  auto dense_store = [&]() {
-#pragma unroll
-    for (int k = 0; k < kEdgeMaxDenseVec; ++k) {
-      const int i = k * kEdgeThreads + tid;
-      if (i < 128 * cpr) {
-        const int px = i / cpr, j = i % cpr;
-        *reinterpret_cast<uint4*>(sA + (j >> 3) * 16384 + px * 128 + (((j & 7) ^ (px & 7)) << 4)) = dpre[k];
-      }
-    }
-  };
-  if (t0 < t1) {
-    patch_fetch<CH>(p, g, t0, pre);
-    dense_fetch(t0);
-  }
+  const int per = (g.tiles + gridDim.x - 1) / gridDim.x;
+  const int t0 = blockIdx.x * per;
+  const int n = max(0, min(t0 + per, g.tiles) - t0);
 
   if (tid == 0) {
-    mbar_init(bar, 1);
+    tma_prefetch_desc(&p.map_img);
+    tma_prefetch_desc(&p.map_dense);
+    if (MUL) tma_prefetch_desc(&p.map_mul);
+    for (int s = 0; s < STAGES; ++s) mbar_init(bar_full + s, 1);
+    mbar_init(bar_done, 1);
+    mbar_init(bar_done + 1, 1);
     fence_mbar_init();
   }
   if (warp == 0) {
     tmem_alloc(tmem_slot, 64);
     tmem_relinquish();
   }
-  // zero the operand tiles once: dense channels beyond M and the padding columns of the column tile stay zero;
-  // the constant-1 column of the bias gradient is written once as well (the tile builder never touches those groups)
-  for (int i = tid; i < (32768 + 16384) / 16; i += kEdgeThreads) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
-  __syncthreads();
-  if (want_db) {
-    const int r = tid;  // pixel row; group 2*CH holds columns CH*16 .. CH*16+7: (1, 0, 0, ...) in bf16
-    *reinterpret_cast<uint4*>(sB + r * 128 + (((2 * CH) ^ (r & 7)) << 4)) = make_uint4(0x00003F80u, 0u, 0u, 0u);
+  // dense channels beyond M stay zero; columns 48..63 of both column tiles are constants
+  if (nchunk < 2)
+    for (int s = 0; s < STAGES; ++s)
+      for (int i = tid; i < 16384 / 16; i += kEdgeThreads) reinterpret_cast<uint4*>(sA + s * 32768 + 16384)[i] = make_uint4(0u, 0u, 0u, 0u);
+  const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB), patch0 = smem_u32(sPatch);
+  {
+    const uint32_t o6 = (uint32_t)tid * 128u + (uint32_t)((6 ^ (tid & 7)) << 4), o7 = (uint32_t)tid * 128u + (uint32_t)((7 ^ (tid & 7)) << 4);
+    for (int b = 0; b < 2; ++b) {
+      sts_u32x4(b_addr + b * 16384 + o6, want_db ? 0x00003F80u : 0u, 0u, 0u, 0u);
+      sts_u32x4(b_addr + b * 16384 + o7, 0u, 0u, 0u, 0u);
+    }
   }
   fence_proxy_async();
   tc_fence_before();
@@ -346,51 +503,62 @@ __global__ void __launch_bounds__(kEdgeThreads, 3) image_conv_wgrad_kernel(const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const uint32_t idesc = make_idesc_bf16(kBlockM, ncols, 1, 1);
-  constexpr uint64_t dbase = make_smem_desc_base(16384, 1024);  // MN-major: next 64-channel chunk 128 rows * 128 B further
-  const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB);
-  uint32_t phase = 0;
+  const uint32_t tx_bytes = (uint32_t)nchunk * 16384u + (uint32_t)g.patch_bytes * NP;
+  auto issue_loads = [&](int i) {  // local tile i -> stage i % STAGES
+    const int s = i % STAGES, tile = t0 + i;
+    mbar_expect_tx(bar_full + s, tx_bytes);
+    for (int c = 0; c < nchunk; ++c) tma_load_2d(sA + s * 32768 + c * 16384, &p.map_dense, bar_full + s, c * 64, tile * 128);
+    const uint32_t pd = patch0 + (uint32_t)(s * NP) * g.patch_stride;
+    patch_load(g, &p.map_img, pd, bar_full + s, tile);
+    if (MUL) patch_load(g, &p.map_mul, pd + g.patch_stride, bar_full + s, tile);
+  };
+  if (tid == 0)
+    for (int i = 0; i < STAGES - 1 && i < n; ++i) issue_loads(i);
 
-  for (int tile = t0; tile < t1; ++tile) {
-    patch_store<CH>(g, s_patch, pre);
-    dense_store();
-    __syncthreads();
-    if (tile + 1 < t1) {
-      patch_fetch<CH>(p, g, tile + 1, pre);
-      dense_fetch(tile + 1);
-    }
-    build_col_row<CH, GP_COMP_NONE>(g, p.Wi, s_patch, tid, b_addr, 0u);
+  const uint32_t idesc = make_idesc_bf16(kBlockM, 64, 1, 1);
+  constexpr uint64_t dbase = make_smem_desc_base(16384, 1024);  // MN-major: next 64-channel chunk 128 rows * 128 B further
+  const uint32_t row_off = (uint32_t)(2 * (tid / g.Wo)) * g.pitch_b + (uint32_t)(2 * (tid % g.Wo) + 3) * 4u;
+
+  for (int i = 0; i < n; ++i) {
+    const int s = i % STAGES, b = i & 1;
+    edge_wait(bar_full + s, (uint32_t)(i / STAGES) & 1u, p.dbg, 3, (uint32_t)i);
+    if (i >= 2) edge_wait(bar_done + b, (uint32_t)((i - 2) >> 1) & 1u, p.dbg, 4, (uint32_t)i);  // the MMAs of tile i - 2 have read this column tile
+    const uint32_t pd = patch0 + (uint32_t)(s * NP) * g.patch_stride;
+    build_col_row<GP_COMP_NONE, MUL>(g, pd, pd + g.patch_stride, row_off, tid, b_addr + b * 16384, 0u);
     fence_proxy_async();
-    tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
+      const uint32_t sa = a_addr + s * 32768, sb = b_addr + b * 16384;
 #pragma unroll
-      for (int k = 0; k < 128 / kUmmaK; ++k)  // K = the tile's 128 pixels
-        umma_bf16(tmem_base, smem_desc(dbase, a_addr + k * (kUmmaK * 128)), smem_desc(dbase, b_addr + k * (kUmmaK * 128)), idesc,
-                  (tile != t0 || k != 0) ? 1u : 0u);
-      umma_commit(bar);
+      for (int k = 0; k < 128 / kUmmaK; ++k)
+        umma_bf16(tmem_base, smem_desc(dbase, sa + k * (kUmmaK * 128)), smem_desc(dbase, sb + k * (kUmmaK * 128)), idesc,
+                  (i != 0 || k != 0) ? 1u : 0u);
+      umma_commit(bar_done + b);
+      const int nxt = i + STAGES - 1;  // its stage was last read by the MMAs of tile i - 1
+      if (nxt < n) {
+        if (i >= 1) edge_wait(bar_done + (b ^ 1), (uint32_t)((i - 1) >> 1) & 1u, p.dbg, 5, (uint32_t)i);
+        issue_loads(nxt);
+      }
     }
-    mbar_wait(bar, phase);  // the MMAs have read both tiles: they may be overwritten
-    phase ^= 1;
   }
 
-  if (t0 < t1) {
+  if (n > 0) {
+    edge_wait(bar_done + ((n - 1) & 1), (uint32_t)((n - 1) >> 1) & 1u, p.dbg, 6, (uint32_t)n);
     tc_fence_after();
-    const int m = tid;  // accumulator row = dense channel
-#pragma unroll 1
-    for (int c = 0; c < (ncols + 31) / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, r);
-      tmem_ld_wait_regs(r);
-      if (m < M) {
+    uint32_t ra[32], rb[32];
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    tmem_ld_32x32(trow, ra);
+    tmem_ld_32x32(trow + 32, rb);
+    tmem_ld_wait_regs(ra);
+    tmem_ld_wait_regs(rb);
+    if (tid < M) {  // accumulator row = dense channel
+      float* drow = p.dw + (long long)tid * 48;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = c * 32 + j;
-          if (col < CH * 16) atomicAdd(p.dw + (long long)m * (CH * 16) + col, __uint_as_float(r[j]));
-          else if (want_db && col == CH * 16) atomicAdd(p.dbias + m, __uint_as_float(r[j]));
-        }
-      }
+      for (int q = 0; q < 8; ++q) red_add_v4(drow + 4 * q, ra[4 * q], ra[4 * q + 1], ra[4 * q + 2], ra[4 * q + 3]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) red_add_v4(drow + 32 + 4 * q, rb[4 * q], rb[4 * q + 1], rb[4 * q + 2], rb[4 * q + 3]);
+      if (want_db) atomicAdd(p.dbias + tid, __uint_as_float(rb[16]));
     }
   }
   tc_fence_before();
@@ -404,29 +572,21 @@ __global__ void __launch_bounds__(kEdgeThreads, 3) image_conv_wgrad_kernel(const
 // ------------------------------------------------------------------------------------------------ transposed direction
 // img[n, c, oh, ow] = act(bias[c] + sum_{(ih,kh): 2ih-1+kh = oh} sum_{(iw,kw): 2iw-1+kw = ow} col[(n,ih,iw)][(c*4+kh)*4+kw]),
 // col[px][j] = sum_ci x[px][ci] * w[ci][j]           (G's last ConvTranspose2d + Tanh; the image gradient of D's first conv)
-// One CTA tile = 128 pixels of the small grid (R rows) plus one halo row above and below: (R + 2) * Ws <= 256 rows =
-// two M = 128 MMAs per K step into two 64-column TMEM accumulators; the fp32 column values never leave the SM — they
-// are exchanged through shared memory one image channel at a time (16 columns per pixel) and summed into the 2R output
-// rows this tile owns. x: K-major A tile copied with cp.async (16-byte chunks, SWIZZLE_128B by address arithmetic);
-// w: its torch layout [C][ch*16] IS the MN-major B tile (one 128-byte row per input channel).
-struct ImageConvTParams {
-  const uint16_t* x;     // 2-byte elements: bf16 (hi) or fp16
-  const uint16_t* x_lo;  // bf16x3: low halves
-  const float* w;        // fp32 [C][48]
-  const float* bias;     // fp32 [3] or null
-  float* img;            // fp32 NCHW (NB, 3, 2Hs, 2Ws)
+// One tile = 128 pixels of the small grid (R whole rows, accumulator half 0) plus the row above and the row below
+// (2 * Ws rows of accumulator half 1). Thread t owns pixel t: it reads the pixel's 48 column values from TMEM, forms the
+// horizontal pair sums with its lane neighbours (shuffles), publishes the kh = 0 / kh = 3 partial sums its vertical
+// neighbours need, and after one barrier writes the 2 x 2 x 3 output values of its pixel.
+struct EdgeConvTParams {
+  CUtensorMap map_x, map_x_halo, map_lo, map_lo_halo;
+  const float* w;     // fp32 [C][48]
+  const float* bias;  // fp32 [3] or null
+  float* img;         // fp32 NCHW (NB, 3, 2Hs, 2Ws)
   int act;
   int NB, Hs, Ws, C;
-  int tiles;
+  int tiles, tiles_per_img, R;
+  unsigned int* dbg;
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-// 32 lanes x 16 columns of fp32
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -438,49 +598,66 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "memory");
 }
 
-constexpr int kColPitch = 17;  // fp32 words per pixel in the exchange buffer (16 columns of one channel + 1: no bank conflicts)
+constexpr int kExRows = 192;  // exchange rows: 128 owned pixels + 2 * Ws halo pixels, Ws <= 32
 
-// shared memory: [A hi 2 x 16 KB | A lo 2 x 16 KB (bf16x3) | B hi 8 KB | B lo 8 KB (bf16x3) | exchange 256 x 17 fp32 | barrier]
+// shared memory: [NS slots x (A hi: C/64 chunks x 2 halves x 16 KB | A lo likewise (bf16x3)) | B hi C*128 | B lo (bf16x3) |
+//                 exchange 12 x 192 fp32 | barriers | TMEM slot]; NS = 2 (1 for bf16x3): the next tile's loads fly during the
+// epilogue, and the next tile's MMAs run into the second TMEM accumulator while this tile's is drained.
 template <int FMT>
-__global__ void __launch_bounds__(kEdgeThreads, 3) image_convt_fwd_kernel(const __grid_constant__ ImageConvTParams p) {
+__global__ void __launch_bounds__(kEdgeThreads, 1) image_convt_fwd_kernel(const __grid_constant__ EdgeConvTParams p) {
   constexpr bool X3 = FMT == GP_COMP_LO;
-  constexpr int CH = 3;
+  constexpr int NS = X3 ? 1 : 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int C = p.C, Ws = p.Ws, Hs = p.Hs, R = p.R;
+  const int kch = C / 64;
+  const uint32_t half_bytes = (uint32_t)kch * 32768u;             // hi (or lo) operand of one tile
+  const uint32_t slot_bytes = half_bytes * (X3 ? 2u : 1u);
   uint8_t* sA = smem;
-  uint8_t* sB = sA + (X3 ? 2 : 1) * 32768;
-  float* s_col = reinterpret_cast<float*>(sB + (X3 ? 2 : 1) * 8192);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(s_col + 256 * kColPitch);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint8_t* sB = sA + NS * slot_bytes;
+  float* s_ex = reinterpret_cast<float*>(sB + (X3 ? 2 : 1) * C * 128);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_ex + 12 * kExRows);
+  uint64_t* bar_acc = bar_full + NS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 2);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int Hs = p.Hs, Ws = p.Ws, C = p.C;
-  const int R = 128 / Ws;
-  const int live = (R + 2) * Ws;  // pixel rows of the A tile in use
-  const int cpr = C / 8;
-  const int Ho = 2 * Hs, Wo = 2 * Ws;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t a_addr = smem_u32(sA), b_hi = smem_u32(sB), b_lo = b_hi + (uint32_t)C * 128u;
 
   if (tid == 0) {
-    mbar_init(bar, 1);
+    tma_prefetch_desc(&p.map_x);
+    tma_prefetch_desc(&p.map_x_halo);
+    if (X3) {
+      tma_prefetch_desc(&p.map_lo);
+      tma_prefetch_desc(&p.map_lo_halo);
+    }
+    for (int s = 0; s < NS; ++s) mbar_init(bar_full + s, 1);
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_acc + 1, 1);
     fence_mbar_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 128);
+    tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
-  // zero the A tiles once (rows past `live` feed accumulator rows nobody reads, but keep them finite)
-  for (int i = tid; i < (X3 ? 2 : 1) * 32768 / 16; i += kEdgeThreads) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
+  // rows of the halo halves that no box writes feed accumulator rows nobody reads, but keep them finite
+  for (uint32_t i = tid; i < NS * slot_bytes / 16; i += kEdgeThreads) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
   // weights: row ci = 48 columns = 6 groups, swizzled by the row index (MN-major B: K rows of 128 bytes)
   for (int ci = tid; ci < C; ci += kEdgeThreads) {
+    const uint32_t rowb = (uint32_t)ci * 128u;
 #pragma unroll
-    for (int gi = 0; gi < 2 * CH; ++gi) {
-      float f[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = __ldg(p.w + (long long)ci * (CH * 16) + gi * 8 + j);
-      const Packed8c pk = pack8c(FMT, f);
-      uint8_t* d = sB + ci * 128 + ((gi ^ (ci & 7)) << 4);
-      *reinterpret_cast<uint4*>(d) = FMT == GP_COMP_F16 ? pk.comp : pk.hi;
-      if (X3) *reinterpret_cast<uint4*>(d + 8192) = pk.comp;
+    for (int gi = 0; gi < 8; ++gi) {
+      const uint32_t off = rowb + (uint32_t)((gi ^ (ci & 7)) << 4);
+      if (gi < 6) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w + (long long)ci * 48 + gi * 8));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w + (long long)ci * 48 + gi * 8 + 4));
+        const float f[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const Packed8c pk = pack8c(FMT, f);
+        sts_u32x4(b_hi + off, FMT == GP_COMP_F16 ? pk.comp : pk.hi);
+        if (X3) sts_u32x4(b_lo + off, pk.comp);
+      } else {
+        sts_u32x4(b_hi + off, 0u, 0u, 0u, 0u);
+        if (X3) sts_u32x4(b_lo + off, 0u, 0u, 0u, 0u);
+      }
     }
   }
   fence_proxy_async();
@@ -489,108 +666,187 @@ __global__ void __launch_bounds__(kEdgeThreads, 3) image_convt_fwd_kernel(const 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const uint32_t idesc = make_idesc_bf16(kBlockM, CH * 16, 0, 1) & ~(FMT == GP_COMP_F16 ? ((1u << 7) | (1u << 10)) : 0u);
+  // this CTA's tiles: blockIdx.x, blockIdx.x + gridDim.x, ...; local index i
+  const int n_local = p.tiles > (int)blockIdx.x ? (p.tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const uint32_t tx_bytes = (uint32_t)kch * (uint32_t)(128 + 2 * Ws) * 128u * (X3 ? 2u : 1u);
+  auto issue_loads = [&](int i) {
+    const int s = i % NS, tile = (int)blockIdx.x + i * (int)gridDim.x;
+    const int nimg = tile / p.tiles_per_img, ih0 = (tile - nimg * p.tiles_per_img) * R;
+    uint8_t* dst = sA + s * slot_bytes;
+    mbar_expect_tx(bar_full + s, tx_bytes);
+    for (int kc = 0; kc < kch; ++kc) {
+      uint8_t* d = dst + kc * 32768;
+      tma_load_4d(d, &p.map_x, bar_full + s, kc * 64, 0, ih0, nimg);
+      tma_load_4d(d + 16384, &p.map_x_halo, bar_full + s, kc * 64, 0, ih0 - 1, nimg);
+      tma_load_4d(d + 16384 + Ws * 128, &p.map_x_halo, bar_full + s, kc * 64, 0, ih0 + R, nimg);
+      if (X3) {
+        tma_load_4d(d + half_bytes, &p.map_lo, bar_full + s, kc * 64, 0, ih0, nimg);
+        tma_load_4d(d + half_bytes + 16384, &p.map_lo_halo, bar_full + s, kc * 64, 0, ih0 - 1, nimg);
+        tma_load_4d(d + half_bytes + 16384 + Ws * 128, &p.map_lo_halo, bar_full + s, kc * 64, 0, ih0 + R, nimg);
+      }
+    }
+  };
+  const uint32_t idesc = make_idesc_bf16(kBlockM, 48, 0, 1) & ~(FMT == GP_COMP_F16 ? ((1u << 7) | (1u << 10)) : 0u);
   constexpr uint64_t da_base = make_smem_desc_base(0, 1024);     // K-major A
   constexpr uint64_t db_base = make_smem_desc_base(8192, 1024);  // MN-major B (one 64-column chunk: LBO unused)
-  const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + 32768, b_hi = smem_u32(sB), b_lo = b_hi + 8192;
-  uint32_t phase = 0;
-
-  for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-    const long long pix0 = (long long)tile * 128;
-    const int n = (int)(pix0 / (Hs * Ws));
-    const int ih0 = (int)(pix0 % (Hs * Ws)) / Ws;
-    // ---- A tile: rows ih0 - 1 .. ih0 + R of image n (zero outside the image)
-    for (int i = tid; i < live * cpr; i += kEdgeThreads) {
-      const int lp = i / cpr, j = i % cpr;
-      const int ih = ih0 - 1 + lp / Ws, iw = lp % Ws;
-      const uint32_t off = (uint32_t)(lp >> 7) * 16384u + (uint32_t)(lp & 127) * 128u + (uint32_t)((j ^ (lp & 7)) << 4);
-      if (ih >= 0 && ih < Hs) {
-        const long long src = (((long long)n * Hs + ih) * Ws + iw) * C + j * 8;
-        cp_async16(a_hi + off, p.x + src);
-        if (X3) cp_async16(a_lo + off, p.x_lo + src);
-      } else {
-        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a_hi + off), "r"(0u) : "memory");
-        if (X3) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a_lo + off), "r"(0u) : "memory");
-      }
-    }
-    cp_async_wait_all();
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      for (int mi = 0; mi < 2; ++mi) {
-        for (int k = 0; k < C / kUmmaK; ++k) {
-          const uint64_t ah = smem_desc(da_base, a_hi + mi * 16384 + k * 32);
-          const uint64_t bh = smem_desc(db_base, b_hi + k * (kUmmaK * 128));
-          umma_bf16(tmem_base + mi * 64, ah, bh, idesc, k != 0);
-          if (X3) {
-            umma_bf16(tmem_base + mi * 64, smem_desc(da_base, a_lo + mi * 16384 + k * 32), bh, idesc, 1u);
-            umma_bf16(tmem_base + mi * 64, ah, smem_desc(db_base, b_lo + k * (kUmmaK * 128)), idesc, 1u);
-          }
-        }
-      }
-      umma_commit(bar);
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1;
+  auto issue_mmas = [&](int i) {  // tile i -> accumulator i & 1 (half 0 at column 0, the halo half at column 64)
+    const int s = i % NS;
+    edge_wait(bar_full + s, (uint32_t)(i / NS) & 1u, p.dbg, 7, (uint32_t)i);
     tc_fence_after();
-    // ---- col2im, one image channel at a time through the exchange buffer
-#pragma unroll 1
-    for (int c = 0; c < CH; ++c) {
+    const uint32_t sa = a_addr + s * slot_bytes, acc = tmem_base + (uint32_t)(i & 1) * 128u;
+    for (int mh = 0; mh < 2; ++mh)
+      for (int kc = 0; kc < kch; ++kc)
 #pragma unroll
-      for (int mi = 0; mi < 2; ++mi) {
-        uint32_t r[16];
-        tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + mi * 64 + c * 16, r);
-        const int lp = mi * 128 + tid;
-        if (lp < live) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) s_col[lp * kColPitch + j] = __uint_as_float(r[j]);
-        }
-      }
-      if (c == CH - 1) tc_fence_before();
-      __syncthreads();
-      const float b0 = p.bias != nullptr ? __ldg(p.bias + c) : 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {  // 2R x 2Ws = 512 outputs per channel
-        const int idx = k * kEdgeThreads + tid;
-        const int ol = idx / Wo, ow = idx % Wo;
-        const int oh = 2 * ih0 + ol;
-        const int kh0 = (oh + 1) & 1, kw0 = (ow + 1) & 1;
-        float acc = b0;
-#pragma unroll
-        for (int a = 0; a < 2; ++a) {
-          const int kh = kh0 + 2 * a;
-          const int lr = (oh + 1 - kh) / 2 - (ih0 - 1);  // local row 0 .. R + 1 (rows outside the image hold zeros)
-#pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            const int kw = kw0 + 2 * b;
-            const int iw2 = ow + 1 - kw;  // = 2 * iw
-            if (iw2 >= 0 && iw2 < Wo) acc += s_col[(lr * Ws + (iw2 >> 1)) * kColPitch + kh * 4 + kw];
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ah = smem_desc(da_base, sa + kc * 32768 + mh * 16384 + k * 32);
+          const uint64_t bh = smem_desc(db_base, b_hi + (kc * 4 + k) * (kUmmaK * 128));
+          umma_bf16(acc + mh * 64, ah, bh, idesc, (kc | k) != 0);
+          if (X3) {
+            umma_bf16(acc + mh * 64, smem_desc(da_base, sa + half_bytes + kc * 32768 + mh * 16384 + k * 32), bh, idesc, 1u);
+            umma_bf16(acc + mh * 64, ah, smem_desc(db_base, b_lo + (kc * 4 + k) * (kUmmaK * 128)), idesc, 1u);
           }
         }
-        p.img[(((long long)n * CH + c) * Ho + oh) * Wo + ow] = act_fwd(acc, p.act);
+    umma_commit(bar_acc + (i & 1));
+  };
+
+  if (tid == 0)
+    for (int i = 0; i < NS && i < n_local; ++i) issue_loads(i);
+  if (tid == 32 && n_local > 0) issue_mmas(0);
+
+  const int lr = tid / Ws, iw = tid - lr * Ws;
+  const bool left_edge = iw == 0, right_edge = iw == Ws - 1;
+  const bool halo_warp = warp * 32 < 2 * Ws;  // its threads also own one pixel of the rows above / below the tile
+  const bool halo_bottom = tid >= Ws;
+  const int Ho = 2 * Hs, Wo = 2 * Ws;
+  float bias3[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) bias3[c] = p.bias != nullptr ? __ldg(p.bias + c) : 0.f;
+  // exchange arrays: [kind (0: kh = 3, for the row below; 1: kh = 0, for the row above)][c][b][192]; slot rows: owned pixel t at
+  // Ws + t, the row above the tile at 0 .. Ws - 1, the row below at Ws + 128 ..
+  const uint32_t ex = smem_u32(s_ex);
+  auto ex_at = [&](int kind, int c, int b, int pos) -> uint32_t { return ex + (uint32_t)((((kind * 3 + c) * 2 + b) * kExRows + pos) * 4); };
+
+  for (int i = 0; i < n_local; ++i) {
+    // the next tile's MMAs run into the other accumulator (drained at the end of iteration i - 1) during this epilogue
+    if (tid == 32 && i + 1 < n_local && NS > 1) issue_mmas(i + 1);
+    edge_wait(bar_acc + (i & 1), (uint32_t)(i >> 1) & 1u, p.dbg, 8, (uint32_t)i);
+    tc_fence_after();
+    if (tid == 0 && i + NS < n_local) issue_loads(i + NS);  // the MMAs of tile i are done: its slot is free
+    if (tid == 32 && i + 1 < n_local && NS == 1) issue_mmas(i + 1);  // waits for those loads: one slot, no overlap of loads and MMAs
+
+    const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+    const int nimg = tile / p.tiles_per_img, ih0 = (tile - nimg * p.tiles_per_img) * R;
+    const uint32_t acc = tmem_base + (uint32_t)(i & 1) * 128u + (static_cast<uint32_t>(warp * 32) << 16);
+    float H[3][2][2];  // [c][a: output row 2ih + a][b: output column 2iw + b], own-row terms (kh = 1 / kh = 2)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      uint32_t v[16];
+      tmem_ld_32x16(acc + c * 16, v);
+      // horizontal pair sums for every kh: ow = 2iw <- kw = 1 (own) + kw = 3 (pixel iw - 1); ow = 2iw + 1 <- kw = 2 (own) + kw = 0 (pixel iw + 1)
+      float hs[4][2];
+#pragma unroll
+      for (int kh = 0; kh < 4; ++kh) {
+        const float from_left = __shfl_up_sync(0xffffffffu, __uint_as_float(v[kh * 4 + 3]), 1);
+        const float from_right = __shfl_down_sync(0xffffffffu, __uint_as_float(v[kh * 4 + 0]), 1);
+        hs[kh][0] = __uint_as_float(v[kh * 4 + 1]) + (left_edge ? 0.f : from_left);
+        hs[kh][1] = __uint_as_float(v[kh * 4 + 2]) + (right_edge ? 0.f : from_right);
       }
-      __syncthreads();  // the exchange buffer is rewritten for the next channel / TMEM and A for the next tile
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        H[c][0][b] = hs[1][b];
+        H[c][1][b] = hs[2][b];
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(ex_at(0, c, b, Ws + tid)), "f"(hs[3][b]) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(ex_at(1, c, b, Ws + tid)), "f"(hs[0][b]) : "memory");
+      }
     }
+    if (halo_warp) {  // warp-uniform: pixel tid of the halo half (row above: tid < Ws, row below: Ws <= tid < 2 Ws)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x16(acc + 64 + c * 16, v);
+        // the row above contributes its kh = 3 sums, the row below its kh = 0 sums
+        const float k1 = halo_bottom ? __uint_as_float(v[1]) : __uint_as_float(v[13]);
+        const float k2 = halo_bottom ? __uint_as_float(v[2]) : __uint_as_float(v[14]);
+        const float k3 = halo_bottom ? __uint_as_float(v[3]) : __uint_as_float(v[15]);
+        const float k0 = halo_bottom ? __uint_as_float(v[0]) : __uint_as_float(v[12]);
+        const float from_left = __shfl_up_sync(0xffffffffu, k3, 1);
+        const float from_right = __shfl_down_sync(0xffffffffu, k0, 1);
+        const float s0 = k1 + (left_edge ? 0.f : from_left), s1 = k2 + (right_edge ? 0.f : from_right);
+        if (tid < 2 * Ws) {
+          const int pos = halo_bottom ? 128 + tid : tid;  // (R + 1) * Ws + iw = 128 + tid for the row below
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(ex_at(halo_bottom ? 1 : 0, c, 0, pos)), "f"(s0) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(ex_at(halo_bottom ? 1 : 0, c, 1, pos)), "f"(s1) : "memory");
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // partial sums published; this accumulator is drained
+    {
+      const int oh = 2 * (ih0 + lr);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float o[2][2];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          float up, dn;  // kh = 3 sums of the row above (slot row lr), kh = 0 sums of the row below (slot row lr + 2)
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(up) : "r"(ex_at(0, c, b, tid)) : "memory");
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dn) : "r"(ex_at(1, c, b, 2 * Ws + tid)) : "memory");
+          o[0][b] = act_fwd(H[c][0][b] + up + bias3[c], p.act);
+          o[1][b] = act_fwd(H[c][1][b] + dn + bias3[c], p.act);
+        }
+        float* dst = p.img + (((long long)nimg * 3 + c) * Ho + oh) * Wo + 2 * iw;
+        *reinterpret_cast<float2*>(dst) = make_float2(o[0][0], o[0][1]);
+        *reinterpret_cast<float2*>(dst + Wo) = make_float2(o[1][0], o[1][1]);
+      }
+    }
+    __syncthreads();  // the exchange arrays are rewritten by the next tile
   }
 
+  tc_fence_before();
+  __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 128);
+    tmem_dealloc(tmem_base, 256);
   }
 }
 
 static bool edge_geometry_ok(int ch, int Hi, int Wi, int C) {
   if (ch != 3 || Hi <= 0 || Wi <= 0 || (Hi & 1) || (Wi & 3)) return false;
   const int Ho = Hi / 2, Wo = Wi / 2;
-  if (Wo > 128 || 128 % Wo != 0 || (Ho * Wo) % 128 != 0) return false;
-  return C > 0 && C % 8 == 0 && C <= 128;
+  if (Wo > 64 || 128 % Wo != 0 || (Ho * Wo) % 128 != 0) return false;
+  return C == 64 || C == 128;
 }
 
-static int edge_grid(int tiles, int ctas_per_sm) {
-  const long long cap = (long long)num_sms() * ctas_per_sm;
-  return (int)(tiles < cap ? tiles : cap);
+// GP_EDGE_DEBUG=1: every launch is followed by a stream synchronisation; a failure prints what the timed-out wait recorded
+static unsigned int* edge_debug_buffer() {
+  static unsigned int* buf = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* e = getenv("GP_EDGE_DEBUG");
+    if (e != nullptr && e[0] == '1' && cudaHostAlloc(&buf, 64, cudaHostAllocMapped) == cudaSuccess) memset(buf, 0, 64);
+    else buf = nullptr;
+  }
+  return buf;
+}
+static int edge_debug_check(const char* what, void* stream) {
+  unsigned int* buf = edge_debug_buffer();
+  if (buf == nullptr) return GP_OK;
+  const cudaError_t e = cudaStreamSynchronize(as_stream(stream));
+  if (e != cudaSuccess || buf[0] != 0) {
+    fprintf(stderr, "[gp edge debug] %s: %s; wait code %u block %u thread %u parity %u aux %u\n", what, cudaGetErrorString(e),
+            buf[0], buf[1], buf[2], buf[3], buf[4]);
+    return set_error(GP_ERR_CUDA, "%s failed: %s (wait code %u block %u thread %u parity %u aux %u)", what, cudaGetErrorString(e),
+                     buf[0], buf[1], buf[2], buf[3], buf[4]);
+  }
+  return GP_OK;
+}
+
+template <typename K>
+static int edge_occupancy(K kfn, int smem) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, kEdgeThreads, smem) != cudaSuccess || occ < 1) occ = 1;
+  return occ;
 }
 
 }  // namespace gp
@@ -602,34 +858,42 @@ extern "C" int gp_image_conv_k4s2_fwd(const float* img, const float* mul, const 
                                       void* stream) {
   GP_REQUIRE(img && w && out && NB > 0, "gp_image_conv_k4s2_fwd: null pointer / empty batch");
   GP_REQUIRE(edge_geometry_ok(ch, Hi, Wi, Cout),
-             "gp_image_conv_k4s2_fwd: unsupported geometry ch=%d %dx%d Cout=%d (ch == 3, Wo | 128, Ho*Wo %% 128 == 0, Cout %% 8 == 0 <= 128)",
+             "gp_image_conv_k4s2_fwd: unsupported geometry ch=%d %dx%d Cout=%d (ch == 3, Wo | 128 <= 64, Ho*Wo %% 128 == 0, Cout 64 or 128)",
              ch, Hi, Wi, Cout);
   GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_image_conv_k4s2_fwd: unknown companion format %d", comp_fmt);
   GP_REQUIRE(comp_fmt == GP_COMP_NONE || out_comp != nullptr, "gp_image_conv_k4s2_fwd: companion format %d without out_comp", comp_fmt);
+  GP_REQUIRE(mul == nullptr || comp_fmt == GP_COMP_NONE, "gp_image_conv_k4s2_fwd: the tanh' factor is a backward-side (bf16) feature");
   GP_REQUIRE(act == GP_ACT_NONE || act == GP_ACT_RELU || act == GP_ACT_LRELU, "gp_image_conv_k4s2_fwd: activation %d not supported", act);
-  ImageEdgeParams p;
+  GP_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0, "gp_image_conv_k4s2_fwd: weights not 16-byte aligned");
+  EdgeFwdParams p;
   memset(&p, 0, sizeof(p));
-  p.img = img, p.mul = mul, p.w = w, p.bias = bias;
-  p.out = static_cast<__nv_bfloat16*>(out), p.out_comp = out_comp, p.comp_fmt = comp_fmt;
+  p.g = make_geom(NB, Hi, Wi);
+  p.w = w, p.bias = bias, p.N = Cout;
+  p.dbg = edge_debug_buffer();
   p.slope = act == GP_ACT_NONE ? 1.f : (act == GP_ACT_RELU ? 0.f : 0.2f);
-  p.NB = NB, p.Hi = Hi, p.Wi = Wi, p.N = Cout;
-  p.tiles = (int)((long long)NB * (Hi / 2) * (Wi / 2) / 128);
-  const int Npad = (Cout + 15) & ~15;
-  p.tmem_cols = Npad <= 32 ? 32 : (Npad <= 64 ? 64 : 128);
+  const long long P = (long long)p.g.tiles * 128;
+  int rc = make_map_image(&p.map_img, img, NB, ch, Hi, Wi, 2 * p.g.R + 2);
+  if (rc == GP_OK && mul != nullptr) rc = make_map_image(&p.map_mul, mul, NB, ch, Hi, Wi, 2 * p.g.R + 2);
+  if (rc == GP_OK) rc = make_map_rows(&p.map_out, out, P, Cout, 32);
+  if (rc == GP_OK && comp_fmt != GP_COMP_NONE) rc = make_map_rows(&p.map_comp, out_comp, P, Cout, 32);
+  if (rc != GP_OK) return rc;
   const int halves = comp_fmt == GP_COMP_LO ? 2 : 1;
-  const int smem = 1024 + halves * (16384 + Npad * 128) + kEdgePatchFloats * 4 + 160 * 4 + 8192 + 64;
-  const int per_sm = (220 * 1024) / smem < 512 / p.tmem_cols ? (220 * 1024) / smem : 512 / p.tmem_cols;
-  const int grid = edge_grid(p.tiles, per_sm > 6 ? 6 : per_sm);
+  const int smem = 1024 + halves * (16384 + Cout * 128) + 32768 + (mul != nullptr ? 2 : 1) * p.g.patch_stride + 64;
   auto launch = [&](auto kfn) -> int {
     GP_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int per_sm = edge_occupancy(kfn, smem);
+    if (per_sm > 512 / Cout) per_sm = 512 / Cout;  // TMEM columns
+    const long long cap = (long long)num_sms() * per_sm;
+    const int grid = (int)(p.g.tiles < cap ? p.g.tiles : cap);
     kfn<<<grid, kEdgeThreads, smem, as_stream(stream)>>>(p);
     GP_CHECK_LAUNCH();
-    return 0;
+    return edge_debug_check(__func__, stream);
   };
+  if (mul != nullptr) return launch(image_conv_fwd_kernel<GP_COMP_NONE, true>);
   switch (comp_fmt) {
-    case GP_COMP_LO: return launch(image_conv_fwd_kernel<3, GP_COMP_LO>);
-    case GP_COMP_F16: return launch(image_conv_fwd_kernel<3, GP_COMP_F16>);
-    default: return launch(image_conv_fwd_kernel<3, GP_COMP_NONE>);
+    case GP_COMP_LO: return launch(image_conv_fwd_kernel<GP_COMP_LO, false>);
+    case GP_COMP_F16: return launch(image_conv_fwd_kernel<GP_COMP_F16, false>);
+    default: return launch(image_conv_fwd_kernel<GP_COMP_NONE, false>);
   }
 }
 
@@ -637,21 +901,29 @@ extern "C" int gp_image_conv_k4s2_wgrad(const void* dense, const float* img, con
                                         int NB, int ch, int Hi, int Wi, int M, void* stream) {
   GP_REQUIRE(dense && img && dw && NB > 0, "gp_image_conv_k4s2_wgrad: null pointer / empty batch");
   GP_REQUIRE(edge_geometry_ok(ch, Hi, Wi, M),
-             "gp_image_conv_k4s2_wgrad: unsupported geometry ch=%d %dx%d M=%d (ch == 3, Wo | 128, Ho*Wo %% 128 == 0, M %% 8 == 0 <= 128)",
+             "gp_image_conv_k4s2_wgrad: unsupported geometry ch=%d %dx%d M=%d (ch == 3, Wo | 128 <= 64, Ho*Wo %% 128 == 0, M 64 or 128)",
              ch, Hi, Wi, M);
-  ImageEdgeParams p;
+  GP_REQUIRE((reinterpret_cast<uintptr_t>(dw) & 15) == 0, "gp_image_conv_k4s2_wgrad: dw not 16-byte aligned");
+  EdgeWgradParams p;
   memset(&p, 0, sizeof(p));
-  p.img = img, p.mul = mul, p.dense = static_cast<const __nv_bfloat16*>(dense), p.dw = dw, p.dbias = dbias;
-  p.NB = NB, p.Hi = Hi, p.Wi = Wi, p.N = M;
-  p.tiles = (int)((long long)NB * (Hi / 2) * (Wi / 2) / 128);
-  p.tmem_cols = 64;
-  const int smem = 1024 + 32768 + 16384 + kEdgePatchFloats * 4 + 64;
-  const int grid = edge_grid(p.tiles, 3);
-  auto kfn = image_conv_wgrad_kernel<3>;
-  GP_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kfn<<<grid, kEdgeThreads, smem, as_stream(stream)>>>(p);
-  GP_CHECK_LAUNCH();
-  return 0;
+  p.g = make_geom(NB, Hi, Wi);
+  p.dw = dw, p.dbias = dbias, p.M = M;
+  p.dbg = edge_debug_buffer();
+  const long long P = (long long)p.g.tiles * 128;
+  int rc = make_map_image(&p.map_img, img, NB, ch, Hi, Wi, 2 * p.g.R + 2);
+  if (rc == GP_OK && mul != nullptr) rc = make_map_image(&p.map_mul, mul, NB, ch, Hi, Wi, 2 * p.g.R + 2);
+  if (rc == GP_OK) rc = make_map_rows(&p.map_dense, dense, P, M, 128);
+  if (rc != GP_OK) return rc;
+  const int grid = p.g.tiles < num_sms() ? p.g.tiles : num_sms();
+  auto launch = [&](auto kfn, int stages) -> int {
+    const int smem = 1024 + stages * 32768 + 2 * 16384 + stages * (mul != nullptr ? 2 : 1) * p.g.patch_stride + 128;
+    GP_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kfn<<<grid, kEdgeThreads, smem, as_stream(stream)>>>(p);
+    GP_CHECK_LAUNCH();
+    return edge_debug_check(__func__, stream);
+  };
+  if (mul != nullptr) return launch(image_conv_wgrad_kernel<true, 3>, 3);
+  return launch(image_conv_wgrad_kernel<false, 4>, 4);
 }
 
 extern "C" int gp_image_convt_k4s2_fwd(const void* x, const void* x_lo, int fmt, const float* w, const float* bias, float* img,
@@ -659,23 +931,32 @@ extern "C" int gp_image_convt_k4s2_fwd(const void* x, const void* x_lo, int fmt,
   GP_REQUIRE(x && w && img && NB > 0, "gp_image_convt_k4s2_fwd: null pointer / empty batch");
   GP_REQUIRE(fmt >= GP_COMP_NONE && fmt <= GP_COMP_F16, "gp_image_convt_k4s2_fwd: unknown operand format %d", fmt);
   GP_REQUIRE(fmt != GP_COMP_LO || x_lo != nullptr, "gp_image_convt_k4s2_fwd: bf16x3 operands need x_lo");
-  GP_REQUIRE(ch == 3 && Hs > 0 && Ws > 0 && Ws <= 64 && 128 % Ws == 0 && (Hs * Ws) % 128 == 0 && C % 16 == 0 && C > 0 && C <= 64,
-             "gp_image_convt_k4s2_fwd: unsupported geometry ch=%d %dx%d C=%d (ch == 3, Ws | 128 <= 64, Hs*Ws %% 128 == 0, C %% 16 == 0 <= 64)",
+  GP_REQUIRE(ch == 3 && Hs > 0 && (Ws == 16 || Ws == 32) && (Hs * Ws) % 128 == 0 && (C == 64 || C == 128),
+             "gp_image_convt_k4s2_fwd: unsupported geometry ch=%d %dx%d C=%d (ch == 3, Ws 16 or 32, Hs*Ws %% 128 == 0, C 64 or 128)",
              ch, Hs, Ws, C);
-  ImageConvTParams p;
+  GP_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(img) & 7) == 0,
+             "gp_image_convt_k4s2_fwd: weights / image not aligned");
+  EdgeConvTParams p;
   memset(&p, 0, sizeof(p));
-  p.x = static_cast<const uint16_t*>(x), p.x_lo = static_cast<const uint16_t*>(x_lo), p.w = w, p.bias = bias, p.img = img;
-  p.act = act, p.NB = NB, p.Hs = Hs, p.Ws = Ws, p.C = C;
-  p.tiles = (int)((long long)NB * Hs * Ws / 128);
-  const int halves = fmt == GP_COMP_LO ? 2 : 1;
-  const int smem = 1024 + halves * (32768 + 8192) + 256 * kColPitch * 4 + 64;
-  const int per_sm = (220 * 1024) / smem < 3 ? (220 * 1024) / smem : 3;
-  const int grid = edge_grid(p.tiles, per_sm);
+  p.w = w, p.bias = bias, p.img = img, p.act = act, p.NB = NB, p.Hs = Hs, p.Ws = Ws, p.C = C;
+  p.R = 128 / Ws;
+  p.dbg = edge_debug_buffer();
+  p.tiles_per_img = Hs * Ws / 128;
+  p.tiles = NB * p.tiles_per_img;
+  int rc = make_map_nhwc_rows(&p.map_x, x, C, Ws, Hs, NB, p.R);
+  if (rc == GP_OK) rc = make_map_nhwc_rows(&p.map_x_halo, x, C, Ws, Hs, NB, 1);
+  if (rc == GP_OK && fmt == GP_COMP_LO) rc = make_map_nhwc_rows(&p.map_lo, x_lo, C, Ws, Hs, NB, p.R);
+  if (rc == GP_OK && fmt == GP_COMP_LO) rc = make_map_nhwc_rows(&p.map_lo_halo, x_lo, C, Ws, Hs, NB, 1);
+  if (rc != GP_OK) return rc;
+  const bool x3 = fmt == GP_COMP_LO;
+  const int slot = (C / 64) * 32768 * (x3 ? 2 : 1);
+  const int smem = 1024 + (x3 ? 1 : 2) * slot + (x3 ? 2 : 1) * C * 128 + 12 * kExRows * 4 + 128;
+  const int grid = p.tiles < num_sms() ? p.tiles : num_sms();
   auto launch = [&](auto kfn) -> int {
     GP_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     kfn<<<grid, kEdgeThreads, smem, as_stream(stream)>>>(p);
     GP_CHECK_LAUNCH();
-    return 0;
+    return edge_debug_check(__func__, stream);
   };
   switch (fmt) {
     case GP_COMP_LO: return launch(image_convt_fwd_kernel<GP_COMP_LO>);

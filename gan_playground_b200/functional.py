@@ -566,7 +566,8 @@ class ImageConvT(torch.autograd.Function):
         dout = dout.contiguous()
         dweight = dbias = dx = None
         mul = out if act == ops.ACT_TANH else None
-        if ops.image_edge_ok(ch, 2 * H, 2 * W, Cin) and weight.is_contiguous() and ctx.in_link is None:
+        bwd = _link_bwd(ctx.in_link, x.shape, x.device) if ctx.needs_input_grad[0] else None
+        if ops.image_edge_ok(ch, 2 * H, 2 * W, Cin) and weight.is_contiguous() and bwd is None:
             # fused: the column tile of dout * tanh' is rebuilt in shared memory by both kernels instead of stored
             if ctx.needs_input_grad[2]:
                 tw = ops.grad_target(ctx.params[0])
@@ -595,7 +596,6 @@ class ImageConvT(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             wpd = cache.get((key, "dgrad"), weight,
                             lambda: ops.pack_matrix(weight.detach(), Cin, ch * 16, Cin, 64, ch * 16, 1))
-            bwd = _link_bwd(ctx.in_link, x.shape, x.device)
             dx = ops.conv_fwd(dcol, wpd, None, ops.KIND_CONV_K1S1, H, W, flops=fl, bwd=bwd)
             if bwd is not None:
                 ctx.in_link.produced(dx)

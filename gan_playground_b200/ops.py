@@ -1025,15 +1025,16 @@ _SIGS.update({
 
 def image_edge_ok(ch, Hi, Wi, C, transposed=False):
     """Shapes the fused image-edge kernels (csrc/image_edge.cu) take; anything else goes through im2col / col2im.
-    (Hi, Wi): the IMAGE side; C: channels of the NHWC side. GP_IMAGE_EDGE=0 forces the column-buffer path."""
+    (Hi, Wi): the IMAGE side; C: channels of the NHWC side (whole 64-channel TMA boxes: 64 or 128 — every full-width
+    DCGAN-family net of the reference). GP_IMAGE_EDGE=0 forces the column-buffer path."""
     import os
 
-    if os.environ.get("GP_IMAGE_EDGE", "1") == "0" or ch != 3 or Hi % 2 or Wi % 4:
+    if os.environ.get("GP_IMAGE_EDGE", "1") == "0" or ch != 3 or Hi % 2 or Wi % 4 or C not in (64, 128):
         return False
     Ho, Wo = Hi // 2, Wi // 2
-    if Wo > (64 if transposed else 128) or 128 % Wo or (Ho * Wo) % 128:
+    if (Ho * Wo) % 128:
         return False
-    return C > 0 and (C % 16 == 0 and C <= 64 if transposed else C % 8 == 0 and C <= 128)
+    return Wo in (16, 32) if transposed else (Wo <= 64 and 128 % Wo == 0)
 
 
 def image_conv_fwd(img, w, bias, act, comp_fmt=COMP_NONE, mul=None):

@@ -13,6 +13,14 @@ torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 dev = torch.device("cuda:0")
 FAILED = []
+ONLY = None
+for _i, _a in enumerate(sys.argv):
+    if _a == "--only":
+        ONLY = sys.argv[_i + 1]      # fwd | wgrad | convt: one kernel family per process (a faulting kernel poisons the context)
+
+
+def want(what):
+    return ONLY is None or ONLY == what
 
 
 def rel(a, b):
@@ -38,15 +46,20 @@ def case(NB, res, C, seed):
     ref = F.leaky_relu(F.conv2d(img, w, b, stride=2, padding=1), 0.2)
     tag = "B%d r%d C%d" % (NB, res, C)
     for fmt, name, tol in ((ops.COMP_NONE, "bf16", 1.5e-2), (ops.COMP_LO, "bf16x3", 2e-4), (ops.COMP_F16, "fp16", 2e-3)):
+        if not want("fwd"):
+            break
         out, comp = ops.image_conv_fwd(img, w, b, ops.ACT_LRELU, fmt)
         val = out.float() + comp.float() if fmt == ops.COMP_LO else (comp.float() if fmt == ops.COMP_F16 else out.float())
         report("image_conv_fwd %s %s" % (name, tag), rel(val, nhwc(ref)), tol)
         report("image_conv_fwd %s %s (bf16 tensor)" % (name, tag), rel(out, nhwc(ref)), 1.5e-2)
     # data-gradient use: mul = tanh output, no bias, no activation
     t = torch.tanh(torch.randn(NB, 3, res, res, generator=g)).to(dev)
-    ref = F.conv2d(img * (1 - t * t), w, None, stride=2, padding=1)
-    out, _ = ops.image_conv_fwd(img, w, None, ops.ACT_NONE, ops.COMP_NONE, mul=t)
-    report("image_conv_fwd mul=tanh' %s" % tag, rel(out, nhwc(ref)), 1.5e-2)
+    if want("fwd"):
+        ref = F.conv2d(img * (1 - t * t), w, None, stride=2, padding=1)
+        out, _ = ops.image_conv_fwd(img, w, None, ops.ACT_NONE, ops.COMP_NONE, mul=t)
+        report("image_conv_fwd mul=tanh' %s" % tag, rel(out, nhwc(ref)), 1.5e-2)
+    if not want("wgrad"):
+        return
     # weight gradient: dense = bf16 dy
     dy = (torch.randn(NB, res // 2, res // 2, C, generator=g) * 0.1).to(dev).to(torch.bfloat16)
     for mul in (None, t):
@@ -73,6 +86,8 @@ def case_t(NB, res, C, seed):
     b = (torch.randn(3, generator=g) * 0.1).to(dev)
     ref = torch.tanh(F.conv_transpose2d(x, w, b, stride=2, padding=1))
     tag = "B%d r%d C%d" % (NB, res, C)
+    if not want("convt"):
+        return
     xn = nhwc(x)
     hi = xn.to(torch.bfloat16)
     lo = (xn - hi.float()).to(torch.bfloat16)
@@ -96,7 +111,8 @@ def timeit(fn, reps=20):
     return a.elapsed_time(b) / reps * 1e3
 
 
-def timing(NB=1024, res=64, C=64):
+def timing(NB=1024, res=64, C=128):
+    """The benched shape: DCGAN-64's D block 0 is 3 -> 128 at 32x32 output, G's last layer 128 -> 3."""
     img = torch.rand(NB, 3, res, res, device=dev) * 2 - 1
     t = torch.tanh(torch.randn(NB, 3, res, res, device=dev))
     w = torch.randn(C, 3, 4, 4, device=dev) * 0.05
@@ -139,19 +155,35 @@ def timing(NB=1024, res=64, C=64):
     print("  (old) K=64 GEMM %.1f us + col2im %.1f us = %.1f us" % (us4, us5, us4 + us5))
 
 
+def unsupported():
+    """Shapes outside the fused kernels' set must be refused loudly (the Python side then takes the column-buffer path)."""
+    img = torch.zeros(2, 3, 64, 64, device=dev)
+    w = torch.zeros(8, 3, 4, 4, device=dev)
+    try:
+        ops.image_conv_fwd(img, w, None, ops.ACT_NONE)
+        ok = False
+    except Exception as e:  # GpError
+        ok = "unsupported geometry" in str(e)
+    print("%-66s %s" % ("image_conv_fwd refuses Cout=8", "ok" if ok else "FAILED"))
+    if not ok:
+        FAILED.append("refusal")
+    assert not ops.image_edge_ok(3, 64, 64, 8) and ops.image_edge_ok(3, 64, 64, 128)
+    assert ops.image_edge_ok(3, 64, 64, 128, transposed=True) and not ops.image_edge_ok(3, 128, 128, 64, transposed=True)
+
+
 if __name__ == "__main__":
     case(4, 64, 64, 0)
-    case(3, 64, 64, 1)       # odd number of images: tiles never straddle images
-    case(2, 32, 64, 2)
-    case(2, 32, 8, 3)
-    case(2, 128, 32, 4)
-    case(2, 64, 128, 5)
-    case(160, 64, 64, 6)     # more tiles than CTAs: the persistent loop and the register prefetch
+    case(3, 64, 128, 1)      # odd number of images: tiles never straddle images
+    case(2, 32, 128, 2)      # Wo = 16: eight output rows per tile
+    case(2, 128, 64, 4)      # Wo = 64: two output rows per tile
+    case(160, 64, 128, 6)    # more tiles than resident CTAs: the persistent loops, ring reuse, stage wrap-around
+    case(40, 32, 64, 7)
     case_t(4, 64, 64, 10)
-    case_t(3, 32, 64, 11)
-    case_t(2, 128, 32, 12)
-    case_t(2, 64, 16, 13)
-    case_t(160, 64, 64, 14)
+    case_t(3, 32, 128, 11)   # Ws = 16
+    case_t(3, 64, 128, 12)
+    case_t(160, 64, 128, 14)
+    case_t(300, 32, 64, 15)
+    unsupported()
     if "--time" in sys.argv:
         timing()
     print("\nimage edge: %s" % ("ALL OK" if not FAILED else "FAILED: %s" % FAILED))
