@@ -497,6 +497,7 @@ def main():
     own_per_step = _lib.launch_count() - l0
     launches = own_per_step * args.steps   # own kernels per step x timed steps
     gemm = prof.summary()
+    edge = prof.summary(hbm=True)   # fused image-edge launches (csrc/image_edge.cu): HBM-bound, accounted in bytes
     peaks, peaks_src = load_peaks()
     burst, sustained = peaks["bf16_tflops"], peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     label = precision_label(runner)
@@ -522,6 +523,12 @@ def main():
                                "follows %d graph-replayed steps, i.e. at sustained clocks)" % (peaks_src, args.steps * 2),
                 "gemm_ms_per_step": gemm["ms"], "gemm_share_of_step": gemm["ms"] / ms_per_step,
                 "algorithmic_flops_per_step": gemm["flops"],
+                "image_edge": None if edge["launches"] == 0 else {
+                    "kernel": "gp::image_conv_fwd / image_conv_wgrad / image_convt_fwd kernels (fp32 NCHW image <-> first / last "
+                              "NHWC activation without a column buffer; %d launches of one step)" % edge["launches"],
+                    "bound": "hbm", "achieved": edge["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": edge["gbs"] / peaks["hbm_gbs"], "ms_per_step": edge["ms"],
+                    "algorithmic_bytes_per_step": edge["bytes"], "algorithmic_flops_per_step": edge["flops"]},
                 "whole_step_tflops": cfg["flops_img"] * per_gpu / (ms_per_step * 1e-3) / 1e12,
                 "whole_step_frac": cfg["flops_img"] * per_gpu / (ms_per_step * 1e-3) / 1e12 / burst}
 

@@ -412,7 +412,8 @@ class ImageConv(torch.autograd.Function):
         if ctx.fused:
             # csrc/image_edge.cu: the column tile lives in shared memory only; the image itself is what wgrad re-reads
             fmt = ops.COMP_LO if config.x3() else (ops.COMP_F16 if config.fp16() else ops.COMP_NONE)
-            a, a_lo = _timed_edge("image_conv_fwd", fl, lambda: ops.image_conv_fwd(x.detach(), weight.detach(), bias.detach(), act, fmt))
+            a, a_lo = _timed_edge("image_conv_fwd", fl, lambda: ops.image_conv_fwd(x.detach(), weight.detach(), bias.detach(), act, fmt),
+                                  x, _act_bytes(NB, H // 2, W // 2, Cout, 1 if fmt == ops.COMP_NONE else 2))
             if a_lo is not None:
                 ctx.mark_non_differentiable(a_lo)
             ctx.save_for_backward(x, weight, a)
@@ -470,7 +471,7 @@ class ImageConv(torch.autograd.Function):
                 db = None
                 if ctx.needs_input_grad[2]:
                     db = tb if tb is not None else ops.zeros((Cout,), dy.device)
-                _timed_edge("image_conv_wgrad", fl, lambda: ops.image_conv_wgrad(dy, x, None, dw, db))
+                _timed_edge("image_conv_wgrad", fl, lambda: ops.image_conv_wgrad(dy, x, None, dw, db), dy, x)
                 dweight = None if tw is not None else dw
                 dbias = None if (tb is not None or db is None) else db
             if ctx.needs_input_grad[0]:
@@ -486,16 +487,28 @@ class ImageConv(torch.autograd.Function):
         return dx, dweight, dbias, None, None, None, None
 
 
-def _timed_edge(name, flops, fn):
-    """The fused image-edge launches are tensor-core launches too: keep them in bench.py's GEMM accounting."""
-    return ops._timed(name, flops, fn)
+def _timed_edge(name, flops, fn, *tensors):
+    """The fused image-edge launches are HBM-bound: bench.py accounts them by the bytes of the tensors they stream."""
+    return ops._timed(name, flops, fn, nbytes=sum(t.numel() * t.element_size() for t in tensors if t is not None))
+
+
+def _act_bytes(NB, H, W, C, copies=1):
+    """a stand-in with .numel() / .element_size() for an NHWC 2-byte activation (or `copies` of them) not yet allocated"""
+    class _B:
+        def numel(self):
+            return NB * H * W * C * copies
+
+        def element_size(self):
+            return 2
+    return _B()
 
 
 def _image_dgrad(dy, weight, ch, cache, key, H, W, fl):
     """Image gradient of D's first conv: dx = col2im(dy * W) — fused (csrc/image_edge.cu) when the shape allows."""
     Cout = weight.shape[0]
     if ops.image_edge_ok(ch, H, W, Cout, transposed=True) and weight.is_contiguous():
-        return _timed_edge("image_convt_fwd (dgrad)", fl, lambda: ops.image_convt_fwd(dy, None, weight.detach(), None, ch, ops.ACT_NONE))
+        return _timed_edge("image_convt_fwd (dgrad)", fl, lambda: ops.image_convt_fwd(dy, None, weight.detach(), None, ch, ops.ACT_NONE),
+                           dy, _act_bytes(dy.shape[0], H, W, ch, 2))   # fp32 image gradient out
     # dcol[px][j] = sum_o dy[px][o] * W[o][j]  -> weights [64][Cout] = W^T (rows j >= ch*16 are zero)
     wpt = cache.get((key, "dgrad"), weight,
                     lambda: ops.pack_matrix(weight.detach(), ch * 16, Cout, 64, Cout, 1, ch * 16))
@@ -528,7 +541,8 @@ class ImageConvT(torch.autograd.Function):
                 xa, xl = _f16_operand(x, x_lo), None
             else:
                 xa, xl = x, None
-            out = _timed_edge("image_convt_fwd", fl, lambda: ops.image_convt_fwd(xa, xl, weight.detach(), bias.detach(), ch, act))
+            out = _timed_edge("image_convt_fwd", fl, lambda: ops.image_convt_fwd(xa, xl, weight.detach(), bias.detach(), ch, act),
+                              xa, xl, _act_bytes(NB, 2 * H, 2 * W, ch, 2))   # fp32 image out
             ctx.save_for_backward(x, weight, out)
             ctx.misc = (act, cache, key)
             ctx.params = _params(weight, bias)
@@ -572,7 +586,7 @@ class ImageConvT(torch.autograd.Function):
             if ctx.needs_input_grad[2]:
                 tw = ops.grad_target(ctx.params[0])
                 dw = tw if tw is not None else ops.zeros(tuple(weight.shape), x.device)
-                _timed_edge("image_conv_wgrad", fl, lambda: ops.image_conv_wgrad(x, dout, mul, dw))
+                _timed_edge("image_conv_wgrad", fl, lambda: ops.image_conv_wgrad(x, dout, mul, dw), x, dout, mul)
                 dweight = None if tw is not None else dw
             if ctx.needs_input_grad[3]:
                 tgt = ops.grad_target(ctx.params[1])
@@ -581,7 +595,8 @@ class ImageConvT(torch.autograd.Function):
                     dbias = None
             if ctx.needs_input_grad[0]:
                 dx, _ = _timed_edge("image_conv_fwd (dgrad)", fl,
-                                    lambda: ops.image_conv_fwd(dout, weight.detach(), None, ops.ACT_NONE, ops.COMP_NONE, mul=mul))
+                                    lambda: ops.image_conv_fwd(dout, weight.detach(), None, ops.ACT_NONE, ops.COMP_NONE, mul=mul),
+                                    dout, mul, x)
             return dx, None, dweight, dbias, None, None, None, None
         # dcol[(n,ih,iw)][(co,kh,kw)] = dpre[n, co, 2ih-1+kh, 2iw-1+kw], dpre = dout * (1 - out^2) fused into the gather
         dcol = ops.im2col_k4s2(dout, out if act == ops.ACT_TANH else None)

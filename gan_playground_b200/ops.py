@@ -154,7 +154,9 @@ def zeros(shape, device):
 # ------------------------------------------------------------------------------------------------ conv GEMMs
 class GemmProfiler:
     """Times every tensor-core GEMM launch (gp::conv_gemm_kernel) with CUDA events on the launching stream and
-    accumulates its ALGORITHMIC FLOPs — bench.py's roofline numbers come from here (measured live, no profiler)."""
+    accumulates its ALGORITHMIC FLOPs — bench.py's roofline numbers come from here (measured live, no profiler).
+    The fused image-edge launches (csrc/image_edge.cu) are HBM-bound: they are recorded with their algorithmic BYTES and
+    summarised separately (`summary(hbm=True)`), not against the tensor-core peak."""
 
     active = None
 
@@ -168,18 +170,23 @@ class GemmProfiler:
     def __exit__(self, *exc):
         GemmProfiler.active = None
 
-    def summary(self):
+    def summary(self, hbm=False):
         torch.cuda.synchronize()
-        ms = sum(a.elapsed_time(b) for a, b, _, _ in self.records)
-        fl = sum(f for _, _, f, _ in self.records)
-        return {"ms": ms, "flops": fl, "tflops": fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0, "launches": len(self.records)}
+        recs = [r for r in self.records if (r[4] is not None) == hbm]
+        ms = sum(a.elapsed_time(b) for a, b, _, _, _ in recs)
+        fl = sum(f for _, _, f, _, _ in recs)
+        out = {"ms": ms, "flops": fl, "tflops": fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0, "launches": len(recs)}
+        if hbm:
+            by = sum(nb for _, _, _, _, nb in recs)
+            out.update(bytes=by, gbs=by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0)
+        return out
 
     def per_launch(self):
         torch.cuda.synchronize()
-        return [(name, a.elapsed_time(b), f) for a, b, f, name in self.records]
+        return [(name, a.elapsed_time(b), f) for a, b, f, name, _ in self.records]
 
 
-def _timed(name, flops, fn):
+def _timed(name, flops, fn, nbytes=None):
     if CallProfiler.active is not None:
         CallProfiler.note = (name, flops)
     prof = GemmProfiler.active
@@ -189,7 +196,7 @@ def _timed(name, flops, fn):
     a.record()
     r = fn()
     b.record()
-    prof.records.append((a, b, flops, name))
+    prof.records.append((a, b, flops, name, nbytes))
     return r
 
 

@@ -49,6 +49,15 @@ def algorithmic_bytes(name, a):
     if name in ("gp_col2im_k4s2", "gp_col2im_k4s2_f32"):
         col, bias, img, NB, ch, Hi, Wi = a[:7]
         return NB * ch * Hi * Wi * 4 + NB * (Hi // 2) * (Wi // 2) * 64 * (2 if name == "gp_col2im_k4s2" else 4)
+    if name == "gp_image_conv_k4s2_fwd":   # fused image-edge kernels (csrc/image_edge.cu): image (+ tanh factor) in, activation(s) out
+        img, mul, w, bias, out, comp, fmt, NB, ch, Hi, Wi, C = a[:12]
+        return NB * ch * Hi * Wi * 4 * (2 if mul else 1) + NB * (Hi // 2) * (Wi // 2) * C * 2 * (2 if comp else 1)
+    if name == "gp_image_conv_k4s2_wgrad":
+        dense, img, mul, dw, db, NB, ch, Hi, Wi, M = a[:10]
+        return NB * ch * Hi * Wi * 4 * (2 if mul else 1) + NB * (Hi // 2) * (Wi // 2) * M * 2
+    if name == "gp_image_convt_k4s2_fwd":
+        x, x_lo, fmt, w, bias, img, NB, Hs, Ws, C, ch = a[:11]
+        return NB * Hs * Ws * C * 2 * (2 if x_lo else 1) + NB * ch * 4 * Hs * Ws * 4
     if name == "gp_image_bias_grad":
         dout, mul, db, NB, ch, HW = a[:6]
         return NB * ch * HW * 4 * (2 if mul else 1)
@@ -109,7 +118,7 @@ def main():
     for name, a, e0, e1, note in prof.records:
         ms = e0.elapsed_time(e1)
         tot += ms
-        if note is not None:
+        if note is not None and not name.startswith("gp_image_conv"):
             gemms.append((note[0], ms, note[1]))
             key = name + " [tensor]"
             ent = agg.setdefault(key, [0, 0.0, 0.0, 0.0])
