@@ -600,27 +600,31 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
 
 constexpr int kExRows = 192;  // exchange rows: 128 owned pixels + 2 * Ws halo pixels, Ws <= 32
 
-// shared memory: [NS slots x (A hi: C/64 chunks x 2 halves x 16 KB | A lo likewise (bf16x3)) | B hi C*128 | B lo (bf16x3) |
-//                 exchange 12 x 192 fp32 | barriers | TMEM slot]; NS = 2 (1 for bf16x3): the next tile's loads fly during the
-// epilogue, and the next tile's MMAs run into the second TMEM accumulator while this tile's is drained.
+// shared memory: [A: C/64 main chunks (128 pixel rows x 128 B = 16 KB each), then C/64 halo chunks (2 * Ws rows each) |
+//                 B hi C*128 | B lo (bf16x3) | exchange 12 x 192 fp32 | barriers | TMEM slot]
+// The halo MMAs (M = 128) read 16 KB from the start of a 2*Ws-row halo chunk: the rows past it belong to whatever follows
+// in shared memory and only feed accumulator rows nobody reads. 74 KB for C = 128 (bf16 / fp16): three CTAs share an SM,
+// so one CTA's loads and MMAs run under another's epilogue; within a CTA the next tile's loads fly during the epilogue.
+// bf16x3 streams the hi halves and then the lo halves of a tile through the SAME operand tile (hi * w_hi + hi * w_lo, then
+// lo * w_hi): 90 KB, two CTAs per SM.
 template <int FMT>
-__global__ void __launch_bounds__(kEdgeThreads, 1) image_convt_fwd_kernel(const __grid_constant__ EdgeConvTParams p) {
+__global__ void __launch_bounds__(kEdgeThreads) image_convt_fwd_kernel(const __grid_constant__ EdgeConvTParams p) {
   constexpr bool X3 = FMT == GP_COMP_LO;
-  constexpr int NS = X3 ? 1 : 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int C = p.C, Ws = p.Ws, Hs = p.Hs, R = p.R;
   const int kch = C / 64;
-  const uint32_t half_bytes = (uint32_t)kch * 32768u;             // hi (or lo) operand of one tile
-  const uint32_t slot_bytes = half_bytes * (X3 ? 2u : 1u);
+  const uint32_t halo_bytes = (uint32_t)(2 * Ws) * 128u;                  // one halo chunk: the row above, then the row below
+  const uint32_t half_bytes = (uint32_t)kch * (16384u + halo_bytes);     // one operand tile (hi or lo)
   uint8_t* sA = smem;
-  uint8_t* sB = sA + NS * slot_bytes;
+  uint8_t* sB = sA + half_bytes;
   float* s_ex = reinterpret_cast<float*>(sB + (X3 ? 2 : 1) * C * 128);
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_ex + 12 * kExRows);
-  uint64_t* bar_acc = bar_full + NS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc + 2);
+  uint64_t* bar_acc = bar_full + 1;
+  uint64_t* bar_mid = bar_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_full + 3);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t a_addr = smem_u32(sA), b_hi = smem_u32(sB), b_lo = b_hi + (uint32_t)C * 128u;
 
   if (tid == 0) {
@@ -630,17 +634,15 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) image_convt_fwd_kernel(const 
       tma_prefetch_desc(&p.map_lo);
       tma_prefetch_desc(&p.map_lo_halo);
     }
-    for (int s = 0; s < NS; ++s) mbar_init(bar_full + s, 1);
+    mbar_init(bar_full, 1);
     mbar_init(bar_acc, 1);
-    mbar_init(bar_acc + 1, 1);
+    mbar_init(bar_mid, 1);
     fence_mbar_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 128);
     tmem_relinquish();
   }
-  // rows of the halo halves that no box writes feed accumulator rows nobody reads, but keep them finite
-  for (uint32_t i = tid; i < NS * slot_bytes / 16; i += kEdgeThreads) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0u, 0u, 0u, 0u);
   // weights: row ci = 48 columns = 6 groups, swizzled by the row index (MN-major B: K rows of 128 bytes)
   for (int ci = tid; ci < C; ci += kEdgeThreads) {
     const uint32_t rowb = (uint32_t)ci * 128u;
@@ -668,49 +670,54 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) image_convt_fwd_kernel(const 
 
   // this CTA's tiles: blockIdx.x, blockIdx.x + gridDim.x, ...; local index i
   const int n_local = p.tiles > (int)blockIdx.x ? (p.tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const uint32_t tx_bytes = (uint32_t)kch * (uint32_t)(128 + 2 * Ws) * 128u * (X3 ? 2u : 1u);
-  auto issue_loads = [&](int i) {
-    const int s = i % NS, tile = (int)blockIdx.x + i * (int)gridDim.x;
+  auto issue_loads = [&](int i, int part) {  // part 0: the bf16 / fp16 operand (bf16x3: hi halves); part 1: the lo halves
+    const int tile = (int)blockIdx.x + i * (int)gridDim.x;
     const int nimg = tile / p.tiles_per_img, ih0 = (tile - nimg * p.tiles_per_img) * R;
-    uint8_t* dst = sA + s * slot_bytes;
-    mbar_expect_tx(bar_full + s, tx_bytes);
+    const CUtensorMap* mm = part == 0 ? &p.map_x : &p.map_lo;
+    const CUtensorMap* mh = part == 0 ? &p.map_x_halo : &p.map_lo_halo;
+    mbar_expect_tx(bar_full, half_bytes);
     for (int kc = 0; kc < kch; ++kc) {
-      uint8_t* d = dst + kc * 32768;
-      tma_load_4d(d, &p.map_x, bar_full + s, kc * 64, 0, ih0, nimg);
-      tma_load_4d(d + 16384, &p.map_x_halo, bar_full + s, kc * 64, 0, ih0 - 1, nimg);
-      tma_load_4d(d + 16384 + Ws * 128, &p.map_x_halo, bar_full + s, kc * 64, 0, ih0 + R, nimg);
-      if (X3) {
-        tma_load_4d(d + half_bytes, &p.map_lo, bar_full + s, kc * 64, 0, ih0, nimg);
-        tma_load_4d(d + half_bytes + 16384, &p.map_lo_halo, bar_full + s, kc * 64, 0, ih0 - 1, nimg);
-        tma_load_4d(d + half_bytes + 16384 + Ws * 128, &p.map_lo_halo, bar_full + s, kc * 64, 0, ih0 + R, nimg);
-      }
+      uint8_t* dm = sA + kc * 16384;                       // 128 owned pixels
+      uint8_t* dh = sA + kch * 16384 + kc * halo_bytes;    // the rows above / below the tile (zero outside the image)
+      tma_load_4d(dm, mm, bar_full, kc * 64, 0, ih0, nimg);
+      tma_load_4d(dh, mh, bar_full, kc * 64, 0, ih0 - 1, nimg);
+      tma_load_4d(dh + Ws * 128, mh, bar_full, kc * 64, 0, ih0 + R, nimg);
     }
   };
   const uint32_t idesc = make_idesc_bf16(kBlockM, 48, 0, 1) & ~(FMT == GP_COMP_F16 ? ((1u << 7) | (1u << 10)) : 0u);
   constexpr uint64_t da_base = make_smem_desc_base(0, 1024);     // K-major A
   constexpr uint64_t db_base = make_smem_desc_base(8192, 1024);  // MN-major B (one 64-column chunk: LBO unused)
-  auto issue_mmas = [&](int i) {  // tile i -> accumulator i & 1 (half 0 at column 0, the halo half at column 64)
-    const int s = i % NS;
-    edge_wait(bar_full + s, (uint32_t)(i / NS) & 1u, p.dbg, 7, (uint32_t)i);
-    tc_fence_after();
-    const uint32_t sa = a_addr + s * slot_bytes, acc = tmem_base + (uint32_t)(i & 1) * 128u;
+  // accumulator columns 0..47: the owned pixels, 64..111: the halo rows. part 0: a * w_hi (+ a * w_lo for bf16x3), zeroing
+  // the accumulator; part 1 (bf16x3): a_lo * w_hi on top
+  auto mma_block = [&](int part) {
     for (int mh = 0; mh < 2; ++mh)
-      for (int kc = 0; kc < kch; ++kc)
+      for (int kc = 0; kc < kch; ++kc) {
+        const uint32_t sa = a_addr + (mh == 0 ? (uint32_t)kc * 16384u : (uint32_t)kch * 16384u + (uint32_t)kc * halo_bytes);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint64_t ah = smem_desc(da_base, sa + kc * 32768 + mh * 16384 + k * 32);
-          const uint64_t bh = smem_desc(db_base, b_hi + (kc * 4 + k) * (kUmmaK * 128));
-          umma_bf16(acc + mh * 64, ah, bh, idesc, (kc | k) != 0);
-          if (X3) {
-            umma_bf16(acc + mh * 64, smem_desc(da_base, sa + half_bytes + kc * 32768 + mh * 16384 + k * 32), bh, idesc, 1u);
-            umma_bf16(acc + mh * 64, ah, smem_desc(db_base, b_lo + (kc * 4 + k) * (kUmmaK * 128)), idesc, 1u);
-          }
+          const uint64_t ad = smem_desc(da_base, sa + k * 32);
+          umma_bf16(tmem_base + mh * 64, ad, smem_desc(db_base, b_hi + (kc * 4 + k) * (kUmmaK * 128)), idesc,
+                    (part != 0 || (kc | k) != 0) ? 1u : 0u);
+          if (X3 && part == 0) umma_bf16(tmem_base + mh * 64, ad, smem_desc(db_base, b_lo + (kc * 4 + k) * (kUmmaK * 128)), idesc, 1u);
         }
-    umma_commit(bar_acc + (i & 1));
+      }
+  };
+  auto issue_mmas = [&](int i) {  // by ONE thread; the part-0 loads of tile i have been issued
+    edge_wait(bar_full, X3 ? 0u : ((uint32_t)i & 1u), p.dbg, 7, (uint32_t)i);
+    tc_fence_after();
+    mma_block(0);
+    if (X3) {
+      umma_commit(bar_mid);
+      edge_wait(bar_mid, (uint32_t)i & 1u, p.dbg, 9, (uint32_t)i);  // the hi halves have been consumed
+      issue_loads(i, 1);
+      edge_wait(bar_full, 1u, p.dbg, 10, (uint32_t)i);
+      tc_fence_after();
+      mma_block(1);
+    }
+    umma_commit(bar_acc);
   };
 
-  if (tid == 0)
-    for (int i = 0; i < NS && i < n_local; ++i) issue_loads(i);
+  if (tid == 0 && n_local > 0) issue_loads(0, 0);
   if (tid == 32 && n_local > 0) issue_mmas(0);
 
   const int lr = tid / Ws, iw = tid - lr * Ws;
@@ -725,18 +732,15 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) image_convt_fwd_kernel(const 
   // Ws + t, the row above the tile at 0 .. Ws - 1, the row below at Ws + 128 ..
   const uint32_t ex = smem_u32(s_ex);
   auto ex_at = [&](int kind, int c, int b, int pos) -> uint32_t { return ex + (uint32_t)((((kind * 3 + c) * 2 + b) * kExRows + pos) * 4); };
+  const uint32_t acc = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
 
   for (int i = 0; i < n_local; ++i) {
-    // the next tile's MMAs run into the other accumulator (drained at the end of iteration i - 1) during this epilogue
-    if (tid == 32 && i + 1 < n_local && NS > 1) issue_mmas(i + 1);
-    edge_wait(bar_acc + (i & 1), (uint32_t)(i >> 1) & 1u, p.dbg, 8, (uint32_t)i);
+    edge_wait(bar_acc, (uint32_t)i & 1u, p.dbg, 8, (uint32_t)i);
     tc_fence_after();
-    if (tid == 0 && i + NS < n_local) issue_loads(i + NS);  // the MMAs of tile i are done: its slot is free
-    if (tid == 32 && i + 1 < n_local && NS == 1) issue_mmas(i + 1);  // waits for those loads: one slot, no overlap of loads and MMAs
+    if (tid == 0 && i + 1 < n_local) issue_loads(i + 1, 0);  // the MMAs of tile i are done: the operand tile is free
 
     const int tile = (int)blockIdx.x + i * (int)gridDim.x;
     const int nimg = tile / p.tiles_per_img, ih0 = (tile - nimg * p.tiles_per_img) * R;
-    const uint32_t acc = tmem_base + (uint32_t)(i & 1) * 128u + (static_cast<uint32_t>(warp * 32) << 16);
     float H[3][2][2];  // [c][a: output row 2ih + a][b: output column 2iw + b], own-row terms (kh = 1 / kh = 2)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -780,7 +784,8 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) image_convt_fwd_kernel(const 
       }
     }
     tc_fence_before();
-    __syncthreads();  // partial sums published; this accumulator is drained
+    __syncthreads();  // partial sums published; the accumulator is drained
+    if (tid == 32 && i + 1 < n_local) issue_mmas(i + 1);  // the loads had the first half of the epilogue to land
     {
       const int oh = 2 * (ih0 + lr);
 #pragma unroll
@@ -806,7 +811,7 @@ __global__ void __launch_bounds__(kEdgeThreads, 1) image_convt_fwd_kernel(const 
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 128);
   }
 }
 
@@ -842,11 +847,15 @@ static int edge_debug_check(const char* what, void* stream) {
   return GP_OK;
 }
 
+// resident CTAs per SM by shared memory (228 KB per SM, 1 KB reserved per CTA) and registers
 template <typename K>
 static int edge_occupancy(K kfn, int smem) {
-  int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, kEdgeThreads, smem) != cudaSuccess || occ < 1) occ = 1;
-  return occ;
+  cudaFuncAttributes attr;
+  int by_regs = 16;
+  if (cudaFuncGetAttributes(&attr, kfn) == cudaSuccess && attr.numRegs > 0) by_regs = 65536 / (attr.numRegs * kEdgeThreads);
+  const int by_smem = (228 * 1024) / (smem + 1024);
+  const int occ = by_regs < by_smem ? by_regs : by_smem;
+  return occ < 1 ? 1 : occ;
 }
 
 }  // namespace gp
@@ -949,11 +958,14 @@ extern "C" int gp_image_convt_k4s2_fwd(const void* x, const void* x_lo, int fmt,
   if (rc == GP_OK && fmt == GP_COMP_LO) rc = make_map_nhwc_rows(&p.map_lo_halo, x_lo, C, Ws, Hs, NB, 1);
   if (rc != GP_OK) return rc;
   const bool x3 = fmt == GP_COMP_LO;
-  const int slot = (C / 64) * 32768 * (x3 ? 2 : 1);
-  const int smem = 1024 + (x3 ? 1 : 2) * slot + (x3 ? 2 : 1) * C * 128 + 12 * kExRows * 4 + 128;
-  const int grid = p.tiles < num_sms() ? p.tiles : num_sms();
+  const int half = (C / 64) * (16384 + 2 * Ws * 128);
+  const int smem = 1024 + half + (x3 ? 2 : 1) * C * 128 + 12 * kExRows * 4 + 128;
   auto launch = [&](auto kfn) -> int {
     GP_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int per_sm = edge_occupancy(kfn, smem);
+    if (per_sm > 4) per_sm = 4;  // TMEM: 128 columns per CTA
+    const long long cap = (long long)num_sms() * per_sm;
+    const int grid = (int)(p.tiles < cap ? p.tiles : cap);
     kfn<<<grid, kEdgeThreads, smem, as_stream(stream)>>>(p);
     GP_CHECK_LAUNCH();
     return edge_debug_check(__func__, stream);
