@@ -489,6 +489,8 @@ def main():
 
     # ---- roofline of the dominant kernel family: tcgen05 implicit-GEMM convs, timed per launch with CUDA events
     # (one eager step: same kernels as the graph replays, launched one by one so they can be bracketed by events)
+    runner.step_eager(*x_dev)       # un-timed: the eager path allocates outside the graph's private pool the first time
+    torch.cuda.synchronize()
     prof = ops.GemmProfiler()
     l0 = _lib.launch_count()
     with prof:

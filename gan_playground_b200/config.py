@@ -134,3 +134,17 @@ def bwd_fusion():
 def set_bwd_fusion(on):
     global _bwd_fusion
     _bwd_fusion = bool(on)
+
+
+# Batched weight staging (functional.WeightCache.get_conv -> ops.stage_conv_weights): every 4x4 conv weight of a network in
+# every operand format / orientation from one launch per optimiser step. GP_BATCH_STAGE=0 restores one launch per tensor.
+_batch_stage = os.environ.get("GP_BATCH_STAGE", "1") != "0"
+
+
+def batch_stage():
+    return _batch_stage
+
+
+def set_batch_stage(on):
+    global _batch_stage
+    _batch_stage = bool(on)

@@ -18,11 +18,27 @@ BN_MOMENTUM = 0.1
 
 
 class WeightCache:
-    """bf16 GEMM-operand copies of fp32 parameters, re-staged only when the parameter changes (optimizer.step bumps
-    tensor._version). One D forward per step packs; the other two reuse (main_dcgan.py:70,80,91)."""
+    """GEMM-operand copies of fp32 parameters, re-staged only when the parameter changes (optimizer.step bumps
+    tensor._version). One D forward per step packs; the other two reuse (main_dcgan.py:70,80,91).
+
+    4x4 conv weights go through `get_conv`, which remembers (parameter, format, orientation) of every request: the first
+    stale request after an optimiser step re-stages EVERY remembered copy of the network in one launch
+    (ops.stage_conv_weights — each fp32 weight is read once for all its formats) instead of one launch per layer, format
+    and orientation. `clear()` drops the copies, not the list."""
 
     def __init__(self):
         self._d = {}
+        self._recipes = {}
+
+    @staticmethod
+    def _ver(param):
+        # _version: bumped by torch in-place updates (torch.optim.Adam); _gp_epoch: bumped by optim.FusedAdam, whose
+        # kernel updates the storage behind autograd's back
+        return (param._version, getattr(param, "_gp_epoch", 0))
+
+    def _fresh(self, key, param):
+        ent = self._d.get(key)
+        return ent is not None and ent[0] == self._ver(param) and ent[1] == param.data_ptr()
 
     def get(self, key, param, make):
         # only real parameters are cached. A derived weight (W / sigma of spectral norm) is a new tensor every forward;
@@ -30,15 +46,32 @@ class WeightCache:
         # again next forward, so neither is_leaf nor (version, data_ptr) can tell two of them apart
         if not isinstance(param, torch.nn.Parameter) or not param.is_leaf:
             return make()
-        # _version: bumped by torch in-place updates (torch.optim.Adam); _gp_epoch: bumped by optim.FusedAdam, whose
-        # kernel updates the storage behind autograd's back
-        ver = (param._version, getattr(param, "_gp_epoch", 0))
-        ent = self._d.get(key)
-        if ent is not None and ent[0] == ver and ent[1] == param.data_ptr():
-            return ent[2]
+        if self._fresh(key, param):
+            return self._d[key][2]
         val = make()
-        self._d[key] = (ver, param.data_ptr(), val)
+        self._d[key] = (self._ver(param), param.data_ptr(), val)
         return val
+
+    def get_conv(self, key, param, fmt, n_dim, make):
+        """A conv weight as [N][tap][C] operand in format `fmt` (ops.STAGE_*), orientation n_dim; `make` is the
+        per-tensor fallback (shapes / devices the batched kernel does not take)."""
+        if not isinstance(param, torch.nn.Parameter) or not param.is_leaf:
+            return make()
+        if not (config.batch_stage() and ops.stage_conv_ok(param)):
+            return self.get(key, param, make)
+        self._recipes[key] = (param, fmt, n_dim)
+        if self._fresh(key, param):
+            return self._d[key][2]
+        stale = {}
+        for k, (p, f, nd) in self._recipes.items():
+            if not self._fresh(k, p):
+                stale.setdefault(id(p), (p, []))[1].append((k, f, nd))
+        groups = list(stale.values())
+        outs = ops.stage_conv_weights([(p, [(f, nd) for _, f, nd in reqs]) for p, reqs in groups])
+        for (p, reqs), tensors in zip(groups, outs):
+            for (k, _, _), t in zip(reqs, tensors):
+                self._d[k] = (self._ver(p), p.data_ptr(), t)
+        return self._d[key][2]
 
     def clear(self):
         self._d.clear()
@@ -245,7 +278,7 @@ class ConvBlock(torch.autograd.Function):
         if has_bn and training and config.fused_stats() and Cout <= 2048:
             st = ops.zeros((2, Cout), x.device)
         if x3:
-            wp = cache.get((key, "fwd3"), weight, lambda: ops.split_conv_weight(weight.detach(), n_dim))
+            wp = cache.get_conv((key, "fwd3"), weight, ops.STAGE_SPLIT, n_dim, lambda: ops.split_conv_weight(weight.detach(), n_dim))
             if x_lo is None or x_lo.dtype != torch.bfloat16:   # produced by a bf16 / fp16 pass: no low half to add
                 x_lo = torch.zeros_like(x)
             y = ops.conv_fwd(x, wp, b, kind, Ho, Wo, ops.ACT_NONE if has_bn else act, stats=st, x_lo=x_lo,
@@ -253,13 +286,13 @@ class ConvBlock(torch.autograd.Function):
         elif fp16:
             # one MMA on fp16 operands; the output pair is (bf16, fp16) — or a (hi, lo) bf16 pair when the head, which is
             # not a GEMM, consumes it
-            wp = cache.get((key, "fwdh"), weight, lambda: ops.conv_weight_f16(weight.detach(), n_dim))
+            wp = cache.get_conv((key, "fwdh"), weight, ops.STAGE_F16, n_dim, lambda: ops.conv_weight_f16(weight.detach(), n_dim))
             # pre-BatchNorm output: 2-byte fp16 storage when the statistics come from the epilogue (fp32 accumulators)
             prebn = "f16" if (st is not None and config.fp16_prebn() == "f16") else "f32"
             y = ops.conv_fwd(_f16_operand(x, x_lo), wp, b, kind, Ho, Wo, ops.ACT_NONE if has_bn else act, stats=st,
                              fp16_in=True, out_mode=prebn if has_bn else ("split" if feeds_head else "pair"))
         else:
-            wp = cache.get((key, "fwd"), weight, lambda: ops.pack_conv_weight(weight.detach(), n_dim))
+            wp = cache.get_conv((key, "fwd"), weight, ops.STAGE_BF16, n_dim, lambda: ops.pack_conv_weight(weight.detach(), n_dim))
             y = ops.conv_fwd(x, wp, b, kind, Ho, Wo, ops.ACT_NONE if has_bn else act, stats=st)
         ctx.transposed, ctx.act, ctx.has_bn, ctx.cache, ctx.key = transposed, act, has_bn, cache, key
         ctx.params = _params(weight, bias, gamma, beta)   # the Parameter objects: gradients go straight into their .grad
@@ -310,10 +343,10 @@ class ConvBlock(torch.autograd.Function):
             NB, H, W, _ = x.shape
             bwd = _link_bwd(ctx.in_link, x.shape, x.device)   # the producing block's backward work, in this epilogue
             if ctx.transposed:   # dgrad of ConvT == strided conv over dy with weights [Cin][tap][Cout]
-                wpd = ctx.cache.get((ctx.key, "dgrad"), weight, lambda: ops.pack_conv_weight(weight.detach(), 0))
+                wpd = ctx.cache.get_conv((ctx.key, "dgrad"), weight, ops.STAGE_BF16, 0, lambda: ops.pack_conv_weight(weight.detach(), 0))
                 dx = ops.conv_fwd(dy, wpd, None, ops.KIND_CONV_K4S2, H, W, bwd=bwd)
             else:                # dgrad of Conv == 4-phase transposed conv over dy with weights [Cin][tap][Cout]
-                wpd = ctx.cache.get((ctx.key, "dgrad"), weight, lambda: ops.pack_conv_weight(weight.detach(), 1))
+                wpd = ctx.cache.get_conv((ctx.key, "dgrad"), weight, ops.STAGE_BF16, 1, lambda: ops.pack_conv_weight(weight.detach(), 1))
                 dx = ops.conv_fwd(dy, wpd, None, ops.KIND_CONVT_K4S2, H, W, bwd=bwd)
             if bwd is not None:
                 ctx.in_link.produced(dx)

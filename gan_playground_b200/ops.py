@@ -320,6 +320,63 @@ def pack_conv_weight(w, n_dim, inv_scale=None):
     return dst
 
 
+# ---- batched staging of 4x4 conv weights (csrc/weight_stage.cu)
+STAGE_BF16, STAGE_F16, STAGE_SPLIT = 0, 1, 2
+STAGE_MAX_LAYERS, STAGE_MAX_DST = 12, 4
+_SIGS.update({"gp_stage_conv_weights": [_vp, _vp]})
+
+
+class StageDst(ctypes.Structure):
+    """gp_stage_dst_t of include/gpb200.h."""
+    _fields_ = [("ptr", ctypes.c_void_p), ("ld", ctypes.c_longlong), ("n_dim", ctypes.c_int32), ("fmt", ctypes.c_int32)]
+
+
+class StageLayer(ctypes.Structure):
+    """gp_stage_layer_t of include/gpb200.h."""
+    _fields_ = [("src", ctypes.c_void_p), ("D0", ctypes.c_int32), ("D1", ctypes.c_int32), ("tile0", ctypes.c_int32),
+                ("ndst", ctypes.c_int32), ("dst", StageDst * STAGE_MAX_DST)]
+
+
+class StageTable(ctypes.Structure):
+    """gp_stage_table_t of include/gpb200.h."""
+    _fields_ = [("count", ctypes.c_int32), ("total_tiles", ctypes.c_int32), ("layer", StageLayer * STAGE_MAX_LAYERS)]
+
+
+def stage_conv_ok(w):
+    """Weights the batched staging kernel takes: fp32 CUDA (D0, D1, 4, 4) with D0, D1 multiples of 32."""
+    return (w.is_cuda and w.dtype == torch.float32 and w.dim() == 4 and w.shape[2] * w.shape[3] == 16 and w.is_contiguous()
+            and w.shape[0] % 32 == 0 and w.shape[1] % 32 == 0 and w.data_ptr() % 16 == 0)
+
+
+def stage_conv_weights(items):
+    """items: [(w fp32 (D0, D1, 4, 4), [(fmt, n_dim), ...]), ...] -> [[operand tensor per request], ...]: rows [N][tap][C] as
+    pack_conv_weight (STAGE_BF16), conv_weight_f16 (STAGE_F16) or split_conv_weight (STAGE_SPLIT: hi | lo) write them, all
+    layers and formats from one launch per STAGE_MAX_LAYERS layers."""
+    outs = []
+    for i0 in range(0, len(items), STAGE_MAX_LAYERS):
+        chunk = items[i0:i0 + STAGE_MAX_LAYERS]
+        tb = StageTable()
+        tb.count = len(chunk)
+        for li, (w, reqs) in enumerate(chunk):
+            _chk(w, torch.float32, "w")
+            if not stage_conv_ok(w) or not 0 < len(reqs) <= STAGE_MAX_DST:
+                raise _lib.GpError("stage_conv_weights: weight %s with %d requests is outside the batched kernel's set"
+                                   % (tuple(w.shape), len(reqs)))
+            D0, D1 = w.shape[0], w.shape[1]
+            L = tb.layer[li]
+            L.src, L.D0, L.D1, L.ndst = _p(w), D0, D1, len(reqs)
+            res = []
+            for di, (fmt, n_dim) in enumerate(reqs):
+                N, C = (D0, D1) if n_dim == 0 else (D1, D0)
+                ld = (32 if fmt == STAGE_SPLIT else 16) * C
+                t = torch.empty((N, ld), device=w.device, dtype=torch.float16 if fmt == STAGE_F16 else torch.bfloat16)
+                L.dst[di].ptr, L.dst[di].ld, L.dst[di].n_dim, L.dst[di].fmt = _p(t), ld, n_dim, fmt
+                res.append(t)
+            outs.append(res)
+        check(_fn("gp_stage_conv_weights")(ctypes.addressof(tb), _stream()), "gp_stage_conv_weights")
+    return outs
+
+
 UNPACK_ACCUMULATE = 1 << 30
 
 

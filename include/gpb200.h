@@ -140,6 +140,36 @@ int gp_conv_wgrad(const gp_conv_wgrad_t* p, void* stream);
 #define GP_UNPACK_ACCUMULATE (1 << 30)
 int gp_pack_conv_weight(const float* src, void* dst, int D0, int D1, int taps, int n_dim, const float* inv_scale,
                         void* stream);
+/* gp_stage_conv_weights: the batched form for 16-tap (4x4) weights — every listed layer in every listed orientation /
+ * format from ONE launch that reads each fp32 source once (the per-tensor calls above cost ~30 launches per DCGAN step
+ * whose bytes do not shrink with the batch). Destination rows are [N][tap][C] as gp_pack_conv_weight writes them:
+ * GP_STAGE_BF16 bf16, GP_STAGE_F16 fp16 (the single-MMA fp16 operand), GP_STAGE_SPLIT bf16 hi block | lo block per row
+ * (gp_split_conv_weight's layout); ld = elements per destination row; D0, D1 multiples of 32. tile0 / total_tiles are
+ * filled by the library. */
+#define GP_STAGE_MAX_LAYERS 12
+#define GP_STAGE_MAX_DST 4
+#define GP_STAGE_BF16 0
+#define GP_STAGE_F16 1
+#define GP_STAGE_SPLIT 2
+typedef struct {
+  void* ptr;
+  long long ld;
+  int32_t n_dim;
+  int32_t fmt;
+} gp_stage_dst_t;
+typedef struct {
+  const float* src;   /* (D0, D1, 16) fp32, torch layout of Conv2d (Cout, Cin, 4, 4) / ConvTranspose2d (Cin, Cout, 4, 4) */
+  int32_t D0, D1;
+  int32_t tile0;
+  int32_t ndst;
+  gp_stage_dst_t dst[GP_STAGE_MAX_DST];
+} gp_stage_layer_t;
+typedef struct {
+  int32_t count;
+  int32_t total_tiles;
+  gp_stage_layer_t layer[GP_STAGE_MAX_LAYERS];
+} gp_stage_table_t;
+int gp_stage_conv_weights(const gp_stage_table_t* table, void* stream);
 int gp_unpack_conv_wgrad(const float* src, float* dst, int M, int N, int taps, void* stream);
 int gp_pack_matrix(const float* src, void* dst, int R, int K, int Rpad, int ld_dst, long long s_r, long long s_k,
                    int perm, const float* inv_scale, void* stream);

@@ -1,0 +1,59 @@
+"""Batched weight staging (csrc/weight_stage.cu, ops.stage_conv_weights, functional.WeightCache.get_conv): bit-exact against
+the per-tensor staging entry points it replaces, and the same training step with fewer launches."""
+import contextlib
+import io
+
+import pytest
+import torch
+
+
+@pytest.mark.gpu
+def test_batched_staging_matches_the_per_tensor_kernels():
+    from gan_playground_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    ws = [torch.randn(s, generator=g).mul_(0.05).to(dev) for s in ((256, 128, 4, 4), (64, 96, 4, 4), (512, 1024, 4, 4), (32, 32, 4, 4))]
+    reqs = [(ops.STAGE_BF16, 0), (ops.STAGE_F16, 0), (ops.STAGE_SPLIT, 0), (ops.STAGE_BF16, 1)]
+    reqs_t = [(ops.STAGE_F16, 1), (ops.STAGE_SPLIT, 1), (ops.STAGE_BF16, 0)]
+    items = [(w, reqs if i % 2 == 0 else reqs_t) for i, w in enumerate(ws)]
+    outs = ops.stage_conv_weights(items)
+    for (w, rq), res in zip(items, outs):
+        for (fmt, nd), t in zip(rq, res):
+            if fmt == ops.STAGE_BF16:
+                ref = ops.pack_conv_weight(w, nd)
+            elif fmt == ops.STAGE_SPLIT:
+                ref = ops.split_conv_weight(w, nd)
+            else:   # fp16(w) in [N][tap][C] order
+                ref = (w.permute(0, 2, 3, 1) if nd == 0 else w.permute(1, 2, 3, 0)).reshape(t.shape).half()
+            assert t.shape == ref.shape and t.dtype == ref.dtype
+            assert torch.equal(t, ref), (tuple(w.shape), fmt, nd)
+
+
+@pytest.mark.gpu
+def test_a_step_with_batched_staging_is_the_step_without_it_in_fewer_launches():
+    from gan_playground_b200 import _lib, config
+    from gan_playground_b200.criterion import GANLoss
+    from gan_playground_b200.models import dcgan
+
+    def run(batched):
+        config.set_batch_stage(batched)
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            netG, netD = dcgan.Generator(ngf=32, resolution=32).cuda(), dcgan.Discriminator(ndf=32, resolution=32).cuda()
+        crit = GANLoss("vanilla", 0.9, 0.1, 0.9).cuda()
+        z = torch.randn(8, 100, generator=torch.Generator().manual_seed(1)).cuda()
+        l0 = _lib.launch_count()
+        loss = crit(netD(netG(z)), False, True)
+        loss.backward()
+        torch.cuda.synchronize()
+        grads = torch.cat([p.grad.flatten() for p in list(netG.parameters()) + list(netD.parameters())])
+        return loss.item(), grads, _lib.launch_count() - l0
+
+    try:
+        la, ga, na = run(True)
+        lb, gb, nb = run(False)
+    finally:
+        config.set_batch_stage(True)
+    assert la == lb
+    assert torch.equal(ga, gb)
+    assert na < nb, (na, nb)
