@@ -46,7 +46,9 @@ def test_a_step_with_batched_staging_is_the_step_without_it_in_fewer_launches():
         loss = crit(netD(netG(z)), False, True)
         loss.backward()
         torch.cuda.synchronize()
-        grads = torch.cat([p.grad.flatten() for p in list(netG.parameters()) + list(netD.parameters())])
+        # a conv bias in front of BatchNorm gets no gradient tensor at all (analytically zero, functional.ConvBlock.backward)
+        grads = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).flatten()
+                           for p in list(netG.parameters()) + list(netD.parameters())])
         return loss.item(), grads, _lib.launch_count() - l0
 
     try:
