@@ -148,3 +148,57 @@ def batch_stage():
 def set_batch_stage(on):
     global _batch_stage
     _batch_stage = bool(on)
+
+
+# Weight-gradient GEMMs on a side stream (engine._AdversarialStep): dW of a layer is needed only at the optimiser step, so
+# the step drivers fork it off the backward chain (dgrad -> BatchNorm backward -> next dgrad ...) and join before the
+# gradient exchange / optimiser. Pays where one launch cannot fill the GPU (the 128-image shards of the 8-GPU run: 64-128
+# tiles and 20-60 us per launch); GP_WGRAD_STREAM = 1 / 0 forces it, "auto" (default) enables it at <= 256 images per GPU.
+# Only inside a step driver, and only for parameters whose gradient is delivered in place (ops.grad_target): plain
+# autograd users read .grad right after backward() with no join.
+_wgrad_stream_mode = os.environ.get("GP_WGRAD_STREAM", "auto")
+if _wgrad_stream_mode not in ("auto", "0", "1"):
+    raise ValueError("GP_WGRAD_STREAM must be auto, 0 or 1")
+_wgrad_side = None      # (stream, list of tensors kept alive until the join) while a step driver runs its loop body
+
+
+def set_wgrad_stream_mode(mode):
+    global _wgrad_stream_mode
+    if mode not in ("auto", "0", "1"):
+        raise ValueError("wgrad stream mode must be auto, 0 or 1")
+    _wgrad_stream_mode = mode
+
+
+def wgrad_stream_wanted(per_gpu_batch):
+    if _wgrad_stream_mode == "auto":
+        return per_gpu_batch <= 256
+    return _wgrad_stream_mode == "1"
+
+
+def wgrad_side():
+    return _wgrad_side
+
+
+class wgrad_side_scope:
+    def __init__(self, stream):
+        self.stream = stream
+
+    def __enter__(self):
+        global _wgrad_side
+        self.prev = _wgrad_side
+        _wgrad_side = (self.stream, []) if self.stream is not None else None
+
+    def __exit__(self, *exc):
+        global _wgrad_side
+        join_wgrad_side()
+        _wgrad_side = self.prev
+
+
+def join_wgrad_side():
+    """The current stream waits for every weight gradient issued on the side stream; the tensors they read may be freed."""
+    if _wgrad_side is None:
+        return
+    import torch
+    stream, hold = _wgrad_side
+    torch.cuda.current_stream().wait_stream(stream)
+    del hold[:]

@@ -38,6 +38,7 @@ __device__ __forceinline__ int reflect1(int q, int n) {
 __global__ void blur3x3_fwd_kernel(const __nv_bfloat16* __restrict__ in, const void* __restrict__ in_comp,
                                    __nv_bfloat16* __restrict__ out, void* __restrict__ out_comp, int fmt, int NB, int H,
                                    int W, int C, int s, int Ho, int Wo) {
+  gp::pdl_sync();
   const int cgs = C / 8;
   const long long total = (long long)NB * Ho * Wo * cgs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -68,6 +69,7 @@ __global__ void blur3x3_fwd_kernel(const __nv_bfloat16* __restrict__ in, const v
 // H+1 when ih == H-2), taps kh with (q - kh) divisible by s, and the same along the width, of w[kh] w[kw]/16 * dout.
 __global__ void blur3x3_bwd_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ din, int NB, int H,
                                    int W, int C, int s, int Ho, int Wo) {
+  gp::pdl_sync();
   const int cgs = C / 8;
   const long long total = (long long)NB * H * W * cgs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -127,8 +129,7 @@ int gp_blur3x3_fwd(const void* in, const void* in_comp, void* out, void* out_com
              "gp_blur3x3_fwd: bad arguments (C %% 8 == 0, H, W >= 2, stride 1 or 2)");
   GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_blur3x3_fwd: unknown companion format %d", comp_fmt);
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-  blur3x3_fwd_kernel<<<blur_grid((long long)NB * Ho * Wo * (C / 8)), 256, 0, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(in), in_comp, static_cast<__nv_bfloat16*>(out), out_comp, comp_fmt, NB, H, W, C,
+  gp::launch_pdl(blur3x3_fwd_kernel, blur_grid((long long)NB * Ho * Wo * (C / 8)), 256, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(in), in_comp, static_cast<__nv_bfloat16*>(out), out_comp, comp_fmt, NB, H, W, C,
       stride, Ho, Wo);
   GP_CHECK_LAUNCH();
   return GP_OK;
@@ -138,8 +139,7 @@ int gp_blur3x3_bwd(const void* dout, void* din, int NB, int H, int W, int C, int
   GP_REQUIRE(dout && din && NB > 0 && H >= 2 && W >= 2 && C > 0 && C % 8 == 0 && (stride == 1 || stride == 2),
              "gp_blur3x3_bwd: bad arguments (C %% 8 == 0, H, W >= 2, stride 1 or 2)");
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-  blur3x3_bwd_kernel<<<blur_grid((long long)NB * H * W * (C / 8)), 256, 0, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(dout), static_cast<__nv_bfloat16*>(din), NB, H, W, C, stride, Ho, Wo);
+  gp::launch_pdl(blur3x3_bwd_kernel, blur_grid((long long)NB * H * W * (C / 8)), 256, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(dout), static_cast<__nv_bfloat16*>(din), NB, H, W, C, stride, Ho, Wo);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }

@@ -155,6 +155,7 @@ __device__ __forceinline__ RowRange row_range(long long P, int rows_per_block) {
 template <typename TY, bool SQ>
 __global__ void col_stats_kernel(const TY* __restrict__ x, long long P, int C, float* __restrict__ sum,
                                  float* __restrict__ sumsq, int rows_per_block) {
+  gp::pdl_sync();
   const ColLayout L = col_layout(C);
   constexpr int NQ = SQ ? 2 : 1;
   float acc[NQ][8];
@@ -200,6 +201,7 @@ template <typename TY, bool LOH = false>
 __global__ void bn_apply_kernel(const TY* __restrict__ y, __nv_bfloat16* __restrict__ out_hi,
                                 __nv_bfloat16* __restrict__ out_lo, long long P, int C, const float* __restrict__ scale,
                                 const float* __restrict__ shift, int act, int rows_per_block) {
+  gp::pdl_sync();
   const ColLayout L = col_layout(C);
   if (!L.active) return;
   float sc[8], sh[8];
@@ -242,6 +244,7 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, const
                                      const float* __restrict__ scale, const float* __restrict__ shift,
                                      const float* __restrict__ mean, const float* __restrict__ rstd, int act,
                                      float* __restrict__ sum_dz, float* __restrict__ sum_dzx, int rows_per_block) {
+  gp::pdl_sync();
   const ColLayout L = col_layout(C);
   float acc[2][8];
 #pragma unroll
@@ -298,6 +301,7 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const 
                                     const float* __restrict__ rstd, const float* __restrict__ sum_dz,
                                     const float* __restrict__ sum_dzx, float inv_count, int act, int rows_per_block,
                                     float* __restrict__ acc_dbeta, float* __restrict__ acc_dgamma, float acc_scale) {
+  gp::pdl_sync();
   // affine-parameter gradients delivered straight into the parameters' .grad buffers (dbeta = sum dz, dgamma =
   // sum dz * xhat, times 1 / world under data parallelism): one block does it, no separate accumulation launches
   if (acc_dbeta != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {

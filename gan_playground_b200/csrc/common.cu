@@ -1,5 +1,6 @@
 #include "common.h"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace gp {
@@ -16,6 +17,15 @@ int set_error(int code, const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("GP_PDL");
+    on = (e != nullptr && e[0] == '1') ? 1 : 0;   // measured (profiles/r02_pdl_ab.txt): no gain inside CUDA graphs; off
+  }
+  return on == 1;
+}
 
 int num_sms() {
   static int cached[64] = {0};

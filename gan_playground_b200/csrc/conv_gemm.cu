@@ -106,7 +106,7 @@ static int launch_cfg(const ConvGemmParams& prm, int grid, cudaStream_t st) {
     GP_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<BNV, MTV, X3V>::kSmemBytes));
     attr_set = true;
   }
-  kfn<<<grid, kNumThreads, GemmCfg<BNV, MTV, X3V>::kSmemBytes, st>>>(prm);
+  gp::launch_pdl(kfn, grid, kNumThreads, GemmCfg<BNV, MTV, X3V>::kSmemBytes, st, prm);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -132,20 +132,8 @@ static int launch_fwd_pair(const ConvGemmParams& prm, int pair_tiles, cudaStream
   int pairs = num_sms() / 2;
   if (pair_tiles < pairs) pairs = pair_tiles;
   if (pairs <= 0) return GP_OK;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(2 * pairs, 1, 1);
-  cfg.blockDim = dim3(kNumThreads, 1, 1);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  GP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, prm));
+  GP_CHECK_CUDA(gp::launch_attrs(kfn, dim3(2 * pairs, 1, 1), dim3(kNumThreads, 1, 1), Cfg::kSmemBytes, st, gp::pdl_enabled(),
+                                 2u, prm));
   gp::count_launch();
   return GP_OK;
 }
@@ -163,20 +151,8 @@ static int launch_wgrad_pair(const ConvGemmParams& prm, int grid, cudaStream_t s
   }
   grid &= ~1;
   if (grid < 2) grid = 2;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(grid, 1, 1);
-  cfg.blockDim = dim3(kNumThreads, 1, 1);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  GP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, prm));
+  GP_CHECK_CUDA(gp::launch_attrs(kfn, dim3(grid, 1, 1), dim3(kNumThreads, 1, 1), Cfg::kSmemBytes, st, gp::pdl_enabled(), 2u,
+                                 prm));
   gp::count_launch();
   return GP_OK;
 }
@@ -544,6 +520,15 @@ extern "C" int gp_conv_wgrad(const gp_conv_wgrad_t* a, void* stream) {
   const long long total_ksteps = (long long)base_tiles * prm.kblocks_total;
   int grid = num_sms();
   if (total_ksteps < 4LL * grid) grid = (int)((total_ksteps + 3) / 4);
+  // Less than one wave of tiles, but most of one (e.g. 128 tiles of 256 x 256 for dW[1024][16][512] on 148 SMs): cutting
+  // every tile's K range over all CTAs would add each tile to dW twice (two partial accumulators per CTA, two atomic
+  // passes over a 33 MB gradient that a short K loop cannot hide). One whole tile per CTA on fewer CTAs moves half the
+  // atomic traffic for 1 / 0.75 more K steps at worst. GP_WGRAD_WHOLE=0 keeps the even cut.
+  {
+    static const bool whole = [] { const char* e = getenv("GP_WGRAD_WHOLE"); return e == nullptr || e[0] != '0'; }();
+    const int T = splits * base_tiles;
+    if (whole && grid == num_sms() && T < grid && 4 * T >= 3 * grid) grid = T;
+  }
   if (bn == 256 && mt_sub == 2 && grid == num_sms() && wgrad_pair_enabled())
     return launch_wgrad_pair(prm, grid, as_stream(stream));   // same 256 x 256 tiles, one per CTA pair
   return launch<MODE_WGRAD>(prm, bn, mt_sub, grid, as_stream(stream));

@@ -20,6 +20,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include "common.h"
 #include "sm100_ptx.cuh"
 
 namespace gp {
@@ -143,6 +144,10 @@ __device__ __forceinline__ void warp_transpose_sum32(float (&v)[32], int lane) {
 //   stage: this warp's 2 KB buffer (shared address); seg[4]: the lane's own row as four 16-byte vectors; base +
 //   row_byte_off: global address of the lane's own row; row_ok: that row is inside the tensor; col_lim: number of valid
 //   16-byte segments (partial last column tile).
+// RED: the 16-byte vectors are fp32 quadruples ADDED to global memory (red.global.add.v4.f32, the weight-gradient
+// epilogue): the same transposition makes every reduction instruction cover full 32-byte sectors of 8 rows instead of
+// half a sector of 32 rows - half as many L2 atomic transactions per tile.
+template <bool RED = false>
 __device__ __forceinline__ void store_rows_coalesced(uint32_t stage, const uint4 (&seg)[4], uint8_t* __restrict__ base,
                                                      long long row_byte_off, bool row_ok, int col_lim, int lane) {
   // swizzle: 16-byte slot (s ^ ((row >> 1) & 3)) of a 64-byte row -> conflict-free for both the row-wise writes and the
@@ -164,7 +169,10 @@ __device__ __forceinline__ void store_rows_coalesced(uint32_t stage, const uint4
     uint4 v;
     const uint32_t a = stage + r * 64 + ((sg ^ ((r >> 1) & 3)) << 4);
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
-    if (((okmask >> r) & 1u) && sg < col_lim) *reinterpret_cast<uint4*>(base + off + sg * 16) = v;
+    if (((okmask >> r) & 1u) && sg < col_lim) {
+      if constexpr (RED) red_add_v4(reinterpret_cast<float*>(base + off + sg * 16), v.x, v.y, v.z, v.w);
+      else *reinterpret_cast<uint4*>(base + off + sg * 16) = v;
+    }
   }
   __syncwarp();  // the buffer is rewritten by the next call
 }
@@ -227,6 +235,7 @@ template <int MODE, int BN, int MT, bool X3 = false, bool C2 = false>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   static_assert(!(X3 && MODE == MODE_WGRAD), "bf16x3 applies to the forward GEMMs only");
   using Cfg = GemmCfg<BN, MT, X3, C2>;
+  gp::pdl_launch_dependents();  // the next launch may become resident as this grid's CTAs retire (common.h)
   const uint32_t pair_rank = C2 ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs), 1 = peer
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -258,6 +267,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     fence_mbar_init();
   }
   if constexpr (C2) cluster_sync_all();  // the peer's barriers exist before anything can arrive on them
+  // Everything above touched shared memory and kernel parameters only. From here on the grids this one depends on must have
+  // completed and flushed. The wait also comes BEFORE the TMEM allocation: a CTA parked here while its predecessor still
+  // runs must not hold (or queue for) tensor memory that a co-resident CTA of the predecessor has yet to allocate.
+  gp::pdl_wait();
   if (warp == 1) {
     if constexpr (C2) {
       tmem_alloc_2cta(tmem_slot, Cfg::kTmemCols);
@@ -736,13 +749,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             if (mi + 1 < MT) tmem_ld_32x32(tbase + (mi + 1) * BN + c * 32, r);
             else if (c + 1 < nchunks) tmem_ld_32x32(tbase + (c + 1) * 32, r);
             const int m = (C2 ? 2 * mt + (int)pair_rank : mt * MT + mi) * kBlockM + q * 32 + lane;
-            if (m < p.M) {
-              float* drow = p.dw + static_cast<long long>(m) * p.ldw + col_base + col0;
+            // 16-byte vector reductions (red.global.add.v4.f32), transposed through the warp's staging buffer so that each
+            // instruction adds 8 rows x 64 contiguous bytes (two 64-byte halves of the lane's 32 columns)
+            const uint32_t stage = smem_u32(s_store) + (warp - 2) * 2048;
+            uint8_t* base = reinterpret_cast<uint8_t*>(p.dw + col_base + col0);
+            const long long row_off = static_cast<long long>(m) * p.ldw * 4;
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                // 16-byte vector reductions (red.global.add.v4.f32): 4x fewer L2 atomic transactions than scalar
-                if (col0 + g * 4 < ncols) red_add_v4(drow + g * 4, v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-              }
+            for (int hlf = 0; hlf < 2; ++hlf) {
+              uint4 seg[4];
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                seg[g] = make_uint4(v[hlf * 16 + 4 * g], v[hlf * 16 + 4 * g + 1], v[hlf * 16 + 4 * g + 2], v[hlf * 16 + 4 * g + 3]);
+              const int lim = (ncols - col0 - hlf * 16 + 3) / 4;  // valid 4-float segments of this half (<= 0: none)
+              store_rows_coalesced<true>(stage, seg, base + hlf * 64, row_off, m < p.M, lim, lane);
             }
           }
         }

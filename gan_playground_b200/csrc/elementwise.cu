@@ -16,6 +16,7 @@ namespace gp {
 __global__ void pack_matrix_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int K,
                                    int Rpad, int ld_dst, long long s_r, long long s_k, int perm,
                                    const float* __restrict__ inv_scale) {
+  gp::pdl_sync();
   const long long total = (long long)Rpad * ld_dst;
   const float sc = inv_scale ? 1.f / __ldg(inv_scale) : 1.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -41,6 +42,7 @@ constexpr int kPackCT = 64;  // channels per tile (n_dim == 0)
 __global__ void pack_conv_weight_n0_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                            __nv_bfloat16* __restrict__ lo, int N, int C, int taps, long long ld,
                                            int flip, const float* __restrict__ inv_scale) {
+  gp::pdl_sync();
   extern __shared__ float s_tile[];  // [kPackCT][taps + 1]
   const int n = blockIdx.y, c0 = blockIdx.x * kPackCT;
   const int ct = min(kPackCT, C - c0);
@@ -61,6 +63,7 @@ constexpr int kPackC1 = 32, kPackN1 = 8;  // tile of the n_dim == 1 variant: 32 
 __global__ void pack_conv_weight_n1_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                            __nv_bfloat16* __restrict__ lo, int N, int C, int taps, long long ld,
                                            int flip, const float* __restrict__ inv_scale) {
+  gp::pdl_sync();
   extern __shared__ float s_tile[];  // [kPackC1][kPackN1 * taps + 1]
   const int c0 = blockIdx.x * kPackC1, n0 = blockIdx.y * kPackN1;
   const int ct = min(kPackC1, C - c0), nt = min(kPackN1, N - n0);
@@ -88,6 +91,7 @@ constexpr int kPack16C = 128;
 __global__ void __launch_bounds__(256) pack_conv_weight16_n0_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                                     __nv_bfloat16* __restrict__ lo, int N, int C, long long ld,
                                                                     const float* __restrict__ inv_scale) {
+  gp::pdl_sync();
   __shared__ float s_tile[kPack16C * 17];  // [c][16 taps + 1 pad]
   const int n = blockIdx.y, c0 = blockIdx.x * kPack16C;  // C % 128 == 0 on this path
   const float sc = inv_scale ? 1.f / __ldg(inv_scale) : 1.f;
@@ -113,6 +117,7 @@ __global__ void __launch_bounds__(256) pack_conv_weight16_n0_kernel(const float*
 __global__ void __launch_bounds__(256) pack_conv_weight16_n1_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                                     __nv_bfloat16* __restrict__ lo, int N, int C, long long ld,
                                                                     const float* __restrict__ inv_scale) {
+  gp::pdl_sync();
   __shared__ float s_tile[32 * 129];  // [c][8 n x 16 taps + 1 pad]
   const int c0 = blockIdx.x * 32, n0 = blockIdx.y * 8;  // C % 32 == 0, N % 8 == 0 on this path
   const float sc = inv_scale ? 1.f / __ldg(inv_scale) : 1.f;
@@ -140,6 +145,7 @@ __global__ void __launch_bounds__(256) pack_conv_weight16_n1_kernel(const float*
 // acc != 0: dst += value (the parameter's .grad buffer is the destination: no AccumulateGrad pass afterwards)
 __global__ void __launch_bounds__(256) unpack_conv_wgrad16_kernel(const float* __restrict__ src, float* __restrict__ dst, int M,
                                                                   int N, int acc) {
+  gp::pdl_sync();
   __shared__ float s_tile[16 * 65];  // [t][64 n + 1 pad]
   const int m = blockIdx.y, n0 = blockIdx.x * 64;  // N % 64 == 0 on this path
   {
@@ -169,6 +175,7 @@ __global__ void __launch_bounds__(256) unpack_conv_wgrad16_kernel(const float* _
 constexpr int kUnpackNT = 64;
 __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int M, int N, int taps,
                                          int acc) {
+  gp::pdl_sync();
   extern __shared__ float s_tile[];  // [taps][kUnpackNT + 1]
   const int m = blockIdx.y, n0 = blockIdx.x * kUnpackNT;
   const int nt = min(kUnpackNT, N - n0);
@@ -187,6 +194,7 @@ __global__ void unpack_conv_wgrad_kernel(const float* __restrict__ src, float* _
 // fp32 [Rpad][ld_src] (gradient of a packed matrix) -> dst[map(r) * s_r + k * s_k] for r < R, k < K (inverse of pack_matrix)
 __global__ void unpack_matrix_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int K, int ld_src,
                                      long long s_r, long long s_k, int perm, int acc) {
+  gp::pdl_sync();
   const long long total = (long long)R * K;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / K), k = (int)(i % K);
@@ -211,6 +219,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
                                    const float* __restrict__ beta, float* __restrict__ mean, float* __restrict__ rstd,
                                    float* __restrict__ scale, float* __restrict__ shift, float* running_mean,
                                    float* running_var, long long* num_batches_tracked) {
+  gp::pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
   if (c >= C) return;
@@ -235,6 +244,7 @@ __global__ void bn_eval_kernel(const float* __restrict__ rm, const float* __rest
                                const float* __restrict__ gamma, const float* __restrict__ beta, int C, float eps,
                                float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ scale,
                                float* __restrict__ shift) {
+  gp::pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float r = rsqrtf(rv[c] + eps);
@@ -248,6 +258,7 @@ __global__ void bn_eval_kernel(const float* __restrict__ rm, const float* __rest
 // dy = da * act'(a)   (activation applied directly on the conv output: a has the sign of the pre-activation)
 __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ a,
                                __nv_bfloat16* __restrict__ dy, long long n8, int act) {
+  gp::pdl_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     Vec8<__nv_bfloat16> va, vd;
     va.load(a + i * 8);
@@ -282,6 +293,7 @@ constexpr int kIm2colRows = 4;
 __global__ void im2col_k4s2_kernel(const float* __restrict__ img, const float* __restrict__ mul,
                                    __nv_bfloat16* __restrict__ col, __nv_bfloat16* __restrict__ col_lo, int NB, int ch,
                                    int Hi, int Wi) {
+  gp::pdl_sync();
   extern __shared__ float s_img[];  // [ch][2*kIm2colRows + 2][Wi]
   constexpr int kInRows = 2 * kIm2colRows + 2;
   const int Ho = Hi / 2, Wo = Wi / 2;
@@ -326,6 +338,7 @@ constexpr int kCol2imRows = 8;
 template <typename TC, int CH>
 __global__ void __launch_bounds__(256) col2im_k4s2_kernel(const TC* __restrict__ col, const float* __restrict__ bias,
                                                           float* __restrict__ img, int NB, int Hi, int Wi, int act) {
+  gp::pdl_sync();
   extern __shared__ float s_col[];  // [kCol2imRows/2 + 2][Wo][CH*16 + 1]
   constexpr int kColRows = kCol2imRows / 2 + 2;
   constexpr int live = CH * 16, pitch = live + 1, groups = live / 8;
@@ -388,6 +401,7 @@ __global__ void __launch_bounds__(256) col2im_k4s2_kernel(const TC* __restrict__
 // dbias[c] += sum_{n,h,w} dout[n,c,h,w] * (mul ? 1 - mul^2 : 1)   (bias gradient of the last ConvT under Tanh)
 __global__ void image_bias_grad_kernel(const float* __restrict__ dout, const float* __restrict__ mul,
                                        float* __restrict__ dbias, int NB, int ch, int HW) {
+  gp::pdl_sync();
   const int c = blockIdx.y;
   float acc = 0.f;
   const long long total = (long long)NB * HW;
@@ -418,6 +432,7 @@ __global__ void image_bias_grad_kernel(const float* __restrict__ dout, const flo
 __global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ a, const void* __restrict__ a_comp, int fmt,
                                 const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
                                 int HW, int C, int O, long long s_o, long long s_c, long long s_hw) {
+  gp::pdl_sync();
   const int b = blockIdx.x, o = blockIdx.y;
   float acc = 0.f;
   const long long base = (long long)b * HW * C;
@@ -477,6 +492,7 @@ __global__ void __launch_bounds__(256) head_fwd_multi_kernel(const __nv_bfloat16
                                                              int fmt, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ out, int HW,
                                                              int C, int O, long long s_o, long long s_c, long long s_hw) {
+  gp::pdl_sync();
   const int b = blockIdx.x;
   float acc[kHeadMaxO];
 #pragma unroll
@@ -518,6 +534,7 @@ __global__ void __launch_bounds__(256) head_fwd_multi_kernel(const __nv_bfloat16
 __global__ void head_bwd_data_kernel(const float* __restrict__ dout, const float* __restrict__ w,
                                      __nv_bfloat16* __restrict__ da, int NB, int HW, int C, int O, long long s_o,
                                      long long s_c, long long s_hw) {
+  gp::pdl_sync();
   const int c8 = C / 8;
   const long long total = (long long)NB * HW * c8;
   const bool vec = s_c == 1 && ((s_o | s_hw) & 3) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0;
@@ -548,6 +565,7 @@ __global__ void head_bwd_data_kernel(const float* __restrict__ dout, const float
 __global__ void head_bwd_weight_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ a,
                                        float* __restrict__ dw, float* __restrict__ dbias, int NB, int HW, int C, int O,
                                        long long s_o, long long s_c, long long s_hw) {
+  gp::pdl_sync();
   const int o = blockIdx.y;
   const int c8 = C / 8;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // index over HW * C/8
@@ -611,6 +629,7 @@ __global__ void head_bwd_weight_kernel(const float* __restrict__ dout, const __n
 __global__ void __launch_bounds__(256) head_bwd_weight_pool_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ a,
                                                                    float* __restrict__ dw, int NB, int HW, int C, int O,
                                                                    long long s_o, long long s_c) {
+  gp::pdl_sync();
   __shared__ float s_acc[8][256];
   const int o = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = (blockIdx.x * 32 + lane) * 8;
@@ -670,6 +689,7 @@ __global__ void __launch_bounds__(256) head_bwd_weight_pool_multi_kernel(const f
                                                                          const __nv_bfloat16* __restrict__ a,
                                                                          float* __restrict__ dw, int NB, int HW, int C, int O,
                                                                          long long s_o, long long s_c) {
+  gp::pdl_sync();
   __shared__ float s_acc[8][256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = (blockIdx.x * 32 + lane) * 8;
@@ -722,6 +742,7 @@ __global__ void __launch_bounds__(256) head_bwd_weight_pool_multi_kernel(const f
 
 // dbias[o] = sum_b dout[b][o]   (one block per output)
 __global__ void head_bias_grad_kernel(const float* __restrict__ dout, float* __restrict__ dbias, int NB, int O) {
+  gp::pdl_sync();
   const int o = blockIdx.x;
   float s = 0.f;
   for (int b = threadIdx.x; b < NB; b += blockDim.x) s += __ldg(dout + (long long)b * O + o);
@@ -772,6 +793,7 @@ __device__ __forceinline__ float block_sum(float acc, float* red) {
 
 __global__ void gan_loss_kernel(const float* __restrict__ pred, int n, int mode, float target, float inv_n,
                                 float* __restrict__ loss, float* __restrict__ dpred) {
+  gp::pdl_sync();
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     float l, d;
@@ -792,6 +814,7 @@ __global__ void gan_loss_kernel(const float* __restrict__ pred, int n, int mode,
 __global__ void acgan_loss_kernel(const float* __restrict__ logits, const float* __restrict__ labels, int NB, int K,
                                   int mode, float target, float aux_weight, float* __restrict__ out,
                                   float* __restrict__ dlogits) {
+  gp::pdl_sync();
   const int ld = K + 1;
   const float inv_nb = 1.f / (float)NB, inv_aux = 1.f / ((float)NB * (float)K);
   float s_adv = 0.f, s_aux = 0.f, s_sig = 0.f;
@@ -835,17 +858,16 @@ static int launch_pack_conv_weight(const float* src, __nv_bfloat16* dst, __nv_bf
   const int n_dim = n_dim_flags & 1, flip = (n_dim_flags >> 1) & 1;
   const int N = n_dim == 0 ? D0 : D1, C = n_dim == 0 ? D1 : D0;
   if (taps == 16 && !flip && n_dim == 0 && C % kPack16C == 0) {
-    pack_conv_weight16_n0_kernel<<<dim3(C / kPack16C, N), 256, 0, st>>>(src, dst, lo, N, C, ld, inv_scale);
+    gp::launch_pdl(pack_conv_weight16_n0_kernel, dim3(C / kPack16C, N), 256, 0, st, src, dst, lo, N, C, ld, inv_scale);
   } else if (taps == 16 && !flip && n_dim == 1 && C % 32 == 0 && N % 8 == 0) {
-    pack_conv_weight16_n1_kernel<<<dim3(C / 32, N / 8), 256, 0, st>>>(src, dst, lo, N, C, ld, inv_scale);
+    gp::launch_pdl(pack_conv_weight16_n1_kernel, dim3(C / 32, N / 8), 256, 0, st, src, dst, lo, N, C, ld, inv_scale);
   } else if (n_dim == 0) {
     dim3 grid((D1 + kPackCT - 1) / kPackCT, D0);
-    pack_conv_weight_n0_kernel<<<grid, 256, (size_t)kPackCT * (taps + 1) * sizeof(float), st>>>(src, dst, lo, D0, D1, taps,
+    gp::launch_pdl(pack_conv_weight_n0_kernel, grid, 256, (size_t)kPackCT * (taps + 1) * sizeof(float), st, src, dst, lo, D0, D1, taps,
                                                                                              ld, flip, inv_scale);
   } else {
     dim3 grid((D0 + kPackC1 - 1) / kPackC1, (D1 + kPackN1 - 1) / kPackN1);
-    pack_conv_weight_n1_kernel<<<grid, 256, (size_t)kPackC1 * (kPackN1 * taps + 1) * sizeof(float), st>>>(
-        src, dst, lo, D1, D0, taps, ld, flip, inv_scale);
+    gp::launch_pdl(pack_conv_weight_n1_kernel, grid, 256, (size_t)kPackC1 * (kPackN1 * taps + 1) * sizeof(float), st, src, dst, lo, D1, D0, taps, ld, flip, inv_scale);
   }
   GP_CHECK_LAUNCH();
   return GP_OK;
@@ -861,8 +883,7 @@ int gp_pack_matrix(const float* src, void* dst, int R, int K, int Rpad, int ld_d
                    int perm, const float* inv_scale, void* stream) {
   GP_REQUIRE(src && dst && R > 0 && K > 0 && Rpad >= R && ld_dst >= K, "gp_pack_matrix: bad arguments");
   GP_REQUIRE(perm <= 1 || R % perm == 0, "gp_pack_matrix: perm must divide R");
-  pack_matrix_kernel<<<grid_for((long long)Rpad * ld_dst), 256, 0, as_stream(stream)>>>(
-      src, static_cast<__nv_bfloat16*>(dst), R, K, Rpad, ld_dst, s_r, s_k, perm, inv_scale);
+  gp::launch_pdl(pack_matrix_kernel, grid_for((long long)Rpad * ld_dst), 256, 0, as_stream(stream), src, static_cast<__nv_bfloat16*>(dst), R, K, Rpad, ld_dst, s_r, s_k, perm, inv_scale);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -870,7 +891,7 @@ int gp_pack_matrix(const float* src, void* dst, int R, int K, int Rpad, int ld_d
 int gp_unpack_matrix(const float* src, float* dst, int R, int K, int ld_src, long long s_r, long long s_k, int perm,
                      void* stream) {
   GP_REQUIRE(src && dst && R > 0 && K > 0 && ld_src >= K, "gp_unpack_matrix: bad arguments");
-  unpack_matrix_kernel<<<grid_for((long long)R * K), 256, 0, as_stream(stream)>>>(src, dst, R, K, ld_src, s_r, s_k,
+  gp::launch_pdl(unpack_matrix_kernel, grid_for((long long)R * K), 256, 0, as_stream(stream), src, dst, R, K, ld_src, s_r, s_k,
                                                                                   perm & 0x3fffffff, (perm >> 30) & 1);
   GP_CHECK_LAUNCH();
   return GP_OK;
@@ -901,12 +922,12 @@ int gp_unpack_conv_wgrad(const float* src, float* dst, int M, int N, int taps, v
   taps &= 0x3fffffff;
   GP_REQUIRE(src && dst && M > 0 && N > 0 && taps > 0 && taps <= 64, "gp_unpack_conv_wgrad: bad arguments");
   if (taps == 16 && N % 64 == 0) {
-    unpack_conv_wgrad16_kernel<<<dim3(N / 64, M), 256, 0, as_stream(stream)>>>(src, dst, M, N, acc);
+    gp::launch_pdl(unpack_conv_wgrad16_kernel, dim3(N / 64, M), 256, 0, as_stream(stream), src, dst, M, N, acc);
     GP_CHECK_LAUNCH();
     return GP_OK;
   }
   dim3 grid((N + kUnpackNT - 1) / kUnpackNT, M);
-  unpack_conv_wgrad_kernel<<<grid, 256, (size_t)taps * (kUnpackNT + 1) * sizeof(float), as_stream(stream)>>>(src, dst, M,
+  gp::launch_pdl(unpack_conv_wgrad_kernel, grid, 256, (size_t)taps * (kUnpackNT + 1) * sizeof(float), as_stream(stream), src, dst, M,
                                                                                                           N, taps, acc);
   GP_CHECK_LAUNCH();
   return GP_OK;
@@ -915,8 +936,7 @@ int gp_unpack_conv_wgrad(const float* src, float* dst, int M, int N, int taps, v
 int gp_bn_stats(const void* x, long long P, int C, float* sum, float* sumsq, void* stream) {
   GP_REQUIRE(x && sum && sumsq && P > 0 && C > 0 && C % 8 == 0, "gp_bn_stats: bad arguments (C %% 8 == 0 required)");
   const ColLaunch L = col_launch(P, C, 2);
-  col_stats_kernel<__nv_bfloat16, true><<<L.grid, L.block, L.smem, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), P, C, sum, sumsq, L.rpb);
+  gp::launch_pdl(col_stats_kernel<__nv_bfloat16, true>, L.grid, L.block, L.smem, as_stream(stream), static_cast<const __nv_bfloat16*>(x), P, C, sum, sumsq, L.rpb);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -925,7 +945,7 @@ int gp_bn_finalize(const float* sum, const float* sumsq, double count, int C, fl
                    const float* gamma, const float* beta, float* mean, float* rstd, float* scale, float* shift,
                    float* running_mean, float* running_var, long long* num_batches_tracked, void* stream) {
   GP_REQUIRE(sum && sumsq && mean && rstd && scale && shift && C > 0 && count > 0, "gp_bn_finalize: bad arguments");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(sum, sumsq, count, C, eps, momentum, gamma, beta,
+  gp::launch_pdl(bn_finalize_kernel, (C + 127) / 128, 128, 0, as_stream(stream), sum, sumsq, count, C, eps, momentum, gamma, beta,
                                                                     mean, rstd, scale, shift, running_mean,
                                                                     running_var, num_batches_tracked);
   GP_CHECK_LAUNCH();
@@ -935,7 +955,7 @@ int gp_bn_finalize(const float* sum, const float* sumsq, double count, int C, fl
 int gp_bn_eval_params(const float* running_mean, const float* running_var, const float* gamma, const float* beta, int C,
                       float eps, float* mean, float* rstd, float* scale, float* shift, void* stream) {
   GP_REQUIRE(running_mean && running_var && mean && rstd && scale && shift && C > 0, "gp_bn_eval_params: bad arguments");
-  bn_eval_kernel<<<(C + 127) / 128, 128, 0, as_stream(stream)>>>(running_mean, running_var, gamma, beta, C, eps, mean,
+  gp::launch_pdl(bn_eval_kernel, (C + 127) / 128, 128, 0, as_stream(stream), running_mean, running_var, gamma, beta, C, eps, mean,
                                                                 rstd, scale, shift);
   GP_CHECK_LAUNCH();
   return GP_OK;
@@ -945,8 +965,7 @@ int gp_bn_apply_act(const void* y, void* out, long long P, int C, const float* s
                     void* stream) {
   GP_REQUIRE(y && out && scale && shift && P > 0 && C % 8 == 0, "gp_bn_apply_act: bad arguments");
   const ColLaunch L = col_launch(P, C, 0);
-  bn_apply_kernel<__nv_bfloat16><<<L.grid, L.block, 0, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(out), nullptr, P, C, scale, shift, act, L.rpb);
+  gp::launch_pdl(bn_apply_kernel<__nv_bfloat16>, L.grid, L.block, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(out), nullptr, P, C, scale, shift, act, L.rpb);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -955,8 +974,7 @@ int gp_bn_bwd_reduce(const void* da, const void* y, long long P, int C, const fl
                      const float* mean, const float* rstd, int act, float* sum_dz, float* sum_dzx, void* stream) {
   GP_REQUIRE(da && y && sum_dz && sum_dzx && P > 0 && C % 8 == 0, "gp_bn_bwd_reduce: bad arguments");
   const ColLaunch L = col_launch(P, C, 2, 2);
-  bn_bwd_reduce_kernel<__nv_bfloat16><<<L.grid, L.block, L.smem, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), P, C, scale, shift, mean, rstd, act,
+  gp::launch_pdl(bn_bwd_reduce_kernel<__nv_bfloat16>, L.grid, L.block, L.smem, as_stream(stream), static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), P, C, scale, shift, mean, rstd, act,
       sum_dz, sum_dzx, L.rpb);
   GP_CHECK_LAUNCH();
   return GP_OK;
@@ -969,8 +987,7 @@ int gp_bn_bwd_apply(const void* da, const void* y, void* dy, long long P, int C,
   GP_REQUIRE(da && y && dy && P > 0 && C % 8 == 0 && count > 0, "gp_bn_bwd_apply: bad arguments");
   GP_REQUIRE((acc_dbeta == nullptr) == (acc_dgamma == nullptr), "gp_bn_bwd_apply: acc_dbeta and acc_dgamma go together");
   const ColLaunch L = col_launch(P, C, 0);
-  bn_bwd_apply_kernel<__nv_bfloat16><<<L.grid, L.block, 0, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(dy), P, C,
+  gp::launch_pdl(bn_bwd_apply_kernel<__nv_bfloat16>, L.grid, L.block, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(dy), P, C,
       scale, shift, mean, rstd, sum_dz, sum_dzx, (float)(1.0 / count), act, L.rpb, acc_dbeta, acc_dgamma, acc_scale);
   GP_CHECK_LAUNCH();
   return GP_OK;
@@ -978,7 +995,7 @@ int gp_bn_bwd_apply(const void* da, const void* y, void* dy, long long P, int C,
 
 int gp_act_bwd(const void* da, const void* a, void* dy, long long n, int act, void* stream) {
   GP_REQUIRE(da && a && dy && n > 0 && n % 8 == 0, "gp_act_bwd: bad arguments");
-  act_bwd_kernel<<<grid_for(n / 8), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(da),
+  gp::launch_pdl(act_bwd_kernel, grid_for(n / 8), 256, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(da),
                                                                  static_cast<const __nv_bfloat16*>(a),
                                                                  static_cast<__nv_bfloat16*>(dy), n / 8, act);
   GP_CHECK_LAUNCH();
@@ -988,8 +1005,7 @@ int gp_act_bwd(const void* da, const void* a, void* dy, long long n, int act, vo
 int gp_colsum(const void* x, long long P, int C, float* out, void* stream) {
   GP_REQUIRE(x && out && P > 0 && C % 8 == 0, "gp_colsum: bad arguments");
   const ColLaunch L = col_launch(P, C, 1);
-  col_stats_kernel<__nv_bfloat16, false><<<L.grid, L.block, L.smem, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), P, C, out, nullptr, L.rpb);
+  gp::launch_pdl(col_stats_kernel<__nv_bfloat16, false>, L.grid, L.block, L.smem, as_stream(stream), static_cast<const __nv_bfloat16*>(x), P, C, out, nullptr, L.rpb);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -1002,7 +1018,7 @@ static int launch_im2col(const float* img, const float* mul, void* col, void* co
   const size_t smem = (size_t)ch * (2 * kIm2colRows + 2) * Wi * sizeof(float);
   GP_REQUIRE(smem <= 48 * 1024, "gp_im2col_k4s2: image rows too wide (Wi=%d)", Wi);
   dim3 grid((Hi / 2 + kIm2colRows - 1) / kIm2colRows, NB);
-  im2col_k4s2_kernel<<<grid, 256, smem, as_stream(stream)>>>(img, mul, static_cast<__nv_bfloat16*>(col),
+  gp::launch_pdl(im2col_k4s2_kernel, grid, 256, smem, as_stream(stream), img, mul, static_cast<__nv_bfloat16*>(col),
                                                              static_cast<__nv_bfloat16*>(col_lo), NB, ch, Hi, Wi);
   GP_CHECK_LAUNCH();
   return GP_OK;
@@ -1017,7 +1033,7 @@ static int launch_col2im_ch(const TC* col, const float* bias, float* img, int NB
     GP_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   dim3 grid((Hi + kCol2imRows - 1) / kCol2imRows, NB);
-  kfn<<<grid, 256, smem, st>>>(col, bias, img, NB, Hi, Wi, act);
+  gp::launch_pdl(kfn, grid, 256, smem, st, col, bias, img, NB, Hi, Wi, act);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -1058,7 +1074,7 @@ int gp_col2im_k4s2_f32(const float* col, const float* bias, float* img, int NB, 
 int gp_image_bias_grad(const float* dout, const float* mul, float* dbias, int NB, int ch, int HW, void* stream) {
   GP_REQUIRE(dout && dbias && NB > 0 && ch > 0 && HW > 0, "gp_image_bias_grad: bad arguments");
   dim3 grid(grid_for((long long)NB * HW, 256, 148 * 2), ch);
-  image_bias_grad_kernel<<<grid, 256, 0, as_stream(stream)>>>(dout, mul, dbias, NB, ch, HW);
+  gp::launch_pdl(image_bias_grad_kernel, grid, 256, 0, as_stream(stream), dout, mul, dbias, NB, ch, HW);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -1067,13 +1083,13 @@ int gp_head_fwd(const void* a, const float* w, const float* bias, float* out, in
                 long long s_o, long long s_c, long long s_hw, void* stream) {
   GP_REQUIRE(a && w && out && NB > 0 && HW > 0 && C > 0 && C % 8 == 0 && O > 0, "gp_head_fwd: bad arguments");
   if (O > 1 && O <= kHeadMaxO) {
-    head_fwd_multi_kernel<<<NB, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(a), nullptr, GP_COMP_NONE, w, bias,
+    gp::launch_pdl(head_fwd_multi_kernel, NB, 256, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(a), nullptr, GP_COMP_NONE, w, bias,
                                                              out, HW, C, O, s_o, s_c, s_hw);
     GP_CHECK_LAUNCH();
     return GP_OK;
   }
   dim3 grid(NB, O);
-  head_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(a), nullptr, GP_COMP_NONE, w, bias,
+  gp::launch_pdl(head_fwd_kernel, grid, 256, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(a), nullptr, GP_COMP_NONE, w, bias,
                                                        out, HW, C, O, s_o, s_c, s_hw);
   GP_CHECK_LAUNCH();
   return GP_OK;
@@ -1083,7 +1099,7 @@ int gp_head_fwd_split(const void* a_hi, const void* a_lo, const float* w, const 
                       int C, int O, long long s_o, long long s_c, long long s_hw, void* stream) {
   GP_REQUIRE(a_hi && a_lo && w && out && NB > 0 && HW > 0 && C > 0 && C % 8 == 0 && O > 0, "gp_head_fwd_split: bad arguments");
   dim3 grid(NB, O);
-  head_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(a_hi), a_lo, GP_COMP_LO, w, bias,
+  gp::launch_pdl(head_fwd_kernel, grid, 256, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(a_hi), a_lo, GP_COMP_LO, w, bias,
                                                        out, HW, C, O, s_o, s_c, s_hw);
   GP_CHECK_LAUNCH();
   return GP_OK;
@@ -1094,13 +1110,13 @@ int gp_head_fwd_comp(const void* a, const void* a_comp, int comp_fmt, const floa
   GP_REQUIRE(a && w && out && NB > 0 && HW > 0 && C > 0 && C % 8 == 0 && O > 0, "gp_head_fwd_comp: bad arguments");
   GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_head_fwd_comp: unknown companion format %d", comp_fmt);
   if (O > 1 && O <= kHeadMaxO) {   // several heads packed: read the features once for all of them
-    head_fwd_multi_kernel<<<NB, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(a), a_comp, comp_fmt, w, bias, out,
+    gp::launch_pdl(head_fwd_multi_kernel, NB, 256, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(a), a_comp, comp_fmt, w, bias, out,
                                                              HW, C, O, s_o, s_c, s_hw);
     GP_CHECK_LAUNCH();
     return GP_OK;
   }
   dim3 grid(NB, O);
-  head_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(a), a_comp, comp_fmt, w, bias, out,
+  gp::launch_pdl(head_fwd_kernel, grid, 256, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(a), a_comp, comp_fmt, w, bias, out,
                                                        HW, C, O, s_o, s_c, s_hw);
   GP_CHECK_LAUNCH();
   return GP_OK;
@@ -1110,8 +1126,7 @@ int gp_head_bwd(const float* dout, const void* a, const float* w, void* da, floa
                 int C, int O, long long s_o, long long s_c, long long s_hw, void* stream) {
   GP_REQUIRE(dout && a && w && NB > 0 && HW > 0 && C > 0 && C % 8 == 0 && O > 0, "gp_head_bwd: bad arguments");
   if (da != nullptr) {
-    head_bwd_data_kernel<<<grid_for((long long)NB * HW * (C / 8)), 256, 0, as_stream(stream)>>>(
-        dout, w, static_cast<__nv_bfloat16*>(da), NB, HW, C, O, s_o, s_c, s_hw);
+    gp::launch_pdl(head_bwd_data_kernel, grid_for((long long)NB * HW * (C / 8)), 256, 0, as_stream(stream), dout, w, static_cast<__nv_bfloat16*>(da), NB, HW, C, O, s_o, s_c, s_hw);
     GP_CHECK_LAUNCH();
   }
   if (dw != nullptr && s_hw == 0 && O > 1 && O <= kHeadMaxO) {
@@ -1119,11 +1134,10 @@ int gp_head_bwd(const float* dout, const void* a, const float* w, void* da, floa
     int zsplit = (2 * num_sms()) / gx;
     if (zsplit < 1) zsplit = 1;
     if (zsplit > (NB + 7) / 8) zsplit = (NB + 7) / 8;
-    head_bwd_weight_pool_multi_kernel<<<dim3(gx, zsplit), 256, 0, as_stream(stream)>>>(
-        dout, static_cast<const __nv_bfloat16*>(a), dw, NB, HW, C, O, s_o, s_c);
+    gp::launch_pdl(head_bwd_weight_pool_multi_kernel, dim3(gx, zsplit), 256, 0, as_stream(stream), dout, static_cast<const __nv_bfloat16*>(a), dw, NB, HW, C, O, s_o, s_c);
     GP_CHECK_LAUNCH();
     if (dbias != nullptr) {
-      head_bias_grad_kernel<<<O, 256, 0, as_stream(stream)>>>(dout, dbias, NB, O);
+      gp::launch_pdl(head_bias_grad_kernel, O, 256, 0, as_stream(stream), dout, dbias, NB, O);
       GP_CHECK_LAUNCH();
     }
   } else if (dw != nullptr && s_hw == 0) {
@@ -1131,11 +1145,11 @@ int gp_head_bwd(const float* dout, const void* a, const float* w, void* da, floa
     int zsplit = (4 * num_sms()) / (gx * O);
     if (zsplit < 1) zsplit = 1;
     if (zsplit > NB) zsplit = NB;
-    head_bwd_weight_pool_kernel<<<dim3(gx, O, zsplit), 256, 0, as_stream(stream)>>>(dout, static_cast<const __nv_bfloat16*>(a),
+    gp::launch_pdl(head_bwd_weight_pool_kernel, dim3(gx, O, zsplit), 256, 0, as_stream(stream), dout, static_cast<const __nv_bfloat16*>(a),
                                                                                  dw, NB, HW, C, O, s_o, s_c);
     GP_CHECK_LAUNCH();
     if (dbias != nullptr) {
-      head_bias_grad_kernel<<<O, 256, 0, as_stream(stream)>>>(dout, dbias, NB, O);
+      gp::launch_pdl(head_bias_grad_kernel, O, 256, 0, as_stream(stream), dout, dbias, NB, O);
       GP_CHECK_LAUNCH();
     }
   } else if (dw != nullptr) {
@@ -1145,7 +1159,7 @@ int gp_head_bwd(const float* dout, const void* a, const float* w, void* da, floa
     if (zsplit > 64) zsplit = 64;
     if (zsplit > NB) zsplit = NB;
     dim3 grid(gx, O, zsplit);
-    head_bwd_weight_kernel<<<grid, 128, 0, as_stream(stream)>>>(dout, static_cast<const __nv_bfloat16*>(a), dw, dbias, NB,
+    gp::launch_pdl(head_bwd_weight_kernel, grid, 128, 0, as_stream(stream), dout, static_cast<const __nv_bfloat16*>(a), dw, dbias, NB,
                                                                 HW, C, O, s_o, s_c, s_hw);
     GP_CHECK_LAUNCH();
   }
@@ -1154,7 +1168,7 @@ int gp_head_bwd(const float* dout, const void* a, const float* w, void* da, floa
 
 int gp_gan_loss(const float* pred, int n, int mode, float target, float* loss, float* dpred, void* stream) {
   GP_REQUIRE(pred && loss && dpred && n > 0 && mode >= 0 && mode <= 4, "gp_gan_loss: bad arguments");
-  gan_loss_kernel<<<1, 256, 0, as_stream(stream)>>>(pred, n, mode, target, 1.f / (float)n, loss, dpred);
+  gp::launch_pdl(gan_loss_kernel, 1, 256, 0, as_stream(stream), pred, n, mode, target, 1.f / (float)n, loss, dpred);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -1164,7 +1178,7 @@ int gp_acgan_loss(const float* logits, const float* labels, int NB, int K, int m
   GP_REQUIRE(logits && labels && out4 && dlogits && NB > 0 && K > 0 && mode >= 0 && mode <= 4 &&
                  (long long)NB * (K + 1) < (1ll << 30),
              "gp_acgan_loss: bad arguments");
-  acgan_loss_kernel<<<1, 256, 0, as_stream(stream)>>>(logits, labels, NB, K, mode, target, aux_weight, out4, dlogits);
+  gp::launch_pdl(acgan_loss_kernel, 1, 256, 0, as_stream(stream), logits, labels, NB, K, mode, target, aux_weight, out4, dlogits);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }

@@ -223,6 +223,7 @@ struct EdgeFwdParams {
 //                 patch (| mul patch) | 2 barriers | TMEM slot]
 template <int FMT, bool MUL>
 __global__ void __launch_bounds__(kEdgeThreads) image_conv_fwd_kernel(const __grid_constant__ EdgeFwdParams p) {
+  gp::pdl_sync();
   constexpr bool X3 = FMT == GP_COMP_LO;
   constexpr bool COMP = FMT != GP_COMP_NONE;
   constexpr int HALVES = X3 ? 2 : 1;
@@ -451,6 +452,7 @@ struct EdgeWgradParams {
 // wanted, so accumulator column 48 = sum_px dense.
 template <bool MUL, int STAGES>
 __global__ void __launch_bounds__(kEdgeThreads, 1) image_conv_wgrad_kernel(const __grid_constant__ EdgeWgradParams p) {
+  gp::pdl_sync();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const EdgeGeom g = p.g;
@@ -609,6 +611,7 @@ constexpr int kExRows = 192;  // exchange rows: 128 owned pixels + 2 * Ws halo p
 // lo * w_hi): 90 KB, two CTAs per SM.
 template <int FMT>
 __global__ void __launch_bounds__(kEdgeThreads) image_convt_fwd_kernel(const __grid_constant__ EdgeConvTParams p) {
+  gp::pdl_sync();
   constexpr bool X3 = FMT == GP_COMP_LO;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -894,7 +897,7 @@ extern "C" int gp_image_conv_k4s2_fwd(const float* img, const float* mul, const 
     if (per_sm > 512 / Cout) per_sm = 512 / Cout;  // TMEM columns
     const long long cap = (long long)num_sms() * per_sm;
     const int grid = (int)(p.g.tiles < cap ? p.g.tiles : cap);
-    kfn<<<grid, kEdgeThreads, smem, as_stream(stream)>>>(p);
+    gp::launch_pdl(kfn, grid, kEdgeThreads, smem, as_stream(stream), p);
     GP_CHECK_LAUNCH();
     return edge_debug_check(__func__, stream);
   };
@@ -927,7 +930,7 @@ extern "C" int gp_image_conv_k4s2_wgrad(const void* dense, const float* img, con
   auto launch = [&](auto kfn, int stages) -> int {
     const int smem = 1024 + stages * 32768 + 2 * 16384 + stages * (mul != nullptr ? 2 : 1) * p.g.patch_stride + 128;
     GP_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kfn<<<grid, kEdgeThreads, smem, as_stream(stream)>>>(p);
+    gp::launch_pdl(kfn, grid, kEdgeThreads, smem, as_stream(stream), p);
     GP_CHECK_LAUNCH();
     return edge_debug_check(__func__, stream);
   };
@@ -966,7 +969,7 @@ extern "C" int gp_image_convt_k4s2_fwd(const void* x, const void* x_lo, int fmt,
     if (per_sm > 4) per_sm = 4;  // TMEM: 128 columns per CTA
     const long long cap = (long long)num_sms() * per_sm;
     const int grid = (int)(p.tiles < cap ? p.tiles : cap);
-    kfn<<<grid, kEdgeThreads, smem, as_stream(stream)>>>(p);
+    gp::launch_pdl(kfn, grid, kEdgeThreads, smem, as_stream(stream), p);
     GP_CHECK_LAUNCH();
     return edge_debug_check(__func__, stream);
   };

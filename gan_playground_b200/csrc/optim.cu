@@ -12,6 +12,7 @@ namespace gp {
 __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                  float* __restrict__ v, long long n4, float lr, float beta1, float beta2, float w1,
                                  float w2, float eps, const float* __restrict__ step, float grad_scale) {
+  gp::pdl_sync();
   // w1 = 1 - beta1, w2 = 1 - beta2 are rounded from the host's double arithmetic, as torch does (python floats)
   const float t = __ldg(step) + 1.f;
   const float bc1 = 1.f - powf(beta1, t);
@@ -54,8 +55,7 @@ extern "C" int gp_adam_flat(float* p, const float* g, float* m, float* v, long l
   long long blocks = (n4 + 255) / 256;
   const long long cap = (long long)gp::num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  gp::adam_flat_kernel<<<(int)blocks, 256, 0, gp::as_stream(stream)>>>(
-      p, g, m, v, n4, (float)lr, (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, step,
+  gp::launch_pdl(gp::adam_flat_kernel, (int)blocks, 256, 0, gp::as_stream(stream), p, g, m, v, n4, (float)lr, (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, step,
       (float)grad_scale);
   GP_CHECK_LAUNCH();
   return GP_OK;

@@ -79,6 +79,7 @@ __device__ void peer_exchange_sum(const PeerCtx& px, const float* src, int n, fl
 }
 
 __global__ void __launch_bounds__(512) peer_allreduce_kernel(const PeerCtx px, float* data, int n) {
+  gp::pdl_sync();
   __shared__ float s_tot[kPeerMaxFloats];
   peer_exchange_sum(px, data, n, s_tot);
   for (int i = threadIdx.x; i < n; i += blockDim.x) data[i] = s_tot[i];
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(512) bn_finalize_peer_kernel(const PeerCtx px,
                                                                float* __restrict__ rstd, float* __restrict__ scale,
                                                                float* __restrict__ shift, float* running_mean,
                                                                float* running_var, long long* num_batches_tracked) {
+  gp::pdl_sync();
   __shared__ float s_tot[kPeerMaxFloats];
   peer_exchange_sum(px, st, 2 * C, s_tot);
   if (threadIdx.x == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;
@@ -140,7 +142,7 @@ int gp_peer_allreduce_sum(const gp_peer_t* peer, float* data, int n, void* strea
   PeerCtx px;
   int rc = make_ctx(peer, &px);
   if (rc) return rc;
-  peer_allreduce_kernel<<<1, 512, 0, as_stream(stream)>>>(px, data, n);
+  gp::launch_plain(peer_allreduce_kernel, 1, 512, 0, as_stream(stream), px, data, n);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -153,7 +155,7 @@ int gp_bn_finalize_peer(const gp_peer_t* peer, float* st, double count, int C, f
   PeerCtx px;
   int rc = make_ctx(peer, &px);
   if (rc) return rc;
-  bn_finalize_peer_kernel<<<1, 512, 0, as_stream(stream)>>>(px, st, count, C, eps, momentum, gamma, beta, mean, rstd, scale,
+  gp::launch_plain(bn_finalize_peer_kernel, 1, 512, 0, as_stream(stream), px, st, count, C, eps, momentum, gamma, beta, mean, rstd, scale,
                                                            shift, running_mean, running_var, num_batches_tracked);
   GP_CHECK_LAUNCH();
   return GP_OK;

@@ -18,6 +18,7 @@ namespace x3 {
 __global__ void split_matrix_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int K,
                                     int Rpad, int ld, int width, long long s_r, long long s_k, int perm,
                                     long long lo_off) {
+  gp::pdl_sync();
   const long long total = (long long)Rpad * width;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / width), k = (int)(i % width);
@@ -40,6 +41,7 @@ __global__ void split_matrix_kernel(const float* __restrict__ src, __nv_bfloat16
 // (hi + lo carries ~16 significant bits, so the double rounding is below fp16's own). 8 columns per thread.
 __global__ void pair_to_f16_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
                                    long long ld_in, __half* __restrict__ out, long long ld_out, long long rows, int cols8) {
+  gp::pdl_sync();
   const long long total = rows * cols8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cols8;
@@ -65,6 +67,7 @@ __global__ void pair_to_f16_kernel(const __nv_bfloat16* __restrict__ hi, const _
 __global__ void col_stats_comp_kernel(const __nv_bfloat16* __restrict__ x, const void* __restrict__ x_comp, int fmt,
                                       long long P, int C, float* __restrict__ sum, float* __restrict__ sumsq,
                                       int rows_per_block) {
+  gp::pdl_sync();
   const ColLayout L = col_layout(C);
   float acc[2][8];
 #pragma unroll
@@ -100,6 +103,7 @@ __global__ void bn_apply_comp_kernel(const __nv_bfloat16* __restrict__ y, const 
                                      __nv_bfloat16* __restrict__ out, void* __restrict__ out_comp, int fmt, long long P,
                                      int C, const float* __restrict__ scale, const float* __restrict__ shift, int act,
                                      int rows_per_block) {
+  gp::pdl_sync();
   const ColLayout L = col_layout(C);
   if (!L.active) return;
   float sc[8], sh[8];
@@ -136,6 +140,7 @@ __global__ void bn_bwd_reduce_comp_kernel(const __nv_bfloat16* __restrict__ da, 
                                           const float* __restrict__ scale, const float* __restrict__ shift,
                                           const float* __restrict__ mean, const float* __restrict__ rstd, int act,
                                           float* __restrict__ sum_dz, float* __restrict__ sum_dzx, int rows_per_block) {
+  gp::pdl_sync();
   const ColLayout L = col_layout(C);
   float acc[2][8];
 #pragma unroll
@@ -184,6 +189,7 @@ __global__ void bn_bwd_apply_comp_kernel(const __nv_bfloat16* __restrict__ da, c
                                          const float* __restrict__ rstd, const float* __restrict__ sum_dz,
                                          const float* __restrict__ sum_dzx, float inv_count, int act, int rows_per_block,
                                          float* __restrict__ acc_dbeta, float* __restrict__ acc_dgamma, float acc_scale) {
+  gp::pdl_sync();
   if (acc_dbeta != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       acc_dbeta[c] += sum_dz[c] * acc_scale;
@@ -242,7 +248,7 @@ int gp_split_matrix(const float* src, void* dst, int R, int K, int Rpad, int ld,
   GP_REQUIRE(perm <= 1 || R % perm == 0, "gp_split_matrix: perm must divide R");
   long long g = ((long long)Rpad * width + 255) / 256;
   if (g > (long long)num_sms() * 16) g = (long long)num_sms() * 16;
-  x3::split_matrix_kernel<<<(int)g, 256, 0, as_stream(stream)>>>(src, static_cast<__nv_bfloat16*>(dst), R, K, Rpad, ld,
+  gp::launch_pdl(x3::split_matrix_kernel, (int)g, 256, 0, as_stream(stream), src, static_cast<__nv_bfloat16*>(dst), R, K, Rpad, ld,
                                                                  width, s_r, s_k, perm, lo_off);
   GP_CHECK_LAUNCH();
   return GP_OK;
@@ -251,7 +257,7 @@ int gp_split_matrix(const float* src, void* dst, int R, int K, int Rpad, int ld,
 int gp_bn_stats_f32(const float* y, long long P, int C, float* sum, float* sumsq, void* stream) {
   GP_REQUIRE(y && sum && sumsq && P > 0 && C > 0 && C % 8 == 0, "gp_bn_stats_f32: bad arguments");
   const ColLaunch L = col_launch(P, C, 2);
-  col_stats_kernel<float, true><<<L.grid, L.block, L.smem, as_stream(stream)>>>(y, P, C, sum, sumsq, L.rpb);
+  gp::launch_pdl(col_stats_kernel<float, true>, L.grid, L.block, L.smem, as_stream(stream), y, P, C, sum, sumsq, L.rpb);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -260,7 +266,7 @@ int gp_bn_apply_act_split(const float* y, void* out_hi, void* out_lo, long long 
                           const float* shift, int act, void* stream) {
   GP_REQUIRE(y && out_hi && scale && shift && P > 0 && C % 8 == 0, "gp_bn_apply_act_split: bad arguments");
   const ColLaunch L = col_launch(P, C, 0);
-  bn_apply_kernel<float><<<L.grid, L.block, 0, as_stream(stream)>>>(y, static_cast<__nv_bfloat16*>(out_hi),
+  gp::launch_pdl(bn_apply_kernel<float>, L.grid, L.block, 0, as_stream(stream), y, static_cast<__nv_bfloat16*>(out_hi),
                                                                     static_cast<__nv_bfloat16*>(out_lo), P, C, scale,
                                                                     shift, act, L.rpb);
   GP_CHECK_LAUNCH();
@@ -276,7 +282,7 @@ int gp_pair_to_f16(const void* hi, const void* lo, long long ld_in, void* out, l
              "gp_pair_to_f16: pointers must be 16-byte aligned");
   long long g = (rows * (cols / 8) + 255) / 256;
   if (g > (long long)num_sms() * 16) g = (long long)num_sms() * 16;
-  x3::pair_to_f16_kernel<<<(int)g, 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(hi),
+  gp::launch_pdl(x3::pair_to_f16_kernel, (int)g, 256, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(hi),
                                                                 static_cast<const __nv_bfloat16*>(lo), ld_in,
                                                                 static_cast<__half*>(out), ld_out, rows, cols / 8);
   GP_CHECK_LAUNCH();
@@ -287,7 +293,7 @@ int gp_bn_apply_act_pair(const float* y, void* out_bf16, void* out_f16, long lon
                          const float* shift, int act, void* stream) {
   GP_REQUIRE(y && out_bf16 && out_f16 && scale && shift && P > 0 && C % 8 == 0, "gp_bn_apply_act_pair: bad arguments");
   const ColLaunch L = col_launch(P, C, 0);
-  bn_apply_kernel<float, true><<<L.grid, L.block, 0, as_stream(stream)>>>(y, static_cast<__nv_bfloat16*>(out_bf16),
+  gp::launch_pdl(bn_apply_kernel<float, true>, L.grid, L.block, 0, as_stream(stream), y, static_cast<__nv_bfloat16*>(out_bf16),
                                                                           static_cast<__nv_bfloat16*>(out_f16), P, C, scale,
                                                                           shift, act, L.rpb);
   GP_CHECK_LAUNCH();
@@ -299,7 +305,7 @@ int gp_bn_stats_comp(const void* x, const void* x_comp, int comp_fmt, long long 
   GP_REQUIRE(x && sum && sumsq && P > 0 && C > 0 && C % 8 == 0, "gp_bn_stats_comp: bad arguments (C %% 8 == 0 required)");
   GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_bn_stats_comp: unknown companion format %d", comp_fmt);
   const ColLaunch L = col_launch(P, C, 2);
-  x3::col_stats_comp_kernel<<<L.grid, L.block, L.smem, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(x), x_comp,
+  gp::launch_pdl(x3::col_stats_comp_kernel, L.grid, L.block, L.smem, as_stream(stream), static_cast<const __nv_bfloat16*>(x), x_comp,
                                                                             comp_fmt, P, C, sum, sumsq, L.rpb);
   GP_CHECK_LAUNCH();
   return GP_OK;
@@ -310,7 +316,7 @@ int gp_bn_apply_act_comp(const void* y, const void* y_comp, void* out, void* out
   GP_REQUIRE(y && out && scale && shift && P > 0 && C % 8 == 0, "gp_bn_apply_act_comp: bad arguments");
   GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_bn_apply_act_comp: unknown companion format %d", comp_fmt);
   const ColLaunch L = col_launch(P, C, 0);
-  x3::bn_apply_comp_kernel<<<L.grid, L.block, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(y), y_comp,
+  gp::launch_pdl(x3::bn_apply_comp_kernel, L.grid, L.block, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(y), y_comp,
                                                                       static_cast<__nv_bfloat16*>(out), out_comp, comp_fmt,
                                                                       P, C, scale, shift, act, L.rpb);
   GP_CHECK_LAUNCH();
@@ -323,8 +329,7 @@ int gp_bn_bwd_reduce_comp(const void* da, const void* y, const void* y_comp, int
   GP_REQUIRE(da && y && sum_dz && sum_dzx && P > 0 && C % 8 == 0, "gp_bn_bwd_reduce_comp: bad arguments");
   GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_bn_bwd_reduce_comp: unknown companion format %d", comp_fmt);
   const ColLaunch L = col_launch(P, C, 2, 2);
-  x3::bn_bwd_reduce_comp_kernel<<<L.grid, L.block, L.smem, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), y_comp, comp_fmt, P, C, scale, shift, mean,
+  gp::launch_pdl(x3::bn_bwd_reduce_comp_kernel, L.grid, L.block, L.smem, as_stream(stream), static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), y_comp, comp_fmt, P, C, scale, shift, mean,
       rstd, act, sum_dz, sum_dzx, L.rpb);
   GP_CHECK_LAUNCH();
   return GP_OK;
@@ -338,8 +343,7 @@ int gp_bn_bwd_apply_comp(const void* da, const void* y, const void* y_comp, int 
   GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_bn_bwd_apply_comp: unknown companion format %d", comp_fmt);
   GP_REQUIRE((acc_dbeta == nullptr) == (acc_dgamma == nullptr), "gp_bn_bwd_apply_comp: acc_dbeta and acc_dgamma go together");
   const ColLaunch L = col_launch(P, C, 0);
-  x3::bn_bwd_apply_comp_kernel<<<L.grid, L.block, 0, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), y_comp, comp_fmt,
+  gp::launch_pdl(x3::bn_bwd_apply_comp_kernel, L.grid, L.block, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), y_comp, comp_fmt,
       static_cast<__nv_bfloat16*>(dy), P, C, scale, shift, mean, rstd, sum_dz, sum_dzx, (float)(1.0 / count), act, L.rpb,
       acc_dbeta, acc_dgamma, acc_scale);
   GP_CHECK_LAUNCH();
@@ -350,8 +354,7 @@ int gp_bn_bwd_reduce_f32(const void* da, const float* y, long long P, int C, con
                          const float* mean, const float* rstd, int act, float* sum_dz, float* sum_dzx, void* stream) {
   GP_REQUIRE(da && y && sum_dz && sum_dzx && P > 0 && C % 8 == 0, "gp_bn_bwd_reduce_f32: bad arguments");
   const ColLaunch L = col_launch(P, C, 2, 2);
-  bn_bwd_reduce_kernel<float><<<L.grid, L.block, L.smem, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(da), y, P, C, scale, shift, mean, rstd, act, sum_dz, sum_dzx, L.rpb);
+  gp::launch_pdl(bn_bwd_reduce_kernel<float>, L.grid, L.block, L.smem, as_stream(stream), static_cast<const __nv_bfloat16*>(da), y, P, C, scale, shift, mean, rstd, act, sum_dz, sum_dzx, L.rpb);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -363,8 +366,7 @@ int gp_bn_bwd_apply_f32(const void* da, const float* y, void* dy, long long P, i
   GP_REQUIRE(da && y && dy && P > 0 && C % 8 == 0 && count > 0, "gp_bn_bwd_apply_f32: bad arguments");
   GP_REQUIRE((acc_dbeta == nullptr) == (acc_dgamma == nullptr), "gp_bn_bwd_apply_f32: acc_dbeta and acc_dgamma go together");
   const ColLaunch L = col_launch(P, C, 0);
-  bn_bwd_apply_kernel<float><<<L.grid, L.block, 0, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(da), y, static_cast<__nv_bfloat16*>(dy), P, C, scale, shift, mean, rstd, sum_dz,
+  gp::launch_pdl(bn_bwd_apply_kernel<float>, L.grid, L.block, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(da), y, static_cast<__nv_bfloat16*>(dy), P, C, scale, shift, mean, rstd, sum_dz,
       sum_dzx, (float)(1.0 / count), act, L.rpb, acc_dbeta, acc_dgamma, acc_scale);
   GP_CHECK_LAUNCH();
   return GP_OK;

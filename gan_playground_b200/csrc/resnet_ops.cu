@@ -46,6 +46,7 @@ __global__ void cbn_apply_kernel(const __nv_bfloat16* __restrict__ y, const void
                                  int C, const float* __restrict__ mean, const float* __restrict__ rstd,
                                  const float* __restrict__ emb, const long long* __restrict__ labels, int act, int up,
                                  int px_per_block) {
+  gp::pdl_sync();
   const int n = blockIdx.y;
   const int cgs = C / 8;
   const int g = threadIdx.x % cgs, lane = threadIdx.x / cgs, lanes = blockDim.x / cgs;
@@ -108,6 +109,7 @@ __global__ void cbn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, cons
                                       const void* __restrict__ y_comp, int fmt, int H, int W, int C, const float* __restrict__ mean, const float* __restrict__ rstd,
                                       const float* __restrict__ emb, const long long* __restrict__ labels, int act,
                                       int up, float* __restrict__ part, int px_per_block) {
+  gp::pdl_sync();
   const int n = blockIdx.y;
   const int cgs = C / 8;
   const int g = threadIdx.x % cgs, lane = threadIdx.x / cgs, lanes = blockDim.x / cgs;
@@ -159,6 +161,7 @@ __global__ void cbn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ da, cons
 __global__ void cbn_bwd_finalize_kernel(const float* __restrict__ part, int NB, int C, const float* __restrict__ emb,
                                         const long long* __restrict__ labels, float* __restrict__ S,
                                         float* __restrict__ demb) {
+  gp::pdl_sync();
   // grid (channel blocks, sample slices): S is zeroed by the caller and receives one atomic per slice
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -189,6 +192,7 @@ __global__ void cbn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const
                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                      const float* __restrict__ emb, const long long* __restrict__ labels,
                                      const float* __restrict__ S, float inv_count, int act, int up, int px_per_block) {
+  gp::pdl_sync();
   const int n = blockIdx.y;
   const int cgs = C / 8;
   const int g = threadIdx.x % cgs, lane = threadIdx.x / cgs, lanes = blockDim.x / cgs;
@@ -225,6 +229,7 @@ __global__ void cbn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ da, const
 // out[n, 2h+a, 2w+b, c] = scale * in[n, h, w, c]
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, long long NB,
                                   int H, int W, int C, float scale) {
+  gp::pdl_sync();
   const int cgs = C / 8;
   const long long total = NB * H * W * cgs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -252,6 +257,7 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfl
 __global__ void pool2x_kernel(const __nv_bfloat16* __restrict__ in, const void* __restrict__ in_comp,
                               __nv_bfloat16* __restrict__ out, void* __restrict__ out_comp, int fmt, long long NB, int H,
                               int W, int C, float scale) {
+  gp::pdl_sync();
   const int cgs = C / 8;
   const long long total = NB * H * W * cgs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -278,6 +284,7 @@ __global__ void pool2x_kernel(const __nv_bfloat16* __restrict__ in, const void* 
 __global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ in, const void* __restrict__ in_comp,
                                __nv_bfloat16* __restrict__ out, void* __restrict__ out_comp, int fmt, long long n8,
                                int act) {
+  gp::pdl_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float f[8];
     load8c(in, in_comp, fmt, i * 8, f);
@@ -291,6 +298,7 @@ __global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ in, const void*
 // col[(n,h,w)][(c*3+kh)*3+kw] = img[n, c, h+kh-1, w+kw-1] (zero padded), columns >= ch*9 are zero; col row = 32 bf16.
 __global__ void im2col_k3s1_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ col,
                                    void* __restrict__ col_comp, int fmt, int NB, int ch, int H, int W) {
+  gp::pdl_sync();
   const long long total = (long long)NB * H * W * 4;  // 4 groups of 8 columns
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(i % 4);
@@ -311,6 +319,7 @@ __global__ void im2col_k3s1_kernel(const float* __restrict__ img, __nv_bfloat16*
 // img[n,c,ih,iw] = sum_{kh,kw} col[(n, ih-kh+1, iw-kw+1)][(c*3+kh)*3+kw]
 __global__ void col2im_k3s1_kernel(const __nv_bfloat16* __restrict__ col, float* __restrict__ img, int NB, int ch, int H,
                                    int W) {
+  gp::pdl_sync();
   const long long total = (long long)NB * ch * H * W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int iw = (int)(i % W), ih = (int)((i / W) % H);
@@ -335,6 +344,7 @@ __global__ void col2im_k3s1_kernel(const __nv_bfloat16* __restrict__ col, float*
 // in_f32 != 0: `in` is the fp32 output of the GEMM (the precise modes keep the pre-tanh image out of bf16).
 __global__ void nhwc8_to_image_kernel(const void* __restrict__ in, int in_f32, float* __restrict__ img, long long NB, int ch,
                                       int HW, int tanh_act) {
+  gp::pdl_sync();
   const long long total = NB * ch * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long p = i % HW;
@@ -348,6 +358,7 @@ __global__ void nhwc8_to_image_kernel(const void* __restrict__ in, int in_f32, f
 // dy[p][c] = dout[n,c,p] * (1 - out^2) for c < ch, 0 for c >= ch
 __global__ void image_to_nhwc8_grad_kernel(const float* __restrict__ dout, const float* __restrict__ out,
                                            __nv_bfloat16* __restrict__ dy, long long NB, int ch, int HW, int tanh_act) {
+  gp::pdl_sync();
   const long long total = NB * HW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long p = i % HW, n = i / HW;
@@ -373,6 +384,7 @@ __global__ void image_to_nhwc8_grad_kernel(const float* __restrict__ dout, const
 // h[n][c] = sum_hw relu(a[n,hw,c])     (models/sngan_projection.py:190-191)
 __global__ void relu_sumpool_kernel(const __nv_bfloat16* __restrict__ a, const void* __restrict__ a_comp, int fmt,
                                     float* __restrict__ h, int HW, int C) {
+  gp::pdl_sync();
   const int n = blockIdx.y;
   const int g = blockIdx.x * blockDim.x + threadIdx.x;  // 8-channel group
   if (g * 8 >= C) return;
@@ -390,6 +402,7 @@ __global__ void relu_sumpool_kernel(const __nv_bfloat16* __restrict__ a, const v
 }
 __global__ void relu_sumpool_bwd_kernel(const float* __restrict__ dh, const __nv_bfloat16* __restrict__ a,
                                         __nv_bfloat16* __restrict__ da, long long total, int HW, int C) {
+  gp::pdl_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const long long n = i / ((long long)C * HW);
@@ -402,6 +415,7 @@ __global__ void relu_sumpool_bwd_kernel(const float* __restrict__ dh, const __nv
 __global__ void proj_head_fwd_kernel(const float* __restrict__ h, const float* __restrict__ w, const float* __restrict__ b,
                                      const float* __restrict__ E, const long long* __restrict__ labels,
                                      float* __restrict__ out, int NB, int C) {
+  gp::pdl_sync();
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= NB) return;
@@ -417,6 +431,7 @@ __global__ void proj_head_bwd_kernel(const float* __restrict__ dout, const float
                                      const long long* __restrict__ labels, float* __restrict__ dh,
                                      float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dE, int NB,
                                      int C) {
+  gp::pdl_sync();
   // grid (channel blocks, sample slices): dw / db are zeroed by the caller and receive one atomic per slice
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -481,7 +496,7 @@ int gp_cbn_apply_act(const void* y, const void* y_comp, void* out, void* out_com
   GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_cbn_apply_act: unknown companion format %d", comp_fmt);
   GP_REQUIRE(emb == nullptr || labels != nullptr, "gp_cbn_apply_act: labels required with an embedding table");
   const CbnLaunch L = cbn_launch(NB, H * W, C);
-  cbn_apply_kernel<<<L.grid, L.block, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(y), y_comp,
+  gp::launch_pdl(cbn_apply_kernel, L.grid, L.block, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(y), y_comp,
                                                               static_cast<__nv_bfloat16*>(out), out_comp, comp_fmt, H, W, C,
                                                               mean, rstd, emb, labels, act, upsample, L.ppb);
   GP_CHECK_LAUNCH();
@@ -499,12 +514,11 @@ int gp_cbn_bwd_reduce(const void* da, const void* y, const void* y_comp, int com
   GP_CHECK_CUDA(cudaMemsetAsync(part, 0, sizeof(float) * NB * 2 * C, st));
   if (demb != nullptr) GP_CHECK_CUDA(cudaMemsetAsync(demb, 0, sizeof(float) * n_classes * 2 * C, st));
   const CbnLaunch L = cbn_launch(NB, H * W, C);
-  cbn_bwd_reduce_kernel<<<L.grid, L.block, 2 * C * sizeof(float), st>>>(
-      static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), y_comp, comp_fmt, H, W, C, mean, rstd,
+  gp::launch_pdl(cbn_bwd_reduce_kernel, L.grid, L.block, 2 * C * sizeof(float), st, static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), y_comp, comp_fmt, H, W, C, mean, rstd,
       emb, labels, act, upsample, part, L.ppb);
   GP_CHECK_LAUNCH();
   GP_CHECK_CUDA(cudaMemsetAsync(S, 0, sizeof(float) * 2 * C, st));
-  cbn_bwd_finalize_kernel<<<dim3((C + 127) / 128, sample_slices(NB)), 128, 0, st>>>(part, NB, C, emb, labels, S, demb);
+  gp::launch_pdl(cbn_bwd_finalize_kernel, dim3((C + 127) / 128, sample_slices(NB)), 128, 0, st, part, NB, C, emb, labels, S, demb);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -515,8 +529,7 @@ int gp_cbn_bwd_apply(const void* da, const void* y, const void* y_comp, int comp
   GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_cbn_bwd_apply: unknown companion format %d", comp_fmt);
   GP_REQUIRE(da && y && dy && S && NB > 0 && C % 8 == 0 && count > 0, "gp_cbn_bwd_apply: bad arguments");
   const CbnLaunch L = cbn_launch(NB, H * W, C);
-  cbn_bwd_apply_kernel<<<L.grid, L.block, 0, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), y_comp, comp_fmt,
+  gp::launch_pdl(cbn_bwd_apply_kernel, L.grid, L.block, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(da), static_cast<const __nv_bfloat16*>(y), y_comp, comp_fmt,
       static_cast<__nv_bfloat16*>(dy), H, W, C, mean, rstd, emb, labels, S, (float)(1.0 / count), act, upsample, L.ppb);
   GP_CHECK_LAUNCH();
   return GP_OK;
@@ -524,8 +537,7 @@ int gp_cbn_bwd_apply(const void* da, const void* y, const void* y_comp, int comp
 
 int gp_upsample2x(const void* in, void* out, int NB, int H, int W, int C, float scale, void* stream) {
   GP_REQUIRE(in && out && NB > 0 && C % 8 == 0, "gp_upsample2x: bad arguments");
-  upsample2x_kernel<<<grid1((long long)NB * H * W * (C / 8)), 256, 0, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), NB, H, W, C, scale);
+  gp::launch_pdl(upsample2x_kernel, grid1((long long)NB * H * W * (C / 8)), 256, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), NB, H, W, C, scale);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -534,8 +546,7 @@ int gp_pool2x(const void* in, const void* in_comp, void* out, void* out_comp, in
               int C, float scale, void* stream) {
   GP_REQUIRE(in && out && NB > 0 && C % 8 == 0, "gp_pool2x: bad arguments");
   GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_pool2x: unknown companion format %d", comp_fmt);
-  pool2x_kernel<<<grid1((long long)NB * Hout * Wout * (C / 8)), 256, 0, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(in), in_comp, static_cast<__nv_bfloat16*>(out), out_comp, comp_fmt, NB, Hout, Wout,
+  gp::launch_pdl(pool2x_kernel, grid1((long long)NB * Hout * Wout * (C / 8)), 256, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(in), in_comp, static_cast<__nv_bfloat16*>(out), out_comp, comp_fmt, NB, Hout, Wout,
       C, scale);
   GP_CHECK_LAUNCH();
   return GP_OK;
@@ -545,7 +556,7 @@ int gp_act_fwd(const void* in, const void* in_comp, void* out, void* out_comp, i
                void* stream) {
   GP_REQUIRE(in && out && n > 0 && n % 8 == 0, "gp_act_fwd: bad arguments");
   GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_act_fwd: unknown companion format %d", comp_fmt);
-  act_fwd_kernel<<<grid1(n / 8), 256, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(in), in_comp,
+  gp::launch_pdl(act_fwd_kernel, grid1(n / 8), 256, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(in), in_comp,
                                                               static_cast<__nv_bfloat16*>(out), out_comp, comp_fmt, n / 8,
                                                               act);
   GP_CHECK_LAUNCH();
@@ -555,23 +566,21 @@ int gp_act_fwd(const void* in, const void* in_comp, void* out, void* out_comp, i
 int gp_im2col_k3s1(const float* img, void* col, void* col_comp, int comp_fmt, int NB, int ch, int H, int W, void* stream) {
   GP_REQUIRE(img && col && NB > 0 && ch > 0 && ch * 9 <= 32, "gp_im2col_k3s1: bad arguments");
   GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_im2col_k3s1: unknown companion format %d", comp_fmt);
-  im2col_k3s1_kernel<<<grid1((long long)NB * H * W * 4), 256, 0, as_stream(stream)>>>(
-      img, static_cast<__nv_bfloat16*>(col), col_comp, comp_fmt, NB, ch, H, W);
+  gp::launch_pdl(im2col_k3s1_kernel, grid1((long long)NB * H * W * 4), 256, 0, as_stream(stream), img, static_cast<__nv_bfloat16*>(col), col_comp, comp_fmt, NB, ch, H, W);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
 
 int gp_col2im_k3s1(const void* col, float* img, int NB, int ch, int H, int W, void* stream) {
   GP_REQUIRE(img && col && NB > 0 && ch > 0 && ch * 9 <= 32, "gp_col2im_k3s1: bad arguments");
-  col2im_k3s1_kernel<<<grid1((long long)NB * ch * H * W), 256, 0, as_stream(stream)>>>(
-      static_cast<const __nv_bfloat16*>(col), img, NB, ch, H, W);
+  gp::launch_pdl(col2im_k3s1_kernel, grid1((long long)NB * ch * H * W), 256, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(col), img, NB, ch, H, W);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
 
 int gp_nhwc8_to_image(const void* in, int in_f32, float* img, int NB, int ch, int HW, int tanh_act, void* stream) {
   GP_REQUIRE(in && img && NB > 0 && ch > 0 && ch <= 8, "gp_nhwc8_to_image: bad arguments");
-  nhwc8_to_image_kernel<<<grid1((long long)NB * ch * HW), 256, 0, as_stream(stream)>>>(in, in_f32, img, NB, ch, HW,
+  gp::launch_pdl(nhwc8_to_image_kernel, grid1((long long)NB * ch * HW), 256, 0, as_stream(stream), in, in_f32, img, NB, ch, HW,
                                                                                        tanh_act);
   GP_CHECK_LAUNCH();
   return GP_OK;
@@ -580,8 +589,7 @@ int gp_nhwc8_to_image(const void* in, int in_f32, float* img, int NB, int ch, in
 int gp_image_to_nhwc8_grad(const float* dout, const float* out, void* dy, int NB, int ch, int HW, int tanh_act,
                            void* stream) {
   GP_REQUIRE(dout && dy && NB > 0 && ch > 0 && ch <= 8 && (!tanh_act || out), "gp_image_to_nhwc8_grad: bad arguments");
-  image_to_nhwc8_grad_kernel<<<grid1((long long)NB * HW), 256, 0, as_stream(stream)>>>(
-      dout, out, static_cast<__nv_bfloat16*>(dy), NB, ch, HW, tanh_act);
+  gp::launch_pdl(image_to_nhwc8_grad_kernel, grid1((long long)NB * HW), 256, 0, as_stream(stream), dout, out, static_cast<__nv_bfloat16*>(dy), NB, ch, HW, tanh_act);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -590,7 +598,7 @@ int gp_relu_sumpool(const void* a, const void* a_comp, int comp_fmt, float* h, i
   GP_REQUIRE(a && h && NB > 0 && HW > 0 && C > 0 && C % 8 == 0, "gp_relu_sumpool: bad arguments (C %% 8 == 0)");
   GP_REQUIRE(comp_fmt >= GP_COMP_NONE && comp_fmt <= GP_COMP_F16, "gp_relu_sumpool: unknown companion format %d", comp_fmt);
   dim3 grid((C / 8 + 63) / 64, NB);
-  relu_sumpool_kernel<<<grid, 64, 0, as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(a), a_comp, comp_fmt, h, HW, C);
+  gp::launch_pdl(relu_sumpool_kernel, grid, 64, 0, as_stream(stream), static_cast<const __nv_bfloat16*>(a), a_comp, comp_fmt, h, HW, C);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -598,7 +606,7 @@ int gp_relu_sumpool(const void* a, const void* a_comp, int comp_fmt, float* h, i
 int gp_relu_sumpool_bwd(const float* dh, const void* a, void* da, int NB, int HW, int C, void* stream) {
   GP_REQUIRE(dh && a && da && NB > 0, "gp_relu_sumpool_bwd: bad arguments");
   const long long total = (long long)NB * HW * C;
-  relu_sumpool_bwd_kernel<<<grid1(total), 256, 0, as_stream(stream)>>>(dh, static_cast<const __nv_bfloat16*>(a),
+  gp::launch_pdl(relu_sumpool_bwd_kernel, grid1(total), 256, 0, as_stream(stream), dh, static_cast<const __nv_bfloat16*>(a),
                                                                       static_cast<__nv_bfloat16*>(da), total, HW, C);
   GP_CHECK_LAUNCH();
   return GP_OK;
@@ -607,7 +615,7 @@ int gp_relu_sumpool_bwd(const float* dh, const void* a, void* da, int NB, int HW
 int gp_proj_head_fwd(const float* h, const float* w, const float* b, const float* E, const long long* labels, float* out,
                      int NB, int C, void* stream) {
   GP_REQUIRE(h && w && out && NB > 0 && C > 0 && (E == nullptr || labels != nullptr), "gp_proj_head_fwd: bad arguments");
-  proj_head_fwd_kernel<<<(NB + 7) / 8, 256, 0, as_stream(stream)>>>(h, w, b, E, labels, out, NB, C);
+  gp::launch_pdl(proj_head_fwd_kernel, (NB + 7) / 8, 256, 0, as_stream(stream), h, w, b, E, labels, out, NB, C);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -619,7 +627,7 @@ int gp_proj_head_bwd(const float* dout, const float* h, const float* w, const fl
   if (dE != nullptr) GP_CHECK_CUDA(cudaMemsetAsync(dE, 0, sizeof(float) * n_classes * C, st));
   GP_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * C, st));
   if (db != nullptr) GP_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float), st));
-  proj_head_bwd_kernel<<<dim3((C + 127) / 128, sample_slices(NB)), 128, 0, st>>>(dout, h, w, E, labels, dh, dw, db, dE, NB, C);
+  gp::launch_pdl(proj_head_bwd_kernel, dim3((C + 127) / 128, sample_slices(NB)), 128, 0, st, dout, h, w, E, labels, dh, dw, db, dE, NB, C);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }

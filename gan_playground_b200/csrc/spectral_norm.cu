@@ -38,6 +38,7 @@ __device__ __forceinline__ float block_sum(float v) {
 // t1[c] += sum_{r in chunk} W[r][c] * u[r]      grid: (ceil(cols/256), row chunks)
 __global__ void sn_gemv_t_kernel(const float* __restrict__ w, SnLayout L, const float* __restrict__ u,
                                  float* __restrict__ t1, int rows_per_block) {
+  gp::pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= L.cols()) return;
   const int r0 = blockIdx.y * rows_per_block;
@@ -50,6 +51,7 @@ __global__ void sn_gemv_t_kernel(const float* __restrict__ w, SnLayout L, const 
 // t2[r] = sum_c W[r][c] * v[c]      grid: rows
 __global__ void sn_gemv_kernel(const float* __restrict__ w, SnLayout L, const float* __restrict__ v,
                                float* __restrict__ t2) {
+  gp::pdl_sync();
   const int r = blockIdx.x;
   float acc = 0.f;
   for (int c = threadIdx.x; c < L.cols(); c += blockDim.x) acc += __ldg(w + L.addr(r, c)) * __ldg(v + c);
@@ -60,6 +62,7 @@ __global__ void sn_gemv_kernel(const float* __restrict__ w, SnLayout L, const fl
 // out[i] = t[i] / max(||t||, eps); sigma (optional) = sum t^2 / max(||t||, eps)      single block
 __global__ void sn_normalize_kernel(const float* __restrict__ t, int n, float eps, float* __restrict__ out,
                                     float* __restrict__ sigma) {
+  gp::pdl_sync();
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc += t[i] * t[i];
   acc = block_sum(acc);
@@ -70,6 +73,7 @@ __global__ void sn_normalize_kernel(const float* __restrict__ t, int n, float ep
 
 // eval mode: sigma = u . t2      single block
 __global__ void sn_dot_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, float* __restrict__ out) {
+  gp::pdl_sync();
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc += a[i] * b[i];
   acc = block_sum(acc);
@@ -79,6 +83,7 @@ __global__ void sn_dot_kernel(const float* __restrict__ a, const float* __restri
 // out = w / sigma
 __global__ void sn_scale_kernel(const float* __restrict__ w, const float* __restrict__ sigma, float* __restrict__ out,
                                 long long n) {
+  gp::pdl_sync();
   const float inv = 1.f / __ldg(sigma);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = w[i] * inv;
@@ -87,6 +92,7 @@ __global__ void sn_scale_kernel(const float* __restrict__ w, const float* __rest
 // dot += sum g * w_sn
 __global__ void sn_grad_dot_kernel(const float* __restrict__ g, const float* __restrict__ wsn, long long n,
                                    float* __restrict__ dot) {
+  gp::pdl_sync();
   float acc = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     acc += g[i] * wsn[i];
@@ -98,6 +104,7 @@ __global__ void sn_grad_dot_kernel(const float* __restrict__ g, const float* __r
 __global__ void sn_grad_kernel(const float* __restrict__ g, SnLayout L, const float* __restrict__ u,
                                const float* __restrict__ v, const float* __restrict__ sigma,
                                const float* __restrict__ dot, float* __restrict__ out) {
+  gp::pdl_sync();
   const long long n = (long long)L.A * L.B * L.T;
   const float inv = 1.f / __ldg(sigma), d = __ldg(dot);
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
@@ -131,6 +138,7 @@ struct SnBatch {
 };
 
 __global__ void snb_gemv_t_kernel(const __grid_constant__ SnBatch b) {
+  gp::pdl_sync();
   const int m = blockIdx.y;
   const SnLayout L{b.A[m], b.B[m], b.T[m], b.dim[m]};
   const int cb = (L.cols() + 255) / 256, rc = (L.rows() + kSnRowChunk - 1) / kSnRowChunk;
@@ -155,6 +163,7 @@ __global__ void snb_gemv_t_kernel(const __grid_constant__ SnBatch b) {
 
 // which = 0: v <- t1 / max(||t1||, eps) (+ copy);  which = 1: u <- t2 / ..., sigma = ||t2||^2 / max(||t2||, eps) (+ copy)
 __global__ void snb_normalize_kernel(const __grid_constant__ SnBatch b, int which) {
+  gp::pdl_sync();
   const int m = blockIdx.x;
   const SnLayout L{b.A[m], b.B[m], b.T[m], b.dim[m]};
   const int n = which == 0 ? L.cols() : L.rows();
@@ -174,6 +183,7 @@ __global__ void snb_normalize_kernel(const __grid_constant__ SnBatch b, int whic
 }
 
 __global__ void snb_gemv_kernel(const __grid_constant__ SnBatch b) {
+  gp::pdl_sync();
   const int m = blockIdx.y, r = blockIdx.x;
   const SnLayout L{b.A[m], b.B[m], b.T[m], b.dim[m]};
   if (r >= L.rows()) return;
@@ -205,6 +215,7 @@ __global__ void snb_gemv_kernel(const __grid_constant__ SnBatch b) {
 
 // eval mode: sigma = u . (W v) with the stored u, v (+ copies for the backward)
 __global__ void snb_eval_sigma_kernel(const __grid_constant__ SnBatch b) {
+  gp::pdl_sync();
   const int m = blockIdx.x;
   const SnLayout L{b.A[m], b.B[m], b.T[m], b.dim[m]};
   float acc = 0.f;
@@ -219,6 +230,7 @@ __global__ void snb_eval_sigma_kernel(const __grid_constant__ SnBatch b) {
 }
 
 __global__ void snb_scale_kernel(const __grid_constant__ SnBatch b) {
+  gp::pdl_sync();
   const int m = blockIdx.y;
   const long long n = (long long)b.A[m] * b.B[m] * b.T[m];
   const float inv = 1.f / __ldg(b.sigma[m]);
@@ -242,6 +254,7 @@ struct SnGradBatch {
 };
 
 __global__ void snb_grad_dot_kernel(const __grid_constant__ SnGradBatch b) {
+  gp::pdl_sync();
   const int m = blockIdx.y;
   if (b.g[m] == nullptr) return;
   const long long n = (long long)b.A[m] * b.B[m] * b.T[m];
@@ -255,6 +268,7 @@ __global__ void snb_grad_dot_kernel(const __grid_constant__ SnGradBatch b) {
 }
 
 __global__ void snb_grad_kernel(const __grid_constant__ SnGradBatch b) {
+  gp::pdl_sync();
   const int m = blockIdx.y;
   if (b.g[m] == nullptr) return;
   const SnLayout L{b.A[m], b.B[m], b.T[m], b.dim[m]};
@@ -299,18 +313,18 @@ int gp_sn_sigma(const float* w, int A, int B, int T, int dim, float* u, float* v
     GP_CHECK_CUDA(cudaMemsetAsync(t1, 0, sizeof(float) * Cc, st));
     const int rpb = R > 64 ? 64 : R;
     dim3 grid((Cc + 255) / 256, (R + rpb - 1) / rpb);
-    sn_gemv_t_kernel<<<grid, 256, 0, st>>>(w, L, u, t1, rpb);
+    gp::launch_pdl(sn_gemv_t_kernel, grid, 256, 0, st, w, L, u, t1, rpb);
     GP_CHECK_LAUNCH();
-    sn_normalize_kernel<<<1, 1024, 0, st>>>(t1, Cc, eps, v, nullptr);
+    gp::launch_pdl(sn_normalize_kernel, 1, 1024, 0, st, t1, Cc, eps, v, nullptr);
     GP_CHECK_LAUNCH();
-    sn_gemv_kernel<<<R, 256, 0, st>>>(w, L, v, t2);
+    gp::launch_pdl(sn_gemv_kernel, R, 256, 0, st, w, L, v, t2);
     GP_CHECK_LAUNCH();
-    sn_normalize_kernel<<<1, 1024, 0, st>>>(t2, R, eps, u, sigma);
+    gp::launch_pdl(sn_normalize_kernel, 1, 1024, 0, st, t2, R, eps, u, sigma);
     GP_CHECK_LAUNCH();
   } else {
-    sn_gemv_kernel<<<R, 256, 0, st>>>(w, L, v, t2);
+    gp::launch_pdl(sn_gemv_kernel, R, 256, 0, st, w, L, v, t2);
     GP_CHECK_LAUNCH();
-    sn_dot_kernel<<<1, 1024, 0, st>>>(u, t2, R, sigma);
+    gp::launch_pdl(sn_dot_kernel, 1, 1024, 0, st, u, t2, R, sigma);
     GP_CHECK_LAUNCH();
   }
   return GP_OK;
@@ -318,7 +332,7 @@ int gp_sn_sigma(const float* w, int A, int B, int T, int dim, float* u, float* v
 
 int gp_sn_scale(const float* w, const float* sigma, float* out, long long n, void* stream) {
   GP_REQUIRE(w && sigma && out && n > 0, "gp_sn_scale: bad arguments");
-  sn_scale_kernel<<<grid1d(n), 256, 0, as_stream(stream)>>>(w, sigma, out, n);
+  gp::launch_pdl(sn_scale_kernel, grid1d(n), 256, 0, as_stream(stream), w, sigma, out, n);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -331,9 +345,9 @@ int gp_sn_grad(const float* g, const float* w_sn, int A, int B, int T, int dim, 
   const long long n = (long long)A * B * T;
   cudaStream_t st = as_stream(stream);
   GP_CHECK_CUDA(cudaMemsetAsync(dot, 0, sizeof(float), st));
-  sn_grad_dot_kernel<<<grid1d(n), 256, 0, st>>>(g, w_sn, n, dot);
+  gp::launch_pdl(sn_grad_dot_kernel, grid1d(n), 256, 0, st, g, w_sn, n, dot);
   GP_CHECK_LAUNCH();
-  sn_grad_kernel<<<grid1d(n), 256, 0, st>>>(g, L, u, v, sigma, dot, out);
+  gp::launch_pdl(sn_grad_kernel, grid1d(n), 256, 0, st, g, L, u, v, sigma, dot, out);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -371,24 +385,24 @@ int gp_sn_batched(const gp_sn_batch_t* p, void* stream) {
   cudaStream_t st = as_stream(stream);
   if (p->training) {
     GP_CHECK_CUDA(cudaMemsetAsync(p->scratch, 0, sizeof(float) * off, st));
-    snb_gemv_t_kernel<<<dim3(max_tblocks, b.count), 256, 0, st>>>(b);
+    gp::launch_pdl(snb_gemv_t_kernel, dim3(max_tblocks, b.count), 256, 0, st, b);
     GP_CHECK_LAUNCH();
-    snb_normalize_kernel<<<b.count, 1024, 0, st>>>(b, 0);
+    gp::launch_pdl(snb_normalize_kernel, b.count, 1024, 0, st, b, 0);
     GP_CHECK_LAUNCH();
-    snb_gemv_kernel<<<dim3(max_rows, b.count), 256, 0, st>>>(b);
+    gp::launch_pdl(snb_gemv_kernel, dim3(max_rows, b.count), 256, 0, st, b);
     GP_CHECK_LAUNCH();
-    snb_normalize_kernel<<<b.count, 1024, 0, st>>>(b, 1);
+    gp::launch_pdl(snb_normalize_kernel, b.count, 1024, 0, st, b, 1);
     GP_CHECK_LAUNCH();
   } else {
-    snb_gemv_kernel<<<dim3(max_rows, b.count), 256, 0, st>>>(b);
+    gp::launch_pdl(snb_gemv_kernel, dim3(max_rows, b.count), 256, 0, st, b);
     GP_CHECK_LAUNCH();
-    snb_eval_sigma_kernel<<<b.count, 1024, 0, st>>>(b);
+    gp::launch_pdl(snb_eval_sigma_kernel, b.count, 1024, 0, st, b);
     GP_CHECK_LAUNCH();
   }
   int gx = (int)((max_elems + 255) / 256);
   const int cap = num_sms() * 4;
   if (gx > cap) gx = cap;
-  snb_scale_kernel<<<dim3(gx, b.count), 256, 0, st>>>(b);
+  gp::launch_pdl(snb_scale_kernel, dim3(gx, b.count), 256, 0, st, b);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }
@@ -415,9 +429,9 @@ int gp_sn_grad_batched(const gp_sn_grad_batch_t* p, void* stream) {
   int gx = (int)((max_elems + 255) / 256);
   const int cap = num_sms() * 4;
   if (gx > cap) gx = cap;
-  snb_grad_dot_kernel<<<dim3(gx, b.count), 256, 0, st>>>(b);
+  gp::launch_pdl(snb_grad_dot_kernel, dim3(gx, b.count), 256, 0, st, b);
   GP_CHECK_LAUNCH();
-  snb_grad_kernel<<<dim3(gx, b.count), 256, 0, st>>>(b);
+  gp::launch_pdl(snb_grad_kernel, dim3(gx, b.count), 256, 0, st, b);
   GP_CHECK_LAUNCH();
   return GP_OK;
 }

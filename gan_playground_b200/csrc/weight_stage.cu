@@ -50,6 +50,7 @@ __device__ __forceinline__ void stage_store8(const gp_stage_dst_t& d, long long 
 }
 
 __global__ void __launch_bounds__(256) stage_conv16_kernel(const __grid_constant__ gp_stage_table_t tb) {
+  gp::pdl_sync();
   extern __shared__ float s_tile[];  // [32 d0][32 d1][16 t], pitches kStageP0 / kStageP1
   const int tid = threadIdx.x;
   for (int tile = blockIdx.x; tile < tb.total_tiles; tile += gridDim.x) {
@@ -130,7 +131,7 @@ extern "C" int gp_stage_conv_weights(const gp_stage_table_t* table, void* stream
     attr_set = true;
   }
   const int cap = num_sms() * 3;
-  stage_conv16_kernel<<<total < cap ? total : cap, 256, kStageSmem, as_stream(stream)>>>(tb);
+  gp::launch_pdl(stage_conv16_kernel, total < cap ? total : cap, 256, kStageSmem, as_stream(stream), tb);
   GP_CHECK_LAUNCH();
   return 0;
 }

@@ -61,6 +61,9 @@ class _AdversarialStep:
         self.arena = ops.ZeroArena(device)
         self._d_params = [p for p in netD.parameters() if p.requires_grad]
         self._side = torch.cuda.Stream(device=device) if device.type == "cuda" else None
+        # weight-gradient GEMMs leave the backward chain for this stream when a launch cannot fill the GPU (config.py)
+        self._wg_stream = (torch.cuda.Stream(device=device)
+                           if device.type == "cuda" and config.wgrad_stream_wanted(batch) else None)
 
     # kept for callers that look at the single-variant graph (DcganStep / AcganStep)
     @property
@@ -75,7 +78,8 @@ class _AdversarialStep:
         self.arena.begin()
         ops.ZeroArena.active = self.arena
         try:
-            self._loop(data, noise, log, i)
+            with config.wgrad_side_scope(self._wg_stream):
+                self._loop(data, noise, log, i)
         finally:
             ops.ZeroArena.active = None
 
@@ -88,6 +92,7 @@ class _AdversarialStep:
 
     @staticmethod
     def _step(opt, bucket):
+        config.join_wgrad_side()          # every weight gradient of this network has landed in its .grad buffer
         if bucket is not None:
             bucket.all_reduce_mean()
         opt.step()

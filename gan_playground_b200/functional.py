@@ -238,6 +238,21 @@ def _deliver_conv_wgrad(dwp, shape, param):
     return ops.unpack_conv_wgrad(dwp, shape)
 
 
+def _wgrad_off_chain(param, fn, *reads):
+    """Run `fn` (a weight-gradient GEMM + its delivery into param.grad) on the step driver's side stream when there is
+    one (config.wgrad_side) and the gradient is delivered in place; `reads` are the tensors it reads, kept alive until the
+    join so that the allocator cannot hand their memory to main-stream work that runs concurrently."""
+    side = config.wgrad_side()
+    if side is None or ops.grad_target(param) is None:
+        return fn()
+    stream, hold = side
+    stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(stream):
+        out = fn()
+    hold.extend(reads)
+    return out
+
+
 def _deliver_matrix_grad(src, shape, param, *args, **kw):
     tgt = ops.grad_target(param)
     if tgt is not None:
@@ -334,11 +349,13 @@ class ConvBlock(torch.autograd.Function):
             dbias = _deliver_colsum(dy, ctx.params[1]) if ctx.needs_input_grad[3] else None
         dweight = dx = None
         if ctx.needs_input_grad[2]:
-            if ctx.transposed:   # dW[Cin][tap][Cout]: dense = x (input grid), gathered = dy (output grid)
-                dwp = ops.conv_wgrad(x, dy, ops.KIND_CONV_K4S2, 16)
-            else:                # dW[Cout][tap][Cin]: dense = dy (output grid), gathered = x (input grid)
-                dwp = ops.conv_wgrad(dy, x, ops.KIND_CONV_K4S2, 16)
-            dweight = _deliver_conv_wgrad(dwp, weight.shape, ctx.params[0])
+            def wgrad():
+                if ctx.transposed:   # dW[Cin][tap][Cout]: dense = x (input grid), gathered = dy (output grid)
+                    dwp = ops.conv_wgrad(x, dy, ops.KIND_CONV_K4S2, 16)
+                else:                # dW[Cout][tap][Cin]: dense = dy (output grid), gathered = x (input grid)
+                    dwp = ops.conv_wgrad(dy, x, ops.KIND_CONV_K4S2, 16)
+                return _deliver_conv_wgrad(dwp, weight.shape, ctx.params[0])
+            dweight = _wgrad_off_chain(ctx.params[0], wgrad, x, dy)
         if ctx.needs_input_grad[0]:
             NB, H, W, _ = x.shape
             bwd = _link_bwd(ctx.in_link, x.shape, x.device)   # the producing block's backward work, in this epilogue

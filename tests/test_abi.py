@@ -51,6 +51,24 @@ def test_sass_is_blackwell_native(built_lib):
     assert "HMMA." not in sass.replace("UTCHMMA", "")
 
 
+def test_every_kernel_waits_on_its_grid_dependencies(built_lib):
+    """Programmatic dependent launch (csrc/common.h): ordering between launches is only transitive if EVERY kernel of
+    the library executes griddepcontrol.wait (SASS: ACQBULK) before it exits, and the overlap only happens if every
+    kernel releases its dependents (griddepcontrol.launch_dependents, SASS: PREEXIT)."""
+    import shutil
+    import subprocess
+
+    if shutil.which("cuobjdump") is None:
+        import pytest
+
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run(["cuobjdump", "-sass", built_lib], stdout=subprocess.PIPE, text=True).stdout
+    funcs = sass.split("Function : ")[1:]
+    assert len(funcs) > 50
+    missing = [f.split("\n")[0][:80] for f in funcs if "ACQBULK" not in f or "PREEXIT" not in f]
+    assert not missing, missing
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     from gan_playground_b200 import _lib
     import pytest

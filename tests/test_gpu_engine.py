@@ -75,3 +75,32 @@ def test_eager_step_after_replays_restages_the_weights():
     # and replaying again after an eager step still works (the graph owns its own staging kernels)
     out2 = runner.step(x, z)
     assert all(math.isfinite(v) for v in out2)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_weight_gradients_on_the_side_stream_are_the_same_step(use_graph):
+    """config.wgrad_side: the step drivers fork the weight-gradient GEMMs off the backward chain and join before the
+    optimiser. Same inputs, same seeds: losses and updated weights must agree with the in-chain run to atomics noise."""
+    from gan_playground_b200 import config
+
+    gen = torch.Generator().manual_seed(7)
+    steps = 3
+    xs = (torch.rand(steps, 16, 3, 32, 32, generator=gen) * 2 - 1).cuda()
+    zs = torch.randn(steps, 2, 16, 100, generator=gen).cuda()
+    runs = []
+    try:
+        for mode in ("1", "0"):
+            config.set_wgrad_stream_mode(mode)
+            netG, netD, runner = _build(use_graph)
+            assert (runner._wg_stream is not None) == (mode == "1")
+            losses = [runner.step(xs[i], zs[i]) for i in range(steps)]
+            torch.cuda.synchronize()
+            runs.append((losses, [p.detach().clone() for p in list(netG.parameters()) + list(netD.parameters())]))
+    finally:
+        config.set_wgrad_stream_mode("auto")
+    (la, pa), (lb, pb) = runs
+    assert max(abs(x - y) for x, y in zip(la[0], lb[0])) < 1e-4, (la[0], lb[0])
+    for a, b in zip(la[1:], lb[1:]):
+        assert max(abs(x - y) for x, y in zip(a, b)) < 2e-2, (a, b)
+    for x, y in zip(pa, pb):
+        assert (x - y).abs().max().item() <= 4 * 4e-4 * steps + 1e-4

@@ -56,6 +56,7 @@ def test_a_step_with_batched_staging_is_the_step_without_it_in_fewer_launches():
         lb, gb, nb = run(False)
     finally:
         config.set_batch_stage(True)
-    assert la == lb
-    assert torch.equal(ga, gb)
+    assert abs(la - lb) <= 1e-5 * abs(lb)
+    # the weight-gradient and statistics kernels accumulate with fp32 atomics: two runs agree to rounding, not bit for bit
+    assert torch.allclose(ga, gb, rtol=0, atol=1e-4 * float(ga.abs().max()))
     assert na < nb, (na, nb)
