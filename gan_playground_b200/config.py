@@ -159,7 +159,7 @@ def set_batch_stage(on):
 _wgrad_stream_mode = os.environ.get("GP_WGRAD_STREAM", "auto")
 if _wgrad_stream_mode not in ("auto", "0", "1"):
     raise ValueError("GP_WGRAD_STREAM must be auto, 0 or 1")
-_wgrad_side = None      # (stream, list of tensors kept alive until the join) while a step driver runs its loop body
+_wgrad_side = None      # [stream, tensors kept alive until the join, forked?] while a step driver runs its loop body
 
 
 def set_wgrad_stream_mode(mode):
@@ -186,7 +186,8 @@ class wgrad_side_scope:
     def __enter__(self):
         global _wgrad_side
         self.prev = _wgrad_side
-        _wgrad_side = (self.stream, []) if self.stream is not None else None
+        # [stream, tensors kept alive, forked since the last join]
+        _wgrad_side = [self.stream, [], False] if self.stream is not None else None
 
     def __exit__(self, *exc):
         global _wgrad_side
@@ -196,9 +197,10 @@ class wgrad_side_scope:
 
 def join_wgrad_side():
     """The current stream waits for every weight gradient issued on the side stream; the tensors they read may be freed."""
-    if _wgrad_side is None:
-        return
+    if _wgrad_side is None or not _wgrad_side[2]:
+        return      # nothing was forked: waiting on the idle stream would tie a graph capture to uncaptured work
     import torch
-    stream, hold = _wgrad_side
+    stream, hold, _ = _wgrad_side
     torch.cuda.current_stream().wait_stream(stream)
     del hold[:]
+    _wgrad_side[2] = False

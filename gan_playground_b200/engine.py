@@ -102,6 +102,9 @@ class _AdversarialStep:
         data parallelism D's exchange + update run on a side stream while `g_work` runs on the main one; whatever reads D
         next waits for the join."""
         if parallel.enabled() and self.overlap:
+            # join on the MAIN stream first: the join releases the tensors the weight gradients read, and the main stream's
+            # allocator must not reuse them before those GEMMs are done
+            config.join_wgrad_side()
             cur = torch.cuda.current_stream()
             self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):

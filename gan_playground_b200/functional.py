@@ -245,8 +245,9 @@ def _wgrad_off_chain(param, fn, *reads):
     side = config.wgrad_side()
     if side is None or ops.grad_target(param) is None:
         return fn()
-    stream, hold = side
+    stream, hold = side[0], side[1]
     stream.wait_stream(torch.cuda.current_stream())
+    side[2] = True
     with torch.cuda.stream(stream):
         out = fn()
     hold.extend(reads)

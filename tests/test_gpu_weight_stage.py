@@ -57,6 +57,7 @@ def test_a_step_with_batched_staging_is_the_step_without_it_in_fewer_launches():
     finally:
         config.set_batch_stage(True)
     assert abs(la - lb) <= 1e-5 * abs(lb)
-    # the weight-gradient and statistics kernels accumulate with fp32 atomics: two runs agree to rounding, not bit for bit
-    assert torch.allclose(ga, gb, rtol=0, atol=1e-4 * float(ga.abs().max()))
+    # the weight-gradient and statistics kernels accumulate with fp32 atomics: two runs agree to rounding (and the
+    # occasional bf16 activation that rounds the other way because of it), not bit for bit
+    assert float((ga - gb).norm() / gb.norm()) < 2e-3
     assert na < nb, (na, nb)
