@@ -544,6 +544,8 @@ def main():
             "config": {"workload": cfg["workload"], "name": args.config, "global_batch": global_batch,
                        "per_gpu_batch": per_gpu, "parallelism": "dp%d" % world, "precision": label,
                        "cuda_graph": use_graph,
+                       "small_shard_overlap": {"wgrad_side_stream": getattr(runner, "_wg_stream", None) is not None,
+                                               "g_forward_next_to_real_pass": getattr(runner, "_g_stream", None) is not None},
                        "optimizer": "torch.optim.Adam" if args.torch_adam else "FusedAdam(flat%s)" % (", zero1" if world > 1 else ""),
                        "syncbn": "n/a (1 rank)" if world == 1 else ("one-shot NVLink peer exchange fused with the statistics finalize"
                                                                    if peer_sync else "NCCL all-reduce"),

@@ -204,3 +204,25 @@ def join_wgrad_side():
     torch.cuda.current_stream().wait_stream(stream)
     del hold[:]
     _wgrad_side[2] = False
+
+
+# Generator forward of the D-fake chain (main_dcgan.py:77, G(z1)) on its own stream NEXT TO the real-image D pass
+# (:70-74): neither reads what the other writes, and at shard sizes where one launch cannot fill the GPU the two chains
+# interleave. GP_G_AHEAD = 1 / 0 forces it, "auto" (default) enables it at <= 256 images per GPU. Under data parallelism
+# the SyncBN exchanges of that forward use the second peer lane (parallel.peer_lane).
+_g_ahead_mode = os.environ.get("GP_G_AHEAD", "auto")
+if _g_ahead_mode not in ("auto", "0", "1"):
+    raise ValueError("GP_G_AHEAD must be auto, 0 or 1")
+
+
+def set_g_ahead_mode(mode):
+    global _g_ahead_mode
+    if mode not in ("auto", "0", "1"):
+        raise ValueError("g-ahead mode must be auto, 0 or 1")
+    _g_ahead_mode = mode
+
+
+def g_ahead_wanted(per_gpu_batch):
+    if _g_ahead_mode == "auto":
+        return per_gpu_batch <= 256
+    return _g_ahead_mode == "1"

@@ -256,6 +256,9 @@ class DcganStep(_AdversarialStep):
             measured = all(type(n).__module__.endswith("models.dcgan") for n in (netG, netD))
             fake_precision = os.environ.get("GP_FAKE_PRECISION", "") or ("fp16" if measured else "bf16x3")
         self.fake_precision = fake_precision if (mixed_precision and config.x3() and fake_precision != "bf16x3") else None
+        # G(z1) of the D-fake chain runs on its own stream next to the real-image pass at small shard sizes (config.py)
+        self._g_stream = (torch.cuda.Stream(device=device)
+                          if device.type == "cuda" and config.g_ahead_wanted(batch) else None)
 
     def _draw_noise(self):
         return torch.randn(self.batch, self.z_dim, device=self.dev), torch.randn(self.batch, self.z_dim, device=self.dev)
@@ -264,13 +267,24 @@ class DcganStep(_AdversarialStep):
         netG, netD, crit = self.netG, self.netD, self.crit
         (inputs,), (z1, z2) = data, noise
         self._zero(self.optD, self.bucketD)                      # optD.zero_grad()
+        ahead = self._g_stream is not None
+        if ahead:
+            # main_dcgan.py:77 issued early on a side stream: G(z1) reads only G, the real-image pass only D
+            cur = torch.cuda.current_stream()
+            self._g_stream.wait_stream(cur)
+            with torch.cuda.stream(self._g_stream), parallel.peer_lane(1), \
+                    config.precision_scope(self.fake_precision or config.precision()):
+                outG = netG(z1)
         with config.precision_scope(self.real_precision or config.precision()):
             outD = netD(inputs)
         log(3, outD.mean())
         lossD_real = crit(outD, True)
         lossD_real.backward()
         with config.precision_scope(self.fake_precision or config.precision()):
-            outG = netG(z1)
+            if ahead:
+                cur.wait_stream(self._g_stream)
+            else:
+                outG = netG(z1)
             outD = netD(outG.detach())
         log(4, outD.mean())
         lossD_fake = crit(outD, False)

@@ -59,6 +59,9 @@ def sync_grads():
     return _state["sync_grads"]
 
 
+PEER_LANES = 2
+
+
 def init_peer_sync(device=None):
     """Set up the one-shot NVLink exchange used for the SyncBN reductions (csrc/peer_sync.cu): a symmetric buffer per
     rank, mapped into every peer through torch's symmetric-memory rendezvous (plumbing only: the exchange itself is our
@@ -74,22 +77,25 @@ def init_peer_sync(device=None):
     from . import ops
 
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
-    local_ok, why, pending = 1, "", None
+    local_ok, why, pending = 1, "", []
     try:
         import torch.distributed._symmetric_memory as symm_mem
 
-        n = ops.peer_buffer_bytes() // 4
-        buf = symm_mem.empty(n, dtype=torch.float32, device=dev)
-        buf.zero_()
-        torch.cuda.synchronize()
-        hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
-        ptrs = [int(p) for p in hdl.buffer_ptrs]
-        epoch = torch.zeros(1, dtype=torch.int32, device=dev)
-        torch.cuda.synchronize()
-        if len(ptrs) != _state["world"] or not all(ptrs):
-            local_ok, why = 0, "incomplete peer mapping"
-        else:
-            pending = {"ctx": ops.make_peer_ctx(ptrs, _state["rank"], epoch), "buf": buf, "hdl": hdl, "epoch": epoch}
+        # PEER_LANES independent contexts (buffer + epoch each): exchanges issued on two streams that run side by side (the
+        # step drivers' generator forward next to the real-image pass) must not share slots, flags or epochs
+        for _ in range(PEER_LANES):
+            n = ops.peer_buffer_bytes() // 4
+            buf = symm_mem.empty(n, dtype=torch.float32, device=dev)
+            buf.zero_()
+            torch.cuda.synchronize()
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+            ptrs = [int(p) for p in hdl.buffer_ptrs]
+            epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+            torch.cuda.synchronize()
+            if len(ptrs) != _state["world"] or not all(ptrs):
+                local_ok, why = 0, "incomplete peer mapping"
+                break
+            pending.append({"ctx": ops.make_peer_ctx(ptrs, _state["rank"], epoch), "buf": buf, "hdl": hdl, "epoch": epoch})
     except Exception as exc:  # noqa: BLE001 — any rendezvous problem means "use NCCL", never a crash
         local_ok, why = 0, str(exc)
     ok = torch.tensor([local_ok], device=dev)
@@ -104,9 +110,26 @@ def init_peer_sync(device=None):
 
 
 def peer_ctx():
-    """The peer-exchange context (ops.PeerCtx) or None when SyncBN sums go through NCCL."""
+    """The peer-exchange context (ops.PeerCtx) of the current lane, or None when SyncBN sums go through NCCL."""
     p = _state.get("peer")
-    return None if p is None else p["ctx"]
+    return None if p is None else p[_state.get("peer_lane", 0)]["ctx"]
+
+
+class peer_lane:
+    """`with peer_lane(1): ...` — SyncBN exchanges issued inside use the second peer context. Every rank must issue the
+    same exchanges in the same order PER LANE; lanes are independent of each other (different streams may interleave)."""
+
+    def __init__(self, lane):
+        if not 0 <= lane < PEER_LANES:
+            raise ValueError("peer lane out of range")
+        self.lane = lane
+
+    def __enter__(self):
+        self.prev = _state.get("peer_lane", 0)
+        _state["peer_lane"] = self.lane
+
+    def __exit__(self, *exc):
+        _state["peer_lane"] = self.prev
 
 
 def all_reduce_sum_(t):

@@ -104,3 +104,34 @@ def test_weight_gradients_on_the_side_stream_are_the_same_step(use_graph):
         assert max(abs(x - y) for x, y in zip(a, b)) < 2e-2, (a, b)
     for x, y in zip(pa, pb):
         assert (x - y).abs().max().item() <= 4 * 4e-4 * steps + 1e-4
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_generator_forward_next_to_the_real_pass_is_the_same_step(use_graph):
+    """config.g_ahead: G(z1) of the D-fake chain is issued on its own stream before the real-image pass. Same inputs,
+    same seeds: the step must agree with the in-order run to atomics noise."""
+    from gan_playground_b200 import config
+
+    gen = torch.Generator().manual_seed(8)
+    steps = 3
+    xs = (torch.rand(steps, 16, 3, 32, 32, generator=gen) * 2 - 1).cuda()
+    zs = torch.randn(steps, 2, 16, 100, generator=gen).cuda()
+    runs = []
+    try:
+        for mode in ("1", "0"):
+            config.set_g_ahead_mode(mode)
+            netG, netD, runner = _build(use_graph)
+            assert (runner._g_stream is not None) == (mode == "1")
+            losses = [runner.step(xs[i], zs[i]) for i in range(steps)]
+            torch.cuda.synchronize()
+            runs.append((losses, [p.detach().clone() for p in list(netG.parameters()) + list(netD.parameters())],
+                         netG.blocks[0][1].running_mean.clone()))
+    finally:
+        config.set_g_ahead_mode("auto")
+    (la, pa, ra), (lb, pb, rb) = runs
+    assert max(abs(x - y) for x, y in zip(la[0], lb[0])) < 1e-4, (la[0], lb[0])
+    for a, b in zip(la[1:], lb[1:]):
+        assert max(abs(x - y) for x, y in zip(a, b)) < 2e-2, (a, b)
+    for x, y in zip(pa, pb):
+        assert (x - y).abs().max().item() <= 4 * 4e-4 * steps + 1e-4
+    assert torch.allclose(ra, rb, atol=2e-3)
