@@ -42,6 +42,13 @@ def test_a_step_with_batched_staging_is_the_step_without_it_in_fewer_launches():
             netG, netD = dcgan.Generator(ngf=32, resolution=32).cuda(), dcgan.Discriminator(ndf=32, resolution=32).cuda()
         crit = GANLoss("vanilla", 0.9, 0.1, 0.9).cuda()
         z = torch.randn(8, 100, generator=torch.Generator().manual_seed(1)).cuda()
+        # first pass: the cache learns which copies the step needs (one request at a time); then an in-place parameter
+        # update, as an optimiser step would do, makes every copy stale; the second pass is the one compared and counted
+        crit(netD(netG(z)), False, True).backward()
+        with torch.no_grad():
+            for p in list(netG.parameters()) + list(netD.parameters()):
+                p.grad = None
+                p.mul_(1.0)
         l0 = _lib.launch_count()
         loss = crit(netD(netG(z)), False, True)
         loss.backward()
