@@ -56,15 +56,20 @@ def test_a_step_with_batched_staging_is_the_step_without_it_in_fewer_launches():
         # a conv bias in front of BatchNorm gets no gradient tensor at all (analytically zero, functional.ConvBlock.backward)
         grads = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).flatten()
                            for p in list(netG.parameters()) + list(netD.parameters())])
-        return loss.item(), grads, _lib.launch_count() - l0
+        return loss.item(), grads, netD.out_layer.weight.grad.clone(), _lib.launch_count() - l0
 
     try:
-        la, ga, na = run(True)
-        lb, gb, nb = run(False)
+        la, ga, ha, na = run(True)
+        lb, gb, hb, nb = run(False)
     finally:
         config.set_batch_stage(True)
     assert abs(la - lb) <= 1e-5 * abs(lb)
-    # the weight-gradient and statistics kernels accumulate with fp32 atomics: two runs agree to rounding (and the
-    # occasional bf16 activation that rounds the other way because of it), not bit for bit
-    assert float((ga - gb).norm() / gb.norm()) < 2e-3
+    # The staged operands themselves are bit-identical (test above). Two runs of the SAME code are not: the statistics and
+    # weight-gradient kernels accumulate with fp32 atomics (1e-6 on the loss), and every bf16 rounding of the single-bf16
+    # backward turns a relative perturbation d into ~sqrt(d * 2^-8), so the difference climbs 1e-5 -> 2e-4 -> 1e-3 -> 5e-3 from
+    # D's last block back to G and saturates at the bf16 rounding level (tools/probe/stage_noise.py, profiles/r02_stage_noise.log:
+    # 4e-3 .. 8e-3 between two identical runs, batched or not). The bound is that floor (cosine 0.9998, five times inside the
+    # parity bar), and the last layer of D - in front of any rounding - must agree to accumulation order.
+    assert float((ga - gb).norm() / gb.norm()) < 2e-2
+    assert float((ha - hb).norm() / hb.norm()) < 1e-3
     assert na < nb, (na, nb)
