@@ -147,6 +147,25 @@ def dcgan_discriminator(sd, x, *, sn=False, acgan=False, flatten_head=False, tra
     return out
 
 
+def dcgan_up_generator(sd, z, *, bottom_width=4, training=True, buffers=None):
+    """Generator.forward of models/dcgan_specnorm_up.py:49-58: relu(linear(z)) -> view -> [Upsample x2 (nearest) ->
+    spectral-normed Conv3x3 s1 p1 (dim 0) -> BN -> ReLU]* (blocks at :36-42) -> Upsample x2 -> spectral-normed Conv3x3 ->
+    Tanh (:43-47). The discriminator of that file (:111-135) is dcgan_specnorm's: `dcgan_discriminator(sn=True,
+    flatten_head=True)`."""
+    h = F.relu(F.linear(z, sd["linear.weight"], sd["linear.bias"]))
+    h = h.view(h.size(0), -1, bottom_width, bottom_width)
+    i = 0
+    while ("blocks.%d.1.bias" % i) in sd:
+        p = "blocks.%d." % i
+        h = F.interpolate(h, scale_factor=2)
+        h = F.conv2d(h, spectral_norm_weight(sd, p + "1.", 0, training), sd[p + "1.bias"], stride=1, padding=1)
+        h = F.relu(batch_norm_train(h, sd[p + "2.weight"], sd[p + "2.bias"], buffers, p + "2."))
+        i += 1
+    h = F.interpolate(h, scale_factor=2)
+    h = F.conv2d(h, spectral_norm_weight(sd, "out_layer.1.", 0, training), sd["out_layer.1.bias"], stride=1, padding=1)
+    return torch.tanh(h)
+
+
 # --------------------------------------------------------------------------------------------------------------
 # dcgan_blur (models/dcgan_blur.py + models/ops.py::BlurPool2d) — what main_dcgan.py:52-53 instantiates
 # --------------------------------------------------------------------------------------------------------------
@@ -304,6 +323,10 @@ def dcgan_step_grads(sd_g, sd_d, x_real, z1, z2, labels=(0.9, 0.1, 0.9), mode="v
     rl, fl, gl = labels
     g_kw = {k: v for k, v in net_kw.items() if k in ("sn", "bottom_width")}
     d_kw = {k: v for k, v in net_kw.items() if k in ("sn", "flatten_head")}
+    if net_kw.get("up"):     # models/dcgan_specnorm_up.py: upsample + SN conv3x3 generator, dcgan_specnorm's discriminator
+        g_kw = {k: v for k, v in net_kw.items() if k == "bottom_width"}
+        return _step_grads(dcgan_up_generator, dcgan_discriminator, g_kw, dict(sn=True, flatten_head=True), sd_g, sd_d,
+                           x_real, z1, z2, labels, mode)
     if net_kw.get("blur"):   # models/dcgan_blur.py instead of models/dcgan.py
         g_kw = {k: v for k, v in net_kw.items() if k == "bottom_width"}
         d_kw = {}

@@ -24,7 +24,7 @@ def ref_modules():
     import importlib.util
 
     mods = {}
-    for name in ("dcgan", "dcgan_specnorm", "sngan_projection", "acgan"):
+    for name in ("dcgan", "dcgan_specnorm", "dcgan_specnorm_up", "sngan_projection", "acgan"):
         spec = importlib.util.spec_from_file_location("ref_models_" + name, os.path.join(REF, "models", name + ".py"))
         m = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(m)
@@ -134,6 +134,8 @@ def dcgan_like_fixture(mods, modname, res, width, batch, mode, labels, seed, z_d
     kw = dict(sn=(modname == "dcgan_specnorm"), flatten_head=(modname == "dcgan_specnorm"))
     if modname == "dcgan_blur":
         kw = dict(blur=True)
+    if modname == "dcgan_specnorm_up":
+        kw = dict(up=True)
     og = {k: v.clone() for k, v in sd_g0.items()}
     od = {k: v.clone() for k, v in sd_d0.items()}
     r = O.dcgan_step_grads(og, od, x, z1, z2, labels=labels, mode=mode, **kw)
@@ -501,6 +503,11 @@ def key_lists(mods):
         out["acgan.Discriminator@32c5"] = desc(mods["acgan"].Discriminator(ndf=8, resolution=32, n_class=5))
         out["sngan_projection.ResNetGenerator@uncond"] = desc(mods["sngan_projection"].ResNetGenerator(ch=8, n_classes=0))
         out["sngan_projection.SNResNetProjectionDiscriminator@uncond"] = desc(mods["sngan_projection"].SNResNetProjectionDiscriminator(ch=8, n_classes=0))
+        U = mods["dcgan_specnorm_up"]
+        out["dcgan_specnorm_up.Generator"] = desc(U.Generator(ngf=8))
+        out["dcgan_specnorm_up.Discriminator"] = desc(U.Discriminator(ndf=8))
+        out["dcgan_specnorm_up.Generator@32"] = desc(U.Generator(ngf=8, resolution=32))
+        out["dcgan_specnorm_up.Discriminator@128"] = desc(U.Discriminator(ndf=4, resolution=128))
         out["dcgan_blur.Generator"] = desc(mods["dcgan_blur"].Generator())
         out["dcgan_blur.Discriminator"] = desc(mods["dcgan_blur"].Discriminator())
         out["dcgan_blur.Generator@32"] = desc(mods["dcgan_blur"].Generator(resolution=32))
@@ -519,6 +526,8 @@ def key_lists(mods):
                                                        S.SNResNetProjectionDiscriminator(ch=8, n_classes=0))),
             "acgan": probes(lambda: (A.Generator(z_dim=16, ngf=8, n_class=10), A.Discriminator(ndf=8, n_class=10))),
             "dcgan_specnorm": probes(lambda: (N.Generator(z_dim=16, ngf=8, resolution=32), N.Discriminator(ndf=8, resolution=32))),
+            "dcgan_specnorm_up": probes(lambda: (mods["dcgan_specnorm_up"].Generator(z_dim=16, ngf=8, resolution=32),
+                                                 mods["dcgan_specnorm_up"].Discriminator(ndf=8, resolution=32))),
         }
         # RNG-order parity: first weights of a seed-0 construction
         torch.manual_seed(0)
@@ -546,6 +555,7 @@ def main():
         "dcgan_r32_w4.pt": lambda: dcgan_like_fixture(mods, "dcgan", 32, 4, 8, "vanilla", (0.9, 0.1, 0.9), 0, z_dim=100),
         "dcgan_r64_w4.pt": lambda: dcgan_like_fixture(mods, "dcgan", 64, 4, 2, "vanilla", (0.9, 0.1, 0.9), 1, z_dim=16),
         "snd_r32_w4.pt": lambda: dcgan_like_fixture(mods, "dcgan_specnorm", 32, 4, 8, "hinge", (1.0, 0.0, 1.0), 2, z_dim=16),
+        "snd_up_r32_w4.pt": lambda: dcgan_like_fixture(mods, "dcgan_specnorm_up", 32, 4, 8, "hinge", (1.0, 0.0, 1.0), 7, z_dim=16),
         "dcgan_blur_r32_w8.pt": lambda: dcgan_like_fixture(mods, "dcgan_blur", 32, 8, 4, "vanilla", (0.9, 0.1, 0.9), 6, z_dim=16),
         "dcgan_trace_r32_w4.pt": lambda: dcgan_trace_fixture(mods, 32, 4, 8, 20, 3),
         "sngan_proj_ch8.pt": lambda: sngan_fixture(mods, 8, 2, 4),

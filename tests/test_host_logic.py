@@ -28,9 +28,13 @@ def test_state_dict_layout_matches_reference(name, ctor, capsys):
 
 
 def _family_ctors():
-    from gan_playground_b200.models import acgan, dcgan_specnorm, sngan_projection as S
+    from gan_playground_b200.models import acgan, dcgan_specnorm, dcgan_specnorm_up, sngan_projection as S
 
     return {
+        "dcgan_specnorm_up.Generator": lambda: dcgan_specnorm_up.Generator(ngf=8),
+        "dcgan_specnorm_up.Discriminator": lambda: dcgan_specnorm_up.Discriminator(ndf=8),
+        "dcgan_specnorm_up.Generator@32": lambda: dcgan_specnorm_up.Generator(ngf=8, resolution=32),
+        "dcgan_specnorm_up.Discriminator@128": lambda: dcgan_specnorm_up.Discriminator(ndf=4, resolution=128),
         "dcgan.Generator@128": lambda: dcgan.Generator(ngf=8, resolution=128),
         "dcgan.Discriminator@128": lambda: dcgan.Discriminator(ndf=8, resolution=128),
         "dcgan_specnorm.Generator": lambda: dcgan_specnorm.Generator(ngf=8),
@@ -193,14 +197,17 @@ def test_forward_tile_cost_model_fills_the_machine(built_lib):
         assert bn // 2 < shape[6] or bn == 64                                            # never mostly padding
 
 
-@pytest.mark.parametrize("family", ["sngan_projection", "sngan_projection@uncond", "acgan", "dcgan_specnorm"])
+@pytest.mark.parametrize("family", ["sngan_projection", "sngan_projection@uncond", "acgan", "dcgan_specnorm",
+                                    "dcgan_specnorm_up"])
 def test_same_seed_construction_of_every_family_matches_reference(family, capsys):
     """The mirrors create their torch parameter holders, apply the initialisers and wrap spectral norm in the reference's
     order, so a construction under the same seed consumes the same RNG stream: every parameter AND buffer (spectral-norm
     u / v included) is identical to the unmodified reference's — (sum, first element) probes of each state_dict entry."""
-    from gan_playground_b200.models import acgan, dcgan_specnorm, sngan_projection as S
+    from gan_playground_b200.models import acgan, dcgan_specnorm, dcgan_specnorm_up, sngan_projection as S
 
     build = {
+        "dcgan_specnorm_up": lambda: (dcgan_specnorm_up.Generator(z_dim=16, ngf=8, resolution=32),
+                                      dcgan_specnorm_up.Discriminator(ndf=8, resolution=32)),
         "sngan_projection": lambda: (S.ResNetGenerator(ch=8, dim_z=16, bottom_width=2, n_classes=10),
                                      S.SNResNetProjectionDiscriminator(ch=8, n_classes=10)),
         "sngan_projection@uncond": lambda: (S.ResNetGenerator(ch=8, dim_z=16, n_classes=0),

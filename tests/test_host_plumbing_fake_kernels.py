@@ -56,7 +56,7 @@ def fake_kernels(monkeypatch):
     monkeypatch.setattr(ops, "_chk", chk)
     monkeypatch.setattr(ops, "_stream", lambda: 0)
     monkeypatch.setattr(_common, "require_cuda", lambda t, what: None)
-    for mod in ("dcgan", "dcgan_specnorm", "dcgan_blur", "acgan", "sngan_projection"):
+    for mod in ("dcgan", "dcgan_specnorm", "dcgan_specnorm_up", "dcgan_blur", "acgan", "sngan_projection"):
         m = __import__("gan_playground_b200.models." + mod, fromlist=["x"])
         if hasattr(m, "require_cuda"):
             monkeypatch.setattr(m, "require_cuda", lambda t, what: None)
@@ -92,11 +92,12 @@ def _step(netG, netD, crit, d_args, g_args, second_g=True):
 
 
 @pytest.mark.parametrize("mode", ["bf16", "fp16", "bf16x3"])
-@pytest.mark.parametrize("family", ["dcgan", "dcgan_specnorm", "dcgan_blur", "sngan_projection", "sngan_unconditional"])
+@pytest.mark.parametrize("family", ["dcgan", "dcgan_specnorm", "dcgan_specnorm_up", "dcgan_blur", "sngan_projection",
+                                    "sngan_unconditional"])
 def test_forward_backward_plumbing(fake_kernels, mode, family):
     from gan_playground_b200 import config
     from gan_playground_b200.criterion import GANLoss
-    from gan_playground_b200.models import dcgan, dcgan_blur, dcgan_specnorm, sngan_projection
+    from gan_playground_b200.models import dcgan, dcgan_blur, dcgan_specnorm, dcgan_specnorm_up, sngan_projection
 
     torch.manual_seed(0)
     B = 4
@@ -116,7 +117,8 @@ def test_forward_backward_plumbing(fake_kernels, mode, family):
             missing, wrong = _step(netG, netD, GANLoss("hinge"), (torch.randn(B, 3, 32, 32),), (torch.randn(B, 16), None),
                                    second_g=False)
         else:
-            M = {"dcgan": dcgan, "dcgan_specnorm": dcgan_specnorm, "dcgan_blur": dcgan_blur}[family]
+            M = {"dcgan": dcgan, "dcgan_specnorm": dcgan_specnorm, "dcgan_specnorm_up": dcgan_specnorm_up,
+                 "dcgan_blur": dcgan_blur}[family]
             netG = quiet(lambda: M.Generator(z_dim=16, ngf=8, resolution=32))
             netD = quiet(lambda: M.Discriminator(ndf=8, resolution=32))
             missing, wrong = _step(netG, netD, GANLoss("vanilla", 0.9, 0.1, 0.9), (torch.randn(B, 3, 32, 32),),

@@ -26,7 +26,7 @@ def check_grads(got, ref, tol=2e-3, floor=1e-5):
 
 @pytest.mark.parametrize("name,kw", [
     ("dcgan_r32_w4.pt", {}), ("dcgan_r64_w4.pt", {}), ("snd_r32_w4.pt", {"sn": True, "flatten_head": True}),
-    ("dcgan_blur_r32_w8.pt", {"blur": True}),
+    ("dcgan_blur_r32_w8.pt", {"blur": True}), ("snd_up_r32_w4.pt", {"up": True}),
 ])
 def test_dcgan_family_step_matches_golden(name, kw):
     fx = load_golden(name)
