@@ -191,4 +191,6 @@ def test_backward_link_fusion_gives_the_same_gradients():
     cos = (a @ b / (a.norm() * b.norm())).item()
     rel = ((a - b).norm() / a.norm()).item()
     print("BwdLink fusion on vs off: gradient cosine %.7f, relative difference %.2e" % (cos, rel))
-    assert cos > 0.99999 and rel < 5e-3
+    # two runs of the single-bf16 backward differ by up to ~8e-3 on generator gradients even with identical code (fp32 atomics
+    # + bf16 rounding, profiles/r02_stage_noise.log; measured here: 2.6e-3); a wrong fusion shows up as an O(1) difference
+    assert cos > 0.9999 and rel < 1e-2
